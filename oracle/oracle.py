@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper around the CPU oracle (oracle/*.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product (mopa_rl_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(force=False):
+    """Compile both oracle flavours with the committed Makefile."""
+    targets = [os.path.join(_HERE, "libmopa_oracle_f32.so"), os.path.join(_HERE, "libmopa_oracle_f64.so")]
+    if force or not all(os.path.exists(t) for t in targets):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return targets
+
+
+def lib(precision="f32"):
+    if precision not in _LIBS:
+        path = os.path.join(_HERE, "libmopa_oracle_%s.so" % precision)
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_npair.argtypes = [C.c_void_p]
+        L.orc_scene_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_is_valid.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_pair_dists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_fk.argtypes = [C.c_void_p] * 8
+        L.orc_primitive_dist.restype = C.c_double
+        L.orc_primitive_dist.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIBS[precision] = L
+    return _LIBS[precision]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleScene:
+    """State-validity oracle for one compiled scene (see orc_collide.c)."""
+
+    def __init__(self, model, ignored_pairs=(), contact_threshold=0.0, precision="f32"):
+        from mopa_rl_b200.model import make_desc  # data-format helper only (struct layout)
+
+        self.model = model
+        self.L = lib(precision)
+        self.precision = precision
+        desc, self._keep = make_desc(model)
+        ign = np.ascontiguousarray(np.array(list(ignored_pairs), dtype=np.int32).reshape(-1, 2))
+        self._ign = ign
+        self.h = self.L.orc_scene_create(C.byref(desc), _p(ign) if len(ign) else None, len(ign), float(contact_threshold))
+        self.npair = self.L.orc_scene_npair(self.h)
+
+    def __del__(self):
+        try:
+            self.L.orc_scene_destroy(self.h)
+        except Exception:
+            pass
+
+    def pairs(self):
+        g1 = np.zeros(self.npair, np.int32)
+        g2 = np.zeros(self.npair, np.int32)
+        self.L.orc_scene_pairs(self.h, _p(g1), _p(g2))
+        return g1, g2
+
+    def is_valid(self, qpos, with_dist=False):
+        q = np.ascontiguousarray(np.atleast_2d(qpos), dtype=np.float64)
+        assert q.shape[1] == self.model.nq
+        res = np.zeros(len(q), np.uint32)
+        md = np.zeros(len(q), np.float64) if with_dist else None
+        self.L.orc_is_valid(self.h, _p(q), len(q), _p(res), _p(md) if with_dist else None)
+        return (res, md) if with_dist else res
+
+    def pair_dists(self, qpos):
+        q = np.ascontiguousarray(qpos, dtype=np.float64)
+        d = np.zeros(self.npair, np.float64)
+        self.L.orc_pair_dists(self.h, _p(q), _p(d))
+        return d
+
+    def fk(self, qpos):
+        m = self.model
+        q = np.ascontiguousarray(qpos, dtype=np.float64)
+        out = dict(body_xpos=np.zeros((m.nbody, 3)), body_xmat=np.zeros((m.nbody, 9)), geom_xpos=np.zeros((m.ngeom, 3)),
+                   geom_xmat=np.zeros((m.ngeom, 9)), site_xpos=np.zeros((m.nsite, 3)), site_xmat=np.zeros((m.nsite, 9)))
+        self.L.orc_fk(self.h, _p(q), *[_p(out[k]) for k in ("body_xpos", "body_xmat", "geom_xpos", "geom_xmat", "site_xpos", "site_xmat")])
+        return out
+
+
+def primitive_dist(t1, p1, m1, s1, t2, p2, m2, s2, precision="f64"):
+    a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (p1, m1, s1, p2, m2, s2)]
+    return lib(precision).orc_primitive_dist(int(t1), _p(a[0]), _p(a[1]), _p(a[2]), int(t2), _p(a[3]), _p(a[4]), _p(a[5]))
