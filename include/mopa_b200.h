@@ -1,0 +1,79 @@
+/* C ABI of libmopa_b200.so — the B200-native drop-in for the native half of MoPA-RL's
+ * experience-collection path.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * clvrai/mopa-rl checkout).  Conventions: every function returns 0 on success and a negative
+ * code on failure (message via mopa_last_error()); no exception crosses the ABI; the caller
+ * owns every buffer; handles are owned by the library; one host thread per handle; device
+ * entry points enqueue on the caller-supplied cudaStream_t (passed as void*) and do not
+ * synchronise; *_host entry points take host memory, perform the copies themselves and
+ * return when the result is in the caller's buffer.
+ */
+#ifndef MOPA_B200_H
+#define MOPA_B200_H
+#include <stdint.h>
+
+#include "mopa_model_desc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mopa_planner mopa_planner;
+
+#define MOPA_OK 0
+#define MOPA_ERR_ARG (-1)
+#define MOPA_ERR_CUDA (-2)
+#define MOPA_ERR_MODEL (-3)
+
+/* mopa_is_valid_* flags */
+#define MOPA_VALID_FAST 0        /* result word: bit0 = valid; other bits 0 */
+#define MOPA_VALID_FIRST_PAIR 1  /* no early-out; bits 8.. = 1 + canonical index of the first offending pair */
+
+/* planner status codes written by mopa_plan_* (the reference signals them with sentinel rows:
+ * KinematicPlanner.cpp:181-184 (-5, invalid goal) and :249-250 (-4, no exact solution)) */
+#define MOPA_PLAN_OK 0
+#define MOPA_PLAN_NOT_EXACT (-4)
+#define MOPA_PLAN_INVALID_GOAL (-5)
+
+/* Last error message of the calling thread ("" if none). */
+const char *mopa_last_error(void);
+
+/* Library / device probe: returns the number of visible CUDA devices (<0 on error). */
+int mopa_device_count(void);
+
+/* Replaces KinematicPlanner::KinematicPlanner (motion_planners/KinematicPlanner.cpp:42-120,
+ * bound by PyKinematicPlanner.__cinit__, motion_planners/planner.pyx:33-41).
+ *   model              compiled scene (instead of the XML file name; MuJoCo is not available)
+ *   passive_qpos_idx   qpos indices frozen during a plan ("passive_joint_idx")
+ *   ignored_pairs      ordered geom-id pairs whose contacts never invalidate ("ignored_contacts")
+ *   contact_threshold  a contact invalidates the state iff dist <= contact_threshold
+ *   range              RRT-Connect extension range (setRange, KinematicPlanner.cpp:101)
+ *   resolution         state validity checking resolution (0.005 in KinematicPlanner.cpp:87)
+ *   seed               ompl::RNG::setSeed(seed) (KinematicPlanner.cpp:93); keys the counter-based RNG
+ */
+int mopa_planner_create(const mopa_model_desc *model, const int32_t *passive_qpos_idx, int32_t n_passive,
+                        const int32_t *ignored_pairs, int32_t n_ignored, double contact_threshold, double range,
+                        double resolution, uint64_t seed, int32_t device, mopa_planner **out);
+void mopa_planner_destroy(mopa_planner *p);
+
+/* Scene facts: qpos length, candidate-pair count, number of active (planned) joints. */
+int mopa_planner_info(const mopa_planner *p, int32_t *nq, int32_t *n_pairs, int32_t *n_active);
+/* Canonical candidate pair list (mjModel geom ids), n_pairs entries each. */
+int mopa_planner_pairs(const mopa_planner *p, int32_t *geom1, int32_t *geom2);
+
+/* Replaces MujocoStateValidityChecker::isValid (mujoco_ompl_interface.cpp:909-978), batched.
+ *   d_qpos      device, n rows of fp32 qpos, row_stride floats apart (row_stride >= nq)
+ *   d_result    device, n result words (see MOPA_VALID_*)
+ */
+int mopa_is_valid_batch(mopa_planner *p, const float *d_qpos, int32_t row_stride, int32_t n, uint32_t *d_result,
+                        int32_t flags, void *stream);
+
+/* Replaces KinematicPlanner::isValidState (KinematicPlanner.cpp:253-286, planner.pyx:51-52) for
+ * n host states of nq doubles each.  valid[i] in {0,1}; words (nullable) receives the result words. */
+int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *valid, uint32_t *words, int32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,108 @@
+"""ctypes binding of libmopa_b200.so (include/mopa_b200.h).
+
+This is the stand-in for the reference's Cython binding (motion_planners/planner.pyx:31-52):
+plain pointers and sizes, no torch types.  There is no CPU fallback: if the library is
+missing it is built with nvcc, and if no CUDA device is visible planner creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .model import make_desc
+
+_LIB = None
+
+
+class MopaError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
+        L = C.CDLL(path)
+        L.mopa_last_error.restype = C.c_char_p
+        L.mopa_device_count.restype = C.c_int
+        L.mopa_planner_create.restype = C.c_int
+        L.mopa_planner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_double,
+                                          C.c_double, C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]
+        L.mopa_planner_destroy.argtypes = [C.c_void_p]
+        L.mopa_planner_destroy.restype = None
+        L.mopa_planner_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.mopa_planner_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mopa_is_valid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.mopa_is_valid_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise MopaError("libmopa_b200 error %d: %s" % (rc, lib().mopa_last_error().decode("utf-8", "replace")))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+VALID_FAST, VALID_FIRST_PAIR = 0, 1
+
+
+class NativePlanner:
+    """Owner of one ``mopa_planner*`` (the counterpart of the heap ``KinematicPlanner*`` held by
+    ``PyKinematicPlanner``, planner.pyx:32-43)."""
+
+    def __init__(self, model, passive_joint_idx, ignored_contacts, contact_threshold, range_, resolution=0.005, seed=0, device=0):
+        L = lib()
+        self._L = L
+        self.model = model
+        desc, self._keep = make_desc(model)
+        passive = np.ascontiguousarray(np.array(list(passive_joint_idx), dtype=np.int32).reshape(-1))
+        ign = np.ascontiguousarray(np.array([tuple(x) for x in ignored_contacts], dtype=np.int32).reshape(-1, 2))
+        h = C.c_void_p()
+        check(L.mopa_planner_create(C.byref(desc), _p(passive) if len(passive) else None, len(passive),
+                                    _p(ign) if len(ign) else None, len(ign), float(contact_threshold), float(range_),
+                                    float(resolution), int(seed) & 0xFFFFFFFFFFFFFFFF, int(device), C.byref(h)))
+        self.h = h
+        nq, npair, nact = C.c_int32(), C.c_int32(), C.c_int32()
+        check(L.mopa_planner_info(self.h, C.byref(nq), C.byref(npair), C.byref(nact)))
+        self.nq, self.n_pairs, self.n_active = nq.value, npair.value, nact.value
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mopa_planner_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pairs(self):
+        g1 = np.zeros(self.n_pairs, np.int32)
+        g2 = np.zeros(self.n_pairs, np.int32)
+        check(self._L.mopa_planner_pairs(self.h, _p(g1), _p(g2)))
+        return g1, g2
+
+    def is_valid_host(self, qpos, flags=VALID_FAST, return_words=False):
+        q = np.ascontiguousarray(np.atleast_2d(qpos), dtype=np.float64)
+        if q.shape[1] != self.nq:
+            raise ValueError("state vector has dimension %d but should be nq: %d" % (q.shape[1], self.nq))
+        valid = np.zeros(len(q), np.uint8)
+        words = np.zeros(len(q), np.uint32)
+        check(self._L.mopa_is_valid_host(self.h, _p(q), len(q), _p(valid), _p(words), int(flags)))
+        return (valid, words) if return_words else valid
+
+    def is_valid_device(self, qpos_ptr, row_stride, n, result_ptr, flags=VALID_FAST, stream=0):
+        """Raw device-pointer entry (ints from torch ``data_ptr()``); enqueues, does not sync."""
+        check(self._L.mopa_is_valid_batch(self.h, C.c_void_p(qpos_ptr), int(row_stride), int(n), C.c_void_p(result_ptr),
+                                          int(flags), C.c_void_p(stream)))

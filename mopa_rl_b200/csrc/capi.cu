@@ -1,0 +1,156 @@
+// extern "C" surface of libmopa_b200.so (declared in include/mopa_b200.h).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mopa_b200.h"
+#include "planner_state.h"
+
+namespace mopa {
+void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored, double threshold, HostScene &out);
+cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream);
+}  // namespace mopa
+
+static thread_local std::string g_err;
+void mopa_set_error(const std::string &s) { g_err = s; }
+#define CUDA_TRY(x)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) {                                                                 \
+            g_err = std::string(#x) + ": " + cudaGetErrorString(e_);                             \
+            return MOPA_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+extern "C" {
+
+const char *mopa_last_error(void) { return g_err.c_str(); }
+
+int mopa_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return MOPA_ERR_CUDA;
+    }
+    return n;
+}
+
+int mopa_planner_create(const mopa_model_desc *model, const int32_t *passive_qpos_idx, int32_t n_passive,
+                        const int32_t *ignored_pairs, int32_t n_ignored, double contact_threshold, double range,
+                        double resolution, uint64_t seed, int32_t device, mopa_planner **out) {
+    if (!model || !out || n_passive < 0 || n_ignored < 0) { g_err = "mopa_planner_create: bad argument"; return MOPA_ERR_ARG; }
+    *out = nullptr;
+    mopa_planner *p = new mopa_planner();
+    try {
+        mopa::build_scene(model, ignored_pairs, n_ignored, contact_threshold, p->scene);
+        mopa::build_space(model, passive_qpos_idx, n_passive, range, resolution, seed, p->space);
+    } catch (const std::exception &e) {
+        g_err = std::string("mopa_planner_create: ") + e.what();
+        delete p;
+        return MOPA_ERR_MODEL;
+    }
+    p->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_blob, p->scene.blob.size());
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_blob, p->scene.blob.data(), p->scene.blob.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_err = std::string("mopa_planner_create: ") + cudaGetErrorString(e) +
+                " (libmopa_b200 needs a CUDA device; there is no CPU fallback)";
+        mopa_planner_destroy(p);
+        return MOPA_ERR_CUDA;
+    }
+    *out = p;
+    return MOPA_OK;
+}
+
+void mopa_planner_destroy(mopa_planner *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->d_blob) cudaFree(p->d_blob);
+    if (p->d_stage_q) cudaFree(p->d_stage_q);
+    if (p->d_stage_r) cudaFree(p->d_stage_r);
+    if (p->h_stage_q) cudaFreeHost(p->h_stage_q);
+    if (p->h_stage_r) cudaFreeHost(p->h_stage_r);
+    mopa::free_plan_buffers(p);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int mopa_planner_info(const mopa_planner *p, int32_t *nq, int32_t *n_pairs, int32_t *n_active) {
+    if (!p) { g_err = "null planner"; return MOPA_ERR_ARG; }
+    if (nq) *nq = p->scene.hdr.nq;
+    if (n_pairs) *n_pairs = (int32_t)p->scene.canon_g1.size();
+    if (n_active) *n_active = p->space.n_active;
+    return MOPA_OK;
+}
+
+int mopa_planner_pairs(const mopa_planner *p, int32_t *geom1, int32_t *geom2) {
+    if (!p || !geom1 || !geom2) { g_err = "bad argument"; return MOPA_ERR_ARG; }
+    for (size_t i = 0; i < p->scene.canon_g1.size(); i++) { geom1[i] = p->scene.canon_g1[i]; geom2[i] = p->scene.canon_g2[i]; }
+    return MOPA_OK;
+}
+
+int mopa_is_valid_batch(mopa_planner *p, const float *d_qpos, int32_t row_stride, int32_t n, uint32_t *d_result,
+                        int32_t flags, void *stream) {
+    if (!p || n < 0 || (n > 0 && (!d_qpos || !d_result)) || row_stride < p->scene.hdr.nq) {
+        g_err = "mopa_is_valid_batch: bad argument";
+        return MOPA_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(mopa::launch_is_valid(p->d_blob, p->scene.hdr, d_qpos, row_stride, n, d_result, flags & MOPA_VALID_FIRST_PAIR,
+                                   p->sm_count, (cudaStream_t)stream));
+    return MOPA_OK;
+}
+
+static int ensure_stage(mopa_planner *p, size_t n) {
+    if (n <= p->stage_cap) return MOPA_OK;
+    size_t cap = p->stage_cap ? p->stage_cap : 256;
+    while (cap < n) cap *= 2;
+    if (p->d_stage_q) cudaFree(p->d_stage_q);
+    if (p->d_stage_r) cudaFree(p->d_stage_r);
+    if (p->h_stage_q) cudaFreeHost(p->h_stage_q);
+    if (p->h_stage_r) cudaFreeHost(p->h_stage_r);
+    p->d_stage_q = nullptr; p->d_stage_r = nullptr; p->h_stage_q = nullptr; p->h_stage_r = nullptr;
+    p->stage_cap = 0;
+    const size_t row = (size_t)p->scene.hdr.nq4 * 4;
+    CUDA_TRY(cudaMalloc(&p->d_stage_q, cap * row * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&p->d_stage_r, cap * sizeof(uint32_t)));
+    CUDA_TRY(cudaMallocHost(&p->h_stage_q, cap * row * sizeof(float)));
+    CUDA_TRY(cudaMallocHost(&p->h_stage_r, cap * sizeof(uint32_t)));
+    p->stage_cap = cap;
+    return MOPA_OK;
+}
+
+int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *valid, uint32_t *words, int32_t flags) {
+    if (!p || n < 0 || (n > 0 && (!qpos || !valid))) { g_err = "mopa_is_valid_host: bad argument"; return MOPA_ERR_ARG; }
+    if (n == 0) return MOPA_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_stage(p, (size_t)n);
+    if (rc) return rc;
+    const int nq = p->scene.hdr.nq, row = p->scene.hdr.nq4 * 4;
+    for (int i = 0; i < n; i++) {
+        float *dst = p->h_stage_q + (size_t)i * row;
+        const double *src = qpos + (size_t)i * nq;
+        for (int k = 0; k < nq; k++) dst[k] = (float)src[k];
+        for (int k = nq; k < row; k++) dst[k] = 0.0f;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_stage_q, p->h_stage_q, (size_t)n * row * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(mopa::launch_is_valid(p->d_blob, p->scene.hdr, p->d_stage_q, row, n, p->d_stage_r, flags & MOPA_VALID_FIRST_PAIR,
+                                   p->sm_count, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_stage_r, p->d_stage_r, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (int i = 0; i < n; i++) {
+        valid[i] = (uint8_t)(p->h_stage_r[i] & 1u);
+        if (words) words[i] = p->h_stage_r[i];
+    }
+    return MOPA_OK;
+}
+
+}  // extern "C"

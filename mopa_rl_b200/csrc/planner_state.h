@@ -1,0 +1,46 @@
+// Planner handle behind the C ABI (include/mopa_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/mopa_model_desc.h"
+#include "scene.h"
+
+namespace mopa {
+
+// The OMPL state space the reference builds over the active joints
+// (makeCompoundStateSpace, motion_planners/src/mujoco_ompl_interface.cpp:149-281): one
+// weight-1 subspace per joint, R^1 with jnt_range bounds for limited hinge/slide joints,
+// SO(2) for unlimited hinges.
+struct Space {
+    int nq = 0, n_active = 0;
+    std::vector<int> active_qadr;
+    std::vector<float> lo, hi;
+    std::vector<int> is_so2;
+    float range = 0.f, resolution = 0.005f;
+    uint64_t seed = 0;
+};
+
+void build_space(const mopa_model_desc *d, const int32_t *passive, int n_passive, double range, double resolution,
+                 uint64_t seed, Space &out);
+
+}  // namespace mopa
+
+struct mopa_planner {
+    int device = 0, sm_count = 148;
+    mopa::HostScene scene;
+    mopa::Space space;
+    unsigned char *d_blob = nullptr;
+    cudaStream_t stream = nullptr;
+    // staging for the *_host entry points (pinned host + device)
+    size_t stage_cap = 0;
+    float *d_stage_q = nullptr, *h_stage_q = nullptr;
+    uint32_t *d_stage_r = nullptr, *h_stage_r = nullptr;
+    // RRT-Connect work buffers (plan.cu)
+    void *plan_buffers = nullptr;
+};
+
+namespace mopa {
+void free_plan_buffers(mopa_planner *p);
+}

@@ -1,0 +1,84 @@
+// Device-side scene tables for the state-validity kernel.
+//
+// Built once per planner (host, scene_build.cu) from the flat mjModel-style arrays; plays
+// the role of the mjModel/mjData pair the reference planner owns
+// (motion_planners/KinematicPlanner.cpp:62-95).  Everything the kernel needs per query is
+// derived from qpos on chip; nothing here depends on the query.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+#include "collide.cuh"
+
+namespace mopa {
+
+enum { SEL_CUR = 0, SEL_SLOT0 = 1, SEL_SLOT1 = 2, SEL_CONST = 3 };
+enum { SAVE_NONE = -1 };
+enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
+
+struct FkJoint {
+    int type, qadr, has_jpos, pad;
+    float qpos0, ax, ay, az;
+    float jx, jy, jz, pad2;
+};
+struct FkBody {  // one body of the kinematic sub-tree that carries collidable geoms (DFS order)
+    float px, py, pz, pad0;       // body_pos
+    float qw, qx, qy, qz;         // body_quat
+    int parent_sel, const_idx, save_sel, pad1;
+    int jnt_begin, jnt_end, geom_begin, geom_end;
+};
+struct FkGeom {  // collidable geom attached to an FkBody
+    float px, py, pz;
+    int kind;
+    float m[9];
+    int slot;     // float offset of this geom's world frame in the per-query frame store
+    int rec;      // index into GeomRec
+    int pad;
+};
+struct ConstFrame {  // world frame of a static (world-welded) parent body
+    float px, py, pz, pad;
+    float qw, qx, qy, qz;
+    float m[9];
+    float pad2[3];
+};
+struct GeomRec {  // every collidable geom that appears in at least one candidate pair
+    float sx, sy, sz;
+    int kind;
+    int slot;        // >= 0: moving geom, float offset in the frame store;  -1: static
+    float px, py, pz;  // world frame when static
+    float m[9];
+    float rbound;
+    int geom_id;     // mjModel geom id
+    int pad;
+};
+struct PairRec {  // 32 bytes; candidate pair in kernel order (grouped by anchor = first moving geom)
+    float px, py, pz;   // centre of the partner when it is static
+    float bound2;       // squared bounding-sphere cull distance; < 0: no sphere test (plane pair)
+    uint16_t anchor_slot, partner_slot;  // frame-store offsets; partner_slot == 0xFFFF: static partner
+    uint16_t ga, gb;    // GeomRec indices, kind(ga) <= kind(gb)  (the order the narrowphase expects)
+    uint16_t canon;     // index in the canonical (g1<g2 lexicographic) candidate list
+    uint8_t cls;        // PairClass
+    uint8_t flags;
+    uint32_t pad;
+};
+
+struct SceneHeader {
+    int nq, nq4;             // qpos row length, and in float4 units (row stride = 4*nq4 floats)
+    int n_body, n_joint, n_geom, n_const, n_rec, n_pair;
+    int frame_floats;        // floats per query in the frame store
+    int n_site_pad;
+    float threshold;
+    int off_body, off_joint, off_geom, off_const, off_rec, off_pair;  // byte offsets from blob start
+    int blob_bytes;
+    int pad[2];
+};
+
+struct HostScene {
+    SceneHeader hdr;
+    std::vector<unsigned char> blob;   // header + tables, 16-byte aligned sections
+    std::vector<int> canon_g1, canon_g2;  // canonical pair list (mjModel geom ids)
+};
+
+struct mopa_model_desc_fwd;
+
+}  // namespace mopa

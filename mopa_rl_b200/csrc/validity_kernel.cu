@@ -1,0 +1,136 @@
+// mopa_is_valid_batch: batched state-validity checks on sm_100a.
+//
+// Layout per CTA (NQ threads = NQ queries per tile, persistent over tiles):
+//   shared: [scene blob][frame store: frame_floats x NQ][result word x NQ][two work queues]
+//   phase A  thread-per-query FK (registers), moving-geom frames -> shared (stride NQ, conflict free)
+//   phase B  thread-per-query loop over candidate pairs: bounding-sphere cull, cheap analytic
+//            pairs evaluated inline, box-box / MPR survivors pushed to CTA-wide queues
+//   phase C  the whole CTA drains the queues (one item per thread) so that the expensive,
+//            rarely-needed routines run with full lanes instead of one lane per warp
+// HBM traffic is the qpos row in and one 32-bit word out per query.
+#include <cuda_runtime.h>
+
+#include "validity_kernel.cuh"
+
+namespace mopa {
+
+struct RowQ {
+    const float *row;
+    __device__ __forceinline__ float operator()(int i) const { return __ldg(row + i); }
+};
+
+template <int NQ, int QCAP>
+__global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
+                                                      const float *__restrict__ qpos, int row_stride, int n,
+                                                      uint32_t *__restrict__ out, int exact) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < blob_bytes / 16; i += NQ) reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(blob_g)[i];
+    __syncthreads();
+    const SceneView S = view_scene(smem);
+    float *frames = reinterpret_cast<float *>(smem + blob_bytes);
+    uint32_t *res = reinterpret_cast<uint32_t *>(frames + (size_t)S.H->frame_floats * NQ);
+    uint32_t *queue = res + NQ;          // [2][QCAP]
+    int *qcount = reinterpret_cast<int *>(queue + 2 * QCAP);  // [2]
+    const float thr = S.H->threshold;
+    const int npair = S.H->n_pair;
+    const int ntile = (n + NQ - 1) / NQ;
+
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const int q = tile * NQ + tid;
+        const bool active = q < n;
+        if (tid < 2) qcount[tid] = 0;
+        uint32_t first = 0xFFFFFFFFu;
+        if (active) {
+            RowQ rq{qpos + (size_t)q * row_stride};
+            fk_state(S, rq, frames, NQ, tid);
+        }
+        __syncthreads();
+        if (active) {
+            int cur_anchor = -1;
+            V3 ac{0, 0, 0};
+            for (int p = 0; p < npair; p++) {
+                const PairRec pr = S.pairs[p];
+                if (pr.anchor_slot != cur_anchor) {
+                    cur_anchor = pr.anchor_slot;
+                    const float *f = frames + (size_t)cur_anchor * NQ + tid;
+                    ac = V3{f[0], f[NQ], f[2 * NQ]};
+                }
+                if (pr.bound2 >= 0.0f) {
+                    V3 pc{pr.px, pr.py, pr.pz};
+                    if (pr.partner_slot != 0xFFFF) {
+                        const float *f = frames + (size_t)pr.partner_slot * NQ + tid;
+                        pc = V3{f[0], f[NQ], f[2 * NQ]};
+                    }
+                    V3 d = pc - ac;
+                    if (dot(d, d) > pr.bound2) continue;
+                }
+                if (pr.cls >= PC_BOX_BOX) {
+                    if (pr.cls > PC_MPR) continue;
+                    const int k = pr.cls - PC_BOX_BOX;
+                    int idx = atomicAdd(&qcount[k], 1);
+                    if (idx < QCAP) { queue[k * QCAP + idx] = ((uint32_t)tid << 16) | (uint32_t)p; continue; }
+                }
+                Geom a, b;
+                load_geom(a, S.recs[pr.ga], frames, NQ, tid);
+                load_geom(b, S.recs[pr.gb], frames, NQ, tid);
+                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist(pr.cls, a, b) : cheap_dist(pr.cls, a, b);
+                if (dist <= thr) {
+                    first = min(first, (uint32_t)pr.canon);
+                    if (!exact) break;
+                }
+            }
+        }
+        res[tid] = first;
+        __syncthreads();
+        for (int k = 0; k < 2; k++) {
+            const int cnt = min(qcount[k], QCAP);
+            for (int i = tid; i < cnt; i += NQ) {
+                const uint32_t item = queue[k * QCAP + i];
+                const int ql = item >> 16, p = item & 0xFFFF;
+                if (!exact && res[ql] != 0xFFFFFFFFu) continue;
+                const PairRec pr = S.pairs[p];
+                Geom a, b;
+                load_geom(a, S.recs[pr.ga], frames, NQ, ql);
+                load_geom(b, S.recs[pr.gb], frames, NQ, ql);
+                float dist = heavy_dist(pr.cls, a, b);
+                if (dist <= thr) atomicMin(&res[ql], (uint32_t)pr.canon);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            uint32_t r = res[tid];
+            out[q] = (r == 0xFFFFFFFFu) ? 1u : (exact ? ((r + 1u) << 8) : 0u);
+        }
+    }
+}
+
+constexpr int VK_NQ = 128;
+constexpr int VK_QCAP = 1024;
+
+size_t validity_smem_bytes(const SceneHeader &H) {
+    return (size_t)H.blob_bytes + (size_t)H.frame_floats * VK_NQ * 4 + VK_NQ * 4 + 2 * VK_QCAP * 4 + 16;
+}
+
+cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    size_t smem = validity_smem_bytes(H);
+    auto kern = is_valid_kernel<VK_NQ, VK_QCAP>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int ntile = (n + VK_NQ - 1) / VK_NQ;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = sm_count * per_sm;
+    if (grid > ntile) grid = ntile;
+    kern<<<grid, VK_NQ, smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact);
+    return cudaGetLastError();
+}
+
+}  // namespace mopa

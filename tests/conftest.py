@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def push_model():
+    from mopa_rl_b200.model import load_model
+
+    return load_model("SawyerPushObstacle-v0")
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    from oracle import oracle
+
+    oracle.build()
+    return oracle

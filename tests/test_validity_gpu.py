@@ -1,0 +1,70 @@
+"""GPU <-> oracle parity of the state-validity kernel, through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+
+from helpers import PUSH_INIT_QPOS, planner_setup, random_qpos
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def push_pair(push_model, oracle_built):
+    from mopa_rl_b200.capi import NativePlanner
+
+    ignored, passive, ref = planner_setup(push_model)
+    native = NativePlanner(push_model, passive, ignored, -0.002, 0.1, seed=1234)
+    orc = oracle_built.OracleScene(push_model, ignored, -0.002, "f32")
+    return native, orc, ref
+
+
+def test_pair_list_matches_oracle(push_pair):
+    native, orc, _ = push_pair
+    g1, g2 = native.pairs()
+    o1, o2 = orc.pairs()
+    assert native.n_pairs == orc.npair == 241
+    assert np.array_equal(g1, o1) and np.array_equal(g2, o2)
+
+
+def test_init_pose_valid(push_pair, push_model):
+    native, orc, ref = push_pair
+    q = push_model.qpos0.copy()
+    q[ref] = PUSH_INIT_QPOS
+    assert native.is_valid_host(q)[0] == 1
+
+
+@pytest.mark.parametrize("seed,n", [(1234, 200000), (7, 50000)])
+def test_random_states_bit_exact(push_pair, push_model, seed, n):
+    native, orc, ref = push_pair
+    q = random_qpos(push_model, n, seed, ref)
+    ow = orc.is_valid(q)
+    v, w = native.is_valid_host(q, flags=1, return_words=True)
+    assert np.array_equal(w, ow), "first-offending-pair words differ at %d states" % (w != ow).sum()
+    vf = native.is_valid_host(q, flags=0)
+    assert np.array_equal(vf, (ow & 1).astype(np.uint8))
+    assert 0.2 < vf.mean() < 0.7
+
+
+def test_edge_sizes(push_pair, push_model):
+    native, orc, ref = push_pair
+    for n in (1, 2, 127, 128, 129, 1000):
+        q = random_qpos(push_model, n, 100 + n, ref)
+        assert np.array_equal(native.is_valid_host(q, flags=1, return_words=True)[1], orc.is_valid(q))
+    assert len(native.is_valid_host(np.zeros((0, push_model.nq)))) == 0
+    with pytest.raises(ValueError):
+        native.is_valid_host(np.zeros(push_model.nq - 1))
+
+
+def test_passive_dims_matter_only_where_they_should(push_pair, push_model):
+    """Ghost-arm joints (contype=conaffinity=0 chains) never change validity; the cube pose does."""
+    native, orc, ref = push_pair
+    q = random_qpos(push_model, 20000, 99, ref)
+    base = native.is_valid_host(q)
+    q2 = q.copy()
+    rng = np.random.default_rng(5)
+    q2[:, 9:27] = rng.uniform(-1, 1, (len(q), 18)).astype(np.float32)
+    assert np.array_equal(native.is_valid_host(q2), base)
+    q3 = q.copy()
+    q3[:, 27:30] = np.float32(0.6), np.float32(0.0), np.float32(1.2)  # cube floating in the arm's workspace
+    w3 = native.is_valid_host(q3, flags=1, return_words=True)[1]
+    assert np.array_equal(w3, orc.is_valid(q3))
+    assert (w3 & 1).mean() < base.mean()
