@@ -73,6 +73,30 @@ int mopa_is_valid_batch(mopa_planner *p, const float *d_qpos, int32_t row_stride
  * n host states of nq doubles each.  valid[i] in {0,1}; words (nullable) receives the result words. */
 int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *valid, uint32_t *words, int32_t flags);
 
+/* Node capacity of each RRT tree (default 4096).  A tree that fills up stops growing. */
+int mopa_planner_set_max_nodes(mopa_planner *p, int32_t max_nodes);
+
+/* Replaces KinematicPlanner::plan (KinematicPlanner.cpp:125-251, planner.pyx:45-46), batched: n
+ * independent problems, one warp each.  RRT-Connect with `range`, edge validation at
+ * `resolution`, passive dims frozen at the start values (KinematicPlanner.cpp:166,238).
+ *   d_start, d_goal  device, n rows of fp32 qpos (row_stride floats apart)
+ *   d_keys           device, n 64-bit problem keys for the counter-based RNG (with `seed`)
+ *   max_iter         cap on main-loop iterations (stands in for the wall-clock `timelimit`)
+ *   d_path           device, [n][max_path][row_stride] fp32 waypoints incl. the start row
+ *   d_node_ids       device, [n][max_path] tree-node index of each waypoint (bit 30: goal tree)
+ *   d_path_len       device, [n] rows written (0 on failure)
+ *   d_status         device, [n] MOPA_PLAN_*
+ *   d_iters,d_nodes  device, nullable: [n] iterations used, [n][2] tree sizes
+ */
+int mopa_plan_batch(mopa_planner *p, const float *d_start, const float *d_goal, int32_t row_stride, const uint64_t *d_keys,
+                    int32_t n, int32_t max_iter, float *d_path, int32_t *d_node_ids, int32_t max_path, int32_t *d_path_len,
+                    int32_t *d_status, int32_t *d_iters, int32_t *d_nodes, void *stream);
+
+/* Host-buffer variant (what PyKinematicPlanner.plan hands over: vectors of nq doubles).
+ *   path [n][max_path][nq] doubles, node_ids [n][max_path] (nullable), path_len/status/iters [n]. */
+int mopa_plan_host(mopa_planner *p, const double *start, const double *goal, const uint64_t *keys, int32_t n, int32_t max_iter,
+                   double *path, int32_t *node_ids, int32_t max_path, int32_t *path_len, int32_t *status, int32_t *iters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,11 @@ def lib():
         L.mopa_planner_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mopa_is_valid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.mopa_is_valid_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.mopa_planner_set_max_nodes.argtypes = [C.c_void_p, C.c_int32]
+        L.mopa_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mopa_plan_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -106,3 +111,31 @@ class NativePlanner:
         """Raw device-pointer entry (ints from torch ``data_ptr()``); enqueues, does not sync."""
         check(self._L.mopa_is_valid_batch(self.h, C.c_void_p(qpos_ptr), int(row_stride), int(n), C.c_void_p(result_ptr),
                                           int(flags), C.c_void_p(stream)))
+
+    def set_max_nodes(self, max_nodes):
+        check(self._L.mopa_planner_set_max_nodes(self.h, int(max_nodes)))
+
+    def plan_host(self, start, goal, keys, max_iter, max_path=512):
+        """n problems from host arrays.  Returns dict(status[n], path_len[n], path[n,max_path,nq], node_ids, iters)."""
+        s = np.ascontiguousarray(np.atleast_2d(start), dtype=np.float64)
+        g = np.ascontiguousarray(np.atleast_2d(goal), dtype=np.float64)
+        if s.shape[1] != self.nq or g.shape != s.shape:
+            raise ValueError("start/goal vectors must have dimension nq: %d" % self.nq)
+        n = len(s)
+        k = np.ascontiguousarray(np.broadcast_to(np.asarray(keys, dtype=np.uint64), (n,)))
+        path = np.zeros((n, max_path, self.nq), np.float64)
+        ids = np.zeros((n, max_path), np.int32)
+        plen = np.zeros(n, np.int32)
+        status = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        check(self._L.mopa_plan_host(self.h, _p(s), _p(g), _p(k), n, int(max_iter), _p(path), _p(ids), int(max_path), _p(plen),
+                                     _p(status), _p(iters)))
+        return dict(status=status, path_len=plen, path=path, node_ids=ids, iters=iters)
+
+    def plan_device(self, start_ptr, goal_ptr, row_stride, keys_ptr, n, max_iter, path_ptr, ids_ptr, max_path, len_ptr, status_ptr,
+                    iters_ptr=0, nodes_ptr=0, stream=0):
+        """Raw device-pointer entry; enqueues on `stream`, does not sync."""
+        check(self._L.mopa_plan_batch(self.h, C.c_void_p(start_ptr), C.c_void_p(goal_ptr), int(row_stride), C.c_void_p(keys_ptr),
+                                      int(n), int(max_iter), C.c_void_p(path_ptr), C.c_void_p(ids_ptr), int(max_path),
+                                      C.c_void_p(len_ptr), C.c_void_p(status_ptr), C.c_void_p(iters_ptr or None),
+                                      C.c_void_p(nodes_ptr or None), C.c_void_p(stream)))

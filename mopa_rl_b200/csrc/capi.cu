@@ -153,4 +153,38 @@ int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *
     return MOPA_OK;
 }
 
+int mopa_planner_set_max_nodes(mopa_planner *p, int32_t max_nodes) {
+    if (!p || max_nodes < 2) { g_err = "mopa_planner_set_max_nodes: bad argument"; return MOPA_ERR_ARG; }
+    p->max_nodes = max_nodes;
+    return MOPA_OK;
+}
+
+int mopa_plan_batch(mopa_planner *p, const float *d_start, const float *d_goal, int32_t row_stride, const uint64_t *d_keys,
+                    int32_t n, int32_t max_iter, float *d_path, int32_t *d_node_ids, int32_t max_path, int32_t *d_path_len,
+                    int32_t *d_status, int32_t *d_iters, int32_t *d_nodes, void *stream) {
+    if (!p || n < 0 || max_path < 2 || row_stride < p->scene.hdr.nq ||
+        (n > 0 && (!d_start || !d_goal || !d_keys || !d_path || !d_node_ids || !d_path_len || !d_status))) {
+        g_err = "mopa_plan_batch: bad argument";
+        return MOPA_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(mopa::launch_plan(p, d_start, d_goal, row_stride, (const unsigned long long *)d_keys, n, max_iter, d_path, d_node_ids,
+                               max_path, d_path_len, d_status, d_iters, d_nodes, (cudaStream_t)stream));
+    return MOPA_OK;
+}
+
+int mopa_plan_host(mopa_planner *p, const double *start, const double *goal, const uint64_t *keys, int32_t n, int32_t max_iter,
+                   double *path, int32_t *node_ids, int32_t max_path, int32_t *path_len, int32_t *status, int32_t *iters) {
+    if (!p || n < 0 || max_path < 2 || (n > 0 && (!start || !goal || !keys || !path || !path_len || !status))) {
+        g_err = "mopa_plan_host: bad argument";
+        return MOPA_ERR_ARG;
+    }
+    if (n == 0) return MOPA_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    std::string err;
+    int rc = mopa::plan_host(p, start, goal, keys, n, max_iter, path, node_ids, max_path, path_len, status, iters, err);
+    if (rc) { g_err = "mopa_plan_host: " + err; return MOPA_ERR_CUDA; }
+    return MOPA_OK;
+}
+
 }  // extern "C"

@@ -9,6 +9,10 @@
 
 namespace mopa {
 
+constexpr int PLAN_MAXD = 8;  // active joints per planner (Sawyer 7, Pusher 4)
+#define MOPA_PLAN_NOT_EXACT_ (-4)
+#define MOPA_PLAN_INVALID_GOAL_ (-5)
+
 // The OMPL state space the reference builds over the active joints
 // (makeCompoundStateSpace, motion_planners/src/mujoco_ompl_interface.cpp:149-281): one
 // weight-1 subspace per joint, R^1 with jnt_range bounds for limited hinge/slide joints,
@@ -39,8 +43,15 @@ struct mopa_planner {
     uint32_t *d_stage_r = nullptr, *h_stage_r = nullptr;
     // RRT-Connect work buffers (plan.cu)
     void *plan_buffers = nullptr;
+    int max_nodes = 4096;  // node capacity per tree
 };
 
+#include <string>
 namespace mopa {
 void free_plan_buffers(mopa_planner *p);
+cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_goal, int row_stride, const unsigned long long *d_keys,
+                        int n, int max_iter, float *d_path, int *d_node_ids, int max_path, int *d_path_len, int *d_status,
+                        int *d_iters, int *d_nodes, cudaStream_t stream);
+int plan_host(mopa_planner *p, const double *start, const double *goal, const uint64_t *keys, int n, int max_iter, double *path,
+              int32_t *node_ids, int max_path, int32_t *path_len, int32_t *status, int32_t *iters, std::string &err);
 }

@@ -100,3 +100,59 @@ class OracleScene:
 def primitive_dist(t1, p1, m1, s1, t2, p2, m2, s2, precision="f64"):
     a = [np.ascontiguousarray(x, dtype=np.float64).ravel() for x in (p1, m1, s1, p2, m2, s2)]
     return lib(precision).orc_primitive_dist(int(t1), _p(a[0]), _p(a[1]), _p(a[2]), int(t2), _p(a[3]), _p(a[4]), _p(a[5]))
+
+
+class OraclePlanner:
+    """RRT-Connect oracle for one scene (see orc_plan.c)."""
+
+    def __init__(self, scene: OracleScene, active_qadr, lo, hi, is_so2, range_, resolution=0.005, seed=0, max_nodes=4096):
+        self.scene = scene
+        L = scene.L
+        L.orc_planner_create.restype = C.c_void_p
+        L.orc_planner_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                         C.c_double, C.c_uint64, C.c_int]
+        L.orc_planner_destroy.argtypes = [C.c_void_p]
+        L.orc_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L = L
+        a = np.ascontiguousarray(active_qadr, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        so2 = np.ascontiguousarray(is_so2, dtype=np.int32)
+        self.h = L.orc_planner_create(scene.h, _p(a), _p(lo), _p(hi), _p(so2), len(a), float(range_), float(resolution),
+                                      int(seed) & 0xFFFFFFFFFFFFFFFF, int(max_nodes))
+        self.nq = scene.model.nq
+
+    def __del__(self):
+        try:
+            self.L.orc_planner_destroy(self.h)
+        except Exception:
+            pass
+
+    def plan(self, start, goal, key, max_iter, max_path=512):
+        s = np.ascontiguousarray(start, dtype=np.float64)
+        g = np.ascontiguousarray(goal, dtype=np.float64)
+        path = np.zeros((max_path, self.nq), np.float64)
+        ids = np.zeros(max_path, np.int32)
+        n = C.c_int32()
+        it = C.c_int32()
+        nn = np.zeros(2, np.int32)
+        st = self.L.orc_plan(self.h, _p(s), _p(g), int(key) & 0xFFFFFFFFFFFFFFFF, int(max_iter), _p(path), _p(ids), max_path,
+                             C.byref(n), C.byref(it), _p(nn))
+        return dict(status=st, path=path[: n.value].copy(), node_ids=ids[: n.value].copy(), iters=it.value, n_nodes=nn)
+
+
+def space_from_model(model, passive_idx):
+    """Active joints / bounds as makeCompoundStateSpace derives them (mujoco_ompl_interface.cpp:149-281)."""
+    adr, lo, hi, so2 = [], [], [], []
+    passive = set(int(i) for i in passive_idx)
+    for j in range(model.njnt):
+        a = int(model.jnt_qposadr[j])
+        if a in passive:
+            continue
+        adr.append(a)
+        if model.jnt_type[j] == 3 and not model.jnt_limited[j]:
+            so2.append(1), lo.append(-np.pi), hi.append(np.pi)
+        else:
+            so2.append(0), lo.append(model.jnt_range[j, 0]), hi.append(model.jnt_range[j, 1])
+    return adr, lo, hi, so2

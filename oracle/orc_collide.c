@@ -632,3 +632,13 @@ double orc_primitive_dist(int t1, const double *p1, const double *m1, const doub
     s.geom_type = gt; s.gpos = gp; s.gmat = gm; s.geom_size = gs; s.geom_margin = mg; s.geom_rbound = rb;
     return (double)pair_dist(&s, 0, 1);
 }
+
+/* single-state predicate for the planner oracle (orc_plan.c); q has nq entries */
+int orc_valid_one(void *h, const R *q) {
+    orc_scene *s = (orc_scene *)h;
+    fk(s, q);
+    for (int p = 0; p < s->npair; p++)
+        if (pair_dist(s, s->pair_g1[p], s->pair_g2[p]) <= s->threshold) return 0;
+    return 1;
+}
+int orc_scene_nq(void *h) { return ((orc_scene *)h)->nq; }

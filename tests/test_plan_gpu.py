@@ -1,0 +1,83 @@
+"""GPU <-> oracle parity of the RRT-Connect kernel: status, waypoints, tree-node indices."""
+import numpy as np
+import pytest
+
+from helpers import PUSH_INIT_QPOS, planner_setup, random_qpos
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def planners(push_model, oracle_built):
+    from mopa_rl_b200.capi import NativePlanner
+
+    ignored, passive, ref = planner_setup(push_model)
+    native = NativePlanner(push_model, passive, ignored, -0.002, 0.1, seed=1234)
+    scene = oracle_built.OracleScene(push_model, ignored, -0.002, "f32")
+    adr, lo, hi, so2 = oracle_built.space_from_model(push_model, passive)
+    orc = oracle_built.OraclePlanner(scene, adr, lo, hi, so2, 0.1, 0.005, seed=1234, max_nodes=4096)
+    return native, scene, orc, ref
+
+
+def _problems(model, scene, ref, n, seed):
+    q = random_qpos(model, 6 * n, seed, ref, spread=0.5)
+    v = q[(scene.is_valid(q) & 1) == 1]
+    assert len(v) >= 2 * n
+    return v[:n], v[n:2 * n]
+
+
+def test_plan_matches_oracle(planners, push_model):
+    native, scene, orc, ref = planners
+    n = 96
+    start, goal = _problems(push_model, scene, ref, n, 21)
+    keys = np.arange(n, dtype=np.uint64) + 1000
+    out = native.plan_host(start, goal, keys, max_iter=400, max_path=512)
+    n_ok = 0
+    for i in range(n):
+        r = orc.plan(start[i], goal[i], int(keys[i]), 400, 512)
+        assert out["status"][i] == r["status"], i
+        assert out["iters"][i] == r["iters"], i
+        L = len(r["path"])
+        assert out["path_len"][i] == L
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.array_equal(out["node_ids"][i, :L], r["node_ids"]), "waypoint indices differ for problem %d" % i
+            assert np.array_equal(out["path"][i, :L], r["path"]), "waypoints differ for problem %d" % i
+            # path invariants (OMPL): starts at start, ends at goal, hops within range (L1), every vertex valid
+            p = r["path"][:, ref]
+            assert np.allclose(p[0], start[i][ref].astype(np.float32)) and np.allclose(p[-1], goal[i][ref].astype(np.float32))
+            assert np.abs(np.diff(p, axis=0)).sum(1).max() <= 0.1 + 1e-5
+            assert (scene.is_valid(r["path"]) & 1).all()
+    assert n_ok >= n // 2
+
+
+def test_sentinels(planners, push_model):
+    native, scene, orc, ref = planners
+    q0 = push_model.qpos0.copy()
+    q0[ref] = PUSH_INIT_QPOS
+    cand = random_qpos(push_model, 64, 5, ref)
+    bad = cand[(scene.is_valid(cand) & 1) == 0][0]  # some colliding arm configuration
+    assert scene.is_valid(bad)[0] & 1 == 0 and scene.is_valid(q0)[0] & 1 == 1
+    out = native.plan_host(np.stack([q0, bad, q0]), np.stack([bad, q0, q0]), [1, 2, 3], max_iter=50)
+    assert out["status"][0] == -5 and out["path_len"][0] == 0     # invalid goal -> the reference's -5 row
+    assert out["status"][1] == -4 and out["path_len"][1] == 0     # invalid start -> no exact solution (-4 row)
+    assert out["status"][2] == 0                                  # start == goal: trivially connected
+    oob = q0.copy()
+    oob[ref[0]] = 3.2  # outside jnt_range of right_j0
+    out = native.plan_host(q0[None], oob[None], [9], max_iter=50)
+    assert out["status"][0] in (-4, -5)
+    r = orc.plan(q0, oob, 9, 50)
+    assert r["status"] == out["status"][0]
+
+
+def test_passive_dims_frozen_and_key_dependence(planners, push_model):
+    native, scene, orc, ref = planners
+    start, goal = _problems(push_model, scene, ref, 8, 33)
+    a = native.plan_host(start, goal, np.arange(8) + 1, max_iter=300)
+    b = native.plan_host(start, goal, np.arange(8) + 1, max_iter=300)
+    assert np.array_equal(a["path"], b["path"]) and np.array_equal(a["status"], b["status"])  # deterministic
+    passive = [i for i in range(push_model.nq) if i not in ref]
+    for i in range(8):
+        L = a["path_len"][i]
+        if L:
+            assert np.array_equal(a["path"][i, :L][:, passive], np.tile(start[i][passive].astype(np.float32), (L, 1)))
