@@ -73,6 +73,11 @@ int mopa_is_valid_batch(mopa_planner *p, const float *d_qpos, int32_t row_stride
  * n host states of nq doubles each.  valid[i] in {0,1}; words (nullable) receives the result words. */
 int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *valid, uint32_t *words, int32_t flags);
 
+/* Same check for n host rows that are already fp32 (row_stride floats apart, pinned memory
+ * recommended): the rows are streamed to the device in chunks on two streams so that the
+ * host->device copy, the kernel and the device->host copy of the result words overlap. */
+int mopa_is_valid_host_f32(mopa_planner *p, const float *qpos, int32_t row_stride, int32_t n, uint32_t *words, int32_t flags);
+
 /* Node capacity of each RRT tree (default 4096).  A tree that fills up stops growing. */
 int mopa_planner_set_max_nodes(mopa_planner *p, int32_t max_nodes);
 

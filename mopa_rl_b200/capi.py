@@ -39,6 +39,7 @@ def lib():
         L.mopa_planner_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mopa_is_valid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.mopa_is_valid_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.mopa_is_valid_host_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         L.mopa_planner_set_max_nodes.argtypes = [C.c_void_p, C.c_int32]
         L.mopa_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -111,6 +112,10 @@ class NativePlanner:
         """Raw device-pointer entry (ints from torch ``data_ptr()``); enqueues, does not sync."""
         check(self._L.mopa_is_valid_batch(self.h, C.c_void_p(qpos_ptr), int(row_stride), int(n), C.c_void_p(result_ptr),
                                           int(flags), C.c_void_p(stream)))
+
+    def is_valid_host_f32(self, qpos_ptr, row_stride, n, words_ptr, flags=VALID_FAST):
+        """Host fp32 rows (ideally pinned) -> result words in host memory; pipelined copies; blocks until done."""
+        check(self._L.mopa_is_valid_host_f32(self.h, C.c_void_p(qpos_ptr), int(row_stride), int(n), C.c_void_p(words_ptr), int(flags)))
 
     def set_max_nodes(self, max_nodes):
         check(self._L.mopa_planner_set_max_nodes(self.h, int(max_nodes)))

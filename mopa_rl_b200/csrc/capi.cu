@@ -79,6 +79,11 @@ void mopa_planner_destroy(mopa_planner *p) {
     if (p->h_stage_q) cudaFreeHost(p->h_stage_q);
     if (p->h_stage_r) cudaFreeHost(p->h_stage_r);
     mopa::free_plan_buffers(p);
+    for (int k = 0; k < 2; k++) {
+        if (p->pipe_q[k]) cudaFree(p->pipe_q[k]);
+        if (p->pipe_r[k]) cudaFree(p->pipe_r[k]);
+        if (p->pipe_stream[k]) cudaStreamDestroy(p->pipe_stream[k]);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -150,6 +155,35 @@ int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *
         valid[i] = (uint8_t)(p->h_stage_r[i] & 1u);
         if (words) words[i] = p->h_stage_r[i];
     }
+    return MOPA_OK;
+}
+
+int mopa_is_valid_host_f32(mopa_planner *p, const float *qpos, int32_t row_stride, int32_t n, uint32_t *words, int32_t flags) {
+    if (!p || n < 0 || row_stride < p->scene.hdr.nq || (n > 0 && (!qpos || !words))) { g_err = "mopa_is_valid_host_f32: bad argument"; return MOPA_ERR_ARG; }
+    if (n == 0) return MOPA_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int chunk = 1 << 19;
+    if (!p->pipe_q[0] || p->pipe_stride != row_stride) {
+        for (int k = 0; k < 2; k++) {
+            if (p->pipe_q[k]) cudaFree(p->pipe_q[k]);
+            if (p->pipe_r[k]) cudaFree(p->pipe_r[k]);
+            p->pipe_q[k] = nullptr; p->pipe_r[k] = nullptr;
+            CUDA_TRY(cudaMalloc(&p->pipe_q[k], (size_t)chunk * row_stride * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&p->pipe_r[k], (size_t)chunk * sizeof(uint32_t)));
+            if (!p->pipe_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&p->pipe_stream[k], cudaStreamNonBlocking));
+        }
+        p->pipe_stride = row_stride;
+    }
+    int k = 0;
+    for (int off = 0; off < n; off += chunk, k ^= 1) {
+        const int m = (n - off) < chunk ? (n - off) : chunk;
+        cudaStream_t st = p->pipe_stream[k];
+        CUDA_TRY(cudaMemcpyAsync(p->pipe_q[k], qpos + (size_t)off * row_stride, (size_t)m * row_stride * sizeof(float), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(mopa::launch_is_valid(p->d_blob, p->scene.hdr, p->pipe_q[k], row_stride, m, p->pipe_r[k], flags & MOPA_VALID_FIRST_PAIR, p->sm_count, st));
+        CUDA_TRY(cudaMemcpyAsync(words + off, p->pipe_r[k], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[1]));
     return MOPA_OK;
 }
 

@@ -41,6 +41,11 @@ struct mopa_planner {
     size_t stage_cap = 0;
     float *d_stage_q = nullptr, *h_stage_q = nullptr;
     uint32_t *d_stage_r = nullptr, *h_stage_r = nullptr;
+    // double-buffered pipeline of mopa_is_valid_host_f32
+    float *pipe_q[2] = {nullptr, nullptr};
+    uint32_t *pipe_r[2] = {nullptr, nullptr};
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+    int pipe_stride = 0;
     // RRT-Connect work buffers (plan.cu)
     void *plan_buffers = nullptr;
     int max_nodes = 4096;  // node capacity per tree
