@@ -13,6 +13,7 @@
 #define MOPA_B200_H
 #include <stdint.h>
 
+#include "mopa_dyn_desc.h"
 #include "mopa_model_desc.h"
 
 #ifdef __cplusplus
@@ -101,6 +102,52 @@ int mopa_plan_batch(mopa_planner *p, const float *d_start, const float *d_goal, 
  *   path [n][max_path][nq] doubles, node_ids [n][max_path] (nullable), path_len/status/iters [n]. */
 int mopa_plan_host(mopa_planner *p, const double *start, const double *goal, const uint64_t *keys, int32_t n, int32_t max_iter,
                    double *path, int32_t *node_ids, int32_t max_path, int32_t *path_len, int32_t *status, int32_t *iters);
+
+/* ------------------------------------------------------------------------------------------
+ * Vectorised environments (replaces BaseEnv.step / SawyerPushObstacleEnv._step, compute_reward,
+ * _get_obs and BaseEnv._after_step: env/base.py:232-314, env/sawyer/sawyer_push_obstacle.py:71-208).
+ * One thread integrates one environment; the 75 mj_step-equivalent substeps of an env.step stay
+ * on chip.  All state lives in caller-owned device arrays (torch tensors on the Python side).
+ */
+typedef struct mopa_env mopa_env;
+
+typedef struct mopa_sawyer_task {
+    int32_t kind;                 /* 0: SawyerPushObstacle-v0 */
+    int32_t arm_qadr[7], arm_vadr[7], arm_dof[7];   /* qpos / qvel addresses and simulated-dof indices of right_j0..6 */
+    int32_t grip_qadr[2], grip_vadr[2];             /* rc_close, lc_close */
+    int32_t body_ee, body_cube, body_rclaw, body_lclaw; /* simulated-body indices */
+    int32_t target_qadr[2];
+    int32_t max_episode_steps, nsub;                /* 250; int(frame_dt / timestep) = 75 */
+    double site_right_eef[3], site_left_eef[3], site_grip[3];  /* site positions in their body frames */
+    double target_base[3];                          /* body_pos of the target body */
+    double ac_scale, distance_threshold, success_reward;
+} mopa_sawyer_task;
+
+typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
+    double *qpos;        /* [n][nq] */
+    double *qvel;        /* [n][nv] */
+    double *prev_state;  /* [n][7]  SawyerEnv._prev_state */
+    double *bias_prev;   /* [n][16] qfrc_bias of the previous mj_step on the simulated dofs */
+    uint8_t *has_prev;   /* [n]     _prev_state is not None */
+    int32_t *ep_len;     /* [n]     _episode_length */
+    double *ep_rew;      /* [n]     _episode_reward */
+    float *obs;          /* [n][40] observation in the reference's key order */
+    double *reward;      /* [n] */
+    uint8_t *done;       /* [n]     _terminal after _after_step */
+    uint8_t *success;    /* [n]     _success */
+    int32_t *ncon;       /* [n]     contacts in the last substep */
+} mopa_env_buffers;
+
+int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out);
+void mopa_env_destroy(mopa_env *e);
+int mopa_env_enable_contacts(mopa_env *e, int32_t on);
+/* sim.forward() + _get_obs() for the listed envs (d_ids nullable = all n): refreshes bias_prev and obs
+ * from qpos/qvel.  Called after reset / set_state. */
+int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_ids, int32_t n, void *stream);
+/* env.step(action, is_planner) for every env whose mask byte is non-zero (d_mask nullable = all).
+ * d_action [n][action_stride] fp32 (first 7 used), d_is_planner [n] (nullable = all false). */
+int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
+                  const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,259 @@
+// Vectorised Sawyer environments: env.step on sm_100a, one thread per environment.
+//
+// Replaces BaseEnv.step -> SawyerPushObstacleEnv._step -> 75 x sim.step() -> compute_reward /
+// _get_obs -> BaseEnv._after_step (env/base.py:232-314, env/sawyer/sawyer_push_obstacle.py:71-208,
+// env/sawyer/sawyer.py:317-338).  The physics is dyn.cuh; this file adds the reference's env
+// logic around it: the latched _prev_state, action clipping, gravity compensation by the
+// previous step's qfrc_bias, reward / success, the 40-float observation and the joint-limit
+// projection + episode accounting of _after_step.  Per env.step HBM sees the state row in and
+// out plus the observation; the substeps never leave the SM.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/mopa_b200.h"
+#include "dyn.cuh"
+#include "contact.cuh"
+
+struct mopa_env {
+    int device = 0;
+    mopa::DynDev *d_model = nullptr;
+    mopa::DynDev h_model;
+    mopa_sawyer_task task;
+};
+
+namespace mopa {
+
+__device__ __forceinline__ void site_world(double *out, const DynData &D, int b, const double *local) {
+    double t[3];
+    d_mv(t, D.xmat[b], local);
+    for (int k = 0; k < 3; k++) out[k] = D.xpos[b][k] + t[k];
+}
+
+// observation in the reference's key order (SawyerEnv._get_obs + SawyerPushObstacleEnv._get_obs)
+__device__ void write_obs(const mopa_sawyer_task &T, const DynData &D, const double *q, const double *v, float *obs) {
+    int o = 0;
+    for (int k = 0; k < 7; k++) obs[o++] = (float)q[T.arm_qadr[k]];
+    for (int k = 0; k < 7; k++) obs[o++] = (float)v[T.arm_vadr[k]];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)q[T.grip_qadr[k]];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)v[T.grip_vadr[k]];
+    double eef[3];
+    site_world(eef, D, T.body_ee, T.site_grip);
+    for (int k = 0; k < 3; k++) obs[o++] = (float)eef[k];
+    const double *eq = D.xquat[T.body_ee];  // wxyz -> xyzw
+    obs[o++] = (float)eq[1]; obs[o++] = (float)eq[2]; obs[o++] = (float)eq[3]; obs[o++] = (float)eq[0];
+    double target[3] = {T.target_base[0] + q[T.target_qadr[0]], T.target_base[1] + q[T.target_qadr[1]], T.target_base[2]};
+    for (int k = 0; k < 3; k++) obs[o++] = (float)target[k];
+    const double *cube = D.xpos[T.body_cube], *cq = D.xquat[T.body_cube];
+    for (int k = 0; k < 3; k++) obs[o++] = (float)cube[k];
+    obs[o++] = (float)cq[1]; obs[o++] = (float)cq[2]; obs[o++] = (float)cq[3]; obs[o++] = (float)cq[0];
+    for (int k = 0; k < 3; k++) obs[o++] = (float)(eef[k] - cube[k]);
+    for (int k = 0; k < 2; k++) obs[o++] = (float)(cube[k] - target[k]);
+}
+
+__global__ void __launch_bounds__(64) env_forward_kernel(const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B,
+                                                         const int32_t *__restrict__ ids, int n) {
+    __shared__ DynDev m;
+    for (int i = threadIdx.x; i < (int)(sizeof(DynDev) / 4); i += blockDim.x) reinterpret_cast<int *>(&m)[i] = reinterpret_cast<const int *>(mg)[i];
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int e = ids ? ids[t] : t;
+    double q[64], v[64], zero[DMAXD], ctrl[DMAXA];
+    for (int k = 0; k < m.nq; k++) q[k] = B.qpos[(size_t)e * m.nq + k];
+    for (int k = 0; k < m.nv; k++) v[k] = B.qvel[(size_t)e * m.nv + k];
+    for (int k = 0; k < DMAXD; k++) zero[k] = 0;
+    for (int k = 0; k < DMAXA; k++) ctrl[k] = 0;
+    DynData D;
+    dyn_substep(m, q, v, ctrl, zero, D, false);
+    for (int k = 0; k < DMAXD; k++) B.bias_prev[(size_t)e * DMAXD + k] = k < m.nd ? D.bias[k] : 0.0;
+    write_obs(T, D, q, v, B.obs + (size_t)e * 40);
+}
+
+__global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B,
+                                                      const float *__restrict__ action, int action_stride,
+                                                      const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n) {
+    __shared__ DynDev m;
+    for (int i = threadIdx.x; i < (int)(sizeof(DynDev) / 4); i += blockDim.x) reinterpret_cast<int *>(&m)[i] = reinterpret_cast<const int *>(mg)[i];
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || (mask && !mask[e])) return;
+    double q[64], v[64], applied[DMAXD], bias_prev[DMAXD], ctrl[DMAXA], prev[7];
+    for (int k = 0; k < m.nq; k++) q[k] = B.qpos[(size_t)e * m.nq + k];
+    for (int k = 0; k < m.nv; k++) v[k] = B.qvel[(size_t)e * m.nv + k];
+    for (int k = 0; k < DMAXD; k++) bias_prev[k] = B.bias_prev[(size_t)e * DMAXD + k];
+    const bool planner = is_planner && is_planner[e];
+    const bool had_prev = B.has_prev[e] != 0;
+    for (int k = 0; k < 7; k++) prev[k] = (!planner || !had_prev) ? q[T.arm_qadr[k]] : B.prev_state[(size_t)e * 7 + k];
+    for (int k = 0; k < DMAXA; k++) ctrl[k] = 0;
+    for (int k = 0; k < 7; k++) {
+        double a = (double)action[(size_t)e * action_stride + k];
+        if (!planner) a = a * T.ac_scale;
+        a = a < -T.ac_scale ? -T.ac_scale : (a > T.ac_scale ? T.ac_scale : a);
+        ctrl[k] = prev[k] + a;  // desired_state
+    }
+    // which simulated dofs get qfrc_applied = previous qfrc_bias (gravity compensation on the arm)
+    unsigned comp = 0;
+    for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
+    DynData D;
+    for (int s = 0; s < T.nsub; s++) {
+        for (int k = 0; k < DMAXD; k++) applied[k] = (comp >> k) & 1u ? bias_prev[k] : 0.0;
+        dyn_substep(m, q, v, ctrl, applied, D, true);
+        for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
+    }
+    // reward (frames are those of the last substep's start state, as mjData holds them after mj_step)
+    double re[3], le[3];
+    site_world(re, D, T.body_rclaw, T.site_right_eef);
+    site_world(le, D, T.body_lclaw, T.site_left_eef);
+    const double *cube = D.xpos[T.body_cube];
+    const double target[2] = {T.target_base[0] + q[T.target_qadr[0]], T.target_base[1] + q[T.target_qadr[1]]};
+    double dgc = 0;
+    for (int k = 0; k < 3; k++) { const double d = cube[k] - 0.5 * (re[k] + le[k]); dgc += d * d; }
+    dgc = sqrt(dgc);
+    const double dct = sqrt((cube[0] - target[0]) * (cube[0] - target[0]) + (cube[1] - target[1]) * (cube[1] - target[1]));
+    double reward = 0;
+    if (dct < 0.1) reward += 0.5 * (1 - tanh(5 * dct));
+    if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
+    bool success = false, terminal = false;
+    if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
+    write_obs(T, D, q, v, B.obs + (size_t)e * 40);
+    // _after_step: project limited joints back into range (set_state + forward), episode accounting
+    bool clipped = false;
+    for (int k = 0; k < m.nd; k++) {
+        if (!m.d_limited[k] || m.d_qadr[k] < 0) continue;
+        double &x = q[m.d_qadr[k]];
+        if (x < m.d_range[k][0]) { x = m.d_range[k][0]; clipped = true; }
+        else if (x > m.d_range[k][1]) { x = m.d_range[k][1]; clipped = true; }
+    }
+    if (clipped) {
+        dyn_substep(m, q, v, ctrl, applied, D, false);
+        for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
+    }
+    const int len = B.ep_len[e] + 1;
+    if (len == T.max_episode_steps) terminal = true;
+    for (int k = 0; k < m.nq; k++) B.qpos[(size_t)e * m.nq + k] = q[k];
+    for (int k = 0; k < m.nv; k++) B.qvel[(size_t)e * m.nv + k] = v[k];
+    for (int k = 0; k < 7; k++) B.prev_state[(size_t)e * 7 + k] = ctrl[k];
+    for (int k = 0; k < DMAXD; k++) B.bias_prev[(size_t)e * DMAXD + k] = bias_prev[k];
+    B.has_prev[e] = 1;
+    B.ep_len[e] = len;
+    B.ep_rew[e] += reward;
+    B.reward[e] = reward;
+    B.done[e] = terminal ? 1 : 0;
+    B.success[e] = success ? 1 : 0;
+    if (B.ncon) B.ncon[e] = D.ncon;
+}
+
+static void fill_model(const mopa_dyn_desc *d, DynDev &m) {
+    memset(&m, 0, sizeof(m));
+    m.nq = d->nq; m.nv = d->nv; m.nb = d->nb; m.nd = d->nd; m.nact = d->nact; m.ngeom = d->ngeom; m.npair = d->npair;
+    m.iterations = d->iterations; m.h = d->timestep;
+    for (int k = 0; k < 3; k++) m.g[k] = d->gravity[k];
+    for (int i = 0; i < d->nb; i++) {
+        m.b_parent[i] = d->b_parent[i]; m.b_jtype[i] = d->b_jtype[i]; m.b_qadr[i] = d->b_qadr[i]; m.b_vadr[i] = d->b_vadr[i];
+        m.b_dadr[i] = d->b_dadr[i]; m.b_qpos0[i] = d->b_qpos0[i]; m.b_mass[i] = d->b_mass[i];
+        for (int k = 0; k < 3; k++) {
+            m.b_pos[i][k] = d->b_pos[3 * i + k]; m.b_rootpos[i][k] = d->b_rootpos[3 * i + k]; m.b_jaxis[i][k] = d->b_jaxis[3 * i + k];
+            m.b_jpos[i][k] = d->b_jpos[3 * i + k]; m.b_ipos[i][k] = d->b_ipos[3 * i + k]; m.b_inertia[i][k] = d->b_inertia[3 * i + k];
+        }
+        for (int k = 0; k < 4; k++) { m.b_quat[i][k] = d->b_quat[4 * i + k]; m.b_rootquat[i][k] = d->b_rootquat[4 * i + k]; m.b_iquat[i][k] = d->b_iquat[4 * i + k]; }
+    }
+    for (int i = 0; i < d->nd; i++) {
+        m.d_body[i] = d->d_body[i]; m.d_qadr[i] = d->d_qadr[i]; m.d_vadr[i] = d->d_vadr[i]; m.d_limited[i] = d->d_limited[i];
+        m.d_armature[i] = d->d_armature[i]; m.d_damping[i] = d->d_damping[i]; m.d_margin[i] = d->d_margin[i];
+        for (int k = 0; k < 2; k++) { m.d_range[i][k] = d->d_range[2 * i + k]; m.d_solref[i][k] = d->d_solref[2 * i + k]; }
+        for (int k = 0; k < 5; k++) m.d_solimp[i][k] = d->d_solimp[5 * i + k];
+        const int b = m.d_body[i];
+        if (i > 0 && m.d_body[i - 1] == b) { m.d_parent[i] = i - 1; continue; }
+        int p = m.b_parent[b];
+        while (p >= 0 && m.b_jtype[p] < 0) p = m.b_parent[p];
+        m.d_parent[i] = p < 0 ? -1 : m.b_dadr[p] + (m.b_jtype[p] == 0 ? 5 : 0);
+    }
+    for (int i = 0; i < d->nact; i++) {
+        m.a_dof[i] = d->a_dof[i]; m.a_kind[i] = d->a_kind[i]; m.a_ctrllimited[i] = d->a_ctrllimited[i]; m.a_forcelimited[i] = d->a_forcelimited[i];
+        m.a_kp[i] = d->a_kp[i]; m.a_kv[i] = d->a_kv[i]; m.a_gear[i] = d->a_gear[i];
+        for (int k = 0; k < 2; k++) { m.a_ctrlrange[i][k] = d->a_ctrlrange[2 * i + k]; m.a_forcerange[i][k] = d->a_forcerange[2 * i + k]; }
+    }
+    for (int i = 0; i < d->ngeom; i++) {
+        m.g_body[i] = d->g_body[i]; m.g_type[i] = d->g_type[i]; m.g_rbound[i] = d->g_rbound[i]; m.g_margin[i] = d->g_margin[i];
+        for (int k = 0; k < 3; k++) { m.g_pos[i][k] = d->g_pos[3 * i + k]; m.g_size[i][k] = d->g_size[3 * i + k]; m.g_friction[i][k] = d->g_friction[3 * i + k]; }
+        for (int k = 0; k < 4; k++) m.g_quat[i][k] = d->g_quat[4 * i + k];
+        for (int k = 0; k < 2; k++) m.g_solref[i][k] = d->g_solref[2 * i + k];
+        for (int k = 0; k < 5; k++) m.g_solimp[i][k] = d->g_solimp[5 * i + k];
+    }
+    for (int i = 0; i < d->npair; i++) { m.p_g1[i] = d->p_g1[i]; m.p_g2[i] = d->p_g2[i]; }
+    m.enable_contacts = 1;
+}
+
+}  // namespace mopa
+
+void mopa_set_error(const std::string &s);
+#define ENV_TRY(x)                                                                                  \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) { mopa_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return MOPA_ERR_CUDA; } \
+    } while (0)
+
+extern "C" {
+
+int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out) {
+    if (!dyn || !task || !out) { mopa_set_error("mopa_env_create: bad argument"); return MOPA_ERR_ARG; }
+    *out = nullptr;
+    if (dyn->nb > mopa::DMAXB || dyn->nd > mopa::DMAXD || dyn->nact > mopa::DMAXA || dyn->ngeom > mopa::DMAXG || dyn->npair > 512 ||
+        dyn->nq > 64 || dyn->nv > 64) {
+        mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
+        return MOPA_ERR_MODEL;
+    }
+    if (task->kind != 0) { mopa_set_error("mopa_env_create: only the SawyerPushObstacle task is built"); return MOPA_ERR_MODEL; }
+    mopa_env *e = new mopa_env();
+    e->device = device;
+    e->task = *task;
+    mopa::fill_model(dyn, e->h_model);
+    cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaMalloc(&e->d_model, sizeof(mopa::DynDev));
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        mopa_set_error(std::string("mopa_env_create: ") + cudaGetErrorString(err) + " (a CUDA device is required; there is no CPU fallback)");
+        delete e;
+        return MOPA_ERR_CUDA;
+    }
+    *out = e;
+    return MOPA_OK;
+}
+
+void mopa_env_destroy(mopa_env *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->d_model) cudaFree(e->d_model);
+    delete e;
+}
+
+int mopa_env_enable_contacts(mopa_env *e, int32_t on) {
+    if (!e) return MOPA_ERR_ARG;
+    e->h_model.enable_contacts = on ? 1 : 0;
+    ENV_TRY(cudaSetDevice(e->device));
+    ENV_TRY(cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice));
+    return MOPA_OK;
+}
+
+int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_ids, int32_t n, void *stream) {
+    if (!e || !buf || n < 0) { mopa_set_error("mopa_env_forward: bad argument"); return MOPA_ERR_ARG; }
+    if (n == 0) return MOPA_OK;
+    ENV_TRY(cudaSetDevice(e->device));
+    mopa::env_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_ids, n);
+    ENV_TRY(cudaGetLastError());
+    return MOPA_OK;
+}
+
+int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
+                  const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream) {
+    if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
+    if (n_envs == 0) return MOPA_OK;
+    ENV_TRY(cudaSetDevice(e->device));
+    mopa::env_step_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_action, action_stride,
+                                                                              d_is_planner, d_mask, n_envs);
+    ENV_TRY(cudaGetLastError());
+    return MOPA_OK;
+}
+
+}  // extern "C"

@@ -124,7 +124,7 @@ cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, c
         attr_set = true;
     }
     int ntile = (n + VK_NQ - 1) / VK_NQ;
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int grid = sm_count * per_sm;

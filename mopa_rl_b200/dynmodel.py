@@ -1,0 +1,191 @@
+"""Selects the simulated sub-trees of a compiled scene and packs them as ``mopa_dyn_desc``
+(include/mopa_dyn_desc.h) for the env-step kernel and its oracle.
+
+The reference steps the whole ``mjModel`` (``sim.step()``, env/base.py:388-392).  A kinematic
+tree can only move if something acts on it, i.e. if it holds an actuated joint or a collidable
+geom; the indicator / target "ghost" arms and the target slider hold neither, so they are left
+out of the integration and keep the qpos that reset wrote.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .mjcf import JNT_FREE, JNT_HINGE, JNT_SLIDE, quat_mul, quat_to_mat
+
+_I = C.POINTER(C.c_int32)
+_D = C.POINTER(C.c_double)
+
+
+class DynDesc(C.Structure):
+    _fields_ = [
+        ("nq", C.c_int32), ("nv", C.c_int32), ("nb", C.c_int32), ("nd", C.c_int32), ("nact", C.c_int32),
+        ("ngeom", C.c_int32), ("npair", C.c_int32), ("iterations", C.c_int32),
+        ("timestep", C.c_double), ("gravity", C.c_double * 3),
+        ("b_parent", _I), ("b_bodyid", _I), ("b_pos", _D), ("b_quat", _D), ("b_rootpos", _D), ("b_rootquat", _D),
+        ("b_jtype", _I), ("b_qadr", _I), ("b_vadr", _I), ("b_dadr", _I), ("b_jaxis", _D), ("b_jpos", _D), ("b_qpos0", _D),
+        ("b_mass", _D), ("b_ipos", _D), ("b_iquat", _D), ("b_inertia", _D),
+        ("d_body", _I), ("d_qadr", _I), ("d_vadr", _I), ("d_armature", _D), ("d_damping", _D), ("d_limited", _I),
+        ("d_range", _D), ("d_solref", _D), ("d_solimp", _D), ("d_margin", _D),
+        ("a_dof", _I), ("a_kind", _I), ("a_ctrllimited", _I), ("a_forcelimited", _I), ("a_kp", _D), ("a_kv", _D),
+        ("a_gear", _D), ("a_ctrlrange", _D), ("a_forcerange", _D),
+        ("g_body", _I), ("g_geomid", _I), ("g_type", _I), ("g_pos", _D), ("g_quat", _D), ("g_size", _D), ("g_rbound", _D),
+        ("g_margin", _D), ("g_friction", _D), ("g_solref", _D), ("g_solimp", _D), ("g_condim", _I), ("p_g1", _I), ("p_g2", _I),
+    ]
+
+
+def static_frames(m):
+    """World frames (pos, quat) of bodies with no joint in their ancestry (weld id 0)."""
+    pos = np.zeros((m.nbody, 3))
+    quat = np.tile(np.array([1.0, 0, 0, 0]), (m.nbody, 1))
+    for b in range(1, m.nbody):
+        if m.body_weldid[b] != 0:
+            continue
+        p = m.body_parentid[b]
+        pos[b] = pos[p] + quat_to_mat(quat[p]) @ m.body_pos[b]
+        quat[b] = quat_mul(quat[p], m.body_quat[b])
+    return pos, quat
+
+
+def candidate_pairs(m):
+    """Geom pairs that survive MuJoCo's static collision filters."""
+    out = []
+    excl = {(int(a), int(b)) for a, b in m.exclude_body} | {(int(b), int(a)) for a, b in m.exclude_body}
+    for g1 in range(m.ngeom):
+        for g2 in range(g1 + 1, m.ngeom):
+            b1, b2 = int(m.geom_bodyid[g1]), int(m.geom_bodyid[g2])
+            w1, w2 = int(m.body_weldid[b1]), int(m.body_weldid[b2])
+            if w1 == w2:
+                continue
+            if w1 != 0 and w2 != 0:
+                wp1, wp2 = int(m.body_weldid[m.body_parentid[w1]]), int(m.body_weldid[m.body_parentid[w2]])
+                if wp1 == w2 or wp2 == w1:
+                    continue
+            if (b1, b2) in excl:
+                continue
+            if not ((m.geom_contype[g1] & m.geom_conaffinity[g2]) or (m.geom_contype[g2] & m.geom_conaffinity[g1])):
+                continue
+            if m.geom_type[g1] == 0 and m.geom_type[g2] == 0:
+                continue
+            out.append((g1, g2))
+    return out
+
+
+class DynModel:
+    def __init__(self, m):
+        self.model = m
+        nb = m.nbody
+        # tree root of every moving body = first ancestor-or-self whose parent is static
+        root = np.full(nb, -1, dtype=np.int64)
+        for b in range(1, nb):
+            if m.body_weldid[b] == 0:
+                continue
+            p = int(m.body_parentid[b])
+            root[b] = b if m.body_weldid[p] == 0 else root[p]
+        collidable = (m.geom_contype | m.geom_conaffinity) != 0
+        acted = set(int(m.jnt_bodyid[j]) for j in m.actuator_trnid)
+        live_roots = set()
+        for g in range(m.ngeom):
+            if collidable[g] and root[m.geom_bodyid[g]] >= 0:
+                live_roots.add(int(root[m.geom_bodyid[g]]))
+        for b in acted:
+            live_roots.add(int(root[b]))
+        self.bodies = [b for b in range(1, nb) if root[b] in live_roots]
+        idx = {b: i for i, b in enumerate(self.bodies)}
+        spos, squat = static_frames(m)
+        A = lambda *shape: np.zeros(shape)
+        n = len(self.bodies)
+        b_parent = np.full(n, -1, np.int32)
+        b_jtype = np.full(n, -1, np.int32)
+        b_qadr, b_vadr, b_dadr = np.full(n, -1, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+        b_rootpos, b_rootquat = A(n, 3), np.tile(np.array([1.0, 0, 0, 0]), (n, 1))
+        b_jaxis, b_jpos, b_qpos0 = A(n, 3), A(n, 3), A(n)
+        d_body, d_qadr, d_vadr, d_arm, d_damp, d_lim, d_range, d_solref, d_solimp, d_margin = [], [], [], [], [], [], [], [], [], []
+        for i, b in enumerate(self.bodies):
+            p = int(m.body_parentid[b])
+            if p in idx:
+                b_parent[i] = idx[p]
+            else:
+                b_rootpos[i], b_rootquat[i] = spos[p], squat[p]
+            if m.body_jntnum[b] > 1:
+                raise NotImplementedError("simulated body %s has more than one joint" % m.names["body"][b])
+            if m.body_jntnum[b] == 1:
+                j = int(m.body_jntadr[b])
+                t = int(m.jnt_type[j])
+                if t not in (JNT_FREE, JNT_SLIDE, JNT_HINGE):
+                    raise NotImplementedError("ball joints")
+                if t == JNT_FREE and (p in idx):
+                    raise NotImplementedError("free joint below a moving body")
+                b_jtype[i], b_qadr[i], b_vadr[i], b_dadr[i] = t, m.jnt_qposadr[j], m.jnt_dofadr[j], len(d_body)
+                b_jaxis[i], b_jpos[i], b_qpos0[i] = m.jnt_axis[j], m.jnt_pos[j], m.jnt_ref[j]
+                for k in range(6 if t == JNT_FREE else 1):
+                    d_body.append(i)
+                    d_qadr.append(int(m.jnt_qposadr[j]) + k if (t != JNT_FREE or k < 3) else -1)
+                    d_vadr.append(int(m.jnt_dofadr[j]) + k)
+                    d_arm.append(m.dof_armature[m.jnt_dofadr[j] + k])
+                    d_damp.append(m.dof_damping[m.jnt_dofadr[j] + k])
+                    d_lim.append(int(m.jnt_limited[j]) if t != JNT_FREE else 0)
+                    d_range.append(m.jnt_range[j])
+                    d_solref.append(m.jnt_solref[j])
+                    d_solimp.append(m.jnt_solimp[j])
+                    d_margin.append(m.jnt_margin[j])
+        self.nb, self.nd = n, len(d_body)
+        self.dof_vadr = np.array(d_vadr, np.int32)
+        self.dof_qadr = np.array(d_qadr, np.int32)
+        # actuators whose joint is simulated
+        a_dof, a_ids = [], []
+        for a in range(m.nu):
+            j = int(m.actuator_trnid[a])
+            va = int(m.jnt_dofadr[j])
+            a_dof.append(d_vadr.index(va))
+            a_ids.append(a)
+        # contact geoms / pairs
+        pairs = [(g1, g2) for g1, g2 in candidate_pairs(m)
+                 if (int(m.geom_bodyid[g1]) in idx or int(m.geom_bodyid[g2]) in idx)]
+        used = sorted(set(g for pr in pairs for g in pr))
+        gidx = {g: i for i, g in enumerate(used)}
+        g_body = np.array([idx.get(int(m.geom_bodyid[g]), -1) for g in used], np.int32)
+        g_pos, g_quat = A(len(used), 3), A(len(used), 4)
+        for i, g in enumerate(used):
+            b = int(m.geom_bodyid[g])
+            if g_body[i] >= 0:
+                g_pos[i], g_quat[i] = m.geom_pos[g], m.geom_quat[g]
+            else:
+                g_pos[i] = spos[b] + quat_to_mat(squat[b]) @ m.geom_pos[g]
+                g_quat[i] = quat_mul(squat[b], m.geom_quat[g])
+        self.pairs = pairs
+        self.geoms = used
+        arr = dict(
+            b_parent=b_parent, b_bodyid=np.array(self.bodies, np.int32), b_pos=m.body_pos[self.bodies], b_quat=m.body_quat[self.bodies],
+            b_rootpos=b_rootpos, b_rootquat=b_rootquat, b_jtype=b_jtype, b_qadr=b_qadr, b_vadr=b_vadr, b_dadr=b_dadr,
+            b_jaxis=b_jaxis, b_jpos=b_jpos, b_qpos0=b_qpos0, b_mass=m.body_mass[self.bodies], b_ipos=m.body_ipos[self.bodies],
+            b_iquat=m.body_iquat[self.bodies], b_inertia=m.body_inertia[self.bodies],
+            d_body=np.array(d_body, np.int32), d_qadr=self.dof_qadr, d_vadr=self.dof_vadr, d_armature=np.array(d_arm),
+            d_damping=np.array(d_damp), d_limited=np.array(d_lim, np.int32), d_range=np.array(d_range).reshape(-1, 2),
+            d_solref=np.array(d_solref).reshape(-1, 2), d_solimp=np.array(d_solimp).reshape(-1, 5), d_margin=np.array(d_margin),
+            a_dof=np.array(a_dof, np.int32), a_kind=m.actuator_kind[a_ids].astype(np.int32),
+            a_ctrllimited=m.actuator_ctrllimited[a_ids].astype(np.int32), a_forcelimited=m.actuator_forcelimited[a_ids].astype(np.int32),
+            a_kp=m.actuator_kp[a_ids], a_kv=m.actuator_kv[a_ids], a_gear=m.actuator_gear[a_ids],
+            a_ctrlrange=m.actuator_ctrlrange[a_ids].reshape(-1, 2), a_forcerange=m.actuator_forcerange[a_ids].reshape(-1, 2),
+            g_body=g_body, g_geomid=np.array(used, np.int32), g_type=m.geom_type[used].astype(np.int32), g_pos=g_pos, g_quat=g_quat,
+            g_size=m.geom_size[used], g_rbound=m.geom_rbound[used], g_margin=m.geom_margin[used], g_friction=m.geom_friction[used],
+            g_solref=m.geom_solref[used], g_solimp=m.geom_solimp[used], g_condim=m.geom_condim[used].astype(np.int32),
+            p_g1=np.array([gidx[a] for a, _ in pairs], np.int32), p_g2=np.array([gidx[b] for _, b in pairs], np.int32),
+        )
+        self.nact = len(a_ids)
+        self._arr = {}
+        d = DynDesc()
+        d.nq, d.nv, d.nb, d.nd, d.nact = m.nq, m.nv, self.nb, self.nd, self.nact
+        d.ngeom, d.npair, d.iterations = len(used), len(pairs), int(m.opt_iterations)
+        d.timestep = float(m.opt_timestep)
+        for k in range(3):
+            d.gravity[k] = float(m.opt_gravity[k])
+        for name, ctype in DynDesc._fields_:
+            if ctype is _I or ctype is _D:
+                a = np.ascontiguousarray(arr[name], dtype=np.int32 if ctype is _I else np.float64)
+                if a.size == 0:
+                    a = np.zeros(1, a.dtype)
+                self._arr[name] = a
+                setattr(d, name, a.ctypes.data_as(ctype))
+        self.desc = d

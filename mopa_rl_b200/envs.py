@@ -1,0 +1,199 @@
+"""Vectorised Sawyer environments on the GPU behind the reference's env semantics.
+
+``VecSawyerPushObstacle`` holds N independent copies of SawyerPushObstacle-v0
+(env/sawyer/sawyer_push_obstacle.py) as device arrays (torch tensors) and advances them with
+``mopa_env_step`` (one thread per env, 75 substeps on chip).  Reset follows
+``SawyerPushObstacleEnv._reset`` (:36-51): arm = init_qpos + N(0, 0.02^2), target slide joints +=
+U(-0.01, 0.01), with draws from the counter-based generator keyed by (seed, env id, episode #).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import rng
+from .capi import check, lib
+from .dynmodel import DynModel
+from .model import load_model
+
+PUSH_INIT_QPOS = np.array([0.000457, -0.114, 0.0321, -0.00712, 0.0303, -0.0302, -0.00994])
+OBS_KEYS = (("joint_pos", 7), ("joint_vel", 7), ("gripper_qpos", 2), ("gripper_qvel", 2), ("eef_pos", 3), ("eef_quat", 4),
+            ("target_pos", 3), ("cube_pos", 3), ("cube_quat", 4), ("gripper_to_cube", 3), ("cube_to_target", 2))
+OBS_DIM = 40
+BIAS_PAD = 16
+
+
+class SawyerTask(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("arm_qadr", C.c_int32 * 7), ("arm_vadr", C.c_int32 * 7), ("arm_dof", C.c_int32 * 7),
+                ("grip_qadr", C.c_int32 * 2), ("grip_vadr", C.c_int32 * 2), ("body_ee", C.c_int32), ("body_cube", C.c_int32),
+                ("body_rclaw", C.c_int32), ("body_lclaw", C.c_int32), ("target_qadr", C.c_int32 * 2),
+                ("max_episode_steps", C.c_int32), ("nsub", C.c_int32), ("site_right_eef", C.c_double * 3),
+                ("site_left_eef", C.c_double * 3), ("site_grip", C.c_double * 3), ("target_base", C.c_double * 3),
+                ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double)]
+
+
+class EnvBuffers(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("qpos", "qvel", "prev_state", "bias_prev", "has_prev", "ep_len", "ep_rew", "obs",
+                                           "reward", "done", "success", "ncon")]
+
+
+def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0):
+    t = SawyerTask()
+    t.kind = 0
+    joints = ["right_j%d" % i for i in range(7)]
+    sim_body = {b: i for i, b in enumerate(dyn.bodies)}
+    for k, j in enumerate(joints):
+        t.arm_qadr[k] = model.get_joint_qpos_addr(j)
+        t.arm_vadr[k] = model.get_joint_qvel_addr(j)
+        t.arm_dof[k] = list(dyn.dof_vadr).index(t.arm_vadr[k])
+    for k, j in enumerate(["rc_close", "lc_close"]):
+        t.grip_qadr[k] = model.get_joint_qpos_addr(j)
+        t.grip_vadr[k] = model.get_joint_qvel_addr(j)
+    t.body_ee = sim_body[model.body_name2id("right_ee_attchment")]
+    t.body_cube = sim_body[model.body_name2id("cube")]
+    t.body_rclaw = sim_body[model.body_name2id("rightclaw")]
+    t.body_lclaw = sim_body[model.body_name2id("leftclaw")]
+    for k, j in enumerate(["target_x", "target_y"]):
+        t.target_qadr[k] = model.get_joint_qpos_addr(j)
+    t.max_episode_steps = int(max_episode_steps)
+    t.nsub = int(frame_dt / model.opt_timestep)
+    for name, field in (("right_eef", t.site_right_eef), ("left_eef", t.site_left_eef), ("grip_site", t.site_grip)):
+        p = model.site_pos[model.site_name2id(name)]
+        for k in range(3):
+            field[k] = float(p[k])
+    tb = model.body_pos[model.body_name2id("target")]
+    for k in range(3):
+        t.target_base[k] = float(tb[k])
+    t.ac_scale, t.distance_threshold, t.success_reward = float(ac_scale), float(distance_threshold), float(success_reward)
+    return t
+
+
+def push_reset_state(model, seed, env_ids, episode_idx):
+    """Reset distribution of SawyerPushObstacleEnv._reset for the given (env id, episode #) pairs."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64).reshape(-1)
+    ep = np.broadcast_to(np.asarray(episode_idx, dtype=np.uint64), env_ids.shape)
+    n = len(env_ids)
+    qpos = np.tile(model.qpos0, (n, 1))
+    ref = [model.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+    tgt = [model.get_joint_qpos_addr(j) for j in ("target_x", "target_y")]
+    dims = np.arange(7, dtype=np.uint64)
+    qpos[:, ref] = PUSH_INIT_QPOS + 0.02 * rng.normal(seed, env_ids[:, None], ep[:, None], dims[None, :])
+    u = rng.uniform01(seed, env_ids[:, None], ep[:, None], np.array([100, 101], dtype=np.uint64)[None, :])
+    qpos[:, tgt] += -0.01 + 0.02 * u
+    return qpos, np.zeros((n, model.nv))
+
+
+class VecSawyerPushObstacle:
+    """N device-resident SawyerPushObstacle-v0 environments."""
+
+    def __init__(self, n_envs, seed=1234, device=0, env_id_offset=0, model=None, max_episode_steps=250, contacts=True, **task_kwargs):
+        import torch
+
+        self.torch = torch
+        self.n = int(n_envs)
+        self.seed = int(seed)
+        self.model = model if model is not None else load_model("SawyerPushObstacle-v0")
+        self.dyn = DynModel(self.model)
+        self.task = make_push_task(self.model, self.dyn, max_episode_steps=max_episode_steps, **task_kwargs)
+        self.dev = torch.device("cuda", device)
+        self.device_index = device
+        L = lib()
+        L.mopa_env_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.mopa_env_destroy.argtypes = [C.c_void_p]
+        L.mopa_env_destroy.restype = None
+        L.mopa_env_enable_contacts.argtypes = [C.c_void_p, C.c_int32]
+        L.mopa_env_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.mopa_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        self._L = L
+        h = C.c_void_p()
+        check(L.mopa_env_create(C.byref(self.dyn.desc), C.byref(self.task), int(device), C.byref(h)))
+        self.h = h
+        if not contacts:
+            check(L.mopa_env_enable_contacts(self.h, 0))
+        m, n = self.model, self.n
+        f64, dev = torch.float64, self.dev
+        self.qpos = torch.zeros(n, m.nq, dtype=f64, device=dev)
+        self.qvel = torch.zeros(n, m.nv, dtype=f64, device=dev)
+        self.prev_state = torch.zeros(n, 7, dtype=f64, device=dev)
+        self.bias_prev = torch.zeros(n, BIAS_PAD, dtype=f64, device=dev)
+        self.has_prev = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ep_rew = torch.zeros(n, dtype=f64, device=dev)
+        self.obs = torch.zeros(n, OBS_DIM, dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=f64, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.success = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.ncon = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.buf = EnvBuffers(*[getattr(self, k).data_ptr() for k, _ in EnvBuffers._fields_])
+        self.env_ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
+        self.episode_idx = np.zeros(n, dtype=np.int64)
+        self.ref_joint_pos_indexes = [int(self.task.arm_qadr[k]) for k in range(7)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mopa_env_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def forward(self, ids=None):
+        """sim.forward(): refresh bias / observation of the given envs (torch int32 tensor) or all."""
+        if ids is None:
+            check(self._L.mopa_env_forward(self.h, C.byref(self.buf), None, self.n, C.c_void_p(self._stream())))
+        elif len(ids):
+            ids = ids.to(device=self.dev, dtype=self.torch.int32).contiguous()
+            check(self._L.mopa_env_forward(self.h, C.byref(self.buf), C.c_void_p(ids.data_ptr()), int(len(ids)), C.c_void_p(self._stream())))
+            self.torch.cuda.current_stream(self.dev).synchronize()  # ids must outlive the launch
+
+    def reset(self, ids=None):
+        """env.reset() for the listed env rows (numpy int array) or all; returns the observation tensor."""
+        torch = self.torch
+        ids = np.arange(self.n) if ids is None else np.asarray(ids, dtype=np.int64).reshape(-1)
+        if len(ids) == 0:
+            return self.obs
+        qpos, qvel = push_reset_state(self.model, self.seed, self.env_ids[ids], self.episode_idx[ids])
+        self.episode_idx[ids] += 1
+        t_ids = torch.as_tensor(ids, device=self.dev)
+        self.qpos[t_ids] = torch.as_tensor(qpos, device=self.dev)
+        self.qvel[t_ids] = torch.as_tensor(qvel, device=self.dev)
+        self.has_prev[t_ids] = 0
+        self.ep_len[t_ids] = 0
+        self.ep_rew[t_ids] = 0
+        self.done[t_ids] = 0
+        self.success[t_ids] = 0
+        self.forward(t_ids)
+        return self.obs
+
+    def set_state(self, ids, qpos, qvel):
+        """BaseEnv.set_state(qpos, qvel) + sim.forward() (env/base.py:419-427) for the listed env rows."""
+        torch = self.torch
+        t_ids = torch.as_tensor(np.asarray(ids, dtype=np.int64).reshape(-1), device=self.dev)
+        self.qpos[t_ids] = torch.as_tensor(np.atleast_2d(qpos), dtype=torch.float64, device=self.dev)
+        self.qvel[t_ids] = torch.as_tensor(np.atleast_2d(qvel), dtype=torch.float64, device=self.dev)
+        self.forward(t_ids)
+
+    def step(self, action, is_planner=None, mask=None):
+        """env.step for all envs (or those with mask != 0).  action: float32 cuda tensor [n, >=7];
+        is_planner / mask: uint8 cuda tensors [n] or None.  Results land in self.obs/reward/done/success."""
+        a = action if action.dtype == self.torch.float32 else action.float()
+        a = a.contiguous()
+        check(self._L.mopa_env_step(self.h, C.byref(self.buf), C.c_void_p(a.data_ptr()), int(a.shape[1]),
+                                    C.c_void_p(is_planner.data_ptr()) if is_planner is not None else None,
+                                    C.c_void_p(mask.data_ptr()) if mask is not None else None, self.n, C.c_void_p(self._stream())))
+        self._keep = (a, is_planner, mask)
+        return self.obs, self.reward, self.done
+
+    def reset_prev_state(self, mask=None):
+        """env._reset_prev_state() (env/base.py:228-229)."""
+        if mask is None:
+            self.has_prev.zero_()
+        else:
+            self.has_prev[mask.bool()] = 0

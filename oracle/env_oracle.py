@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE — numpy restatement of the SawyerPushObstacle-v0 env logic around the
+physics oracle (orc_dyn.c).  Follows, line by line:
+  SawyerPushObstacleEnv._step           env/sawyer/sawyer_push_obstacle.py:162-208
+  SawyerPushObstacleEnv.compute_reward  :71-100
+  SawyerEnv._get_obs + push _get_obs    env/sawyer/sawyer.py:317-338, sawyer_push_obstacle.py:102-116
+  BaseEnv.step / _after_step            env/base.py:232-314
+One instance = one environment, exactly like the reference.  Body / site frames read after a step
+are those of the last mj_step's START state (mjData is not refreshed after integration).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .oracle import OracleDyn
+
+
+def _q2m(q):
+    w, x, y, z = q
+    return np.array([[w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z]])
+
+
+class PushEnvOracle:
+    def __init__(self, model, dynmodel, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06,
+                 success_reward=150.0, contacts=True):
+        self.m, self.dm = model, dynmodel
+        self.dyn = OracleDyn(dynmodel)
+        self.dyn.enable_contacts(contacts)
+        m = model
+        self.ref_q = [m.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+        self.ref_v = [m.get_joint_qvel_addr("right_j%d" % i) for i in range(7)]
+        self.grip_q = [m.get_joint_qpos_addr(j) for j in ("rc_close", "lc_close")]
+        self.grip_v = [m.get_joint_qvel_addr(j) for j in ("rc_close", "lc_close")]
+        self.tgt_q = [m.get_joint_qpos_addr(j) for j in ("target_x", "target_y")]
+        sim = {b: i for i, b in enumerate(dynmodel.bodies)}
+        self.b_ee, self.b_cube = sim[m.body_name2id("right_ee_attchment")], sim[m.body_name2id("cube")]
+        self.b_rc, self.b_lc = sim[m.body_name2id("rightclaw")], sim[m.body_name2id("leftclaw")]
+        self.s_re, self.s_le, self.s_grip = (m.site_pos[m.site_name2id(n)] for n in ("right_eef", "left_eef", "grip_site"))
+        self.target_base = m.body_pos[m.body_name2id("target")]
+        self.comp = np.zeros(dynmodel.nd, np.int32)
+        self.comp[[list(dynmodel.dof_vadr).index(v) for v in self.ref_v]] = 1
+        self.nsub = int(frame_dt / m.opt_timestep)
+        self.ac_scale, self.dthr, self.succ_rew, self.max_steps = ac_scale, distance_threshold, success_reward, max_episode_steps
+        self.lim = [(int(q), dynmodel._arr["d_range"][k]) for k, q in enumerate(dynmodel.dof_qadr) if q >= 0 and dynmodel._arr["d_limited"][k]]
+
+    def set_state(self, qpos, qvel):
+        self.qpos, self.qvel = np.array(qpos, np.float64), np.array(qvel, np.float64)
+        self.bias_prev, self.xpos, self.xquat = self.dyn.forward(self.qpos, self.qvel)
+
+    def reset_to(self, qpos, qvel):
+        self.set_state(qpos, qvel)
+        self.prev_state = None
+        self.ep_len, self.ep_rew, self.terminal, self.success = 0, 0.0, False, False
+        return self.obs()
+
+    def _site(self, b, local):
+        return self.xpos[b] + _q2m(self.xquat[b]) @ local
+
+    def obs(self):
+        q, v = self.qpos, self.qvel
+        eef = self._site(self.b_ee, self.s_grip)
+        target = self.target_base + np.array([q[self.tgt_q[0]], q[self.tgt_q[1]], 0.0])
+        cube, cq, eq = self.xpos[self.b_cube], self.xquat[self.b_cube], self.xquat[self.b_ee]
+        return np.concatenate([q[self.ref_q], v[self.ref_v], q[self.grip_q], v[self.grip_v], eef, eq[[1, 2, 3, 0]], target, cube,
+                               cq[[1, 2, 3, 0]], eef - cube, cube[:2] - target[:2]])
+
+    def step(self, action, is_planner=False):
+        action = np.asarray(action, np.float64)
+        if not is_planner or self.prev_state is None:
+            self.prev_state = self.qpos[self.ref_q].copy()
+        a = action[:7] if is_planner else action[:7] * self.ac_scale
+        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
+        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
+            self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
+        self.prev_state = desired.copy()
+        # compute_reward
+        gs = 0.5 * (self._site(self.b_rc, self.s_re) + self._site(self.b_lc, self.s_le))
+        cube = self.xpos[self.b_cube]
+        target = self.target_base + np.array([self.qpos[self.tgt_q[0]], self.qpos[self.tgt_q[1]], 0.0])
+        d_gc, d_ct = np.linalg.norm(cube - gs), np.linalg.norm(cube[:2] - target[:2])
+        reward = 0.0
+        if d_ct < 0.1:
+            reward += 0.5 * (1 - np.tanh(5 * d_ct))
+        if d_gc < 0.1:
+            reward += 0.1 * (1 - np.tanh(10 * d_gc))
+        terminal = False
+        if d_ct < self.dthr:
+            reward += self.succ_rew
+            self.success, terminal = True, True
+        ob = self.obs()
+        # _after_step
+        clipped = False
+        for qa, (lo, hi) in self.lim:
+            if self.qpos[qa] < lo or self.qpos[qa] > hi:
+                self.qpos[qa] = min(max(self.qpos[qa], lo), hi)
+                clipped = True
+        if clipped:
+            self.set_state(self.qpos, self.qvel)
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return ob, reward, terminal

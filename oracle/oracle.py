@@ -156,3 +156,58 @@ def space_from_model(model, passive_idx):
         else:
             so2.append(0), lo.append(model.jnt_range[j, 0]), hi.append(model.jnt_range[j, 1])
     return adr, lo, hi, so2
+
+
+class OracleDyn:
+    """Physics-step oracle (orc_dyn.c) for the simulated sub-trees of a scene."""
+
+    def __init__(self, dynmodel, precision="f64"):
+        self.dm = dynmodel
+        self.L = lib(precision)
+        L = self.L
+        L.orc_dyn_create.restype = C.c_void_p
+        L.orc_dyn_create.argtypes = [C.c_void_p]
+        L.orc_dyn_destroy.argtypes = [C.c_void_p]
+        L.orc_dyn_enable_contacts.argtypes = [C.c_void_p, C.c_int]
+        L.orc_dyn_step.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
+        L.orc_dyn_forward.argtypes = [C.c_void_p] * 6
+        L.orc_dyn_mass_bias.argtypes = [C.c_void_p] * 6
+        self.h = L.orc_dyn_create(C.byref(dynmodel.desc))
+        if not self.h:
+            raise RuntimeError("scene too large for the dynamics oracle")
+        self.nd, self.nb = dynmodel.nd, dynmodel.nb
+
+    def __del__(self):
+        try:
+            self.L.orc_dyn_destroy(self.h)
+        except Exception:
+            pass
+
+    def enable_contacts(self, on):
+        self.L.orc_dyn_enable_contacts(self.h, int(on))
+
+    def forward(self, qpos, qvel):
+        q = np.ascontiguousarray(qpos, np.float64)
+        v = np.ascontiguousarray(qvel, np.float64)
+        bias, xpos, xquat = np.zeros(self.nd), np.zeros((self.nb, 3)), np.zeros((self.nb, 4))
+        self.L.orc_dyn_forward(self.h, _p(q), _p(v), _p(bias), _p(xpos), _p(xquat))
+        return bias, xpos, xquat
+
+    def step(self, qpos, qvel, ctrl, comp, bias_prev, nsub=1):
+        """In-place on copies; returns (qpos, qvel, bias_prev, xpos, xquat, ncon)."""
+        q = np.array(qpos, np.float64)
+        v = np.array(qvel, np.float64)
+        c = np.ascontiguousarray(ctrl, np.float64)
+        cm = np.ascontiguousarray(comp, np.int32)
+        b = np.array(bias_prev, np.float64)
+        xpos, xquat = np.zeros((self.nb, 3)), np.zeros((self.nb, 4))
+        ncon = C.c_int32()
+        self.L.orc_dyn_step(self.h, _p(q), _p(v), _p(c), _p(cm), _p(b), int(nsub), _p(xpos), _p(xquat), C.byref(ncon))
+        return q, v, b, xpos, xquat, ncon.value
+
+    def mass_bias(self, qpos, qvel):
+        q = np.ascontiguousarray(qpos, np.float64)
+        v = np.ascontiguousarray(qvel, np.float64)
+        M, bias, com = np.zeros((self.nd, self.nd)), np.zeros(self.nd), np.zeros((self.nb, 3))
+        self.L.orc_dyn_mass_bias(self.h, _p(q), _p(v), _p(M), _p(bias), _p(com))
+        return M, bias, com

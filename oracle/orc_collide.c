@@ -391,8 +391,15 @@ static inline int normalize3(R *v) {
     return 1;
 }
 #define MPR_EPS RC(1.1920929e-07)
-#define MPR_TOL RC(1e-6)
-#define MPR_MAXIT 50
+/* tolerance / iteration cap; adjustable for convergence studies (orc_set_mpr) */
+static R MPR_TOL = RC(1e-6);
+static int MPR_MAXIT = 50;
+static long g_mpr_calls = 0, g_mpr_iters = 0, g_mpr_hits = 0;
+void orc_set_mpr(int maxit, double tol) { MPR_MAXIT = maxit; MPR_TOL = (R)tol; }
+void orc_mpr_stats(long *out, int reset) {
+    out[0] = g_mpr_calls; out[1] = g_mpr_iters; out[2] = g_mpr_hits;
+    if (reset) g_mpr_calls = g_mpr_iters = g_mpr_hits = 0;
+}
 static inline int is_zero(R x) { return FABS_(x) < MPR_EPS; }
 
 /* squared distance from the origin to triangle (a,b,c) (region classification) */
@@ -440,6 +447,7 @@ static R origin_tri_dist2(const R *a, const R *b, const R *c) {
 static int mpr_penetration(const cvx *g1, const cvx *g2, R *depth) {
     R v0[3], v1[3], v2[3], v3[3], v4[3], dir[3], va[3], vb[3];
     R dot;
+    g_mpr_calls++;
     /* phase 1: portal discovery */
     sub3(v0, g1->pos, g2->pos);
     if (v0[0] == 0 && v0[1] == 0 && v0[2] == 0) v0[0] = MPR_EPS * RC(10.0);
@@ -505,6 +513,7 @@ static int mpr_penetration(const cvx *g1, const cvx *g2, R *depth) {
             if (!(is_zero(dv4) || dv4 > 0) || reached || it >= MPR_MAXIT) return 0;
         } else if (reached || it >= MPR_MAXIT) {
             *depth = RSQRT_(origin_tri_dist2(v1, v2, v3));
+            g_mpr_iters += it; g_mpr_hits++;
             return 1;
         }
         /* expand the portal with v4 */

@@ -1,0 +1,57 @@
+"""GPU <-> oracle parity of the vectorised env.step (physics + env logic), through the C ABI.
+Tolerance stated by BASELINE.json north_star: qpos / qvel within 1e-5 absolute."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _run(push_model, contacts, n=48, steps=4, planner_steps=True):
+    import torch
+
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerPushObstacle, push_reset_state
+    from oracle.env_oracle import PushEnvOracle
+
+    venv = VecSawyerPushObstacle(n, seed=77, contacts=contacts, max_episode_steps=3)
+    venv.reset()
+    dm = DynModel(push_model)
+    q0, v0 = push_reset_state(push_model, 77, np.arange(n), np.zeros(n, dtype=np.int64))
+    assert np.allclose(venv.qpos.cpu().numpy(), q0, atol=0, rtol=0)
+    envs = [PushEnvOracle(push_model, dm, contacts=contacts, max_episode_steps=3) for _ in range(n)]
+    obs0 = np.stack([e.reset_to(q0[i], v0[i]) for i, e in enumerate(envs)])
+    assert np.abs(venv.obs.cpu().numpy() - obs0).max() < 1e-5
+    rng = np.random.default_rng(5)
+    worst = dict(qpos=0.0, qvel=0.0, obs=0.0, rew=0.0)
+    for s in range(steps):
+        act = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        isp = np.zeros(n, np.uint8)
+        if planner_steps and s >= 1:
+            isp[::2] = 1
+            act[::2] *= 0.08  # planner-mode actions are joint displacements, clipped to +-ac_scale
+        venv.step(torch.as_tensor(act, device="cuda"), torch.as_tensor(isp, device="cuda"))
+        torch.cuda.synchronize()
+        gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
+        gobs, grew, gdone = venv.obs.cpu().numpy(), venv.reward.cpu().numpy(), venv.done.cpu().numpy()
+        for i, e in enumerate(envs):
+            ob, r, d = e.step(act[i].astype(np.float64), bool(isp[i]))
+            worst["qpos"] = max(worst["qpos"], np.abs(gq[i] - e.qpos).max())
+            worst["qvel"] = max(worst["qvel"], np.abs(gv[i] - e.qvel).max())
+            worst["obs"] = max(worst["obs"], np.abs(gobs[i] - ob).max())
+            worst["rew"] = max(worst["rew"], abs(grew[i] - r))
+            assert bool(gdone[i]) == d
+            assert venv.ep_len[i].item() == e.ep_len
+    assert worst["qpos"] < TOL and worst["qvel"] < TOL, worst
+    assert worst["obs"] < 1e-4 and worst["rew"] < 1e-6, worst   # obs is fp32 on the device side
+    return worst
+
+
+def test_env_step_matches_oracle_no_contacts(push_model, oracle_built):
+    w = _run(push_model, contacts=False)
+    print("max abs error (no contacts):", w)
+
+
+def test_env_step_matches_oracle_with_contacts(push_model, oracle_built):
+    w = _run(push_model, contacts=True, steps=4)
+    print("max abs error (contacts):", w)
