@@ -121,7 +121,7 @@ DYN_HD inline void d_kbi(const DynDev &m, const double *solref, const double *so
     imp = im;
 }
 
-DYN_HD int contact_rows(const DynDev &m, const DynData &D, const Sv6 *S, CRow *rows, int maxrows);
+struct DynDev; DYN_HD inline int contact_rows(const DynDev &m, const DynData &D, const Sv6 *S, CRow *rows, int maxrows);
 
 // in-place Cholesky solve with the lower factor L (row-major DMAXD x DMAXD)
 DYN_HD inline void chol_solve(const double *L, int nd, double *x) {
