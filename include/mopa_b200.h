@@ -145,7 +145,9 @@ int mopa_env_enable_contacts(mopa_env *e, int32_t on);
  * from qpos/qvel.  Called after reset / set_state. */
 int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_ids, int32_t n, void *stream);
 /* env.step(action, is_planner) for every env whose mask byte is non-zero (d_mask nullable = all).
- * d_action [n][action_stride] fp32 (first 7 used), d_is_planner [n] (nullable = all false). */
+ * d_action [n][action_stride] fp32 (first 7 used); d_is_planner [n] (nullable = all 0):
+ *   0  direct action (scaled by ac_scale), 1  planner waypoint (is_planner=True: joint displacement),
+ *   2  planner failure: compute_reward + _after_step without simulation (rl/mopa_rollouts.py:304-327). */
 int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
                   const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream);
 

@@ -316,32 +316,29 @@ DYN_HD inline int pair_contacts(CPoint *out, const CGeom &ga, const CGeom &gb, d
 
 DYN_HD inline int contact_rows(const DynDev &m, const DynData &D, const Sv6 *S, CRow *rows, int maxrows) {
     int nrow = 0;
+    // world centres of all contact geoms once per step; rotations only for pairs that survive the cull
+    double gpos[DMAXG][3];
+    for (int g = 0; g < m.ngeom; g++) {
+        const int body = m.g_body[g];
+        if (body < 0) { for (int k = 0; k < 3; k++) gpos[g][k] = m.g_pos[g][k]; continue; }
+        const double *X = D.xmat[body];
+        for (int k = 0; k < 3; k++)
+            gpos[g][k] = D.xpos[body][k] + X[3 * k] * m.g_pos[g][0] + X[3 * k + 1] * m.g_pos[g][1] + X[3 * k + 2] * m.g_pos[g][2];
+    }
     for (int p = 0; p < m.npair; p++) {
         const int a = m.p_g1[p], b = m.p_g2[p];
+        const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
+        if (m.g_type[a] != 0 && m.g_type[b] != 0) {
+            double d[3] = {gpos[b][0] - gpos[a][0], gpos[b][1] - gpos[a][1], gpos[b][2] - gpos[a][2]}, bound = m.g_rbound[a] + m.g_rbound[b] + margin;
+            if (d_dot(d, d) > bound * bound) continue;
+        }
         double gc[2][3], gR[2][9];
         for (int side = 0; side < 2; side++) {
             const int g = side ? b : a, body = m.g_body[g];
+            for (int k = 0; k < 3; k++) gc[side][k] = gpos[g][k];
             double Rl[9];
             d_q2m(Rl, m.g_quat[g]);
-            if (body < 0) {
-                for (int k = 0; k < 3; k++) gc[side][k] = m.g_pos[g][k];
-                for (int k = 0; k < 9; k++) gR[side][k] = Rl[k];
-                continue;
-            }
-            const double *X = D.xmat[body];
-            for (int k = 0; k < 3; k++)
-                gc[side][k] = D.xpos[body][k] + X[3 * k] * m.g_pos[g][0] + X[3 * k + 1] * m.g_pos[g][1] + X[3 * k + 2] * m.g_pos[g][2];
-        }
-        const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
-        if (m.g_type[a] != 0 && m.g_type[b] != 0) {
-            double d[3] = {gc[1][0] - gc[0][0], gc[1][1] - gc[0][1], gc[1][2] - gc[0][2]}, bound = m.g_rbound[a] + m.g_rbound[b] + margin;
-            if (d_dot(d, d) > bound * bound) continue;
-        }
-        for (int side = 0; side < 2; side++) {
-            const int g = side ? b : a, body = m.g_body[g];
-            if (body < 0) continue;
-            double Rl[9];
-            d_q2m(Rl, m.g_quat[g]);
+            if (body < 0) { for (int k = 0; k < 9; k++) gR[side][k] = Rl[k]; continue; }
             const double *X = D.xmat[body];
             for (int r = 0; r < 3; r++)
                 for (int c = 0; c < 3; c++) gR[side][3 * r + c] = X[3 * r] * Rl[c] + X[3 * r + 1] * Rl[3 + c] + X[3 * r + 2] * Rl[6 + c];

@@ -23,7 +23,7 @@ constexpr int DMAXB = 20;  // simulated bodies
 constexpr int DMAXD = 16;  // simulated dofs
 constexpr int DMAXA = 12;  // actuators
 constexpr int DMAXG = 48;  // contact geoms
-constexpr int DMAXC = 48;  // constraint rows
+constexpr int DMAXC = 36;  // constraint rows
 #define DYN_MINVAL 1e-15
 
 struct DynDev {

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
     for (int k = 0; k < m.nq; k++) q[k] = B.qpos[(size_t)e * m.nq + k];
     for (int k = 0; k < m.nv; k++) v[k] = B.qvel[(size_t)e * m.nv + k];
     for (int k = 0; k < DMAXD; k++) bias_prev[k] = B.bias_prev[(size_t)e * DMAXD + k];
-    const bool planner = is_planner && is_planner[e];
+    const int mode = is_planner ? is_planner[e] : 0;  // 0 direct, 1 planner waypoint, 2 planner failure (no simulation)
+    const bool planner = mode == 1;
     const bool had_prev = B.has_prev[e] != 0;
     for (int k = 0; k < 7; k++) prev[k] = (!planner || !had_prev) ? q[T.arm_qadr[k]] : B.prev_state[(size_t)e * 7 + k];
     for (int k = 0; k < DMAXA; k++) ctrl[k] = 0;
@@ -96,10 +97,16 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
     DynData D;
-    for (int s = 0; s < T.nsub; s++) {
-        for (int k = 0; k < DMAXD; k++) applied[k] = (comp >> k) & 1u ? bias_prev[k] : 0.0;
-        dyn_substep(m, q, v, ctrl, applied, D, true);
-        for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
+    if (mode == 2) {
+        // planner failure (rl/mopa_rollouts.py:304-327): reward at the current state, no physics
+        for (int k = 0; k < DMAXD; k++) applied[k] = 0.0;
+        dyn_substep(m, q, v, ctrl, applied, D, false);
+    } else {
+        for (int s = 0; s < T.nsub; s++) {
+            for (int k = 0; k < DMAXD; k++) applied[k] = (comp >> k) & 1u ? bias_prev[k] : 0.0;
+            dyn_substep(m, q, v, ctrl, applied, D, true);
+            for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
+        }
     }
     // reward (frames are those of the last substep's start state, as mjData holds them after mj_step)
     double re[3], le[3];
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
     if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
     bool success = false, terminal = false;
     if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
-    write_obs(T, D, q, v, B.obs + (size_t)e * 40);
+    if (mode != 2) write_obs(T, D, q, v, B.obs + (size_t)e * 40);
     // _after_step: project limited joints back into range (set_state + forward), episode accounting
     bool clipped = false;
     for (int k = 0; k < m.nd; k++) {
@@ -133,9 +140,11 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
     if (len == T.max_episode_steps) terminal = true;
     for (int k = 0; k < m.nq; k++) B.qpos[(size_t)e * m.nq + k] = q[k];
     for (int k = 0; k < m.nv; k++) B.qvel[(size_t)e * m.nv + k] = v[k];
-    for (int k = 0; k < 7; k++) B.prev_state[(size_t)e * 7 + k] = ctrl[k];
+    if (mode != 2) {
+        for (int k = 0; k < 7; k++) B.prev_state[(size_t)e * 7 + k] = ctrl[k];
+        B.has_prev[e] = 1;
+    }
     for (int k = 0; k < DMAXD; k++) B.bias_prev[(size_t)e * DMAXD + k] = bias_prev[k];
-    B.has_prev[e] = 1;
     B.ep_len[e] = len;
     B.ep_rew[e] += reward;
     B.reward[e] = reward;

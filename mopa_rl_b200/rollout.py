@@ -1,0 +1,392 @@
+"""Vectorised MoPA experience collection — the batched replacement of ``MoPARolloutRunner.run``
+(rl/mopa_rollouts.py:22-399) together with the planner glue it calls in ``SACAgent``
+(rl/sac_agent.py:145-318: is_planner_ac, convert2planner_displacement, clip_qpos,
+simple_interpolate, plan).
+
+The reference drives ONE env through a Python generator.  Here N envs live on the GPU and every
+``tick()`` advances each of them by exactly one ``env.step``: an env either executes the next
+waypoint of its current plan (``is_planner=True``), or — when it has no plan left — receives a
+fresh policy action, which is executed directly (|a| <= omega) or turned into a plan by the same
+sequence the reference uses: displacement map -> target clip -> invalid-target back-off ->
+straight-line interpolation -> RRT-Connect -> densification.  All validity checks of a tick are
+batched into a few ``mopa_is_valid_batch`` launches and all RRT problems into one
+``mopa_plan_batch`` launch.  A finished macro action emits one SMDP transition record
+(ob 40, ac 8, rew, done, intra_steps, pad, ob_next 40 = 92 floats), exactly the content of the
+reference's ``Rollout`` entries (rl/rollouts.py:15-36).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import NativePlanner
+
+TRANSITION_FLOATS = 92
+
+
+class MoPAConfig:
+    """Hyper-parameters of scripts/3d/push/mopa.sh + config/sawyer.py + config/motion_planner.py."""
+    omega = 0.7
+    action_range = 0.5
+    ac_scale = 0.05            # SawyerEnv._ac_scale
+    discount_factor = 0.99
+    invalid_target_handling = True
+    num_trials = 100
+    step_size = 0.02
+    joint_margin = 0.001
+    interpolation = True
+    contact_threshold = -0.002
+    range = 0.1
+    simple_planner_range = 0.05
+    max_iter = 1000            # iteration cap standing in for --timelimit (2.0 s in the push preset)
+    max_path = 384
+    max_traj = 1280
+    seed = 1234
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(type(self), k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+def planner_inputs(model, static_bodies=("table", "bin1"), manipulation_geoms=("cube",)):
+    """ignored contact pairs / passive joints as rl/trainer.py:62-75 derives them."""
+    static_ids = [g for g in range(model.ngeom) if model.names["body"][model.geom_bodyid[g]] in static_bodies]
+    ignored = []
+    for name in manipulation_geoms:
+        mg = model.geom_name2id(name)
+        ignored += [(min(mg, g), max(mg, g)) for g in static_ids]
+    ref = [model.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+    passive = [i for i in range(model.nq) if i not in ref]
+    return ignored, passive, ref
+
+
+class UniformPolicy:
+    """random_exploration=True: ac_space.sample(), uniform in [-1, 1]^7 (rl/base_agent.py:15-22)."""
+
+    def __init__(self, torch, device, seed):
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(int(seed))
+        self.torch, self.device = torch, device
+
+    def __call__(self, obs, env_ids=None, macro_index=None):
+        return self.torch.rand(obs.shape[0], 7, generator=self.gen, device=self.device) * 2 - 1
+
+
+class CounterPolicy:
+    """Uniform [-1,1]^7 actions that are a pure function of (seed, env id, macro-action index):
+    the stand-in for random_exploration whose draws do not depend on batch composition."""
+
+    def __init__(self, torch, device, seed):
+        self.torch, self.device, self.seed = torch, device, int(seed)
+
+    def __call__(self, obs, env_ids, macro_index):
+        from . import rng
+
+        e = env_ids.cpu().numpy().astype(np.uint64)[:, None]
+        c = macro_index.cpu().numpy().astype(np.uint64)[:, None]
+        u = rng.uniform01(self.seed, e, c, np.arange(7, dtype=np.uint64)[None, :])
+        return self.torch.as_tensor((2.0 * u - 1.0).astype(np.float32), device=self.device)
+
+
+class VecMoPARolloutRunner:
+    def __init__(self, venv, config=None, policy=None, transition_capacity=1 << 20):
+        import torch
+
+        self.torch = torch
+        self.venv, self.cfg = venv, config or MoPAConfig()
+        cfg, m, dev = self.cfg, venv.model, venv.dev
+        self.dev = dev
+        ignored, passive, ref = planner_inputs(m)
+        assert ref == list(range(7)), "arm joints are expected to be the first qpos entries (sac_agent.py uses [:7])"
+        self.planner = NativePlanner(m, passive, ignored, cfg.contact_threshold, cfg.range, 0.005, cfg.seed, venv.device_index)
+        self.policy = policy or UniformPolicy(torch, dev, cfg.seed + 17 * int(venv.env_ids[0]))
+        n = venv.n
+        self.nq = m.nq
+        self.row = ((m.nq + 3) // 4) * 4
+        jid = [list(m.jnt_qposadr).index(a) for a in ref]
+        self.jlo = torch.as_tensor(m.jnt_range[jid, 0], device=dev)
+        self.jhi = torch.as_tensor(m.jnt_range[jid, 1], device=dev)
+        f64 = torch.float64
+        self.traj = torch.zeros(n, cfg.max_traj, 7, dtype=f64, device=dev)
+        self.traj_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.traj_pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.kind = torch.zeros(n, dtype=torch.uint8, device=dev)      # 0 direct, 1 plan, 2 planner failure
+        self.pending = torch.zeros(n, dtype=torch.bool, device=dev)    # a macro action is in flight
+        self.prev_ob = torch.zeros(n, 40, dtype=torch.float32, device=dev)
+        self.ac = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+        self.meta_rew = torch.zeros(n, dtype=f64, device=dev)
+        self.executed = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.macro_done = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.step_action = torch.zeros(n, 8, dtype=torch.float32, device=dev)
+        self.step_mode = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.plan_calls = 0
+        self.plan_count = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.macro_index = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.env_gid = torch.as_tensor(venv.env_ids, dtype=torch.int64, device=dev)
+        self.transitions = torch.zeros(transition_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
+        self.n_transitions = 0
+        self.env_steps = 0
+        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, densify_fallback=0, episodes=0,
+                             success=0, mp_path_len=0, interpolation_path_len=0)
+        self.launches = 0
+        venv.reset()
+
+    # ---------------------------------------------------------------- batched planner glue
+    def _valid(self, states64):
+        """states64 [M, nq] float64 -> bool [M] (MujocoStateValidityChecker::isValid, batched)."""
+        torch = self.torch
+        M = states64.shape[0]
+        if M == 0:
+            return torch.zeros(0, dtype=torch.bool, device=self.dev)
+        q = torch.zeros(M, self.row, dtype=torch.float32, device=self.dev)
+        q[:, :self.nq] = states64.float()
+        out = torch.zeros(M, dtype=torch.int32, device=self.dev)
+        self.planner.is_valid_device(q.data_ptr(), self.row, M, out.data_ptr(), 0, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.launches += 1
+        self._keep_v = (q, out)
+        return (out & 1).bool()
+
+    def _clip_qpos(self, q):
+        """SACAgent.clip_qpos (rl/sac_agent.py:237-259): only when some limited joint is out of range."""
+        torch = self.torch
+        arm = q[:, :7]
+        out = ((arm < self.jlo) | (arm > self.jhi)).any(dim=1)
+        clipped = torch.minimum(torch.maximum(arm, self.jlo + self.cfg.joint_margin), self.jhi - self.cfg.joint_margin)
+        q = q.clone()
+        q[:, :7] = torch.where(out[:, None], clipped, arm)
+        return q
+
+    def _interp_points(self, start, target, jmax):
+        """simple_interpolate (rl/sac_agent.py:262-298): per-joint steps of at most 0.8*ac_scale.
+        Returns nstep [M] and the interpolated states [M, jmax, nq] (rows j >= nstep are padding)."""
+        torch = self.torch
+        lim = self.cfg.ac_scale * 0.8
+        diff = target[:, :7] - start[:, :7]
+        sf = torch.clamp((diff.abs() / lim).max(dim=1).values, min=1.0)
+        # scales only count joints whose |diff| exceeds the limit; below it the factor is 1 anyway
+        nstep = torch.clamp(sf.floor().to(torch.int64), max=jmax)
+        scaled = diff / sf[:, None]
+        pts = start[:, None, :].repeat(1, jmax, 1)
+        run = start[:, :7].clone()
+        for j in range(jmax):  # the reference accumulates interp_qpos += scaled_ac: same running sum
+            run = run + scaled
+            pts[:, j, :7] = run
+        return nstep, pts
+
+    def _plan(self, idx, ac):
+        """Plan for envs `idx` (int64 tensor) with actions ac [K,7].  Fills traj / traj_len / kind."""
+        torch, cfg, venv = self.torch, self.cfg, self.venv
+        K = idx.numel()
+        curr = venv.qpos[idx]
+        a = ac.double()
+        w = cfg.omega
+        disp = torch.where(a.abs() < w, a / (w / cfg.ac_scale),
+                           torch.sign(a) * (cfg.ac_scale + (cfg.action_range - cfg.ac_scale) * ((a.abs() - w) / (1 - w))))
+        target = curr.clone()
+        target[:, :7] = torch.minimum(torch.maximum(curr[:, :7] + disp, self.jlo), self.jhi)
+        ok = self._valid(target)
+        if cfg.invalid_target_handling and not bool(ok.all()):
+            bad = torch.nonzero(~ok).squeeze(1)
+            t = target[bad].clone()
+            c = curr[bad]
+            cands = torch.empty(bad.numel(), cfg.num_trials, self.nq, dtype=torch.float64, device=self.dev)
+            for k in range(cfg.num_trials):
+                d = c - t
+                t = t + cfg.step_size * d / torch.linalg.norm(d, dim=1, keepdim=True)
+                cands[:, k] = t
+            v = self._valid(cands.reshape(-1, self.nq)).reshape(bad.numel(), cfg.num_trials)
+            anyv = v.any(dim=1)
+            first = torch.argmax(v.to(torch.int8), dim=1)
+            chosen = cands[torch.arange(bad.numel(), device=self.dev), first]
+            target[bad] = torch.where(anyv[:, None], chosen, cands[:, -1])
+            ok[bad] = anyv
+        kind = torch.full((K,), 2, dtype=torch.uint8, device=self.dev)   # failure unless proven otherwise
+        tlen = torch.ones(K, dtype=torch.int32, device=self.dev)
+        n_invalid = int((~ok).sum())
+        self.counters["invalid"] += n_invalid
+        good = torch.nonzero(ok).squeeze(1)
+        if good.numel():
+            c = self._clip_qpos(curr[good])
+            tg = target[good]
+            jmax = 16
+            nstep, pts = self._interp_points(c, tg, jmax)
+            jj = torch.arange(jmax, device=self.dev)
+            live = jj[None, :] < nstep[:, None]
+            v = self._valid(pts.reshape(-1, self.nq)).reshape(-1, jmax)
+            straight = (v | ~live).all(dim=1)
+            # interpolation success: the interpolated states followed by the target
+            s_idx = torch.nonzero(straight).squeeze(1)
+            if s_idx.numel():
+                rows = idx[good[s_idx]]
+                tr = torch.zeros(s_idx.numel(), jmax + 1, 7, dtype=torch.float64, device=self.dev)
+                tr[:, :jmax] = pts[s_idx][:, :, :7]
+                tr[torch.arange(s_idx.numel(), device=self.dev), nstep[s_idx]] = tg[s_idx][:, :7]
+                self.traj[rows, :jmax + 1] = tr
+                kind[good[s_idx]] = 1
+                tlen[good[s_idx]] = (nstep[s_idx] + 1).to(torch.int32)
+                self.counters["interpolation"] += int(s_idx.numel())
+                self.counters["interpolation_path_len"] += int((nstep[s_idx] + 1).sum())
+            r_idx = torch.nonzero(~straight).squeeze(1)
+            if r_idx.numel():
+                self._rrt(idx, good[r_idx], c[r_idx], tg[r_idx], kind, tlen)
+        self.counters["mp_fail"] += int((kind == 2).sum())
+        self.kind[idx] = kind
+        self.traj_len[idx] = tlen
+        self.traj_pos[idx] = 0
+
+    def _rrt(self, idx, sub, start, goal, kind, tlen):
+        """RRT-Connect for the envs idx[sub]; on success re-base, densify and store the path."""
+        torch, cfg = self.torch, self.cfg
+        R = sub.numel()
+        row, mp = self.row, cfg.max_path
+        s32 = torch.zeros(R, row, dtype=torch.float32, device=self.dev)
+        g32 = torch.zeros(R, row, dtype=torch.float32, device=self.dev)
+        s32[:, :self.nq] = start.float()
+        g32[:, :self.nq] = goal.float()
+        rows_r = idx[sub]
+        keys = (self.env_gid[rows_r] << 32) + self.plan_count[rows_r]   # invariant to batching / GPU count
+        self.plan_count[rows_r] += 1
+        self.plan_calls += R
+        path = torch.zeros(R, mp, row, dtype=torch.float32, device=self.dev)
+        ids = torch.zeros(R, mp, dtype=torch.int32, device=self.dev)
+        plen = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        status = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        self.planner.plan_device(s32.data_ptr(), g32.data_ptr(), row, keys.data_ptr(), R, cfg.max_iter, path.data_ptr(), ids.data_ptr(),
+                                 mp, plen.data_ptr(), status.data_ptr(), 0, 0, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.launches += 1
+        okp = status == 0
+        self.counters["approximate"] += int((~okp).sum())
+        w = torch.nonzero(okp).squeeze(1)
+        if not w.numel():
+            return
+        self.counters["mp"] += int(w.numel())
+        P = path[w][:, :, :7].double()
+        L = plen[w].to(torch.int64)                                  # rows incl. the start row
+        st = start[w][:, :7]
+        # SamplingBasedPlanner.plan re-bases the path on `start`; PlannerAgent.plan drops the first row
+        P = st[:, None, :] + (P - P[:, :1])
+        hops_end = P[:, 1:]                                          # traj[i]
+        hops_start = torch.cat([st[:, None, :], P[:, 1:-1]], dim=1)  # start of hop i
+        H = mp - 1
+        hop_live = torch.arange(H, device=self.dev)[None, :] < (L - 1)[:, None]
+        diff = hops_end - hops_start
+        if cfg.interpolation:
+            lim = cfg.ac_scale * 0.8
+            need = (diff.abs() > cfg.ac_scale).any(dim=2) & hop_live
+            sf = torch.clamp((diff.abs() / lim).max(dim=2).values, min=1.0)
+            kmax = int(cfg.range / lim) + 1
+            nst = torch.where(need, torch.clamp(sf.floor().to(torch.int64), max=kmax), torch.zeros_like(L)[:, None].expand(-1, H))
+            scaled = diff / sf[..., None]
+            inter = torch.empty(w.numel(), H, kmax, 7, dtype=torch.float64, device=self.dev)
+            run = hops_start.clone()
+            for j in range(kmax):
+                run = run + scaled
+                inter[:, :, j] = run
+            live = (torch.arange(kmax, device=self.dev)[None, None, :] < nst[..., None])
+            if bool(live.any()):
+                full = start[w][:, None, None, :].expand(-1, H, kmax, -1).clone()
+                full[..., :7] = inter
+                sel = torch.nonzero(live.reshape(-1)).squeeze(1)
+                vv = torch.ones(live.numel(), dtype=torch.bool, device=self.dev)
+                vv[sel] = self._valid(full.reshape(-1, self.nq)[sel])
+                hop_bad = (~vv.reshape(live.shape) & live).any(dim=2)
+                if bool(hop_bad.any()):
+                    # the reference would call the simple planner / main planner here (sac_agent.py:300-311);
+                    # such hops keep only their end point and are counted
+                    self.counters["densify_fallback"] += int(hop_bad.sum())
+                    nst = torch.where(hop_bad, torch.zeros_like(nst), nst)
+                    live = live & ~hop_bad[..., None]
+        else:
+            kmax = 1
+            nst = torch.zeros(w.numel(), H, dtype=torch.int64, device=self.dev)
+            inter = hops_end[:, :, None, :]
+            live = torch.zeros(w.numel(), H, 1, dtype=torch.bool, device=self.dev)
+        cnt = (nst + 1) * hop_live
+        off = torch.cumsum(cnt, dim=1) - cnt
+        total = cnt.sum(dim=1)
+        over = total > cfg.max_traj
+        rows = idx[sub[w]]
+        out = torch.zeros(w.numel(), cfg.max_traj, 7, dtype=torch.float64, device=self.dev)
+        ar = torch.arange(w.numel(), device=self.dev)[:, None].expand(-1, H)
+        for j in range(kmax):
+            msk = live[:, :, j] & hop_live & ~over[:, None]
+            if bool(msk.any()):
+                out[ar[msk], (off + j)[msk]] = inter[:, :, j][msk]
+        msk = hop_live & ~over[:, None]
+        out[ar[msk], (off + nst)[msk]] = hops_end[msk]
+        self.traj[rows] = out
+        k_ok = torch.where(over, torch.full_like(total, 2), torch.ones_like(total)).to(torch.uint8)
+        kind[sub[w]] = k_ok
+        tlen[sub[w]] = torch.where(over, torch.ones_like(total), total).to(torch.int32)
+        self.counters["mp_path_len"] += int(total[~over].sum())
+
+    # ---------------------------------------------------------------- one env.step for every env
+    def tick(self):
+        torch, cfg, venv = self.torch, self.cfg, self.venv
+        need = torch.nonzero(self.traj_pos >= self.traj_len).squeeze(1)
+        if need.numel():
+            # finished macro actions -> transition records; finished episodes -> reset
+            fin = need[self.pending[need]]
+            if fin.numel():
+                rec = torch.zeros(fin.numel(), TRANSITION_FLOATS, dtype=torch.float32, device=self.dev)
+                rec[:, 0:40] = self.prev_ob[fin]
+                rec[:, 40:48] = self.ac[fin]
+                rec[:, 48] = self.meta_rew[fin].float()
+                rec[:, 49] = self.macro_done[fin].float()
+                rec[:, 50] = (self.executed[fin] - 1).clamp(min=0).float()
+                rec[:, 52:92] = venv.obs[fin]
+                k = fin.numel()
+                w0 = self.n_transitions % self.transitions.shape[0]
+                k1 = min(k, self.transitions.shape[0] - w0)
+                self.transitions[w0:w0 + k1] = rec[:k1]
+                if k1 < k:
+                    self.transitions[:k - k1] = rec[k1:]
+                self.n_transitions += k
+                dn = fin[self.macro_done[fin]]
+                if dn.numel():
+                    self.counters["episodes"] += int(dn.numel())
+                    self.counters["success"] += int(venv.success[dn].sum())
+                    venv.reset(dn.cpu().numpy())
+            venv.has_prev[need] = 0                                   # env._reset_prev_state()
+            obs = venv.obs[need]
+            ac = self.policy(obs, self.env_gid[need], self.macro_index[need]).float().clamp(-1, 1)
+            self.macro_index[need] += 1
+            self.prev_ob[need] = obs
+            self.ac[need, :7] = ac
+            self.meta_rew[need] = 0
+            self.executed[need] = 0
+            self.macro_done[need] = False
+            self.pending[need] = True
+            is_mp = (ac.abs() > cfg.omega).any(dim=1)
+            d_idx = need[~is_mp]
+            if d_idx.numel():
+                self.kind[d_idx] = 0
+                self.traj_len[d_idx] = 1
+                self.traj_pos[d_idx] = 0
+                self.counters["rl"] += int(d_idx.numel())
+            p_idx = need[is_mp]
+            if p_idx.numel():
+                self._plan(p_idx, ac[is_mp])
+        # stage the action of every env for this tick
+        kind = self.kind
+        self.step_mode.copy_(kind)
+        direct = kind == 0
+        self.step_action[:, :7] = torch.where(direct[:, None], self.ac[:, :7] / cfg.omega, self.step_action[:, :7])
+        plan = kind == 1
+        if bool(plan.any()):
+            pos = self.traj_pos.to(torch.int64).clamp(max=cfg.max_traj - 1)
+            nxt = self.traj[torch.arange(venv.n, device=self.dev), pos]
+            delta = (nxt - venv.qpos[:, :7]).float()                  # env.form_action(next_qpos)
+            self.step_action[:, :7] = torch.where(plan[:, None], delta, self.step_action[:, :7])
+        venv.step(self.step_action, self.step_mode)
+        self.launches += 1
+        disc = torch.pow(torch.full_like(self.meta_rew, cfg.discount_factor), self.traj_pos.double())
+        self.meta_rew += torch.where(plan, disc, torch.ones_like(disc)) * venv.reward
+        self.executed += 1
+        self.traj_pos += 1
+        done = venv.done.bool()
+        self.macro_done |= done
+        self.traj_len = torch.where(done, self.traj_pos, self.traj_len)
+        self.env_steps += venv.n
+        return venv.n

@@ -7,7 +7,7 @@
 #define DMAXD 24
 #define DMAXA 16
 #define DMAXG 64
-#define DMAXC 48 /* constraint rows (same cap as the kernel) */
+#define DMAXC 36 /* constraint rows (same cap as the kernel) */
 #define MINVAL 1e-15
 
 typedef struct { double w[3], v[3]; } sv6; /* spatial motion (w, v_O) or force (n_O, f) about the world origin */
