@@ -11,7 +11,7 @@ sequence the reference uses: displacement map -> target clip -> invalid-target b
 straight-line interpolation -> RRT-Connect -> densification.  All validity checks of a tick are
 batched into a few ``mopa_is_valid_batch`` launches and all RRT problems into one
 ``mopa_plan_batch`` launch.  A finished macro action emits one SMDP transition record
-(ob 40, ac 8, rew, done, intra_steps, pad, ob_next 40 = 92 floats), exactly the content of the
+(ob 40, ac 8, rew, done, intra_steps, env id, ob_next 40 = 92 floats), exactly the content of the
 reference's ``Rollout`` entries (rl/rollouts.py:15-36).
 """
 from __future__ import annotations
@@ -335,6 +335,7 @@ class VecMoPARolloutRunner:
                 rec[:, 48] = self.meta_rew[fin].float()
                 rec[:, 49] = self.macro_done[fin].float()
                 rec[:, 50] = (self.executed[fin] - 1).clamp(min=0).float()
+                rec[:, 51] = self.env_gid[fin].float()
                 rec[:, 52:92] = venv.obs[fin]
                 k = fin.numel()
                 w0 = self.n_transitions % self.transitions.shape[0]
@@ -372,7 +373,7 @@ class VecMoPARolloutRunner:
         kind = self.kind
         self.step_mode.copy_(kind)
         direct = kind == 0
-        self.step_action[:, :7] = torch.where(direct[:, None], self.ac[:, :7] / cfg.omega, self.step_action[:, :7])
+        self.step_action[:, :7] = torch.where(direct[:, None], (self.ac[:, :7].double() / cfg.omega).float(), self.step_action[:, :7])
         plan = kind == 1
         if bool(plan.any()):
             pos = self.traj_pos.to(torch.int64).clamp(max=cfg.max_traj - 1)

@@ -103,3 +103,27 @@ class PushEnvOracle:
             terminal = True
         self.terminal = terminal
         return ob, reward, terminal
+
+    def null_step(self):
+        """Planner failure (rl/mopa_rollouts.py:304-327): compute_reward(zeros) + _after_step, no simulation.
+        Frames are refreshed by a forward pass first (the device path does the same)."""
+        self.set_state(self.qpos, self.qvel)
+        gs = 0.5 * (self._site(self.b_rc, self.s_re) + self._site(self.b_lc, self.s_le))
+        cube = self.xpos[self.b_cube]
+        target = self.target_base + np.array([self.qpos[self.tgt_q[0]], self.qpos[self.tgt_q[1]], 0.0])
+        d_gc, d_ct = np.linalg.norm(cube - gs), np.linalg.norm(cube[:2] - target[:2])
+        reward = 0.0
+        if d_ct < 0.1:
+            reward += 0.5 * (1 - np.tanh(5 * d_ct))
+        if d_gc < 0.1:
+            reward += 0.1 * (1 - np.tanh(10 * d_gc))
+        terminal = False
+        if d_ct < self.dthr:
+            reward += self.succ_rew
+            self.success, terminal = True, True
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return reward, terminal

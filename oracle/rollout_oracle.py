@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE — scalar restatement of the reference's experience-collection loop for ONE
+environment, built on the CPU oracles (PushEnvOracle, OracleScene, OraclePlanner).  Follows:
+
+  MoPARolloutRunner.run                 rl/mopa_rollouts.py:22-399   (train branch, every_steps=1,
+                                                                      no IK, no discrete action, no reuse_data)
+  SACAgent.is_planner_ac / convert2planner_displacement / plan / clip_qpos / simple_interpolate
+                                        rl/sac_agent.py:148-318
+  PlannerAgent.plan                     rl/planner_agent.py:42-52
+  SamplingBasedPlanner.plan             motion_planners/sampling_based_planner.py:60-101
+
+It yields the same SMDP transition records the vectorised runner emits (92 floats) so the two can
+be compared env by env, and it is the "reference path on host cores" that bench.py times.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .env_oracle import PushEnvOracle
+from .oracle import OraclePlanner, OracleScene, space_from_model
+
+
+class ScalarMoPARunner:
+    def __init__(self, model, dynmodel, cfg, ignored, passive, env_gid, seed_env, policy, contacts=True, max_episode_steps=250):
+        """policy(env_gid, macro_index) -> action (7,) in [-1, 1]."""
+        self.m, self.cfg, self.gid, self.policy = model, cfg, int(env_gid), policy
+        self.env = PushEnvOracle(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
+        self.scene = OracleScene(model, ignored, cfg.contact_threshold, "f32")
+        adr, lo, hi, so2 = space_from_model(model, passive)
+        self.planner = OraclePlanner(self.scene, adr, lo, hi, so2, cfg.range, 0.005, cfg.seed, max_nodes=4096)
+        self.ref = adr
+        jid = [list(model.jnt_qposadr).index(a) for a in adr]
+        self.jlo, self.jhi = model.jnt_range[jid, 0], model.jnt_range[jid, 1]
+        self.seed_env = seed_env
+        self.episode = 0
+        self.plan_count = 0
+        self.macro_index = 0
+        self.env_steps = 0
+        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0)
+        self.ob = self._reset()
+
+    def _reset(self):
+        from mopa_rl_b200.envs import push_reset_state  # reset draws are input data shared with the product
+
+        q, v = push_reset_state(self.m, self.seed_env, [self.gid], [self.episode])
+        self.episode += 1
+        return self.env.reset_to(q[0], v[0])
+
+    def _valid(self, q):
+        return bool(self.scene.is_valid(np.asarray(q, np.float64).astype(np.float32).astype(np.float64))[0] & 1)
+
+    def _clip_qpos(self, q):
+        arm = q[:7]
+        if np.any(arm < self.jlo) or np.any(arm > self.jhi):
+            q = q.copy()
+            q[:7] = np.clip(arm, self.jlo + self.cfg.joint_margin, self.jhi - self.cfg.joint_margin)
+        return q
+
+    def _simple_interpolate(self, curr, target):
+        """rl/sac_agent.py:262-318 with use_planner=False.  Returns (traj, valid)."""
+        lim = self.cfg.ac_scale * 0.8
+        curr = self._clip_qpos(curr)
+        diff = target[:7] - curr[:7]
+        sf = max(np.max(np.abs(diff) / lim), 1.0)
+        scaled = diff / sf
+        traj, interp = [], curr.copy()
+        for _ in range(int(sf)):
+            interp[:7] += scaled
+            if not self._valid(interp):
+                return traj, False
+            traj.append(interp.copy())
+        traj.append(target)
+        return traj, True
+
+    def _plan(self, curr, target):
+        """SACAgent.plan: interpolation first, RRT-Connect when the straight line is blocked, densify."""
+        cfg = self.cfg
+        curr = self._clip_qpos(curr)
+        traj, ok = self._simple_interpolate(curr, target)
+        if ok:
+            return traj, True, True, True
+        key = (self.gid << 32) + self.plan_count
+        self.plan_count += 1
+        r = self.planner.plan(curr.astype(np.float32).astype(np.float64), target.astype(np.float32).astype(np.float64), key, cfg.max_iter, cfg.max_path)
+        if r["status"] != 0:
+            return None, False, False, r["status"] != -4
+        states = r["path"]
+        path = [curr + (s - states[0]) for s in states][1:]       # re-based on start, first row dropped
+        if cfg.interpolation:
+            new, start = [], curr
+            for p in path:
+                d = p[:7] - start[:7]
+                if np.any(np.abs(d) > cfg.ac_scale):
+                    lim = cfg.ac_scale * 0.8
+                    sf = max(np.max(np.abs(d) / lim), 1.0)
+                    inner, interp, good = [], start.copy(), True
+                    for _ in range(min(int(sf), int(cfg.range / lim) + 1)):
+                        interp[:7] += d / sf
+                        if not self._valid(interp):
+                            good = False
+                            break
+                        inner.append(interp.copy())
+                    new.extend((inner if good else []) + [p])
+                else:
+                    new.append(p)
+                start = p
+            path = new
+        if len(path) > cfg.max_traj:
+            return None, False, False, True
+        return path, True, False, True
+
+    def macro_step(self):
+        """One iteration of the `while not done` loop of run(); returns the 92-float transition record."""
+        cfg, env = self.cfg, self.env
+        if env.terminal:
+            self.ob = self._reset()
+        prev_ob = self.ob.copy()
+        ac = np.asarray(self.policy(self.gid, self.macro_index), np.float64)
+        ac = ac.astype(np.float32).astype(np.float64)
+        self.macro_index += 1
+        curr = env.qpos.copy()
+        is_mp = bool(np.any(np.abs(ac) > cfg.omega))
+        steps = 0
+        if is_mp:
+            w = cfg.omega
+            disp = np.where(np.abs(ac) < w, ac / (w / cfg.ac_scale),
+                            np.sign(ac) * (cfg.ac_scale + (cfg.action_range - cfg.ac_scale) * ((np.abs(ac) - w) / (1 - w))))
+            target = curr.copy()
+            target[:7] = np.clip(curr[:7] + disp, self.jlo, self.jhi)
+            if cfg.invalid_target_handling and not self._valid(target):
+                trial = 0
+                while not self._valid(target) and trial < cfg.num_trials:
+                    d = curr - target
+                    target = target + cfg.step_size * d / np.linalg.norm(d)
+                    trial += 1
+            if self._valid(target):
+                traj, success, interpolation, exact = self._plan(curr, target)
+                valid = True
+            else:
+                traj, success, interpolation, valid, exact = None, False, False, False, True
+            if success:
+                self.counters["interpolation" if interpolation else "mp"] += 1
+                meta, done = 0.0, False
+                for i, nq in enumerate(traj):
+                    a = np.asarray(nq[:7] - env.qpos[:7], np.float32).astype(np.float64)   # form_action (fp32 action row)
+                    self.ob, rew, done = env.step(a, is_planner=True)
+                    meta += cfg.discount_factor ** i * rew
+                    steps += 1
+                    if done:
+                        break
+                rec_rew, intra = meta, i
+            else:
+                self.counters["mp_fail"] += 1
+                if not valid:
+                    self.counters["invalid"] += 1
+                if not exact:
+                    self.counters["approximate"] += 1
+                rec_rew, done = env.null_step()
+                intra, steps = 0, 1
+        else:
+            self.counters["rl"] += 1
+            self.ob, rec_rew, done = env.step((ac / cfg.omega).astype(np.float32).astype(np.float64), is_planner=False)
+            intra, steps = 0, 1
+        env.prev_state = None                                       # env._reset_prev_state()
+        self.env_steps += steps
+        rec = np.zeros(92, np.float32)
+        rec[0:40], rec[40:47], rec[48], rec[49], rec[50], rec[52:92] = prev_ob, ac, rec_rew, float(done), intra, self.ob
+        return rec

@@ -1,0 +1,51 @@
+"""Conformance of the vectorised MoPA runner against the scalar restatement of
+MoPARolloutRunner.run (oracle/rollout_oracle.py): same policy draws, same planner keys -> the
+per-env sequences of SMDP transition records must agree."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vectorised_runner_matches_scalar_reference_loop(push_model, oracle_built):
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, VecMoPARolloutRunner, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    n, ticks, seed = 12, 60, 4321
+    cfg = MoPAConfig(max_iter=150, seed=99)
+    venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=25, env_id_offset=100)
+    runner = VecMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 7))
+    for _ in range(ticks):
+        runner.tick()
+    torch.cuda.synchronize()
+    rec = runner.transitions[:runner.n_transitions].cpu().numpy()
+    assert runner.env_steps == n * ticks and len(rec) > n
+
+    def policy(gid, k):
+        u = rng.uniform01(7, np.uint64(gid), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ignored, passive, _ = planner_inputs(push_model)
+    dm = DynModel(push_model)
+    kinds = set()
+    worst = 0.0
+    for e in range(n):
+        gid = 100 + e
+        mine = rec[rec[:, 51] == gid]
+        ref = ScalarMoPARunner(push_model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=25)
+        for k, r in enumerate(mine):
+            o = ref.macro_step()
+            assert np.array_equal(r[40:47], o[40:47]), (e, k)                    # same action
+            assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])  # done flag, intra_steps
+            assert abs(r[48] - o[48]) < 1e-5, (e, k)                              # (discounted) reward
+            d = max(np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+            worst = max(worst, d)
+            assert d < 1e-4, (e, k, d)
+            kinds.add("plan" if r[50] > 0 else "single")
+    assert kinds == {"plan", "single"}
+    print("vectorised vs scalar runner: %d transitions, worst |obs diff| %.2e, counters %s" % (len(rec), worst, runner.counters))
