@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the MoPA-RL experience-collection hot path on B200.
+"""Benchmark of the MoPA-RL experience-collection hot path on B200 ("Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload validity|plan|rollout] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rollout|validity] [--impl reference]
 
-One JSON line on stdout (rank 0).  Under torchrun every rank drives its own GPU; the timed
-region is bracketed by barrier + synchronize and the max over ranks is reported.
+rollout  (default, BASELINE.json metric): env-steps/sec incl. planner, SawyerPushObstacle-v0 MoPA,
+         4096 vectorised envs per GPU.  One "step" = one tick of the vectorised runner = one env.step
+         (75 physics substeps) for every env, plus the policy / validity / RRT work of the envs that
+         finished their macro action.  With N > 1 every rank owns its own env shard and the ranks
+         all-gather the new transition records each tick (NCCL) into a replicated replay.
+validity BASELINE config 5: 10M random Sawyer qpos state-validity queries per GPU.
+One JSON line on stdout (rank 0); max over ranks of device-timed regions bracketed by barriers.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -22,8 +28,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+METRIC = "env-steps/sec (incl. planner) SawyerPushObstacle-v0"
+WORKLOADS = {
+    "rollout": "SawyerPushObstacle-v0 MoPA (omega 0.7, action_range 0.5, RRT-Connect range 0.1), %d vectorised envs per GPU, uniform random-exploration policy",
+    "validity": "config5 collision-check microbench: SawyerPushObstacle-v0, %d random 7-DoF qpos state-validity queries per GPU, contact_threshold -0.002, cube x {table,bin1} ignored",
+}
 
-# ----------------------------------------------------------------------------- helpers
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -36,21 +47,17 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device = device
-        self.proc = None
-        self.lines = []
+        self.device, self.proc, self.lines = device, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -88,16 +95,15 @@ def dist_env():
 
 
 def push_setup():
-    from helpers import planner_setup
     from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import planner_inputs
 
     model = load_model("SawyerPushObstacle-v0")
-    ignored, passive, ref = planner_setup(model)
+    ignored, passive, ref = planner_inputs(model)
     return model, ignored, passive, ref
 
 
 def synth_qpos_f32(model, ref, n, seed, pad):
-    """BASELINE config 5 queries: active joints ~ U(joint range), passive dims at qpos0; fp32 rows padded to `pad` floats."""
     rng = np.random.Generator(np.random.PCG64(seed))
     jid = [list(model.jnt_qposadr).index(a) for a in ref]
     lo, hi = model.jnt_range[jid, 0].astype(np.float32), model.jnt_range[jid, 1].astype(np.float32)
@@ -107,9 +113,46 @@ def synth_qpos_f32(model, ref, n, seed, pad):
     return q
 
 
-# ----------------------------------------------------------------------------- CPU arms (oracle)
+# ----------------------------------------------------------------------------- CPU arms (the oracle = C/numpy restatement
+# of the reference path; MuJoCo 2.0 + OMPL cannot be built here)
+def _cpu_rollout_worker(args):
+    gid, macros, seed, max_iter = args
+    sys.path.insert(0, ROOT)
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import MoPAConfig, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    model = load_model("SawyerPushObstacle-v0")
+    ignored, passive, _ = planner_inputs(model)
+
+    def policy(g, k):
+        u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter), ignored, passive, gid, seed, policy)
+    t0 = time.perf_counter()
+    for _ in range(macros):
+        r.macro_step()
+    return r.env_steps, time.perf_counter() - t0
+
+
+def cpu_rollout_rate(cores, macros, seed, max_iter, base_gid=0):
+    """One scalar runner (env + planner, like one MPI rank of the reference) per host core."""
+    from oracle import oracle
+
+    oracle.build()
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_rollout_worker, [(base_gid + i, macros, seed, max_iter) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    steps = sum(s for s, _ in res)
+    busy = max(t for _, t in res)
+    return steps / busy, steps, busy, wall
+
+
 def oracle_validity_rate(model, ignored, q64, threads):
-    """Oracle (C restatement of the reference path) on `threads` host threads, one scene per thread."""
     from oracle import oracle
 
     oracle.build()
@@ -132,35 +175,165 @@ def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    model, ignored, passive, ref = push_setup()
     cores = os.cpu_count() or 1
-    n = args.ref_sample
-    rates = []
-    for step in range(args.warmup + args.steps):
-        q = synth_qpos_f32(model, ref, n, 1234 + step, model.nq)[:, :model.nq].astype(np.float64)
-        rate, dt, _ = oracle_validity_rate(model, ignored, q, cores)
-        if step >= args.warmup:
-            rates.append((rate, dt))
-    value = float(np.mean([r for r, _ in rates]))
-    line = {
-        "impl": "reference", "metric": "state-validity queries/sec (collision-check microbench)", "value": value, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([d for _, d in rates]) * 1e3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES["validity"], "sample_queries_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": "%d queries per step, one oracle scene per host thread (MuJoCo+OMPL cannot be built here: the oracle is the C restatement)" % n},
-        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+    if args.workload == "validity":
+        model, ignored, passive, ref = push_setup()
+        rates = []
+        for step in range(args.warmup + args.steps):
+            q = synth_qpos_f32(model, ref, args.ref_sample, 1234 + step, model.nq)[:, :model.nq].astype(np.float64)
+            rate, dt, _ = oracle_validity_rate(model, ignored, q, cores)
+            if step >= args.warmup:
+                rates.append((rate, dt))
+        value, ms = float(np.mean([r for r, _ in rates])), float(np.mean([d for _, d in rates]) * 1e3)
+        metric, unit, sample = "state-validity queries/sec (collision-check microbench)", "queries/s", "%d queries per step" % args.ref_sample
+        cfg = {"workload": WORKLOADS["validity"] % args.queries}
+    else:
+        rates = []
+        for step in range(args.warmup + args.steps):
+            rate, steps, busy, wall = cpu_rollout_rate(cores, args.ref_macros, 1234, args.max_iter, base_gid=1000 * step)
+            if step >= args.warmup:
+                rates.append((rate, busy))
+        value, ms = float(np.mean([r for r, _ in rates])), float(np.mean([d for _, d in rates]) * 1e3)
+        metric, unit = METRIC, "env-steps/s"
+        sample = "%d macro actions per scalar runner per step, one runner (env + planner) per host core" % args.ref_macros
+        cfg = {"workload": WORKLOADS["rollout"] % args.envs, "max_iter": args.max_iter}
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": sample + " (oracle = C/numpy restatement of the reference path; MuJoCo 2.0 + OMPL cannot be built here)"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
-WORKLOAD_NAMES = {
-    "validity": "config5 collision-check microbench: SawyerPushObstacle-v0, 10M random 7-DoF qpos state-validity queries per GPU, contact_threshold -0.002, cube x {table,bin1} ignored",
-}
+# ----------------------------------------------------------------------------- GPU arm: rollout
+class HostLoopPolicy:
+    """End-to-end arm: the policy lives on the host (as the reference's actor loop does): observations
+    of the envs that need an action come back to pinned host memory, actions go up from pinned memory."""
+
+    def __init__(self, torch, device, seed, n_max):
+        self.torch, self.device = torch, device
+        self.rng = np.random.Generator(np.random.PCG64(seed))
+        self.h_obs = torch.zeros(n_max, 40, dtype=torch.float32).pin_memory()
+        self.h_act = torch.zeros(n_max, 7, dtype=torch.float32).pin_memory()
+        self.h2d = self.d2h = 0
+
+    def __call__(self, obs, env_ids=None, macro_index=None):
+        k = obs.shape[0]
+        self.h_obs[:k].copy_(obs, non_blocking=False)
+        self.h_act[:k] = self.torch.from_numpy(self.rng.uniform(-1, 1, (k, 7)).astype(np.float32))
+        self.d2h += k * 40 * 4
+        self.h2d += k * 7 * 4
+        return self.h_act[:k].to(self.device, non_blocking=True)
 
 
-# ----------------------------------------------------------------------------- GPU arm
+def run_rollout(args):
+    import torch
+    import torch.distributed as dist
+
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.replay import ReplicatedReplay
+    from mopa_rl_b200.rollout import MoPAConfig, VecMoPARolloutRunner
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    cfg = MoPAConfig(max_iter=args.max_iter)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make(policy=None):
+        venv = VecSawyerPushObstacle(n, seed=1234, device=local_rank, env_id_offset=rank * n)
+        return VecMoPARolloutRunner(venv, cfg, policy=policy)
+
+    def timed(runner, replay, h_trans=None):
+        """W warm-up ticks, then K timed ticks.  Returns (ms, env_steps, launches, kernel_ms list, d2h bytes)."""
+        d2h = 0
+        for _ in range(args.warmup):
+            runner.tick()
+            replay.exchange(runner.last_emitted)
+        barrier()
+        runner.step_events = []
+        l0, s0 = runner.launches, runner.env_steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            runner.tick()
+            replay.exchange(runner.last_emitted)
+            if h_trans is not None and runner.last_emitted is not None:
+                k = runner.last_emitted.shape[0]
+                h_trans[:k].copy_(runner.last_emitted, non_blocking=False)
+                d2h += k * 92 * 4
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        kms = [a.elapsed_time(b) for a, b in runner.step_events]
+        runner.step_events = None
+        return max(dev_ms, 0.0), wall_ms, runner.env_steps - s0, runner.launches - l0, kms, d2h
+
+    # device-resident arm
+    runner = make()
+    replay = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=max(8192, n))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_ms, steps, launches, kms, _ = timed(runner, replay)
+    clocks = sampler.stop() if rank == 0 else None
+    counters = dict(runner.counters)
+    # end-to-end arm: host-side policy loop + transition records read back to pinned host memory every tick
+    hp = HostLoopPolicy(torch, dev, 99 + rank, n)
+    runner2 = make(policy=hp)
+    replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=max(8192, n))
+    h_trans = torch.zeros(n, 92, dtype=torch.float32).pin_memory()
+    hp.h2d = hp.d2h = 0
+    _, wall2_ms, steps2, _, _, d2h_tr = timed(runner2, replay2, h_trans)
+    t = torch.tensor([wall_ms, wall2_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([steps, steps2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    wall_ms, wall2_ms = float(t[0]), float(t[1])
+    tot_steps, tot_steps2 = float(cnt[0]), float(cnt[1])
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        bytes_per_env_step = 816  # SURVEY.md 8(d): 352 B state/action in + 464 B state/obs out
+        k_ms = float(np.mean(kms)) if kms else float("nan")
+        achieved = bytes_per_env_step * n / (k_ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter)
+        line = {
+            "metric": METRIC, "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 physics / f32 collision", "data": "synthetic",
+            "config": {"workload": WORKLOADS["rollout"] % n, "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
+                       "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
+                       "device_ms_per_step": dev_ms / args.steps, "counters": counters},
+            "clocks": clocks,
+            "e2e": {"value": tot_steps2 / (wall2_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": hp.h2d / args.steps,
+                    "d2h_bytes_per_step": (hp.d2h + d2h_tr) / args.steps,
+                    "api": "VecMoPARolloutRunner.tick() with a host-side policy loop (obs D2H, actions H2D from pinned memory) and transition records read back every tick"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind, "kernel": "env_step_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
+                         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * len(kms) / max(dev_ms, 1e-9),
+                         "note": "75 substeps per env.step run on chip: the kernel is fp64 compute/latency bound, not HBM bound"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d macro actions on each of %d scalar runners (%d env-steps, %.1f s)" % (args.cpu_macros, cores, cpu_steps, cpu_busy)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- GPU arm: validity microbench
 def run_validity(args):
     import torch
     import torch.distributed as dist
@@ -179,7 +352,7 @@ def run_validity(args):
     hq = synth_qpos_f32(model, ref, n, 1234 + rank, row)
     h_pinned = torch.from_numpy(hq).pin_memory()
     d_q = h_pinned.to(dev, non_blocking=False)
-    d_r = torch.zeros(n, dtype=torch.int32, device=dev)  # uint32 words
+    d_r = torch.zeros(n, dtype=torch.int32, device=dev)
     h_words = torch.zeros(n, dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -206,7 +379,6 @@ def run_validity(args):
     barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    # end-to-end: host rows in pinned memory -> result words back in host memory, through the C ABI
     e2e_steps = max(1, min(args.steps, 5))
     planner.is_valid_host_f32(h_pinned.data_ptr(), row, n, h_words.data_ptr(), 0)
     barrier()
@@ -222,24 +394,20 @@ def run_validity(args):
     total_ms, e2e_s = float(t[0]), float(t[1])
     words = d_r.cpu().numpy().view(np.uint32)
     assert np.array_equal(words & 1, h_words.numpy().view(np.uint32) & 1), "device-resident and end-to-end paths disagree"
-
     if rank == 0:
         peak, peak_kind = measured_peaks()
         bytes_per_query = row * 4 + 4
         ms_step = total_ms / args.steps
-        value = world * n / (ms_step * 1e-3)
         achieved = bytes_per_query * n / (float(np.mean(kernel_ms)) * 1e-3) / 1e9
-        # CPU baseline on a bounded sample of the same queries, all host threads, checked against the GPU words
         cores = os.cpu_count() or 1
         ns = min(n, args.cpu_sample)
         rate, dt, ow = oracle_validity_rate(model, ignored, hq[:ns, :model.nq].astype(np.float64), cores)
         mism = int(((ow & 1) != (words[:ns] & 1)).sum())
-        rate1, _, _ = oracle_validity_rate(model, ignored, hq[:max(1, ns // cores), :model.nq].astype(np.float64), 1)
-        line = {
-            "metric": "state-validity queries/sec (collision-check microbench)", "value": value, "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        print(json.dumps({
+            "metric": "state-validity queries/sec (collision-check microbench)", "value": world * n / (ms_step * 1e-3), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES["validity"], "queries_per_gpu": n, "row_bytes": row * 4,
+            "config": {"workload": WORKLOADS["validity"] % n, "queries_per_gpu": n, "row_bytes": row * 4,
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % (n * row * 4 / 1e9), "valid_fraction": float((words & 1).mean())},
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * row * 4, "d2h_bytes_per_step": n * 4,
@@ -247,10 +415,8 @@ def run_validity(args):
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query},
-            "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port", "single_thread": rate1,
-                             "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism},
-        }
-        print(json.dumps(line))
+            "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -258,19 +424,24 @@ def run_validity(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="validity", choices=["validity"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
+    ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
+    ap.add_argument("--cpu-macros", type=int, default=24, help="macro actions per scalar runner in the cpu_baseline leg")
+    ap.add_argument("--ref-macros", type=int, default=16, help="macro actions per scalar runner per step of --impl reference")
     ap.add_argument("--queries", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=1_000_000)
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
-    run_validity(args)
+    if args.workload == "validity":
+        return run_validity(args)
+    run_rollout(args)
 
 
 if __name__ == "__main__":

@@ -130,6 +130,8 @@ class VecMoPARolloutRunner:
         self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, densify_fallback=0, episodes=0,
                              success=0, mp_path_len=0, interpolation_path_len=0)
         self.launches = 0
+        self.step_events = None      # set to [] to collect CUDA events around every env-step launch
+        self.last_emitted = None     # transition records emitted by the latest tick (for the replay exchange)
         venv.reset()
 
     # ---------------------------------------------------------------- batched planner glue
@@ -325,6 +327,7 @@ class VecMoPARolloutRunner:
     def tick(self):
         torch, cfg, venv = self.torch, self.cfg, self.venv
         need = torch.nonzero(self.traj_pos >= self.traj_len).squeeze(1)
+        self.last_emitted = None
         if need.numel():
             # finished macro actions -> transition records; finished episodes -> reset
             fin = need[self.pending[need]]
@@ -344,6 +347,7 @@ class VecMoPARolloutRunner:
                 if k1 < k:
                     self.transitions[:k - k1] = rec[k1:]
                 self.n_transitions += k
+                self.last_emitted = rec
                 dn = fin[self.macro_done[fin]]
                 if dn.numel():
                     self.counters["episodes"] += int(dn.numel())
@@ -380,7 +384,14 @@ class VecMoPARolloutRunner:
             nxt = self.traj[torch.arange(venv.n, device=self.dev), pos]
             delta = (nxt - venv.qpos[:, :7]).float()                  # env.form_action(next_qpos)
             self.step_action[:, :7] = torch.where(plan[:, None], delta, self.step_action[:, :7])
-        venv.step(self.step_action, self.step_mode)
+        if self.step_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            venv.step(self.step_action, self.step_mode)
+            e1.record()
+            self.step_events.append((e0, e1))
+        else:
+            venv.step(self.step_action, self.step_mode)
         self.launches += 1
         disc = torch.pow(torch.full_like(self.meta_rew, cfg.discount_factor), self.traj_pos.double())
         self.meta_rew += torch.where(plan, disc, torch.ones_like(disc)) * venv.reward
