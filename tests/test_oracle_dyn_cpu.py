@@ -1,0 +1,188 @@
+"""Physics-step oracle: rigid-body identities, closed-form cases, contacts, env logic, goldens."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import PUSH_INIT_QPOS
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dyn(push_model, oracle_built):
+    from mopa_rl_b200.dynmodel import DynModel
+
+    dm = DynModel(push_model)
+    return dm, oracle_built.OracleDyn(dm)
+
+
+def test_simulated_subtrees(dyn, push_model):
+    dm, od = dyn
+    names = [push_model.names["body"][b] for b in dm.bodies]
+    assert names == ["right_l0", "head", "screen", "right_l1", "right_l2", "right_l3", "right_l4", "right_l5", "right_l6",
+                     "right_ee_attchment", "clawGripper", "rightclaw", "leftclaw", "cube"]
+    assert dm.nd == 15 and dm.nact == 7 and len(dm.pairs) == 250
+    assert not any("indicator" in n or "target" in n for n in names)        # ghost arms / target slider are not integrated
+
+
+def _integrate(m, dm, q, v, eps):
+    from mopa_rl_b200.mjcf import quat_mul
+
+    q2 = q.copy()
+    for qa, va in zip(dm.dof_qadr, dm.dof_vadr):
+        if qa >= 0:
+            q2[qa] += eps * v[va]
+    a, va = m.get_joint_qpos_addr("cube")[0], m.get_joint_qvel_addr("cube")[0]
+    w = v[va + 3:va + 6]
+    ang = np.linalg.norm(w) * abs(eps)
+    if ang > 0:
+        ax = w / np.linalg.norm(w) * np.sign(eps)
+        q2[a + 3:a + 7] = quat_mul(q2[a + 3:a + 7], np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * ax]))
+    return q2
+
+
+def test_mass_matrix_and_bias_identities(dyn, push_model):
+    m = push_model
+    dm, od = dyn
+    rng = np.random.default_rng(0)
+    q = m.qpos0.copy()
+    q[:7] = PUSH_INIT_QPOS + rng.uniform(-0.5, 0.5, 7)
+    v = np.zeros(m.nv)
+    v[dm.dof_vadr] = rng.uniform(-1, 1, dm.nd)
+    M, bias, com = od.mass_bias(q, v)
+    assert np.abs(M - M.T).max() == 0 and np.linalg.eigvalsh(M).min() > 0
+    mass = m.body_mass[dm.bodies]
+    eps = 1e-6
+    # gravity torque = dV/dq (bias at zero velocity)
+    _, b0, _ = od.mass_bias(q, np.zeros(m.nv))
+
+    def V(qq):
+        return 9.81 * np.sum(mass * od.mass_bias(qq, np.zeros(m.nv))[2][:, 2])
+
+    g = np.zeros(dm.nd)
+    for k in range(dm.nd):
+        e = np.zeros(m.nv)
+        e[dm.dof_vadr[k]] = 1
+        g[k] = (V(_integrate(m, dm, q, e, eps)) - V(_integrate(m, dm, q, e, -eps))) / (2 * eps)
+    assert np.abs(g - b0).max() < 1e-6
+    # Coriolis forces: qd . C(q, qd) = 1/2 qd^T Mdot qd
+    qd = v[dm.dof_vadr]
+    M1 = od.mass_bias(_integrate(m, dm, q, v, eps), v)[0]
+    M0 = od.mass_bias(_integrate(m, dm, q, v, -eps), v)[0]
+    assert abs(qd @ (bias - b0) - 0.5 * qd @ ((M1 - M0) / (2 * eps)) @ qd) < 1e-6
+    # kinetic energy from finite-difference COM velocities (translation part) is bounded by 1/2 qd^T M qd
+    c1 = od.mass_bias(_integrate(m, dm, q, v, eps), v)[2]
+    c0 = od.mass_bias(_integrate(m, dm, q, v, -eps), v)[2]
+    T_lin = 0.5 * np.sum(mass * np.sum(((c1 - c0) / (2 * eps)) ** 2, axis=1))
+    assert 0 < T_lin < 0.5 * qd @ (M - np.diag(m.dof_armature[dm.dof_vadr])) @ qd
+
+
+def test_free_fall_and_hold(dyn, push_model):
+    m = push_model
+    dm, od = dyn
+    od.enable_contacts(0)
+    q = m.qpos0.copy()
+    q[:7] = PUSH_INIT_QPOS
+    v = np.zeros(m.nv)
+    bias, _, _ = od.forward(q, v)
+    comp = np.zeros(dm.nd, np.int32)
+    comp[:7] = 1
+    n = 50
+    q1, v1, _, _, _, _ = od.step(q, v, q[:7], comp, bias, n)
+    t = n * m.opt_timestep
+    # cube in free fall (semi-implicit Euler: z = z0 - g h^2 n(n+1)/2), tiny free-joint damping 5e-4 ignored at 1e-4
+    assert abs(q1[29] - (0.88 - 9.81 * m.opt_timestep ** 2 * n * (n + 1) / 2)) < 1e-4
+    assert abs(v1[m.get_joint_qvel_addr("cube")[0] + 2] + 9.81 * t) < 1e-3
+    # arm held by the position actuators + gravity compensation: stays where it is
+    assert np.abs(q1[:7] - q[:7]).max() < 2e-4
+    od.enable_contacts(1)
+
+
+def test_actuator_tracking_and_joint_limits(dyn, push_model):
+    m = push_model
+    dm, od = dyn
+    q = m.qpos0.copy()
+    q[:7] = PUSH_INIT_QPOS
+    v = np.zeros(m.nv)
+    bias, _, _ = od.forward(q, v)
+    comp = np.zeros(dm.nd, np.int32)
+    comp[:7] = 1
+    target = q[:7] + np.array([0.05, -0.05, 0.05, 0.05, -0.05, 0.05, -0.05])
+    q1, v1, bias, _, _, _ = od.step(q, v, target, comp, bias, 75)
+    moved = (q1[:7] - q[:7]) / (target - q[:7])
+    assert (moved > 0.15).all() and (moved < 1.1).all()                    # heads to the target, no overshoot beyond 10 %
+    q2, v2, bias, _, _, _ = od.step(q1, v1, target, comp, bias, 600)
+    assert np.abs(q2[:7] - target).max() < 5e-3 and np.abs(v2[:7]).max() < 1e-2   # settles on the target
+    # drive right_j1 (range [-3.8, 1.25]) far past its upper limit: the soft limit holds it near 1.25
+    q3 = q.copy()
+    q3[1] = 1.2
+    tgt = q3[:7].copy()
+    tgt[1] = 3.0
+    b3, _, _ = od.forward(q3, v)
+    q4, _, _, _, _, _ = od.step(q3, v, tgt, comp, b3, 400)
+    assert 1.2 < q4[1] < 1.25 + 0.05
+
+
+def test_cube_rests_on_the_bin_floor(dyn, push_model):
+    m = push_model
+    dm, od = dyn
+    q = m.qpos0.copy()
+    q[:7] = PUSH_INIT_QPOS
+    v = np.zeros(m.nv)
+    bias, _, _ = od.forward(q, v)
+    comp = np.zeros(dm.nd, np.int32)
+    comp[:7] = 1
+    q1, v1, bias, _, _, ncon = od.step(q, v, q[:7], comp, bias, 300)
+    cv = m.get_joint_qvel_addr("cube")[0]
+    assert ncon == 4                                                        # box-on-box face contact: four clipped corners
+    assert abs(q1[29] - 0.86) < 1e-3 and np.abs(v1[cv:cv + 6]).max() < 1e-3  # bin floor top 0.83 + half cube 0.03, sub-mm sink
+    assert np.abs(q1[27:29] - [0.92, 0.0]).max() < 1e-3                      # does not slide
+    assert abs(np.linalg.norm(q1[30:34]) - 1) < 1e-12
+
+
+def test_golden_env_steps(dyn, push_model):
+    from mopa_rl_b200.envs import push_reset_state
+    from oracle.env_oracle import PushEnvOracle
+
+    g = np.load(os.path.join(GOLD, "push_env_steps.npz"))
+    n = g["actions"].shape[1]
+    q0, v0 = push_reset_state(push_model, int(g["seed"]), np.arange(n), np.zeros(n, dtype=np.int64))
+    for e in range(n):
+        env = PushEnvOracle(push_model, dyn[0])
+        ob = env.reset_to(q0[e], v0[e])
+        assert ob.shape == (40,)
+        for s in range(3):
+            ob, r, d = env.step(g["actions"][s, e].astype(np.float64))
+            assert np.abs(env.qpos - g["qpos"][s, e]).max() < 1e-9 and np.abs(env.qvel - g["qvel"][s, e]).max() < 1e-9
+            assert abs(r - g["reward"][s, e]) < 1e-12 and not d
+
+
+def test_env_logic(dyn, push_model):
+    from mopa_rl_b200.envs import push_reset_state
+    from oracle.env_oracle import PushEnvOracle
+
+    q0, v0 = push_reset_state(push_model, 3, [0], [0])
+    env = PushEnvOracle(push_model, dyn[0], max_episode_steps=3)
+    ob = env.reset_to(q0[0], v0[0])
+    # observation layout (SawyerEnv._get_obs + push _get_obs): 7+7+2+2+3+4+3+3+4+3+2
+    assert np.allclose(ob[:7], q0[0][:7]) and np.allclose(ob[7:14], 0)
+    assert np.allclose(ob[35:38], ob[18:21] - ob[28:31]) and np.allclose(ob[38:40], ob[28:30] - ob[25:27])
+    assert np.isclose(np.linalg.norm(ob[21:25]), 1) and np.allclose(ob[31:35], [0, 0, 0, 1])      # quats xyzw
+    # direct step latches prev_state from the live qpos, clips the action to +-1 * ac_scale
+    env.step(np.full(7, 5.0))
+    assert np.allclose(env.prev_state, q0[0][:7] + 0.05)
+    # planner steps keep integrating the latched desired state and clip the displacement to +-ac_scale
+    live = env.qpos[:7].copy()
+    env.step(np.full(7, 0.2), is_planner=True)
+    assert np.allclose(env.prev_state, q0[0][:7] + 0.10) and not np.allclose(env.prev_state, live + 0.05)
+    _, _, done = env.step(np.zeros(7))
+    assert done and env.ep_len == 3                                                                   # max_episode_steps
+    # success: cube within distance_threshold of the target -> +150 and terminal
+    q = q0[0].copy()
+    q[27:29] = push_model.body_pos[push_model.body_name2id("target")][:2] + q[34:36] + [0.03, 0.0]
+    q[29] = 0.86
+    env2 = PushEnvOracle(push_model, dyn[0])
+    env2.reset_to(q, v0[0])
+    _, r, done = env2.step(np.zeros(7))
+    assert done and env2.success and r > 150

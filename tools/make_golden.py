@@ -1,0 +1,73 @@
+"""Generates the self-consistency golden fixtures under tests/golden/ from the CPU oracle.
+
+The reference has no tests or golden vectors of its own and cannot be executed
+here, so these pin the ORACLE (and through it the CUDA path) against accidental change; they are
+not MuJoCo / OMPL ground truth.  Re-run after an intentional change of the restated algorithms:
+
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import PUSH_INIT_QPOS, planner_setup, random_qpos  # noqa: E402
+from mopa_rl_b200.dynmodel import DynModel  # noqa: E402
+from mopa_rl_b200.envs import push_reset_state  # noqa: E402
+from mopa_rl_b200.model import load_model  # noqa: E402
+from oracle import oracle  # noqa: E402
+from oracle.env_oracle import PushEnvOracle  # noqa: E402
+
+out = os.path.join(ROOT, "tests", "golden")
+os.makedirs(out, exist_ok=True)
+oracle.build()
+m = load_model("SawyerPushObstacle-v0")
+ignored, passive, ref = planner_setup(m)
+scene = oracle.OracleScene(m, ignored, -0.002, "f32")
+scene64 = oracle.OracleScene(m, ignored, -0.002, "f64")
+
+# 1. state validity: seeded qpos -> result words (f32 oracle) and booleans of the f64 build
+q = random_qpos(m, 4096, 1234, ref)
+w32, d32 = scene.is_valid(q, True)
+w64 = scene64.is_valid(q)
+np.savez_compressed(os.path.join(out, "push_validity.npz"), seed=1234, active=q[:, ref].astype(np.float32), words_f32=w32,
+                    valid_f64=(w64 & 1).astype(np.uint8), min_dist_f32=d32.astype(np.float32))
+
+# 2. RRT-Connect traces: seeded (start, goal) -> status, iterations, node ids, waypoints
+adr, lo, hi, so2 = oracle.space_from_model(m, passive)
+pl = oracle.OraclePlanner(scene, adr, lo, hi, so2, 0.1, 0.005, seed=1234)
+cand = random_qpos(m, 400, 21, ref, spread=0.5)
+v = cand[(scene.is_valid(cand) & 1) == 1]
+starts, goals, status, iters, plen, ids, paths = [], [], [], [], [], [], []
+for i in range(16):
+    r = pl.plan(v[i], v[16 + i], 1000 + i, 400, 512)
+    starts.append(v[i][ref]), goals.append(v[16 + i][ref]), status.append(r["status"]), iters.append(r["iters"])
+    plen.append(len(r["path"]))
+    pad_ids = np.full(512, -1, np.int32)
+    pad_ids[: len(r["node_ids"])] = r["node_ids"]
+    ids.append(pad_ids)
+    pp = np.zeros((512, 7), np.float32)
+    pp[: len(r["path"])] = r["path"][:, ref]
+    paths.append(pp)
+np.savez_compressed(os.path.join(out, "push_rrt.npz"), starts=np.array(starts, np.float32), goals=np.array(goals, np.float32),
+                    keys=np.arange(16) + 1000, max_iter=400, status=np.array(status), iters=np.array(iters), path_len=np.array(plen),
+                    node_ids=np.array(ids), paths=np.array(paths))
+
+# 3. env.step trajectories: seeded resets + action table -> qpos / qvel / reward after each of 3 env steps
+dm = DynModel(m)
+n = 4
+q0, v0 = push_reset_state(m, 77, np.arange(n), np.zeros(n, dtype=np.int64))
+rng = np.random.default_rng(5)
+acts = rng.uniform(-1, 1, (3, n, 7)).astype(np.float32)
+Q, V, R = np.zeros((3, n, m.nq)), np.zeros((3, n, m.nv)), np.zeros((3, n))
+for e in range(n):
+    env = PushEnvOracle(m, dm)
+    env.reset_to(q0[e], v0[e])
+    for s in range(3):
+        _, R[s, e], _ = env.step(acts[s, e].astype(np.float64))
+        Q[s, e], V[s, e] = env.qpos, env.qvel
+np.savez_compressed(os.path.join(out, "push_env_steps.npz"), seed=77, actions=acts, qpos=Q, qvel=V, reward=R)
+print("golden fixtures written to", out, [f for f in os.listdir(out)])
