@@ -22,6 +22,7 @@ typedef struct mopa_dyn_desc {
     int32_t iterations;       /* constraint solver sweeps (option iterations) */
     double timestep;
     double gravity[3];
+    double tolerance;         /* solver early-termination threshold (option tolerance) */
     /* simulated bodies, parents first */
     const int32_t *b_parent;  /* [nb] index of the simulated parent, -1: static parent */
     const int32_t *b_bodyid;  /* [nb] mjModel body id */

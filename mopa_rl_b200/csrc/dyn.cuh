@@ -28,7 +28,7 @@ constexpr int DMAXC = 36;  // constraint rows
 
 struct DynDev {
     int nq, nv, nb, nd, nact, ngeom, npair, iterations;
-    double h, g[3];
+    double h, g[3], tolerance;
     int b_parent[DMAXB], b_jtype[DMAXB], b_qadr[DMAXB], b_vadr[DMAXB], b_dadr[DMAXB];
     double b_pos[DMAXB][3], b_quat[DMAXB][4], b_rootpos[DMAXB][3], b_rootquat[DMAXB][4], b_jaxis[DMAXB][3], b_jpos[DMAXB][3];
     double b_qpos0[DMAXB], b_mass[DMAXB], b_ipos[DMAXB][3], b_iquat[DMAXB][4], b_inertia[DMAXB][3];
@@ -56,7 +56,9 @@ struct CRow {
     double J[DMAXD];
     double pos, margin, solref[2], solimp[5], mu;
     int type;  // 0 limit, 1 contact normal, 2 tangent
+    int sig;   // identity of the row across substeps (warm start)
 };
+struct WarmStart { int n; int sig[DMAXC]; double f[DMAXC]; };  // constraint forces of the previous substep
 
 DYN_HD inline void d_q2m(double *M, const double *q) {
     double w = q[0], x = q[1], y = q[2], z = q[3];
@@ -148,7 +150,7 @@ DYN_HD inline void chol_factor(const double *M, const double *diag_add, double h
 // One mj_step.  qpos / qvel are FULL rows (nq / nv) updated in place.  `integrate` = false turns
 // the call into the kinematics + bias part of mj_forward.
 DYN_HD inline void dyn_substep(const DynDev &m, double *qpos, double *qvel, const double *ctrl, const double *applied, DynData &D,
-                               bool integrate) {
+                               bool integrate, WarmStart *warm = nullptr) {
     const int nb = m.nb, nd = m.nd;
     Sv6 S[DMAXD], vel[DMAXB], frc[DMAXB];
     SInert I[DMAXB];
@@ -305,7 +307,7 @@ DYN_HD inline void dyn_substep(const DynDev &m, double *qpos, double *qvel, cons
             CRow &r = rows[nc++];
             for (int j = 0; j < nd; j++) r.J[j] = 0;
             r.J[k] = side == 0 ? 1.0 : -1.0;
-            r.pos = dist; r.margin = m.d_margin[k]; r.type = 0; r.mu = 0;
+            r.pos = dist; r.margin = m.d_margin[k]; r.type = 0; r.mu = 0; r.sig = -(2 * k + side + 1);
             r.solref[0] = m.d_solref[k][0]; r.solref[1] = m.d_solref[k][1];
             for (int j = 0; j < 5; j++) r.solimp[j] = m.d_solimp[k][j];
         }
@@ -325,6 +327,11 @@ DYN_HD inline void dyn_substep(const DynDev &m, double *qpos, double *qvel, cons
             chol_solve(L, nd, MiJ[r]);
             f[r] = 0;
         }
+        if (warm && warm->n == nc) {
+            bool same = true;
+            for (int r = 0; r < nc; r++) if (warm->sig[r] != rows[r].sig) same = false;
+            if (same) for (int r = 0; r < nc; r++) f[r] = warm->f[r];
+        }
         for (int r = 0; r < nc; r++)
             for (int s = 0; s < nc; s++) {
                 double a = 0;
@@ -340,28 +347,47 @@ DYN_HD inline void dyn_substep(const DynDev &m, double *qpos, double *qvel, cons
             if (Rg[r] < DYN_MINVAL) Rg[r] = DYN_MINVAL;
             b[r] = ja - aref;
         }
+        double trM = 0;
+        for (int k = 0; k < nd; k++) trM += M[k * DMAXD + k];
+        const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
         for (int it = 0; it < m.iterations; it++) {
+            double imp = 0;
             for (int r = 0; r < nc; r++) {
                 if (rows[r].type >= 2) continue;
                 double res = b[r] + Rg[r] * f[r];
                 for (int s = 0; s < nc; s++) res += A[r * nc + s] * f[s];
-                const double fn = f[r] - res / (A[r * nc + r] + Rg[r]);
-                f[r] = fn > 0 ? fn : 0;
+                double fn = f[r] - res / (A[r * nc + r] + Rg[r]);
+                fn = fn > 0 ? fn : 0;
+                imp += 0.5 * (A[r * nc + r] + Rg[r]) * (fn - f[r]) * (fn - f[r]);
+                f[r] = fn;
                 if (rows[r].type == 1) {
                     for (int t = 1; t <= 2; t++) {
                         const int q = r + t;
                         double rs = b[q] + Rg[q] * f[q];
                         for (int s = 0; s < nc; s++) rs += A[q * nc + s] * f[s];
-                        f[q] = f[q] - rs / (A[q * nc + q] + Rg[q]);
+                        const double ft_new = f[q] - rs / (A[q * nc + q] + Rg[q]);
+                        imp += 0.5 * (A[q * nc + q] + Rg[q]) * (ft_new - f[q]) * (ft_new - f[q]);
+                        f[q] = ft_new;
                     }
                     const double lim = rows[r].mu * f[r], ft = sqrt(f[r + 1] * f[r + 1] + f[r + 2] * f[r + 2]);
-                    if (ft > lim) { const double sc = ft > DYN_MINVAL ? lim / ft : 0; f[r + 1] *= sc; f[r + 2] *= sc; }
+                    if (ft > lim) {
+                        const double sc = ft > DYN_MINVAL ? lim / ft : 0;
+                        for (int t = 1; t <= 2; t++) {
+                            const int q = r + t;
+                            const double fs = f[q] * sc;
+                            imp += 0.5 * (A[q * nc + q] + Rg[q]) * (fs - f[q]) * (fs - f[q]);
+                            f[q] = fs;
+                        }
+                    }
                 }
             }
+            if (scale * imp < m.tolerance) break;
         }
         for (int r = 0; r < nc; r++)
             for (int k = 0; k < nd; k++) fc[k] += rows[r].J[k] * f[r];
-    }
+        if (warm) { warm->n = nc; for (int r = 0; r < nc; r++) { warm->sig[r] = rows[r].sig; warm->f[r] = f[r]; } }
+    } else if (warm)
+        warm->n = 0;
     // semi-implicit Euler with implicit joint damping
     chol_factor(M, m.d_damping, m.h, nd, L);
     double rhs[DMAXD];

@@ -9,14 +9,25 @@
 // out plus the observation; the substeps never leave the SM.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/mopa_b200.h"
 #include "dyn.cuh"
 #include "contact.cuh"
 
+namespace mopa {
+struct DynDev;
+cudaError_t upload_env_model(int slot, const DynDev &h_model);
+cudaError_t launch_env_warp(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
+                            const int32_t *ids, cudaStream_t stream);
+}
+
 struct mopa_env {
     int device = 0;
+    int model_slot = 0;          // slot of this scene in the warp kernel's constant memory
+    int use_thread_kernel = 0;   // MOPA_ENV_KERNEL=thread selects the one-thread-per-env kernel (debug / comparison)
     mopa::DynDev *d_model = nullptr;
     mopa::DynDev h_model;
     mopa_sawyer_task task;
@@ -102,9 +113,11 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
         for (int k = 0; k < DMAXD; k++) applied[k] = 0.0;
         dyn_substep(m, q, v, ctrl, applied, D, false);
     } else {
+        WarmStart warm;
+        warm.n = 0;
         for (int s = 0; s < T.nsub; s++) {
             for (int k = 0; k < DMAXD; k++) applied[k] = (comp >> k) & 1u ? bias_prev[k] : 0.0;
-            dyn_substep(m, q, v, ctrl, applied, D, true);
+            dyn_substep(m, q, v, ctrl, applied, D, true, &warm);
             for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
         }
     }
@@ -156,7 +169,7 @@ __global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__
 static void fill_model(const mopa_dyn_desc *d, DynDev &m) {
     memset(&m, 0, sizeof(m));
     m.nq = d->nq; m.nv = d->nv; m.nb = d->nb; m.nd = d->nd; m.nact = d->nact; m.ngeom = d->ngeom; m.npair = d->npair;
-    m.iterations = d->iterations; m.h = d->timestep;
+    m.iterations = d->iterations; m.h = d->timestep; m.tolerance = d->tolerance;
     for (int k = 0; k < 3; k++) m.g[k] = d->gravity[k];
     for (int i = 0; i < d->nb; i++) {
         m.b_parent[i] = d->b_parent[i]; m.b_jtype[i] = d->b_jtype[i]; m.b_qadr[i] = d->b_qadr[i]; m.b_vadr[i] = d->b_vadr[i];
@@ -217,10 +230,15 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     mopa_env *e = new mopa_env();
     e->device = device;
     e->task = *task;
+    const char *kk = getenv("MOPA_ENV_KERNEL");
+    e->use_thread_kernel = (kk && std::string(kk) == "thread") ? 1 : 0;
     mopa::fill_model(dyn, e->h_model);
     cudaError_t err = cudaSetDevice(device);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_model, sizeof(mopa::DynDev));
     if (err == cudaSuccess) err = cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice);
+    static int next_slot = 0;
+    e->model_slot = (next_slot++) % 2;   // up to 2 live scenes per process share the constant bank round-robin
+    if (err == cudaSuccess) err = mopa::upload_env_model(e->model_slot, e->h_model);
     if (err != cudaSuccess) {
         mopa_set_error(std::string("mopa_env_create: ") + cudaGetErrorString(err) + " (a CUDA device is required; there is no CPU fallback)");
         delete e;
@@ -242,6 +260,7 @@ int mopa_env_enable_contacts(mopa_env *e, int32_t on) {
     e->h_model.enable_contacts = on ? 1 : 0;
     ENV_TRY(cudaSetDevice(e->device));
     ENV_TRY(cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice));
+    ENV_TRY(mopa::upload_env_model(e->model_slot, e->h_model));
     return MOPA_OK;
 }
 
@@ -249,8 +268,12 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
     if (!e || !buf || n < 0) { mopa_set_error("mopa_env_forward: bad argument"); return MOPA_ERR_ARG; }
     if (n == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    mopa::env_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_ids, n);
-    ENV_TRY(cudaGetLastError());
+    if (e->use_thread_kernel) {
+        mopa::env_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_ids, n);
+        ENV_TRY(cudaGetLastError());
+    } else {
+        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
+    }
     return MOPA_OK;
 }
 
@@ -259,9 +282,14 @@ int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_actio
     if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
     if (n_envs == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    mopa::env_step_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_action, action_stride,
-                                                                              d_is_planner, d_mask, n_envs);
-    ENV_TRY(cudaGetLastError());
+    if (e->use_thread_kernel) {
+        mopa::env_step_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_action, action_stride,
+                                                                                  d_is_planner, d_mask, n_envs);
+        ENV_TRY(cudaGetLastError());
+    } else {
+        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->task, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr,
+                                      (cudaStream_t)stream));
+    }
     return MOPA_OK;
 }
 

@@ -1,0 +1,793 @@
+// env.step on sm_100a, ONE WARP PER ENVIRONMENT (the production path).
+//
+// Same mathematics as dyn.cuh / contact.cuh (one mj_step equivalent per substep, 75 substeps per
+// env.step, reward / observation / _after_step fused; reference call sites in env_kernel.cu), but
+// every stage is spread over the 32 lanes of the warp that owns the environment and the
+// per-environment matrices live in a shared-memory workspace instead of per-thread local memory:
+//
+//   kinematics chain            uniform (all lanes), frames -> shared
+//   body inertias, RNE terms    lane = body          chain accumulations: lanes = vector components
+//   CRBA rows, bias, forces     lane = dof
+//   Cholesky (M, M + hD)        lane = row, right-looking
+//   contact broad phase         lanes stride the candidate pairs, ballot compaction
+//   contact narrow phase        lane = surviving pair
+//   constraint rows             lane = row: Jacobian, Y = L^-1 J^T (forward substitution), A = Y Y^T
+//   projected Gauss-Seidel      lane r owns residual g_r; row updates are broadcast by shuffle
+//
+// 4096 environments = 4096 warps, i.e. 8-9 resident warps per SM instead of < 1 for the
+// thread-per-env kernel.  Reductions change summation order, so agreement with the CPU oracle is
+// at rounding level (tests: 1e-5 absolute on qpos / qvel as BASELINE.json states).
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/mopa_b200.h"
+#include "dyn.cuh"
+#include "contact.cuh"
+
+namespace mopa {
+
+constexpr int WB = DMAXB;       // bodies
+constexpr int WD = DMAXD;       // dofs
+constexpr int WC = 32;          // constraint rows = lanes
+constexpr int WCP = 10;         // contact points kept per substep
+constexpr int WCAND = 64;       // broad-phase survivors kept per substep
+constexpr int YS = WD + 1;      // padded row stride of Y (bank-conflict free, lane = row)
+constexpr int MS = WD + 1;
+
+struct WarpKin {
+    double xpos[WB][3], xquat[WB][4], xmat[WB][9];
+    double S[WD][6];
+    double vel[WB][6], frc[WB][6];
+    double inert[WB][13];
+};
+struct WarpWS {
+    double q[64], v[64];
+    union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
+        WarpKin k;
+        double A[WC * WC];   // A[s * WC + r] = A_rs (column s contiguous over lanes r)
+    };
+    double kxpos[4][3], kxquat[4][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
+    double rD[WC];
+    double M[WD * MS], L[WD * MS];
+    double qd[WD], bias[WD], tau[WD], qacc0[WD], fc[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
+    double Y[WC * YS];
+    double f[WC];
+    double gpos[DMAXG][3];
+    double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
+    int cga[WCP], cgb[WCP], csig[WCP];
+    int wsig[WC];            // warm start: row identities and forces of the previous substep
+    double wf[WC];
+    int wn;
+    int cand[WCAND];
+    int ncand, ncp;
+};
+
+#define FULL 0xffffffffu
+
+// scene constants: uniform reads go through the constant cache instead of global loads
+constexpr int ENV_MODEL_SLOTS = 2;
+__constant__ DynDev c_models[ENV_MODEL_SLOTS];
+
+__device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(FULL, x, src); }
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+// ---- lane = row right-looking Cholesky of (M + hs * diag) into L (lower, stride MS)
+__device__ __noinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane) {
+    if (lane < nd)
+        for (int k = 0; k <= lane; k++) L[lane * MS + k] = M[lane * MS + k] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
+    __syncwarp();
+    for (int j = 0; j < nd; j++) {
+        const double d = sqrt(L[j * MS + j]);
+        __syncwarp();
+        if (lane == j) L[j * MS + j] = d;
+        if (lane > j && lane < nd) L[lane * MS + j] = L[lane * MS + j] / d;
+        __syncwarp();
+        if (lane > j && lane < nd) {
+            const double lij = L[lane * MS + j];
+            for (int k = j + 1; k <= lane; k++) L[lane * MS + k] -= lij * L[k * MS + j];
+        }
+        __syncwarp();
+    }
+}
+// single right-hand side, lane-parallel column-oriented substitution; x (shared, nd entries) in place
+__device__ __noinline__ void w_solve(const double *L, int nd, double *x, int lane) {
+    for (int i = 0; i < nd; i++) {
+        const double xi = x[i] / L[i * MS + i];
+        __syncwarp();
+        if (lane == i) x[i] = xi;
+        if (lane > i && lane < nd) x[lane] -= L[lane * MS + i] * xi;
+        __syncwarp();
+    }
+    for (int i = nd - 1; i >= 0; i--) {
+        const double xi = x[i] / L[i * MS + i];
+        __syncwarp();
+        if (lane == i) x[i] = xi;
+        if (lane < i) x[lane] -= L[i * MS + lane] * xi;
+        __syncwarp();
+    }
+}
+
+// Out-of-line wrappers keep one copy of the big routines in the instruction stream (the kernel is
+// instruction-cache bound otherwise: 9 warps per SM walk different phases of a long program).
+__device__ __noinline__ int pair_contacts_ni(CPoint *out, const CGeom &ga, const CGeom &gb, double margin) {
+    return pair_contacts(out, ga, gb, margin);
+}
+__device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const double *solimp, double pos, double margin, double &K,
+                                    double &B, double &imp) {
+    d_kbi(m, solref, solimp, pos, margin, K, B, imp);
+}
+
+// One mj_step for the warp's environment.  W.q / W.v hold the state, W.ctrl the controls,
+// `comp` the dofs whose qfrc_applied is the previous qfrc_bias.  integrate=false: kinematics + bias only.
+// `sync`: the warps of a CTA walk the stages in step (CTA barrier between stages) so that they share
+// instruction-cache lines; `active` = false warps only take part in the barriers.
+#define STAGE_SYNC() do { if (sync) __syncthreads(); } while (0)
+__device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int *keep,
+                                       bool active, bool sync) {
+    const int nb = m.nb, nd = m.nd;
+    if (!active) {   // barrier-only participant: one barrier per stage boundary below
+        for (int k = 0; k < 7; k++) STAGE_SYNC();
+        return;
+    }
+    if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
+    __syncwarp();
+    // ---- kinematics chain (uniform across lanes), joint motion axes
+    for (int i = 0; i < nb; i++) {
+        double Pp[3], Pq[4], PM[9];
+        const int p = m.b_parent[i];
+        if (p >= 0) {
+            for (int k = 0; k < 3; k++) Pp[k] = W.k.xpos[p][k];
+            for (int k = 0; k < 4; k++) Pq[k] = W.k.xquat[p][k];
+            for (int k = 0; k < 9; k++) PM[k] = W.k.xmat[p][k];
+        } else {
+            for (int k = 0; k < 3; k++) Pp[k] = m.b_rootpos[i][k];
+            for (int k = 0; k < 4; k++) Pq[k] = m.b_rootquat[i][k];
+            d_q2m(PM, Pq);
+        }
+        double pos[3], quat[4], t[3], R[9], bp[3] = {m.b_pos[i][0], m.b_pos[i][1], m.b_pos[i][2]};
+        double bq[4] = {m.b_quat[i][0], m.b_quat[i][1], m.b_quat[i][2], m.b_quat[i][3]};
+        d_mv(t, PM, bp);
+        for (int k = 0; k < 3; k++) pos[k] = Pp[k] + t[k];
+        d_qmul(quat, Pq, bq);
+        const int jt = m.b_jtype[i], da = m.b_dadr[i];
+        double s0[6];
+        if (jt == 3) {
+            double anchor[3], ql[4], ax[3], qn[4], jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
+            double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+            d_q2m(R, quat);
+            d_mv(t, R, jp);
+            for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t[k];
+            const double ang = W.q[m.b_qadr[i]] - m.b_qpos0[i], sn = sin(0.5 * ang), cs = cos(0.5 * ang);
+            ql[0] = cs; ql[1] = sn * ja[0]; ql[2] = sn * ja[1]; ql[3] = sn * ja[2];
+            d_qmul(qn, quat, ql);
+            for (int k = 0; k < 4; k++) quat[k] = qn[k];
+            d_q2m(R, quat);
+            d_mv(t, R, jp);
+            for (int k = 0; k < 3; k++) pos[k] = anchor[k] - t[k];
+            d_mv(ax, R, ja);
+            for (int k = 0; k < 3; k++) s0[k] = ax[k];
+            d_cross(s0 + 3, anchor, ax);
+            if (lane < 6) W.k.S[da][lane] = s0[lane];
+        } else if (jt == 2) {
+            double ax[3], ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+            d_q2m(R, quat);
+            d_mv(ax, R, ja);
+            const double dq = W.q[m.b_qadr[i]] - m.b_qpos0[i];
+            for (int k = 0; k < 3; k++) { pos[k] += ax[k] * dq; s0[k] = 0; s0[3 + k] = ax[k]; }
+            if (lane < 6) W.k.S[da][lane] = s0[lane];
+        } else if (jt == 0) {
+            const int a = m.b_qadr[i];
+            for (int k = 0; k < 3; k++) pos[k] = W.q[a + k];
+            const double n = sqrt(W.q[a + 3] * W.q[a + 3] + W.q[a + 4] * W.q[a + 4] + W.q[a + 5] * W.q[a + 5] + W.q[a + 6] * W.q[a + 6]);
+            for (int k = 0; k < 4; k++) quat[k] = W.q[a + 3 + k] / n;
+            d_q2m(R, quat);
+            if (lane < 3) {
+                for (int c = 0; c < 6; c++) W.k.S[da + lane][c] = 0;
+                W.k.S[da + lane][3 + lane] = 1;
+                double e[3] = {R[lane], R[3 + lane], R[6 + lane]}, cr[3];
+                d_cross(cr, pos, e);
+                for (int c = 0; c < 3; c++) { W.k.S[da + 3 + lane][c] = e[c]; W.k.S[da + 3 + lane][3 + c] = cr[c]; }
+            }
+        }
+        d_q2m(R, quat);
+        if (lane < 3) W.k.xpos[i][lane] = pos[lane];
+        if (lane < 4) W.k.xquat[i][lane] = quat[lane];
+        if (lane < 9) W.k.xmat[i][lane] = R[lane];
+        __syncwarp();
+    }
+    if (lane < 4) {
+        const int b = keep[lane];
+        for (int k = 0; k < 3; k++) W.kxpos[lane][k] = W.k.xpos[b][k];
+        for (int k = 0; k < 4; k++) W.kxquat[lane][k] = W.k.xquat[b][k];
+        for (int k = 0; k < 9; k++) W.kxmat[lane][k] = W.k.xmat[b][k];
+    }
+    STAGE_SYNC();   // 1: kinematics done
+    // ---- spatial inertia about the origin, lane = body
+    if (lane < nb) {
+        const int i = lane;
+        double R[9], c[3], t[3], Mi[9], Ri[9], Iw[9], ip[3] = {m.b_ipos[i][0], m.b_ipos[i][1], m.b_ipos[i][2]};
+        double iq[4] = {m.b_iquat[i][0], m.b_iquat[i][1], m.b_iquat[i][2], m.b_iquat[i][3]};
+        for (int k = 0; k < 9; k++) R[k] = W.k.xmat[i][k];
+        d_mv(t, R, ip);
+        for (int k = 0; k < 3; k++) c[k] = W.k.xpos[i][k] + t[k];
+        d_q2m(Mi, iq);
+        for (int r = 0; r < 3; r++)
+            for (int cc = 0; cc < 3; cc++) Ri[3 * r + cc] = R[3 * r] * Mi[cc] + R[3 * r + 1] * Mi[3 + cc] + R[3 * r + 2] * Mi[6 + cc];
+        const double i0 = m.b_inertia[i][0], i1 = m.b_inertia[i][1], i2 = m.b_inertia[i][2];
+        for (int r = 0; r < 3; r++)
+            for (int cc = 0; cc < 3; cc++) Iw[3 * r + cc] = Ri[3 * r] * i0 * Ri[3 * cc] + Ri[3 * r + 1] * i1 * Ri[3 * cc + 1] + Ri[3 * r + 2] * i2 * Ri[3 * cc + 2];
+        const double ms = m.b_mass[i], cc2 = d_dot(c, c);
+        W.k.inert[i][0] = ms;
+        for (int k = 0; k < 3; k++) W.k.inert[i][1 + k] = ms * c[k];
+        for (int r = 0; r < 3; r++)
+            for (int cc = 0; cc < 3; cc++) W.k.inert[i][4 + 3 * r + cc] = Iw[3 * r + cc] + ms * ((r == cc ? cc2 : 0) - c[r] * c[cc]);
+    }
+    __syncwarp();
+    // ---- velocities down the chain, lanes = components
+    for (int i = 0; i < nb; i++) {
+        const int p = m.b_parent[i], jt = m.b_jtype[i], da = m.b_dadr[i];
+        if (lane < 6) {
+            double x = p >= 0 ? W.k.vel[p][lane] : 0.0;
+            const int ndj = jt < 0 ? 0 : (jt == 0 ? 6 : 1);
+            for (int k = 0; k < ndj; k++) x += W.k.S[da + k][lane] * W.qd[da + k];
+            W.k.vel[i][lane] = x;
+        }
+        __syncwarp();
+    }
+    // ---- RNE: local acceleration terms (lane = body), chain sum, body forces, backward sum, bias
+    if (lane < nb) {
+        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i];
+        Sv6 vi, acc;
+        for (int k = 0; k < 3; k++) { vi.w[k] = W.k.vel[i][k]; vi.v[k] = W.k.vel[i][3 + k]; acc.w[k] = 0; acc.v[k] = 0; }
+        const int ndj = jt < 0 ? 0 : (jt == 0 ? 6 : 1);
+        for (int k = 0; k < ndj; k++) {
+            if (jt == 0 && k < 3) continue;
+            Sv6 s, sd;
+            for (int c = 0; c < 3; c++) { s.w[c] = W.k.S[da + k][c]; s.v[c] = W.k.S[da + k][3 + c]; }
+            sv_cross_motion(sd, vi, s);
+            for (int c = 0; c < 3; c++) { acc.w[c] += sd.w[c] * W.qd[da + k]; acc.v[c] += sd.v[c] * W.qd[da + k]; }
+        }
+        for (int c = 0; c < 3; c++) { W.k.frc[i][c] = acc.w[c]; W.k.frc[i][3 + c] = acc.v[c]; }
+    }
+    __syncwarp();
+    for (int i = 0; i < nb; i++) {
+        const int p = m.b_parent[i];
+        if (lane < 6) W.k.frc[i][lane] += p >= 0 ? W.k.frc[p][lane] : (lane >= 3 ? -m.g[lane - 3] : 0.0);
+        __syncwarp();
+    }
+    if (lane < nb) {
+        const int i = lane;
+        Sv6 vi, acc, Ia, Iv, vIv;
+        SInert I;
+        I.m = W.k.inert[i][0];
+        for (int k = 0; k < 3; k++) { I.h[k] = W.k.inert[i][1 + k]; vi.w[k] = W.k.vel[i][k]; vi.v[k] = W.k.vel[i][3 + k]; acc.w[k] = W.k.frc[i][k]; acc.v[k] = W.k.frc[i][3 + k]; }
+        for (int k = 0; k < 9; k++) I.I[k] = W.k.inert[i][4 + k];
+        inert_apply(Ia, I, acc);
+        inert_apply(Iv, I, vi);
+        sv_cross_force(vIv, vi, Iv);
+        for (int c = 0; c < 3; c++) { W.k.frc[i][c] = Ia.w[c] + vIv.w[c]; W.k.frc[i][3 + c] = Ia.v[c] + vIv.v[c]; }
+    }
+    __syncwarp();
+    for (int i = nb - 1; i >= 0; i--) {
+        const int p = m.b_parent[i];
+        if (p >= 0 && lane < 6) W.k.frc[p][lane] += W.k.frc[i][lane];
+        __syncwarp();
+    }
+    if (lane < nd) {
+        const int b = m.d_body[lane];
+        double s = 0;
+        for (int c = 0; c < 6; c++) s += W.k.S[lane][c] * W.k.frc[b][c];
+        W.bias[lane] = s;
+    }
+    __syncwarp();
+    if (!integrate) return;
+    STAGE_SYNC();   // 2: RNE done
+    // ---- composite inertias (lanes = 13 components), joint-space inertia (lane = dof)
+    for (int i = nb - 1; i >= 0; i--) {
+        const int p = m.b_parent[i];
+        if (p >= 0 && lane < 13) W.k.inert[p][lane] += W.k.inert[i][lane];
+        __syncwarp();
+    }
+    for (int e = lane; e < WD * MS; e += 32) W.M[e] = 0;
+    __syncwarp();
+    if (lane < nd) {
+        const int i = lane, b = m.d_body[i];
+        SInert I;
+        Sv6 s, F;
+        I.m = W.k.inert[b][0];
+        for (int k = 0; k < 3; k++) { I.h[k] = W.k.inert[b][1 + k]; s.w[k] = W.k.S[i][k]; s.v[k] = W.k.S[i][3 + k]; }
+        for (int k = 0; k < 9; k++) I.I[k] = W.k.inert[b][4 + k];
+        inert_apply(F, I, s);
+        for (int j = i; j >= 0; j = m.d_parent[j]) {
+            double dsum = 0;
+            for (int c = 0; c < 3; c++) dsum += W.k.S[j][c] * F.w[c];
+            for (int c = 0; c < 3; c++) dsum += W.k.S[j][3 + c] * F.v[c];
+            if (j == i) dsum += m.d_armature[i];
+            W.M[i * MS + j] = dsum;
+            W.M[j * MS + i] = dsum;
+        }
+    }
+    __syncwarp();
+    // ---- forces
+    if (lane < nd) W.tau[lane] = -m.d_damping[lane] * W.qd[lane] - W.bias[lane] + (((comp >> lane) & 1u) ? W.bias_prev[lane] : 0.0);
+    __syncwarp();
+    if (lane < m.nact) {
+        const int a = lane, k = m.a_dof[a];
+        double c = W.ctrl[a];
+        if (m.a_ctrllimited[a]) c = c < m.a_ctrlrange[a][0] ? m.a_ctrlrange[a][0] : (c > m.a_ctrlrange[a][1] ? m.a_ctrlrange[a][1] : c);
+        const double qq = m.d_qadr[k] >= 0 ? W.q[m.d_qadr[k]] : 0.0;
+        double f;
+        if (m.a_kind[a] == 1) f = m.a_kp[a] * c - m.a_kp[a] * (m.a_gear[a] * qq);
+        else if (m.a_kind[a] == 2) f = m.a_kv[a] * c - m.a_kv[a] * (m.a_gear[a] * W.qd[k]);
+        else f = c;
+        if (m.a_forcelimited[a]) f = f < m.a_forcerange[a][0] ? m.a_forcerange[a][0] : (f > m.a_forcerange[a][1] ? m.a_forcerange[a][1] : f);
+        W.tau[k] += m.a_gear[a] * f;   // one actuator per dof in the scenes compiled here
+    }
+    __syncwarp();
+    STAGE_SYNC();   // 3: inertia matrix and forces done
+    w_chol(W.M, nullptr, 0.0, nd, W.L, lane);
+    if (lane < nd) W.qacc0[lane] = W.tau[lane];
+    __syncwarp();
+    w_solve(W.L, nd, W.qacc0, lane);
+
+    STAGE_SYNC();   // 4: unconstrained acceleration done
+    // ---- constraint rows.  Limits first (dof order), then contacts (pair order).
+    int nlim = 0;
+    {
+        // each lane inspects one (dof, side); compaction keeps dof-major order
+        const int k = lane >> 1, side = lane & 1;
+        bool act = false;
+        double dist = 0;
+        if (k < nd && m.d_limited[k] && m.d_qadr[k] >= 0) {
+            const double qq = W.q[m.d_qadr[k]];
+            dist = side == 0 ? qq - m.d_range[k][0] : m.d_range[k][1] - qq;
+            act = dist < m.d_margin[k];
+        }
+        const unsigned mask = __ballot_sync(FULL, act);
+        nlim = __popc(mask);
+        const int r = __popc(mask & ((1u << lane) - 1));
+        if (act) {
+            for (int j = 0; j < nd; j++) W.Y[r * YS + j] = 0;
+            W.Y[r * YS + k] = side == 0 ? 1.0 : -1.0;
+        }
+        // row parameters are kept in registers of the lane that owns the row: gather them below
+        // by recomputing from (k, side) of the r-th set bit
+        __syncwarp();
+    }
+    int ncp = 0;
+    if (m.enable_contacts && m.npair > 0) {
+        for (int g = lane; g < m.ngeom; g += 32) {
+            const int body = m.g_body[g];
+            if (body < 0) { for (int k = 0; k < 3; k++) W.gpos[g][k] = m.g_pos[g][k]; }
+            else {
+                const double *X = W.k.xmat[body];
+                for (int k = 0; k < 3; k++)
+                    W.gpos[g][k] = W.k.xpos[body][k] + X[3 * k] * m.g_pos[g][0] + X[3 * k + 1] * m.g_pos[g][1] + X[3 * k + 2] * m.g_pos[g][2];
+            }
+        }
+        __syncwarp();
+        int ncand = 0;
+        for (int base = 0; base < m.npair; base += 32) {
+            const int p = base + lane;
+            bool keep = false;
+            if (p < m.npair) {
+                const int a = m.p_g1[p], b = m.p_g2[p];
+                keep = true;
+                if (m.g_type[a] != 0 && m.g_type[b] != 0) {
+                    const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
+                    const double d[3] = {W.gpos[b][0] - W.gpos[a][0], W.gpos[b][1] - W.gpos[a][1], W.gpos[b][2] - W.gpos[a][2]};
+                    const double bound = m.g_rbound[a] + m.g_rbound[b] + margin;
+                    keep = !(d_dot(d, d) > bound * bound);
+                }
+            }
+            const unsigned mask = __ballot_sync(FULL, keep);
+            const int pos = ncand + __popc(mask & ((1u << lane) - 1));
+            if (keep && pos < WCAND) W.cand[pos] = p;
+            ncand += __popc(mask);
+        }
+        if (ncand > WCAND) ncand = WCAND;
+        __syncwarp();
+        const int maxcp = min(WCP, (WC - nlim) / 3);
+        for (int base = 0; base < ncand; base += 32) {
+            const int ci = base + lane;
+            CPoint cps[4];
+            int nc = 0, a = 0, b = 0;
+            double margin = 0;
+            if (ci < ncand) {
+                const int p = W.cand[ci];
+                a = m.p_g1[p]; b = m.p_g2[p];
+                margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
+                double gR[2][9], gc[2][3], gs[2][3];
+                for (int side = 0; side < 2; side++) {
+                    const int g = side ? b : a, body = m.g_body[g];
+                    double Rl[9], gq[4] = {m.g_quat[g][0], m.g_quat[g][1], m.g_quat[g][2], m.g_quat[g][3]};
+                    d_q2m(Rl, gq);
+                    for (int k = 0; k < 3; k++) { gc[side][k] = W.gpos[g][k]; gs[side][k] = m.g_size[g][k]; }
+                    if (body < 0) { for (int k = 0; k < 9; k++) gR[side][k] = Rl[k]; }
+                    else {
+                        const double *X = W.k.xmat[body];
+                        for (int r = 0; r < 3; r++)
+                            for (int c = 0; c < 3; c++) gR[side][3 * r + c] = X[3 * r] * Rl[c] + X[3 * r + 1] * Rl[3 + c] + X[3 * r + 2] * Rl[6 + c];
+                    }
+                }
+                CGeom ga{gc[0], gR[0], gs[0], m.g_type[a]}, gb{gc[1], gR[1], gs[1], m.g_type[b]};
+                nc = pair_contacts_ni(cps, ga, gb, margin);
+            }
+            // ordered compaction of the contact points of this round
+            int incl = nc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int start = ncp + incl - nc;
+            for (int qn = 0; qn < nc; qn++) {
+                const int slot = start + qn;
+                if (slot >= maxcp) break;
+                for (int k = 0; k < 3; k++) { W.cpos[slot][k] = cps[qn].pos[k]; W.cn[slot][k] = cps[qn].n[k]; }
+                W.cdist[slot] = cps[qn].dist;
+                W.cmargin[slot] = margin;
+                W.cmu[slot] = m.g_friction[a][0] > m.g_friction[b][0] ? m.g_friction[a][0] : m.g_friction[b][0];
+                for (int k = 0; k < 2; k++) W.csolref[slot][k] = 0.5 * (m.g_solref[a][k] + m.g_solref[b][k]);
+                for (int k = 0; k < 5; k++) W.csolimp[slot][k] = 0.5 * (m.g_solimp[a][k] + m.g_solimp[b][k]);
+                W.cga[slot] = a; W.cgb[slot] = b;
+                W.csig[slot] = W.cand[ci] * 16 + qn * 4;
+            }
+            ncp += __shfl_sync(FULL, incl, 31);
+            if (ncp >= maxcp) { ncp = maxcp; break; }
+        }
+        __syncwarp();
+    }
+    ncon_out = ncp;
+    STAGE_SYNC();   // 5: contact points done
+    const int nc = nlim + 3 * ncp;
+    double fcv = 0.0;  // lane k: constraint force on dof k
+    if (nc > 0) {
+        // ---- lane = row: parameters, Jacobian (contacts), reference acceleration
+        const int r = lane;
+        int type = -1, sig = 0;
+        double pos = 0, margin = 0, mu = 0, solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2};
+        if (r < nlim) {
+            // recover (dof, side) of the r-th active limit in dof-major order
+            int cnt = 0;
+            for (int k = 0; k < nd; k++) {
+                if (!m.d_limited[k] || m.d_qadr[k] < 0) continue;
+                const double qq = W.q[m.d_qadr[k]];
+                for (int side = 0; side < 2; side++) {
+                    const double dist = side == 0 ? qq - m.d_range[k][0] : m.d_range[k][1] - qq;
+                    if (dist < m.d_margin[k]) {
+                        if (cnt == r) {
+                            type = 0; pos = dist; margin = m.d_margin[k]; sig = -(2 * k + side + 1);
+                            solref[0] = m.d_solref[k][0]; solref[1] = m.d_solref[k][1];
+                            for (int j = 0; j < 5; j++) solimp[j] = m.d_solimp[k][j];
+                        }
+                        cnt++;
+                    }
+                }
+            }
+        } else if (r < nc) {
+            const int c = (r - nlim) / 3, dirn = (r - nlim) % 3;
+            type = dirn == 0 ? 1 : 2;
+            sig = W.csig[c] + dirn;
+            pos = W.cdist[c]; margin = W.cmargin[c]; mu = W.cmu[c];
+            solref[0] = W.csolref[c][0]; solref[1] = W.csolref[c][1];
+            for (int j = 0; j < 5; j++) solimp[j] = W.csolimp[c][j];
+            double n[3] = {W.cn[c][0], W.cn[c][1], W.cn[c][2]}, t1[3], t2[3], ref[3] = {0, 0, 0}, cp[3] = {W.cpos[c][0], W.cpos[c][1], W.cpos[c][2]};
+            ref[fabs(n[0]) < 0.7 ? 0 : 1] = 1.0;
+            d_cross(t1, n, ref);
+            const double l = sqrt(d_dot(t1, t1));
+            for (int k = 0; k < 3; k++) t1[k] /= l;
+            d_cross(t2, n, t1);
+            const double *dir = dirn == 0 ? n : (dirn == 1 ? t1 : t2);
+            for (int j = 0; j < nd; j++) W.Y[r * YS + j] = 0;
+            for (int side = 0; side < 2; side++) {
+                int body = m.g_body[side ? W.cgb[c] : W.cga[c]];
+                const double sg = side ? 1.0 : -1.0;
+                while (body >= 0 && m.b_jtype[body] < 0) body = m.b_parent[body];
+                if (body < 0) continue;
+                for (int k = m.b_dadr[body] + (m.b_jtype[body] == 0 ? 5 : 0); k >= 0; k = m.d_parent[k]) {
+                    double t[3], j3[3], sw[3] = {W.k.S[k][0], W.k.S[k][1], W.k.S[k][2]};
+                    d_cross(t, sw, cp);
+                    for (int cc = 0; cc < 3; cc++) j3[cc] = W.k.S[k][3 + cc] + t[cc];
+                    W.Y[r * YS + k] += sg * d_dot(dir, j3);
+                }
+            }
+        }
+        double jv = 0, ja = 0;
+        if (r < nc)
+            for (int k = 0; k < nd; k++) { jv += W.Y[r * YS + k] * W.qd[k]; ja += W.Y[r * YS + k] * W.qacc0[k]; }
+        // ---- Y = L^-1 J^T (forward substitution, lane = row), A = Y Y^T
+        if (r < nc) {
+            double *yr = W.Y + r * YS;
+            for (int k = 0; k < nd; k++) {
+                double s = yr[k];
+                for (int j = 0; j < k; j++) s -= W.L[k * MS + j] * yr[j];
+                yr[k] = s / W.L[k * MS + k];
+            }
+            for (int k = nd; k < WD; k++) yr[k] = 0.0;
+        }
+        __syncwarp();
+        double diag = 0;
+        for (int s = 0; s < nc; s++) {
+            double a = 0;
+            if (r < nc)
+                for (int k = 0; k < nd; k++) a += W.Y[r * YS + k] * W.Y[s * YS + k];
+            W.A[s * WC + r] = a;
+            if (s == r) diag = a;
+        }
+        double Rg = 0, b = 0, inv = 0;
+        if (r < nc) {
+            double K, B, imp;
+            kbi_ni(m, solref, solimp, pos, margin, K, B, imp);
+            const double aref = type <= 1 ? (-B * jv - K * imp * (pos - margin)) : (-B * jv);
+            Rg = (1 - imp) / imp * diag;
+            if (Rg < DYN_MINVAL) Rg = DYN_MINVAL;
+            b = ja - aref;
+            inv = 1.0 / (diag + Rg);
+        }
+        __syncwarp();
+        // ---- projected Gauss-Seidel; lane r keeps g_r = (A f + b)_r and f_r.  Stops when the scaled
+        // cost improvement of a sweep drops below `tolerance` (MuJoCo's termination rule).
+        W.rD[lane] = diag + Rg;
+        double trM = (lane < nd) ? W.M[lane * MS + lane] : 0.0;
+        trM = warp_sum(trM);
+        const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
+        __syncwarp();
+        double g = b, f = 0.0;
+        {   // warm start from the previous substep when the constraint set is unchanged
+            const bool same = __all_sync(FULL, r >= nc || W.wsig[r] == sig) && W.wn == nc;
+            if (same) {
+                f = (r < nc) ? W.wf[r] : 0.0;
+                for (int s = 0; s < nc; s++) g += W.A[s * WC + r] * shfl_d(f, s);
+            }
+        }
+        const unsigned types = __ballot_sync(FULL, type == 1);  // rows that start a contact
+        for (int it = 0; it < m.iterations; it++) {
+            double imp = 0.0;
+            for (int s = 0; s < nc; s++) {
+                const bool is_contact = (types >> s) & 1u;
+                if (!is_contact && s >= nlim) continue;   // tangent rows are handled with their normal row
+                double dl = 0.0;
+                if (lane == s) {
+                    double fn = f - (g + Rg * f) * inv;
+                    fn = fn > 0 ? fn : 0;
+                    dl = fn - f;
+                    f = fn;
+                }
+                dl = shfl_d(dl, s);
+                imp += 0.5 * W.rD[s] * dl * dl;
+                g += W.A[s * WC + r] * dl;
+                if (is_contact) {
+#pragma unroll 1
+                    for (int t = 1; t <= 2; t++) {
+                        double dt = 0.0;
+                        if (lane == s + t) { const double fn = f - (g + Rg * f) * inv; dt = fn - f; f = fn; }
+                        dt = shfl_d(dt, s + t);
+                        imp += 0.5 * W.rD[s + t] * dt * dt;
+                        g += W.A[(s + t) * WC + r] * dt;
+                    }
+                    const double fnn = shfl_d(f, s), f1 = shfl_d(f, s + 1), f2 = shfl_d(f, s + 2), mus = shfl_d(mu, s);
+                    const double lim = mus * fnn, ft = sqrt(f1 * f1 + f2 * f2);
+                    if (ft > lim) {
+                        const double sc = ft > DYN_MINVAL ? lim / ft : 0.0;
+#pragma unroll 1
+                        for (int t = 1; t <= 2; t++) {
+                            double dt = 0.0;
+                            if (lane == s + t) { const double fn = f * sc; dt = fn - f; f = fn; }
+                            dt = shfl_d(dt, s + t);
+                            imp += 0.5 * W.rD[s + t] * dt * dt;
+                            g += W.A[(s + t) * WC + r] * dt;
+                        }
+                    }
+                }
+            }
+            if (scale * imp < m.tolerance) break;
+        }
+        W.wsig[lane] = sig;
+        W.wf[lane] = f;
+        if (lane == 0) W.wn = nc;
+        // ---- J^T f = L (Y^T f)
+        W.f[lane] = (r < nc) ? f : 0.0;
+        __syncwarp();
+        if (lane < nd) {
+            double zz = 0;
+            for (int s = 0; s < nc; s++) zz += W.Y[s * YS + lane] * W.f[s];
+            W.z[lane] = zz;
+        }
+        __syncwarp();
+        if (lane < nd) {
+            double s = 0;
+            for (int j = 0; j <= lane; j++) s += W.L[lane * MS + j] * W.z[j];
+            fcv = s;
+        }
+        __syncwarp();
+    }
+    else if (lane == 0)
+        W.wn = 0;
+    STAGE_SYNC();   // 6: constraint forces done
+    // ---- semi-implicit Euler with implicit joint damping
+    if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
+    __syncwarp();
+    w_chol(W.M, m.d_damping, m.h, nd, W.L, lane);
+    w_solve(W.L, nd, W.rhs, lane);
+    if (lane < nd) {
+        W.qd[lane] += m.h * W.rhs[lane];
+        W.v[m.d_vadr[lane]] = W.qd[lane];
+    }
+    __syncwarp();
+    if (lane < nb) {
+        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i], a = m.b_qadr[i];
+        if (jt == 2 || jt == 3) W.q[a] += m.h * W.qd[da];
+        else if (jt == 0) {
+            for (int k = 0; k < 3; k++) W.q[a + k] += m.h * W.qd[da + k];
+            const double w[3] = {W.qd[da + 3], W.qd[da + 4], W.qd[da + 5]}, n = sqrt(d_dot(w, w)), ang = n * m.h;
+            if (ang > 0) {
+                const double sn = sin(0.5 * ang) / n, dq[4] = {cos(0.5 * ang), w[0] * sn, w[1] * sn, w[2] * sn};
+                double qn[4], q0[4] = {W.q[a + 3], W.q[a + 4], W.q[a + 5], W.q[a + 6]};
+                d_qmul(qn, q0, dq);
+                const double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+                for (int k = 0; k < 4; k++) W.q[a + 3 + k] = qn[k] / nn;
+            }
+        }
+    }
+    __syncwarp();
+    STAGE_SYNC();   // 7: state advanced
+}
+
+// kept frame slots: 0 = end-effector body, 1 = cube, 2 = right claw, 3 = left claw
+__device__ __forceinline__ void w_site(double *out, const WarpWS &W, int slot, const double *local) {
+    double t[3];
+    d_mv(t, W.kxmat[slot], local);
+    for (int k = 0; k < 3; k++) out[k] = W.kxpos[slot][k] + t[k];
+}
+
+__device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS &W, float *obs, int lane) {
+    if (lane != 0) return;
+    int o = 0;
+    for (int k = 0; k < 7; k++) obs[o++] = (float)W.q[T.arm_qadr[k]];
+    for (int k = 0; k < 7; k++) obs[o++] = (float)W.v[T.arm_vadr[k]];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)W.q[T.grip_qadr[k]];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)W.v[T.grip_vadr[k]];
+    double eef[3];
+    w_site(eef, W, 0, T.site_grip);
+    for (int k = 0; k < 3; k++) obs[o++] = (float)eef[k];
+    const double *eq = W.kxquat[0];
+    obs[o++] = (float)eq[1]; obs[o++] = (float)eq[2]; obs[o++] = (float)eq[3]; obs[o++] = (float)eq[0];
+    const double target[3] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]], T.target_base[2]};
+    for (int k = 0; k < 3; k++) obs[o++] = (float)target[k];
+    const double *cube = W.kxpos[1], *cq = W.kxquat[1];
+    for (int k = 0; k < 3; k++) obs[o++] = (float)cube[k];
+    obs[o++] = (float)cq[1]; obs[o++] = (float)cq[2]; obs[o++] = (float)cq[3]; obs[o++] = (float)cq[0];
+    for (int k = 0; k < 3; k++) obs[o++] = (float)(eef[k] - cube[k]);
+    for (int k = 0; k < 2; k++) obs[o++] = (float)(cube[k] - target[k]);
+}
+
+constexpr int ENV_WARPS = 8;
+
+__global__ void __launch_bounds__(ENV_WARPS * 32)
+env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
+                     int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
+                     const int32_t *__restrict__ ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWS &W = reinterpret_cast<WarpWS *>(smem_raw)[warp];
+    const DynDev &m = c_models[model_slot];
+    const int t = blockIdx.x * ENV_WARPS + warp;
+    const int e = t < n ? (ids ? ids[t] : t) : 0;
+    const bool live = t < n && (forward_only || !mask || mask[e]);
+    if (!live) {   // still take part in the CTA barriers of the substep loop
+        if (!forward_only) {
+            int dummy = 0;
+            for (int s = 0; s < T.nsub; s++) w_substep(m, W, 0u, true, lane, dummy, nullptr, false, true);
+        }
+        return;
+    }
+    for (int k = lane; k < m.nq; k += 32) W.q[k] = B.qpos[(size_t)e * m.nq + k];
+    for (int k = lane; k < m.nv; k += 32) W.v[k] = B.qvel[(size_t)e * m.nv + k];
+    if (lane < WD) W.bias_prev[lane] = B.bias_prev[(size_t)e * WD + lane];
+    if (lane < DMAXA) W.ctrl[lane] = 0.0;
+    if (lane == 0) W.wn = 0;
+    __syncwarp();
+    int ncon = 0;
+    const int keep[4] = {T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw};
+    if (forward_only) {
+        w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+        if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
+        w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+        return;
+    }
+    const int mode = is_planner ? is_planner[e] : 0;
+    const bool planner = mode == 1;
+    const bool had_prev = B.has_prev[e] != 0;
+    if (lane < 7) {
+        const double prev = (!planner || !had_prev) ? W.q[T.arm_qadr[lane]] : B.prev_state[(size_t)e * 7 + lane];
+        double a = (double)action[(size_t)e * action_stride + lane];
+        if (!planner) a = a * T.ac_scale;
+        a = a < -T.ac_scale ? -T.ac_scale : (a > T.ac_scale ? T.ac_scale : a);
+        W.ctrl[lane] = prev + a;
+    }
+    __syncwarp();
+    unsigned comp = 0;
+    for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
+    if (mode == 2) w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+    for (int s = 0; s < T.nsub; s++) {
+        w_substep(m, W, comp, true, lane, ncon, keep, mode != 2, true);
+        if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
+        __syncwarp();
+    }
+    // reward / success (frames of the last substep's start state)
+    double re[3], le[3];
+    w_site(re, W, 2, T.site_right_eef);
+    w_site(le, W, 3, T.site_left_eef);
+    const double *cube = W.kxpos[1];
+    const double target[2] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]]};
+    double dgc = 0;
+    for (int k = 0; k < 3; k++) { const double d = cube[k] - 0.5 * (re[k] + le[k]); dgc += d * d; }
+    dgc = sqrt(dgc);
+    const double dct = sqrt((cube[0] - target[0]) * (cube[0] - target[0]) + (cube[1] - target[1]) * (cube[1] - target[1]));
+    double reward = 0;
+    if (dct < 0.1) reward += 0.5 * (1 - tanh(5 * dct));
+    if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
+    bool success = false, terminal = false;
+    if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
+    if (mode != 2) w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+    __syncwarp();
+    // _after_step: joint-limit projection (set_state + forward), episode accounting
+    bool clipped = false;
+    if (lane < m.nd && m.d_limited[lane] && m.d_qadr[lane] >= 0) {
+        double &x = W.q[m.d_qadr[lane]];
+        if (x < m.d_range[lane][0]) { x = m.d_range[lane][0]; clipped = true; }
+        else if (x > m.d_range[lane][1]) { x = m.d_range[lane][1]; clipped = true; }
+    }
+    clipped = __any_sync(FULL, clipped);
+    __syncwarp();
+    if (clipped) {
+        w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+        if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
+        __syncwarp();
+    }
+    for (int k = lane; k < m.nq; k += 32) B.qpos[(size_t)e * m.nq + k] = W.q[k];
+    for (int k = lane; k < m.nv; k += 32) B.qvel[(size_t)e * m.nv + k] = W.v[k];
+    if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias_prev[lane] : 0.0;
+    if (mode != 2 && lane < 7) B.prev_state[(size_t)e * 7 + lane] = W.ctrl[lane];
+    if (lane == 0) {
+        if (mode != 2) B.has_prev[e] = 1;
+        const int len = B.ep_len[e] + 1;
+        if (len == T.max_episode_steps) terminal = true;
+        B.ep_len[e] = len;
+        B.ep_rew[e] += reward;
+        B.reward[e] = reward;
+        B.done[e] = terminal ? 1 : 0;
+        B.success[e] = success ? 1 : 0;
+        if (B.ncon) B.ncon[e] = ncon;
+    }
+}
+
+cudaError_t upload_env_model(int slot, const DynDev &h_model) {
+    if (slot < 0 || slot >= ENV_MODEL_SLOTS) return cudaErrorInvalidValue;
+    return cudaMemcpyToSymbol(c_models, &h_model, sizeof(DynDev), sizeof(DynDev) * slot);
+}
+
+cudaError_t launch_env_warp(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
+                            const int32_t *ids, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = sizeof(WarpWS) * ENV_WARPS;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(env_step_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    env_step_warp_kernel<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, T, B, action, action_stride, is_planner,
+                                                                                         mask, n, forward_only, ids);
+    return cudaGetLastError();
+}
+
+size_t env_warp_smem_per_warp() { return sizeof(WarpWS); }
+
+}  // namespace mopa

@@ -22,7 +22,7 @@ class DynDesc(C.Structure):
     _fields_ = [
         ("nq", C.c_int32), ("nv", C.c_int32), ("nb", C.c_int32), ("nd", C.c_int32), ("nact", C.c_int32),
         ("ngeom", C.c_int32), ("npair", C.c_int32), ("iterations", C.c_int32),
-        ("timestep", C.c_double), ("gravity", C.c_double * 3),
+        ("timestep", C.c_double), ("gravity", C.c_double * 3), ("tolerance", C.c_double),
         ("b_parent", _I), ("b_bodyid", _I), ("b_pos", _D), ("b_quat", _D), ("b_rootpos", _D), ("b_rootquat", _D),
         ("b_jtype", _I), ("b_qadr", _I), ("b_vadr", _I), ("b_dadr", _I), ("b_jaxis", _D), ("b_jpos", _D), ("b_qpos0", _D),
         ("b_mass", _D), ("b_ipos", _D), ("b_iquat", _D), ("b_inertia", _D),
@@ -179,6 +179,7 @@ class DynModel:
         d.nq, d.nv, d.nb, d.nd, d.nact = m.nq, m.nv, self.nb, self.nd, self.nact
         d.ngeom, d.npair, d.iterations = len(used), len(pairs), int(m.opt_iterations)
         d.timestep = float(m.opt_timestep)
+        d.tolerance = float(m.opt_tolerance)
         for k in range(3):
             d.gravity[k] = float(m.opt_gravity[k])
         for name, ctype in DynDesc._fields_:

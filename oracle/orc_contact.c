@@ -404,6 +404,7 @@ int orc_contact_rows(const dyn_model *m, const dyn_data *D, const sv6 *S, crow *
                 memset(row, 0, sizeof(crow));
                 row->type = r == 0 ? 1 : 2;
                 row->pos = cps[q].dist; row->margin = margin; row->mu = mu;
+                row->sig = p * 16 + q * 4 + r;
                 for (int k = 0; k < 2; k++) row->solref[k] = 0.5 * (m->g_solref[a][k] + m->g_solref[b][k]);
                 for (int k = 0; k < 5; k++) row->solimp[k] = 0.5 * (m->g_solimp[a][k] + m->g_solimp[b][k]);
                 for (int side = 0; side < 2; side++) {

@@ -10,7 +10,8 @@
  *   solref/solimp impedance and elliptic cones) -> semi-implicit Euler with implicit damping.
  * Documented departures: the constraint forces are found by projected Gauss-Seidel
  * on the dual problem (MuJoCo's own "PGS" solver family; the reference uses the Newton solver,
- * same convex problem) with a fixed number of sweeps and no warm start; the regulariser uses the
+ * same convex problem), at most `iterations` sweeps, stopped early when the scaled cost improvement
+ * of a sweep falls below `tolerance` (as MuJoCo's solvers do), no warm start; the regulariser uses the
  * exact diagonal of J M^-1 J^T instead of MuJoCo's precomputed invweight0 approximation; contacts
  * are condim-3 (no torsional / rolling friction); no noslip post-pass.
  */
@@ -74,7 +75,7 @@ void *orc_dyn_create(const mopa_dyn_desc *d) {
     if (d->nb > DMAXB || d->nd > DMAXD || d->nact > DMAXA || d->ngeom > DMAXG) return NULL;
     dyn_model *m = (dyn_model *)calloc(1, sizeof(dyn_model));
     m->nq = d->nq; m->nv = d->nv; m->nb = d->nb; m->nd = d->nd; m->nact = d->nact; m->ngeom = d->ngeom; m->npair = d->npair;
-    m->iterations = d->iterations; m->h = d->timestep;
+    m->iterations = d->iterations; m->h = d->timestep; m->tolerance = d->tolerance;
     memcpy(m->g, d->gravity, sizeof(m->g));
     for (int i = 0; i < d->nb; i++) {
         m->b_parent[i] = d->b_parent[i]; m->b_jtype[i] = d->b_jtype[i]; m->b_qadr[i] = d->b_qadr[i];
@@ -127,6 +128,8 @@ void orc_dyn_destroy(void *h) {
     if (!m) return;
     free(m->p_g1); free(m->p_g2); free(m);
 }
+static long g_pgs_calls = 0, g_pgs_sweeps = 0;
+void orc_pgs_stats(long *out, int reset) { out[0] = g_pgs_calls; out[1] = g_pgs_sweeps; if (reset) g_pgs_calls = g_pgs_sweeps = 0; }
 void orc_dyn_enable_contacts(void *h, int on) { ((dyn_model *)h)->enable_contacts = on; }
 
 /* impedance / reference parameters of one constraint row (mj_makeImpedance semantics) */
@@ -150,7 +153,7 @@ static void kbi(const dyn_model *m, const double *solref, const double *solimp, 
 
 /* one mj_step.  qpos[nq], qvel[nv] updated in place; ctrl[nact]; applied[nd] = qfrc_applied on the
    simulated dofs; data receives the kinematics / bias of this step. */
-static void substep(const dyn_model *m, double *qpos, double *qvel, const double *ctrl, const double *applied, dyn_data *D) {
+static void substep(const dyn_model *m, double *qpos, double *qvel, const double *ctrl, const double *applied, dyn_data *D, warm_t *warm) {
     const int nb = m->nb, nd = m->nd;
     sv6 S[DMAXD], vel[DMAXB], acc[DMAXB], frc[DMAXB];
     sinert I[DMAXB], Ic[DMAXB];
@@ -313,7 +316,7 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
             crow *r = &rows[nc++];
             memset(r, 0, sizeof(crow));
             r->J[k] = side == 0 ? 1.0 : -1.0;
-            r->pos = dist; r->margin = m->d_margin[k]; r->type = 0;
+            r->pos = dist; r->margin = m->d_margin[k]; r->type = 0; r->sig = -(2 * k + side + 1);
             memcpy(r->solref, m->d_solref[k], sizeof(r->solref)); memcpy(r->solimp, m->d_solimp[k], sizeof(r->solimp));
         }
     }
@@ -333,6 +336,12 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
             memcpy(MiJ[r], rows[r].J, sizeof(double) * nd);
             CHOL_SOLVE(L, MiJ[r]);
         }
+        /* warm start: reuse the previous substep's forces when the constraint set is unchanged */
+        if (warm && warm->n == nc) {
+            int same = 1;
+            for (int r = 0; r < nc; r++) if (warm->sig[r] != rows[r].sig) same = 0;
+            if (same) for (int r = 0; r < nc; r++) f[r] = warm->f[r];
+        }
         for (int r = 0; r < nc; r++)
             for (int s = 0; s < nc; s++) {
                 double a = 0;
@@ -350,29 +359,50 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
             if (Rg[r] < MINVAL) Rg[r] = MINVAL;
             b[r] = ja - aref;
         }
+        double trM = 0;
+        for (int k = 0; k < nd; k++) trM += M[k][k];
+        const double scale = 1.0 / (trM > MINVAL ? trM : MINVAL); /* 1 / (meaninertia * nv) */
+        g_pgs_calls++;
         for (int it = 0; it < m->iterations; it++) {
+            double imp = 0;
+            g_pgs_sweeps++;
             for (int r = 0; r < nc; r++) {
                 if (rows[r].type >= 2) continue; /* tangent rows are updated with their normal row */
                 double res = b[r] + Rg[r] * f[r];
                 for (int s = 0; s < nc; s++) res += A[r * nc + s] * f[s];
                 double fn = f[r] - res / (A[r * nc + r] + Rg[r]);
-                f[r] = fn > 0 ? fn : 0;
+                fn = fn > 0 ? fn : 0;
+                imp += 0.5 * (A[r * nc + r] + Rg[r]) * (fn - f[r]) * (fn - f[r]);
+                f[r] = fn;
                 if (rows[r].type == 1) { /* elliptic cone: tangential rows r+1, r+2, |f_t| <= mu f_n */
                     for (int t = 1; t <= 2; t++) {
                         int q = r + t;
                         double rs = b[q] + Rg[q] * f[q];
                         for (int s = 0; s < nc; s++) rs += A[q * nc + s] * f[s];
-                        f[q] = f[q] - rs / (A[q * nc + q] + Rg[q]);
+                        double ft_new = f[q] - rs / (A[q * nc + q] + Rg[q]);
+                        imp += 0.5 * (A[q * nc + q] + Rg[q]) * (ft_new - f[q]) * (ft_new - f[q]);
+                        f[q] = ft_new;
                     }
                     double lim = rows[r].mu * f[r], ft = sqrt(f[r + 1] * f[r + 1] + f[r + 2] * f[r + 2]);
-                    if (ft > lim) { double sc = ft > MINVAL ? lim / ft : 0; f[r + 1] *= sc; f[r + 2] *= sc; }
+                    if (ft > lim) {
+                        double sc = ft > MINVAL ? lim / ft : 0;
+                        for (int t = 1; t <= 2; t++) {
+                            int q = r + t;
+                            double fs = f[q] * sc;
+                            imp += 0.5 * (A[q * nc + q] + Rg[q]) * (fs - f[q]) * (fs - f[q]);
+                            f[q] = fs;
+                        }
+                    }
                 }
             }
+            if (scale * imp < m->tolerance) break;
         }
         for (int r = 0; r < nc; r++)
             for (int k = 0; k < nd; k++) fc[k] += rows[r].J[k] * f[r];
+        if (warm) { warm->n = nc; for (int r = 0; r < nc; r++) { warm->sig[r] = rows[r].sig; warm->f[r] = f[r]; } }
         free(MiJ); free(A); free(b); free(Rg); free(f);
     }
+    if (warm && nc == 0) warm->n = 0;
     free(rows);
     /* ---- semi-implicit Euler with implicit joint damping: (M + h D) qacc = tau + J^T f */
     double Lh[DMAXD][DMAXD], rhs[DMAXD];
@@ -413,9 +443,11 @@ int orc_dyn_step(void *h, double *qpos, double *qvel, const double *ctrl, const 
     dyn_data D;
     memset(&D, 0, sizeof(D));
     double applied[DMAXD];
+    warm_t warm;
+    warm.n = 0; /* the warm start lives for the substeps of one call (one env.step) */
     for (int s = 0; s < nsub; s++) {
         for (int k = 0; k < m->nd; k++) applied[k] = comp[k] ? bias_prev[k] : 0.0;
-        substep(m, qpos, qvel, ctrl, applied, &D);
+        substep(m, qpos, qvel, ctrl, applied, &D, &warm);
         memcpy(bias_prev, D.bias, sizeof(double) * m->nd);
     }
     if (xpos) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 3; k++) xpos[3 * i + k] = D.xpos[i][k];
@@ -433,7 +465,7 @@ int orc_dyn_forward(void *h, const double *qpos, const double *qvel, double *bia
     memcpy(q, qpos, sizeof(double) * m->nq); memcpy(v, qvel, sizeof(double) * m->nv);
     int ec = m->enable_contacts;
     m->enable_contacts = 0;
-    substep(m, q, v, ctrl, zero, &D);
+    substep(m, q, v, ctrl, zero, &D, NULL);
     m->enable_contacts = ec;
     if (bias) memcpy(bias, D.bias, sizeof(double) * m->nd);
     if (xpos) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 3; k++) xpos[3 * i + k] = D.xpos[i][k];
@@ -449,7 +481,7 @@ int orc_dyn_mass_bias(void *h, const double *qpos, const double *qvel, double *M
     memcpy(q, qpos, sizeof(double) * m->nq); memcpy(v, qvel, sizeof(double) * m->nv);
     int ec = m->enable_contacts;
     m->enable_contacts = 0;
-    substep(m, q, v, ctrl, zero, D);
+    substep(m, q, v, ctrl, zero, D, NULL);
     m->enable_contacts = ec;
     memcpy(M, D->M, sizeof(double) * m->nd * m->nd);
     memcpy(bias, D->bias, sizeof(double) * m->nd);

@@ -15,7 +15,7 @@ typedef struct { double m, h[3], I[9]; } sinert; /* mass, m*c, inertia about the
 
 typedef struct {
     int nq, nv, nb, nd, nact, ngeom, npair, iterations;
-    double h, g[3];
+    double h, g[3], tolerance;
     int b_parent[DMAXB], b_jtype[DMAXB], b_qadr[DMAXB], b_vadr[DMAXB], b_dadr[DMAXB];
     double b_pos[DMAXB][3], b_quat[DMAXB][4], b_rootpos[DMAXB][3], b_rootquat[DMAXB][4], b_jaxis[DMAXB][3], b_jpos[DMAXB][3],
         b_qpos0[DMAXB], b_mass[DMAXB], b_ipos[DMAXB][3], b_iquat[DMAXB][4], b_inertia[DMAXB][3];
@@ -46,6 +46,8 @@ typedef struct {
     double pos, margin, solref[2], solimp[5];
     int type; /* 0 limit, 1 contact normal, 2 tangent */
     double mu;
+    int sig;  /* identity of the row across substeps (warm start): limits -(2*dof+side+1), contacts pair*16 + point*4 + dir */
 } crow;
+typedef struct { int n; int sig[DMAXC]; double f[DMAXC]; } warm_t; /* constraint forces of the previous substep */
 int orc_contact_rows(const dyn_model *m, const dyn_data *d, const sv6 *S, crow *rows, int maxrows);
 #endif

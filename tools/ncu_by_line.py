@@ -50,5 +50,15 @@ for k, v in inst.items():
     byfile[k[0]] += v
 print("by file:", {k: "%.1f%%" % (100 * v / ti) for k, v in byfile.most_common()})
 print("%-28s %8s %8s %8s" % ("file:line", "inst%", "samp%", "thr/inst"))
-for k, v in inst.most_common(45):
-    print("%-28s %7.2f%% %7.2f%% %8.1f" % ("%s:%d" % k, 100 * v / ti, 100 * samp[k] / max(ts, 1), thr[k] / max(v, 1)))
+import glob, os
+_src = {}
+def _line(fn, ln):
+    if fn not in _src:
+        hits = glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "mopa_rl_b200", "csrc", fn))
+        _src[fn] = open(hits[0]).read().splitlines() if hits else []
+    L = _src[fn]
+    return L[ln - 1].strip()[:90] if 0 < ln <= len(L) else ""
+order = samp if (len(sys.argv) > 5 and sys.argv[5] == "samples") else inst
+for k, _ in order.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 45):
+    v = inst[k]
+    print("%-24s %6.2f%% %6.2f%% %5.1f  %s" % ("%s:%d" % k, 100 * v / ti, 100 * samp[k] / max(ts, 1), thr[k] / max(v, 1), _line(*k)))
