@@ -130,6 +130,10 @@ class VecMoPARolloutRunner:
         self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, densify_fallback=0, episodes=0,
                              success=0, mp_path_len=0, interpolation_path_len=0)
         self.launches = 0
+        self.plan_stream = torch.cuda.Stream(device=dev)
+        self.rrt_queue, self.rrt_inflight = [], None
+        self.n_waiting = 0
+        self.async_rrt = True
         self.step_events = None      # set to [] to collect CUDA events around every env-step launch
         self.last_emitted = None     # transition records emitted by the latest tick (for the replay exchange)
         venv.reset()
@@ -230,38 +234,71 @@ class VecMoPARolloutRunner:
                 self.counters["interpolation"] += int(s_idx.numel())
                 self.counters["interpolation_path_len"] += int((nstep[s_idx] + 1).sum())
             r_idx = torch.nonzero(~straight).squeeze(1)
-            if r_idx.numel():
-                self._rrt(idx, good[r_idx], c[r_idx], tg[r_idx], kind, tlen)
-        self.counters["mp_fail"] += int((kind == 2).sum())
+        else:
+            r_idx = good
+        self.counters["mp_fail"] += int((~ok).sum())
         self.kind[idx] = kind
         self.traj_len[idx] = tlen
         self.traj_pos[idx] = 0
+        if r_idx.numel():
+            # straight line blocked: RRT-Connect, asynchronously (these envs wait, kind 3)
+            self.rrt_queue.append((idx[good[r_idx]], c[r_idx], tg[r_idx]))
 
-    def _rrt(self, idx, sub, start, goal, kind, tlen):
-        """RRT-Connect for the envs idx[sub]; on success re-base, densify and store the path."""
+    def _rrt_launch(self, rows, start, goal):
+        """Enqueue RRT-Connect for env rows `rows` on the planner stream; the envs wait (kind 3) until
+        the batch is finalised by a later tick, so the planner runs under the env-step kernels."""
         torch, cfg = self.torch, self.cfg
-        R = sub.numel()
+        R = rows.numel()
         row, mp = self.row, cfg.max_path
         s32 = torch.zeros(R, row, dtype=torch.float32, device=self.dev)
         g32 = torch.zeros(R, row, dtype=torch.float32, device=self.dev)
         s32[:, :self.nq] = start.float()
         g32[:, :self.nq] = goal.float()
-        rows_r = idx[sub]
-        keys = (self.env_gid[rows_r] << 32) + self.plan_count[rows_r]   # invariant to batching / GPU count
-        self.plan_count[rows_r] += 1
+        keys = (self.env_gid[rows] << 32) + self.plan_count[rows]   # invariant to batching / GPU count
+        self.plan_count[rows] += 1
         self.plan_calls += R
         path = torch.zeros(R, mp, row, dtype=torch.float32, device=self.dev)
         ids = torch.zeros(R, mp, dtype=torch.int32, device=self.dev)
         plen = torch.zeros(R, dtype=torch.int32, device=self.dev)
         status = torch.zeros(R, dtype=torch.int32, device=self.dev)
+        main = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.plan_stream.wait_event(ready)
         self.planner.plan_device(s32.data_ptr(), g32.data_ptr(), row, keys.data_ptr(), R, cfg.max_iter, path.data_ptr(), ids.data_ptr(),
-                                 mp, plen.data_ptr(), status.data_ptr(), 0, 0, torch.cuda.current_stream(self.dev).cuda_stream)
+                                 mp, plen.data_ptr(), status.data_ptr(), 0, 0, self.plan_stream.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(self.plan_stream)
         self.launches += 1
+        self.kind[rows] = 3
+        self.traj_len[rows] = 1
+        self.traj_pos[rows] = 0
+        return dict(rows=rows, start=start, s32=s32, g32=g32, keys=keys, path=path, ids=ids, plen=plen, status=status, done=done)
+
+    def _rrt_finalize(self, batch):
+        """Re-base, densify and store the paths of a finished RRT batch (SamplingBasedPlanner.plan /
+        PlannerAgent.plan / SACAgent.plan densification, rl/sac_agent.py:216-233)."""
+        torch, cfg = self.torch, self.cfg
+        torch.cuda.current_stream(self.dev).wait_event(batch["done"])
+        rows_all, start, path, plen, status = batch["rows"], batch["start"], batch["path"], batch["plen"], batch["status"]
+        mp = cfg.max_path
+        R = rows_all.numel()
+        kind = torch.full((R,), 2, dtype=torch.uint8, device=self.dev)
+        tlen = torch.ones(R, dtype=torch.int32, device=self.dev)
         okp = status == 0
-        self.counters["approximate"] += int((~okp).sum())
+        n_fail = int((~okp).sum())
+        self.counters["approximate"] += n_fail
+        self.counters["mp_fail"] += n_fail
         w = torch.nonzero(okp).squeeze(1)
-        if not w.numel():
-            return
+        if w.numel():
+            self._densify(rows_all, w, start, path, plen, kind, tlen)
+        self.kind[rows_all] = kind
+        self.traj_len[rows_all] = tlen
+        self.traj_pos[rows_all] = 0
+
+    def _densify(self, rows_all, w, start, path, plen, kind, tlen):
+        torch, cfg = self.torch, self.cfg
+        mp = cfg.max_path
         self.counters["mp"] += int(w.numel())
         P = path[w][:, :, :7].double()
         L = plen[w].to(torch.int64)                                  # rows incl. the start row
@@ -308,7 +345,7 @@ class VecMoPARolloutRunner:
         off = torch.cumsum(cnt, dim=1) - cnt
         total = cnt.sum(dim=1)
         over = total > cfg.max_traj
-        rows = idx[sub[w]]
+        rows = rows_all[w]
         out = torch.zeros(w.numel(), cfg.max_traj, 7, dtype=torch.float64, device=self.dev)
         ar = torch.arange(w.numel(), device=self.dev)[:, None].expand(-1, H)
         for j in range(kmax):
@@ -318,14 +355,17 @@ class VecMoPARolloutRunner:
         msk = hop_live & ~over[:, None]
         out[ar[msk], (off + nst)[msk]] = hops_end[msk]
         self.traj[rows] = out
-        k_ok = torch.where(over, torch.full_like(total, 2), torch.ones_like(total)).to(torch.uint8)
-        kind[sub[w]] = k_ok
-        tlen[sub[w]] = torch.where(over, torch.ones_like(total), total).to(torch.int32)
+        kind[w] = torch.where(over, torch.full_like(total, 2), torch.ones_like(total)).to(torch.uint8)
+        tlen[w] = torch.where(over, torch.ones_like(total), total).to(torch.int32)
+        self.counters["mp_fail"] += int(over.sum())
         self.counters["mp_path_len"] += int(total[~over].sum())
 
     # ---------------------------------------------------------------- one env.step for every env
     def tick(self):
         torch, cfg, venv = self.torch, self.cfg, self.venv
+        if self.rrt_inflight is not None and (not self.async_rrt or self.rrt_inflight["done"].query()):
+            self._rrt_finalize(self.rrt_inflight)
+            self.rrt_inflight = None
         need = torch.nonzero(self.traj_pos >= self.traj_len).squeeze(1)
         self.last_emitted = None
         if need.numel():
@@ -373,6 +413,21 @@ class VecMoPARolloutRunner:
             p_idx = need[is_mp]
             if p_idx.numel():
                 self._plan(p_idx, ac[is_mp])
+        if self.rrt_inflight is None and self.rrt_queue:
+            rows = torch.cat([r for r, _, _ in self.rrt_queue])
+            st = torch.cat([a for _, a, _ in self.rrt_queue])
+            gl = torch.cat([b for _, _, b in self.rrt_queue])
+            self.rrt_queue = []
+            self.rrt_inflight = self._rrt_launch(rows, st, gl)
+            if not self.async_rrt:
+                self._rrt_finalize(self.rrt_inflight)
+                self.rrt_inflight = None
+        elif self.rrt_queue:
+            for r, _, _ in self.rrt_queue:      # queued behind the batch in flight: wait as well
+                self.kind[r] = 3
+                self.traj_len[r] = 1
+                self.traj_pos[r] = 0
+        self.n_waiting = int((self.kind == 3).sum()) if (self.rrt_inflight is not None or self.rrt_queue) else 0
         # stage the action of every env for this tick
         kind = self.kind
         self.step_mode.copy_(kind)
@@ -384,21 +439,33 @@ class VecMoPARolloutRunner:
             nxt = self.traj[torch.arange(venv.n, device=self.dev), pos]
             delta = (nxt - venv.qpos[:, :7]).float()                  # env.form_action(next_qpos)
             self.step_action[:, :7] = torch.where(plan[:, None], delta, self.step_action[:, :7])
+        stepping = kind != 3                                          # envs waiting for their RRT plan do not step
+        mask = stepping.to(torch.uint8) if self.n_waiting else None
         if self.step_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            venv.step(self.step_action, self.step_mode)
+            venv.step(self.step_action, self.step_mode, mask)
             e1.record()
             self.step_events.append((e0, e1))
         else:
-            venv.step(self.step_action, self.step_mode)
+            venv.step(self.step_action, self.step_mode, mask)
         self.launches += 1
         disc = torch.pow(torch.full_like(self.meta_rew, cfg.discount_factor), self.traj_pos.double())
-        self.meta_rew += torch.where(plan, disc, torch.ones_like(disc)) * venv.reward
-        self.executed += 1
-        self.traj_pos += 1
-        done = venv.done.bool()
+        gain = torch.where(plan, disc, torch.ones_like(disc)) * venv.reward
+        self.meta_rew += torch.where(stepping, gain, torch.zeros_like(gain))
+        one = stepping.to(torch.int32)
+        self.executed += one
+        self.traj_pos += one
+        done = venv.done.bool() & stepping
         self.macro_done |= done
         self.traj_len = torch.where(done, self.traj_pos, self.traj_len)
-        self.env_steps += venv.n
-        return venv.n
+        stepped = venv.n - self.n_waiting
+        self.env_steps += stepped
+        return stepped
+
+    def drain(self):
+        """Finish any RRT batch in flight (end of a collection run)."""
+        while self.rrt_inflight is not None or self.rrt_queue:
+            if self.rrt_inflight is not None:
+                self.rrt_inflight["done"].synchronize()
+            self.tick()
