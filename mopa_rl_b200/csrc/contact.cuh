@@ -108,8 +108,10 @@ DYN_HD inline int convex_pocs(CPoint &cp, const CGeom &g1, const CGeom &g2, doub
     int in1 = 0, in2 = 0;
     for (int k = 0; k < 3; k++) p1[k] = g1.c[k];
     for (int it = 0; it < 16; it++) {
+        double o1[3] = {p1[0], p1[1], p1[2]};
         in2 = core_closest(p2, g2, rho2, p1, n2);
         in1 = core_closest(p1, g1, rho1, p2, n1);
+        if (it > 0 && o1[0] == p1[0] && o1[1] == p1[1] && o1[2] == p1[2]) break;   // exact fixed point: later sweeps repeat it
     }
     in2 = core_closest(p2, g2, rho2, p1, n2);
     double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, len = sqrt(d_dot(d, d)), n[3], dist;
@@ -150,6 +152,7 @@ DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2
         double s = fabs(tp) - ra - h2[j];
         if (s > best) { best = s; code = 3 + j; }
     }
+    if (best >= margin) return 0;   /* separated on a face axis: no axis can bring the maximum below margin */
     double ebest = -1e30;
     int ecode = -1;
     for (int i = 0; i < 3; i++) {

@@ -19,7 +19,7 @@
 namespace mopa {
 struct DynDev;
 cudaError_t upload_env_model(int slot, const DynDev &h_model);
-cudaError_t launch_env_warp(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream);
 }
@@ -272,7 +272,7 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
         mopa::env_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_ids, n);
         ENV_TRY(cudaGetLastError());
     } else {
-        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
+        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->h_model.nb, e->h_model.ngeom, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
     }
     return MOPA_OK;
 }
@@ -287,7 +287,7 @@ int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_actio
                                                                                   d_is_planner, d_mask, n_envs);
         ENV_TRY(cudaGetLastError());
     } else {
-        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->task, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr,
+        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->h_model.nb, e->h_model.ngeom, e->task, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr,
                                       (cudaStream_t)stream));
     }
     return MOPA_OK;

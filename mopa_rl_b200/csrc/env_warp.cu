@@ -27,38 +27,43 @@
 
 namespace mopa {
 
-constexpr int WB = DMAXB;       // bodies
 constexpr int WD = DMAXD;       // dofs
-constexpr int WC = 32;          // constraint rows = lanes
-constexpr int WCP = 10;         // contact points kept per substep
-constexpr int WCAND = 64;       // broad-phase survivors kept per substep
+constexpr int WC = 24;          // constraint rows (one lane each)
+constexpr int WCP = 8;          // contact points kept per substep
+constexpr int WCAND = 48;       // broad-phase survivors kept per substep
 constexpr int YS = WD + 1;      // padded row stride of Y (bank-conflict free, lane = row)
-constexpr int MS = WD + 1;
+constexpr int NTRI = WD * (WD + 1) / 2;   // lower-triangular storage of M and its Cholesky factors
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
+// WB / WG: body and contact-geom capacity of the workspace (two instantiations: small scenes such as
+// Sawyer-Push fit 14 warps per SM, which turns 4096 envs into exactly two waves on 148 SMs)
+template <int WB>
 struct WarpKin {
     double xpos[WB][3], xquat[WB][4], xmat[WB][9];
     double S[WD][6];
     double vel[WB][6], frc[WB][6];
     double inert[WB][13];
 };
+template <int WB, int WG>
 struct WarpWS {
-    double q[64], v[64];
+    double q[40], v[40];
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
-        WarpKin k;
+        WarpKin<WB> k;
         double A[WC * WC];   // A[s * WC + r] = A_rs (column s contiguous over lanes r)
     };
     double kxpos[4][3], kxquat[4][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
     double rD[WC];
-    double M[WD * MS], L[WD * MS];
+    double M[NTRI], L[NTRI];
     double qd[WD], bias[WD], tau[WD], qacc0[WD], fc[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
     double Y[WC * YS];
     double f[WC];
-    double gpos[DMAXG][3];
+    double gpos[WG][3];
     double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
     int cga[WCP], cgb[WCP], csig[WCP];
     int wsig[WC];            // warm start: row identities and forces of the previous substep
     double wf[WC];
     int wn;
+    int blk[WD];             // first dof of the kinematic tree that owns each dof
     int cand[WCAND];
     int ncand, ncp;
 };
@@ -77,19 +82,23 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // ---- lane = row right-looking Cholesky of (M + hs * diag) into L (lower, stride MS)
-__device__ __noinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane) {
+// `blk[i]` = first dof of the kinematic tree that owns dof i: M is block diagonal by tree, so all entries
+// outside a row's block are exact zeros and are skipped (bitwise the same factor as the dense algorithm).
+__device__ __noinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane, const int *blk) {
+    const int b0 = lane < nd ? blk[lane] : 0;
     if (lane < nd)
-        for (int k = 0; k <= lane; k++) L[lane * MS + k] = M[lane * MS + k] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
+        for (int k = 0; k <= lane; k++) L[TRI(lane, k)] = M[TRI(lane, k)] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
     __syncwarp();
     for (int j = 0; j < nd; j++) {
-        const double d = sqrt(L[j * MS + j]);
+        const double d = sqrt(L[TRI(j, j)]);
         __syncwarp();
-        if (lane == j) L[j * MS + j] = d;
-        if (lane > j && lane < nd) L[lane * MS + j] = L[lane * MS + j] / d;
+        if (lane == j) L[TRI(j, j)] = d;
+        const bool mine = lane > j && lane < nd && b0 <= j;   // same tree as column j
+        if (mine) L[TRI(lane, j)] = L[TRI(lane, j)] / d;
         __syncwarp();
-        if (lane > j && lane < nd) {
-            const double lij = L[lane * MS + j];
-            for (int k = j + 1; k <= lane; k++) L[lane * MS + k] -= lij * L[k * MS + j];
+        if (mine) {
+            const double lij = L[TRI(lane, j)];
+            for (int k = j + 1; k <= lane; k++) L[TRI(lane, k)] -= lij * L[TRI(k, j)];
         }
         __syncwarp();
     }
@@ -97,17 +106,17 @@ __device__ __noinline__ void w_chol(const double *M, const double *diag, double 
 // single right-hand side, lane-parallel column-oriented substitution; x (shared, nd entries) in place
 __device__ __noinline__ void w_solve(const double *L, int nd, double *x, int lane) {
     for (int i = 0; i < nd; i++) {
-        const double xi = x[i] / L[i * MS + i];
+        const double xi = x[i] / L[TRI(i, i)];
         __syncwarp();
         if (lane == i) x[i] = xi;
-        if (lane > i && lane < nd) x[lane] -= L[lane * MS + i] * xi;
+        if (lane > i && lane < nd) x[lane] -= L[TRI(lane, i)] * xi;
         __syncwarp();
     }
     for (int i = nd - 1; i >= 0; i--) {
-        const double xi = x[i] / L[i * MS + i];
+        const double xi = x[i] / L[TRI(i, i)];
         __syncwarp();
         if (lane == i) x[i] = xi;
-        if (lane < i) x[lane] -= L[i * MS + lane] * xi;
+        if (lane < i) x[lane] -= L[TRI(i, lane)] * xi;
         __syncwarp();
     }
 }
@@ -127,7 +136,8 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 // `sync`: the warps of a CTA walk the stages in step (CTA barrier between stages) so that they share
 // instruction-cache lines; `active` = false warps only take part in the barriers.
 #define STAGE_SYNC() do { if (sync) __syncthreads(); } while (0)
-__device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int *keep,
+template <int WB, int WG>
+__device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int *keep,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     if (!active) {   // barrier-only participant: one barrier per stage boundary below
@@ -136,63 +146,64 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
     }
     if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
     __syncwarp();
-    // ---- kinematics chain (uniform across lanes), joint motion axes
-    for (int i = 0; i < nb; i++) {
-        double Pp[3], Pq[4], PM[9];
-        const int p = m.b_parent[i];
-        if (p >= 0) {
-            for (int k = 0; k < 3; k++) Pp[k] = W.k.xpos[p][k];
-            for (int k = 0; k < 4; k++) Pq[k] = W.k.xquat[p][k];
-            for (int k = 0; k < 9; k++) PM[k] = W.k.xmat[p][k];
-        } else {
-            for (int k = 0; k < 3; k++) Pp[k] = m.b_rootpos[i][k];
-            for (int k = 0; k < 4; k++) Pq[k] = m.b_rootquat[i][k];
-            d_q2m(PM, Pq);
-        }
-        double pos[3], quat[4], t[3], R[9], bp[3] = {m.b_pos[i][0], m.b_pos[i][1], m.b_pos[i][2]};
-        double bq[4] = {m.b_quat[i][0], m.b_quat[i][1], m.b_quat[i][2], m.b_quat[i][3]};
-        d_mv(t, PM, bp);
-        for (int k = 0; k < 3; k++) pos[k] = Pp[k] + t[k];
-        d_qmul(quat, Pq, bq);
-        const int jt = m.b_jtype[i], da = m.b_dadr[i];
-        double s0[6];
+    // ---- kinematics.  (1) lane = body: the joint's local transform (the expensive sin / cos run in
+    // parallel), (2) short uniform chain composing parent frames, (3) lane = body: joint motion axes.
+    if (lane < nb) {
+        const int i = lane, jt = m.b_jtype[i];
+        double lp[3] = {m.b_pos[i][0], m.b_pos[i][1], m.b_pos[i][2]};
+        double lq[4] = {m.b_quat[i][0], m.b_quat[i][1], m.b_quat[i][2], m.b_quat[i][3]};
         if (jt == 3) {
-            double anchor[3], ql[4], ax[3], qn[4], jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
-            double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
-            d_q2m(R, quat);
-            d_mv(t, R, jp);
-            for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t[k];
+            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
             const double ang = W.q[m.b_qadr[i]] - m.b_qpos0[i], sn = sin(0.5 * ang), cs = cos(0.5 * ang);
-            ql[0] = cs; ql[1] = sn * ja[0]; ql[2] = sn * ja[1]; ql[3] = sn * ja[2];
-            d_qmul(qn, quat, ql);
-            for (int k = 0; k < 4; k++) quat[k] = qn[k];
-            d_q2m(R, quat);
-            d_mv(t, R, jp);
-            for (int k = 0; k < 3; k++) pos[k] = anchor[k] - t[k];
-            d_mv(ax, R, ja);
-            for (int k = 0; k < 3; k++) s0[k] = ax[k];
-            d_cross(s0 + 3, anchor, ax);
-            if (lane < 6) W.k.S[da][lane] = s0[lane];
+            const double ql[4] = {cs, sn * ja[0], sn * ja[1], sn * ja[2]};
+            double qn[4];
+            d_qmul(qn, lq, ql);
+            if (jp[0] != 0.0 || jp[1] != 0.0 || jp[2] != 0.0) {   // rotation about an offset anchor
+                double R0[9], R1[9], t0[3], t1[3];
+                d_q2m(R0, lq); d_q2m(R1, qn);
+                d_mv(t0, R0, jp); d_mv(t1, R1, jp);
+                for (int k = 0; k < 3; k++) lp[k] += t0[k] - t1[k];
+            }
+            for (int k = 0; k < 4; k++) lq[k] = qn[k];
         } else if (jt == 2) {
-            double ax[3], ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
-            d_q2m(R, quat);
-            d_mv(ax, R, ja);
+            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+            double R0[9], ax[3];
+            d_q2m(R0, lq);
+            d_mv(ax, R0, ja);
             const double dq = W.q[m.b_qadr[i]] - m.b_qpos0[i];
-            for (int k = 0; k < 3; k++) { pos[k] += ax[k] * dq; s0[k] = 0; s0[3 + k] = ax[k]; }
-            if (lane < 6) W.k.S[da][lane] = s0[lane];
+            for (int k = 0; k < 3; k++) lp[k] += ax[k] * dq;
         } else if (jt == 0) {
             const int a = m.b_qadr[i];
-            for (int k = 0; k < 3; k++) pos[k] = W.q[a + k];
+            for (int k = 0; k < 3; k++) lp[k] = W.q[a + k];
             const double n = sqrt(W.q[a + 3] * W.q[a + 3] + W.q[a + 4] * W.q[a + 4] + W.q[a + 5] * W.q[a + 5] + W.q[a + 6] * W.q[a + 6]);
-            for (int k = 0; k < 4; k++) quat[k] = W.q[a + 3 + k] / n;
-            d_q2m(R, quat);
-            if (lane < 3) {
-                for (int c = 0; c < 6; c++) W.k.S[da + lane][c] = 0;
-                W.k.S[da + lane][3 + lane] = 1;
-                double e[3] = {R[lane], R[3 + lane], R[6 + lane]}, cr[3];
-                d_cross(cr, pos, e);
-                for (int c = 0; c < 3; c++) { W.k.S[da + 3 + lane][c] = e[c]; W.k.S[da + 3 + lane][3 + c] = cr[c]; }
+            for (int k = 0; k < 4; k++) lq[k] = W.q[a + 3 + k] / n;
+        }
+        for (int k = 0; k < 3; k++) W.k.inert[i][k] = lp[k];       // scratch: inert[] is filled later
+        for (int k = 0; k < 4; k++) W.k.inert[i][3 + k] = lq[k];
+    }
+    __syncwarp();
+    for (int i = 0; i < nb; i++) {
+        const int p = m.b_parent[i], jt = m.b_jtype[i];
+        double pos[3], quat[4], R[9];
+        const double lp[3] = {W.k.inert[i][0], W.k.inert[i][1], W.k.inert[i][2]};
+        const double lq[4] = {W.k.inert[i][3], W.k.inert[i][4], W.k.inert[i][5], W.k.inert[i][6]};
+        if (jt == 0) {   // free joint: absolute pose
+            for (int k = 0; k < 3; k++) pos[k] = lp[k];
+            for (int k = 0; k < 4; k++) quat[k] = lq[k];
+        } else {
+            double Pp[3], Pq[4], PM[9], t[3];
+            if (p >= 0) {
+                for (int k = 0; k < 3; k++) Pp[k] = W.k.xpos[p][k];
+                for (int k = 0; k < 4; k++) Pq[k] = W.k.xquat[p][k];
+                for (int k = 0; k < 9; k++) PM[k] = W.k.xmat[p][k];
+            } else {
+                for (int k = 0; k < 3; k++) Pp[k] = m.b_rootpos[i][k];
+                for (int k = 0; k < 4; k++) Pq[k] = m.b_rootquat[i][k];
+                d_q2m(PM, Pq);
             }
+            d_mv(t, PM, lp);
+            for (int k = 0; k < 3; k++) pos[k] = Pp[k] + t[k];
+            d_qmul(quat, Pq, lq);
         }
         d_q2m(R, quat);
         if (lane < 3) W.k.xpos[i][lane] = pos[lane];
@@ -200,6 +211,34 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
         if (lane < 9) W.k.xmat[i][lane] = R[lane];
         __syncwarp();
     }
+    if (lane < nb) {
+        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i];
+        const double *R = W.k.xmat[i], *pos = W.k.xpos[i];
+        if (jt == 3) {
+            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
+            double ax[3], t[3], anchor[3], cr[3];
+            d_mv(ax, R, ja);
+            d_mv(t, R, jp);
+            for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t[k];
+            d_cross(cr, anchor, ax);
+            for (int k = 0; k < 3; k++) { W.k.S[da][k] = ax[k]; W.k.S[da][3 + k] = cr[k]; }
+        } else if (jt == 2) {
+            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+            double ax[3];
+            d_mv(ax, R, ja);
+            for (int k = 0; k < 3; k++) { W.k.S[da][k] = 0; W.k.S[da][3 + k] = ax[k]; }
+        } else if (jt == 0) {
+            for (int a = 0; a < 3; a++) {
+                for (int c = 0; c < 6; c++) W.k.S[da + a][c] = 0;
+                W.k.S[da + a][3 + a] = 1;
+                const double e[3] = {R[a], R[3 + a], R[6 + a]};
+                double cr[3];
+                d_cross(cr, pos, e);
+                for (int c = 0; c < 3; c++) { W.k.S[da + 3 + a][c] = e[c]; W.k.S[da + 3 + a][3 + c] = cr[c]; }
+            }
+        }
+    }
+    __syncwarp();
     if (lane < 4) {
         const int b = keep[lane];
         for (int k = 0; k < 3; k++) W.kxpos[lane][k] = W.k.xpos[b][k];
@@ -293,7 +332,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
         if (p >= 0 && lane < 13) W.k.inert[p][lane] += W.k.inert[i][lane];
         __syncwarp();
     }
-    for (int e = lane; e < WD * MS; e += 32) W.M[e] = 0;
+    for (int e = lane; e < NTRI; e += 32) W.M[e] = 0;
     __syncwarp();
     if (lane < nd) {
         const int i = lane, b = m.d_body[i];
@@ -308,8 +347,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
             for (int c = 0; c < 3; c++) dsum += W.k.S[j][c] * F.w[c];
             for (int c = 0; c < 3; c++) dsum += W.k.S[j][3 + c] * F.v[c];
             if (j == i) dsum += m.d_armature[i];
-            W.M[i * MS + j] = dsum;
-            W.M[j * MS + i] = dsum;
+            W.M[TRI(i, j)] = dsum;   // j <= i along the ancestor chain: lower triangle
         }
     }
     __syncwarp();
@@ -330,7 +368,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
     }
     __syncwarp();
     STAGE_SYNC();   // 3: inertia matrix and forces done
-    w_chol(W.M, nullptr, 0.0, nd, W.L, lane);
+    w_chol(W.M, nullptr, 0.0, nd, W.L, lane, W.blk);
     if (lane < nd) W.qacc0[lane] = W.tau[lane];
     __syncwarp();
     w_solve(W.L, nd, W.qacc0, lane);
@@ -378,11 +416,43 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
             if (p < m.npair) {
                 const int a = m.p_g1[p], b = m.p_g2[p];
                 keep = true;
-                if (m.g_type[a] != 0 && m.g_type[b] != 0) {
-                    const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
+                const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
+                const int ta = m.g_type[a], tb = m.g_type[b];
+                if (ta != 0 && tb != 0) {
                     const double d[3] = {W.gpos[b][0] - W.gpos[a][0], W.gpos[b][1] - W.gpos[a][1], W.gpos[b][2] - W.gpos[a][2]};
                     const double bound = m.g_rbound[a] + m.g_rbound[b] + margin;
                     keep = !(d_dot(d, d) > bound * bound);
+                    // capsule / cylinder pairs: both shapes lie inside the capsule (segment, radius) around
+                    // their axis, so the segment-segment distance bounds the true distance from below
+                    if (keep && (ta == 3 || ta == 5) && (tb == 3 || tb == 5)) {
+                        double a1[3], a2[3];
+                        for (int side = 0; side < 2; side++) {
+                            const int g = side ? b : a, body = m.g_body[g];
+                            double Rl[9], gq[4] = {m.g_quat[g][0], m.g_quat[g][1], m.g_quat[g][2], m.g_quat[g][3]}, zl[3], *ax = side ? a2 : a1;
+                            d_q2m(Rl, gq);
+                            zl[0] = Rl[2]; zl[1] = Rl[5]; zl[2] = Rl[8];
+                            if (body < 0) { ax[0] = zl[0]; ax[1] = zl[1]; ax[2] = zl[2]; }
+                            else d_mv(ax, W.k.xmat[body], zl);
+                        }
+                        const double h1 = m.g_size[a][1], h2 = m.g_size[b][1];
+                        const double r[3] = {-d[0], -d[1], -d[2]};
+                        const double bb = d_dot(a1, a2), c = d_dot(a1, r), f = d_dot(a2, r), den = 1.0 - bb * bb;
+                        double sp = den > 1e-9 ? c_clamp((bb * f - c) / den, -h1, h1) : 0.0, tp = bb * sp + f;
+                        if (tp < -h2) { tp = -h2; sp = c_clamp(bb * tp - c, -h1, h1); }
+                        else if (tp > h2) { tp = h2; sp = c_clamp(bb * tp - c, -h1, h1); }
+                        double w[3];
+                        for (int k = 0; k < 3; k++) w[k] = r[k] + sp * a1[k] - tp * a2[k];
+                        const double lo = sqrt(d_dot(w, w)) - m.g_size[a][0] - m.g_size[b][0];
+                        keep = lo < margin + 1e-9;
+                    }
+                } else {
+                    // plane pairs: nothing of geom b is closer to the plane than its centre height minus rbound
+                    const int gp = ta == 0 ? a : b, go = ta == 0 ? b : a;
+                    double Rl[9], gq[4] = {m.g_quat[gp][0], m.g_quat[gp][1], m.g_quat[gp][2], m.g_quat[gp][3]};
+                    d_q2m(Rl, gq);
+                    const double hgt = (W.gpos[go][0] - W.gpos[gp][0]) * Rl[2] + (W.gpos[go][1] - W.gpos[gp][1]) * Rl[5] +
+                                       (W.gpos[go][2] - W.gpos[gp][2]) * Rl[8];
+                    keep = hgt - m.g_rbound[go] < margin + 1e-9;
                 }
             }
             const unsigned mask = __ballot_sync(FULL, keep);
@@ -504,10 +574,13 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
         // ---- Y = L^-1 J^T (forward substitution, lane = row), A = Y Y^T
         if (r < nc) {
             double *yr = W.Y + r * YS;
-            for (int k = 0; k < nd; k++) {
+            int k0 = 0;
+            while (k0 < nd && yr[k0] == 0.0) k0++;          // leading exact zeros stay zero
+            for (int k = k0; k < nd; k++) {
                 double s = yr[k];
-                for (int j = 0; j < k; j++) s -= W.L[k * MS + j] * yr[j];
-                yr[k] = s / W.L[k * MS + k];
+                const int j0 = W.blk[k] > k0 ? W.blk[k] : k0;   // L[k][j] = 0 outside k's tree
+                for (int j = j0; j < k; j++) s -= W.L[TRI(k, j)] * yr[j];
+                yr[k] = s / W.L[TRI(k, k)];
             }
             for (int k = nd; k < WD; k++) yr[k] = 0.0;
         }
@@ -517,7 +590,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
             double a = 0;
             if (r < nc)
                 for (int k = 0; k < nd; k++) a += W.Y[r * YS + k] * W.Y[s * YS + k];
-            W.A[s * WC + r] = a;
+            if (r < WC) W.A[s * WC + r] = a;
             if (s == r) diag = a;
         }
         double Rg = 0, b = 0, inv = 0;
@@ -533,8 +606,9 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
         __syncwarp();
         // ---- projected Gauss-Seidel; lane r keeps g_r = (A f + b)_r and f_r.  Stops when the scaled
         // cost improvement of a sweep drops below `tolerance` (MuJoCo's termination rule).
-        W.rD[lane] = diag + Rg;
-        double trM = (lane < nd) ? W.M[lane * MS + lane] : 0.0;
+        if (lane < WC) W.rD[lane] = diag + Rg;
+        const int rr = r < WC ? r : WC - 1;   // lanes beyond the row capacity only mirror the last row (never used)
+        double trM = (lane < nd) ? W.M[TRI(lane, lane)] : 0.0;
         trM = warp_sum(trM);
         const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
         __syncwarp();
@@ -543,7 +617,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
             const bool same = __all_sync(FULL, r >= nc || W.wsig[r] == sig) && W.wn == nc;
             if (same) {
                 f = (r < nc) ? W.wf[r] : 0.0;
-                for (int s = 0; s < nc; s++) g += W.A[s * WC + r] * shfl_d(f, s);
+                for (int s = 0; s < nc; s++) g += W.A[s * WC + rr] * shfl_d(f, s);
             }
         }
         const unsigned types = __ballot_sync(FULL, type == 1);  // rows that start a contact
@@ -561,7 +635,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
                 }
                 dl = shfl_d(dl, s);
                 imp += 0.5 * W.rD[s] * dl * dl;
-                g += W.A[s * WC + r] * dl;
+                g += W.A[s * WC + rr] * dl;
                 if (is_contact) {
 #pragma unroll 1
                     for (int t = 1; t <= 2; t++) {
@@ -569,7 +643,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
                         if (lane == s + t) { const double fn = f - (g + Rg * f) * inv; dt = fn - f; f = fn; }
                         dt = shfl_d(dt, s + t);
                         imp += 0.5 * W.rD[s + t] * dt * dt;
-                        g += W.A[(s + t) * WC + r] * dt;
+                        g += W.A[(s + t) * WC + rr] * dt;
                     }
                     const double fnn = shfl_d(f, s), f1 = shfl_d(f, s + 1), f2 = shfl_d(f, s + 2), mus = shfl_d(mu, s);
                     const double lim = mus * fnn, ft = sqrt(f1 * f1 + f2 * f2);
@@ -581,18 +655,17 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
                             if (lane == s + t) { const double fn = f * sc; dt = fn - f; f = fn; }
                             dt = shfl_d(dt, s + t);
                             imp += 0.5 * W.rD[s + t] * dt * dt;
-                            g += W.A[(s + t) * WC + r] * dt;
+                            g += W.A[(s + t) * WC + rr] * dt;
                         }
                     }
                 }
             }
             if (scale * imp < m.tolerance) break;
         }
-        W.wsig[lane] = sig;
-        W.wf[lane] = f;
+        if (lane < WC) { W.wsig[lane] = sig; W.wf[lane] = f; }
         if (lane == 0) W.wn = nc;
         // ---- J^T f = L (Y^T f)
-        W.f[lane] = (r < nc) ? f : 0.0;
+        if (lane < WC) W.f[lane] = (r < nc) ? f : 0.0;
         __syncwarp();
         if (lane < nd) {
             double zz = 0;
@@ -602,7 +675,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
         __syncwarp();
         if (lane < nd) {
             double s = 0;
-            for (int j = 0; j <= lane; j++) s += W.L[lane * MS + j] * W.z[j];
+            for (int j = 0; j <= lane; j++) s += W.L[TRI(lane, j)] * W.z[j];
             fcv = s;
         }
         __syncwarp();
@@ -613,7 +686,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
     // ---- semi-implicit Euler with implicit joint damping
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
-    w_chol(W.M, m.d_damping, m.h, nd, W.L, lane);
+    w_chol(W.M, m.d_damping, m.h, nd, W.L, lane, W.blk);
     w_solve(W.L, nd, W.rhs, lane);
     if (lane < nd) {
         W.qd[lane] += m.h * W.rhs[lane];
@@ -640,13 +713,15 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS &W, unsigned comp
 }
 
 // kept frame slots: 0 = end-effector body, 1 = cube, 2 = right claw, 3 = left claw
-__device__ __forceinline__ void w_site(double *out, const WarpWS &W, int slot, const double *local) {
+template <int WB, int WG>
+__device__ __forceinline__ void w_site(double *out, const WarpWS<WB, WG> &W, int slot, const double *local) {
     double t[3];
     d_mv(t, W.kxmat[slot], local);
     for (int k = 0; k < 3; k++) out[k] = W.kxpos[slot][k] + t[k];
 }
 
-__device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS &W, float *obs, int lane) {
+template <int WB, int WG>
+__device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, float *obs, int lane) {
     if (lane != 0) return;
     int o = 0;
     for (int k = 0; k < 7; k++) obs[o++] = (float)W.q[T.arm_qadr[k]];
@@ -667,15 +742,15 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS &W, float *o
     for (int k = 0; k < 2; k++) obs[o++] = (float)(cube[k] - target[k]);
 }
 
-constexpr int ENV_WARPS = 8;
 
-__global__ void __launch_bounds__(ENV_WARPS * 32)
+template <int WB, int WG, int ENV_WARPS>
+__global__ void __launch_bounds__(ENV_WARPS * 32, 1)
 env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWS &W = reinterpret_cast<WarpWS *>(smem_raw)[warp];
+    WarpWS<WB, WG> &W = reinterpret_cast<WarpWS<WB, WG> *>(smem_raw)[warp];
     const DynDev &m = c_models[model_slot];
     const int t = blockIdx.x * ENV_WARPS + warp;
     const int e = t < n ? (ids ? ids[t] : t) : 0;
@@ -692,6 +767,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     if (lane < WD) W.bias_prev[lane] = B.bias_prev[(size_t)e * WD + lane];
     if (lane < DMAXA) W.ctrl[lane] = 0.0;
     if (lane == 0) W.wn = 0;
+    if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
     __syncwarp();
     int ncon = 0;
     const int keep[4] = {T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw};
@@ -773,21 +849,31 @@ cudaError_t upload_env_model(int slot, const DynDev &h_model) {
     return cudaMemcpyToSymbol(c_models, &h_model, sizeof(DynDev), sizeof(DynDev) * slot);
 }
 
-cudaError_t launch_env_warp(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
-                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
-                            const int32_t *ids, cudaStream_t stream) {
+template <int WB, int WG, int ENV_WARPS>
+static cudaError_t launch_env_warp_t(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+                                     int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
+                                     const int32_t *ids, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = sizeof(WarpWS) * ENV_WARPS;
+    const size_t smem = sizeof(WarpWS<WB, WG>) * ENV_WARPS;
+    auto kern = env_step_warp_kernel<WB, WG, ENV_WARPS>;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(env_step_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    env_step_warp_kernel<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, T, B, action, action_stride, is_planner,
-                                                                                         mask, n, forward_only, ids);
+    kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, T, B, action, action_stride, is_planner, mask, n,
+                                                                            forward_only, ids);
     return cudaGetLastError();
 }
 
-size_t env_warp_smem_per_warp() { return sizeof(WarpWS); }
+cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
+                            const int32_t *ids, cudaStream_t stream) {
+    if (nb <= 14 && ngeom <= 32)
+        return launch_env_warp_t<14, 32, 14>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+    return launch_env_warp_t<DMAXB, DMAXG, 11>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+}
+
+size_t env_warp_smem_per_warp() { return sizeof(WarpWS<14, 32>); }
 
 }  // namespace mopa

@@ -136,8 +136,10 @@ static int convex_pocs(cpoint *cp, const cgeom *g1, const cgeom *g2, double marg
     int in1 = 0, in2 = 0;
     memcpy(p1, g1->c, sizeof(p1));
     for (int it = 0; it < 16; it++) {
+        double o1[3] = {p1[0], p1[1], p1[2]};
         in2 = core_closest(p2, g2, rho2, p1, n2);
         in1 = core_closest(p1, g1, rho1, p2, n1);
+        if (it > 0 && o1[0] == p1[0] && o1[1] == p1[1] && o1[2] == p1[2]) break; /* exact fixed point: later sweeps repeat it */
     }
     in2 = core_closest(p2, g2, rho2, p1, n2);
     double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, len = sqrt(dot3(d, d)), n[3], dist;
@@ -179,6 +181,7 @@ static int box_box_contacts(cpoint *out, const cgeom *g1, const cgeom *g2, doubl
         double s = fabs(tp) - ra - h2[j];
         if (s > best) { best = s; code = 3 + j; }
     }
+    if (best >= margin) return 0;   /* separated on a face axis: no axis can bring the maximum below margin */
     double ebest = -1e30;
     int ecode = -1;
     double en[3] = {0, 0, 0};

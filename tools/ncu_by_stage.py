@@ -22,10 +22,10 @@ for ln in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m:
         omap[int(m.group(1), 16)] = (cur, inl)
-STAGES = [(80, 97, "w_chol"), (98, 116, "w_solve"), (117, 119, "pair_contacts"), (120, 129, "kbi"), (139, 209, "kinematics"),
-          (210, 230, "inertia"), (231, 241, "velocity chain"), (242, 289, "RNE"), (290, 315, "CRBA"), (316, 338, "forces+qacc0"),
-          (339, 365, "limit rows"), (366, 392, "broadphase"), (393, 447, "narrowphase glue"), (448, 503, "row jacobians"),
-          (504, 533, "Y / A"), (534, 593, "PGS"), (594, 612, "J^T f"), (613, 641, "integrate"), (642, 800, "env epilogue/prologue")]
+STAGES = [(83, 102, "w_chol"), (103, 121, "w_solve"), (122, 124, "pair_contacts"), (125, 134, "kbi"), (144, 214, "kinematics"),
+          (215, 235, "inertia"), (236, 246, "velocity chain"), (247, 294, "RNE"), (295, 320, "CRBA"), (321, 343, "forces+qacc0"),
+          (344, 369, "limit rows"), (370, 432, "broadphase"), (433, 487, "narrowphase glue"), (488, 540, "row jacobians"),
+          (541, 573, "Y / A"), (574, 633, "PGS"), (634, 652, "J^T f"), (653, 682, "integrate"), (683, 900, "env epilogue/prologue")]
 def stage(key):
     (f, l), outer = key
     if f != "env_warp.cu":
