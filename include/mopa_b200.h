@@ -141,6 +141,8 @@ typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
 int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out);
 void mopa_env_destroy(mopa_env *e);
 int mopa_env_enable_contacts(mopa_env *e, int32_t on);
+/* diagnostics: per-stage clock sums of the env-step kernel, collected when MOPA_ENV_PROF=1 is set at create time */
+int mopa_env_debug_prof(mopa_env *e, uint64_t *out32);
 /* sim.forward() + _get_obs() for the listed envs (d_ids nullable = all n): refreshes bias_prev and obs
  * from qpos/qvel.  Called after reset / set_state. */
 int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_ids, int32_t n, void *stream);

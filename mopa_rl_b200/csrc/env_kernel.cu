@@ -19,6 +19,8 @@
 namespace mopa {
 struct DynDev;
 cudaError_t upload_env_model(int slot, const DynDev &h_model);
+cudaError_t env_tune_set(int prof, int sync_mask);
+cudaError_t env_prof_read(unsigned long long *out);
 cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream);
@@ -239,6 +241,10 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     static int next_slot = 0;
     e->model_slot = (next_slot++) % 2;   // up to 2 live scenes per process share the constant bank round-robin
     if (err == cudaSuccess) err = mopa::upload_env_model(e->model_slot, e->h_model);
+    if (err == cudaSuccess) {   // tuning / profiling hooks of the warp kernel (defaults: no profiling, all stage barriers)
+        const char *pf = getenv("MOPA_ENV_PROF"), *sm = getenv("MOPA_ENV_SYNC_MASK");
+        err = mopa::env_tune_set(pf ? atoi(pf) : 0, sm ? (int)strtol(sm, nullptr, 0) : 0xFE);
+    }
     if (err != cudaSuccess) {
         mopa_set_error(std::string("mopa_env_create: ") + cudaGetErrorString(err) + " (a CUDA device is required; there is no CPU fallback)");
         delete e;
@@ -261,6 +267,14 @@ int mopa_env_enable_contacts(mopa_env *e, int32_t on) {
     ENV_TRY(cudaSetDevice(e->device));
     ENV_TRY(cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice));
     ENV_TRY(mopa::upload_env_model(e->model_slot, e->h_model));
+    return MOPA_OK;
+}
+
+int mopa_env_debug_prof(mopa_env *e, uint64_t *out32) {
+    if (!e || !out32) return MOPA_ERR_ARG;
+    ENV_TRY(cudaSetDevice(e->device));
+    ENV_TRY(cudaDeviceSynchronize());
+    ENV_TRY(mopa::env_prof_read((unsigned long long *)out32));
     return MOPA_OK;
 }
 

@@ -19,6 +19,7 @@
 // at rounding level (tests: 1e-5 absolute on qpos / qvel as BASELINE.json states).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/mopa_b200.h"
@@ -49,20 +50,18 @@ struct WarpWS {
     double q[40], v[40];
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
         WarpKin<WB> k;
-        double A[WC * WC];   // A[s * WC + r] = A_rs (column s contiguous over lanes r)
+        double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
     };
     double kxpos[4][3], kxquat[4][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
-    double rD[WC];
     double M[NTRI], L[NTRI];
-    double qd[WD], bias[WD], tau[WD], qacc0[WD], fc[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
+    double qd[WD], bias[WD], tau[WD], qacc0[WD], a[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
     double Y[WC * YS];
     double f[WC];
     double gpos[WG][3];
     double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
     int cga[WCP], cgb[WCP], csig[WCP];
-    int wsig[WC];            // warm start: row identities and forces of the previous substep
-    double wf[WC];
-    int wn;
+    double wa[WD];           // warm start: acceleration of the previous substep (mjData.qacc_warmstart)
+    int wn;                  // ... and whether it exists
     int blk[WD];             // first dof of the kinematic tree that owns each dof
     int cand[WCAND];
     int ncand, ncp;
@@ -73,6 +72,9 @@ struct WarpWS {
 // scene constants: uniform reads go through the constant cache instead of global loads
 constexpr int ENV_MODEL_SLOTS = 2;
 __constant__ DynDev c_models[ENV_MODEL_SLOTS];
+struct EnvTune { int prof, sync_mask; };
+__constant__ EnvTune c_tune;
+__device__ unsigned long long g_prof[32];   // [2k] work before stage barrier k, [2k+1] wait at it; 20 = PGS sweeps, 21 = rows, 22 = substeps
 
 __device__ __forceinline__ double shfl_d(double x, int src) { return __shfl_sync(FULL, x, src); }
 __device__ __forceinline__ double warp_sum(double x) {
@@ -84,11 +86,8 @@ __device__ __forceinline__ double warp_sum(double x) {
 // ---- lane = row right-looking Cholesky of (M + hs * diag) into L (lower, stride MS)
 // `blk[i]` = first dof of the kinematic tree that owns dof i: M is block diagonal by tree, so all entries
 // outside a row's block are exact zeros and are skipped (bitwise the same factor as the dense algorithm).
-__device__ __noinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane, const int *blk) {
-    const int b0 = lane < nd ? blk[lane] : 0;
-    if (lane < nd)
-        for (int k = 0; k <= lane; k++) L[TRI(lane, k)] = M[TRI(lane, k)] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
-    __syncwarp();
+__device__ __noinline__ void w_chol_inplace(double *L, int nd, int lane, const int *blk) {
+    const int b0 = (lane < nd && blk) ? blk[lane] : 0;
     for (int j = 0; j < nd; j++) {
         const double d = sqrt(L[TRI(j, j)]);
         __syncwarp();
@@ -102,6 +101,12 @@ __device__ __noinline__ void w_chol(const double *M, const double *diag, double 
         }
         __syncwarp();
     }
+}
+__device__ __forceinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane, const int *blk) {
+    if (lane < nd)
+        for (int k = 0; k <= lane; k++) L[TRI(lane, k)] = M[TRI(lane, k)] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
+    __syncwarp();
+    w_chol_inplace(L, nd, lane, blk);
 }
 // single right-hand side, lane-parallel column-oriented substitution; x (shared, nd entries) in place
 __device__ __noinline__ void w_solve(const double *L, int nd, double *x, int lane) {
@@ -135,13 +140,16 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 // `comp` the dofs whose qfrc_applied is the previous qfrc_bias.  integrate=false: kinematics + bias only.
 // `sync`: the warps of a CTA walk the stages in step (CTA barrier between stages) so that they share
 // instruction-cache lines; `active` = false warps only take part in the barriers.
-#define STAGE_SYNC() do { if (sync) __syncthreads(); } while (0)
+// profiling / tuning hooks (MOPA_ENV_PROF=1, MOPA_ENV_SYNC_MASK=bits): per-stage clock64 sums, lane 0 of every warp
+#define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
+#define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
 template <int WB, int WG>
-__device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int *keep,
+__device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
+    long long t_last = c_tune.prof ? clock64() : 0;
     if (!active) {   // barrier-only participant: one barrier per stage boundary below
-        for (int k = 0; k < 7; k++) STAGE_SYNC();
+        for (int k = 1; k <= 7; k++) STAGE_SYNC(k);
         return;
     }
     if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
@@ -206,9 +214,13 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
             d_qmul(quat, Pq, lq);
         }
         d_q2m(R, quat);
-        if (lane < 3) W.k.xpos[i][lane] = pos[lane];
-        if (lane < 4) W.k.xquat[i][lane] = quat[lane];
-        if (lane < 9) W.k.xmat[i][lane] = R[lane];
+        // predicated stores with compile-time indices (a lane-indexed register array would live in local memory)
+#pragma unroll
+        for (int k = 0; k < 3; k++) if (lane == k) W.k.xpos[i][k] = pos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (lane == 4 + k) W.k.xquat[i][k] = quat[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) if (lane == 8 + k) W.k.xmat[i][k] = R[k];
         __syncwarp();
     }
     if (lane < nb) {
@@ -240,12 +252,12 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     }
     __syncwarp();
     if (lane < 4) {
-        const int b = keep[lane];
+        const int b = lane == 0 ? keep_bodies.x : (lane == 1 ? keep_bodies.y : (lane == 2 ? keep_bodies.z : keep_bodies.w));
         for (int k = 0; k < 3; k++) W.kxpos[lane][k] = W.k.xpos[b][k];
         for (int k = 0; k < 4; k++) W.kxquat[lane][k] = W.k.xquat[b][k];
         for (int k = 0; k < 9; k++) W.kxmat[lane][k] = W.k.xmat[b][k];
     }
-    STAGE_SYNC();   // 1: kinematics done
+    STAGE_SYNC(1);   // 1: kinematics done
     // ---- spatial inertia about the origin, lane = body
     if (lane < nb) {
         const int i = lane;
@@ -325,7 +337,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     }
     __syncwarp();
     if (!integrate) return;
-    STAGE_SYNC();   // 2: RNE done
+    STAGE_SYNC(2);   // 2: RNE done
     // ---- composite inertias (lanes = 13 components), joint-space inertia (lane = dof)
     for (int i = nb - 1; i >= 0; i--) {
         const int p = m.b_parent[i];
@@ -367,13 +379,13 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
         W.tau[k] += m.a_gear[a] * f;   // one actuator per dof in the scenes compiled here
     }
     __syncwarp();
-    STAGE_SYNC();   // 3: inertia matrix and forces done
+    STAGE_SYNC(3);   // 3: inertia matrix and forces done
     w_chol(W.M, nullptr, 0.0, nd, W.L, lane, W.blk);
     if (lane < nd) W.qacc0[lane] = W.tau[lane];
     __syncwarp();
     w_solve(W.L, nd, W.qacc0, lane);
 
-    STAGE_SYNC();   // 4: unconstrained acceleration done
+    STAGE_SYNC(4);   // 4: unconstrained acceleration done
     // ---- constraint rows.  Limits first (dof order), then contacts (pair order).
     int nlim = 0;
     {
@@ -422,6 +434,28 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
                     const double d[3] = {W.gpos[b][0] - W.gpos[a][0], W.gpos[b][1] - W.gpos[a][1], W.gpos[b][2] - W.gpos[a][2]};
                     const double bound = m.g_rbound[a] + m.g_rbound[b] + margin;
                     keep = !(d_dot(d, d) > bound * bound);
+                    // box pairs: the bounding sphere of a flat box (table, bin walls) is hopelessly loose; test the
+                    // other geom's bounding sphere against the box itself (exact point-to-box distance)
+                    if (keep && (ta == 6 || tb == 6)) {
+                        const bool box_a = ta == 6 && (tb != 6 || m.g_rbound[a] >= m.g_rbound[b]);
+                        const int gx = box_a ? a : b, go = box_a ? b : a, body = m.g_body[gx];
+                        double Rl[9], gq[4] = {m.g_quat[gx][0], m.g_quat[gx][1], m.g_quat[gx][2], m.g_quat[gx][3]};
+                        d_q2m(Rl, gq);
+                        double t[3] = {box_a ? d[0] : -d[0], box_a ? d[1] : -d[1], box_a ? d[2] : -d[2]};   // other centre - box centre
+                        if (body >= 0) {
+                            const double *X = W.k.xmat[body];
+                            const double u0 = X[0] * t[0] + X[3] * t[1] + X[6] * t[2], u1 = X[1] * t[0] + X[4] * t[1] + X[7] * t[2],
+                                         u2 = X[2] * t[0] + X[5] * t[1] + X[8] * t[2];
+                            t[0] = u0; t[1] = u1; t[2] = u2;
+                        }
+                        double e2 = 0;
+                        for (int k = 0; k < 3; k++) {
+                            const double l = Rl[k] * t[0] + Rl[3 + k] * t[1] + Rl[6 + k] * t[2], ex = fabs(l) - m.g_size[gx][k];
+                            if (ex > 0) e2 += ex * ex;
+                        }
+                        const double bo = m.g_rbound[go] + margin + 1e-9;
+                        keep = !(e2 > bo * bo);
+                    }
                     // capsule / cylinder pairs: both shapes lie inside the capsule (segment, radius) around
                     // their axis, so the segment-segment distance bounds the true distance from below
                     if (keep && (ta == 3 || ta == 5) && (tb == 3 || tb == 5)) {
@@ -462,6 +496,8 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
         }
         if (ncand > WCAND) ncand = WCAND;
         __syncwarp();
+        PROF_MARK(23);
+        if (c_tune.prof && lane == 0) atomicAdd(&g_prof[29], (unsigned long long)ncand);
         const int maxcp = min(WCP, (WC - nlim) / 3);
         for (int base = 0; base < ncand; base += 32) {
             const int ci = base + lane;
@@ -512,9 +548,10 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
             if (ncp >= maxcp) { ncp = maxcp; break; }
         }
         __syncwarp();
+        PROF_MARK(24);
     }
     ncon_out = ncp;
-    STAGE_SYNC();   // 5: contact points done
+    STAGE_SYNC(5);   // 5: contact points done
     const int nc = nlim + 3 * ncp;
     double fcv = 0.0;  // lane k: constraint force on dof k
     if (nc > 0) {
@@ -568,121 +605,195 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
                 }
             }
         }
-        double jv = 0, ja = 0;
+        double jv = 0;
         if (r < nc)
-            for (int k = 0; k < nd; k++) { jv += W.Y[r * YS + k] * W.qd[k]; ja += W.Y[r * YS + k] * W.qacc0[k]; }
-        // ---- Y = L^-1 J^T (forward substitution, lane = row), A = Y Y^T
+            for (int k = 0; k < nd; k++) jv += W.Y[r * YS + k] * W.qd[k];
+        __syncwarp();   // every Jacobian row is complete: the kinematic arrays may now be overwritten (W.A aliases them)
+        // ---- regulariser R = (1 - imp) / imp * (J M^-1 J^T)_rr with y = L^-1 J^T by forward substitution (lane = row)
+        double aref = 0, Dr = 0;
         if (r < nc) {
-            double *yr = W.Y + r * YS;
+            const double *jr = W.Y + r * YS;
+            double *yr = W.A + r * WD;
             int k0 = 0;
-            while (k0 < nd && yr[k0] == 0.0) k0++;          // leading exact zeros stay zero
+            while (k0 < nd && jr[k0] == 0.0) k0++;          // leading exact zeros stay zero
+            double diag = 0;
             for (int k = k0; k < nd; k++) {
-                double s = yr[k];
+                double s = jr[k];
                 const int j0 = W.blk[k] > k0 ? W.blk[k] : k0;   // L[k][j] = 0 outside k's tree
                 for (int j = j0; j < k; j++) s -= W.L[TRI(k, j)] * yr[j];
-                yr[k] = s / W.L[TRI(k, k)];
+                s = s / W.L[TRI(k, k)];
+                yr[k] = s;
+                diag += s * s;
             }
-            for (int k = nd; k < WD; k++) yr[k] = 0.0;
-        }
-        __syncwarp();
-        double diag = 0;
-        for (int s = 0; s < nc; s++) {
-            double a = 0;
-            if (r < nc)
-                for (int k = 0; k < nd; k++) a += W.Y[r * YS + k] * W.Y[s * YS + k];
-            if (r < WC) W.A[s * WC + r] = a;
-            if (s == r) diag = a;
-        }
-        double Rg = 0, b = 0, inv = 0;
-        if (r < nc) {
             double K, B, imp;
             kbi_ni(m, solref, solimp, pos, margin, K, B, imp);
-            const double aref = type <= 1 ? (-B * jv - K * imp * (pos - margin)) : (-B * jv);
-            Rg = (1 - imp) / imp * diag;
+            aref = type <= 1 ? (-B * jv - K * imp * (pos - margin)) : (-B * jv);
+            double Rg = (1 - imp) / imp * diag;
             if (Rg < DYN_MINVAL) Rg = DYN_MINVAL;
-            b = ja - aref;
-            inv = 1.0 / (diag + Rg);
+            Dr = 1.0 / Rg;
         }
-        __syncwarp();
-        // ---- projected Gauss-Seidel; lane r keeps g_r = (A f + b)_r and f_r.  Stops when the scaled
-        // cost improvement of a sweep drops below `tolerance` (MuJoCo's termination rule).
-        if (lane < WC) W.rD[lane] = diag + Rg;
-        const int rr = r < WC ? r : WC - 1;   // lanes beyond the row capacity only mirror the last row (never used)
+        // friction rows share the normal row's D (impratio 1); `base` = first row of this lane's block
+        const int dirn = type == 2 ? ((sig & 3)) : 0, base = r - dirn;
+        Dr = shfl_d(Dr, base & 31);
+        PROF_MARK(25);
+        // ---- Newton solver on MuJoCo's primal problem (mj_solNewton; same algorithm as oracle/orc_dyn.c):
+        //   min_a 1/2 (a - a0)^T M (a - a0) + sum_c s_c(J_c a - aref_c),  elliptic cones, exact line search.
+        // lane = row for x = J a - aref, the cone terms and J p; lane = dof for M a, the gradient and the search direction.
+        const int ntri = nd * (nd + 1) / 2;
         double trM = (lane < nd) ? W.M[TRI(lane, lane)] : 0.0;
         trM = warp_sum(trM);
         const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
-        __syncwarp();
-        double g = b, f = 0.0;
-        {   // warm start from the previous substep when the constraint set is unchanged
-            const bool same = __all_sync(FULL, r >= nc || W.wsig[r] == sig) && W.wn == nc;
-            if (same) {
-                f = (r < nc) ? W.wf[r] : 0.0;
-                for (int s = 0; s < nc; s++) g += W.A[s * WC + rr] * shfl_d(f, s);
+        double cost = 0, x0 = 0, x1 = 0, x2 = 0, gsr = 0, h0 = 0, h1 = 0, h2 = 0;
+        // evaluates cost / gradient (W.rhs) / M a - tau (W.z) at W.a; with_hess: Hessian (lower triangle) -> W.L
+        auto newton_eval = [&](bool with_hess) {
+            double mat = 0, cq = 0;
+            if (lane < nd) {
+                for (int j = 0; j < nd; j++) mat += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.a[j];
+                mat -= W.tau[lane];
+                cq = 0.5 * (W.a[lane] - W.qacc0[lane]) * mat;
+                W.z[lane] = mat;
             }
-        }
-        const unsigned types = __ballot_sync(FULL, type == 1);  // rows that start a contact
-        for (int it = 0; it < m.iterations; it++) {
-            double imp = 0.0;
-            for (int s = 0; s < nc; s++) {
-                const bool is_contact = (types >> s) & 1u;
-                if (!is_contact && s >= nlim) continue;   // tangent rows are handled with their normal row
-                double dl = 0.0;
-                if (lane == s) {
-                    double fn = f - (g + Rg * f) * inv;
-                    fn = fn > 0 ? fn : 0;
-                    dl = fn - f;
-                    f = fn;
-                }
-                dl = shfl_d(dl, s);
-                imp += 0.5 * W.rD[s] * dl * dl;
-                g += W.A[s * WC + rr] * dl;
-                if (is_contact) {
-#pragma unroll 1
-                    for (int t = 1; t <= 2; t++) {
-                        double dt = 0.0;
-                        if (lane == s + t) { const double fn = f - (g + Rg * f) * inv; dt = fn - f; f = fn; }
-                        dt = shfl_d(dt, s + t);
-                        imp += 0.5 * W.rD[s + t] * dt * dt;
-                        g += W.A[(s + t) * WC + rr] * dt;
-                    }
-                    const double fnn = shfl_d(f, s), f1 = shfl_d(f, s + 1), f2 = shfl_d(f, s + 2), mus = shfl_d(mu, s);
-                    const double lim = mus * fnn, ft = sqrt(f1 * f1 + f2 * f2);
-                    if (ft > lim) {
-                        const double sc = ft > DYN_MINVAL ? lim / ft : 0.0;
-#pragma unroll 1
-                        for (int t = 1; t <= 2; t++) {
-                            double dt = 0.0;
-                            if (lane == s + t) { const double fn = f * sc; dt = fn - f; f = fn; }
-                            dt = shfl_d(dt, s + t);
-                            imp += 0.5 * W.rD[s + t] * dt * dt;
-                            g += W.A[(s + t) * WC + rr] * dt;
-                        }
-                    }
+            double x = 0;
+            if (r < nc) {
+                for (int k = 0; k < nd; k++) x += W.Y[r * YS + k] * W.a[k];
+                x -= aref;
+            }
+            x0 = shfl_d(x, base & 31); x1 = shfl_d(x, (base + 1) & 31); x2 = shfl_d(x, (base + 2) & 31);
+            double sc = 0;
+            gsr = 0; h0 = 0; h1 = 0; h2 = 0;
+            if (type == 0) {
+                if (x < 0) { gsr = Dr * x; h0 = Dr; sc = 0.5 * Dr * x * x; }
+            } else if (type >= 1) {
+                const double t = sqrt(x1 * x1 + x2 * x2);
+                if (x0 >= mu * t) { }                                   // top zone: inactive
+                else if (mu * x0 + t <= 0) {                            // bottom zone: quadratic in all three rows
+                    gsr = Dr * x; 
+                    if (dirn == 0) { h0 = Dr; sc = 0.5 * Dr * (x0 * x0 + x1 * x1 + x2 * x2); } else if (dirn == 1) h1 = Dr; else h2 = Dr;
+                } else {                                                // middle zone: distance to the cone surface
+                    const double Dm = Dr / (1 + mu * mu), e = x0 - mu * t, u1 = -mu * x1 / t, u2 = -mu * x2 / t;
+                    const double c = -Dm * e * mu / t, t2 = t * t;
+                    if (dirn == 0) { gsr = Dm * e; h0 = Dm; h1 = Dm * u1; h2 = Dm * u2; sc = 0.5 * Dm * e * e; }
+                    else if (dirn == 1) { gsr = Dm * e * u1; h0 = Dm * u1; h1 = Dm * u1 * u1 + c * (1 - x1 * x1 / t2); h2 = Dm * u1 * u2 + c * (-x1 * x2 / t2); }
+                    else { gsr = Dm * e * u2; h0 = Dm * u2; h1 = Dm * u1 * u2 + c * (-x1 * x2 / t2); h2 = Dm * u2 * u2 + c * (1 - x2 * x2 / t2); }
                 }
             }
-            if (scale * imp < m.tolerance) break;
-        }
-        if (lane < WC) { W.wsig[lane] = sig; W.wf[lane] = f; }
-        if (lane == 0) W.wn = nc;
-        // ---- J^T f = L (Y^T f)
-        if (lane < WC) W.f[lane] = (r < nc) ? f : 0.0;
+            cost = warp_sum(cq + sc);
+            if (lane < WC) W.f[lane] = gsr;
+            __syncwarp();
+            if (lane < nd) {
+                double gg = mat;
+                for (int s2 = 0; s2 < nc; s2++) gg += W.Y[s2 * YS + lane] * W.f[s2];
+                W.rhs[lane] = gg;
+            }
+            if (with_hess) {
+                // K_r = sum_q Hc[dirn][q] J_(base+q)  ->  H = M + sum_r J_r^T K_r
+                if (r < nc) {
+                    const bool blockrow = type >= 1;
+                    for (int j = 0; j < nd; j++) {
+                        double kk = h0 * W.Y[base * YS + j];
+                        if (blockrow) kk += h1 * W.Y[(base + 1) * YS + j] + h2 * W.Y[(base + 2) * YS + j];
+                        W.A[r * WD + j] = kk;
+                    }
+                }
+                __syncwarp();
+                for (int e = lane; e < ntri; e += 32) {
+                    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                    while (TRI(i + 1, 0) <= e) i++;
+                    while (TRI(i, 0) > e) i--;
+                    const int j = e - TRI(i, 0);
+                    double hh = W.M[e];
+                    for (int s2 = 0; s2 < nc; s2++) hh += W.Y[s2 * YS + i] * W.A[s2 * WD + j];
+                    W.L[e] = hh;
+                }
+            }
+            __syncwarp();
+        };
+        // warm start: the previous substep's acceleration unless the unconstrained one costs less.
+        // One evaluation site: phase 0 = cost at a0, 1 = full evaluation at the warm start, 2 = full evaluation
+        // at a0 (no / rejected warm start), 3 = evaluation after a Newton step.
+        if (lane < nd) W.a[lane] = W.qacc0[lane];
         __syncwarp();
-        if (lane < nd) {
-            double zz = 0;
-            for (int s = 0; s < nc; s++) zz += W.Y[s * YS + lane] * W.f[s];
-            W.z[lane] = zz;
+        int phase = W.wn ? 0 : 2, it = 0;
+        double c0 = 0, old = 0;
+        for (;;) {
+            newton_eval(phase >= 1);
+            if (phase == 0) {
+                c0 = cost;
+                if (lane < nd) W.a[lane] = W.wa[lane];
+                __syncwarp();
+                phase = 1;
+                continue;
+            }
+            if (phase == 1 && !(cost < c0)) {
+                if (lane < nd) W.a[lane] = W.qacc0[lane];
+                __syncwarp();
+                phase = 2;
+                continue;
+            }
+            if (phase == 3 && scale * (old - cost) < m.tolerance) break;
+            phase = 3;
+            if (it++ >= m.iterations) break;
+            const double gme = lane < nd ? W.rhs[lane] : 0.0;
+            const double gn = warp_sum(gme * gme);
+            if (scale * sqrt(gn) < m.tolerance) break;
+            if (c_tune.prof && lane == 0) { atomicAdd(&g_prof[20], 1ULL); if (it == m.iterations) atomicAdd(&g_prof[28], 1ULL); }
+            // search direction p = -H^-1 g (W.rhs in place; W.z keeps M a - tau)
+            const double matme = lane < nd ? W.z[lane] : 0.0;
+            w_chol_inplace(W.L, nd, lane, nullptr);
+            if (lane < nd) W.rhs[lane] = -gme;
+            __syncwarp();
+            w_solve(W.L, nd, W.rhs, lane);
+            double pme = 0, mp = 0;
+            if (lane < nd) {
+                pme = W.rhs[lane];
+                for (int j = 0; j < nd; j++) mp += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.rhs[j];
+            }
+            const double q1 = warp_sum(pme * matme), q2 = warp_sum(pme * mp), d0 = warp_sum(pme * gme);
+            double jp = 0;
+            if (r < nc)
+                for (int k = 0; k < nd; k++) jp += W.Y[r * YS + k] * W.rhs[k];
+            const double jp0 = shfl_d(jp, base & 31), jp1 = shfl_d(jp, (base + 1) & 31), jp2 = shfl_d(jp, (base + 2) & 31);
+            // exact line search: safeguarded Newton iteration on phi'(alpha)
+            double alpha = 1.0, lo = 0.0, hi = -1.0;
+            for (int ls = 0; ls < 24; ls++) {
+                double d1 = 0, d2 = 0;
+                if (type == 0) {
+                    const double xa = x0 + alpha * jp0;
+                    if (xa < 0) { d1 = Dr * xa * jp0; d2 = Dr * jp0 * jp0; }
+                } else if (type == 1) {
+                    const double a0 = x0 + alpha * jp0, a1 = x1 + alpha * jp1, a2 = x2 + alpha * jp2, t = sqrt(a1 * a1 + a2 * a2);
+                    if (a0 >= mu * t) { }
+                    else if (mu * a0 + t <= 0) { d1 = Dr * (a0 * jp0 + a1 * jp1 + a2 * jp2); d2 = Dr * (jp0 * jp0 + jp1 * jp1 + jp2 * jp2); }
+                    else {
+                        const double Dm = Dr / (1 + mu * mu), e = a0 - mu * t, u1 = -mu * a1 / t, u2 = -mu * a2 / t, c = -Dm * e * mu / t;
+                        const double uj = jp0 + u1 * jp1 + u2 * jp2, tj = (a1 * jp1 + a2 * jp2) / t;
+                        d1 = Dm * e * uj;
+                        d2 = Dm * uj * uj + c * (jp1 * jp1 + jp2 * jp2 - tj * tj);
+                    }
+                }
+                d1 = warp_sum(d1) + q1 + alpha * q2;
+                d2 = warp_sum(d2) + q2;
+                if (fabs(d1) <= 1e-6 * fabs(d0)) break;
+                if (d1 < 0) lo = alpha; else hi = alpha;
+                double an = alpha - d1 / d2;
+                if (hi >= 0) { if (!(an > lo && an < hi)) an = 0.5 * (lo + hi); }
+                else if (!(an > lo)) an = 2 * alpha;
+                alpha = an;
+            }
+            if (lane < nd) W.a[lane] += alpha * pme;
+            __syncwarp();
+            old = cost;
         }
-        __syncwarp();
-        if (lane < nd) {
-            double s = 0;
-            for (int j = 0; j <= lane; j++) s += W.L[TRI(lane, j)] * W.z[j];
-            fcv = s;
-        }
+        if (c_tune.prof && lane == 0) { atomicAdd(&g_prof[21], (unsigned long long)nc); atomicAdd(&g_prof[22], 1ULL); }
+        PROF_MARK(26);
+        // constraint force on the dofs: J^T f = -(J^T grad s) = (M a - tau) - g
+        if (lane < nd) { fcv = W.z[lane] - W.rhs[lane]; W.wa[lane] = W.a[lane]; }
+        if (lane == 0) W.wn = 1;
         __syncwarp();
     }
     else if (lane == 0)
         W.wn = 0;
-    STAGE_SYNC();   // 6: constraint forces done
+    STAGE_SYNC(6);   // 6: constraint forces done
     // ---- semi-implicit Euler with implicit joint damping
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
@@ -709,7 +820,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
         }
     }
     __syncwarp();
-    STAGE_SYNC();   // 7: state advanced
+    STAGE_SYNC(7);   // 7: state advanced
 }
 
 // kept frame slots: 0 = end-effector body, 1 = cube, 2 = right claw, 3 = left claw
@@ -744,7 +855,7 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, 
 
 
 template <int WB, int WG, int ENV_WARPS>
-__global__ void __launch_bounds__(ENV_WARPS * 32, 1)
+__global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 ? 2 : 1))
 env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
@@ -758,7 +869,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (!forward_only) {
             int dummy = 0;
-            for (int s = 0; s < T.nsub; s++) w_substep(m, W, 0u, true, lane, dummy, nullptr, false, true);
+            for (int s = 0; s < T.nsub; s++) w_substep(m, W, 0u, true, lane, dummy, make_int4(0, 0, 0, 0), false, true);
         }
         return;
     }
@@ -770,7 +881,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
     __syncwarp();
     int ncon = 0;
-    const int keep[4] = {T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw};
+    const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw);
     if (forward_only) {
         w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
         if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
@@ -844,6 +955,15 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     }
 }
 
+cudaError_t env_tune_set(int prof, int sync_mask) {
+    EnvTune t{prof, sync_mask};
+    cudaError_t e = cudaMemcpyToSymbol(c_tune, &t, sizeof(t));
+    if (e != cudaSuccess) return e;
+    unsigned long long z[32] = {0};
+    return cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+}
+cudaError_t env_prof_read(unsigned long long *out) { return cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32); }
+
 cudaError_t upload_env_model(int slot, const DynDev &h_model) {
     if (slot < 0 || slot >= ENV_MODEL_SLOTS) return cudaErrorInvalidValue;
     return cudaMemcpyToSymbol(c_models, &h_model, sizeof(DynDev), sizeof(DynDev) * slot);
@@ -869,6 +989,10 @@ static cudaError_t launch_env_warp_t(int model_slot, const mopa_sawyer_task &T, 
 cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream) {
+    static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
+    if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
+    if (nb <= 14 && ngeom <= 32 && small_warps)
+        return launch_env_warp_t<14, 32, 7>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     if (nb <= 14 && ngeom <= 32)
         return launch_env_warp_t<14, 32, 14>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     return launch_env_warp_t<DMAXB, DMAXG, 11>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);

@@ -8,11 +8,10 @@
  *   -> passive damping, position/velocity actuators with ctrl/force clamps, qfrc_applied
  *   -> qacc_smooth = M^-1 tau -> soft constraints (joint limits, frictional contacts with
  *   solref/solimp impedance and elliptic cones) -> semi-implicit Euler with implicit damping.
- * Documented departures: the constraint forces are found by projected Gauss-Seidel
- * on the dual problem (MuJoCo's own "PGS" solver family; the reference uses the Newton solver,
- * same convex problem), at most `iterations` sweeps, stopped early when the scaled cost improvement
- * of a sweep falls below `tolerance` (as MuJoCo's solvers do), no warm start; the regulariser uses the
- * exact diagonal of J M^-1 J^T instead of MuJoCo's precomputed invweight0 approximation; contacts
+ * The constraint forces solve MuJoCo's primal convex problem with the Newton solver the reference
+ * uses (elliptic cones, exact line search, warm start from the previous substep's acceleration,
+ * `iterations` / `tolerance` from the XML).  Documented departures: the regulariser uses
+ * the exact diagonal of J M^-1 J^T instead of MuJoCo's precomputed invweight0 approximation; contacts
  * are condim-3 (no torsional / rolling friction); no noslip post-pass.
  */
 #include <math.h>
@@ -149,6 +148,28 @@ static void kbi(const dyn_model *m, const double *solref, const double *solimp, 
     *K = 1 / (kd > MINVAL ? kd : MINVAL);
     *B = 2 / (bd > MINVAL ? bd : MINVAL);
     *imp = im;
+}
+
+
+/* penalty of one elliptic contact at x = (x_n, x_t1, x_t2): returns s, writes grad[3], H[9] (row-major) and the zone
+   (0 top: inactive, 1 bottom: quadratic, 2 middle: cone surface) */
+static double orc_cone(double mu, double D, const double *x, double *grad, double *H, int *zone) {
+    const double t = sqrt(x[1] * x[1] + x[2] * x[2]);
+    for (int k = 0; k < 9; k++) H[k] = 0;
+    grad[0] = grad[1] = grad[2] = 0;
+    if (x[0] >= mu * t) { *zone = 0; return 0.0; }
+    if (mu * x[0] + t <= 0) {
+        *zone = 1;
+        for (int k = 0; k < 3; k++) { grad[k] = D * x[k]; H[4 * k] = D; }
+        return 0.5 * D * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    }
+    *zone = 2;
+    const double Dm = D / (1 + mu * mu), e = x[0] - mu * t, u[3] = {1.0, -mu * x[1] / t, -mu * x[2] / t};
+    for (int p = 0; p < 3; p++) { grad[p] = Dm * e * u[p]; for (int q = 0; q < 3; q++) H[3 * p + q] = Dm * u[p] * u[q]; }
+    const double c = -Dm * e * mu / t;   /* > 0: curvature of the cone surface */
+    H[4] += c * (1 - x[1] * x[1] / (t * t)); H[5] += c * (-x[1] * x[2] / (t * t));
+    H[7] += c * (-x[1] * x[2] / (t * t));    H[8] += c * (1 - x[2] * x[2] / (t * t));
+    return 0.5 * Dm * e * e;
 }
 
 /* one mj_step.  qpos[nq], qvel[nv] updated in place; ctrl[nact]; applied[nd] = qfrc_applied on the
@@ -329,80 +350,126 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
     double fc[DMAXD];
     memset(fc, 0, sizeof(fc));
     if (nc > 0) {
-        double(*MiJ)[DMAXD] = (double(*)[DMAXD])malloc(sizeof(double) * DMAXD * nc);
-        double *A = (double *)malloc(sizeof(double) * nc * nc), *b = (double *)malloc(sizeof(double) * nc),
-               *Rg = (double *)malloc(sizeof(double) * nc), *f = (double *)calloc(nc, sizeof(double));
+        /* ---- constraint forces: MuJoCo's primal problem
+         *   min_a  1/2 (a - a0)^T M (a - a0) + sum_c s_c(J_c a - aref_c)
+         * solved by Newton's method with an exact line search (mj_solNewton).  s is the quadratic penalty
+         * 1/2 D x^2 for x < 0 on a joint-limit row and, for a frictional contact (rows n, t1, t2 sharing the
+         * normal row's D, impratio 1), 1/2 D dist^2(x, K*) with K* = {x_n >= mu |x_t|} the dual of the elliptic
+         * friction cone: zero inside K* ("top zone"), 1/2 D |x|^2 in the polar cone mu x_n + |x_t| <= 0
+         * ("bottom zone"), 1/2 D (x_n - mu |x_t|)^2 / (1 + mu^2) in between ("middle zone") -
+         * mj_constraintUpdate's elliptic branch.  Strictly convex, so the minimiser is unique. */
+        double *aref = (double *)malloc(sizeof(double) * nc), *Dr = (double *)malloc(sizeof(double) * nc);
         for (int r = 0; r < nc; r++) {
-            memcpy(MiJ[r], rows[r].J, sizeof(double) * nd);
-            CHOL_SOLVE(L, MiJ[r]);
-        }
-        /* warm start: reuse the previous substep's forces when the constraint set is unchanged */
-        if (warm && warm->n == nc) {
-            int same = 1;
-            for (int r = 0; r < nc; r++) if (warm->sig[r] != rows[r].sig) same = 0;
-            if (same) for (int r = 0; r < nc; r++) f[r] = warm->f[r];
-        }
-        for (int r = 0; r < nc; r++)
-            for (int s = 0; s < nc; s++) {
-                double a = 0;
-                for (int k = 0; k < nd; k++) a += rows[r].J[k] * MiJ[s][k];
-                A[r * nc + s] = a;
-            }
-        for (int r = 0; r < nc; r++) {
-            double K, B, imp, jv = 0, ja = 0;
-            for (int k = 0; k < nd; k++) { jv += rows[r].J[k] * qd[k]; ja += rows[r].J[k] * qacc0[k]; }
-            /* friction rows share the impedance of their contact's normal row (same pos) */
+            double K, B, imp, jv = 0, y[DMAXD];
+            for (int k = 0; k < nd; k++) jv += rows[r].J[k] * qd[k];
             kbi(m, rows[r].solref, rows[r].solimp, rows[r].pos, rows[r].margin, &K, &B, &imp);
-            double aref = rows[r].type <= 1 ? (-B * jv - K * imp * (rows[r].pos - rows[r].margin)) : (-B * jv);
-            double diag = A[r * nc + r];
-            Rg[r] = (1 - imp) / imp * diag;
-            if (Rg[r] < MINVAL) Rg[r] = MINVAL;
-            b[r] = ja - aref;
+            aref[r] = rows[r].type <= 1 ? (-B * jv - K * imp * (rows[r].pos - rows[r].margin)) : (-B * jv);
+            /* regulariser R = (1 - imp) / imp * (J M^-1 J^T)_rr ; y = L^-1 J^T */
+            double diag = 0;
+            for (int k = 0; k < nd; k++) {
+                double sacc = rows[r].J[k];
+                for (int j = 0; j < k; j++) sacc -= L[k][j] * y[j];
+                y[k] = sacc / L[k][k];
+                diag += y[k] * y[k];
+            }
+            double Rg = (1 - imp) / imp * diag;
+            if (Rg < MINVAL) Rg = MINVAL;
+            Dr[r] = 1.0 / Rg;
         }
+        for (int r = 0; r < nc; r++) if (rows[r].type == 2) Dr[r] = Dr[r - (rows[r - 1].type == 1 ? 1 : 2)]; /* friction rows take the normal row's D */
         double trM = 0;
         for (int k = 0; k < nd; k++) trM += M[k][k];
         const double scale = 1.0 / (trM > MINVAL ? trM : MINVAL); /* 1 / (meaninertia * nv) */
+        double a[DMAXD], g[DMAXD], H[DMAXD][DMAXD], gs[DMAXC], x[DMAXC], Hc[DMAXC][9], cost = 0;
+        int zone[DMAXC];
+#define NEWTON_EVAL(avec, want_hess)                                                                              \
+    do {                                                                                                          \
+        double mat_[DMAXD];                                                                                       \
+        cost = 0;                                                                                                 \
+        for (int i_ = 0; i_ < nd; i_++) { double s_ = -tau[i_]; for (int j_ = 0; j_ < nd; j_++) s_ += M[i_][j_] * (avec)[j_]; mat_[i_] = s_; } \
+        for (int i_ = 0; i_ < nd; i_++) cost += 0.5 * ((avec)[i_] - qacc0[i_]) * mat_[i_];                        \
+        for (int r_ = 0; r_ < nc; r_++) { double s_ = -aref[r_]; for (int k_ = 0; k_ < nd; k_++) s_ += rows[r_].J[k_] * (avec)[k_]; x[r_] = s_; } \
+        for (int r_ = 0; r_ < nc; r_++) {                                                                         \
+            if (rows[r_].type == 0) { zone[r_] = x[r_] < 0; gs[r_] = zone[r_] ? Dr[r_] * x[r_] : 0.0; if (zone[r_]) cost += 0.5 * Dr[r_] * x[r_] * x[r_]; } \
+            else if (rows[r_].type == 1) cost += orc_cone(rows[r_].mu, Dr[r_], x + r_, gs + r_, Hc[r_], &zone[r_]); \
+        }                                                                                                         \
+        for (int i_ = 0; i_ < nd; i_++) { double s_ = mat_[i_]; for (int r_ = 0; r_ < nc; r_++) s_ += rows[r_].J[i_] * gs[r_]; g[i_] = s_; } \
+        if (want_hess) {                                                                                          \
+            for (int i_ = 0; i_ < nd; i_++) for (int j_ = 0; j_ <= i_; j_++) {                                    \
+                double s_ = M[i_][j_];                                                                            \
+                for (int r_ = 0; r_ < nc; r_++) {                                                                 \
+                    if (rows[r_].type == 0) { if (zone[r_]) s_ += Dr[r_] * rows[r_].J[i_] * rows[r_].J[j_]; }     \
+                    else if (rows[r_].type == 1 && zone[r_])                                                      \
+                        for (int p_ = 0; p_ < 3; p_++) for (int q_ = 0; q_ < 3; q_++) s_ += rows[r_ + p_].J[i_] * Hc[r_][3 * p_ + q_] * rows[r_ + q_].J[j_]; \
+                }                                                                                                 \
+                H[i_][j_] = s_;                                                                                   \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
+        /* warm start: the previous substep's acceleration unless the unconstrained one costs less */
+        memcpy(a, qacc0, sizeof(double) * nd);
+        NEWTON_EVAL(a, 0);
+        if (warm && warm->have_a) {
+            double c0 = cost;
+            NEWTON_EVAL(warm->a, 0);
+            if (cost < c0) memcpy(a, warm->a, sizeof(double) * nd);
+        }
+        NEWTON_EVAL(a, 1);
         g_pgs_calls++;
         for (int it = 0; it < m->iterations; it++) {
-            double imp = 0;
+            double gn = 0;
+            for (int k = 0; k < nd; k++) gn += g[k] * g[k];
+            if (scale * sqrt(gn) < m->tolerance) break;
             g_pgs_sweeps++;
-            for (int r = 0; r < nc; r++) {
-                if (rows[r].type >= 2) continue; /* tangent rows are updated with their normal row */
-                double res = b[r] + Rg[r] * f[r];
-                for (int s = 0; s < nc; s++) res += A[r * nc + s] * f[s];
-                double fn = f[r] - res / (A[r * nc + r] + Rg[r]);
-                fn = fn > 0 ? fn : 0;
-                imp += 0.5 * (A[r * nc + r] + Rg[r]) * (fn - f[r]) * (fn - f[r]);
-                f[r] = fn;
-                if (rows[r].type == 1) { /* elliptic cone: tangential rows r+1, r+2, |f_t| <= mu f_n */
-                    for (int t = 1; t <= 2; t++) {
-                        int q = r + t;
-                        double rs = b[q] + Rg[q] * f[q];
-                        for (int s = 0; s < nc; s++) rs += A[q * nc + s] * f[s];
-                        double ft_new = f[q] - rs / (A[q * nc + q] + Rg[q]);
-                        imp += 0.5 * (A[q * nc + q] + Rg[q]) * (ft_new - f[q]) * (ft_new - f[q]);
-                        f[q] = ft_new;
-                    }
-                    double lim = rows[r].mu * f[r], ft = sqrt(f[r + 1] * f[r + 1] + f[r + 2] * f[r + 2]);
-                    if (ft > lim) {
-                        double sc = ft > MINVAL ? lim / ft : 0;
-                        for (int t = 1; t <= 2; t++) {
-                            int q = r + t;
-                            double fs = f[q] * sc;
-                            imp += 0.5 * (A[q * nc + q] + Rg[q]) * (fs - f[q]) * (fs - f[q]);
-                            f[q] = fs;
-                        }
+            /* search direction p = -H^-1 g */
+            double Lh2[DMAXD][DMAXD], p[DMAXD], Mp[DMAXD], jp[DMAXC];
+            for (int i = 0; i < nd; i++)
+                for (int j = 0; j <= i; j++) {
+                    double sacc = H[i][j];
+                    for (int k = 0; k < j; k++) sacc -= Lh2[i][k] * Lh2[j][k];
+                    Lh2[i][j] = (i == j) ? sqrt(sacc) : sacc / Lh2[j][j];
+                }
+            for (int k = 0; k < nd; k++) p[k] = -g[k];
+            CHOL_SOLVE(Lh2, p);
+            /* exact line search on phi(alpha) = cost(a + alpha p): safeguarded Newton iteration on phi' */
+            double q1 = 0, q2 = 0;
+            for (int i = 0; i < nd; i++) { double sacc = 0; for (int j = 0; j < nd; j++) sacc += M[i][j] * p[j]; Mp[i] = sacc; }
+            for (int i = 0; i < nd; i++) { double ma = -tau[i]; for (int j = 0; j < nd; j++) ma += M[i][j] * a[j]; q1 += p[i] * ma; q2 += p[i] * Mp[i]; }
+            for (int r = 0; r < nc; r++) { double sacc = 0; for (int k = 0; k < nd; k++) sacc += rows[r].J[k] * p[k]; jp[r] = sacc; }
+            double alpha = 1.0, lo = 0.0, hi = -1.0, d0 = 0;
+            for (int ls = 0; ls < 24; ls++) {
+                double d1 = q1 + alpha * q2, d2 = q2;
+                for (int r = 0; r < nc; r++) {
+                    if (rows[r].type == 0) { double xa = x[r] + alpha * jp[r]; if (xa < 0) { d1 += Dr[r] * xa * jp[r]; d2 += Dr[r] * jp[r] * jp[r]; } }
+                    else if (rows[r].type == 1) {
+                        double xa[3] = {x[r] + alpha * jp[r], x[r + 1] + alpha * jp[r + 1], x[r + 2] + alpha * jp[r + 2]}, gg[3], hh[9];
+                        int z;
+                        orc_cone(rows[r].mu, Dr[r], xa, gg, hh, &z);
+                        if (z) for (int p_ = 0; p_ < 3; p_++) { d1 += gg[p_] * jp[r + p_]; for (int q_ = 0; q_ < 3; q_++) d2 += jp[r + p_] * hh[3 * p_ + q_] * jp[r + q_]; }
                     }
                 }
+                if (ls == 0) {   /* derivative at alpha = 1 first; phi'(0) = g.p gives the tolerance */
+                    for (int k = 0; k < nd; k++) d0 += g[k] * p[k];
+                }
+                if (fabs(d1) <= 1e-6 * fabs(d0)) break;
+                if (d1 < 0) lo = alpha; else hi = alpha;
+                double an = alpha - d1 / d2;
+                if (hi >= 0) { if (!(an > lo && an < hi)) an = 0.5 * (lo + hi); }
+                else if (!(an > lo)) an = 2 * alpha;
+                alpha = an;
             }
-            if (scale * imp < m->tolerance) break;
+            for (int k = 0; k < nd; k++) a[k] += alpha * p[k];
+            double old = cost;
+            NEWTON_EVAL(a, 1);
+            if (scale * (old - cost) < m->tolerance) break;
         }
+#undef NEWTON_EVAL
         for (int r = 0; r < nc; r++)
-            for (int k = 0; k < nd; k++) fc[k] += rows[r].J[k] * f[r];
-        if (warm) { warm->n = nc; for (int r = 0; r < nc; r++) { warm->sig[r] = rows[r].sig; warm->f[r] = f[r]; } }
-        free(MiJ); free(A); free(b); free(Rg); free(f);
+            for (int k = 0; k < nd; k++) fc[k] -= rows[r].J[k] * gs[r];   /* constraint force f = -grad s */
+        if (warm) { warm->have_a = 1; memcpy(warm->a, a, sizeof(double) * nd); }
+        free(aref); free(Dr);
     }
-    if (warm && nc == 0) warm->n = 0;
+    else if (warm) warm->have_a = 0;
     free(rows);
     /* ---- semi-implicit Euler with implicit joint damping: (M + h D) qacc = tau + J^T f */
     double Lh[DMAXD][DMAXD], rhs[DMAXD];
@@ -444,7 +511,7 @@ int orc_dyn_step(void *h, double *qpos, double *qvel, const double *ctrl, const 
     memset(&D, 0, sizeof(D));
     double applied[DMAXD];
     warm_t warm;
-    warm.n = 0; /* the warm start lives for the substeps of one call (one env.step) */
+    warm.have_a = 0; /* the warm start lives for the substeps of one call (one env.step) */
     for (int s = 0; s < nsub; s++) {
         for (int k = 0; k < m->nd; k++) applied[k] = comp[k] ? bias_prev[k] : 0.0;
         substep(m, qpos, qvel, ctrl, applied, &D, &warm);

@@ -48,6 +48,6 @@ typedef struct {
     double mu;
     int sig;  /* identity of the row across substeps (warm start): limits -(2*dof+side+1), contacts pair*16 + point*4 + dir */
 } crow;
-typedef struct { int n; int sig[DMAXC]; double f[DMAXC]; } warm_t; /* constraint forces of the previous substep */
+typedef struct { int have_a; double a[DMAXD]; } warm_t; /* qacc of the previous substep (mjData.qacc_warmstart) */
 int orc_contact_rows(const dyn_model *m, const dyn_data *d, const sv6 *S, crow *rows, int maxrows);
 #endif
