@@ -53,10 +53,10 @@ struct WarpWS {
         double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
     };
     double kxpos[4][3], kxquat[4][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
-    double M[NTRI], L[NTRI];
+    double M[NTRI], L[NTRI], invd[WD];
     double qd[WD], bias[WD], tau[WD], qacc0[WD], a[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
     double Y[WC * YS];
-    double f[WC];
+    alignas(16) double f[WC];   // gradient of the penalties per row; also the column buffer of w_factor_solve
     double gpos[WG][3];
     double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
     int cga[WCP], cgb[WCP], csig[WCP];
@@ -83,47 +83,81 @@ __device__ __forceinline__ double warp_sum(double x) {
     return x;
 }
 
-// ---- lane = row right-looking Cholesky of (M + hs * diag) into L (lower, stride MS)
-// `blk[i]` = first dof of the kinematic tree that owns dof i: M is block diagonal by tree, so all entries
-// outside a row's block are exact zeros and are skipped (bitwise the same factor as the dense algorithm).
-__device__ __noinline__ void w_chol_inplace(double *L, int nd, int lane, const int *blk) {
-    const int b0 = (lane < nd && blk) ? blk[lane] : 0;
-    for (int j = 0; j < nd; j++) {
-        const double d = sqrt(L[TRI(j, j)]);
+// ---- Cholesky factorisation + solve, register resident.  Lane i keeps row i of the lower triangle in
+// registers (template recursion = full unrolling: every row[] index is a compile-time constant).
+// Column j: lane j publishes d_jj and its partially reduced right-hand side through a small shared
+// buffer; every lane scales by rsqrt(d_jj) (no fp64 divide / sqrt on the critical path), publishes
+// its l_ij, and the trailing update reads the column back with broadcast 128-bit loads.  The forward
+// substitution L y = b rides along with the elimination.  The factor is then written to shared memory
+// (packed lower triangle, plus 1 / L_ii) for the backward substitution and for later triangular
+// solves of the caller.  Rows / columns nd..WD-1 are identity padding (no bound checks inside).
+//   (M + hs * diag) = L L^T,  x <- (M + hs * diag)^-1 x      x: shared, nd entries; col: shared, WD + 2 doubles, 16-byte aligned
+template <int J, int K>
+__device__ __forceinline__ void wfs_update(double (&row)[WD], const double (&c)[WD], int lane) {
+    if constexpr (K < WD) {
+        if (lane >= K) row[K] -= row[J] * c[K];
+        wfs_update<J, K + 1>(row, c, lane);
+    }
+}
+template <int J, int K2>
+__device__ __forceinline__ void wfs_fetch(double (&c)[WD], const double *col) {
+    if constexpr (2 * K2 < WD) {
+        const double2 v = reinterpret_cast<const double2 *>(col)[K2];
+        c[2 * K2] = v.x; c[2 * K2 + 1] = v.y;
+        wfs_fetch<J, K2 + 1>(c, col);
+    }
+}
+template <int J>
+__device__ __forceinline__ void wfs_column(double (&row)[WD], double &xr, double &rme, int lane, double *col) {
+    if constexpr (J < WD) {
+        if (lane == J) { col[WD] = row[J]; col[WD + 1] = xr; }
         __syncwarp();
-        if (lane == j) L[TRI(j, j)] = d;
-        const bool mine = lane > j && lane < nd && b0 <= j;   // same tree as column j
-        if (mine) L[TRI(lane, j)] = L[TRI(lane, j)] / d;
+        const double djj = col[WD], rinv = rsqrt(djj), yj = col[WD + 1] * rinv;
+        if (lane == J) { row[J] = djj * rinv; rme = rinv; xr = yj; }
+        else if (lane > J) { row[J] *= rinv; xr -= row[J] * yj; if (lane < WD) col[lane] = row[J]; }
         __syncwarp();
-        if (mine) {
-            const double lij = L[TRI(lane, j)];
-            for (int k = j + 1; k <= lane; k++) L[TRI(lane, k)] -= lij * L[TRI(k, j)];
+        if constexpr (J + 1 < WD) {
+            double c[WD];
+            wfs_fetch<J, (J + 1) / 2>(c, col);
+            wfs_update<J, J + 1>(row, c, lane);
         }
-        __syncwarp();
+        wfs_column<J + 1>(row, xr, rme, lane, col);
     }
 }
-__device__ __forceinline__ void w_chol(const double *M, const double *diag, double hs, int nd, double *L, int lane, const int *blk) {
-    if (lane < nd)
-        for (int k = 0; k <= lane; k++) L[TRI(lane, k)] = M[TRI(lane, k)] + ((k == lane && diag) ? hs * diag[lane] : 0.0);
+template <int K>
+__device__ __forceinline__ void wfs_load(double (&row)[WD], const double *Msrc, double dd, int lane, bool live) {
+    if constexpr (K < WD) {
+        row[K] = (live && K <= lane) ? Msrc[TRI(lane, K)] : 0.0;
+        if (K == lane) row[K] = live ? row[K] + dd : 1.0;
+        wfs_load<K + 1>(row, Msrc, dd, lane, live);
+    }
+}
+template <int K>
+__device__ __forceinline__ void wfs_store(const double (&row)[WD], double *Lout, int lane, bool live) {
+    if constexpr (K < WD) {
+        if (live && K <= lane) Lout[TRI(lane, K)] = row[K];
+        wfs_store<K + 1>(row, Lout, lane, live);
+    }
+}
+__device__ __noinline__ void w_factor_solve(const double *Msrc, const double *diag, double hs, int nd, double *Lout, double *invd, double *x,
+                                            double *col, int lane) {
+    double row[WD];
+    const bool live = lane < nd;
+    wfs_load<0>(row, Msrc, (diag && live) ? hs * diag[lane] : 0.0, lane, live);
+    double xr = live ? x[lane] : 0.0, rme = 0.0;
+    wfs_column<0>(row, xr, rme, lane, col);
+    wfs_store<0>(row, Lout, lane, live);
+    if (live) invd[lane] = rme;
     __syncwarp();
-    w_chol_inplace(L, nd, lane, blk);
-}
-// single right-hand side, lane-parallel column-oriented substitution; x (shared, nd entries) in place
-__device__ __noinline__ void w_solve(const double *L, int nd, double *x, int lane) {
-    for (int i = 0; i < nd; i++) {
-        const double xi = x[i] / L[TRI(i, i)];
-        __syncwarp();
-        if (lane == i) x[i] = xi;
-        if (lane > i && lane < nd) x[lane] -= L[TRI(lane, i)] * xi;
-        __syncwarp();
-    }
+    // backward substitution L^T x = y: lane i publishes x_i, the lanes above it eliminate
     for (int i = nd - 1; i >= 0; i--) {
-        const double xi = x[i] / L[TRI(i, i)];
+        if (lane == i) { xr *= rme; col[WD] = xr; }
         __syncwarp();
-        if (lane == i) x[i] = xi;
-        if (lane < i) x[lane] -= L[TRI(i, lane)] * xi;
+        if (lane < i) xr -= Lout[TRI(i, lane)] * col[WD];
         __syncwarp();
     }
+    if (live) x[lane] = xr;
+    __syncwarp();
 }
 
 // Out-of-line wrappers keep one copy of the big routines in the instruction stream (the kernel is
@@ -154,99 +188,110 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     }
     if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
     __syncwarp();
-    // ---- kinematics.  (1) lane = body: the joint's local transform (the expensive sin / cos run in
-    // parallel), (2) short uniform chain composing parent frames, (3) lane = body: joint motion axes.
-    if (lane < nb) {
-        const int i = lane, jt = m.b_jtype[i];
-        double lp[3] = {m.b_pos[i][0], m.b_pos[i][1], m.b_pos[i][2]};
-        double lq[4] = {m.b_quat[i][0], m.b_quat[i][1], m.b_quat[i][2], m.b_quat[i][3]};
-        if (jt == 3) {
-            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
-            const double ang = W.q[m.b_qadr[i]] - m.b_qpos0[i], sn = sin(0.5 * ang), cs = cos(0.5 * ang);
-            const double ql[4] = {cs, sn * ja[0], sn * ja[1], sn * ja[2]};
-            double qn[4];
-            d_qmul(qn, lq, ql);
-            if (jp[0] != 0.0 || jp[1] != 0.0 || jp[2] != 0.0) {   // rotation about an offset anchor
-                double R0[9], R1[9], t0[3], t1[3];
-                d_q2m(R0, lq); d_q2m(R1, qn);
-                d_mv(t0, R0, jp); d_mv(t1, R1, jp);
-                for (int k = 0; k < 3; k++) lp[k] += t0[k] - t1[k];
+    // ---- kinematics, lane = body, in registers: (1) local transform of the body incl. its joint (the
+    // expensive sin / cos run in parallel), (2) world frames by pointer jumping over the parent links
+    // (log2(depth) rounds of shuffle + compose instead of a serial chain), (3) joint motion axes.
+    {
+        const int i = lane < nb ? lane : 0;
+        const int jt = lane < nb ? m.b_jtype[i] : -1;
+        int anc = -1;
+        double lp[3] = {0, 0, 0}, lq[4] = {1, 0, 0, 0};
+        if (lane < nb) {
+            for (int k = 0; k < 3; k++) lp[k] = m.b_pos[i][k];
+            for (int k = 0; k < 4; k++) lq[k] = m.b_quat[i][k];
+            if (jt == 3) {
+                const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
+                const double ang = W.q[m.b_qadr[i]] - m.b_qpos0[i], sn = sin(0.5 * ang), cs = cos(0.5 * ang);
+                const double ql[4] = {cs, sn * ja[0], sn * ja[1], sn * ja[2]};
+                double qn[4];
+                d_qmul(qn, lq, ql);
+                if (jp[0] != 0.0 || jp[1] != 0.0 || jp[2] != 0.0) {   // rotation about an offset anchor
+                    double R0[9], R1[9], t0[3], t1[3];
+                    d_q2m(R0, lq); d_q2m(R1, qn);
+                    d_mv(t0, R0, jp); d_mv(t1, R1, jp);
+                    for (int k = 0; k < 3; k++) lp[k] += t0[k] - t1[k];
+                }
+                for (int k = 0; k < 4; k++) lq[k] = qn[k];
+            } else if (jt == 2) {
+                const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+                double R0[9], ax[3];
+                d_q2m(R0, lq);
+                d_mv(ax, R0, ja);
+                const double dq = W.q[m.b_qadr[i]] - m.b_qpos0[i];
+                for (int k = 0; k < 3; k++) lp[k] += ax[k] * dq;
+            } else if (jt == 0) {   // free joint: absolute pose
+                const int a = m.b_qadr[i];
+                for (int k = 0; k < 3; k++) lp[k] = W.q[a + k];
+                const double n = sqrt(W.q[a + 3] * W.q[a + 3] + W.q[a + 4] * W.q[a + 4] + W.q[a + 5] * W.q[a + 5] + W.q[a + 6] * W.q[a + 6]);
+                for (int k = 0; k < 4; k++) lq[k] = W.q[a + 3 + k] / n;
             }
-            for (int k = 0; k < 4; k++) lq[k] = qn[k];
-        } else if (jt == 2) {
-            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
-            double R0[9], ax[3];
-            d_q2m(R0, lq);
-            d_mv(ax, R0, ja);
-            const double dq = W.q[m.b_qadr[i]] - m.b_qpos0[i];
-            for (int k = 0; k < 3; k++) lp[k] += ax[k] * dq;
-        } else if (jt == 0) {
-            const int a = m.b_qadr[i];
-            for (int k = 0; k < 3; k++) lp[k] = W.q[a + k];
-            const double n = sqrt(W.q[a + 3] * W.q[a + 3] + W.q[a + 4] * W.q[a + 4] + W.q[a + 5] * W.q[a + 5] + W.q[a + 6] * W.q[a + 6]);
-            for (int k = 0; k < 4; k++) lq[k] = W.q[a + 3 + k] / n;
-        }
-        for (int k = 0; k < 3; k++) W.k.inert[i][k] = lp[k];       // scratch: inert[] is filled later
-        for (int k = 0; k < 4; k++) W.k.inert[i][3 + k] = lq[k];
-    }
-    __syncwarp();
-    for (int i = 0; i < nb; i++) {
-        const int p = m.b_parent[i], jt = m.b_jtype[i];
-        double pos[3], quat[4], R[9];
-        const double lp[3] = {W.k.inert[i][0], W.k.inert[i][1], W.k.inert[i][2]};
-        const double lq[4] = {W.k.inert[i][3], W.k.inert[i][4], W.k.inert[i][5], W.k.inert[i][6]};
-        if (jt == 0) {   // free joint: absolute pose
-            for (int k = 0; k < 3; k++) pos[k] = lp[k];
-            for (int k = 0; k < 4; k++) quat[k] = lq[k];
-        } else {
-            double Pp[3], Pq[4], PM[9], t[3];
-            if (p >= 0) {
-                for (int k = 0; k < 3; k++) Pp[k] = W.k.xpos[p][k];
-                for (int k = 0; k < 4; k++) Pq[k] = W.k.xquat[p][k];
-                for (int k = 0; k < 9; k++) PM[k] = W.k.xmat[p][k];
-            } else {
-                for (int k = 0; k < 3; k++) Pp[k] = m.b_rootpos[i][k];
-                for (int k = 0; k < 4; k++) Pq[k] = m.b_rootquat[i][k];
-                d_q2m(PM, Pq);
+            if (jt != 0) {
+                anc = m.b_parent[i];
+                if (anc < 0) {   // tree root: fold the static parent's world frame into the local transform
+                    const double Pq[4] = {m.b_rootquat[i][0], m.b_rootquat[i][1], m.b_rootquat[i][2], m.b_rootquat[i][3]};
+                    double PM[9], t[3], qn[4];
+                    d_q2m(PM, Pq);
+                    d_mv(t, PM, lp);
+                    for (int k = 0; k < 3; k++) lp[k] = m.b_rootpos[i][k] + t[k];
+                    d_qmul(qn, Pq, lq);
+                    for (int k = 0; k < 4; k++) lq[k] = qn[k];
+                }
             }
-            d_mv(t, PM, lp);
-            for (int k = 0; k < 3; k++) pos[k] = Pp[k] + t[k];
-            d_qmul(quat, Pq, lq);
         }
-        d_q2m(R, quat);
-        // predicated stores with compile-time indices (a lane-indexed register array would live in local memory)
+        for (int round = 0; round < 5; round++) {
+            const bool has = anc >= 0;
+            if (!__any_sync(FULL, has)) break;
+            const int src = has ? anc : lane;
+            double ap[3], aq[4];
 #pragma unroll
-        for (int k = 0; k < 3; k++) if (lane == k) W.k.xpos[i][k] = pos[k];
+            for (int k = 0; k < 3; k++) ap[k] = shfl_d(lp[k], src);
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (lane == 4 + k) W.k.xquat[i][k] = quat[k];
+            for (int k = 0; k < 4; k++) aq[k] = shfl_d(lq[k], src);
+            const int aanc = __shfl_sync(FULL, anc, src);
+            if (has) {   // T <- T_anc o T
+                double PM[9], t[3], qn[4];
+                d_q2m(PM, aq);
+                d_mv(t, PM, lp);
+                for (int k = 0; k < 3; k++) lp[k] = ap[k] + t[k];
+                d_qmul(qn, aq, lq);
+                for (int k = 0; k < 4; k++) lq[k] = qn[k];
+                anc = aanc;
+            }
+        }
+        if (lane < nb) {
+            double R[9];
+            d_q2m(R, lq);
 #pragma unroll
-        for (int k = 0; k < 9; k++) if (lane == 8 + k) W.k.xmat[i][k] = R[k];
-        __syncwarp();
-    }
-    if (lane < nb) {
-        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i];
-        const double *R = W.k.xmat[i], *pos = W.k.xpos[i];
-        if (jt == 3) {
-            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
-            double ax[3], t[3], anchor[3], cr[3];
-            d_mv(ax, R, ja);
-            d_mv(t, R, jp);
-            for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t[k];
-            d_cross(cr, anchor, ax);
-            for (int k = 0; k < 3; k++) { W.k.S[da][k] = ax[k]; W.k.S[da][3 + k] = cr[k]; }
-        } else if (jt == 2) {
-            const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
-            double ax[3];
-            d_mv(ax, R, ja);
-            for (int k = 0; k < 3; k++) { W.k.S[da][k] = 0; W.k.S[da][3 + k] = ax[k]; }
-        } else if (jt == 0) {
-            for (int a = 0; a < 3; a++) {
-                for (int c = 0; c < 6; c++) W.k.S[da + a][c] = 0;
-                W.k.S[da + a][3 + a] = 1;
-                const double e[3] = {R[a], R[3 + a], R[6 + a]};
-                double cr[3];
-                d_cross(cr, pos, e);
-                for (int c = 0; c < 3; c++) { W.k.S[da + 3 + a][c] = e[c]; W.k.S[da + 3 + a][3 + c] = cr[c]; }
+            for (int k = 0; k < 3; k++) W.k.xpos[i][k] = lp[k];
+#pragma unroll
+            for (int k = 0; k < 4; k++) W.k.xquat[i][k] = lq[k];
+#pragma unroll
+            for (int k = 0; k < 9; k++) W.k.xmat[i][k] = R[k];
+            const int da = m.b_dadr[i];
+            const double *pos = lp;
+            if (jt == 3) {
+                const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]}, jp[3] = {m.b_jpos[i][0], m.b_jpos[i][1], m.b_jpos[i][2]};
+                double ax[3], t[3], anchor[3], cr[3];
+                d_mv(ax, R, ja);
+                d_mv(t, R, jp);
+                for (int k = 0; k < 3; k++) anchor[k] = pos[k] + t[k];
+                d_cross(cr, anchor, ax);
+                for (int k = 0; k < 3; k++) { W.k.S[da][k] = ax[k]; W.k.S[da][3 + k] = cr[k]; }
+            } else if (jt == 2) {
+                const double ja[3] = {m.b_jaxis[i][0], m.b_jaxis[i][1], m.b_jaxis[i][2]};
+                double ax[3];
+                d_mv(ax, R, ja);
+                for (int k = 0; k < 3; k++) { W.k.S[da][k] = 0; W.k.S[da][3 + k] = ax[k]; }
+            } else if (jt == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    for (int c = 0; c < 6; c++) W.k.S[da + a][c] = 0;
+                    W.k.S[da + a][3 + a] = 1;
+                    const double e[3] = {R[a], R[3 + a], R[6 + a]};
+                    double cr[3];
+                    d_cross(cr, pos, e);
+                    for (int c = 0; c < 3; c++) { W.k.S[da + 3 + a][c] = e[c]; W.k.S[da + 3 + a][3 + c] = cr[c]; }
+                }
             }
         }
     }
@@ -380,10 +425,9 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     }
     __syncwarp();
     STAGE_SYNC(3);   // 3: inertia matrix and forces done
-    w_chol(W.M, nullptr, 0.0, nd, W.L, lane, W.blk);
     if (lane < nd) W.qacc0[lane] = W.tau[lane];
     __syncwarp();
-    w_solve(W.L, nd, W.qacc0, lane);
+    w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.f, lane);
 
     STAGE_SYNC(4);   // 4: unconstrained acceleration done
     // ---- constraint rows.  Limits first (dof order), then contacts (pair order).
@@ -621,7 +665,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
                 double s = jr[k];
                 const int j0 = W.blk[k] > k0 ? W.blk[k] : k0;   // L[k][j] = 0 outside k's tree
                 for (int j = j0; j < k; j++) s -= W.L[TRI(k, j)] * yr[j];
-                s = s / W.L[TRI(k, k)];
+                s = s * W.invd[k];
                 yr[k] = s;
                 diag += s * s;
             }
@@ -739,10 +783,9 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
             if (c_tune.prof && lane == 0) { atomicAdd(&g_prof[20], 1ULL); if (it == m.iterations) atomicAdd(&g_prof[28], 1ULL); }
             // search direction p = -H^-1 g (W.rhs in place; W.z keeps M a - tau)
             const double matme = lane < nd ? W.z[lane] : 0.0;
-            w_chol_inplace(W.L, nd, lane, nullptr);
             if (lane < nd) W.rhs[lane] = -gme;
             __syncwarp();
-            w_solve(W.L, nd, W.rhs, lane);
+            w_factor_solve(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.f, lane);
             double pme = 0, mp = 0;
             if (lane < nd) {
                 pme = W.rhs[lane];
@@ -797,8 +840,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     // ---- semi-implicit Euler with implicit joint damping
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
-    w_chol(W.M, m.d_damping, m.h, nd, W.L, lane, W.blk);
-    w_solve(W.L, nd, W.rhs, lane);
+    w_factor_solve(W.M, m.d_damping, m.h, nd, W.L, W.invd, W.rhs, W.f, lane);
     if (lane < nd) {
         W.qd[lane] += m.h * W.rhs[lane];
         W.v[m.d_vadr[lane]] = W.qd[lane];
