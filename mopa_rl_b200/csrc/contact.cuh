@@ -130,7 +130,9 @@ DYN_HD inline int convex_pocs(CPoint &cp, const CGeom &g1, const CGeom &g2, doub
     return 1;
 }
 
-DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2, double margin) {
+// box-box, part 1: 15-axis SAT.  Returns 0 = separated by more than margin, 1 = edge-edge contact
+// (ecode = 3 * i + j, depth ebest), 2 = face contact (code = face axis 0..5, see box_box_face).
+DYN_HD inline int box_box_sat(const CGeom &g1, const CGeom &g2, double margin, int &code_out, double &depth_out) {
     const double *c1 = g1.c, *c2 = g2.c, *R1 = g1.R, *R2 = g2.R, *h1 = g1.size, *h2 = g2.size;
     double d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]}, T[3], Rm[9], A[9];
     for (int k = 0; k < 3; k++) T[k] = R1[k] * d[0] + R1[3 + k] * d[1] + R1[6 + k] * d[2];
@@ -170,26 +172,38 @@ DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2
     }
     const int use_edge = (ecode >= 0 && ebest > best + 1e-6 + 0.05 * fabs(best));
     if ((use_edge ? ebest : best) >= margin) return 0;
-    if (use_edge) {
-        const int i = ecode / 3, j = ecode % 3;
-        double a[3], b[3], en[3];
-        c_colk(a, R1, i); c_colk(b, R2, j);
-        d_cross(en, a, b);
-        double l = sqrt(d_dot(en, en));
-        for (int k = 0; k < 3; k++) en[k] /= l;
-        if (d_dot(en, d) < 0) for (int k = 0; k < 3; k++) en[k] = -en[k];
-        double p1[3] = {c1[0], c1[1], c1[2]}, p2[3] = {c2[0], c2[1], c2[2]};
-        for (int k = 0; k < 3; k++) {
-            if (k != i) { double ax[3]; c_colk(ax, R1, k); double sg = d_dot(ax, en) > 0 ? 1.0 : -1.0; for (int c = 0; c < 3; c++) p1[c] += sg * h1[k] * ax[c]; }
-            if (k != j) { double ax[3]; c_colk(ax, R2, k); double sg = d_dot(ax, en) > 0 ? -1.0 : 1.0; for (int c = 0; c < 3; c++) p2[c] += sg * h2[k] * ax[c]; }
-        }
-        double w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, ab = d_dot(a, b), aw = d_dot(a, w), bw = d_dot(b, w);
-        double den = 1.0 - ab * ab, s = (ab * bw - aw) / den, t = (bw - ab * aw) / den;
-        s = c_clamp(s, -h1[i], h1[i]); t = c_clamp(t, -h2[j], h2[j]);
-        out[0].dist = ebest;
-        for (int k = 0; k < 3; k++) { out[0].n[k] = en[k]; out[0].pos[k] = 0.5 * ((p1[k] + s * a[k]) + (p2[k] + t * b[k])); }
-        return 1;
+    code_out = use_edge ? ecode : code;
+    depth_out = use_edge ? ebest : best;
+    return use_edge ? 1 : 2;
+}
+// part 2a: closest points of the two edges named by ecode
+DYN_HD inline int box_box_edge(CPoint *out, const CGeom &g1, const CGeom &g2, int ecode, double ebest) {
+    const double *c1 = g1.c, *c2 = g2.c, *R1 = g1.R, *R2 = g2.R, *h1 = g1.size, *h2 = g2.size;
+    const double d[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+    const int i = ecode / 3, j = ecode % 3;
+    double a[3], b[3], en[3];
+    c_colk(a, R1, i); c_colk(b, R2, j);
+    d_cross(en, a, b);
+    double l = sqrt(d_dot(en, en));
+    for (int k = 0; k < 3; k++) en[k] /= l;
+    if (d_dot(en, d) < 0) for (int k = 0; k < 3; k++) en[k] = -en[k];
+    double p1[3] = {c1[0], c1[1], c1[2]}, p2[3] = {c2[0], c2[1], c2[2]};
+    for (int k = 0; k < 3; k++) {
+        if (k != i) { double ax[3]; c_colk(ax, R1, k); double sg = d_dot(ax, en) > 0 ? 1.0 : -1.0; for (int c = 0; c < 3; c++) p1[c] += sg * h1[k] * ax[c]; }
+        if (k != j) { double ax[3]; c_colk(ax, R2, k); double sg = d_dot(ax, en) > 0 ? -1.0 : 1.0; for (int c = 0; c < 3; c++) p2[c] += sg * h2[k] * ax[c]; }
     }
+    double w[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, ab = d_dot(a, b), aw = d_dot(a, w), bw = d_dot(b, w);
+    double den = 1.0 - ab * ab, s = (ab * bw - aw) / den, t = (bw - ab * aw) / den;
+    s = c_clamp(s, -h1[i], h1[i]); t = c_clamp(t, -h2[j], h2[j]);
+    out[0].dist = ebest;
+    for (int k = 0; k < 3; k++) { out[0].n[k] = en[k]; out[0].pos[k] = 0.5 * ((p1[k] + s * a[k]) + (p2[k] + t * b[k])); }
+    return 1;
+}
+// part 2b: face contact - the incident face of the other box clipped against the reference face
+// (Sutherland-Hodgman; a quad clipped by four half planes has at most 8 vertices), <= 4 deepest points kept.
+// poly / tmp [>= 8][3], depth [>= 8], keep [>= 8]: caller-provided scratch (shared memory in the warp kernel).
+DYN_HD inline int box_box_face(CPoint *out, const CGeom &g1, const CGeom &g2, int code, double margin, double (*poly)[3], double (*tmp)[3],
+                               double *depth, int *keep) {
     const CGeom &gr = code < 3 ? g1 : g2, &gi = code < 3 ? g2 : g1;
     const int ax = code < 3 ? code : code - 3;
     double n[3], dd[3] = {gi.c[0] - gr.c[0], gi.c[1] - gr.c[1], gi.c[2] - gr.c[2]};
@@ -204,7 +218,6 @@ DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2
         if (-fabs(dn) < mind) { mind = -fabs(dn); iax = k; isg = dn > 0 ? -1.0 : 1.0; }
     }
     const int u = (iax + 1) % 3, v = (iax + 2) % 3;
-    double poly[16][3], tmp[16][3];
     int np = 4;
     {
         double fa[3], ua[3], va[3];
@@ -234,8 +247,7 @@ DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2
         np = nn;
         for (int q = 0; q < np; q++) for (int k = 0; k < 3; k++) poly[q][k] = tmp[q][k];
     }
-    double depth[16];
-    int keep[16], nk = 0;
+    int nk = 0;
     for (int q = 0; q < np; q++) {
         depth[q] = (poly[q][0] - gr.c[0]) * n[0] + (poly[q][1] - gr.c[1]) * n[1] + (poly[q][2] - gr.c[2]) * n[2] - gr.size[ax];
         if (depth[q] < margin) keep[nk++] = q;
@@ -253,6 +265,16 @@ DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2
         for (int k = 0; k < 3; k++) { out[q].n[k] = flip * n[k]; out[q].pos[k] = P[k] - n[k] * 0.5 * depth[keep[q]]; }
     }
     return nk;
+}
+DYN_HD inline int box_box_contacts(CPoint *out, const CGeom &g1, const CGeom &g2, double margin) {
+    int code = 0;
+    double depth = 0;
+    const int kind = box_box_sat(g1, g2, margin, code, depth);
+    if (kind == 0) return 0;
+    if (kind == 1) return box_box_edge(out, g1, g2, code, depth);
+    double poly[8][3], tmp[8][3], dep[8];
+    int keep[8];
+    return box_box_face(out, g1, g2, code, margin, poly, tmp, dep, keep);
 }
 
 DYN_HD inline int pair_contacts(CPoint *out, const CGeom &ga, const CGeom &gb, double margin) {
@@ -315,75 +337,6 @@ DYN_HD inline int pair_contacts(CPoint *out, const CGeom &ga, const CGeom &gb, d
     }
     if (swapped) for (int q = 0; q < n; q++) for (int k = 0; k < 3; k++) out[q].n[k] = -out[q].n[k];
     return n;
-}
-
-DYN_HD inline int contact_rows(const DynDev &m, const DynData &D, const Sv6 *S, CRow *rows, int maxrows) {
-    int nrow = 0;
-    // world centres of all contact geoms once per step; rotations only for pairs that survive the cull
-    double gpos[DMAXG][3];
-    for (int g = 0; g < m.ngeom; g++) {
-        const int body = m.g_body[g];
-        if (body < 0) { for (int k = 0; k < 3; k++) gpos[g][k] = m.g_pos[g][k]; continue; }
-        const double *X = D.xmat[body];
-        for (int k = 0; k < 3; k++)
-            gpos[g][k] = D.xpos[body][k] + X[3 * k] * m.g_pos[g][0] + X[3 * k + 1] * m.g_pos[g][1] + X[3 * k + 2] * m.g_pos[g][2];
-    }
-    for (int p = 0; p < m.npair; p++) {
-        const int a = m.p_g1[p], b = m.p_g2[p];
-        const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
-        if (m.g_type[a] != 0 && m.g_type[b] != 0) {
-            double d[3] = {gpos[b][0] - gpos[a][0], gpos[b][1] - gpos[a][1], gpos[b][2] - gpos[a][2]}, bound = m.g_rbound[a] + m.g_rbound[b] + margin;
-            if (d_dot(d, d) > bound * bound) continue;
-        }
-        double gc[2][3], gR[2][9];
-        for (int side = 0; side < 2; side++) {
-            const int g = side ? b : a, body = m.g_body[g];
-            for (int k = 0; k < 3; k++) gc[side][k] = gpos[g][k];
-            double Rl[9];
-            d_q2m(Rl, m.g_quat[g]);
-            if (body < 0) { for (int k = 0; k < 9; k++) gR[side][k] = Rl[k]; continue; }
-            const double *X = D.xmat[body];
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) gR[side][3 * r + c] = X[3 * r] * Rl[c] + X[3 * r + 1] * Rl[3 + c] + X[3 * r + 2] * Rl[6 + c];
-        }
-        CGeom ga{gc[0], gR[0], m.g_size[a], m.g_type[a]}, gb{gc[1], gR[1], m.g_size[b], m.g_type[b]};
-        CPoint cps[4];
-        const int nc = pair_contacts(cps, ga, gb, margin);
-        for (int q = 0; q < nc; q++) {
-            if (nrow + 3 > maxrows) return nrow;
-            double *n = cps[q].n, t1[3], t2[3], ref[3] = {0, 0, 0};
-            ref[fabs(n[0]) < 0.7 ? 0 : 1] = 1.0;
-            d_cross(t1, n, ref);
-            double l = sqrt(d_dot(t1, t1));
-            for (int k = 0; k < 3; k++) t1[k] /= l;
-            d_cross(t2, n, t1);
-            const double mu = m.g_friction[a][0] > m.g_friction[b][0] ? m.g_friction[a][0] : m.g_friction[b][0];
-            for (int r = 0; r < 3; r++) {
-                const double *dir = r == 0 ? n : (r == 1 ? t1 : t2);
-                CRow &row = rows[nrow + r];
-                for (int k = 0; k < DMAXD; k++) row.J[k] = 0;
-                row.type = r == 0 ? 1 : 2;
-                row.pos = cps[q].dist; row.margin = margin; row.mu = mu;
-                row.sig = p * 16 + q * 4 + r;
-                for (int k = 0; k < 2; k++) row.solref[k] = 0.5 * (m.g_solref[a][k] + m.g_solref[b][k]);
-                for (int k = 0; k < 5; k++) row.solimp[k] = 0.5 * (m.g_solimp[a][k] + m.g_solimp[b][k]);
-                for (int side = 0; side < 2; side++) {
-                    int body = side ? m.g_body[b] : m.g_body[a];
-                    const double sg = side ? 1.0 : -1.0;
-                    while (body >= 0 && m.b_jtype[body] < 0) body = m.b_parent[body];
-                    if (body < 0) continue;
-                    for (int k = m.b_dadr[body] + (m.b_jtype[body] == 0 ? 5 : 0); k >= 0; k = m.d_parent[k]) {
-                        double t[3], j[3];
-                        d_cross(t, S[k].w, cps[q].pos);
-                        for (int c = 0; c < 3; c++) j[c] = S[k].v[c] + t[c];
-                        row.J[k] += sg * d_dot(dir, j);
-                    }
-                }
-            }
-            nrow += 3;
-        }
-    }
-    return nrow;
 }
 
 }  // namespace mopa

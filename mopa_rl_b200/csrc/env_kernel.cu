@@ -21,7 +21,7 @@ struct DynDev;
 cudaError_t upload_env_model(int slot, const DynDev &h_model);
 cudaError_t env_tune_set(int prof, int sync_mask);
 cudaError_t env_prof_read(unsigned long long *out);
-cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream);
 }
@@ -29,144 +29,12 @@ cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer
 struct mopa_env {
     int device = 0;
     int model_slot = 0;          // slot of this scene in the warp kernel's constant memory
-    int use_thread_kernel = 0;   // MOPA_ENV_KERNEL=thread selects the one-thread-per-env kernel (debug / comparison)
     mopa::DynDev *d_model = nullptr;
     mopa::DynDev h_model;
     mopa_sawyer_task task;
 };
 
 namespace mopa {
-
-__device__ __forceinline__ void site_world(double *out, const DynData &D, int b, const double *local) {
-    double t[3];
-    d_mv(t, D.xmat[b], local);
-    for (int k = 0; k < 3; k++) out[k] = D.xpos[b][k] + t[k];
-}
-
-// observation in the reference's key order (SawyerEnv._get_obs + SawyerPushObstacleEnv._get_obs)
-__device__ void write_obs(const mopa_sawyer_task &T, const DynData &D, const double *q, const double *v, float *obs) {
-    int o = 0;
-    for (int k = 0; k < 7; k++) obs[o++] = (float)q[T.arm_qadr[k]];
-    for (int k = 0; k < 7; k++) obs[o++] = (float)v[T.arm_vadr[k]];
-    for (int k = 0; k < 2; k++) obs[o++] = (float)q[T.grip_qadr[k]];
-    for (int k = 0; k < 2; k++) obs[o++] = (float)v[T.grip_vadr[k]];
-    double eef[3];
-    site_world(eef, D, T.body_ee, T.site_grip);
-    for (int k = 0; k < 3; k++) obs[o++] = (float)eef[k];
-    const double *eq = D.xquat[T.body_ee];  // wxyz -> xyzw
-    obs[o++] = (float)eq[1]; obs[o++] = (float)eq[2]; obs[o++] = (float)eq[3]; obs[o++] = (float)eq[0];
-    double target[3] = {T.target_base[0] + q[T.target_qadr[0]], T.target_base[1] + q[T.target_qadr[1]], T.target_base[2]};
-    for (int k = 0; k < 3; k++) obs[o++] = (float)target[k];
-    const double *cube = D.xpos[T.body_cube], *cq = D.xquat[T.body_cube];
-    for (int k = 0; k < 3; k++) obs[o++] = (float)cube[k];
-    obs[o++] = (float)cq[1]; obs[o++] = (float)cq[2]; obs[o++] = (float)cq[3]; obs[o++] = (float)cq[0];
-    for (int k = 0; k < 3; k++) obs[o++] = (float)(eef[k] - cube[k]);
-    for (int k = 0; k < 2; k++) obs[o++] = (float)(cube[k] - target[k]);
-}
-
-__global__ void __launch_bounds__(64) env_forward_kernel(const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B,
-                                                         const int32_t *__restrict__ ids, int n) {
-    __shared__ DynDev m;
-    for (int i = threadIdx.x; i < (int)(sizeof(DynDev) / 4); i += blockDim.x) reinterpret_cast<int *>(&m)[i] = reinterpret_cast<const int *>(mg)[i];
-    __syncthreads();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const int e = ids ? ids[t] : t;
-    double q[64], v[64], zero[DMAXD], ctrl[DMAXA];
-    for (int k = 0; k < m.nq; k++) q[k] = B.qpos[(size_t)e * m.nq + k];
-    for (int k = 0; k < m.nv; k++) v[k] = B.qvel[(size_t)e * m.nv + k];
-    for (int k = 0; k < DMAXD; k++) zero[k] = 0;
-    for (int k = 0; k < DMAXA; k++) ctrl[k] = 0;
-    DynData D;
-    dyn_substep(m, q, v, ctrl, zero, D, false);
-    for (int k = 0; k < DMAXD; k++) B.bias_prev[(size_t)e * DMAXD + k] = k < m.nd ? D.bias[k] : 0.0;
-    write_obs(T, D, q, v, B.obs + (size_t)e * 40);
-}
-
-__global__ void __launch_bounds__(64) env_step_kernel(const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B,
-                                                      const float *__restrict__ action, int action_stride,
-                                                      const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n) {
-    __shared__ DynDev m;
-    for (int i = threadIdx.x; i < (int)(sizeof(DynDev) / 4); i += blockDim.x) reinterpret_cast<int *>(&m)[i] = reinterpret_cast<const int *>(mg)[i];
-    __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || (mask && !mask[e])) return;
-    double q[64], v[64], applied[DMAXD], bias_prev[DMAXD], ctrl[DMAXA], prev[7];
-    for (int k = 0; k < m.nq; k++) q[k] = B.qpos[(size_t)e * m.nq + k];
-    for (int k = 0; k < m.nv; k++) v[k] = B.qvel[(size_t)e * m.nv + k];
-    for (int k = 0; k < DMAXD; k++) bias_prev[k] = B.bias_prev[(size_t)e * DMAXD + k];
-    const int mode = is_planner ? is_planner[e] : 0;  // 0 direct, 1 planner waypoint, 2 planner failure (no simulation)
-    const bool planner = mode == 1;
-    const bool had_prev = B.has_prev[e] != 0;
-    for (int k = 0; k < 7; k++) prev[k] = (!planner || !had_prev) ? q[T.arm_qadr[k]] : B.prev_state[(size_t)e * 7 + k];
-    for (int k = 0; k < DMAXA; k++) ctrl[k] = 0;
-    for (int k = 0; k < 7; k++) {
-        double a = (double)action[(size_t)e * action_stride + k];
-        if (!planner) a = a * T.ac_scale;
-        a = a < -T.ac_scale ? -T.ac_scale : (a > T.ac_scale ? T.ac_scale : a);
-        ctrl[k] = prev[k] + a;  // desired_state
-    }
-    // which simulated dofs get qfrc_applied = previous qfrc_bias (gravity compensation on the arm)
-    unsigned comp = 0;
-    for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
-    DynData D;
-    if (mode == 2) {
-        // planner failure (rl/mopa_rollouts.py:304-327): reward at the current state, no physics
-        for (int k = 0; k < DMAXD; k++) applied[k] = 0.0;
-        dyn_substep(m, q, v, ctrl, applied, D, false);
-    } else {
-        WarmStart warm;
-        warm.n = 0;
-        for (int s = 0; s < T.nsub; s++) {
-            for (int k = 0; k < DMAXD; k++) applied[k] = (comp >> k) & 1u ? bias_prev[k] : 0.0;
-            dyn_substep(m, q, v, ctrl, applied, D, true, &warm);
-            for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
-        }
-    }
-    // reward (frames are those of the last substep's start state, as mjData holds them after mj_step)
-    double re[3], le[3];
-    site_world(re, D, T.body_rclaw, T.site_right_eef);
-    site_world(le, D, T.body_lclaw, T.site_left_eef);
-    const double *cube = D.xpos[T.body_cube];
-    const double target[2] = {T.target_base[0] + q[T.target_qadr[0]], T.target_base[1] + q[T.target_qadr[1]]};
-    double dgc = 0;
-    for (int k = 0; k < 3; k++) { const double d = cube[k] - 0.5 * (re[k] + le[k]); dgc += d * d; }
-    dgc = sqrt(dgc);
-    const double dct = sqrt((cube[0] - target[0]) * (cube[0] - target[0]) + (cube[1] - target[1]) * (cube[1] - target[1]));
-    double reward = 0;
-    if (dct < 0.1) reward += 0.5 * (1 - tanh(5 * dct));
-    if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
-    bool success = false, terminal = false;
-    if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
-    if (mode != 2) write_obs(T, D, q, v, B.obs + (size_t)e * 40);
-    // _after_step: project limited joints back into range (set_state + forward), episode accounting
-    bool clipped = false;
-    for (int k = 0; k < m.nd; k++) {
-        if (!m.d_limited[k] || m.d_qadr[k] < 0) continue;
-        double &x = q[m.d_qadr[k]];
-        if (x < m.d_range[k][0]) { x = m.d_range[k][0]; clipped = true; }
-        else if (x > m.d_range[k][1]) { x = m.d_range[k][1]; clipped = true; }
-    }
-    if (clipped) {
-        dyn_substep(m, q, v, ctrl, applied, D, false);
-        for (int k = 0; k < m.nd; k++) bias_prev[k] = D.bias[k];
-    }
-    const int len = B.ep_len[e] + 1;
-    if (len == T.max_episode_steps) terminal = true;
-    for (int k = 0; k < m.nq; k++) B.qpos[(size_t)e * m.nq + k] = q[k];
-    for (int k = 0; k < m.nv; k++) B.qvel[(size_t)e * m.nv + k] = v[k];
-    if (mode != 2) {
-        for (int k = 0; k < 7; k++) B.prev_state[(size_t)e * 7 + k] = ctrl[k];
-        B.has_prev[e] = 1;
-    }
-    for (int k = 0; k < DMAXD; k++) B.bias_prev[(size_t)e * DMAXD + k] = bias_prev[k];
-    B.ep_len[e] = len;
-    B.ep_rew[e] += reward;
-    B.reward[e] = reward;
-    B.done[e] = terminal ? 1 : 0;
-    B.success[e] = success ? 1 : 0;
-    if (B.ncon) B.ncon[e] = D.ncon;
-}
 
 static void fill_model(const mopa_dyn_desc *d, DynDev &m) {
     memset(&m, 0, sizeof(m));
@@ -206,6 +74,17 @@ static void fill_model(const mopa_dyn_desc *d, DynDev &m) {
         for (int k = 0; k < 5; k++) m.g_solimp[i][k] = d->g_solimp[5 * i + k];
     }
     for (int i = 0; i < d->npair; i++) { m.p_g1[i] = d->p_g1[i]; m.p_g2[i] = d->p_g2[i]; }
+    // geom rotations: world matrix of a static geom / local matrix of a moving one; moving geoms whose local
+    // rotation is not the identity get a slot in the kernel's per-substep world-matrix cache
+    m.ngm = 0;
+    for (int i = 0; i < d->ngeom; i++) {
+        d_q2m(m.g_mat[i], m.g_quat[i]);
+        const bool ident = m.g_quat[i][0] == 1.0 && m.g_quat[i][1] == 0.0 && m.g_quat[i][2] == 0.0 && m.g_quat[i][3] == 0.0;
+        if (m.g_body[i] < 0) m.g_mslot[i] = -2;
+        else if (ident) m.g_mslot[i] = -1;
+        else if (m.ngm < DMAXGM) { m.gm_geom[m.ngm] = i; m.g_mslot[i] = m.ngm++; }
+        else m.ngm = DMAXGM + 1;   // too many: rejected by mopa_env_create
+    }
     m.enable_contacts = 1;
 }
 
@@ -224,7 +103,7 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     if (!dyn || !task || !out) { mopa_set_error("mopa_env_create: bad argument"); return MOPA_ERR_ARG; }
     *out = nullptr;
     if (dyn->nb > mopa::DMAXB || dyn->nd > mopa::DMAXD || dyn->nact > mopa::DMAXA || dyn->ngeom > mopa::DMAXG || dyn->npair > 512 ||
-        dyn->nq > 64 || dyn->nv > 64) {
+        dyn->nq > 40 || dyn->nv > 40) {
         mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
         return MOPA_ERR_MODEL;
     }
@@ -232,9 +111,8 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     mopa_env *e = new mopa_env();
     e->device = device;
     e->task = *task;
-    const char *kk = getenv("MOPA_ENV_KERNEL");
-    e->use_thread_kernel = (kk && std::string(kk) == "thread") ? 1 : 0;
     mopa::fill_model(dyn, e->h_model);
+    if (e->h_model.ngm > mopa::DMAXGM) { mopa_set_error("mopa_env_create: more rotated moving geoms than the env kernel caches"); delete e; return MOPA_ERR_MODEL; }
     cudaError_t err = cudaSetDevice(device);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_model, sizeof(mopa::DynDev));
     if (err == cudaSuccess) err = cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice);
@@ -282,12 +160,7 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
     if (!e || !buf || n < 0) { mopa_set_error("mopa_env_forward: bad argument"); return MOPA_ERR_ARG; }
     if (n == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    if (e->use_thread_kernel) {
-        mopa::env_forward_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_ids, n);
-        ENV_TRY(cudaGetLastError());
-    } else {
-        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->h_model.nb, e->h_model.ngeom, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
-    }
+    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
     return MOPA_OK;
 }
 
@@ -296,14 +169,8 @@ int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_actio
     if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
     if (n_envs == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    if (e->use_thread_kernel) {
-        mopa::env_step_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, e->task, *buf, d_action, action_stride,
-                                                                                  d_is_planner, d_mask, n_envs);
-        ENV_TRY(cudaGetLastError());
-    } else {
-        ENV_TRY(mopa::launch_env_warp(e->model_slot, e->h_model.nb, e->h_model.ngeom, e->task, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr,
-                                      (cudaStream_t)stream));
-    }
+    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->task, *buf, d_action, action_stride, d_is_planner,
+                                  d_mask, n_envs, 0, nullptr, (cudaStream_t)stream));
     return MOPA_OK;
 }
 

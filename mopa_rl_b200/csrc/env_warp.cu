@@ -58,6 +58,7 @@ struct WarpWS {
     double Y[WC * YS];
     alignas(16) double f[WC];   // gradient of the penalties per row; also the column buffer of w_factor_solve
     double gpos[WG][3];
+    double gmat[DMAXGM][9];  // world rotation of the moving geoms whose local rotation is not the identity
     double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
     int cga[WCP], cgb[WCP], csig[WCP];
     double wa[WD];           // warm start: acceleration of the previous substep (mjData.qacc_warmstart)
@@ -178,7 +179,7 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
 template <int WB, int WG>
-__device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
+__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
@@ -455,64 +456,64 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
     }
     int ncp = 0;
     if (m.enable_contacts && m.npair > 0) {
+        // Lane-indexed model reads go through the global copy `mg` (coalesced, L1 / L2 resident) - the
+        // constant bank serialises divergent addresses.  World frames of the contact geoms: centres for all
+        // of them, rotation matrices only where they are not already available (static geoms: precomputed
+        // in mg->g_mat; moving geoms with an identity local rotation: the body's xmat).
         for (int g = lane; g < m.ngeom; g += 32) {
-            const int body = m.g_body[g];
-            if (body < 0) { for (int k = 0; k < 3; k++) W.gpos[g][k] = m.g_pos[g][k]; }
+            const int body = mg->g_body[g];
+            if (body < 0) { for (int k = 0; k < 3; k++) W.gpos[g][k] = mg->g_pos[g][k]; }
             else {
                 const double *X = W.k.xmat[body];
-                for (int k = 0; k < 3; k++)
-                    W.gpos[g][k] = W.k.xpos[body][k] + X[3 * k] * m.g_pos[g][0] + X[3 * k + 1] * m.g_pos[g][1] + X[3 * k + 2] * m.g_pos[g][2];
+                const double p0 = mg->g_pos[g][0], p1 = mg->g_pos[g][1], p2 = mg->g_pos[g][2];
+                for (int k = 0; k < 3; k++) W.gpos[g][k] = W.k.xpos[body][k] + X[3 * k] * p0 + X[3 * k + 1] * p1 + X[3 * k + 2] * p2;
             }
         }
+        if (lane < m.ngm) {
+            const int g = m.gm_geom[lane];
+            const double *X = W.k.xmat[mg->g_body[g]], *Rl = mg->g_mat[g];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) W.gmat[lane][3 * r + c] = X[3 * r] * Rl[c] + X[3 * r + 1] * Rl[3 + c] + X[3 * r + 2] * Rl[6 + c];
+        }
         __syncwarp();
+        auto geom_R = [&](int g) -> const double * {
+            const int slot = mg->g_mslot[g];
+            return slot == -2 ? mg->g_mat[g] : (slot == -1 ? W.k.xmat[mg->g_body[g]] : W.gmat[slot]);
+        };
         int ncand = 0;
         for (int base = 0; base < m.npair; base += 32) {
             const int p = base + lane;
             bool keep = false;
             if (p < m.npair) {
-                const int a = m.p_g1[p], b = m.p_g2[p];
+                const int a = mg->p_g1[p], b = mg->p_g2[p];
                 keep = true;
-                const double margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
-                const int ta = m.g_type[a], tb = m.g_type[b];
+                const double ma = mg->g_margin[a], mb = mg->g_margin[b], margin = ma > mb ? ma : mb;
+                const int ta = mg->g_type[a], tb = mg->g_type[b];
+                const double ra = mg->g_rbound[a], rb = mg->g_rbound[b];
                 if (ta != 0 && tb != 0) {
                     const double d[3] = {W.gpos[b][0] - W.gpos[a][0], W.gpos[b][1] - W.gpos[a][1], W.gpos[b][2] - W.gpos[a][2]};
-                    const double bound = m.g_rbound[a] + m.g_rbound[b] + margin;
+                    const double bound = ra + rb + margin;
                     keep = !(d_dot(d, d) > bound * bound);
                     // box pairs: the bounding sphere of a flat box (table, bin walls) is hopelessly loose; test the
                     // other geom's bounding sphere against the box itself (exact point-to-box distance)
                     if (keep && (ta == 6 || tb == 6)) {
-                        const bool box_a = ta == 6 && (tb != 6 || m.g_rbound[a] >= m.g_rbound[b]);
-                        const int gx = box_a ? a : b, go = box_a ? b : a, body = m.g_body[gx];
-                        double Rl[9], gq[4] = {m.g_quat[gx][0], m.g_quat[gx][1], m.g_quat[gx][2], m.g_quat[gx][3]};
-                        d_q2m(Rl, gq);
-                        double t[3] = {box_a ? d[0] : -d[0], box_a ? d[1] : -d[1], box_a ? d[2] : -d[2]};   // other centre - box centre
-                        if (body >= 0) {
-                            const double *X = W.k.xmat[body];
-                            const double u0 = X[0] * t[0] + X[3] * t[1] + X[6] * t[2], u1 = X[1] * t[0] + X[4] * t[1] + X[7] * t[2],
-                                         u2 = X[2] * t[0] + X[5] * t[1] + X[8] * t[2];
-                            t[0] = u0; t[1] = u1; t[2] = u2;
-                        }
+                        const bool box_a = ta == 6 && (tb != 6 || ra >= rb);
+                        const int gx = box_a ? a : b;
+                        const double *R = geom_R(gx), sg = box_a ? 1.0 : -1.0;   // other centre - box centre = sg * d
                         double e2 = 0;
                         for (int k = 0; k < 3; k++) {
-                            const double l = Rl[k] * t[0] + Rl[3 + k] * t[1] + Rl[6 + k] * t[2], ex = fabs(l) - m.g_size[gx][k];
+                            const double l = sg * (R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2]), ex = fabs(l) - mg->g_size[gx][k];
                             if (ex > 0) e2 += ex * ex;
                         }
-                        const double bo = m.g_rbound[go] + margin + 1e-9;
+                        const double bo = (box_a ? rb : ra) + margin + 1e-9;
                         keep = !(e2 > bo * bo);
                     }
                     // capsule / cylinder pairs: both shapes lie inside the capsule (segment, radius) around
                     // their axis, so the segment-segment distance bounds the true distance from below
                     if (keep && (ta == 3 || ta == 5) && (tb == 3 || tb == 5)) {
-                        double a1[3], a2[3];
-                        for (int side = 0; side < 2; side++) {
-                            const int g = side ? b : a, body = m.g_body[g];
-                            double Rl[9], gq[4] = {m.g_quat[g][0], m.g_quat[g][1], m.g_quat[g][2], m.g_quat[g][3]}, zl[3], *ax = side ? a2 : a1;
-                            d_q2m(Rl, gq);
-                            zl[0] = Rl[2]; zl[1] = Rl[5]; zl[2] = Rl[8];
-                            if (body < 0) { ax[0] = zl[0]; ax[1] = zl[1]; ax[2] = zl[2]; }
-                            else d_mv(ax, W.k.xmat[body], zl);
-                        }
-                        const double h1 = m.g_size[a][1], h2 = m.g_size[b][1];
+                        const double *Ra = geom_R(a), *Rb = geom_R(b);
+                        const double a1[3] = {Ra[2], Ra[5], Ra[8]}, a2[3] = {Rb[2], Rb[5], Rb[8]};
+                        const double h1 = mg->g_size[a][1], h2 = mg->g_size[b][1];
                         const double r[3] = {-d[0], -d[1], -d[2]};
                         const double bb = d_dot(a1, a2), c = d_dot(a1, r), f = d_dot(a2, r), den = 1.0 - bb * bb;
                         double sp = den > 1e-9 ? c_clamp((bb * f - c) / den, -h1, h1) : 0.0, tp = bb * sp + f;
@@ -520,17 +521,16 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
                         else if (tp > h2) { tp = h2; sp = c_clamp(bb * tp - c, -h1, h1); }
                         double w[3];
                         for (int k = 0; k < 3; k++) w[k] = r[k] + sp * a1[k] - tp * a2[k];
-                        const double lo = sqrt(d_dot(w, w)) - m.g_size[a][0] - m.g_size[b][0];
+                        const double lo = sqrt(d_dot(w, w)) - mg->g_size[a][0] - mg->g_size[b][0];
                         keep = lo < margin + 1e-9;
                     }
                 } else {
                     // plane pairs: nothing of geom b is closer to the plane than its centre height minus rbound
                     const int gp = ta == 0 ? a : b, go = ta == 0 ? b : a;
-                    double Rl[9], gq[4] = {m.g_quat[gp][0], m.g_quat[gp][1], m.g_quat[gp][2], m.g_quat[gp][3]};
-                    d_q2m(Rl, gq);
-                    const double hgt = (W.gpos[go][0] - W.gpos[gp][0]) * Rl[2] + (W.gpos[go][1] - W.gpos[gp][1]) * Rl[5] +
-                                       (W.gpos[go][2] - W.gpos[gp][2]) * Rl[8];
-                    keep = hgt - m.g_rbound[go] < margin + 1e-9;
+                    const double *Rp = geom_R(gp);
+                    const double hgt = (W.gpos[go][0] - W.gpos[gp][0]) * Rp[2] + (W.gpos[go][1] - W.gpos[gp][1]) * Rp[5] +
+                                       (W.gpos[go][2] - W.gpos[gp][2]) * Rp[8];
+                    keep = hgt - (ta == 0 ? rb : ra) < margin + 1e-9;
                 }
             }
             const unsigned mask = __ballot_sync(FULL, keep);
@@ -542,54 +542,70 @@ __device__ __noinline__ void w_substep(const DynDev &m, WarpWS<WB, WG> &W, unsig
         __syncwarp();
         PROF_MARK(23);
         if (c_tune.prof && lane == 0) atomicAdd(&g_prof[29], (unsigned long long)ncand);
+        // ---- narrow phase, lane = surviving pair.  Geometry is referenced in place (shared / global memory):
+        // nothing here may live in a per-thread stack array, a single lane walking local memory drags whole
+        // 32-lane-interleaved lines through L1.  Pairs whose contact needs the polygon clipper (box face
+        // contacts) run that part one lane at a time on the warp's shared scratch; contact points are
+        // committed in pair order.
         const int maxcp = min(WCP, (WC - nlim) / 3);
-        for (int base = 0; base < ncand; base += 32) {
+        for (int base = 0; base < ncand && ncp < maxcp; base += 32) {
             const int ci = base + lane;
             CPoint cps[4];
-            int nc = 0, a = 0, b = 0;
+            int nc = 0, a = 0, b = 0, clip_code = -1;
             double margin = 0;
             if (ci < ncand) {
                 const int p = W.cand[ci];
-                a = m.p_g1[p]; b = m.p_g2[p];
-                margin = m.g_margin[a] > m.g_margin[b] ? m.g_margin[a] : m.g_margin[b];
-                double gR[2][9], gc[2][3], gs[2][3];
-                for (int side = 0; side < 2; side++) {
-                    const int g = side ? b : a, body = m.g_body[g];
-                    double Rl[9], gq[4] = {m.g_quat[g][0], m.g_quat[g][1], m.g_quat[g][2], m.g_quat[g][3]};
-                    d_q2m(Rl, gq);
-                    for (int k = 0; k < 3; k++) { gc[side][k] = W.gpos[g][k]; gs[side][k] = m.g_size[g][k]; }
-                    if (body < 0) { for (int k = 0; k < 9; k++) gR[side][k] = Rl[k]; }
-                    else {
-                        const double *X = W.k.xmat[body];
-                        for (int r = 0; r < 3; r++)
-                            for (int c = 0; c < 3; c++) gR[side][3 * r + c] = X[3 * r] * Rl[c] + X[3 * r + 1] * Rl[3 + c] + X[3 * r + 2] * Rl[6 + c];
+                a = mg->p_g1[p]; b = mg->p_g2[p];
+                const double ma = mg->g_margin[a], mb = mg->g_margin[b];
+                margin = ma > mb ? ma : mb;
+                const int ta = mg->g_type[a], tb = mg->g_type[b];
+                CGeom ga{W.gpos[a], geom_R(a), mg->g_size[a], ta}, gb{W.gpos[b], geom_R(b), mg->g_size[b], tb};
+                if (ta == 6 && tb == 6) {
+                    int code = 0;
+                    double depth = 0;
+                    const int kind = box_box_sat(ga, gb, margin, code, depth);
+                    if (kind == 1) nc = box_box_edge(cps, ga, gb, code, depth);
+                    else if (kind == 2) clip_code = code;
+                } else
+                    nc = pair_contacts_ni(cps, ga, gb, margin);
+            }
+            unsigned pending = __ballot_sync(FULL, nc > 0 || clip_code >= 0);
+            while (pending && ncp < maxcp) {
+                const int l = __ffs(pending) - 1;
+                pending &= pending - 1;
+                int ncl = 0;
+                if (lane == l) {
+                    const CPoint *src = cps;
+                    if (clip_code >= 0) {
+                        CGeom ga{W.gpos[a], geom_R(a), mg->g_size[a], 6}, gb{W.gpos[b], geom_R(b), mg->g_size[b], 6};
+                        // clipper output + scratch: the last rows of W.Y (constraint rows are written after the narrow phase;
+                        // the limit rows already there occupy at most the first nd <= 16 rows)
+                        double *scr = W.Y + (WC - 6) * YS;
+                        static_assert(6 * YS >= 28 + 24 + 24 + 8 + 4 && WC - 6 >= WD, "clipper scratch does not fit behind the limit rows");
+                        CPoint *cout = reinterpret_cast<CPoint *>(scr);
+                        nc = box_box_face(cout, ga, gb, clip_code, margin, reinterpret_cast<double(*)[3]>(scr + 28), reinterpret_cast<double(*)[3]>(scr + 52),
+                                          scr + 76, reinterpret_cast<int *>(scr + 84));
+                        src = cout;
                     }
+                    const double fa = mg->g_friction[a][0], fb = mg->g_friction[b][0];
+                    for (int qn = 0; qn < nc; qn++) {
+                        const int slot = ncp + qn;
+                        if (slot >= maxcp) break;
+                        for (int k = 0; k < 3; k++) { W.cpos[slot][k] = src[qn].pos[k]; W.cn[slot][k] = src[qn].n[k]; }
+                        W.cdist[slot] = src[qn].dist;
+                        W.cmargin[slot] = margin;
+                        W.cmu[slot] = fa > fb ? fa : fb;
+                        for (int k = 0; k < 2; k++) W.csolref[slot][k] = 0.5 * (mg->g_solref[a][k] + mg->g_solref[b][k]);
+                        for (int k = 0; k < 5; k++) W.csolimp[slot][k] = 0.5 * (mg->g_solimp[a][k] + mg->g_solimp[b][k]);
+                        W.cga[slot] = a; W.cgb[slot] = b;
+                        W.csig[slot] = W.cand[ci] * 16 + qn * 4;
+                    }
+                    ncl = nc;
                 }
-                CGeom ga{gc[0], gR[0], gs[0], m.g_type[a]}, gb{gc[1], gR[1], gs[1], m.g_type[b]};
-                nc = pair_contacts_ni(cps, ga, gb, margin);
+                ncp += __shfl_sync(FULL, ncl, l);
+                if (ncp > maxcp) ncp = maxcp;
+                __syncwarp();
             }
-            // ordered compaction of the contact points of this round
-            int incl = nc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int start = ncp + incl - nc;
-            for (int qn = 0; qn < nc; qn++) {
-                const int slot = start + qn;
-                if (slot >= maxcp) break;
-                for (int k = 0; k < 3; k++) { W.cpos[slot][k] = cps[qn].pos[k]; W.cn[slot][k] = cps[qn].n[k]; }
-                W.cdist[slot] = cps[qn].dist;
-                W.cmargin[slot] = margin;
-                W.cmu[slot] = m.g_friction[a][0] > m.g_friction[b][0] ? m.g_friction[a][0] : m.g_friction[b][0];
-                for (int k = 0; k < 2; k++) W.csolref[slot][k] = 0.5 * (m.g_solref[a][k] + m.g_solref[b][k]);
-                for (int k = 0; k < 5; k++) W.csolimp[slot][k] = 0.5 * (m.g_solimp[a][k] + m.g_solimp[b][k]);
-                W.cga[slot] = a; W.cgb[slot] = b;
-                W.csig[slot] = W.cand[ci] * 16 + qn * 4;
-            }
-            ncp += __shfl_sync(FULL, incl, 31);
-            if (ncp >= maxcp) { ncp = maxcp; break; }
         }
         __syncwarp();
         PROF_MARK(24);
@@ -898,7 +914,7 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, 
 
 template <int WB, int WG, int ENV_WARPS>
 __global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 ? 2 : 1))
-env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
+env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -911,7 +927,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (!forward_only) {
             int dummy = 0;
-            for (int s = 0; s < T.nsub; s++) w_substep(m, W, 0u, true, lane, dummy, make_int4(0, 0, 0, 0), false, true);
+            for (int s = 0; s < T.nsub; s++) w_substep(m, mg, W, 0u, true, lane, dummy, make_int4(0, 0, 0, 0), false, true);
         }
         return;
     }
@@ -925,7 +941,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     int ncon = 0;
     const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw);
     if (forward_only) {
-        w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
         if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
         w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
         return;
@@ -943,9 +959,9 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     __syncwarp();
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
-    if (mode == 2) w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+    if (mode == 2) w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
     for (int s = 0; s < T.nsub; s++) {
-        w_substep(m, W, comp, true, lane, ncon, keep, mode != 2, true);
+        w_substep(m, mg, W, comp, true, lane, ncon, keep, mode != 2, true);
         if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -976,7 +992,7 @@ env_step_warp_kernel(int model_slot, mopa_sawyer_task T, mopa_env_buffers B, con
     clipped = __any_sync(FULL, clipped);
     __syncwarp();
     if (clipped) {
-        w_substep(m, W, 0u, false, lane, ncon, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
         if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1012,10 +1028,11 @@ cudaError_t upload_env_model(int slot, const DynDev &h_model) {
 }
 
 template <int WB, int WG, int ENV_WARPS>
-static cudaError_t launch_env_warp_t(int model_slot, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                                      int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                                      const int32_t *ids, cudaStream_t stream) {
     static bool attr_set = false;
+    static_assert(sizeof(WarpWS<WB, WG>) * ENV_WARPS <= 227 * 1024, "warp workspaces exceed the shared memory of an SM");
     const size_t smem = sizeof(WarpWS<WB, WG>) * ENV_WARPS;
     auto kern = env_step_warp_kernel<WB, WG, ENV_WARPS>;
     if (!attr_set) {
@@ -1023,21 +1040,21 @@ static cudaError_t launch_env_warp_t(int model_slot, const mopa_sawyer_task &T, 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, T, B, action, action_stride, is_planner, mask, n,
+    kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n,
                                                                             forward_only, ids);
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_warp(int model_slot, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream) {
     static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
     if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
     if (nb <= 14 && ngeom <= 32 && small_warps)
-        return launch_env_warp_t<14, 32, 7>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 7>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     if (nb <= 14 && ngeom <= 32)
-        return launch_env_warp_t<14, 32, 14>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
-    return launch_env_warp_t<DMAXB, DMAXG, 11>(model_slot, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 14>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+    return launch_env_warp_t<DMAXB, DMAXG, 11>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
 }
 
 size_t env_warp_smem_per_warp() { return sizeof(WarpWS<14, 32>); }
