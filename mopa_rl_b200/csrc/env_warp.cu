@@ -507,6 +507,22 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
                         }
                         const double bo = (box_a ? rb : ra) + margin + 1e-9;
                         keep = !(e2 > bo * bo);
+                        // capsule / cylinder against the box: per box axis the gap between the slab and the projected
+                        // segment; the root sum of squares bounds the segment-box distance from below
+                        const int go = box_a ? b : a, to = box_a ? tb : ta;
+                        if (keep && (to == 3 || to == 5)) {
+                            const double *Ro = geom_R(go);
+                            const double ax[3] = {Ro[2], Ro[5], Ro[8]}, hl = mg->g_size[go][1];
+                            double g2 = 0;
+                            for (int k = 0; k < 3; k++) {
+                                const double l = sg * (R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2]);
+                                const double ak = R[k] * ax[0] + R[3 + k] * ax[1] + R[6 + k] * ax[2];
+                                const double gap = fabs(l) - fabs(ak) * hl - mg->g_size[gx][k];
+                                if (gap > 0) g2 += gap * gap;
+                            }
+                            const double bc = mg->g_size[go][0] + margin + 1e-9;
+                            keep = !(g2 > bc * bc);
+                        }
                     }
                     // capsule / cylinder pairs: both shapes lie inside the capsule (segment, radius) around
                     // their axis, so the segment-segment distance bounds the true distance from below
@@ -704,19 +720,27 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         trM = warp_sum(trM);
         const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
         double cost = 0, x0 = 0, x1 = 0, x2 = 0, gsr = 0, h0 = 0, h1 = 0, h2 = 0;
-        // evaluates cost / gradient (W.rhs) / M a - tau (W.z) at W.a; with_hess: Hessian (lower triangle) -> W.L
-        auto newton_eval = [&](bool with_hess) {
+        // evaluates cost / gradient (W.rhs) / M a - tau (W.z) at W.a
+        auto newton_eval = [&]() {
             double mat = 0, cq = 0;
             if (lane < nd) {
-                for (int j = 0; j < nd; j++) mat += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.a[j];
+                double m1 = 0;   // two accumulators: the dependent-add chain is the latency of these loops
+                for (int j = 0; j + 1 < nd; j += 2) {
+                    mat += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.a[j];
+                    m1 += W.M[j + 1 <= lane ? TRI(lane, j + 1) : TRI(j + 1, lane)] * W.a[j + 1];
+                }
+                if (nd & 1) mat += W.M[TRI(nd - 1, lane)] * W.a[nd - 1];
+                mat += m1;
                 mat -= W.tau[lane];
                 cq = 0.5 * (W.a[lane] - W.qacc0[lane]) * mat;
                 W.z[lane] = mat;
             }
             double x = 0;
             if (r < nc) {
-                for (int k = 0; k < nd; k++) x += W.Y[r * YS + k] * W.a[k];
-                x -= aref;
+                double xb = 0;
+                for (int k = 0; k + 1 < nd; k += 2) { x += W.Y[r * YS + k] * W.a[k]; xb += W.Y[r * YS + k + 1] * W.a[k + 1]; }
+                if (nd & 1) x += W.Y[r * YS + nd - 1] * W.a[nd - 1];
+                x = (x + xb) - aref;
             }
             x0 = shfl_d(x, base & 31); x1 = shfl_d(x, (base + 1) & 31); x2 = shfl_d(x, (base + 2) & 31);
             double sc = 0;
@@ -741,61 +765,54 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             if (lane < WC) W.f[lane] = gsr;
             __syncwarp();
             if (lane < nd) {
-                double gg = mat;
-                for (int s2 = 0; s2 < nc; s2++) gg += W.Y[s2 * YS + lane] * W.f[s2];
-                W.rhs[lane] = gg;
-            }
-            if (with_hess) {
-                // K_r = sum_q Hc[dirn][q] J_(base+q)  ->  H = M + sum_r J_r^T K_r
-                if (r < nc) {
-                    const bool blockrow = type >= 1;
-                    for (int j = 0; j < nd; j++) {
-                        double kk = h0 * W.Y[base * YS + j];
-                        if (blockrow) kk += h1 * W.Y[(base + 1) * YS + j] + h2 * W.Y[(base + 2) * YS + j];
-                        W.A[r * WD + j] = kk;
-                    }
-                }
-                __syncwarp();
-                for (int e = lane; e < ntri; e += 32) {
-                    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-                    while (TRI(i + 1, 0) <= e) i++;
-                    while (TRI(i, 0) > e) i--;
-                    const int j = e - TRI(i, 0);
-                    double hh = W.M[e];
-                    for (int s2 = 0; s2 < nc; s2++) hh += W.Y[s2 * YS + i] * W.A[s2 * WD + j];
-                    W.L[e] = hh;
-                }
+                double gg = mat, g1 = 0;
+                for (int s2 = 0; s2 + 1 < nc; s2 += 2) { gg += W.Y[s2 * YS + lane] * W.f[s2]; g1 += W.Y[(s2 + 1) * YS + lane] * W.f[s2 + 1]; }
+                if (nc & 1) gg += W.Y[(nc - 1) * YS + lane] * W.f[nc - 1];
+                W.rhs[lane] = gg + g1;
             }
             __syncwarp();
         };
-        // warm start: the previous substep's acceleration unless the unconstrained one costs less.
-        // One evaluation site: phase 0 = cost at a0, 1 = full evaluation at the warm start, 2 = full evaluation
-        // at a0 (no / rejected warm start), 3 = evaluation after a Newton step.
-        if (lane < nd) W.a[lane] = W.qacc0[lane];
+        // Hessian (lower triangle) -> W.L from the cone terms of the latest evaluation
+        auto newton_hess = [&]() {
+            // K_r = sum_q Hc[dirn][q] J_(base+q)  ->  H = M + sum_r J_r^T K_r
+            if (r < nc) {
+                const bool blockrow = type >= 1;
+                for (int j = 0; j < nd; j++) {
+                    double kk = h0 * W.Y[base * YS + j];
+                    if (blockrow) kk += h1 * W.Y[(base + 1) * YS + j] + h2 * W.Y[(base + 2) * YS + j];
+                    W.A[r * WD + j] = kk;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < ntri; e += 32) {
+                int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                while (TRI(i + 1, 0) <= e) i++;
+                while (TRI(i, 0) > e) i--;
+                const int j = e - TRI(i, 0);
+                double hh = W.M[e], hb = 0;
+                for (int s2 = 0; s2 + 1 < nc; s2 += 2) { hh += W.Y[s2 * YS + i] * W.A[s2 * WD + j]; hb += W.Y[(s2 + 1) * YS + i] * W.A[(s2 + 1) * WD + j]; }
+                if (nc & 1) hh += W.Y[(nc - 1) * YS + i] * W.A[(nc - 1) * WD + j];
+                W.L[e] = hh + hb;
+            }
+            __syncwarp();
+        };
+        // warm start: the previous substep's acceleration when there is one (the oracle, like MuJoCo, first
+        // compares its cost with the unconstrained acceleration's; the minimiser is the same either way).
+        // One evaluation site; the Hessian is only assembled once it is known that a Newton step follows.
+        if (lane < nd) W.a[lane] = W.wn ? W.wa[lane] : W.qacc0[lane];
         __syncwarp();
-        int phase = W.wn ? 0 : 2, it = 0;
-        double c0 = 0, old = 0;
+        int it = 0;
+        bool first = true;
+        double old = 0;
         for (;;) {
-            newton_eval(phase >= 1);
-            if (phase == 0) {
-                c0 = cost;
-                if (lane < nd) W.a[lane] = W.wa[lane];
-                __syncwarp();
-                phase = 1;
-                continue;
-            }
-            if (phase == 1 && !(cost < c0)) {
-                if (lane < nd) W.a[lane] = W.qacc0[lane];
-                __syncwarp();
-                phase = 2;
-                continue;
-            }
-            if (phase == 3 && scale * (old - cost) < m.tolerance) break;
-            phase = 3;
+            newton_eval();
+            if (!first && scale * (old - cost) < m.tolerance) break;
+            first = false;
             if (it++ >= m.iterations) break;
             const double gme = lane < nd ? W.rhs[lane] : 0.0;
             const double gn = warp_sum(gme * gme);
             if (scale * sqrt(gn) < m.tolerance) break;
+            newton_hess();
             if (c_tune.prof && lane == 0) { atomicAdd(&g_prof[20], 1ULL); if (it == m.iterations) atomicAdd(&g_prof[28], 1ULL); }
             // search direction p = -H^-1 g (W.rhs in place; W.z keeps M a - tau)
             const double matme = lane < nd ? W.z[lane] : 0.0;
@@ -805,12 +822,23 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             double pme = 0, mp = 0;
             if (lane < nd) {
                 pme = W.rhs[lane];
-                for (int j = 0; j < nd; j++) mp += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.rhs[j];
+                double mq = 0;
+                for (int j = 0; j + 1 < nd; j += 2) {
+                    mp += W.M[j <= lane ? TRI(lane, j) : TRI(j, lane)] * W.rhs[j];
+                    mq += W.M[j + 1 <= lane ? TRI(lane, j + 1) : TRI(j + 1, lane)] * W.rhs[j + 1];
+                }
+                if (nd & 1) mp += W.M[TRI(nd - 1, lane)] * W.rhs[nd - 1];
+                mp += mq;
             }
             const double q1 = warp_sum(pme * matme), q2 = warp_sum(pme * mp), d0 = warp_sum(pme * gme);
             double jp = 0;
             if (r < nc)
-                for (int k = 0; k < nd; k++) jp += W.Y[r * YS + k] * W.rhs[k];
+            {
+                double jq = 0;
+                for (int k = 0; k + 1 < nd; k += 2) { jp += W.Y[r * YS + k] * W.rhs[k]; jq += W.Y[r * YS + k + 1] * W.rhs[k + 1]; }
+                if (nd & 1) jp += W.Y[r * YS + nd - 1] * W.rhs[nd - 1];
+                jp += jq;
+            }
             const double jp0 = shfl_d(jp, base & 31), jp1 = shfl_d(jp, (base + 1) & 31), jp2 = shfl_d(jp, (base + 2) & 31);
             // exact line search: safeguarded Newton iteration on phi'(alpha)
             double alpha = 1.0, lo = 0.0, hi = -1.0;
