@@ -207,23 +207,22 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- GPU arm: rollout
 class HostLoopPolicy:
-    """End-to-end arm: the policy lives on the host (as the reference's actor loop does): observations
-    of the envs that need an action come back to pinned host memory, actions go up from pinned memory."""
+    """End-to-end arm: the policy lives on the host (as the reference's actor loop does): every tick the
+    observations of all environments come back to pinned host memory and the actions go up from pinned memory."""
 
-    def __init__(self, torch, device, seed, n_max):
-        self.torch, self.device = torch, device
+    def __init__(self, torch, device, seed, n):
+        self.torch, self.device, self.n = torch, device, n
         self.rng = np.random.Generator(np.random.PCG64(seed))
-        self.h_obs = torch.zeros(n_max, 40, dtype=torch.float32).pin_memory()
-        self.h_act = torch.zeros(n_max, 7, dtype=torch.float32).pin_memory()
+        self.h_obs = torch.zeros(n, 40, dtype=torch.float32).pin_memory()
+        self.h_act = torch.zeros(n, 7, dtype=torch.float32).pin_memory()
         self.h2d = self.d2h = 0
 
     def __call__(self, obs, env_ids=None, macro_index=None):
-        k = obs.shape[0]
-        self.h_obs[:k].copy_(obs, non_blocking=False)
-        self.h_act[:k] = self.torch.from_numpy(self.rng.uniform(-1, 1, (k, 7)).astype(np.float32))
-        self.d2h += k * 40 * 4
-        self.h2d += k * 7 * 4
-        return self.h_act[:k].to(self.device, non_blocking=True)
+        self.h_obs.copy_(obs, non_blocking=False)
+        self.h_act.copy_(self.torch.from_numpy(self.rng.uniform(-1, 1, (self.n, 7)).astype(np.float32)))
+        self.d2h += self.n * 40 * 4
+        self.h2d += self.n * 7 * 4
+        return self.h_act.to(self.device, non_blocking=True)
 
 
 def run_rollout(args):
@@ -232,7 +231,7 @@ def run_rollout(args):
 
     from mopa_rl_b200.envs import VecSawyerPushObstacle
     from mopa_rl_b200.replay import ReplicatedReplay
-    from mopa_rl_b200.rollout import MoPAConfig, VecMoPARolloutRunner
+    from mopa_rl_b200.rollout import MoPAConfig, NativeMoPARolloutRunner
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -250,51 +249,53 @@ def run_rollout(args):
 
     def make(policy=None):
         venv = VecSawyerPushObstacle(n, seed=1234, device=local_rank, env_id_offset=rank * n)
-        return VecMoPARolloutRunner(venv, cfg, policy=policy)
+        return NativeMoPARolloutRunner(venv, cfg, policy=policy)
 
-    def timed(runner, replay, h_trans=None):
-        """W warm-up ticks, then K timed ticks.  Returns (ms, env_steps, launches, kernel_ms list, d2h bytes)."""
+    def timed(runner, replay, h_trans=None, h_flags=None):
+        """W warm-up ticks, then K timed ticks.  Returns (device ms, wall ms, env_steps, launches, env-kernel ms, d2h bytes)."""
         d2h = 0
         for _ in range(args.warmup):
             runner.tick()
-            replay.exchange(runner.last_emitted)
+            replay.exchange_slab(*runner.last_emitted)
         barrier()
-        runner.step_events = []
         l0, s0 = runner.launches, runner.env_steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             runner.tick()
-            replay.exchange(runner.last_emitted)
-            if h_trans is not None and runner.last_emitted is not None:
-                k = runner.last_emitted.shape[0]
-                h_trans[:k].copy_(runner.last_emitted, non_blocking=False)
-                d2h += k * 92 * 4
+            replay.exchange_slab(*runner.last_emitted)
+            if h_trans is not None:   # end-to-end arm: this tick's transition records back to pinned host memory
+                h_trans.copy_(runner.slab, non_blocking=True)
+                h_flags.copy_(runner.emit_flag, non_blocking=False)
+                d2h += n * 93 * 4 - n * 3
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         dev_ms = e0.elapsed_time(e1)
-        kms = [a.elapsed_time(b) for a, b in runner.step_events]
-        runner.step_events = None
-        return max(dev_ms, 0.0), wall_ms, runner.env_steps - s0, runner.launches - l0, kms, d2h
+        k_ms = runner.env_kernel_ms(args.steps)
+        return max(dev_ms, 0.0), wall_ms, runner.env_steps - s0, runner.launches - l0, k_ms, d2h
 
     # device-resident arm
     runner = make()
-    replay = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=max(8192, n))
+    replay = ReplicatedReplay(torch, dev, capacity=1 << 20)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, steps, launches, kms, _ = timed(runner, replay)
+    dev_ms, wall_ms, steps, launches, k_ms, _ = timed(runner, replay)
     clocks = sampler.stop() if rank == 0 else None
     counters = dict(runner.counters)
     # end-to-end arm: host-side policy loop + transition records read back to pinned host memory every tick
     hp = HostLoopPolicy(torch, dev, 99 + rank, n)
     runner2 = make(policy=hp)
-    replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=max(8192, n))
+    replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20)
     h_trans = torch.zeros(n, 92, dtype=torch.float32).pin_memory()
+    h_flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for _ in range(args.warmup):
+        runner2.tick()
     hp.h2d = hp.d2h = 0
-    _, wall2_ms, steps2, _, _, d2h_tr = timed(runner2, replay2, h_trans)
+    _, wall2_ms, steps2, _, _, d2h_tr = timed(runner2, replay2, h_trans, h_flags)
+    e2e_ticks = args.warmup + args.steps   # hp counts the warm-up ticks of timed() as well
     t = torch.tensor([wall_ms, wall2_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([steps, steps2], dtype=torch.float64, device=dev)
     if world > 1:
@@ -305,7 +306,6 @@ def run_rollout(args):
     if rank == 0:
         peak, peak_kind = measured_peaks()
         bytes_per_env_step = 816  # 352 B state/action in + 464 B state/obs out
-        k_ms = float(np.mean(kms)) if kms else float("nan")
         achieved = bytes_per_env_step * n / (k_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter)
@@ -317,14 +317,14 @@ def run_rollout(args):
                        "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
                        "device_ms_per_step": dev_ms / args.steps, "counters": counters},
             "clocks": clocks,
-            "e2e": {"value": tot_steps2 / (wall2_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": hp.h2d / args.steps,
-                    "d2h_bytes_per_step": (hp.d2h + d2h_tr) / args.steps,
-                    "api": "VecMoPARolloutRunner.tick() with a host-side policy loop (obs D2H, actions H2D from pinned memory) and transition records read back every tick"},
+            "e2e": {"value": tot_steps2 / (wall2_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": hp.h2d / e2e_ticks,
+                    "d2h_bytes_per_step": hp.d2h / e2e_ticks + d2h_tr / args.steps,
+                    "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_kind, "kernel": "env_step_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
-                         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * len(kms) / max(dev_ms, 1e-9),
-                         "note": "75 substeps per env.step run on chip: the kernel is fp64 compute/latency bound, not HBM bound"},
+                         "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
+                         "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
+                         "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d macro actions on each of %d scalar runners (%d env-steps, %.1f s)" % (args.cpu_macros, cores, cpu_steps, cpu_busy)},
         }

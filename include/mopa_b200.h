@@ -153,6 +153,40 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
 int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
                   const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-resident experience collection (replaces MoPARolloutRunner.run, rl/mopa_rollouts.py:22-399, and the
+ * planner glue of SACAgent / PlannerAgent / SamplingBasedPlanner.plan it calls, rl/sac_agent.py:145-318).
+ * One tick = mopa_rollout_pre, the caller's policy on the observations of all environments, mopa_rollout_step.
+ */
+typedef struct mopa_rollout mopa_rollout;
+typedef struct mopa_rollout_config {
+    int32_t n_envs, max_iter, max_path, max_traj, rrt_capacity, num_trials, invalid_target_handling, interpolation;
+    double omega, action_range, ac_scale, discount, step_size, joint_margin, range;
+    uint64_t seed_env;            /* seed of the reset draws (keyed by env id and episode number) */
+    int64_t env_id_offset;        /* global id of environment row 0 (shards of a multi-GPU run) */
+    double jnt_lo[7], jnt_hi[7];  /* joint ranges of the arm */
+    double init_qpos[7];          /* arm pose the reset noise is added to */
+    const double *qpos0;          /* host, nq: reset pose of everything else */
+} mopa_rollout_config;
+/* Counter slots of d_counters (int64[16]). */
+#define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting"
+/* Caller-owned device buffers: d_macro_index int64[n] (policy calls per env), d_slab float[n][92] + d_emit_flag
+ * uint8[n] (records emitted by the latest tick, dense by environment), d_ring float[ring_capacity][92] (all
+ * records, slot = running count % capacity), d_counters int64[16]. */
+int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
+                        int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
+                        int64_t *d_counters, mopa_rollout **out);
+void mopa_rollout_destroy(mopa_rollout *r);
+/* wait_rrt != 0: block until the RRT batch in flight (if any) is done, then finalise it. */
+int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
+/* d_actions: device float[n][7], the policy's action for every environment. */
+int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
+int mopa_rollout_busy(mopa_rollout *r);
+/* Kernels of this library launched so far through the handle. */
+int64_t mopa_rollout_launches(mopa_rollout *r);
+/* Mean device time (ms) of the env-step kernel over the latest n_last ticks (synchronises the device). */
+int mopa_rollout_env_ms(mopa_rollout *r, int32_t n_last, double *out_ms);
+
 #ifdef __cplusplus
 }
 #endif

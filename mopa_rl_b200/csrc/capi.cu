@@ -12,7 +12,7 @@
 namespace mopa {
 void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored, double threshold, HostScene &out);
 cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
-                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream);
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n = nullptr, int d_n_mult = 1);
 }  // namespace mopa
 
 static thread_local std::string g_err;

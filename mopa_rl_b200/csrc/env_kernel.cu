@@ -16,23 +16,8 @@
 #include "dyn.cuh"
 #include "contact.cuh"
 
-namespace mopa {
-struct DynDev;
-cudaError_t upload_env_model(int slot, const DynDev &h_model);
-cudaError_t env_tune_set(int prof, int sync_mask);
-cudaError_t env_prof_read(unsigned long long *out);
-cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
-                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
-                            const int32_t *ids, cudaStream_t stream);
-}
+#include "env_state.h"
 
-struct mopa_env {
-    int device = 0;
-    int model_slot = 0;          // slot of this scene in the warp kernel's constant memory
-    mopa::DynDev *d_model = nullptr;
-    mopa::DynDev h_model;
-    mopa_sawyer_task task;
-};
 
 namespace mopa {
 

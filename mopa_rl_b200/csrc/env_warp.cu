@@ -951,7 +951,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     const DynDev &m = c_models[model_slot];
     const int t = blockIdx.x * ENV_WARPS + warp;
     const int e = t < n ? (ids ? ids[t] : t) : 0;
-    const bool live = t < n && (forward_only || !mask || mask[e]);
+    const bool live = t < n && (!mask || mask[e]);
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (!forward_only) {
             int dummy = 0;

@@ -256,8 +256,9 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
             const float *__restrict__ goal, int row_stride, const unsigned long long *__restrict__ keys, int n, int max_iter,
             float *__restrict__ tree_x, int *__restrict__ tree_parent, int max_nodes, float *__restrict__ path,
             int *__restrict__ node_ids, int max_path, int *__restrict__ path_len, int *__restrict__ status_out,
-            int *__restrict__ iters_out, int *__restrict__ nodes_out) {
+            int *__restrict__ iters_out, int *__restrict__ nodes_out, const int *__restrict__ d_n) {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (d_n) { const int m = *d_n; if (m < n) n = m; if (n <= 0) return; }   // problem count produced on the device
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < blob_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(blob_g)[i];
     __syncthreads();
@@ -416,7 +417,7 @@ static cudaError_t ensure_trees(mopa_planner *p, size_t n, int max_nodes) {
 
 cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_goal, int row_stride, const unsigned long long *d_keys,
                         int n, int max_iter, float *d_path, int *d_node_ids, int max_path, int *d_path_len, int *d_status,
-                        int *d_iters, int *d_nodes, cudaStream_t stream) {
+                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n) {
     if (n <= 0) return cudaSuccess;
     cudaError_t e = ensure_trees(p, (size_t)n, p->max_nodes);
     if (e != cudaSuccess) return e;
@@ -444,7 +445,7 @@ cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_go
     if (grid > max_grid) grid = max_grid;
     plan_kernel<<<grid, PLAN_WARPS * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
                                                         b->tree_x, b->tree_parent, b->max_nodes, d_path, d_node_ids, max_path,
-                                                        d_path_len, d_status, d_iters, d_nodes);
+                                                        d_path_len, d_status, d_iters, d_nodes, d_n);
     return cudaGetLastError();
 }
 

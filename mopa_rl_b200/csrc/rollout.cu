@@ -1,0 +1,666 @@
+// Vectorised MoPA experience collection, device resident: the batched replacement of
+// MoPARolloutRunner.run (rl/mopa_rollouts.py:22-399, train branch) and of the planner glue it calls in
+// SACAgent (rl/sac_agent.py:145-318: is_planner_ac, convert2planner_displacement, clip_qpos,
+// simple_interpolate, plan) and PlannerAgent / SamplingBasedPlanner.plan (re-basing, densification).
+//
+// One tick = one env.step for every environment.  An environment whose macro action is finished
+//   emits its SMDP transition record (ob 40, ac 8, rew, done, intra_steps, env id, ob_next 40),
+//   is reset when its episode ended (counter-based draws keyed by env id and episode number),
+//   takes the next policy action and either executes it directly (|a| <= omega) or turns it into a plan:
+//   displacement map -> target clip -> invalid-target back-off -> straight-line interpolation ->
+//   RRT-Connect (asynchronous, on the planner stream; the environment waits) -> densification.
+// Every step is a kernel over all environments (or over a compact work list built with atomics); the
+// row counts of the state-validity and RRT launches stay on the device, so a tick needs no host
+// round trip.  The policy is the only part evaluated outside (between mopa_rollout_pre and _step).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "../../include/mopa_b200.h"
+#include "env_state.h"
+#include "planner_state.h"
+
+void mopa_set_error(const std::string &s);
+
+namespace mopa {
+cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n = nullptr, int d_n_mult = 1);
+
+constexpr int RO_JMAX = 16;     // interpolation points checked per straight-line plan
+constexpr int RO_NQ = 40;       // qpos capacity (same as the env kernel)
+enum { C_MP = 0, C_RL, C_INTERP, C_MP_FAIL, C_APPROX, C_INVALID, C_DENSIFY_FALLBACK, C_EPISODES, C_SUCCESS, C_MP_PATH_LEN,
+       C_INTERP_PATH_LEN, C_ENV_STEPS, C_TRANSITIONS, C_RRT_DROPPED, C_RRT_PROBLEMS, C_WAITING, C_COUNT = 16 };
+
+struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being filled / in flight)
+    int *cnt;                    // problems queued (may exceed the capacity: clamp)
+    int *env;                    // [cap] environment row of each problem
+    float *start32, *goal32;     // [cap][row]
+    double *start64;             // [cap][nq]  clipped current state (re-basing, passive dims of densified states)
+    unsigned long long *keys;    // [cap]
+    float *path;                 // [cap][max_path][row]
+    int *ids, *plen, *status;    // [cap][max_path], [cap], [cap]
+    // densification
+    float *dens32;               // [cap][max_path - 1][kmax][row]
+    uint32_t *dens_res;          // [cap][max_path - 1][kmax]
+    int *nst;                    // [cap][max_path - 1]
+    int *ok;                     // [cap]
+};
+
+struct RoDev {   // everything the kernels need, passed by value
+    int n, nq, row, max_traj, max_path, kmax, rrt_cap, num_trials, invalid_target_handling, interpolation;
+    double omega, action_range, ac_scale, discount, step_size, joint_margin, range;
+    unsigned long long seed_env;
+    long long env_id_offset;
+    double jlo[7], jhi[7], init_qpos[7];
+    int arm_qadr[7], target_qadr[2];
+    const double *qpos0;         // [nq]
+    // per environment
+    double *traj;                // [n][max_traj][7]
+    int *traj_len, *traj_pos, *executed;
+    unsigned char *kind, *pending, *macro_done, *need, *reset_flag, *step_mode, *step_mask;
+    float *prev_ob, *ac, *step_action;   // [n][40], [n][8], [n][8]
+    double *meta_rew;
+    long long *plan_count, *episode_idx;
+    long long *macro_index;      // caller-owned [n]
+    float *slab;                 // caller-owned [n][92]  records emitted by this tick, dense by environment
+    unsigned char *emit_flag;    // caller-owned [n]
+    long long *counters;         // caller-owned [C_COUNT]
+    float *ring;                 // caller-owned [ring_cap][92]  every record ever emitted (slot = running count % capacity)
+    long long ring_cap;
+    // planning work lists of the current tick
+    int *cnt_plan, *cnt_back;    // device counters
+    int *plan_env;               // [n]
+    double *tgt64, *c64;         // [n][nq]
+    float *q32a;                 // [n][row]          targets
+    uint32_t *res_a;             // [n]
+    int *back_of_plan;           // [n] back-off slot or -1
+    float *q32b;                 // [n][num_trials][row]   back-off candidates (compact by back-off slot)
+    uint32_t *res_b;
+    float *q32c;                 // [n][RO_JMAX][row] interpolation points
+    uint32_t *res_c;
+    int *nstep;                  // [n]
+    unsigned char *plan_ok;      // [n]
+};
+
+__device__ __forceinline__ unsigned long long ro_mix(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+// mopa_rl_b200/rng.py: uniform01 / normal (counter-based, keyed by seed, stream, counter, dim)
+__device__ __forceinline__ double ro_uniform(unsigned long long seed, unsigned long long stream, unsigned long long counter, unsigned long long dim) {
+    unsigned long long x = ro_mix(seed ^ (stream * 0x9E3779B97F4A7C15ULL));
+    x = ro_mix(x + ((counter << 8) | dim) * 0xD1342543DE82EF95ULL);
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double ro_normal(unsigned long long seed, unsigned long long stream, unsigned long long counter, unsigned long long dim) {
+    const double u1 = ro_uniform(seed, stream, counter, dim * 2), u2 = ro_uniform(seed, stream, counter, dim * 2 + 1);
+    return sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2);
+}
+__device__ __forceinline__ void ro_count(long long *c, int which, long long v = 1) { atomicAdd((unsigned long long *)(c + which), (unsigned long long)v); }
+
+// ---- 1. finished macro actions: transition records, episode resets (SawyerPushObstacleEnv._reset, :36-51)
+__global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    const bool need = S.traj_pos[e] >= S.traj_len[e];
+    unsigned char emit = 0, reset = 0;
+    if (need) {
+        if (S.pending[e]) {
+            float *rec = S.slab + (size_t)e * 92;
+            for (int k = 0; k < 40; k++) rec[k] = S.prev_ob[(size_t)e * 40 + k];
+            for (int k = 0; k < 8; k++) rec[40 + k] = S.ac[(size_t)e * 8 + k];
+            rec[48] = (float)S.meta_rew[e];
+            rec[49] = S.macro_done[e] ? 1.0f : 0.0f;
+            const int ex = S.executed[e] - 1;
+            rec[50] = (float)(ex > 0 ? ex : 0);
+            rec[51] = (float)(S.env_id_offset + e);
+            for (int k = 0; k < 40; k++) rec[52 + k] = B.obs[(size_t)e * 40 + k];
+            emit = 1;
+            const unsigned long long slot = atomicAdd((unsigned long long *)(S.counters + C_TRANSITIONS), 1ULL) % (unsigned long long)S.ring_cap;
+            float *dst = S.ring + slot * 92;
+            for (int k = 0; k < 92; k++) dst[k] = rec[k];
+            if (S.macro_done[e]) {
+                ro_count(S.counters, C_EPISODES);
+                if (B.success[e]) ro_count(S.counters, C_SUCCESS);
+                const unsigned long long gid = (unsigned long long)(S.env_id_offset + e), ep = (unsigned long long)S.episode_idx[e];
+                double *q = B.qpos + (size_t)e * S.nq;
+                for (int k = 0; k < S.nq; k++) q[k] = S.qpos0[k];
+                for (int k = 0; k < 7; k++) q[S.arm_qadr[k]] = S.init_qpos[k] + 0.02 * ro_normal(S.seed_env, gid, ep, (unsigned long long)k);
+                for (int k = 0; k < 2; k++) q[S.target_qadr[k]] += -0.01 + 0.02 * ro_uniform(S.seed_env, gid, ep, 100ULL + k);
+                for (int k = 0; k < nv; k++) B.qvel[(size_t)e * nv + k] = 0.0;
+                S.episode_idx[e] += 1;
+                B.ep_len[e] = 0; B.ep_rew[e] = 0.0; B.done[e] = 0; B.success[e] = 0;
+                reset = 1;
+            }
+        }
+        B.has_prev[e] = 0;   // env._reset_prev_state()
+    }
+    S.need[e] = need ? 1 : 0;
+    S.emit_flag[e] = emit;
+    S.reset_flag[e] = reset;
+    if (e == 0) { *S.cnt_plan = 0; *S.cnt_back = 0; S.counters[C_WAITING] = 0; }
+}
+
+// ---- 2. new macro actions: direct action, or planner target (SACAgent.convert2planner_displacement + target clip)
+__global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__restrict__ actions) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n || !S.need[e]) return;
+    float a32[7];
+    bool is_mp = false;
+    for (int k = 0; k < 7; k++) {
+        float a = actions[(size_t)e * 7 + k];
+        a = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
+        a32[k] = a;
+        S.ac[(size_t)e * 8 + k] = a;
+        if (fabs((double)a) > S.omega) is_mp = true;
+    }
+    S.macro_index[e] += 1;
+    for (int k = 0; k < 40; k++) S.prev_ob[(size_t)e * 40 + k] = B.obs[(size_t)e * 40 + k];
+    S.meta_rew[e] = 0.0; S.executed[e] = 0; S.macro_done[e] = 0; S.pending[e] = 1;
+    S.traj_len[e] = 1; S.traj_pos[e] = 0;
+    if (!is_mp) { S.kind[e] = 0; ro_count(S.counters, C_RL); return; }
+    S.kind[e] = 2;   // failure unless proven otherwise
+    const int slot = atomicAdd(S.cnt_plan, 1);
+    S.plan_env[slot] = e;
+    const double *curr = B.qpos + (size_t)e * S.nq;
+    double *tg = S.tgt64 + (size_t)slot * S.nq;
+    float *q32 = S.q32a + (size_t)slot * S.row;
+    for (int k = 0; k < S.nq; k++) tg[k] = curr[k];
+    const double w = S.omega;
+    for (int k = 0; k < 7; k++) {
+        const double a = (double)a32[k], aa = fabs(a);
+        const double disp = aa < w ? a / (w / S.ac_scale)
+                                   : (a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0)) * (S.ac_scale + (S.action_range - S.ac_scale) * ((aa - w) / (1 - w)));
+        double t = curr[S.arm_qadr[k]] + disp;
+        t = t < S.jlo[k] ? S.jlo[k] : t;
+        t = t > S.jhi[k] ? S.jhi[k] : t;
+        tg[S.arm_qadr[k]] = t;
+    }
+    for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)tg[k] : 0.0f;
+}
+
+// ---- 3. invalid targets: candidates of the back-off loop (rl/mopa_rollouts.py:119-143)
+__device__ __forceinline__ void ro_backoff_step(const RoDev &S, const double *c, double *t) {
+    double d[RO_NQ], n2 = 0;
+    for (int k = 0; k < S.nq; k++) { d[k] = c[k] - t[k]; n2 += d[k] * d[k]; }
+    const double nrm = sqrt(n2);
+    for (int k = 0; k < S.nq; k++) t[k] = t[k] + S.step_size * d[k] / nrm;
+}
+__global__ void ro_backoff_kernel(RoDev S, mopa_env_buffers B) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *S.cnt_plan) return;
+    S.back_of_plan[slot] = -1;
+    if ((S.res_a[slot] & 1u) || !S.invalid_target_handling) return;
+    const int bs = atomicAdd(S.cnt_back, 1);
+    S.back_of_plan[slot] = bs;
+    const int e = S.plan_env[slot];
+    const double *c = B.qpos + (size_t)e * S.nq;
+    double t[RO_NQ];
+    for (int k = 0; k < S.nq; k++) t[k] = S.tgt64[(size_t)slot * S.nq + k];
+    for (int trial = 0; trial < S.num_trials; trial++) {
+        ro_backoff_step(S, c, t);
+        float *q32 = S.q32b + ((size_t)bs * S.num_trials + trial) * S.row;
+        for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)t[k] : 0.0f;
+    }
+}
+
+// ---- 4. target choice, clip_qpos, interpolation points (SACAgent.clip_qpos / simple_interpolate, :237-298)
+__global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *S.cnt_plan) return;
+    const int e = S.plan_env[slot];
+    const double *curr = B.qpos + (size_t)e * S.nq;
+    double *tg = S.tgt64 + (size_t)slot * S.nq, *c = S.c64 + (size_t)slot * S.nq;
+    bool ok = (S.res_a[slot] & 1u) != 0;
+    const int bs = S.back_of_plan[slot];
+    if (!ok && bs >= 0) {
+        int first = -1;
+        for (int trial = 0; trial < S.num_trials; trial++)
+            if (S.res_b[(size_t)bs * S.num_trials + trial] & 1u) { first = trial; break; }
+        const int upto = first >= 0 ? first + 1 : S.num_trials;   // no valid candidate: the last one (and the plan fails)
+        for (int trial = 0; trial < upto; trial++) ro_backoff_step(S, curr, tg);
+        ok = first >= 0;
+    }
+    S.plan_ok[slot] = ok ? 1 : 0;
+    S.nstep[slot] = 0;
+    if (!ok) { ro_count(S.counters, C_INVALID); ro_count(S.counters, C_MP_FAIL); return; }
+    for (int k = 0; k < S.nq; k++) c[k] = curr[k];
+    bool out = false;
+    for (int k = 0; k < 7; k++) { const double x = curr[S.arm_qadr[k]]; if (x < S.jlo[k] || x > S.jhi[k]) out = true; }
+    if (out)
+        for (int k = 0; k < 7; k++) {
+            double x = curr[S.arm_qadr[k]];
+            const double lo = S.jlo[k] + S.joint_margin, hi = S.jhi[k] - S.joint_margin;
+            x = x < lo ? lo : x;
+            x = x > hi ? hi : x;
+            c[S.arm_qadr[k]] = x;
+        }
+    const double lim = S.ac_scale * 0.8;
+    double diff[7], sf = 1.0;
+    for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; }
+    int nstep = (int)floor(sf);
+    if (nstep > RO_JMAX) nstep = RO_JMAX;
+    S.nstep[slot] = nstep;
+    double run[7];
+    for (int k = 0; k < 7; k++) run[k] = c[S.arm_qadr[k]];
+    for (int j = 0; j < RO_JMAX; j++) {
+        float *q32 = S.q32c + ((size_t)slot * RO_JMAX + j) * S.row;
+        for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)c[k] : 0.0f;
+        if (j < nstep) {
+            for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; q32[S.arm_qadr[k]] = (float)run[k]; }
+        }
+    }
+}
+
+// ---- 5. straight line free -> trajectory; blocked -> RRT-Connect queue (SACAgent.plan, :198-233)
+__global__ void ro_interp_finish_kernel(RoDev S, RrtBatch Q) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *S.cnt_plan || !S.plan_ok[slot]) return;
+    const int e = S.plan_env[slot], nstep = S.nstep[slot];
+    const double *tg = S.tgt64 + (size_t)slot * S.nq, *c = S.c64 + (size_t)slot * S.nq;
+    bool straight = true;
+    for (int j = 0; j < nstep; j++) if (!(S.res_c[(size_t)slot * RO_JMAX + j] & 1u)) straight = false;
+    if (straight) {
+        const double lim = S.ac_scale * 0.8;
+        double diff[7], sf = 1.0, run[7];
+        for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
+        double *tr = S.traj + (size_t)e * S.max_traj * 7;
+        for (int j = 0; j < nstep; j++)
+            for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[j * 7 + k] = run[k]; }
+        for (int k = 0; k < 7; k++) tr[nstep * 7 + k] = tg[S.arm_qadr[k]];
+        S.kind[e] = 1; S.traj_len[e] = nstep + 1; S.traj_pos[e] = 0;
+        ro_count(S.counters, C_INTERP);
+        ro_count(S.counters, C_INTERP_PATH_LEN, nstep + 1);
+        return;
+    }
+    const int r = atomicAdd(Q.cnt, 1);
+    if (r >= S.rrt_cap) { ro_count(S.counters, C_MP_FAIL); ro_count(S.counters, C_RRT_DROPPED); return; }   // kind stays 2
+    Q.env[r] = e;
+    for (int k = 0; k < S.row; k++) {
+        Q.start32[(size_t)r * S.row + k] = k < S.nq ? (float)c[k] : 0.0f;
+        Q.goal32[(size_t)r * S.row + k] = k < S.nq ? (float)tg[k] : 0.0f;
+    }
+    for (int k = 0; k < S.nq; k++) Q.start64[(size_t)r * S.nq + k] = c[k];
+    Q.keys[r] = ((unsigned long long)(S.env_id_offset + e) << 32) + (unsigned long long)S.plan_count[e];   // invariant to batching / GPU count
+    S.plan_count[e] += 1;
+    S.kind[e] = 3; S.traj_len[e] = 1; S.traj_pos[e] = 0;   // waits for the plan
+    ro_count(S.counters, C_RRT_PROBLEMS);
+}
+
+// ---- 6. finished RRT batch: re-base on the start (SamplingBasedPlanner.plan), densify (SACAgent.plan :216-233).
+// One warp per problem; lanes stride the hops.
+__global__ void ro_rrt_densify_kernel(RoDev S, RrtBatch Q) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int cnt = min(*Q.cnt, S.rrt_cap);
+    if (r >= cnt) return;
+    const int e = Q.env[r];
+    const int H = S.max_path - 1;
+    if (Q.status[r] != 0) {
+        if (lane == 0) { Q.ok[r] = 0; S.kind[e] = 2; S.traj_len[e] = 1; S.traj_pos[e] = 0; ro_count(S.counters, C_APPROX); ro_count(S.counters, C_MP_FAIL); }
+        return;
+    }
+    if (lane == 0) Q.ok[r] = 1;
+    const int L = Q.plen[r];
+    const float *path = Q.path + (size_t)r * S.max_path * S.row;
+    const double *st = Q.start64 + (size_t)r * S.nq;
+    const double lim = S.ac_scale * 0.8;
+    for (int i = lane; i < H; i += 32) {
+        int nst = 0;
+        float *rows = Q.dens32 + ((size_t)r * H + i) * S.kmax * S.row;
+        if (i < L - 1) {
+            double hs[7], diff[7], sf = 1.0;
+            bool need = false;
+            for (int k = 0; k < 7; k++) {
+                const int a = S.arm_qadr[k];
+                const double p0 = (double)path[a];
+                const double he = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
+                hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
+                diff[k] = he - hs[k];
+                if (fabs(diff[k]) > S.ac_scale) need = true;
+                const double s = fabs(diff[k]) / lim;
+                if (s > sf) sf = s;
+            }
+            if (need && S.interpolation) { nst = (int)floor(sf); if (nst > S.kmax) nst = S.kmax; }
+            double run[7];
+            for (int k = 0; k < 7; k++) run[k] = hs[k];
+            for (int j = 0; j < S.kmax; j++) {
+                float *q32 = rows + (size_t)j * S.row;
+                for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)st[k] : 0.0f;
+                if (j < nst)
+                    for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; q32[S.arm_qadr[k]] = (float)run[k]; }
+            }
+        } else {
+            for (int j = 0; j < S.kmax; j++)
+                for (int k = 0; k < S.row; k++) rows[(size_t)j * S.row + k] = k < S.nq ? (float)st[k] : 0.0f;
+        }
+        Q.nst[(size_t)r * H + i] = nst;
+    }
+}
+__global__ void ro_rrt_finish_kernel(RoDev S, RrtBatch Q) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int cnt = min(*Q.cnt, S.rrt_cap);
+    if (r >= cnt || !Q.ok[r]) return;
+    const int e = Q.env[r], H = S.max_path - 1, L = Q.plen[r];
+    const float *path = Q.path + (size_t)r * S.max_path * S.row;
+    const double *st = Q.start64 + (size_t)r * S.nq;
+    const double lim = S.ac_scale * 0.8;
+    // pass 1: hops whose interior states are invalid keep only their end point; total length
+    int total = 0, fallback = 0;
+    for (int base = 0; base < H; base += 32) {
+        const int i = base + lane;
+        int c = 0;
+        if (i < L - 1) {
+            int nst = Q.nst[(size_t)r * H + i];
+            bool bad = false;
+            for (int j = 0; j < nst; j++) if (!(Q.dens_res[((size_t)r * H + i) * S.kmax + j] & 1u)) bad = true;
+            if (bad) { nst = 0; Q.nst[(size_t)r * H + i] = 0; fallback++; }
+            c = nst + 1;
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        total += c;
+    }
+    for (int o = 16; o > 0; o >>= 1) fallback += __shfl_xor_sync(0xffffffffu, fallback, o);
+    __syncwarp();
+    if (lane == 0 && fallback) ro_count(S.counters, C_DENSIFY_FALLBACK, fallback);
+    if (total > S.max_traj) {
+        if (lane == 0) { S.kind[e] = 2; S.traj_len[e] = 1; S.traj_pos[e] = 0; ro_count(S.counters, C_MP_FAIL); ro_count(S.counters, C_MP); }
+        return;
+    }
+    // pass 2: write the trajectory (offsets by warp scan over chunks of 32 hops)
+    double *tr = S.traj + (size_t)e * S.max_traj * 7;
+    int carry = 0;
+    for (int base = 0; base < H; base += 32) {
+        const int i = base + lane;
+        const bool live = i < L - 1;
+        const int nst = live ? Q.nst[(size_t)r * H + i] : 0;
+        const int c = live ? nst + 1 : 0;
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int off = carry + incl - c;
+        if (live) {
+            double hs[7], diff[7], sf = 1.0, he[7];
+            for (int k = 0; k < 7; k++) {
+                const int a = S.arm_qadr[k];
+                const double p0 = (double)path[a];
+                he[k] = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
+                hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
+                diff[k] = he[k] - hs[k];
+                const double s = fabs(diff[k]) / lim;
+                if (s > sf) sf = s;
+            }
+            double run[7];
+            for (int k = 0; k < 7; k++) run[k] = hs[k];
+            for (int j = 0; j < nst; j++)
+                for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[(size_t)(off + j) * 7 + k] = run[k]; }
+            for (int k = 0; k < 7; k++) tr[(size_t)(off + nst) * 7 + k] = he[k];
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        S.kind[e] = 1; S.traj_len[e] = total; S.traj_pos[e] = 0;
+        ro_count(S.counters, C_MP);
+        ro_count(S.counters, C_MP_PATH_LEN, total);
+    }
+}
+
+// ---- 7. stage the action of every environment (direct: ac / omega, plan: env.form_action(next_qpos))
+__global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n) return;
+    const int kind = S.kind[e];
+    S.step_mode[e] = (unsigned char)kind;
+    S.step_mask[e] = kind != 3;
+    if (kind == 3) ro_count(S.counters, C_WAITING);   // environments waiting for their RRT plan in this tick
+    float *sa = S.step_action + (size_t)e * 8;
+    if (kind == 0) {
+        for (int k = 0; k < 7; k++) sa[k] = (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
+    } else if (kind == 1) {
+        int pos = S.traj_pos[e];
+        if (pos > S.max_traj - 1) pos = S.max_traj - 1;
+        const double *nx = S.traj + ((size_t)e * S.max_traj + pos) * 7;
+        for (int k = 0; k < 7; k++) sa[k] = (float)(nx[k] - B.qpos[(size_t)e * S.nq + S.arm_qadr[k]]);
+    }
+}
+// ---- 8. after env.step: discounted macro reward, counters, termination
+__global__ void ro_post_kernel(RoDev S, mopa_env_buffers B) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool stepping = e < S.n && S.step_mask[e];
+    if (stepping) {
+        const int pos = S.traj_pos[e];
+        const double disc = S.kind[e] == 1 ? pow(S.discount, (double)pos) : 1.0;
+        S.meta_rew[e] += disc * B.reward[e];
+        S.executed[e] += 1;
+        S.traj_pos[e] = pos + 1;
+        if (B.done[e]) { S.macro_done[e] = 1; S.traj_len[e] = pos + 1; }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, stepping);
+    if ((threadIdx.x & 31) == 0 && m) ro_count(S.counters, C_ENV_STEPS, __popc(m));
+}
+
+}  // namespace mopa
+
+using namespace mopa;
+
+struct mopa_rollout {
+    mopa_env *env = nullptr;
+    mopa_planner *planner = nullptr;
+    mopa_env_buffers buf;
+    RoDev S;
+    RrtBatch batch[2];
+    int fill = 0;                // batch being filled; the other one may be in flight
+    bool inflight = false;
+    int max_iter = 1000;
+    cudaStream_t plan_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    std::vector<void *> allocs;
+    long long launches = 0;      // kernels of this library launched so far
+    static constexpr int EV_RING = 256;
+    cudaEvent_t ev_env0[EV_RING] = {}, ev_env1[EV_RING] = {};   // around the env-step kernel of the latest ticks
+    long long ticks = 0;
+};
+
+#define RO_TRY(x)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) { mopa_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return MOPA_ERR_CUDA; } \
+    } while (0)
+
+template <class T>
+static cudaError_t ro_alloc(mopa_rollout *r, T **p, size_t count) {
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    r->allocs.push_back((void *)*p);
+    return cudaMemset(*p, 0, count * sizeof(T));
+}
+
+extern "C" {
+
+int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
+                        int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
+                        int64_t *d_counters, mopa_rollout **out) {
+    if (!env || !planner || !buf || !cfg || !d_macro_index || !d_slab || !d_emit_flag || !d_ring || ring_capacity <= 0 || !d_counters || !out) {
+        mopa_set_error("mopa_rollout_create: bad argument");
+        return MOPA_ERR_ARG;
+    }
+    *out = nullptr;
+    const DynDev &m = env->h_model;
+    if (m.nq > RO_NQ || cfg->n_envs <= 0 || cfg->max_path < 2 || cfg->rrt_capacity <= 0 || planner->scene.hdr.nq != m.nq) {
+        mopa_set_error("mopa_rollout_create: configuration outside the compiled limits");
+        return MOPA_ERR_ARG;
+    }
+    mopa_rollout *r = new mopa_rollout();
+    r->env = env; r->planner = planner; r->buf = *buf; r->max_iter = cfg->max_iter;
+    RoDev &S = r->S;
+    memset(&S, 0, sizeof(S));
+    const int n = cfg->n_envs, nq = m.nq, row = planner->scene.hdr.nq4 * 4;
+    const double lim = cfg->ac_scale * 0.8;
+    S.n = n; S.nq = nq; S.row = row; S.max_traj = cfg->max_traj; S.max_path = cfg->max_path; S.kmax = (int)(cfg->range / lim) + 1;
+    S.rrt_cap = cfg->rrt_capacity; S.num_trials = cfg->num_trials; S.invalid_target_handling = cfg->invalid_target_handling;
+    S.interpolation = cfg->interpolation;
+    S.omega = cfg->omega; S.action_range = cfg->action_range; S.ac_scale = cfg->ac_scale; S.discount = cfg->discount;
+    S.step_size = cfg->step_size; S.joint_margin = cfg->joint_margin; S.range = cfg->range;
+    S.seed_env = cfg->seed_env; S.env_id_offset = cfg->env_id_offset;
+    for (int k = 0; k < 7; k++) { S.jlo[k] = cfg->jnt_lo[k]; S.jhi[k] = cfg->jnt_hi[k]; S.init_qpos[k] = cfg->init_qpos[k]; S.arm_qadr[k] = env->task.arm_qadr[k]; }
+    for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
+    S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
+    S.ring = d_ring; S.ring_cap = ring_capacity;
+    cudaError_t e = cudaSetDevice(env->device);
+#define A(ptr, count) if (e == cudaSuccess) e = ro_alloc(r, &ptr, (size_t)(count))
+    double *qpos0 = nullptr;
+    A(qpos0, nq);
+    if (e == cudaSuccess) e = cudaMemcpy(qpos0, cfg->qpos0, sizeof(double) * nq, cudaMemcpyHostToDevice);
+    S.qpos0 = qpos0;
+    A(S.traj, (size_t)n * S.max_traj * 7);
+    A(S.traj_len, n); A(S.traj_pos, n); A(S.executed, n);
+    A(S.kind, n); A(S.pending, n); A(S.macro_done, n); A(S.need, n); A(S.reset_flag, n); A(S.step_mode, n); A(S.step_mask, n);
+    A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
+    A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
+    A(S.cnt_plan, 1); A(S.cnt_back, 1);
+    A(S.plan_env, n); A(S.tgt64, (size_t)n * nq); A(S.c64, (size_t)n * nq); A(S.q32a, (size_t)n * row); A(S.res_a, n);
+    A(S.back_of_plan, n); A(S.q32b, (size_t)n * S.num_trials * row); A(S.res_b, (size_t)n * S.num_trials);
+    A(S.q32c, (size_t)n * RO_JMAX * row); A(S.res_c, (size_t)n * RO_JMAX); A(S.nstep, n); A(S.plan_ok, n);
+    const size_t cap = S.rrt_cap, H = S.max_path - 1;
+    for (int b = 0; b < 2; b++) {
+        RrtBatch &Q = r->batch[b];
+        A(Q.cnt, 1); A(Q.env, cap); A(Q.start32, cap * row); A(Q.goal32, cap * row); A(Q.start64, cap * nq); A(Q.keys, cap);
+        A(Q.path, cap * S.max_path * row); A(Q.ids, cap * S.max_path); A(Q.plen, cap); A(Q.status, cap);
+        A(Q.dens32, cap * H * S.kmax * row); A(Q.dens_res, cap * H * S.kmax); A(Q.nst, cap * H); A(Q.ok, cap);
+    }
+#undef A
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->plan_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming);
+    for (int k = 0; k < mopa_rollout::EV_RING && e == cudaSuccess; k++) { e = cudaEventCreate(&r->ev_env0[k]); if (e == cudaSuccess) e = cudaEventCreate(&r->ev_env1[k]); }
+    // episode counters start at 1: episode 0 was drawn by the initial reset of the environments
+    if (e == cudaSuccess) {
+        std::vector<long long> one(n, 1);
+        e = cudaMemcpy(S.episode_idx, one.data(), sizeof(long long) * n, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        mopa_set_error(std::string("mopa_rollout_create: ") + cudaGetErrorString(e));
+        mopa_rollout_destroy(r);
+        return MOPA_ERR_CUDA;
+    }
+    *out = r;
+    return MOPA_OK;
+}
+
+void mopa_rollout_destroy(mopa_rollout *r) {
+    if (!r) return;
+    cudaSetDevice(r->env->device);
+    cudaDeviceSynchronize();
+    for (void *p : r->allocs) cudaFree(p);
+    if (r->plan_stream) cudaStreamDestroy(r->plan_stream);
+    if (r->ev_ready) cudaEventDestroy(r->ev_ready);
+    if (r->ev_done) cudaEventDestroy(r->ev_done);
+    for (int k = 0; k < mopa_rollout::EV_RING; k++) { if (r->ev_env0[k]) cudaEventDestroy(r->ev_env0[k]); if (r->ev_env1[k]) cudaEventDestroy(r->ev_env1[k]); }
+    delete r;
+}
+
+static int ro_finalize_rrt(mopa_rollout *r, cudaStream_t st) {
+    RoDev &S = r->S;
+    RrtBatch &Q = r->batch[1 - r->fill];
+    const int warps_blocks = (S.rrt_cap * 32 + 127) / 128, H = S.max_path - 1;
+    RO_TRY(cudaStreamWaitEvent(st, r->ev_done, 0));
+    ro_rrt_densify_kernel<<<warps_blocks, 128, 0, st>>>(S, Q);
+    RO_TRY(launch_is_valid(r->planner->d_blob, r->planner->scene.hdr, Q.dens32, S.row, S.rrt_cap * H * S.kmax, Q.dens_res, 0,
+                           r->planner->sm_count, st, Q.cnt, H * S.kmax));
+    ro_rrt_finish_kernel<<<warps_blocks, 128, 0, st>>>(S, Q);
+    RO_TRY(cudaGetLastError());
+    r->inflight = false;
+    r->launches += 3;
+    return MOPA_OK;
+}
+
+/* First half of a tick: finished RRT batch -> trajectories; finished macro actions -> transition records
+ * (slab / emit_flag) and episode resets (+ sim.forward of the reset environments). */
+int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
+    if (!r) return MOPA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    RoDev &S = r->S;
+    RO_TRY(cudaSetDevice(r->env->device));
+    if (r->inflight) {
+        cudaError_t q = wait_rrt ? cudaEventSynchronize(r->ev_done) : cudaEventQuery(r->ev_done);
+        if (q == cudaSuccess) { int rc = ro_finalize_rrt(r, st); if (rc) return rc; }
+        else if (q != cudaErrorNotReady) RO_TRY(q);
+    }
+    const int blocks = (S.n + 127) / 128;
+    ro_pre_kernel<<<blocks, 128, 0, st>>>(S, r->buf, r->env->h_model.nv);
+    RO_TRY(cudaGetLastError());
+    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->task, r->buf, nullptr, 0, nullptr,
+                           S.reset_flag, S.n, 1, nullptr, st));
+    r->launches += 2;
+    return MOPA_OK;
+}
+
+/* Second half: d_actions [n][7] = the policy's output for every environment (used where a new macro
+ * action starts).  Planning glue, RRT launch, env.step for every non-waiting environment, bookkeeping. */
+int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
+    if (!r || !d_actions) return MOPA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    RoDev &S = r->S;
+    mopa_planner *p = r->planner;
+    RO_TRY(cudaSetDevice(r->env->device));
+    const int blocks = (S.n + 127) / 128;
+    RrtBatch &Q = r->batch[r->fill];
+    ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, d_actions);
+    RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32a, S.row, S.n, S.res_a, 0, p->sm_count, st, S.cnt_plan, 1));
+    ro_backoff_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32b, S.row, S.n * S.num_trials, S.res_b, 0, p->sm_count, st, S.cnt_back, S.num_trials));
+    ro_interp_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32c, S.row, S.n * RO_JMAX, S.res_c, 0, p->sm_count, st, S.cnt_plan, RO_JMAX));
+    ro_interp_finish_kernel<<<blocks, 128, 0, st>>>(S, Q);
+    RO_TRY(cudaGetLastError());
+    if (!r->inflight) {
+        // hand the filled batch to the planner stream (it runs under the env-step kernels); start filling the other one
+        RO_TRY(cudaEventRecord(r->ev_ready, st));
+        RO_TRY(cudaStreamWaitEvent(r->plan_stream, r->ev_ready, 0));
+        RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
+                           r->plan_stream, Q.cnt));
+        RO_TRY(cudaEventRecord(r->ev_done, r->plan_stream));
+        r->inflight = true;
+        r->launches += 1;
+        r->fill = 1 - r->fill;
+        RO_TRY(cudaMemsetAsync(r->batch[r->fill].cnt, 0, sizeof(int), st));
+    }
+    ro_stage_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    RO_TRY(cudaGetLastError());
+    const int ev = (int)(r->ticks % mopa_rollout::EV_RING);
+    RO_TRY(cudaEventRecord(r->ev_env0[ev], st));
+    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->task, r->buf, S.step_action, 8, S.step_mode,
+                           S.step_mask, S.n, 0, nullptr, st));
+    RO_TRY(cudaEventRecord(r->ev_env1[ev], st));
+    ro_post_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    RO_TRY(cudaGetLastError());
+    r->launches += 10;   // begin, 3 x validity, back-off, interpolation, interpolation finish, stage, env step, post
+    r->ticks += 1;
+    return MOPA_OK;
+}
+
+/* 1 while an RRT batch is in flight or problems are queued behind it (host view; the queue length lives on the device). */
+int mopa_rollout_busy(mopa_rollout *r) { return r && r->inflight ? 1 : 0; }
+
+/* Kernels of this library launched so far by the handle. */
+int64_t mopa_rollout_launches(mopa_rollout *r) { return r ? r->launches : 0; }
+
+/* Mean device time (ms) of the env-step kernel over the latest n_last ticks (synchronises the device). */
+int mopa_rollout_env_ms(mopa_rollout *r, int32_t n_last, double *out_ms) {
+    if (!r || !out_ms || n_last <= 0) return MOPA_ERR_ARG;
+    RO_TRY(cudaSetDevice(r->env->device));
+    RO_TRY(cudaDeviceSynchronize());
+    long long have = r->ticks < mopa_rollout::EV_RING ? r->ticks : mopa_rollout::EV_RING;
+    if (n_last > have) n_last = (int32_t)have;
+    double sum = 0;
+    for (int k = 0; k < n_last; k++) {
+        const int ev = (int)((r->ticks - 1 - k) % mopa_rollout::EV_RING);
+        float ms = 0;
+        RO_TRY(cudaEventElapsedTime(&ms, r->ev_env0[ev], r->ev_env1[ev]));
+        sum += ms;
+    }
+    *out_ms = n_last ? sum / n_last : 0.0;
+    return MOPA_OK;
+}
+
+}  // extern "C"

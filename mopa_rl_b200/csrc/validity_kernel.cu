@@ -22,9 +22,14 @@ struct RowQ {
 template <int NQ, int QCAP>
 __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
                                                       const float *__restrict__ qpos, int row_stride, int n,
-                                                      uint32_t *__restrict__ out, int exact) {
+                                                      uint32_t *__restrict__ out, int exact, const int *__restrict__ d_n, int d_n_mult) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+    if (d_n) {   // row count produced on the device (no host round trip): n is the capacity
+        const long long m = (long long)(*d_n) * d_n_mult;
+        if (m < n) n = (int)m;
+        if (n <= 0) return;
+    }
     for (int i = tid; i < blob_bytes / 16; i += NQ) reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(blob_g)[i];
     __syncthreads();
     const SceneView S = view_scene(smem);
@@ -113,7 +118,7 @@ size_t validity_smem_bytes(const SceneHeader &H) {
 }
 
 cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
-                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream) {
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
     if (n <= 0) return cudaSuccess;
     static bool attr_set = false;
     size_t smem = validity_smem_bytes(H);
@@ -129,7 +134,7 @@ cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, c
     if (per_sm > 8) per_sm = 8;
     int grid = sm_count * per_sm;
     if (grid > ntile) grid = ntile;
-    kern<<<grid, VK_NQ, smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact);
+    kern<<<grid, VK_NQ, smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact, d_n, d_n_mult);
     return cudaGetLastError();
 }
 

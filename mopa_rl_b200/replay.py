@@ -66,7 +66,38 @@ class ReplicatedReplay:
         valid = torch.arange(kmax, device=self.device)[None, :] < counts[:, None]
         self._append(g[valid])   # rank-major order: identical on every rank
 
+    def exchange_slab(self, slab, flags):
+        """Fixed-shape variant for the native runner: ``slab`` [n, 92] holds this tick's records dense by
+        environment, ``flags`` [n] (uint8) marks the rows that are records.  No host round trip: the
+        all-gather moves whole slabs (NVLink makes the padding irrelevant) and the valid rows are
+        appended on the device, rank-major, identically on every rank."""
+        torch = self.torch
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            n = slab.shape[0]
+            g = torch.empty(world * n, TRANSITION_FLOATS, dtype=torch.float32, device=self.device)
+            f = torch.empty(world * n, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(g, slab.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(f, flags.contiguous(), group=self.group)
+            self.bytes_exchanged += world * n * (TRANSITION_FLOATS * 4 + 1)
+            slab, flags = g, f
+        if not hasattr(self, "_size_dev"):
+            self._size_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._ring1 = torch.zeros(self.capacity + 1, TRANSITION_FLOATS, dtype=torch.float32, device=self.device)  # last row: dump
+            self.ring = self._ring1[:self.capacity]
+        live = flags.bool()
+        pos = torch.cumsum(live.to(torch.int64), 0) - 1
+        idx = torch.where(live, (self._size_dev + pos) % self.capacity, torch.full_like(pos, self.capacity))
+        self._ring1.index_copy_(0, idx, slab)
+        self._size_dev += live.sum()
+
+    def device_size(self):
+        """Records stored through exchange_slab (reads the device counter)."""
+        return int(self._size_dev.item()) if hasattr(self, "_size_dev") else self.size
+
     def sample(self, batch_size, generator=None):
-        n = min(self.size, self.capacity)
+        n = min(self.device_size(), self.capacity)
         idx = self.torch.randint(0, n, (batch_size,), device=self.device, generator=generator)
         return self.ring[idx]

@@ -469,3 +469,135 @@ class VecMoPARolloutRunner:
             if self.rrt_inflight is not None:
                 self.rrt_inflight["done"].synchronize()
             self.tick()
+
+
+# ------------------------------------------------------------------------------------ native runner
+import ctypes as _C  # noqa: E402
+
+COUNTER_NAMES = ("mp", "rl", "interpolation", "mp_fail", "approximate", "invalid", "densify_fallback", "episodes", "success",
+                 "mp_path_len", "interpolation_path_len", "env_steps", "transitions", "rrt_dropped", "rrt_problems", "waiting")
+
+
+class _RolloutConfig(_C.Structure):
+    _fields_ = [(k, _C.c_int32) for k in ("n_envs", "max_iter", "max_path", "max_traj", "rrt_capacity", "num_trials",
+                                          "invalid_target_handling", "interpolation")] + \
+               [(k, _C.c_double) for k in ("omega", "action_range", "ac_scale", "discount", "step_size", "joint_margin", "range")] + \
+               [("seed_env", _C.c_uint64), ("env_id_offset", _C.c_int64), ("jnt_lo", _C.c_double * 7), ("jnt_hi", _C.c_double * 7),
+                ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p)]
+
+
+class NativeMoPARolloutRunner:
+    """Same collection loop as ``VecMoPARolloutRunner`` with every step of a tick as a CUDA kernel of
+    libmopa_b200 (csrc/rollout.cu): no host round trip inside a tick, the policy is evaluated once per
+    tick on the observations of ALL environments (its output is used where a macro action starts).
+
+    ``policy(obs [n,40] f32, env_gid [n] i64, macro_index [n] i64) -> [n,7]`` actions in [-1, 1].
+    """
+
+    def __init__(self, venv, config=None, policy=None, transition_capacity=1 << 20, rrt_capacity=1024):
+        import torch
+
+        from .capi import check, lib
+        from .envs import PUSH_INIT_QPOS
+
+        self.torch, self.venv, self.cfg = torch, venv, config or MoPAConfig()
+        cfg, m, dev = self.cfg, venv.model, venv.dev
+        self.dev = dev
+        ignored, passive, ref = planner_inputs(m)
+        self.planner = NativePlanner(m, passive, ignored, cfg.contact_threshold, cfg.range, 0.005, cfg.seed, venv.device_index)
+        self.policy = policy or UniformPolicy(torch, dev, cfg.seed + 17 * int(venv.env_ids[0]))
+        n = venv.n
+        self.n = n
+        self.env_gid = torch.as_tensor(venv.env_ids, dtype=torch.int64, device=dev)
+        self.macro_index = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.slab = torch.zeros(n, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
+        self.emit_flag = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.transitions = torch.zeros(transition_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
+        self._counters = torch.zeros(16, dtype=torch.int64, device=dev)
+        jid = [list(m.jnt_qposadr).index(a) for a in ref]
+        c = _RolloutConfig()
+        c.n_envs, c.max_iter, c.max_path, c.max_traj, c.rrt_capacity = n, cfg.max_iter, cfg.max_path, cfg.max_traj, min(rrt_capacity, max(n, 16))
+        c.num_trials, c.invalid_target_handling, c.interpolation = cfg.num_trials, int(cfg.invalid_target_handling), int(cfg.interpolation)
+        c.omega, c.action_range, c.ac_scale, c.discount = cfg.omega, cfg.action_range, cfg.ac_scale, cfg.discount_factor
+        c.step_size, c.joint_margin, c.range = cfg.step_size, cfg.joint_margin, cfg.range
+        c.seed_env, c.env_id_offset = venv.seed, int(venv.env_ids[0])
+        for k in range(7):
+            c.jnt_lo[k], c.jnt_hi[k], c.init_qpos[k] = float(m.jnt_range[jid[k], 0]), float(m.jnt_range[jid[k], 1]), float(PUSH_INIT_QPOS[k])
+        self._qpos0 = np.ascontiguousarray(m.qpos0, dtype=np.float64)
+        c.qpos0 = self._qpos0.ctypes.data
+        L = lib()
+        L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
+                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.POINTER(_C.c_void_p)]
+        L.mopa_rollout_destroy.argtypes = [_C.c_void_p]
+        L.mopa_rollout_destroy.restype = None
+        L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
+        L.mopa_rollout_step.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.mopa_rollout_busy.argtypes = [_C.c_void_p]
+        L.mopa_rollout_launches.argtypes = [_C.c_void_p]
+        L.mopa_rollout_launches.restype = _C.c_int64
+        L.mopa_rollout_env_ms.argtypes = [_C.c_void_p, _C.c_int32, _C.POINTER(_C.c_double)]
+        self._L, self._check = L, check
+        venv.reset()
+        h = _C.c_void_p()
+        check(L.mopa_rollout_create(venv.h, self.planner.h, _C.byref(venv.buf), _C.byref(c), self.macro_index.data_ptr(), self.slab.data_ptr(),
+                                    self.emit_flag.data_ptr(), self.transitions.data_ptr(), transition_capacity, self._counters.data_ptr(),
+                                    _C.byref(h)))
+        self.h = h
+        self.ticks = 0
+        self.last_emitted = None         # (slab [n,92], emit_flag [n]) of the latest tick
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.mopa_rollout_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return _C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def tick(self, wait_rrt=False):
+        self._check(self._L.mopa_rollout_pre(self.h, int(wait_rrt), self._stream()))
+        ac = self.policy(self.venv.obs, self.env_gid, self.macro_index)
+        ac = ac.to(device=self.dev, dtype=self.torch.float32).contiguous()
+        self._check(self._L.mopa_rollout_step(self.h, ac.data_ptr(), self._stream()))
+        self._keep = ac
+        self.ticks += 1
+        self.last_emitted = (self.slab, self.emit_flag)
+
+    def drain(self, max_ticks=64):
+        """Tick until no environment waits for an RRT plan (end of a collection run)."""
+        for _ in range(max_ticks):
+            self.tick(wait_rrt=True)
+            if self.counter_values()["waiting"] == 0:
+                break
+
+    def counter_values(self):
+        v = self._counters.cpu().numpy()
+        return {k: int(v[i]) for i, k in enumerate(COUNTER_NAMES)}
+
+    @property
+    def counters(self):
+        return self.counter_values()
+
+    @property
+    def env_steps(self):
+        return self.counter_values()["env_steps"]
+
+    @property
+    def n_transitions(self):
+        return self.counter_values()["transitions"]
+
+    @property
+    def launches(self):
+        return int(self._L.mopa_rollout_launches(self.h))
+
+    def env_kernel_ms(self, n_last):
+        """Mean device time of the env-step kernel over the latest ``n_last`` ticks (synchronises)."""
+        out = _C.c_double()
+        self._check(self._L.mopa_rollout_env_ms(self.h, int(n_last), _C.byref(out)))
+        return out.value

@@ -7,19 +7,20 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_vectorised_runner_matches_scalar_reference_loop(push_model, oracle_built):
+@pytest.mark.parametrize("native", [True, False], ids=["native-kernels", "torch-glue"])
+def test_vectorised_runner_matches_scalar_reference_loop(push_model, oracle_built, native):
     import torch
 
     from mopa_rl_b200 import rng
     from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.envs import VecSawyerPushObstacle
-    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, VecMoPARolloutRunner, planner_inputs
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, VecMoPARolloutRunner, planner_inputs
     from oracle.rollout_oracle import ScalarMoPARunner
 
     n, ticks, seed = 12, 60, 4321
     cfg = MoPAConfig(max_iter=150, seed=99)
     venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=25, env_id_offset=100)
-    runner = VecMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 7))
+    runner = (NativeMoPARolloutRunner if native else VecMoPARolloutRunner)(venv, cfg, policy=CounterPolicy(torch, venv.dev, 7))
     for _ in range(ticks):
         runner.tick()
     runner.drain()
