@@ -35,6 +35,15 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return int(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -321,7 +330,7 @@ def run_rollout(args):
                     "d2h_bytes_per_step": hp.d2h / e2e_ticks + d2h_tr / args.steps,
                     "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("r1_envwarp_v3_traffic.json"),
                          "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
@@ -413,7 +422,8 @@ def run_validity(args):
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * row * 4, "d2h_bytes_per_step": n * 4,
                     "api": "mopa_is_valid_host_f32 (pinned host rows in, result words out)"},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v2_traffic.json")),
                          "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query},
             "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism}}))

@@ -112,7 +112,8 @@ int mopa_plan_host(mopa_planner *p, const double *start, const double *goal, con
 typedef struct mopa_env mopa_env;
 
 typedef struct mopa_sawyer_task {
-    int32_t kind;                 /* 0: SawyerPushObstacle-v0 */
+    int32_t kind;                 /* 0: SawyerPushObstacle-v0, 2: SawyerAssemblyObstacle-v0 (body_cube = peg, body_rclaw = the part that
+                                   * carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd) */
     int32_t arm_qadr[7], arm_vadr[7], arm_dof[7];   /* qpos / qvel addresses and simulated-dof indices of right_j0..6 */
     int32_t grip_qadr[2], grip_vadr[2];             /* rc_close, lc_close */
     int32_t body_ee, body_cube, body_rclaw, body_lclaw; /* simulated-body indices */
@@ -121,6 +122,7 @@ typedef struct mopa_sawyer_task {
     double site_right_eef[3], site_left_eef[3], site_grip[3];  /* site positions in their body frames */
     double target_base[3];                          /* body_pos of the target body */
     double ac_scale, distance_threshold, success_reward;
+    double site_hole[3], site_hole_bottom[3];       /* assembly: sites "hole" / "hole_bottom" in their body frame */
 } mopa_sawyer_task;
 
 typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */

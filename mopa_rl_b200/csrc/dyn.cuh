@@ -41,7 +41,7 @@ struct DynDev {
     int g_body[DMAXG], g_type[DMAXG];
     double g_pos[DMAXG][3], g_quat[DMAXG][4], g_size[DMAXG][3], g_rbound[DMAXG], g_margin[DMAXG], g_friction[DMAXG][3];
     double g_solref[DMAXG][2], g_solimp[DMAXG][5];
-    int p_g1[512], p_g2[512];
+    int p_g1[640], p_g2[640];
     double g_mat[DMAXG][9];   // rotation matrix: world (static geom) or local (moving geom)
     int g_mslot[DMAXG];       // -2 static, -1 moving with identity local rotation, >= 0 slot in the per-substep world-matrix cache
     int gm_geom[DMAXGM], ngm;

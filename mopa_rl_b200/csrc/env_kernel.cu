@@ -87,12 +87,12 @@ extern "C" {
 int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out) {
     if (!dyn || !task || !out) { mopa_set_error("mopa_env_create: bad argument"); return MOPA_ERR_ARG; }
     *out = nullptr;
-    if (dyn->nb > mopa::DMAXB || dyn->nd > mopa::DMAXD || dyn->nact > mopa::DMAXA || dyn->ngeom > mopa::DMAXG || dyn->npair > 512 ||
+    if (dyn->nb > mopa::DMAXB || dyn->nd > mopa::DMAXD || dyn->nact > mopa::DMAXA || dyn->ngeom > mopa::DMAXG || dyn->npair > 640 ||
         dyn->nq > 40 || dyn->nv > 40) {
         mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
         return MOPA_ERR_MODEL;
     }
-    if (task->kind != 0) { mopa_set_error("mopa_env_create: only the SawyerPushObstacle task is built"); return MOPA_ERR_MODEL; }
+    if (task->kind != 0 && task->kind != 2) { mopa_set_error("mopa_env_create: only the SawyerPushObstacle (0) and SawyerAssemblyObstacle (2) tasks are built"); return MOPA_ERR_MODEL; }
     mopa_env *e = new mopa_env();
     e->device = device;
     e->task = *task;

@@ -930,6 +930,18 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, 
     for (int k = 0; k < 3; k++) obs[o++] = (float)eef[k];
     const double *eq = W.kxquat[0];
     obs[o++] = (float)eq[1]; obs[o++] = (float)eq[2]; obs[o++] = (float)eq[3]; obs[o++] = (float)eq[0];
+    if (T.kind == 2) {   // SawyerAssemblyObstacleEnv._get_obs (:53-59): hole, pegHead, pegEnd, peg_quat (wxyz)
+        double hole[3], head[3], end[3];
+        w_site(hole, W, 2, T.site_hole);
+        w_site(head, W, 1, T.site_right_eef);
+        w_site(end, W, 1, T.site_left_eef);
+        for (int k = 0; k < 3; k++) obs[o++] = (float)hole[k];
+        for (int k = 0; k < 3; k++) obs[o++] = (float)head[k];
+        for (int k = 0; k < 3; k++) obs[o++] = (float)end[k];
+        for (int k = 0; k < 4; k++) obs[o++] = (float)W.kxquat[1][k];
+        obs[o++] = 0.0f; obs[o++] = 0.0f;   // 38 observation floats, row padded to 40
+        return;
+    }
     const double target[3] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]], T.target_base[2]};
     for (int k = 0; k < 3; k++) obs[o++] = (float)target[k];
     const double *cube = W.kxpos[1], *cq = W.kxquat[1];
@@ -994,20 +1006,31 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         __syncwarp();
     }
     // reward / success (frames of the last substep's start state)
-    double re[3], le[3];
-    w_site(re, W, 2, T.site_right_eef);
-    w_site(le, W, 3, T.site_left_eef);
-    const double *cube = W.kxpos[1];
-    const double target[2] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]]};
-    double dgc = 0;
-    for (int k = 0; k < 3; k++) { const double d = cube[k] - 0.5 * (re[k] + le[k]); dgc += d * d; }
-    dgc = sqrt(dgc);
-    const double dct = sqrt((cube[0] - target[0]) * (cube[0] - target[0]) + (cube[1] - target[1]) * (cube[1] - target[1]));
     double reward = 0;
-    if (dct < 0.1) reward += 0.5 * (1 - tanh(5 * dct));
-    if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
     bool success = false, terminal = false;
-    if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
+    if (T.kind == 2) {   // SawyerAssemblyObstacleEnv.compute_reward (:32-51)
+        double head[3], hole[3], bottom[3], d1 = 0, d2 = 0;
+        w_site(head, W, 1, T.site_right_eef);
+        w_site(hole, W, 2, T.site_hole);
+        w_site(bottom, W, 2, T.site_hole_bottom);
+        for (int k = 0; k < 3; k++) { d1 += (head[k] - hole[k]) * (head[k] - hole[k]); d2 += (head[k] - bottom[k]) * (head[k] - bottom[k]); }
+        d1 = sqrt(d1); d2 = sqrt(d2);
+        if (d1 < 0.3) reward += 0.4 * (1 - tanh(15 * d1));
+        if (d2 < 0.025) { reward += T.success_reward; success = true; terminal = true; }
+    } else {             // SawyerPushObstacleEnv.compute_reward (:71-100)
+        double re[3], le[3];
+        w_site(re, W, 2, T.site_right_eef);
+        w_site(le, W, 3, T.site_left_eef);
+        const double *cube = W.kxpos[1];
+        const double target[2] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]]};
+        double dgc = 0;
+        for (int k = 0; k < 3; k++) { const double d = cube[k] - 0.5 * (re[k] + le[k]); dgc += d * d; }
+        dgc = sqrt(dgc);
+        const double dct = sqrt((cube[0] - target[0]) * (cube[0] - target[0]) + (cube[1] - target[1]) * (cube[1] - target[1]));
+        if (dct < 0.1) reward += 0.5 * (1 - tanh(5 * dct));
+        if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
+        if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
+    }
     if (mode != 2) w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
     __syncwarp();
     // _after_step: joint-limit projection (set_state + forward), episode accounting
