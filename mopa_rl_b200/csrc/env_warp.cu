@@ -29,8 +29,7 @@
 namespace mopa {
 
 constexpr int WD = DMAXD;       // dofs
-constexpr int WC = 24;          // constraint rows (one lane each)
-constexpr int WCP = 8;          // contact points kept per substep
+// WC = constraint-row capacity (one lane each, <= 32), WC / 3 = contact points kept per substep: template parameters
 constexpr int WCAND = 48;       // broad-phase survivors kept per substep
 constexpr int YS = WD + 1;      // padded row stride of Y (bank-conflict free, lane = row)
 constexpr int NTRI = WD * (WD + 1) / 2;   // lower-triangular storage of M and its Cholesky factors
@@ -45,8 +44,9 @@ struct WarpKin {
     double vel[WB][6], frc[WB][6];
     double inert[WB][13];
 };
-template <int WB, int WG>
+template <int WB, int WG, int WC>
 struct WarpWS {
+    static constexpr int WCP = WC / 3;
     double q[40], v[40];
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
         WarpKin<WB> k;
@@ -178,8 +178,8 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 // profiling / tuning hooks (MOPA_ENV_PROF=1, MOPA_ENV_SYNC_MASK=bits): per-stage clock64 sums, lane 0 of every warp
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
-template <int WB, int WG>
-__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
+template <int WB, int WG, int WC>
+__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
@@ -563,7 +563,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         // 32-lane-interleaved lines through L1.  Pairs whose contact needs the polygon clipper (box face
         // contacts) run that part one lane at a time on the warp's shared scratch; contact points are
         // committed in pair order.
-        const int maxcp = min(WCP, (WC - nlim) / 3);
+        const int maxcp = min(WC / 3, (WC - nlim) / 3);
         for (int base = 0; base < ncand && ncp < maxcp; base += 32) {
             const int ci = base + lane;
             CPoint cps[4];
@@ -910,15 +910,15 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
 }
 
 // kept frame slots: 0 = end-effector body, 1 = cube, 2 = right claw, 3 = left claw
-template <int WB, int WG>
-__device__ __forceinline__ void w_site(double *out, const WarpWS<WB, WG> &W, int slot, const double *local) {
+template <int WB, int WG, int WC>
+__device__ __forceinline__ void w_site(double *out, const WarpWS<WB, WG, WC> &W, int slot, const double *local) {
     double t[3];
     d_mv(t, W.kxmat[slot], local);
     for (int k = 0; k < 3; k++) out[k] = W.kxpos[slot][k] + t[k];
 }
 
-template <int WB, int WG>
-__device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, float *obs, int lane) {
+template <int WB, int WG, int WC>
+__device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> &W, float *obs, int lane) {
     if (lane != 0) return;
     int o = 0;
     for (int k = 0; k < 7; k++) obs[o++] = (float)W.q[T.arm_qadr[k]];
@@ -952,14 +952,14 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG> &W, 
 }
 
 
-template <int WB, int WG, int ENV_WARPS>
+template <int WB, int WG, int WC, int ENV_WARPS>
 __global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 ? 2 : 1))
 env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWS<WB, WG> &W = reinterpret_cast<WarpWS<WB, WG> *>(smem_raw)[warp];
+    WarpWS<WB, WG, WC> &W = reinterpret_cast<WarpWS<WB, WG, WC> *>(smem_raw)[warp];
     const DynDev &m = c_models[model_slot];
     const int t = blockIdx.x * ENV_WARPS + warp;
     const int e = t < n ? (ids ? ids[t] : t) : 0;
@@ -1078,14 +1078,14 @@ cudaError_t upload_env_model(int slot, const DynDev &h_model) {
     return cudaMemcpyToSymbol(c_models, &h_model, sizeof(DynDev), sizeof(DynDev) * slot);
 }
 
-template <int WB, int WG, int ENV_WARPS>
+template <int WB, int WG, int WC, int ENV_WARPS>
 static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                                      int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                                      const int32_t *ids, cudaStream_t stream) {
     static bool attr_set = false;
-    static_assert(sizeof(WarpWS<WB, WG>) * ENV_WARPS <= 227 * 1024, "warp workspaces exceed the shared memory of an SM");
-    const size_t smem = sizeof(WarpWS<WB, WG>) * ENV_WARPS;
-    auto kern = env_step_warp_kernel<WB, WG, ENV_WARPS>;
+    static_assert(sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS <= 227 * 1024, "warp workspaces exceed the shared memory of an SM");
+    const size_t smem = sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS;
+    auto kern = env_step_warp_kernel<WB, WG, WC, ENV_WARPS>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1102,12 +1102,12 @@ cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int n
     static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
     if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
     if (nb <= 14 && ngeom <= 32 && small_warps)
-        return launch_env_warp_t<14, 32, 7>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     if (nb <= 14 && ngeom <= 32)
-        return launch_env_warp_t<14, 32, 14>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
-    return launch_env_warp_t<DMAXB, DMAXG, 11>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+    return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
 }
 
-size_t env_warp_smem_per_warp() { return sizeof(WarpWS<14, 32>); }
+size_t env_warp_smem_per_warp() { return sizeof(WarpWS<14, 32, 24>); }
 
 }  // namespace mopa

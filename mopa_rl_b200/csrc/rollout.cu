@@ -181,34 +181,47 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
     for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)tg[k] : 0.0f;
 }
 
-// ---- 3. invalid targets: candidates of the back-off loop (rl/mopa_rollouts.py:119-143)
-__device__ __forceinline__ void ro_backoff_step(const RoDev &S, const double *c, double *t) {
-    double d[RO_NQ], n2 = 0;
-    for (int k = 0; k < S.nq; k++) { d[k] = c[k] - t[k]; n2 += d[k] * d[k]; }
-    const double nrm = sqrt(n2);
-    for (int k = 0; k < S.nq; k++) t[k] = t[k] + S.step_size * d[k] / nrm;
-}
-__global__ void ro_backoff_kernel(RoDev S, mopa_env_buffers B) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= *S.cnt_plan) return;
-    S.back_of_plan[slot] = -1;
-    if ((S.res_a[slot] & 1u) || !S.invalid_target_handling) return;
-    const int bs = atomicAdd(S.cnt_back, 1);
-    S.back_of_plan[slot] = bs;
-    const int e = S.plan_env[slot];
-    const double *c = B.qpos + (size_t)e * S.nq;
-    double t[RO_NQ];
-    for (int k = 0; k < S.nq; k++) t[k] = S.tgt64[(size_t)slot * S.nq + k];
-    for (int trial = 0; trial < S.num_trials; trial++) {
-        ro_backoff_step(S, c, t);
-        float *q32 = S.q32b + ((size_t)bs * S.num_trials + trial) * S.row;
-        for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)t[k] : 0.0f;
+// ---- 3. invalid targets: candidates of the back-off loop (rl/mopa_rollouts.py:119-143):
+//   target += step_size * (curr - target) / |curr - target|   over all nq dims, up to num_trials times.
+// One warp per plan slot, lanes over the qpos dims (two per lane); `upto` steps, optionally recording every
+// iterate as an fp32 row (the validity queries).  Used by the back-off kernel and by the target choice.
+__device__ __forceinline__ void ro_backoff_run(const RoDev &S, const double *c, double &t0, double &t1, int lane, int upto, float *rows) {
+    const int k0 = lane, k1 = lane + 32;
+    const double c0 = k0 < S.nq ? c[k0] : 0.0, c1 = k1 < S.nq ? c[k1] : 0.0;
+    for (int trial = 0; trial < upto; trial++) {
+        const double d0 = k0 < S.nq ? c0 - t0 : 0.0, d1 = k1 < S.nq ? c1 - t1 : 0.0;
+        double n2 = d0 * d0 + d1 * d1;
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        const double nrm = sqrt(n2);
+        t0 = t0 + S.step_size * d0 / nrm;
+        t1 = t1 + S.step_size * d1 / nrm;
+        if (rows) {
+            float *q32 = rows + (size_t)trial * S.row;
+            if (k0 < S.row) q32[k0] = k0 < S.nq ? (float)t0 : 0.0f;
+            if (k1 < S.row) q32[k1] = k1 < S.nq ? (float)t1 : 0.0f;
+        }
     }
 }
+__global__ void ro_backoff_kernel(RoDev S, mopa_env_buffers B) {
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= *S.cnt_plan) return;
+    int bs = -1;
+    if (!(S.res_a[slot] & 1u) && S.invalid_target_handling) {
+        if (lane == 0) bs = atomicAdd(S.cnt_back, 1);
+        bs = __shfl_sync(0xffffffffu, bs, 0);
+    }
+    if (lane == 0) S.back_of_plan[slot] = bs;
+    if (bs < 0) return;
+    const int e = S.plan_env[slot];
+    const double *c = B.qpos + (size_t)e * S.nq, *tg = S.tgt64 + (size_t)slot * S.nq;
+    double t0 = lane < S.nq ? tg[lane] : 0.0, t1 = lane + 32 < S.nq ? tg[lane + 32] : 0.0;
+    ro_backoff_run(S, c, t0, t1, lane, S.num_trials, S.q32b + (size_t)bs * S.num_trials * S.row);
+}
 
-// ---- 4. target choice, clip_qpos, interpolation points (SACAgent.clip_qpos / simple_interpolate, :237-298)
+// ---- 4. target choice, clip_qpos, interpolation points (SACAgent.clip_qpos / simple_interpolate, :237-298).
+// One warp per plan slot: the scalar decisions are taken redundantly by every lane, the rows are written by all.
 __global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (slot >= *S.cnt_plan) return;
     const int e = S.plan_env[slot];
     const double *curr = B.qpos + (size_t)e * S.nq;
@@ -216,40 +229,50 @@ __global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
     bool ok = (S.res_a[slot] & 1u) != 0;
     const int bs = S.back_of_plan[slot];
     if (!ok && bs >= 0) {
-        int first = -1;
-        for (int trial = 0; trial < S.num_trials; trial++)
+        int first = S.num_trials;
+        for (int trial = lane; trial < S.num_trials; trial += 32)
             if (S.res_b[(size_t)bs * S.num_trials + trial] & 1u) { first = trial; break; }
-        const int upto = first >= 0 ? first + 1 : S.num_trials;   // no valid candidate: the last one (and the plan fails)
-        for (int trial = 0; trial < upto; trial++) ro_backoff_step(S, curr, tg);
-        ok = first >= 0;
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        ok = first < S.num_trials;
+        const int upto = ok ? first + 1 : S.num_trials;   // no valid candidate: the last one (and the plan fails)
+        double t0 = lane < S.nq ? tg[lane] : 0.0, t1 = lane + 32 < S.nq ? tg[lane + 32] : 0.0;
+        ro_backoff_run(S, curr, t0, t1, lane, upto, nullptr);
+        if (lane < S.nq) tg[lane] = t0;
+        if (lane + 32 < S.nq) tg[lane + 32] = t1;
+        __syncwarp();
     }
-    S.plan_ok[slot] = ok ? 1 : 0;
-    S.nstep[slot] = 0;
-    if (!ok) { ro_count(S.counters, C_INVALID); ro_count(S.counters, C_MP_FAIL); return; }
-    for (int k = 0; k < S.nq; k++) c[k] = curr[k];
+    if (lane == 0) { S.plan_ok[slot] = ok ? 1 : 0; S.nstep[slot] = 0; }
+    if (!ok) { if (lane == 0) { ro_count(S.counters, C_INVALID); ro_count(S.counters, C_MP_FAIL); } return; }
     bool out = false;
     for (int k = 0; k < 7; k++) { const double x = curr[S.arm_qadr[k]]; if (x < S.jlo[k] || x > S.jhi[k]) out = true; }
-    if (out)
-        for (int k = 0; k < 7; k++) {
-            double x = curr[S.arm_qadr[k]];
-            const double lo = S.jlo[k] + S.joint_margin, hi = S.jhi[k] - S.joint_margin;
-            x = x < lo ? lo : x;
-            x = x > hi ? hi : x;
-            c[S.arm_qadr[k]] = x;
-        }
+    for (int k = lane; k < S.nq; k += 32) c[k] = curr[k];
+    __syncwarp();
+    if (out && lane < 7) {
+        double x = curr[S.arm_qadr[lane]];
+        const double lo = S.jlo[lane] + S.joint_margin, hi = S.jhi[lane] - S.joint_margin;
+        x = x < lo ? lo : x;
+        x = x > hi ? hi : x;
+        c[S.arm_qadr[lane]] = x;
+    }
+    __syncwarp();
     const double lim = S.ac_scale * 0.8;
-    double diff[7], sf = 1.0;
-    for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; }
+    double diff[7], sf = 1.0, run[7];
+    for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
     int nstep = (int)floor(sf);
     if (nstep > RO_JMAX) nstep = RO_JMAX;
-    S.nstep[slot] = nstep;
-    double run[7];
-    for (int k = 0; k < 7; k++) run[k] = c[S.arm_qadr[k]];
+    if (lane == 0) S.nstep[slot] = nstep;
     for (int j = 0; j < RO_JMAX; j++) {
         float *q32 = S.q32c + ((size_t)slot * RO_JMAX + j) * S.row;
-        for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)c[k] : 0.0f;
+        for (int k = lane; k < S.row; k += 32) q32[k] = k < S.nq ? (float)c[k] : 0.0f;
+        __syncwarp();
         if (j < nstep) {
-            for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; q32[S.arm_qadr[k]] = (float)run[k]; }
+            for (int k = 0; k < 7; k++) run[k] = run[k] + diff[k] / sf;
+            if (lane < 7) {
+                double v = run[0];
+#pragma unroll
+                for (int k = 1; k < 7; k++) if (lane == k) v = run[k];
+                q32[S.arm_qadr[lane]] = (float)v;
+            }
         }
     }
 }
@@ -607,9 +630,9 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
     RrtBatch &Q = r->batch[r->fill];
     ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, d_actions);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32a, S.row, S.n, S.res_a, 0, p->sm_count, st, S.cnt_plan, 1));
-    ro_backoff_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    ro_backoff_kernel<<<(S.n * 32 + 127) / 128, 128, 0, st>>>(S, r->buf);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32b, S.row, S.n * S.num_trials, S.res_b, 0, p->sm_count, st, S.cnt_back, S.num_trials));
-    ro_interp_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
+    ro_interp_kernel<<<(S.n * 32 + 127) / 128, 128, 0, st>>>(S, r->buf);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32c, S.row, S.n * RO_JMAX, S.res_c, 0, p->sm_count, st, S.cnt_plan, RO_JMAX));
     ro_interp_finish_kernel<<<blocks, 128, 0, st>>>(S, Q);
     RO_TRY(cudaGetLastError());

@@ -174,6 +174,8 @@ class DynModel:
             p_g1=np.array([gidx[a] for a, _ in pairs], np.int32), p_g2=np.array([gidx[b] for _, b in pairs], np.int32),
         )
         self.nact = len(a_ids)
+        # constraint-row capacity of the env kernel's workspace variant that serves this scene (env_warp.cu: launch_env_warp)
+        self.max_rows = 24 if (self.nb <= 14 and len(used) <= 32) else 32
         self._arr = {}
         d = DynDesc()
         d.nq, d.nv, d.nb, d.nd, d.nact = m.nq, m.nv, self.nb, self.nd, self.nact

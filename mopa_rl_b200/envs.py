@@ -30,7 +30,8 @@ class SawyerTask(C.Structure):
                 ("body_rclaw", C.c_int32), ("body_lclaw", C.c_int32), ("target_qadr", C.c_int32 * 2),
                 ("max_episode_steps", C.c_int32), ("nsub", C.c_int32), ("site_right_eef", C.c_double * 3),
                 ("site_left_eef", C.c_double * 3), ("site_grip", C.c_double * 3), ("target_base", C.c_double * 3),
-                ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double)]
+                ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double),
+                ("site_hole", C.c_double * 3), ("site_hole_bottom", C.c_double * 3)]
 
 
 class EnvBuffers(C.Structure):
@@ -69,6 +70,52 @@ def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.
     return t
 
 
+ASSEMBLY_INIT_QPOS = np.array([0.427, 0.13, 0.0557, 0.114, -0.0622, 0.0276, 0.00356])   # sawyer_assembly_obstacle.py:19-20
+
+
+def make_assembly_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, **_):
+    """SawyerAssemblyObstacle-v0: peg rigidly attached to the gripper, hole sites on the furniture part `4_part4`
+    (env/sawyer/sawyer_assembly_obstacle.py).  kind 2 of mopa_sawyer_task: body_cube = peg, body_rclaw / body_lclaw =
+    the body that carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd."""
+    t = SawyerTask()
+    t.kind = 2
+    sim_body = {b: i for i, b in enumerate(dyn.bodies)}
+    for k in range(7):
+        j = "right_j%d" % k
+        t.arm_qadr[k] = model.get_joint_qpos_addr(j)
+        t.arm_vadr[k] = model.get_joint_qvel_addr(j)
+        t.arm_dof[k] = list(dyn.dof_vadr).index(t.arm_vadr[k])
+    for k, j in enumerate(["rc_close", "lc_close"]):
+        t.grip_qadr[k] = model.get_joint_qpos_addr(j)
+        t.grip_vadr[k] = model.get_joint_qvel_addr(j)
+    hole_body = int(model.site_bodyid[model.site_name2id("hole")])
+    assert hole_body == int(model.site_bodyid[model.site_name2id("hole_bottom")])
+    t.body_ee = sim_body[model.body_name2id("right_ee_attchment")]
+    t.body_cube = sim_body[model.body_name2id("peg")]
+    t.body_rclaw = t.body_lclaw = sim_body[hole_body]
+    t.max_episode_steps = int(max_episode_steps)
+    t.nsub = int(frame_dt / model.opt_timestep)
+    for name, field in (("pegHead", t.site_right_eef), ("pegEnd", t.site_left_eef), ("grip_site", t.site_grip),
+                        ("hole", t.site_hole), ("hole_bottom", t.site_hole_bottom)):
+        p = model.site_pos[model.site_name2id(name)]
+        for k in range(3):
+            field[k] = float(p[k])
+    t.ac_scale, t.distance_threshold, t.success_reward = float(ac_scale), 0.0, float(success_reward)
+    return t
+
+
+def assembly_reset_state(model, seed, env_ids, episode_idx):
+    """Reset distribution of SawyerAssemblyObstacleEnv._reset (:22-30): arm = init_qpos + N(0, 0.02^2), rest at qpos0."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64).reshape(-1)
+    ep = np.broadcast_to(np.asarray(episode_idx, dtype=np.uint64), env_ids.shape)
+    n = len(env_ids)
+    qpos = np.tile(model.qpos0, (n, 1))
+    ref = [model.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+    dims = np.arange(7, dtype=np.uint64)
+    qpos[:, ref] = ASSEMBLY_INIT_QPOS + 0.02 * rng.normal(seed, env_ids[:, None], ep[:, None], dims[None, :])
+    return qpos, np.zeros((n, model.nv))
+
+
 def push_reset_state(model, seed, env_ids, episode_idx):
     """Reset distribution of SawyerPushObstacleEnv._reset for the given (env id, episode #) pairs."""
     env_ids = np.asarray(env_ids, dtype=np.uint64).reshape(-1)
@@ -86,6 +133,10 @@ def push_reset_state(model, seed, env_ids, episode_idx):
 
 class VecSawyerPushObstacle:
     """N device-resident SawyerPushObstacle-v0 environments."""
+    ENV_ID = "SawyerPushObstacle-v0"
+    OBS_DIM = 40
+    make_task = staticmethod(make_push_task)
+    reset_state = staticmethod(push_reset_state)
 
     def __init__(self, n_envs, seed=1234, device=0, env_id_offset=0, model=None, max_episode_steps=250, contacts=True, **task_kwargs):
         import torch
@@ -93,9 +144,9 @@ class VecSawyerPushObstacle:
         self.torch = torch
         self.n = int(n_envs)
         self.seed = int(seed)
-        self.model = model if model is not None else load_model("SawyerPushObstacle-v0")
+        self.model = model if model is not None else load_model(self.ENV_ID)
         self.dyn = DynModel(self.model)
-        self.task = make_push_task(self.model, self.dyn, max_episode_steps=max_episode_steps, **task_kwargs)
+        self.task = self.make_task(self.model, self.dyn, max_episode_steps=max_episode_steps, **task_kwargs)
         self.dev = torch.device("cuda", device)
         self.device_index = device
         L = lib()
@@ -159,7 +210,7 @@ class VecSawyerPushObstacle:
         ids = np.arange(self.n) if ids is None else np.asarray(ids, dtype=np.int64).reshape(-1)
         if len(ids) == 0:
             return self.obs
-        qpos, qvel = push_reset_state(self.model, self.seed, self.env_ids[ids], self.episode_idx[ids])
+        qpos, qvel = self.reset_state(self.model, self.seed, self.env_ids[ids], self.episode_idx[ids])
         self.episode_idx[ids] += 1
         t_ids = torch.as_tensor(ids, device=self.dev)
         self.qpos[t_ids] = torch.as_tensor(qpos, device=self.dev)
@@ -197,3 +248,13 @@ class VecSawyerPushObstacle:
             self.has_prev.zero_()
         else:
             self.has_prev[mask.bool()] = 0
+
+
+class VecSawyerAssemblyObstacle(VecSawyerPushObstacle):
+    """N device-resident SawyerAssemblyObstacle-v0 environments (BASELINE configs[3]).  The observation row keeps the
+    40-float stride; its first 38 floats are joint_pos7, joint_vel7, gripper_qpos2, gripper_qvel2, eef_pos3, eef_quat4,
+    hole3, pegHead3, pegEnd3, peg_quat4 (env/sawyer/sawyer_assembly_obstacle.py:53-59)."""
+    ENV_ID = "SawyerAssemblyObstacle-v0"
+    OBS_DIM = 38
+    make_task = staticmethod(make_assembly_task)
+    reset_state = staticmethod(assembly_reset_state)

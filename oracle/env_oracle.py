@@ -127,3 +127,72 @@ class PushEnvOracle:
             terminal = True
         self.terminal = terminal
         return reward, terminal
+
+
+class AssemblyEnvOracle(PushEnvOracle):
+    """SawyerAssemblyObstacle-v0 (env/sawyer/sawyer_assembly_obstacle.py:32-59, _step :97-143): same step and
+    _after_step logic as the push task; reward from the pegHead / hole / hole_bottom sites, 38-float observation."""
+
+    def __init__(self, model, dynmodel, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, contacts=True):
+        self.m, self.dm = model, dynmodel
+        self.dyn = OracleDyn(dynmodel)
+        self.dyn.enable_contacts(contacts)
+        m = model
+        self.ref_q = [m.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+        self.ref_v = [m.get_joint_qvel_addr("right_j%d" % i) for i in range(7)]
+        self.grip_q = [m.get_joint_qpos_addr(j) for j in ("rc_close", "lc_close")]
+        self.grip_v = [m.get_joint_qvel_addr(j) for j in ("rc_close", "lc_close")]
+        sim = {b: i for i, b in enumerate(dynmodel.bodies)}
+        self.b_ee, self.b_peg = sim[m.body_name2id("right_ee_attchment")], sim[m.body_name2id("peg")]
+        self.b_hole = sim[int(m.site_bodyid[m.site_name2id("hole")])]
+        self.s_head, self.s_end, self.s_grip, self.s_hole, self.s_bottom = (
+            m.site_pos[m.site_name2id(n)] for n in ("pegHead", "pegEnd", "grip_site", "hole", "hole_bottom"))
+        self.comp = np.zeros(dynmodel.nd, np.int32)
+        self.comp[[list(dynmodel.dof_vadr).index(v) for v in self.ref_v]] = 1
+        self.nsub = int(frame_dt / m.opt_timestep)
+        self.ac_scale, self.succ_rew, self.max_steps = ac_scale, success_reward, max_episode_steps
+        self.lim = [(int(q), dynmodel._arr["d_range"][k]) for k, q in enumerate(dynmodel.dof_qadr) if q >= 0 and dynmodel._arr["d_limited"][k]]
+
+    def obs(self):
+        q, v = self.qpos, self.qvel
+        eef, eq = self._site(self.b_ee, self.s_grip), self.xquat[self.b_ee]
+        return np.concatenate([q[self.ref_q], v[self.ref_v], q[self.grip_q], v[self.grip_v], eef, eq[[1, 2, 3, 0]],
+                               self._site(self.b_hole, self.s_hole), self._site(self.b_peg, self.s_head), self._site(self.b_peg, self.s_end),
+                               self.xquat[self.b_peg]])
+
+    def _reward(self):
+        head = self._site(self.b_peg, self.s_head)
+        d_hole = np.linalg.norm(head - self._site(self.b_hole, self.s_hole))
+        d_bottom = np.linalg.norm(head - self._site(self.b_hole, self.s_bottom))
+        reward, terminal = 0.0, False
+        if d_hole < 0.3:
+            reward += 0.4 * (1 - np.tanh(15 * d_hole))
+        if d_bottom < 0.025:
+            reward += self.succ_rew
+            self.success, terminal = True, True
+        return reward, terminal
+
+    def step(self, action, is_planner=False):
+        action = np.asarray(action, np.float64)
+        if not is_planner or self.prev_state is None:
+            self.prev_state = self.qpos[self.ref_q].copy()
+        a = action[:7] if is_planner else action[:7] * self.ac_scale
+        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
+        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
+            self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
+        self.prev_state = desired.copy()
+        reward, terminal = self._reward()
+        ob = self.obs()
+        clipped = False
+        for qa, (lo, hi) in self.lim:
+            if self.qpos[qa] < lo or self.qpos[qa] > hi:
+                self.qpos[qa] = min(max(self.qpos[qa], lo), hi)
+                clipped = True
+        if clipped:
+            self.set_state(self.qpos, self.qvel)
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return ob, reward, terminal

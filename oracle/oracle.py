@@ -169,6 +169,7 @@ class OracleDyn:
         L.orc_dyn_create.argtypes = [C.c_void_p]
         L.orc_dyn_destroy.argtypes = [C.c_void_p]
         L.orc_dyn_enable_contacts.argtypes = [C.c_void_p, C.c_int]
+        L.orc_dyn_set_max_rows.argtypes = [C.c_void_p, C.c_int]
         L.orc_dyn_step.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
         L.orc_dyn_forward.argtypes = [C.c_void_p] * 6
         L.orc_dyn_mass_bias.argtypes = [C.c_void_p] * 6
@@ -176,6 +177,7 @@ class OracleDyn:
         if not self.h:
             raise RuntimeError("scene too large for the dynamics oracle")
         self.nd, self.nb = dynmodel.nd, dynmodel.nb
+        L.orc_dyn_set_max_rows(self.h, int(getattr(dynmodel, "max_rows", 36)))
 
     def __del__(self):
         try:

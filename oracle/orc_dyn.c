@@ -120,6 +120,7 @@ void *orc_dyn_create(const mopa_dyn_desc *d) {
     m->p_g2 = (int *)malloc(sizeof(int) * (d->npair + 1));
     for (int i = 0; i < d->npair; i++) { m->p_g1[i] = d->p_g1[i]; m->p_g2[i] = d->p_g2[i]; }
     m->enable_contacts = 1;
+    m->max_rows = DMAXC;
     return m;
 }
 void orc_dyn_destroy(void *h) {
@@ -130,6 +131,8 @@ void orc_dyn_destroy(void *h) {
 static long g_pgs_calls = 0, g_pgs_sweeps = 0;
 void orc_pgs_stats(long *out, int reset) { out[0] = g_pgs_calls; out[1] = g_pgs_sweeps; if (reset) g_pgs_calls = g_pgs_sweeps = 0; }
 void orc_dyn_enable_contacts(void *h, int on) { ((dyn_model *)h)->enable_contacts = on; }
+/* constraint-row capacity (the env kernel keeps 24 rows for small scenes, 32 for large ones; excess contacts are dropped in pair order) */
+void orc_dyn_set_max_rows(void *h, int n) { ((dyn_model *)h)->max_rows = n < 3 ? 3 : (n > DMAXC ? DMAXC : n); }
 
 /* impedance / reference parameters of one constraint row (mj_makeImpedance semantics) */
 static void kbi(const dyn_model *m, const double *solref, const double *solimp, double pos, double margin, double *K, double *B, double *imp) {
@@ -328,12 +331,13 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
     /* ---- constraints */
     crow *rows = (crow *)malloc(sizeof(crow) * DMAXC);
     int nc = 0;
-    for (int k = 0; k < nd && nc < DMAXC; k++) {
+    const int maxrows = m->max_rows;
+    for (int k = 0; k < nd && nc < maxrows; k++) {
         if (!m->d_limited[k] || m->d_qadr[k] < 0) continue;
         double q = qpos[m->d_qadr[k]];
         for (int side = 0; side < 2; side++) {
             double dist = side == 0 ? q - m->d_range[k][0] : m->d_range[k][1] - q;
-            if (dist >= m->d_margin[k] || nc >= DMAXC) continue;
+            if (dist >= m->d_margin[k] || nc >= maxrows) continue;
             crow *r = &rows[nc++];
             memset(r, 0, sizeof(crow));
             r->J[k] = side == 0 ? 1.0 : -1.0;
@@ -344,7 +348,7 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
     D->ncon = 0;
     if (m->enable_contacts && m->npair > 0) {
         int n0 = nc;
-        nc += orc_contact_rows(m, D, S, rows + nc, DMAXC - nc);
+        nc += orc_contact_rows(m, D, S, rows + nc, maxrows - nc);
         D->ncon = (nc - n0) / 3;
     }
     double fc[DMAXD];

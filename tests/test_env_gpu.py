@@ -55,3 +55,46 @@ def test_env_step_matches_oracle_no_contacts(push_model, oracle_built):
 def test_env_step_matches_oracle_with_contacts(push_model, oracle_built):
     w = _run(push_model, contacts=True, steps=4)
     print("max abs error (contacts):", w)
+
+
+def test_assembly_env_step_matches_oracle(oracle_built):
+    """SawyerAssemblyObstacle-v0 (BASELINE configs[3]): 19 simulated bodies, 39 contact geoms, peg / hole reward and the
+    38-float observation, against the assembly env oracle."""
+    import torch
+
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, assembly_reset_state
+    from mopa_rl_b200.model import load_model
+    from oracle.env_oracle import AssemblyEnvOracle
+
+    model = load_model("SawyerAssemblyObstacle-v0")
+    n, steps = 24, 3
+    venv = VecSawyerAssemblyObstacle(n, seed=31, max_episode_steps=3)
+    venv.reset()
+    dm = DynModel(model)
+    q0, v0 = assembly_reset_state(model, 31, np.arange(n), np.zeros(n, dtype=np.int64))
+    envs = [AssemblyEnvOracle(model, dm, max_episode_steps=3) for _ in range(n)]
+    obs0 = np.stack([e.reset_to(q0[i], v0[i]) for i, e in enumerate(envs)])
+    assert np.abs(venv.obs.cpu().numpy()[:, :38] - obs0).max() < 1e-5
+    rng = np.random.default_rng(9)
+    worst = dict(qpos=0.0, qvel=0.0, obs=0.0, rew=0.0)
+    for s in range(steps):
+        act = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        isp = np.zeros(n, np.uint8)
+        if s >= 1:
+            isp[::2] = 1
+            act[::2] *= 0.08
+        venv.step(torch.as_tensor(act, device="cuda"), torch.as_tensor(isp, device="cuda"))
+        torch.cuda.synchronize()
+        gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
+        gobs, grew, gdone = venv.obs.cpu().numpy(), venv.reward.cpu().numpy(), venv.done.cpu().numpy()
+        for i, e in enumerate(envs):
+            ob, r, d = e.step(act[i].astype(np.float64), bool(isp[i]))
+            worst["qpos"] = max(worst["qpos"], np.abs(gq[i] - e.qpos).max())
+            worst["qvel"] = max(worst["qvel"], np.abs(gv[i] - e.qvel).max())
+            worst["obs"] = max(worst["obs"], np.abs(gobs[i, :38] - ob).max())
+            worst["rew"] = max(worst["rew"], abs(grew[i] - r))
+            assert bool(gdone[i]) == d
+    assert worst["qpos"] < TOL and worst["qvel"] < TOL, worst
+    assert worst["obs"] < 1e-4 and worst["rew"] < 1e-6, worst
+    print("assembly max abs error:", worst)
