@@ -138,6 +138,8 @@ typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
     uint8_t *done;       /* [n]     _terminal after _after_step */
     uint8_t *success;    /* [n]     _success */
     int32_t *ncon;       /* [n]     contacts in the last substep */
+    int32_t *work;       /* [n]     nullable: Newton steps spent by the latest env.step (cost feedback: callers group
+                          *         expensive environments into the same CTAs, see mopa_rollout_step) */
 } mopa_env_buffers;
 
 int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out);

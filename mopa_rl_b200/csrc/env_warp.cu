@@ -179,7 +179,7 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
 template <int WB, int WG, int WC>
-__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, const int4 keep_bodies,
+__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, int &nwt_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
@@ -814,6 +814,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             if (scale * sqrt(gn) < m.tolerance) break;
             newton_hess();
             if (c_tune.prof && lane == 0) { atomicAdd(&g_prof[20], 1ULL); if (it == m.iterations) atomicAdd(&g_prof[28], 1ULL); }
+            nwt_out += 1;
             // search direction p = -H^-1 g (W.rhs in place; W.z keeps M a - tau)
             const double matme = lane < nd ? W.z[lane] : 0.0;
             if (lane < nd) W.rhs[lane] = -gme;
@@ -967,7 +968,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (!forward_only) {
             int dummy = 0;
-            for (int s = 0; s < T.nsub; s++) w_substep(m, mg, W, 0u, true, lane, dummy, make_int4(0, 0, 0, 0), false, true);
+            for (int s = 0; s < T.nsub; s++) w_substep(m, mg, W, 0u, true, lane, dummy, dummy, make_int4(0, 0, 0, 0), false, true);
         }
         return;
     }
@@ -978,10 +979,10 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     if (lane == 0) W.wn = 0;
     if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
     __syncwarp();
-    int ncon = 0;
+    int ncon = 0, nwt = 0;   // contacts of the last substep; Newton steps of this env.step (cost feedback for the caller's grouping)
     const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw);
     if (forward_only) {
-        w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
         if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
         w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
         return;
@@ -999,9 +1000,9 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     __syncwarp();
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
-    if (mode == 2) w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
+    if (mode == 2) w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
     for (int s = 0; s < T.nsub; s++) {
-        w_substep(m, mg, W, comp, true, lane, ncon, keep, mode != 2, true);
+        w_substep(m, mg, W, comp, true, lane, ncon, nwt, keep, mode != 2, true);
         if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1043,7 +1044,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     clipped = __any_sync(FULL, clipped);
     __syncwarp();
     if (clipped) {
-        w_substep(m, mg, W, 0u, false, lane, ncon, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
         if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1061,6 +1062,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         B.done[e] = terminal ? 1 : 0;
         B.success[e] = success ? 1 : 0;
         if (B.ncon) B.ncon[e] = ncon;
+        if (B.work && mode != 2) B.work[e] = nwt;
     }
 }
 

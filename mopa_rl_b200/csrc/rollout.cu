@@ -70,6 +70,8 @@ struct RoDev {   // everything the kernels need, passed by value
     long long ring_cap;
     // planning work lists of the current tick
     int *cnt_plan, *cnt_back;    // device counters
+    int *cnt_ids, *ids;          // [2], [n]: environments ordered for the env-step launch (expensive ones first, together)
+    int heavy_work;              // Newton steps per env.step above which an environment counts as expensive
     int *plan_env;               // [n]
     double *tgt64, *c64;         // [n][nq]
     float *q32a;                 // [n][row]          targets
@@ -140,7 +142,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
     S.need[e] = need ? 1 : 0;
     S.emit_flag[e] = emit;
     S.reset_flag[e] = reset;
-    if (e == 0) { *S.cnt_plan = 0; *S.cnt_back = 0; S.counters[C_WAITING] = 0; }
+    if (e == 0) { *S.cnt_plan = 0; *S.cnt_back = 0; S.cnt_ids[0] = 0; S.cnt_ids[1] = 0; S.counters[C_WAITING] = 0; }
 }
 
 // ---- 2. new macro actions: direct action, or planner target (SACAgent.convert2planner_displacement + target clip)
@@ -436,6 +438,12 @@ __global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
     S.step_mode[e] = (unsigned char)kind;
     S.step_mask[e] = kind != 3;
     if (kind == 3) ro_count(S.counters, C_WAITING);   // environments waiting for their RRT plan in this tick
+    // Launch order of the env-step kernel: the warps of a CTA advance in lockstep (stage barriers), so an environment
+    // that needs 2-3 Newton steps per substep (arm pushing the cube: ~7 % of them) stalls its 13 neighbours.  Grouping
+    // them (cost = Newton steps of their previous env.step) keeps the other CTAs at one step per substep.
+    const int heavy = (B.work && B.work[e] > S.heavy_work) ? 1 : 0;
+    const int pos = atomicAdd(S.cnt_ids + heavy, 1);
+    S.ids[heavy ? pos : S.n - 1 - pos] = e;
     float *sa = S.step_action + (size_t)e * 8;
     if (kind == 0) {
         for (int k = 0; k < 7; k++) sa[k] = (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
@@ -525,6 +533,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.omega = cfg->omega; S.action_range = cfg->action_range; S.ac_scale = cfg->ac_scale; S.discount = cfg->discount;
     S.step_size = cfg->step_size; S.joint_margin = cfg->joint_margin; S.range = cfg->range;
     S.seed_env = cfg->seed_env; S.env_id_offset = cfg->env_id_offset;
+    S.heavy_work = env->task.nsub + env->task.nsub / 8;
     for (int k = 0; k < 7; k++) { S.jlo[k] = cfg->jnt_lo[k]; S.jhi[k] = cfg->jnt_hi[k]; S.init_qpos[k] = cfg->init_qpos[k]; S.arm_qadr[k] = env->task.arm_qadr[k]; }
     for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
@@ -540,7 +549,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     A(S.kind, n); A(S.pending, n); A(S.macro_done, n); A(S.need, n); A(S.reset_flag, n); A(S.step_mode, n); A(S.step_mask, n);
     A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
     A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
-    A(S.cnt_plan, 1); A(S.cnt_back, 1);
+    A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n);
     A(S.plan_env, n); A(S.tgt64, (size_t)n * nq); A(S.c64, (size_t)n * nq); A(S.q32a, (size_t)n * row); A(S.res_a, n);
     A(S.back_of_plan, n); A(S.q32b, (size_t)n * S.num_trials * row); A(S.res_b, (size_t)n * S.num_trials);
     A(S.q32c, (size_t)n * RO_JMAX * row); A(S.res_c, (size_t)n * RO_JMAX); A(S.nstep, n); A(S.plan_ok, n);
@@ -653,7 +662,7 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
     const int ev = (int)(r->ticks % mopa_rollout::EV_RING);
     RO_TRY(cudaEventRecord(r->ev_env0[ev], st));
     RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->task, r->buf, S.step_action, 8, S.step_mode,
-                           S.step_mask, S.n, 0, nullptr, st));
+                           S.step_mask, S.n, 0, S.ids, st));
     RO_TRY(cudaEventRecord(r->ev_env1[ev], st));
     ro_post_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
     RO_TRY(cudaGetLastError());
