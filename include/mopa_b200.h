@@ -186,6 +186,9 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
 /* d_actions: device float[n][7], the policy's action for every environment. */
 int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
 int mopa_rollout_busy(mopa_rollout *r);
+/* Diagnostics of the asynchronous planner: out4 = {device ms of the last finished RRT batch, batches finished, mean device
+ * ms per batch, mean ticks between launch and finalisation}. */
+int mopa_rollout_rrt_stats(mopa_rollout *r, double *out4);
 /* Kernels of this library launched so far through the handle. */
 int64_t mopa_rollout_launches(mopa_rollout *r);
 /* Mean device time (ms) of the env-step kernel over the latest n_last ticks (synchronises the device). */

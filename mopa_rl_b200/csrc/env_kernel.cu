@@ -88,7 +88,7 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     if (!dyn || !task || !out) { mopa_set_error("mopa_env_create: bad argument"); return MOPA_ERR_ARG; }
     *out = nullptr;
     if (dyn->nb > mopa::DMAXB || dyn->nd > mopa::DMAXD || dyn->nact > mopa::DMAXA || dyn->ngeom > mopa::DMAXG || dyn->npair > 640 ||
-        dyn->nq > 40 || dyn->nv > 40) {
+        dyn->nq > 36 || dyn->nv > 36) {
         mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
         return MOPA_ERR_MODEL;
     }
@@ -145,7 +145,7 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
     if (!e || !buf || n < 0) { mopa_set_error("mopa_env_forward: bad argument"); return MOPA_ERR_ARG; }
     if (n == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
+    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->h_model.ngm, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
     return MOPA_OK;
 }
 
@@ -154,7 +154,7 @@ int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_actio
     if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
     if (n_envs == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->task, *buf, d_action, action_stride, d_is_planner,
+    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->h_model.ngm, e->task, *buf, d_action, action_stride, d_is_planner,
                                   d_mask, n_envs, 0, nullptr, (cudaStream_t)stream));
     return MOPA_OK;
 }

@@ -47,24 +47,25 @@ struct WarpKin {
 template <int WB, int WG, int WC>
 struct WarpWS {
     static constexpr int WCP = WC / 3;
-    double q[40], v[40];
+    double q[36], v[36];
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
         WarpKin<WB> k;
         double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
     };
-    double kxpos[4][3], kxquat[4][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
+    double kxpos[4][3], kxquat[2][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
     double M[NTRI], L[NTRI], invd[WD];
     double qd[WD], bias[WD], tau[WD], qacc0[WD], a[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
     double Y[WC * YS];
     alignas(16) double f[WC];   // gradient of the penalties per row; also the column buffer of w_factor_solve
     double gpos[WG][3];
-    double gmat[DMAXGM][9];  // world rotation of the moving geoms whose local rotation is not the identity
-    double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP], csolref[WCP][2], csolimp[WCP][5];
+    static constexpr int WGM = WG <= 32 ? 2 : DMAXGM;
+    double gmat[WGM][9];     // world rotation of the moving geoms whose local rotation is not the identity
+    double cpos[WCP][3], cn[WCP][3], cdist[WCP], cmargin[WCP], cmu[WCP];
     int cga[WCP], cgb[WCP], csig[WCP];
     double wa[WD];           // warm start: acceleration of the previous substep (mjData.qacc_warmstart)
     int wn;                  // ... and whether it exists
     int blk[WD];             // first dof of the kinematic tree that owns each dof
-    int cand[WCAND];
+    unsigned short cand[WCAND];
     int ncand, ncp;
 };
 
@@ -300,7 +301,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
     if (lane < 4) {
         const int b = lane == 0 ? keep_bodies.x : (lane == 1 ? keep_bodies.y : (lane == 2 ? keep_bodies.z : keep_bodies.w));
         for (int k = 0; k < 3; k++) W.kxpos[lane][k] = W.k.xpos[b][k];
-        for (int k = 0; k < 4; k++) W.kxquat[lane][k] = W.k.xquat[b][k];
+        if (lane < 2) for (int k = 0; k < 4; k++) W.kxquat[lane][k] = W.k.xquat[b][k];
         for (int k = 0; k < 9; k++) W.kxmat[lane][k] = W.k.xmat[b][k];
     }
     STAGE_SYNC(1);   // 1: kinematics done
@@ -611,8 +612,6 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
                         W.cdist[slot] = src[qn].dist;
                         W.cmargin[slot] = margin;
                         W.cmu[slot] = fa > fb ? fa : fb;
-                        for (int k = 0; k < 2; k++) W.csolref[slot][k] = 0.5 * (mg->g_solref[a][k] + mg->g_solref[b][k]);
-                        for (int k = 0; k < 5; k++) W.csolimp[slot][k] = 0.5 * (mg->g_solimp[a][k] + mg->g_solimp[b][k]);
                         W.cga[slot] = a; W.cgb[slot] = b;
                         W.csig[slot] = W.cand[ci] * 16 + qn * 4;
                     }
@@ -658,8 +657,11 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             type = dirn == 0 ? 1 : 2;
             sig = W.csig[c] + dirn;
             pos = W.cdist[c]; margin = W.cmargin[c]; mu = W.cmu[c];
-            solref[0] = W.csolref[c][0]; solref[1] = W.csolref[c][1];
-            for (int j = 0; j < 5; j++) solimp[j] = W.csolimp[c][j];
+            {   // pair parameters: mean of the two geoms (solmix 1 : 1)
+                const int ga_ = W.cga[c], gb_ = W.cgb[c];
+                for (int j = 0; j < 2; j++) solref[j] = 0.5 * (mg->g_solref[ga_][j] + mg->g_solref[gb_][j]);
+                for (int j = 0; j < 5; j++) solimp[j] = 0.5 * (mg->g_solimp[ga_][j] + mg->g_solimp[gb_][j]);
+            }
             double n[3] = {W.cn[c][0], W.cn[c][1], W.cn[c][2]}, t1[3], t2[3], ref[3] = {0, 0, 0}, cp[3] = {W.cpos[c][0], W.cpos[c][1], W.cpos[c][2]};
             ref[fabs(n[0]) < 0.7 ? 0 : 1] = 1.0;
             d_cross(t1, n, ref);
@@ -1098,18 +1100,21 @@ static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, int ngm, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
                             int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                             const int32_t *ids, cudaStream_t stream) {
     static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
     if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
-    if (nb <= 14 && ngeom <= 32 && small_warps)
+    const bool small = nb <= 14 && ngeom <= 32 && ngm <= WarpWS<14, 32, 24>::WGM;
+    if (small && small_warps)
         return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
-    if (nb <= 14 && ngeom <= 32)
+    if (small)
         return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
 }
 
+// 14 workspaces + one 1-warp planner CTA (<= 18 KB + 1 KB reserved each) must fit the 228 KB of an SM together
+static_assert(sizeof(WarpWS<14, 32, 24>) * 14 + 1024 + 19 * 1024 <= 228 * 1024, "env CTA leaves no room for a co-resident planner CTA");
 size_t env_warp_smem_per_warp() { return sizeof(WarpWS<14, 32, 24>); }
 
 }  // namespace mopa

@@ -273,7 +273,8 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
     W.frames = wbase + PW_STATES * W.row_pad;
     float *baseq = W.frames + (size_t)ff * PW_STATES;
 
-    for (int prob = blockIdx.x * PLAN_WARPS + warp; prob < n; prob += gridDim.x * PLAN_WARPS) {
+    const int cta_warps = blockDim.x >> 5;   // 8 for stand-alone batches; 1 when the CTAs are meant to co-reside with the env-step kernel
+    for (int prob = blockIdx.x * cta_warps + warp; prob < n; prob += gridDim.x * cta_warps) {
         const float *srow = start + (size_t)prob * row_stride, *grow_ = goal + (size_t)prob * row_stride;
         for (int i = lane; i < sp.nq; i += 32) baseq[i] = srow[i];  // passive dims frozen at the start values
         __syncwarp();
@@ -417,8 +418,9 @@ static cudaError_t ensure_trees(mopa_planner *p, size_t n, int max_nodes) {
 
 cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_goal, int row_stride, const unsigned long long *d_keys,
                         int n, int max_iter, float *d_path, int *d_node_ids, int max_path, int *d_path_len, int *d_status,
-                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n) {
+                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n, int cta_warps) {
     if (n <= 0) return cudaSuccess;
+    if (cta_warps < 1 || cta_warps > PLAN_WARPS) cta_warps = PLAN_WARPS;
     cudaError_t e = ensure_trees(p, (size_t)n, p->max_nodes);
     if (e != cudaSuccess) return e;
     PlanBuffers *b = (PlanBuffers *)p->plan_buffers;
@@ -433,17 +435,17 @@ cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_go
     }
     const SceneHeader &H = p->scene.hdr;
     size_t per_warp = ((size_t)PW_STATES * (H.nq + 1) + (size_t)H.frame_floats * PW_STATES + H.nq) * sizeof(float);
-    size_t smem = (size_t)H.blob_bytes + per_warp * PLAN_WARPS + 16;
+    size_t smem = (size_t)H.blob_bytes + per_warp * cta_warps + 16;
     static bool attr_set = false;
     if (!attr_set) {
         e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int grid = (n + PLAN_WARPS - 1) / PLAN_WARPS;
-    int max_grid = p->sm_count * 4;
+    int grid = (n + cta_warps - 1) / cta_warps;
+    int max_grid = cta_warps == 1 ? p->sm_count * 2 : p->sm_count * 4;
     if (grid > max_grid) grid = max_grid;
-    plan_kernel<<<grid, PLAN_WARPS * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
+    plan_kernel<<<grid, cta_warps * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
                                                         b->tree_x, b->tree_parent, b->max_nodes, d_path, d_node_ids, max_path,
                                                         d_path_len, d_status, d_iters, d_nodes, d_n);
     return cudaGetLastError();

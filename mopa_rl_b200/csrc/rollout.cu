@@ -484,7 +484,9 @@ struct mopa_rollout {
     bool inflight = false;
     int max_iter = 1000;
     cudaStream_t plan_stream = nullptr;
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_plan0 = nullptr;
+    double rrt_last_ms = 0, rrt_sum_ms = 0;   // device time of the finished RRT batches
+    long long rrt_batches = 0, tick_launched = 0, rrt_sum_ticks = 0;
     std::vector<void *> allocs;
     long long launches = 0;      // kernels of this library launched so far
     static constexpr int EV_RING = 256;
@@ -563,7 +565,8 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
 #undef A
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->plan_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&r->ev_done);
+    if (e == cudaSuccess) e = cudaEventCreate(&r->ev_plan0);
     for (int k = 0; k < mopa_rollout::EV_RING && e == cudaSuccess; k++) { e = cudaEventCreate(&r->ev_env0[k]); if (e == cudaSuccess) e = cudaEventCreate(&r->ev_env1[k]); }
     // episode counters start at 1: episode 0 was drawn by the initial reset of the environments
     if (e == cudaSuccess) {
@@ -587,6 +590,7 @@ void mopa_rollout_destroy(mopa_rollout *r) {
     if (r->plan_stream) cudaStreamDestroy(r->plan_stream);
     if (r->ev_ready) cudaEventDestroy(r->ev_ready);
     if (r->ev_done) cudaEventDestroy(r->ev_done);
+    if (r->ev_plan0) cudaEventDestroy(r->ev_plan0);
     for (int k = 0; k < mopa_rollout::EV_RING; k++) { if (r->ev_env0[k]) cudaEventDestroy(r->ev_env0[k]); if (r->ev_env1[k]) cudaEventDestroy(r->ev_env1[k]); }
     delete r;
 }
@@ -596,6 +600,10 @@ static int ro_finalize_rrt(mopa_rollout *r, cudaStream_t st) {
     RrtBatch &Q = r->batch[1 - r->fill];
     const int warps_blocks = (S.rrt_cap * 32 + 127) / 128, H = S.max_path - 1;
     RO_TRY(cudaStreamWaitEvent(st, r->ev_done, 0));
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r->ev_plan0, r->ev_done) == cudaSuccess) { r->rrt_last_ms = ms; r->rrt_sum_ms += ms; r->rrt_batches += 1; r->rrt_sum_ticks += r->ticks - r->tick_launched; }
+    }
     ro_rrt_densify_kernel<<<warps_blocks, 128, 0, st>>>(S, Q);
     RO_TRY(launch_is_valid(r->planner->d_blob, r->planner->scene.hdr, Q.dens32, S.row, S.rrt_cap * H * S.kmax, Q.dens_res, 0,
                            r->planner->sm_count, st, Q.cnt, H * S.kmax));
@@ -613,6 +621,9 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     RoDev &S = r->S;
     RO_TRY(cudaSetDevice(r->env->device));
+    // Keep the host at most one tick ahead of the device: the decision to finalise the RRT batch is taken on the host
+    // (event query), so a host that has queued many ticks would see the planner's progress that many ticks late.
+    if (r->ticks >= 2) RO_TRY(cudaEventSynchronize(r->ev_env1[(r->ticks - 2) % mopa_rollout::EV_RING]));
     if (r->inflight) {
         cudaError_t q = wait_rrt ? cudaEventSynchronize(r->ev_done) : cudaEventQuery(r->ev_done);
         if (q == cudaSuccess) { int rc = ro_finalize_rrt(r, st); if (rc) return rc; }
@@ -621,7 +632,7 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
     const int blocks = (S.n + 127) / 128;
     ro_pre_kernel<<<blocks, 128, 0, st>>>(S, r->buf, r->env->h_model.nv);
     RO_TRY(cudaGetLastError());
-    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->task, r->buf, nullptr, 0, nullptr,
+    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->h_model.ngm, r->env->task, r->buf, nullptr, 0, nullptr,
                            S.reset_flag, S.n, 1, nullptr, st));
     r->launches += 2;
     return MOPA_OK;
@@ -649,8 +660,10 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
         // hand the filled batch to the planner stream (it runs under the env-step kernels); start filling the other one
         RO_TRY(cudaEventRecord(r->ev_ready, st));
         RO_TRY(cudaStreamWaitEvent(r->plan_stream, r->ev_ready, 0));
+        RO_TRY(cudaEventRecord(r->ev_plan0, r->plan_stream));
+        r->tick_launched = r->ticks;
         RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
-                           r->plan_stream, Q.cnt));
+                           r->plan_stream, Q.cnt, 1));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
         RO_TRY(cudaEventRecord(r->ev_done, r->plan_stream));
         r->inflight = true;
         r->launches += 1;
@@ -661,7 +674,7 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
     RO_TRY(cudaGetLastError());
     const int ev = (int)(r->ticks % mopa_rollout::EV_RING);
     RO_TRY(cudaEventRecord(r->ev_env0[ev], st));
-    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->task, r->buf, S.step_action, 8, S.step_mode,
+    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->h_model.ngm, r->env->task, r->buf, S.step_action, 8, S.step_mode,
                            S.step_mask, S.n, 0, S.ids, st));
     RO_TRY(cudaEventRecord(r->ev_env1[ev], st));
     ro_post_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
@@ -673,6 +686,16 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
 
 /* 1 while an RRT batch is in flight or problems are queued behind it (host view; the queue length lives on the device). */
 int mopa_rollout_busy(mopa_rollout *r) { return r && r->inflight ? 1 : 0; }
+
+/* Diagnostics of the asynchronous planner: out[0] = device ms of the last finished RRT batch, out[1] = batches finished,
+ * out[2] = mean device ms per batch, out[3] = mean ticks between launch and finalisation. */
+int mopa_rollout_rrt_stats(mopa_rollout *r, double *out4) {
+    if (!r || !out4) return MOPA_ERR_ARG;
+    out4[0] = r->rrt_last_ms; out4[1] = (double)r->rrt_batches;
+    out4[2] = r->rrt_batches ? r->rrt_sum_ms / r->rrt_batches : 0.0;
+    out4[3] = r->rrt_batches ? (double)r->rrt_sum_ticks / r->rrt_batches : 0.0;
+    return MOPA_OK;
+}
 
 /* Kernels of this library launched so far by the handle. */
 int64_t mopa_rollout_launches(mopa_rollout *r) { return r ? r->launches : 0; }

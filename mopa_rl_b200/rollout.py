@@ -596,6 +596,13 @@ class NativeMoPARolloutRunner:
     def launches(self):
         return int(self._L.mopa_rollout_launches(self.h))
 
+    def rrt_stats(self):
+        """(last batch ms, batches finished, mean ms per batch, mean ticks from launch to finalisation)."""
+        out = (_C.c_double * 4)()
+        self._L.mopa_rollout_rrt_stats.argtypes = [_C.c_void_p, _C.c_void_p]
+        self._check(self._L.mopa_rollout_rrt_stats(self.h, out))
+        return tuple(out)
+
     def env_kernel_ms(self, n_last):
         """Mean device time of the env-step kernel over the latest ``n_last`` ticks (synchronises)."""
         out = _C.c_double()

@@ -13,6 +13,6 @@ for k in range(1, ticks + 1):
     if k % 25 == 0:
         c = r.counters; t1 = time.perf_counter()
         print("ticks %4d  %.1f ms/tick  env-steps/s %7.0f  waiting %4d  rrt queued %5d done %5d  episodes %d" % (
-            k, (t1 - t0) / 25 * 1e3, (c["env_steps"] - prev["env_steps"]) / (t1 - t0), c["waiting"], c["rrt_problems"], c["mp"] + c["approximate"], c["episodes"]))
+            k, (t1 - t0) / 25 * 1e3, (c["env_steps"] - prev["env_steps"]) / (t1 - t0), c["waiting"], c["rrt_problems"], c["mp"] + c["approximate"], c["episodes"]), " rrt batches: last %.1f ms, n %d, mean %.1f ms, %.1f ticks" % r.rrt_stats())
         prev, t0 = c, time.perf_counter()
 print(r.counters)
