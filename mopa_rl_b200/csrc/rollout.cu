@@ -48,7 +48,7 @@ struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being fil
 };
 
 struct RoDev {   // everything the kernels need, passed by value
-    int n, nq, row, max_traj, max_path, kmax, rrt_cap, num_trials, invalid_target_handling, interpolation;
+    int n, nq, row, max_traj, max_path, kmax, rrt_cap, num_trials, invalid_target_handling, interpolation, task_kind;
     double omega, action_range, ac_scale, discount, step_size, joint_margin, range;
     unsigned long long seed_env;
     long long env_id_offset;
@@ -130,7 +130,8 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                 double *q = B.qpos + (size_t)e * S.nq;
                 for (int k = 0; k < S.nq; k++) q[k] = S.qpos0[k];
                 for (int k = 0; k < 7; k++) q[S.arm_qadr[k]] = S.init_qpos[k] + 0.02 * ro_normal(S.seed_env, gid, ep, (unsigned long long)k);
-                for (int k = 0; k < 2; k++) q[S.target_qadr[k]] += -0.01 + 0.02 * ro_uniform(S.seed_env, gid, ep, 100ULL + k);
+                if (S.task_kind == 0)   // push: the target slides (sawyer_push_obstacle.py:41-47)
+                    for (int k = 0; k < 2; k++) q[S.target_qadr[k]] += -0.01 + 0.02 * ro_uniform(S.seed_env, gid, ep, 100ULL + k);
                 for (int k = 0; k < nv; k++) B.qvel[(size_t)e * nv + k] = 0.0;
                 S.episode_idx[e] += 1;
                 B.ep_len[e] = 0; B.ep_rew[e] = 0.0; B.done[e] = 0; B.success[e] = 0;
@@ -532,6 +533,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.n = n; S.nq = nq; S.row = row; S.max_traj = cfg->max_traj; S.max_path = cfg->max_path; S.kmax = (int)(cfg->range / lim) + 1;
     S.rrt_cap = cfg->rrt_capacity; S.num_trials = cfg->num_trials; S.invalid_target_handling = cfg->invalid_target_handling;
     S.interpolation = cfg->interpolation;
+    S.task_kind = env->task.kind;
     S.omega = cfg->omega; S.action_range = cfg->action_range; S.ac_scale = cfg->ac_scale; S.discount = cfg->discount;
     S.step_size = cfg->step_size; S.joint_margin = cfg->joint_margin; S.range = cfg->range;
     S.seed_env = cfg->seed_env; S.env_id_offset = cfg->env_id_offset;

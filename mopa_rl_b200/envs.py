@@ -135,6 +135,9 @@ class VecSawyerPushObstacle:
     """N device-resident SawyerPushObstacle-v0 environments."""
     ENV_ID = "SawyerPushObstacle-v0"
     OBS_DIM = 40
+    INIT_QPOS = PUSH_INIT_QPOS
+    STATIC_BODIES = ("table", "bin1")          # SawyerPushObstacleEnv.static_bodies
+    MANIPULATION_BODIES = ("cube",)            # bodies whose geoms may touch the static ones (manipulation_geom_ids)
     make_task = staticmethod(make_push_task)
     reset_state = staticmethod(push_reset_state)
 
@@ -257,5 +260,8 @@ class VecSawyerAssemblyObstacle(VecSawyerPushObstacle):
     hole3, pegHead3, pegEnd3, peg_quat4 (env/sawyer/sawyer_assembly_obstacle.py:53-59)."""
     ENV_ID = "SawyerAssemblyObstacle-v0"
     OBS_DIM = 38
+    INIT_QPOS = ASSEMBLY_INIT_QPOS
+    STATIC_BODIES = ("table",)                 # sawyer_assembly_obstacle.py:61-67
+    MANIPULATION_BODIES = ("furniture", "0_part0", "1_part1", "4_part4", "2_part2")
     make_task = staticmethod(make_assembly_task)
     reset_state = staticmethod(assembly_reset_state)

@@ -49,16 +49,26 @@ class MoPAConfig:
             setattr(self, k, v)
 
 
-def planner_inputs(model, static_bodies=("table", "bin1"), manipulation_geoms=("cube",)):
-    """ignored contact pairs / passive joints as rl/trainer.py:62-75 derives them."""
-    static_ids = [g for g in range(model.ngeom) if model.names["body"][model.geom_bodyid[g]] in static_bodies]
+def planner_inputs(model, static_bodies=("table", "bin1"), manipulation_geoms=("cube",), manipulation_bodies=None):
+    """ignored contact pairs / passive joints as rl/trainer.py:62-75 derives them: every geom of the manipulation
+    bodies (env.manipulation_geom_ids) against every geom of the static bodies (env.static_geom_ids)."""
+    body_of = lambda g: model.names["body"][model.geom_bodyid[g]]
+    static_ids = [g for g in range(model.ngeom) if body_of(g) in static_bodies]
+    if manipulation_bodies is not None:
+        manip = [g for g in range(model.ngeom) if body_of(g) in manipulation_bodies]
+    else:
+        manip = [model.geom_name2id(name) for name in manipulation_geoms]
     ignored = []
-    for name in manipulation_geoms:
-        mg = model.geom_name2id(name)
+    for mg in manip:
         ignored += [(min(mg, g), max(mg, g)) for g in static_ids]
     ref = [model.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
     passive = [i for i in range(model.nq) if i not in ref]
     return ignored, passive, ref
+
+
+def env_planner_inputs(venv_cls, model):
+    """planner_inputs for a vectorised env class (STATIC_BODIES / MANIPULATION_BODIES)."""
+    return planner_inputs(model, static_bodies=venv_cls.STATIC_BODIES, manipulation_bodies=venv_cls.MANIPULATION_BODIES)
 
 
 class UniformPolicy:
@@ -498,12 +508,11 @@ class NativeMoPARolloutRunner:
         import torch
 
         from .capi import check, lib
-        from .envs import PUSH_INIT_QPOS
 
         self.torch, self.venv, self.cfg = torch, venv, config or MoPAConfig()
         cfg, m, dev = self.cfg, venv.model, venv.dev
         self.dev = dev
-        ignored, passive, ref = planner_inputs(m)
+        ignored, passive, ref = env_planner_inputs(type(venv), m)
         self.planner = NativePlanner(m, passive, ignored, cfg.contact_threshold, cfg.range, 0.005, cfg.seed, venv.device_index)
         self.policy = policy or UniformPolicy(torch, dev, cfg.seed + 17 * int(venv.env_ids[0]))
         n = venv.n
@@ -522,7 +531,7 @@ class NativeMoPARolloutRunner:
         c.step_size, c.joint_margin, c.range = cfg.step_size, cfg.joint_margin, cfg.range
         c.seed_env, c.env_id_offset = venv.seed, int(venv.env_ids[0])
         for k in range(7):
-            c.jnt_lo[k], c.jnt_hi[k], c.init_qpos[k] = float(m.jnt_range[jid[k], 0]), float(m.jnt_range[jid[k], 1]), float(PUSH_INIT_QPOS[k])
+            c.jnt_lo[k], c.jnt_hi[k], c.init_qpos[k] = float(m.jnt_range[jid[k], 0]), float(m.jnt_range[jid[k], 1]), float(venv.INIT_QPOS[k])
         self._qpos0 = np.ascontiguousarray(m.qpos0, dtype=np.float64)
         c.qpos0 = self._qpos0.ctypes.data
         L = lib()

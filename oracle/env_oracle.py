@@ -65,16 +65,8 @@ class PushEnvOracle:
         return np.concatenate([q[self.ref_q], v[self.ref_v], q[self.grip_q], v[self.grip_v], eef, eq[[1, 2, 3, 0]], target, cube,
                                cq[[1, 2, 3, 0]], eef - cube, cube[:2] - target[:2]])
 
-    def step(self, action, is_planner=False):
-        action = np.asarray(action, np.float64)
-        if not is_planner or self.prev_state is None:
-            self.prev_state = self.qpos[self.ref_q].copy()
-        a = action[:7] if is_planner else action[:7] * self.ac_scale
-        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
-        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
-            self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
-        self.prev_state = desired.copy()
-        # compute_reward
+    def _reward(self):
+        """SawyerPushObstacleEnv.compute_reward (:71-100) -> (reward, terminal)."""
         gs = 0.5 * (self._site(self.b_rc, self.s_re) + self._site(self.b_lc, self.s_le))
         cube = self.xpos[self.b_cube]
         target = self.target_base + np.array([self.qpos[self.tgt_q[0]], self.qpos[self.tgt_q[1]], 0.0])
@@ -88,6 +80,18 @@ class PushEnvOracle:
         if d_ct < self.dthr:
             reward += self.succ_rew
             self.success, terminal = True, True
+        return reward, terminal
+
+    def step(self, action, is_planner=False):
+        action = np.asarray(action, np.float64)
+        if not is_planner or self.prev_state is None:
+            self.prev_state = self.qpos[self.ref_q].copy()
+        a = action[:7] if is_planner else action[:7] * self.ac_scale
+        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
+        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
+            self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
+        self.prev_state = desired.copy()
+        reward, terminal = self._reward()   # compute_reward
         ob = self.obs()
         # _after_step
         clipped = False
@@ -108,19 +112,7 @@ class PushEnvOracle:
         """Planner failure (rl/mopa_rollouts.py:304-327): compute_reward(zeros) + _after_step, no simulation.
         Frames are refreshed by a forward pass first (the device path does the same)."""
         self.set_state(self.qpos, self.qvel)
-        gs = 0.5 * (self._site(self.b_rc, self.s_re) + self._site(self.b_lc, self.s_le))
-        cube = self.xpos[self.b_cube]
-        target = self.target_base + np.array([self.qpos[self.tgt_q[0]], self.qpos[self.tgt_q[1]], 0.0])
-        d_gc, d_ct = np.linalg.norm(cube - gs), np.linalg.norm(cube[:2] - target[:2])
-        reward = 0.0
-        if d_ct < 0.1:
-            reward += 0.5 * (1 - np.tanh(5 * d_ct))
-        if d_gc < 0.1:
-            reward += 0.1 * (1 - np.tanh(10 * d_gc))
-        terminal = False
-        if d_ct < self.dthr:
-            reward += self.succ_rew
-            self.success, terminal = True, True
+        reward, terminal = self._reward()
         self.ep_rew += reward
         self.ep_len += 1
         if self.ep_len == self.max_steps:
@@ -171,28 +163,3 @@ class AssemblyEnvOracle(PushEnvOracle):
             reward += self.succ_rew
             self.success, terminal = True, True
         return reward, terminal
-
-    def step(self, action, is_planner=False):
-        action = np.asarray(action, np.float64)
-        if not is_planner or self.prev_state is None:
-            self.prev_state = self.qpos[self.ref_q].copy()
-        a = action[:7] if is_planner else action[:7] * self.ac_scale
-        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
-        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
-            self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
-        self.prev_state = desired.copy()
-        reward, terminal = self._reward()
-        ob = self.obs()
-        clipped = False
-        for qa, (lo, hi) in self.lim:
-            if self.qpos[qa] < lo or self.qpos[qa] > hi:
-                self.qpos[qa] = min(max(self.qpos[qa], lo), hi)
-                clipped = True
-        if clipped:
-            self.set_state(self.qpos, self.qvel)
-        self.ep_rew += reward
-        self.ep_len += 1
-        if self.ep_len == self.max_steps:
-            terminal = True
-        self.terminal = terminal
-        return ob, reward, terminal

@@ -15,15 +15,17 @@ from __future__ import annotations
 
 import numpy as np
 
-from .env_oracle import PushEnvOracle
+from .env_oracle import AssemblyEnvOracle, PushEnvOracle
 from .oracle import OraclePlanner, OracleScene, space_from_model
 
 
 class ScalarMoPARunner:
-    def __init__(self, model, dynmodel, cfg, ignored, passive, env_gid, seed_env, policy, contacts=True, max_episode_steps=250):
+    def __init__(self, model, dynmodel, cfg, ignored, passive, env_gid, seed_env, policy, contacts=True, max_episode_steps=250, task="push"):
         """policy(env_gid, macro_index) -> action (7,) in [-1, 1]."""
         self.m, self.cfg, self.gid, self.policy = model, cfg, int(env_gid), policy
-        self.env = PushEnvOracle(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
+        self.task = task
+        env_cls = AssemblyEnvOracle if task == "assembly" else PushEnvOracle
+        self.env = env_cls(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
         self.scene = OracleScene(model, ignored, cfg.contact_threshold, "f32")
         adr, lo, hi, so2 = space_from_model(model, passive)
         self.planner = OraclePlanner(self.scene, adr, lo, hi, so2, cfg.range, 0.005, cfg.seed, max_nodes=4096)
@@ -39,9 +41,9 @@ class ScalarMoPARunner:
         self.ob = self._reset()
 
     def _reset(self):
-        from mopa_rl_b200.envs import push_reset_state  # reset draws are input data shared with the product
+        from mopa_rl_b200.envs import assembly_reset_state, push_reset_state  # reset draws are input data shared with the product
 
-        q, v = push_reset_state(self.m, self.seed_env, [self.gid], [self.episode])
+        q, v = (assembly_reset_state if self.task == "assembly" else push_reset_state)(self.m, self.seed_env, [self.gid], [self.episode])
         self.episode += 1
         return self.env.reset_to(q[0], v[0])
 
@@ -163,5 +165,6 @@ class ScalarMoPARunner:
         env.prev_state = None                                       # env._reset_prev_state()
         self.env_steps += steps
         rec = np.zeros(92, np.float32)
-        rec[0:40], rec[40:47], rec[48], rec[49], rec[50], rec[52:92] = prev_ob, ac, rec_rew, float(done), intra, self.ob
+        no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
+        rec[0:no], rec[40:47], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
         return rec

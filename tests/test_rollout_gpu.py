@@ -51,3 +51,49 @@ def test_vectorised_runner_matches_scalar_reference_loop(push_model, oracle_buil
             kinds.add("plan" if r[50] > 0 else "single")
     assert kinds == {"plan", "single"}
     print("vectorised vs scalar runner: %d transitions, worst |obs diff| %.2e, counters %s" % (len(rec), worst, runner.counters))
+
+
+def test_native_runner_assembly_matches_scalar_reference_loop(oracle_built):
+    """Same conformance check on SawyerAssemblyObstacle-v0 (BASELINE configs[3]: planner-heavy scene, 39 collidable
+    geoms, ignored pairs = furniture parts x table)."""
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, env_planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    model = load_model("SawyerAssemblyObstacle-v0")
+    n, ticks, seed = 8, 40, 977
+    cfg = MoPAConfig(max_iter=150, seed=5)
+    venv = VecSawyerAssemblyObstacle(n, seed=seed, max_episode_steps=20, env_id_offset=40)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 11))
+    for _ in range(ticks):
+        runner.tick()
+    runner.drain()
+    torch.cuda.synchronize()
+    rec = runner.transitions[:runner.n_transitions].cpu().numpy()
+    assert len(rec) > n
+
+    def policy(gid, k):
+        u = rng.uniform01(11, np.uint64(gid), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ignored, passive, _ = env_planner_inputs(VecSawyerAssemblyObstacle, model)
+    dm = DynModel(model)
+    worst = 0.0
+    for e in range(n):
+        gid = 40 + e
+        mine = rec[rec[:, 51] == gid]
+        ref = ScalarMoPARunner(model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=20, task="assembly")
+        for k, r in enumerate(mine):
+            o = ref.macro_step()
+            assert np.array_equal(r[40:47], o[40:47]), (e, k)
+            assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])
+            assert abs(r[48] - o[48]) < 1e-5, (e, k)
+            d = max(np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+            worst = max(worst, d)
+            assert d < 1e-4, (e, k, d)
+    print("assembly: native vs scalar runner: %d transitions, worst |obs diff| %.2e, counters %s" % (len(rec), worst, runner.counters))
