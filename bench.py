@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "env-steps/sec (incl. planner) SawyerPushObstacle-v0"
+METRIC_ASSEMBLY = "env-steps/sec (incl. planner) SawyerAssemblyObstacle-v0"
 WORKLOADS = {
     "rollout": "SawyerPushObstacle-v0 MoPA (omega 0.7, action_range 0.5, RRT-Connect range 0.1), %d vectorised envs per GPU, uniform random-exploration policy",
     "validity": "config5 collision-check microbench: SawyerPushObstacle-v0, %d random 7-DoF qpos state-validity queries per GPU, contact_threshold -0.002, cube x {table,bin1} ignored",
@@ -125,36 +126,38 @@ def synth_qpos_f32(model, ref, n, seed, pad):
 # ----------------------------------------------------------------------------- CPU arms (the oracle = C/numpy restatement
 # of the reference path; MuJoCo 2.0 + OMPL cannot be built here)
 def _cpu_rollout_worker(args):
-    gid, macros, seed, max_iter = args
+    gid, macros, seed, max_iter, task = args
     sys.path.insert(0, ROOT)
     from mopa_rl_b200 import rng
     from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.model import load_model
-    from mopa_rl_b200.rollout import MoPAConfig, planner_inputs
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import MoPAConfig, env_planner_inputs
     from oracle.rollout_oracle import ScalarMoPARunner
 
-    model = load_model("SawyerPushObstacle-v0")
-    ignored, passive, _ = planner_inputs(model)
+    cls = VecSawyerAssemblyObstacle if task == "assembly" else VecSawyerPushObstacle
+    model = load_model(cls.ENV_ID)
+    ignored, passive, _ = env_planner_inputs(cls, model)
 
     def policy(g, k):
         u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter), ignored, passive, gid, seed, policy)
+    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter), ignored, passive, gid, seed, policy, task=task)
     t0 = time.perf_counter()
     for _ in range(macros):
         r.macro_step()
     return r.env_steps, time.perf_counter() - t0
 
 
-def cpu_rollout_rate(cores, macros, seed, max_iter, base_gid=0):
+def cpu_rollout_rate(cores, macros, seed, max_iter, base_gid=0, task="push"):
     """One scalar runner (env + planner, like one MPI rank of the reference) per host core."""
     from oracle import oracle
 
     oracle.build()
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_rollout_worker, [(base_gid + i, macros, seed, max_iter) for i in range(cores)])
+        res = pool.map(_cpu_rollout_worker, [(base_gid + i, macros, seed, max_iter, task) for i in range(cores)])
     wall = time.perf_counter() - t0
     steps = sum(s for s, _ in res)
     busy = max(t for _, t in res)
@@ -199,13 +202,14 @@ def run_reference_arm(args):
     else:
         rates = []
         for step in range(args.warmup + args.steps):
-            rate, steps, busy, wall = cpu_rollout_rate(cores, args.ref_macros, 1234, args.max_iter, base_gid=1000 * step)
+            rate, steps, busy, wall = cpu_rollout_rate(cores, args.ref_macros, 1234, args.max_iter, base_gid=1000 * step, task=args.task)
             if step >= args.warmup:
                 rates.append((rate, busy))
         value, ms = float(np.mean([r for r, _ in rates])), float(np.mean([d for _, d in rates]) * 1e3)
-        metric, unit = METRIC, "env-steps/s"
+        metric, unit = (METRIC if args.task == "push" else METRIC_ASSEMBLY), "env-steps/s"
         sample = "%d macro actions per scalar runner per step, one runner (env + planner) per host core" % args.ref_macros
-        cfg = {"workload": WORKLOADS["rollout"] % args.envs, "max_iter": args.max_iter}
+        wl = WORKLOADS["rollout"] % args.envs
+        cfg = {"workload": wl if args.task == "push" else wl.replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "max_iter": args.max_iter}
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -238,9 +242,11 @@ def run_rollout(args):
     import torch
     import torch.distributed as dist
 
-    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerPushObstacle
     from mopa_rl_b200.replay import ReplicatedReplay
     from mopa_rl_b200.rollout import MoPAConfig, NativeMoPARolloutRunner
+
+    env_cls = VecSawyerAssemblyObstacle if args.task == "assembly" else VecSawyerPushObstacle
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -257,7 +263,7 @@ def run_rollout(args):
         torch.cuda.synchronize()
 
     def make(policy=None):
-        venv = VecSawyerPushObstacle(n, seed=1234, device=local_rank, env_id_offset=rank * n)
+        venv = env_cls(n, seed=1234, device=local_rank, env_id_offset=rank * n)
         return NativeMoPARolloutRunner(venv, cfg, policy=policy)
 
     def timed(runner, replay, h_trans=None, h_flags=None):
@@ -317,12 +323,12 @@ def run_rollout(args):
         bytes_per_env_step = 816  # 352 B state/action in + 464 B state/obs out
         achieved = bytes_per_env_step * n / (k_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter)
+        cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter, task=args.task)
         line = {
-            "metric": METRIC, "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.task == "push" else METRIC_ASSEMBLY, "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 collision", "data": "synthetic",
-            "config": {"workload": WORKLOADS["rollout"] % n, "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
+            "config": {"workload": (WORKLOADS["rollout"] % n) if args.task == "push" else (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
                        "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
                        "device_ms_per_step": dev_ms / args.steps, "counters": counters},
             "clocks": clocks,
@@ -330,7 +336,8 @@ def run_rollout(args):
                     "d2h_bytes_per_step": hp.d2h / e2e_ticks + d2h_tr / args.steps,
                     "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("r1_envwarp_v3_traffic.json"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("r1_envwarp_v3_traffic.json") if args.task == "push" else None,
                          "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
@@ -439,6 +446,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
+    ap.add_argument("--task", default="push", choices=["push", "assembly"],
+                    help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3])")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
     ap.add_argument("--cpu-macros", type=int, default=24, help="macro actions per scalar runner in the cpu_baseline leg")
     ap.add_argument("--ref-macros", type=int, default=16, help="macro actions per scalar runner per step of --impl reference")
