@@ -280,6 +280,36 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
     }
 }
 
+// Conservative pre-test for the pairs that go to MPR (capsule / cylinder against capsule / cylinder / box): true when
+// the shapes are certainly more than 1e-4 apart, in which case MPR cannot report a penetration at all (the validity
+// predicate needs dist <= contact_threshold <= 0).  A cylinder lies inside the capsule with the same axis, radius and
+// half length, so segment distances minus the radii bound the true distance from below.  This never changes a result,
+// it only skips the expensive, badly diverging portal refinement for the many near-but-separate pairs.
+MOPA_HD bool mpr_certainly_separate(const Geom &a, const Geom &b) {
+    const float eps = 1e-4f;
+    if (b.kind == K_BOX) {   // a: capsule / cylinder.  Per box axis: gap between the slab and the projected segment
+        const V3 ax = col(a.R, 2), d = a.c - b.c;
+        const V3 l = mulMTV(b.R, d), al = mulMTV(b.R, ax);
+        const float gx = fmaxf(0.0f, (fabsf(l.x) - fabsf(al.x) * a.size.y) - b.size.x);
+        const float gy = fmaxf(0.0f, (fabsf(l.y) - fabsf(al.y) * a.size.y) - b.size.y);
+        const float gz = fmaxf(0.0f, (fabsf(l.z) - fabsf(al.z) * a.size.y) - b.size.z);
+        const float r = a.size.x + eps;
+        return fmaf(gz, gz, fmaf(gy, gy, gx * gx)) > r * r;
+    }
+    if (a.kind == K_BOX) return false;
+    // segment - segment distance (both are capsules / cylinders)
+    const V3 a1 = col(a.R, 2), a2 = col(b.R, 2), r = a.c - b.c;
+    const float h1 = a.size.y, h2 = b.size.y;
+    const float bb = dot(a1, a2), c = dot(a1, r), f = dot(a2, r), den = fmaf(-bb, bb, 1.0f);
+    float s = den > 1e-6f ? fminf(h1, fmaxf(-h1, fmaf(bb, f, -c) / den)) : 0.0f;
+    float t = fmaf(bb, s, f);
+    if (t < -h2) { t = -h2; s = fminf(h1, fmaxf(-h1, fmaf(bb, t, -c))); }
+    else if (t > h2) { t = h2; s = fminf(h1, fmaxf(-h1, fmaf(bb, t, -c))); }
+    const V3 w{fmaf(-t, a2.x, fmaf(s, a1.x, r.x)), fmaf(-t, a2.y, fmaf(s, a1.y, r.y)), fmaf(-t, a2.z, fmaf(s, a1.z, r.z))};
+    const float rr = a.size.x + b.size.x + eps;
+    return dot(w, w) > rr * rr;
+}
+
 // dispatch classes (pair of kinds, a.kind <= b.kind)
 enum PairClass : int {
     PC_PLANE_SPHERE = 0, PC_PLANE_CAPSULE, PC_PLANE_CYLINDER, PC_PLANE_BOX, PC_SPHERE_SPHERE, PC_SPHERE_CAPSULE,

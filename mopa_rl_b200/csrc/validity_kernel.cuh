@@ -127,6 +127,7 @@ __device__ __forceinline__ void load_geom(Geom &g, const GeomRec &r, const float
 // signed distance of a deferred (box-box / MPR) pair
 __device__ __forceinline__ float heavy_dist(int cls, const Geom &a, const Geom &b) {
     if (cls == PC_BOX_BOX) return box_box(a, b);
+    if (mpr_certainly_separate(a, b)) return MOPA_BIG;
     float depth;
     if (mpr_penetration(a, b, &depth)) return -depth;
     return MOPA_BIG;
