@@ -143,7 +143,7 @@ def _cpu_rollout_worker(args):
         u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter), ignored, passive, gid, seed, policy, task=task)
+    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15), ignored, passive, gid, seed, policy, task=task)
     t0 = time.perf_counter()
     for _ in range(macros):
         r.macro_step()
@@ -254,7 +254,7 @@ def run_rollout(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
-    cfg = MoPAConfig(max_iter=args.max_iter)
+    cfg = MoPAConfig(max_iter=args.max_iter, reuse_data=True, max_reuse_data=15)   # scripts/3d/push/mopa.sh
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,6 +272,7 @@ def run_rollout(args):
         for _ in range(args.warmup):
             runner.tick()
             replay.exchange_slab(*runner.last_emitted)
+            replay.exchange_slab(*runner.last_reused)
         barrier()
         l0, s0 = runner.launches, runner.env_steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,10 +281,13 @@ def run_rollout(args):
         for _ in range(args.steps):
             runner.tick()
             replay.exchange_slab(*runner.last_emitted)
-            if h_trans is not None:   # end-to-end arm: this tick's transition records back to pinned host memory
-                h_trans.copy_(runner.slab, non_blocking=True)
-                h_flags.copy_(runner.emit_flag, non_blocking=False)
-                d2h += n * 93 * 4 - n * 3
+            replay.exchange_slab(*runner.last_reused)
+            if h_trans is not None:   # end-to-end arm: this tick's transition records (main + relabelled) back to pinned host memory
+                h_trans[:n].copy_(runner.slab, non_blocking=True)
+                h_trans[n:].copy_(runner.reuse_slab, non_blocking=True)
+                h_flags[:n].copy_(runner.emit_flag, non_blocking=True)
+                h_flags[n:].copy_(runner.reuse_flag, non_blocking=False)
+                d2h += (n + n * runner.max_reuse) * (92 * 4 + 1)
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -304,8 +308,8 @@ def run_rollout(args):
     hp = HostLoopPolicy(torch, dev, 99 + rank, n)
     runner2 = make(policy=hp)
     replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20)
-    h_trans = torch.zeros(n, 92, dtype=torch.float32).pin_memory()
-    h_flags = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    h_trans = torch.zeros(n * (1 + runner2.max_reuse), 92, dtype=torch.float32).pin_memory()
+    h_flags = torch.zeros(n * (1 + runner2.max_reuse), dtype=torch.uint8).pin_memory()
     for _ in range(args.warmup):
         runner2.tick()
     hp.h2d = hp.d2h = 0
@@ -328,7 +332,7 @@ def run_rollout(args):
             "metric": METRIC if args.task == "push" else METRIC_ASSEMBLY, "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 collision", "data": "synthetic",
-            "config": {"workload": (WORKLOADS["rollout"] % n) if args.task == "push" else (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
+            "config": {"reuse_data": True, "max_reuse_data": 15, "workload": (WORKLOADS["rollout"] % n) if args.task == "push" else (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
                        "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
                        "device_ms_per_step": dev_ms / args.steps, "counters": counters},
             "clocks": clocks,

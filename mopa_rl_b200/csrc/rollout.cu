@@ -30,7 +30,7 @@ cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, c
 constexpr int RO_JMAX = 16;     // interpolation points checked per straight-line plan
 constexpr int RO_NQ = 40;       // qpos capacity (same as the env kernel)
 enum { C_MP = 0, C_RL, C_INTERP, C_MP_FAIL, C_APPROX, C_INVALID, C_DENSIFY_FALLBACK, C_EPISODES, C_SUCCESS, C_MP_PATH_LEN,
-       C_INTERP_PATH_LEN, C_ENV_STEPS, C_TRANSITIONS, C_RRT_DROPPED, C_RRT_PROBLEMS, C_WAITING, C_COUNT = 16 };
+       C_INTERP_PATH_LEN, C_ENV_STEPS, C_TRANSITIONS, C_RRT_DROPPED, C_RRT_PROBLEMS, C_WAITING, C_REUSED, C_COUNT = 18 };
 
 struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being filled / in flight)
     int *cnt;                    // problems queued (may exceed the capacity: clamp)
@@ -72,6 +72,14 @@ struct RoDev {   // everything the kernels need, passed by value
     int *cnt_plan, *cnt_back;    // device counters
     int *cnt_ids, *ids;          // [2], [n]: environments ordered for the env-step launch (expensive ones first, together)
     int heavy_work;              // Newton steps per env.step above which an environment counts as expensive
+    // reuse_data (rl/mopa_rollouts.py:223-302): per-step history of the plan being executed, relabelled records
+    int reuse_data, max_reuse;
+    unsigned long long seed_reuse;
+    float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
+    double *rew_hist;            // [n][max_traj]      cumulative discounted reward after step i
+    unsigned char *done_hist;    // [n][max_traj]
+    float *xslab;                // caller-owned [n][max_reuse][92] relabelled records of this tick
+    unsigned char *xflag;        // caller-owned [n][max_reuse]
     int *plan_env;               // [n]
     double *tgt64, *c64;         // [n][nq]
     float *q32a;                 // [n][row]          targets
@@ -108,6 +116,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
     if (e >= S.n) return;
     const bool need = S.traj_pos[e] >= S.traj_len[e];
     unsigned char emit = 0, reset = 0;
+    if (S.reuse_data) for (int k = 0; k < S.max_reuse; k++) S.xflag[(size_t)e * S.max_reuse + k] = 0;
     if (need) {
         if (S.pending[e]) {
             float *rec = S.slab + (size_t)e * 92;
@@ -123,6 +132,55 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
             const unsigned long long slot = atomicAdd((unsigned long long *)(S.counters + C_TRANSITIONS), 1ULL) % (unsigned long long)S.ring_cap;
             float *dst = S.ring + slot * 92;
             for (int k = 0; k < 92; k++) dst[k] = rec[k];
+            // reuse_data: resample (start, goal) waypoint pairs of the executed plan as extra SMDP transitions
+            const int L = S.executed[e];
+            if (S.reuse_data && S.kind[e] == 1 && L > 3) {
+                const unsigned long long gid = (unsigned long long)(S.env_id_offset + e), mi = (unsigned long long)(S.macro_index[e] - 1);
+                const int tries = L < S.max_reuse ? L : S.max_reuse;
+                int ps[16], pg[16], np_ = 0;
+                const double *tr = S.traj + (size_t)e * S.max_traj * 7;
+                const float *oh = S.ob_hist + (size_t)e * S.max_traj * 40;
+                const double *rh = S.rew_hist + (size_t)e * S.max_traj;
+                for (int t = 0; t < tries; t++) {
+                    // np.random.randint(0, L - 1), np.random.randint(start + 1, L) with counter-based draws
+                    int start = (int)(ro_uniform(S.seed_reuse, gid, mi, 2ULL * t) * (double)(L - 1));
+                    if (start > L - 2) start = L - 2;
+                    int goal = start + 1 + (int)(ro_uniform(S.seed_reuse, gid, mi, 2ULL * t + 1) * (double)(L - 1 - start));
+                    if (goal > L - 1) goal = L - 1;
+                    bool dup = false;
+                    for (int k = 0; k < np_; k++) if (ps[k] == start && pg[k] == goal) dup = true;
+                    if (dup) continue;
+                    ps[np_] = start; pg[np_] = goal; np_++;
+                    // env.form_action(traj[goal], traj[start]) -> SACAgent.invert_displacement (piecewise)
+                    float ia[7];
+                    bool planner_ac = false, valid_ac = true;
+                    for (int k = 0; k < 7; k++) {
+                        const double d = tr[goal * 7 + k] - tr[start * 7 + k], ad = fabs(d);
+                        const double a = ad < S.ac_scale ? d * (S.omega / S.ac_scale)
+                                                         : (d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0)) *
+                                                               ((ad - S.ac_scale) / ((S.action_range - S.ac_scale) / (1.0 - S.ac_scale)) / ((1.0 - S.ac_scale) / (1.0 - S.omega)) + S.omega);
+                        if (a < -S.omega || a > S.omega) planner_ac = true;
+                        if (a < -1.0 || a > 1.0) valid_ac = false;
+                        ia[k] = (float)a;
+                    }
+                    if (!planner_ac || !valid_ac) continue;
+                    const int xs = np_ - 1;   // slot of this pair among the tick's relabelled records of the environment
+                    float *xr = S.xslab + ((size_t)e * S.max_reuse + xs) * 92;
+                    for (int k = 0; k < 40; k++) xr[k] = oh[start * 40 + k];
+                    for (int k = 0; k < 7; k++) xr[40 + k] = ia[k];
+                    xr[47] = 0.0f;
+                    xr[48] = (float)((rh[goal] - rh[start]) * pow(S.discount, -(double)(start + 1)));
+                    xr[49] = S.done_hist[(size_t)e * S.max_traj + goal] ? 1.0f : 0.0f;
+                    xr[50] = (float)(goal - start - 1);
+                    xr[51] = (float)(S.env_id_offset + e);
+                    for (int k = 0; k < 40; k++) xr[52 + k] = oh[goal * 40 + k];
+                    S.xflag[(size_t)e * S.max_reuse + xs] = 1;
+                    const unsigned long long xslot = atomicAdd((unsigned long long *)(S.counters + C_TRANSITIONS), 1ULL) % (unsigned long long)S.ring_cap;
+                    float *xd = S.ring + xslot * 92;
+                    for (int k = 0; k < 92; k++) xd[k] = xr[k];
+                    ro_count(S.counters, C_REUSED);
+                }
+            }
             if (S.macro_done[e]) {
                 ro_count(S.counters, C_EPISODES);
                 if (B.success[e]) ro_count(S.counters, C_SUCCESS);
@@ -463,6 +521,12 @@ __global__ void ro_post_kernel(RoDev S, mopa_env_buffers B) {
         const int pos = S.traj_pos[e];
         const double disc = S.kind[e] == 1 ? pow(S.discount, (double)pos) : 1.0;
         S.meta_rew[e] += disc * B.reward[e];
+        if (S.reuse_data && S.kind[e] == 1 && pos < S.max_traj) {
+            float *oh = S.ob_hist + ((size_t)e * S.max_traj + pos) * 40;
+            for (int k = 0; k < 40; k++) oh[k] = B.obs[(size_t)e * 40 + k];
+            S.rew_hist[(size_t)e * S.max_traj + pos] = S.meta_rew[e];
+            S.done_hist[(size_t)e * S.max_traj + pos] = B.done[e];
+        }
         S.executed[e] += 1;
         S.traj_pos[e] = pos + 1;
         if (B.done[e]) { S.macro_done[e] = 1; S.traj_len[e] = pos + 1; }
@@ -513,7 +577,7 @@ extern "C" {
 
 int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
                         int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
-                        int64_t *d_counters, mopa_rollout **out) {
+                        int64_t *d_counters, float *d_reuse_slab, uint8_t *d_reuse_flag, mopa_rollout **out) {
     if (!env || !planner || !buf || !cfg || !d_macro_index || !d_slab || !d_emit_flag || !d_ring || ring_capacity <= 0 || !d_counters || !out) {
         mopa_set_error("mopa_rollout_create: bad argument");
         return MOPA_ERR_ARG;
@@ -542,6 +606,9 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
+    S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_flag) ? 1 : 0;
+    S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
+    S.seed_reuse = cfg->seed_reuse; S.xslab = d_reuse_slab; S.xflag = d_reuse_flag;
     cudaError_t e = cudaSetDevice(env->device);
 #define A(ptr, count) if (e == cudaSuccess) e = ro_alloc(r, &ptr, (size_t)(count))
     double *qpos0 = nullptr;
@@ -554,6 +621,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
     A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
     A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n);
+    if (S.reuse_data) { A(S.ob_hist, (size_t)n * S.max_traj * 40); A(S.rew_hist, (size_t)n * S.max_traj); A(S.done_hist, (size_t)n * S.max_traj); }
     A(S.plan_env, n); A(S.tgt64, (size_t)n * nq); A(S.c64, (size_t)n * nq); A(S.q32a, (size_t)n * row); A(S.res_a, n);
     A(S.back_of_plan, n); A(S.q32b, (size_t)n * S.num_trials * row); A(S.res_b, (size_t)n * S.num_trials);
     A(S.q32c, (size_t)n * RO_JMAX * row); A(S.res_c, (size_t)n * RO_JMAX); A(S.nstep, n); A(S.plan_ok, n);

@@ -41,6 +41,8 @@ class MoPAConfig:
     max_path = 384
     max_traj = 1280
     seed = 1234
+    reuse_data = False         # scripts/3d/push/mopa.sh sets True: relabel (start, goal) pairs of every executed plan
+    max_reuse_data = 15
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -485,7 +487,7 @@ class VecMoPARolloutRunner:
 import ctypes as _C  # noqa: E402
 
 COUNTER_NAMES = ("mp", "rl", "interpolation", "mp_fail", "approximate", "invalid", "densify_fallback", "episodes", "success",
-                 "mp_path_len", "interpolation_path_len", "env_steps", "transitions", "rrt_dropped", "rrt_problems", "waiting")
+                 "mp_path_len", "interpolation_path_len", "env_steps", "transitions", "rrt_dropped", "rrt_problems", "waiting", "reused")
 
 
 class _RolloutConfig(_C.Structure):
@@ -493,7 +495,8 @@ class _RolloutConfig(_C.Structure):
                                           "invalid_target_handling", "interpolation")] + \
                [(k, _C.c_double) for k in ("omega", "action_range", "ac_scale", "discount", "step_size", "joint_margin", "range")] + \
                [("seed_env", _C.c_uint64), ("env_id_offset", _C.c_int64), ("jnt_lo", _C.c_double * 7), ("jnt_hi", _C.c_double * 7),
-                ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p)]
+                ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p), ("reuse_data", _C.c_int32), ("max_reuse_data", _C.c_int32),
+                ("seed_reuse", _C.c_uint64)]
 
 
 class NativeMoPARolloutRunner:
@@ -522,7 +525,10 @@ class NativeMoPARolloutRunner:
         self.slab = torch.zeros(n, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
         self.emit_flag = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.transitions = torch.zeros(transition_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
-        self._counters = torch.zeros(16, dtype=torch.int64, device=dev)
+        self._counters = torch.zeros(18, dtype=torch.int64, device=dev)
+        self.max_reuse = max(1, min(16, int(cfg.max_reuse_data)))
+        self.reuse_slab = torch.zeros(n * self.max_reuse, TRANSITION_FLOATS, dtype=torch.float32, device=dev) if cfg.reuse_data else None
+        self.reuse_flag = torch.zeros(n * self.max_reuse, dtype=torch.uint8, device=dev) if cfg.reuse_data else None
         jid = [list(m.jnt_qposadr).index(a) for a in ref]
         c = _RolloutConfig()
         c.n_envs, c.max_iter, c.max_path, c.max_traj, c.rrt_capacity = n, cfg.max_iter, cfg.max_path, cfg.max_traj, min(rrt_capacity, max(n, 16))
@@ -534,9 +540,10 @@ class NativeMoPARolloutRunner:
             c.jnt_lo[k], c.jnt_hi[k], c.init_qpos[k] = float(m.jnt_range[jid[k], 0]), float(m.jnt_range[jid[k], 1]), float(venv.INIT_QPOS[k])
         self._qpos0 = np.ascontiguousarray(m.qpos0, dtype=np.float64)
         c.qpos0 = self._qpos0.ctypes.data
+        c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
-                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.POINTER(_C.c_void_p)]
+                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_void_p)]
         L.mopa_rollout_destroy.argtypes = [_C.c_void_p]
         L.mopa_rollout_destroy.restype = None
         L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
@@ -550,6 +557,7 @@ class NativeMoPARolloutRunner:
         h = _C.c_void_p()
         check(L.mopa_rollout_create(venv.h, self.planner.h, _C.byref(venv.buf), _C.byref(c), self.macro_index.data_ptr(), self.slab.data_ptr(),
                                     self.emit_flag.data_ptr(), self.transitions.data_ptr(), transition_capacity, self._counters.data_ptr(),
+                                    self.reuse_slab.data_ptr() if cfg.reuse_data else None, self.reuse_flag.data_ptr() if cfg.reuse_data else None,
                                     _C.byref(h)))
         self.h = h
         self.ticks = 0
@@ -577,6 +585,7 @@ class NativeMoPARolloutRunner:
         self._keep = ac
         self.ticks += 1
         self.last_emitted = (self.slab, self.emit_flag)
+        self.last_reused = (self.reuse_slab, self.reuse_flag) if self.cfg.reuse_data else None   # relabelled records of this tick
 
     def drain(self, max_ticks=64):
         """Tick until no environment waits for an RRT plan (end of a collection run)."""

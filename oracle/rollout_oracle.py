@@ -37,7 +37,8 @@ class ScalarMoPARunner:
         self.plan_count = 0
         self.macro_index = 0
         self.env_steps = 0
-        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0)
+        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, reused=0)
+        self.extra_records = []   # relabelled records (reuse_data) of the latest macro step
         self.ob = self._reset()
 
     def _reset(self):
@@ -122,6 +123,8 @@ class ScalarMoPARunner:
         curr = env.qpos.copy()
         is_mp = bool(np.any(np.abs(ac) > cfg.omega))
         steps = 0
+        extra_src = None
+        self.extra_records = []
         if is_mp:
             w = cfg.omega
             disp = np.where(np.abs(ac) < w, ac / (w / cfg.ac_scale),
@@ -142,14 +145,18 @@ class ScalarMoPARunner:
             if success:
                 self.counters["interpolation" if interpolation else "mp"] += 1
                 meta, done = 0.0, False
+                ob_list, rew_list, done_list = [], [], []
                 for i, nq in enumerate(traj):
                     a = np.asarray(nq[:7] - env.qpos[:7], np.float32).astype(np.float64)   # form_action (fp32 action row)
                     self.ob, rew, done = env.step(a, is_planner=True)
                     meta += cfg.discount_factor ** i * rew
+                    ob_list.append(self.ob.copy()), rew_list.append(meta), done_list.append(done)
                     steps += 1
                     if done:
                         break
                 rec_rew, intra = meta, i
+                if getattr(cfg, "reuse_data", False) and len(ob_list) > 3:
+                    extra_src = (ob_list, rew_list, done_list, traj)
             else:
                 self.counters["mp_fail"] += 1
                 if not valid:
@@ -164,7 +171,38 @@ class ScalarMoPARunner:
             intra, steps = 0, 1
         env.prev_state = None                                       # env._reset_prev_state()
         self.env_steps += steps
+        if extra_src is not None:
+            self._reuse(*extra_src)
         rec = np.zeros(92, np.float32)
         no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
         rec[0:no], rec[40:47], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
         return rec
+
+    def _reuse(self, ob_list, rew_list, done_list, traj):
+        """rl/mopa_rollouts.py:223-302: resample (start, goal) waypoint pairs of the executed plan; the reference's
+        np.random.randint draws are replaced by the counter-based generator keyed by (env id, macro-action index)."""
+        from mopa_rl_b200 import rng
+
+        cfg, L = self.cfg, len(ob_list)
+        seed = (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
+        mi, pairs = self.macro_index - 1, []
+        for t in range(min(L, cfg.max_reuse_data)):
+            u0 = float(rng.uniform01(seed, np.uint64(self.gid), np.uint64(mi), np.uint64(2 * t)))
+            u1 = float(rng.uniform01(seed, np.uint64(self.gid), np.uint64(mi), np.uint64(2 * t + 1)))
+            start = min(int(u0 * (L - 1)), L - 2)
+            goal = min(start + 1 + int(u1 * (L - 1 - start)), L - 1)
+            if (start, goal) in pairs:
+                continue
+            pairs.append((start, goal))
+            d = traj[goal][:7] - traj[start][:7]                                  # env.form_action(traj[goal], traj[start])
+            s, w, ar = cfg.ac_scale, cfg.omega, cfg.action_range                  # SACAgent.invert_displacement, piecewise
+            a = np.where(np.abs(d) < s, d * (w / s), np.sign(d) * ((np.abs(d) - s) / ((ar - s) / (1.0 - s)) / ((1.0 - s) / (1.0 - w)) + w))
+            if not (np.any(a < -w) or np.any(a > w)) or not (np.all(a >= -1.0) and np.all(a <= 1.0)):
+                continue
+            rec = np.zeros(92, np.float32)
+            no = len(ob_list[start])
+            rec[0:no], rec[40:47] = ob_list[start], a
+            rec[48] = (rew_list[goal] - rew_list[start]) * cfg.discount_factor ** (-(start + 1))
+            rec[49], rec[50], rec[52:52 + no] = float(done_list[goal]), goal - start - 1, ob_list[goal]
+            self.extra_records.append(rec)
+            self.counters["reused"] += 1

@@ -97,3 +97,59 @@ def test_native_runner_assembly_matches_scalar_reference_loop(oracle_built):
             worst = max(worst, d)
             assert d < 1e-4, (e, k, d)
     print("assembly: native vs scalar runner: %d transitions, worst |obs diff| %.2e, counters %s" % (len(rec), worst, runner.counters))
+
+
+def test_native_runner_reuse_data_matches_scalar_reference_loop(push_model, oracle_built):
+    """reuse_data (scripts/3d/push/mopa.sh: reuse_data=True, max_reuse_data=15; rl/mopa_rollouts.py:223-302): every
+    executed plan of more than 3 steps also yields relabelled (start, goal) transitions.  Main and relabelled records
+    of every environment must match the scalar restatement, in order."""
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    n, ticks, seed = 10, 50, 2024
+    cfg = MoPAConfig(max_iter=150, seed=17, reuse_data=True, max_reuse_data=15)
+    venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=30, env_id_offset=7)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 3))
+    n_flagged = 0
+    for _ in range(ticks):
+        runner.tick()
+        n_flagged += int(runner.last_reused[1].sum())
+    runner.drain()
+    torch.cuda.synchronize()
+    c = runner.counters
+    rec = runner.transitions[:c["transitions"]].cpu().numpy()
+    assert c["reused"] > n and n_flagged <= c["reused"]
+
+    def policy(gid, k):
+        u = rng.uniform01(3, np.uint64(gid), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ignored, passive, _ = planner_inputs(push_model)
+    dm = DynModel(push_model)
+    n_extra, worst = 0, 0.0
+    for e in range(n):
+        gid = 7 + e
+        mine = list(rec[rec[:, 51] == gid])
+        ref = ScalarMoPARunner(push_model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=30)
+        k = 0
+        while k < len(mine):
+            expect = [ref.macro_step()] + list(ref.extra_records)
+            n_extra += len(expect) - 1
+            for o in expect:
+                if k >= len(mine):
+                    break   # the collection stopped between a main record and its relabelled ones
+                r = mine[k]
+                assert np.allclose(r[40:47], o[40:47], atol=1e-6), (e, k, r[40:47], o[40:47])
+                assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])
+                assert abs(r[48] - o[48]) < 1e-5, (e, k)
+                d = max(np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+                worst = max(worst, d)
+                assert d < 1e-4, (e, k, d)
+                k += 1
+    assert n_extra > n
+    print("reuse_data: %d records (%d relabelled), worst |obs diff| %.2e" % (len(rec), c["reused"], worst))
