@@ -286,8 +286,8 @@ def run_rollout(args):
                 h_trans[:n].copy_(runner.slab, non_blocking=True)
                 h_trans[n:].copy_(runner.reuse_slab, non_blocking=True)
                 h_flags[:n].copy_(runner.emit_flag, non_blocking=True)
-                h_flags[n:].copy_(runner.reuse_flag, non_blocking=False)
-                d2h += (n + n * runner.max_reuse) * (92 * 4 + 1)
+                h_flags[n:].copy_(runner.last_reused[1], non_blocking=False)
+                d2h += (n + runner.reuse_capacity) * (92 * 4 + 1)
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -308,8 +308,8 @@ def run_rollout(args):
     hp = HostLoopPolicy(torch, dev, 99 + rank, n)
     runner2 = make(policy=hp)
     replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20)
-    h_trans = torch.zeros(n * (1 + runner2.max_reuse), 92, dtype=torch.float32).pin_memory()
-    h_flags = torch.zeros(n * (1 + runner2.max_reuse), dtype=torch.uint8).pin_memory()
+    h_trans = torch.zeros(n + runner2.reuse_capacity, 92, dtype=torch.float32).pin_memory()
+    h_flags = torch.zeros(n + runner2.reuse_capacity, dtype=torch.uint8).pin_memory()
     for _ in range(args.warmup):
         runner2.tick()
     hp.h2d = hp.d2h = 0

@@ -78,8 +78,9 @@ struct RoDev {   // everything the kernels need, passed by value
     float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
     double *rew_hist;            // [n][max_traj]      cumulative discounted reward after step i
     unsigned char *done_hist;    // [n][max_traj]
-    float *xslab;                // caller-owned [n][max_reuse][92] relabelled records of this tick
-    unsigned char *xflag;        // caller-owned [n][max_reuse]
+    float *xslab;                // caller-owned [xcap][92] relabelled records of this tick, compact
+    int *xcount;                 // caller-owned [1]: rows of xslab written by this tick (may exceed xcap: clamp)
+    int xcap;
     int *plan_env;               // [n]
     double *tgt64, *c64;         // [n][nq]
     float *q32a;                 // [n][row]          targets
@@ -116,7 +117,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
     if (e >= S.n) return;
     const bool need = S.traj_pos[e] >= S.traj_len[e];
     unsigned char emit = 0, reset = 0;
-    if (S.reuse_data) for (int k = 0; k < S.max_reuse; k++) S.xflag[(size_t)e * S.max_reuse + k] = 0;
+
     if (need) {
         if (S.pending[e]) {
             float *rec = S.slab + (size_t)e * 92;
@@ -164,8 +165,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                         ia[k] = (float)a;
                     }
                     if (!planner_ac || !valid_ac) continue;
-                    const int xs = np_ - 1;   // slot of this pair among the tick's relabelled records of the environment
-                    float *xr = S.xslab + ((size_t)e * S.max_reuse + xs) * 92;
+                    float xr[92];
                     for (int k = 0; k < 40; k++) xr[k] = oh[start * 40 + k];
                     for (int k = 0; k < 7; k++) xr[40 + k] = ia[k];
                     xr[47] = 0.0f;
@@ -174,7 +174,8 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     xr[50] = (float)(goal - start - 1);
                     xr[51] = (float)(S.env_id_offset + e);
                     for (int k = 0; k < 40; k++) xr[52 + k] = oh[goal * 40 + k];
-                    S.xflag[(size_t)e * S.max_reuse + xs] = 1;
+                    const int xs = atomicAdd(S.xcount, 1);   // compact per-tick slab for the multi-GPU exchange (overflow: ring only)
+                    if (xs < S.xcap) { float *xo = S.xslab + (size_t)xs * 92; for (int k = 0; k < 92; k++) xo[k] = xr[k]; }
                     const unsigned long long xslot = atomicAdd((unsigned long long *)(S.counters + C_TRANSITIONS), 1ULL) % (unsigned long long)S.ring_cap;
                     float *xd = S.ring + xslot * 92;
                     for (int k = 0; k < 92; k++) xd[k] = xr[k];
@@ -577,7 +578,7 @@ extern "C" {
 
 int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
                         int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
-                        int64_t *d_counters, float *d_reuse_slab, uint8_t *d_reuse_flag, mopa_rollout **out) {
+                        int64_t *d_counters, float *d_reuse_slab, int32_t *d_reuse_count, int32_t reuse_capacity, mopa_rollout **out) {
     if (!env || !planner || !buf || !cfg || !d_macro_index || !d_slab || !d_emit_flag || !d_ring || ring_capacity <= 0 || !d_counters || !out) {
         mopa_set_error("mopa_rollout_create: bad argument");
         return MOPA_ERR_ARG;
@@ -606,9 +607,9 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
-    S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_flag) ? 1 : 0;
+    S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_count && reuse_capacity > 0) ? 1 : 0;
     S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
-    S.seed_reuse = cfg->seed_reuse; S.xslab = d_reuse_slab; S.xflag = d_reuse_flag;
+    S.seed_reuse = cfg->seed_reuse; S.xslab = d_reuse_slab; S.xcount = d_reuse_count; S.xcap = reuse_capacity;
     cudaError_t e = cudaSetDevice(env->device);
 #define A(ptr, count) if (e == cudaSuccess) e = ro_alloc(r, &ptr, (size_t)(count))
     double *qpos0 = nullptr;
@@ -700,6 +701,7 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
         else if (q != cudaErrorNotReady) RO_TRY(q);
     }
     const int blocks = (S.n + 127) / 128;
+    if (S.reuse_data) RO_TRY(cudaMemsetAsync(S.xcount, 0, sizeof(int), st));
     ro_pre_kernel<<<blocks, 128, 0, st>>>(S, r->buf, r->env->h_model.nv);
     RO_TRY(cudaGetLastError());
     RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->h_model.ngm, r->env->task, r->buf, nullptr, 0, nullptr,

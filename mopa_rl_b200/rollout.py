@@ -527,8 +527,10 @@ class NativeMoPARolloutRunner:
         self.transitions = torch.zeros(transition_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
         self._counters = torch.zeros(18, dtype=torch.int64, device=dev)
         self.max_reuse = max(1, min(16, int(cfg.max_reuse_data)))
-        self.reuse_slab = torch.zeros(n * self.max_reuse, TRANSITION_FLOATS, dtype=torch.float32, device=dev) if cfg.reuse_data else None
-        self.reuse_flag = torch.zeros(n * self.max_reuse, dtype=torch.uint8, device=dev) if cfg.reuse_data else None
+        self.reuse_capacity = 2 * n      # relabelled records per tick that take part in the replay exchange (steady state: ~0.4 n)
+        self.reuse_slab = torch.zeros(self.reuse_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev) if cfg.reuse_data else None
+        self.reuse_count = torch.zeros(1, dtype=torch.int32, device=dev) if cfg.reuse_data else None
+        self._reuse_iota = torch.arange(self.reuse_capacity, dtype=torch.int32, device=dev)
         jid = [list(m.jnt_qposadr).index(a) for a in ref]
         c = _RolloutConfig()
         c.n_envs, c.max_iter, c.max_path, c.max_traj, c.rrt_capacity = n, cfg.max_iter, cfg.max_path, cfg.max_traj, min(rrt_capacity, max(n, 16))
@@ -543,7 +545,7 @@ class NativeMoPARolloutRunner:
         c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
-                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.POINTER(_C.c_void_p)]
+                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.POINTER(_C.c_void_p)]
         L.mopa_rollout_destroy.argtypes = [_C.c_void_p]
         L.mopa_rollout_destroy.restype = None
         L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
@@ -557,7 +559,8 @@ class NativeMoPARolloutRunner:
         h = _C.c_void_p()
         check(L.mopa_rollout_create(venv.h, self.planner.h, _C.byref(venv.buf), _C.byref(c), self.macro_index.data_ptr(), self.slab.data_ptr(),
                                     self.emit_flag.data_ptr(), self.transitions.data_ptr(), transition_capacity, self._counters.data_ptr(),
-                                    self.reuse_slab.data_ptr() if cfg.reuse_data else None, self.reuse_flag.data_ptr() if cfg.reuse_data else None,
+                                    self.reuse_slab.data_ptr() if cfg.reuse_data else None, self.reuse_count.data_ptr() if cfg.reuse_data else None,
+                                    self.reuse_capacity,
                                     _C.byref(h)))
         self.h = h
         self.ticks = 0
@@ -585,7 +588,8 @@ class NativeMoPARolloutRunner:
         self._keep = ac
         self.ticks += 1
         self.last_emitted = (self.slab, self.emit_flag)
-        self.last_reused = (self.reuse_slab, self.reuse_flag) if self.cfg.reuse_data else None   # relabelled records of this tick
+        # relabelled records of this tick: (slab [2n, 92], flags [2n]) - the first reuse_count rows are records
+        self.last_reused = (self.reuse_slab, (self._reuse_iota < self.reuse_count).to(self.torch.uint8)) if self.cfg.reuse_data else None
 
     def drain(self, max_ticks=64):
         """Tick until no environment waits for an RRT plan (end of a collection run)."""
