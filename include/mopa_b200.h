@@ -157,6 +157,16 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
 int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
                   const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream);
 
+/* Batched inverse kinematics on a site pose - replaces qpos_from_site_pose (env/inverse_kinematics.py:18-135, called by
+ * MoPARolloutRunner._cart2dispalcement, rl/mopa_rollouts.py:683-728): damped least squares with the reference's constants
+ * (regularisation 3e-2, update-norm cap 2.0, progress threshold 20, rot_weight 1).
+ *   d_qpos [n][nq] start states; d_target_pos [n][3]; d_target_quat [n][4] wxyz, nullable (position only)
+ *   body / site_local: simulated-body index and local position of the site; joint_dofs: simulated-dof indices of the
+ *   movable joints (env.robot_joints); outputs: d_qpos_out [n][nq], d_err [n] final error norm, d_steps [n], d_success [n] */
+int mopa_ik_batch(mopa_env *e, const double *d_qpos, const double *d_target_pos, const double *d_target_quat, int32_t body,
+                  const double *site_local, const int32_t *joint_dofs, int32_t n_joints, int32_t n, int32_t max_steps, double tol,
+                  double *d_qpos_out, double *d_err, int32_t *d_steps, uint8_t *d_success, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Device-resident experience collection (replaces MoPARolloutRunner.run, rl/mopa_rollouts.py:22-399, and the
  * planner glue of SACAgent / PlannerAgent / SamplingBasedPlanner.plan it calls, rl/sac_agent.py:145-318).

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmopa_b200.so")
-SOURCES = ["capi.cu", "scene_build.cu", "validity_kernel.cu", "plan.cu", "env_kernel.cu", "env_warp.cu", "rollout.cu"]
+SOURCES = ["capi.cu", "scene_build.cu", "validity_kernel.cu", "plan.cu", "env_kernel.cu", "env_warp.cu", "rollout.cu", "ik.cu"]
 # -fmad=false: the only fused multiply-adds are the explicit fmaf() calls (bit parity with the oracle)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "--shared", "-Xptxas", "-v"]
