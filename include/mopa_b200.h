@@ -140,6 +140,8 @@ typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
     int32_t *ncon;       /* [n]     contacts in the last substep */
     int32_t *work;       /* [n]     nullable: Newton steps spent by the latest env.step (cost feedback: callers group
                           *         expensive environments into the same CTAs, see mopa_rollout_step) */
+    double *cforce;      /* [n]     nullable: BaseEnv.get_contact_force() after the step (env/base.py:568-581): sum over the
+                          *         contacts of the last substep of |f_normal| + |f_tangent1| + |f_tangent2| */
 } mopa_env_buffers;
 
 int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out);

@@ -180,7 +180,7 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
 template <int WB, int WG, int WC>
-__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, int &nwt_out, const int4 keep_bodies,
+__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
@@ -878,11 +878,14 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         PROF_MARK(26);
         // constraint force on the dofs: J^T f = -(J^T grad s) = (M a - tau) - g
         if (lane < nd) { fcv = W.z[lane] - W.rhs[lane]; W.wa[lane] = W.a[lane]; }
+        cforce_out = warp_sum(type >= 1 ? fabs(gsr) : 0.0);   // BaseEnv.get_contact_force: sum of |contact-frame force components|
         if (lane == 0) W.wn = 1;
         __syncwarp();
     }
-    else if (lane == 0)
-        W.wn = 0;
+    else {
+        cforce_out = 0.0;
+        if (lane == 0) W.wn = 0;
+    }
     STAGE_SYNC(6);   // 6: constraint forces done
     // ---- semi-implicit Euler with implicit joint damping
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
@@ -970,7 +973,8 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (!forward_only) {
             int dummy = 0;
-            for (int s = 0; s < T.nsub; s++) w_substep(m, mg, W, 0u, true, lane, dummy, dummy, make_int4(0, 0, 0, 0), false, true);
+            double dummyf = 0;
+            for (int s = 0; s < T.nsub; s++) w_substep(m, mg, W, 0u, true, lane, dummy, dummy, dummyf, make_int4(0, 0, 0, 0), false, true);
         }
         return;
     }
@@ -981,10 +985,11 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     if (lane == 0) W.wn = 0;
     if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
     __syncwarp();
+    double cforce = 0;
     int ncon = 0, nwt = 0;   // contacts of the last substep; Newton steps of this env.step (cost feedback for the caller's grouping)
     const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw);
     if (forward_only) {
-        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
         if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
         w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
         return;
@@ -1002,9 +1007,9 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     __syncwarp();
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
-    if (mode == 2) w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
+    if (mode == 2) w_substep(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
     for (int s = 0; s < T.nsub; s++) {
-        w_substep(m, mg, W, comp, true, lane, ncon, nwt, keep, mode != 2, true);
+        w_substep(m, mg, W, comp, true, lane, ncon, nwt, cforce, keep, mode != 2, true);
         if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1046,7 +1051,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     clipped = __any_sync(FULL, clipped);
     __syncwarp();
     if (clipped) {
-        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, keep, true, false);
+        w_substep(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
         if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1065,6 +1070,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         B.success[e] = success ? 1 : 0;
         if (B.ncon) B.ncon[e] = ncon;
         if (B.work && mode != 2) B.work[e] = nwt;
+        if (B.cforce) B.cforce[e] = mode != 2 ? cforce : 0.0;
     }
 }
 

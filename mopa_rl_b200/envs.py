@@ -36,7 +36,7 @@ class SawyerTask(C.Structure):
 
 class EnvBuffers(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("qpos", "qvel", "prev_state", "bias_prev", "has_prev", "ep_len", "ep_rew", "obs",
-                                           "reward", "done", "success", "ncon", "work")]
+                                           "reward", "done", "success", "ncon", "work", "cforce")]
 
 
 def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0):
@@ -180,6 +180,7 @@ class VecSawyerPushObstacle:
         self.success = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.ncon = torch.zeros(n, dtype=torch.int32, device=dev)
         self.work = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.cforce = torch.zeros(n, dtype=f64, device=dev)   # get_contact_force() of every env after the latest step
         self.buf = EnvBuffers(*[getattr(self, k).data_ptr() for k, _ in EnvBuffers._fields_])
         self.env_ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
         self.episode_idx = np.zeros(n, dtype=np.int64)

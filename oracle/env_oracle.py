@@ -90,6 +90,7 @@ class PushEnvOracle:
         desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
         self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
             self.qpos, self.qvel, desired, self.comp, self.bias_prev, self.nsub)
+        self.contact_force = self.dyn.contact_force   # BaseEnv.get_contact_force()
         self.prev_state = desired.copy()
         reward, terminal = self._reward()   # compute_reward
         ob = self.obs()

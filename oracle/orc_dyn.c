@@ -129,6 +129,7 @@ void orc_dyn_destroy(void *h) {
     free(m->p_g1); free(m->p_g2); free(m);
 }
 static long g_pgs_calls = 0, g_pgs_sweeps = 0;
+static double g_last_cforce = 0; /* contact-force metric of the latest orc_dyn_step call (single-threaded test use) */
 void orc_pgs_stats(long *out, int reset) { out[0] = g_pgs_calls; out[1] = g_pgs_sweeps; if (reset) g_pgs_calls = g_pgs_sweeps = 0; }
 void orc_dyn_enable_contacts(void *h, int on) { ((dyn_model *)h)->enable_contacts = on; }
 /* constraint-row capacity (the env kernel keeps 24 rows for small scenes, 32 for large ones; excess contacts are dropped in pair order) */
@@ -346,6 +347,7 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
         }
     }
     D->ncon = 0;
+    D->cforce = 0;
     if (m->enable_contacts && m->npair > 0) {
         int n0 = nc;
         nc += orc_contact_rows(m, D, S, rows + nc, maxrows - nc);
@@ -470,6 +472,7 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
 #undef NEWTON_EVAL
         for (int r = 0; r < nc; r++)
             for (int k = 0; k < nd; k++) fc[k] -= rows[r].J[k] * gs[r];   /* constraint force f = -grad s */
+        for (int r = 0; r < nc; r++) if (rows[r].type >= 1) D->cforce += fabs(gs[r]);
         if (warm) { warm->have_a = 1; memcpy(warm->a, a, sizeof(double) * nd); }
         free(aref); free(Dr);
     }
@@ -524,8 +527,10 @@ int orc_dyn_step(void *h, double *qpos, double *qvel, const double *ctrl, const 
     if (xpos) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 3; k++) xpos[3 * i + k] = D.xpos[i][k];
     if (xquat) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 4; k++) xquat[4 * i + k] = D.xquat[i][k];
     if (ncon) *ncon = D.ncon;
+    g_last_cforce = D.cforce;
     return 0;
 }
+double orc_dyn_last_contact_force(void) { return g_last_cforce; }
 
 /* mj_forward's part that the env reads: kinematics + bias at the current state (no integration) */
 int orc_dyn_forward(void *h, const double *qpos, const double *qvel, double *bias, double *xpos, double *xquat) {

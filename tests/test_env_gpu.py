@@ -34,8 +34,11 @@ def _run(push_model, contacts, n=48, steps=4, planner_steps=True):
         torch.cuda.synchronize()
         gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
         gobs, grew, gdone = venv.obs.cpu().numpy(), venv.reward.cpu().numpy(), venv.done.cpu().numpy()
+        gcf = venv.cforce.cpu().numpy()
         for i, e in enumerate(envs):
             ob, r, d = e.step(act[i].astype(np.float64), bool(isp[i]))
+            if contacts:   # get_contact_force metric (env/base.py:568-581)
+                assert abs(gcf[i] - e.contact_force) <= 1e-6 * max(1.0, e.contact_force), (i, gcf[i], e.contact_force)
             worst["qpos"] = max(worst["qpos"], np.abs(gq[i] - e.qpos).max())
             worst["qvel"] = max(worst["qvel"], np.abs(gv[i] - e.qvel).max())
             worst["obs"] = max(worst["obs"], np.abs(gobs[i] - ob).max())
