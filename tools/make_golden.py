@@ -70,4 +70,66 @@ for e in range(n):
         _, R[s, e], _ = env.step(acts[s, e].astype(np.float64))
         Q[s, e], V[s, e] = env.qpos, env.qvel
 np.savez_compressed(os.path.join(out, "push_env_steps.npz"), seed=77, actions=acts, qpos=Q, qvel=V, reward=R)
+
+# 4. assembly env.step trajectories (SawyerAssemblyObstacle-v0): qpos / qvel / reward / obs after each of 2 env steps
+from mopa_rl_b200.envs import assembly_reset_state  # noqa: E402
+from oracle.env_oracle import AssemblyEnvOracle  # noqa: E402
+
+ma = load_model("SawyerAssemblyObstacle-v0")
+dma = DynModel(ma)
+na = 2
+qa, va = assembly_reset_state(ma, 31, np.arange(na), np.zeros(na, dtype=np.int64))
+acts_a = np.random.default_rng(9).uniform(-1, 1, (2, na, 7)).astype(np.float32)
+Qa, Va, Ra, Oa = np.zeros((2, na, ma.nq)), np.zeros((2, na, ma.nv)), np.zeros((2, na)), np.zeros((2, na, 38))
+for e in range(na):
+    env = AssemblyEnvOracle(ma, dma)
+    env.reset_to(qa[e], va[e])
+    for s_ in range(2):
+        Oa[s_, e], Ra[s_, e], _ = env.step(acts_a[s_, e].astype(np.float64))
+        Qa[s_, e], Va[s_, e] = env.qpos, env.qvel
+np.savez_compressed(os.path.join(out, "assembly_env_steps.npz"), seed=31, actions=acts_a, qpos=Qa, qvel=Va, reward=Ra, obs=Oa)
+
+# 5. inverse kinematics: seeded (start, target) -> qpos, error, steps, success (position-only and full pose)
+from mopa_rl_b200.envs import make_push_task  # noqa: E402
+from mopa_rl_b200.inverse_kinematics import site_frame  # noqa: E402
+from oracle.ik_oracle import IKOracle, _mat2quat  # noqa: E402
+
+task = make_push_task(m, dm)
+body, local = site_frame(m, dm, "grip_site")
+ik = IKOracle(dm, body, local, [int(task.arm_dof[k]) for k in range(7)])
+rng = np.random.default_rng(3)
+nk = 8
+q0 = np.tile(m.qpos0, (nk, 1))
+q0[:, :7] = PUSH_INIT_QPOS + rng.normal(0, 0.02, (nk, 7))
+tp, tq, res_p, res_q = np.zeros((nk, 3)), np.zeros((nk, 4)), [], []
+for i in range(nk):
+    qt = q0[i].copy()
+    qt[:7] += rng.uniform(-0.4, 0.4, 7)
+    sp, R, _ = ik.site_pose(qt)
+    tp[i], tq[i] = sp + (rng.uniform(-1.5, 1.5, 3) if i % 4 == 3 else 0.0), _mat2quat(R)
+    res_p.append(ik.solve(q0[i], tp[i], None, tol=1e-2))
+    res_q.append(ik.solve(q0[i], tp[i], tq[i], tol=1e-2))
+np.savez_compressed(os.path.join(out, "push_ik.npz"), q0=q0, target_pos=tp, target_quat=tq,
+                    qpos_p=np.array([r[0] for r in res_p]), err_p=np.array([r[1] for r in res_p]), steps_p=np.array([r[2] for r in res_p]),
+                    ok_p=np.array([r[3] for r in res_p]), qpos_q=np.array([r[0] for r in res_q]), err_q=np.array([r[1] for r in res_q]),
+                    steps_q=np.array([r[2] for r in res_q]), ok_q=np.array([r[3] for r in res_q]))
+
+# 6. scalar rollout loop with reuse_data: per-record checksum columns of 10 macro actions of one environment
+from mopa_rl_b200 import rng as crng  # noqa: E402
+from mopa_rl_b200.rollout import MoPAConfig, planner_inputs  # noqa: E402
+from oracle.rollout_oracle import ScalarMoPARunner  # noqa: E402
+
+
+def _policy(g, k):
+    u = crng.uniform01(3, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
+    return (2.0 * u - 1.0).astype(np.float32)
+
+
+ign2, pas2, _ = planner_inputs(m)
+runner = ScalarMoPARunner(m, dm, MoPAConfig(max_iter=150, seed=17, reuse_data=True), ign2, pas2, 7, 2024, _policy, max_episode_steps=30)
+recs = []
+for _ in range(10):
+    recs.append(runner.macro_step())
+    recs.extend(runner.extra_records)
+np.savez_compressed(os.path.join(out, "push_rollout_reuse.npz"), records=np.array(recs, np.float32))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
