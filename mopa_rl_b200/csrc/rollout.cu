@@ -14,6 +14,7 @@
 // round trip.  The policy is the only part evaluated outside (between mopa_rollout_pre and _step).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -549,6 +550,7 @@ struct mopa_rollout {
     int fill = 0;                // batch being filled; the other one may be in flight
     bool inflight = false;
     int max_iter = 1000;
+    int plan_cta_warps = 1;      // tuning hook: MOPA_PLAN_CTA_WARPS
     cudaStream_t plan_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_plan0 = nullptr;
     double rrt_last_ms = 0, rrt_sum_ms = 0;   // device time of the finished RRT batches
@@ -591,6 +593,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     }
     mopa_rollout *r = new mopa_rollout();
     r->env = env; r->planner = planner; r->buf = *buf; r->max_iter = cfg->max_iter;
+    if (const char *w = getenv("MOPA_PLAN_CTA_WARPS")) r->plan_cta_warps = atoi(w);
     RoDev &S = r->S;
     memset(&S, 0, sizeof(S));
     const int n = cfg->n_envs, nq = m.nq, row = planner->scene.hdr.nq4 * 4;
@@ -735,7 +738,7 @@ int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
         RO_TRY(cudaEventRecord(r->ev_plan0, r->plan_stream));
         r->tick_launched = r->ticks;
         RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
-                           r->plan_stream, Q.cnt, 1));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
+                           r->plan_stream, Q.cnt, r->plan_cta_warps));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
         RO_TRY(cudaEventRecord(r->ev_done, r->plan_stream));
         r->inflight = true;
         r->launches += 1;
