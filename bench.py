@@ -341,7 +341,7 @@ def run_rollout(args):
                     "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("r1_envwarp_v3_traffic.json") if args.task == "push" else None,
+                         "traffic": ncu_traffic("r1_envwarp_v4_traffic.json") if args.task == "push" else None,
                          "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
@@ -434,7 +434,7 @@ def run_validity(args):
                     "api": "mopa_is_valid_host_f32 (pinned host rows in, result words out)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v2_traffic.json")),
+                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v4_traffic.json")),
                          "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query},
             "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism}}))
@@ -445,8 +445,8 @@ def run_validity(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=30, help="untimed ticks (the first ~25 ticks carry the start-up burst: every env plans at tick 0)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")

@@ -191,10 +191,13 @@ typedef struct mopa_rollout_config {
 /* Caller-owned device buffers: d_macro_index int64[n] (policy calls per env), d_slab float[n][92] + d_emit_flag
  * uint8[n] (records emitted by the latest tick, dense by environment), d_ring float[ring_capacity][92] (all
  * records, slot = running count % capacity), d_counters int64[18]; with reuse_data: d_reuse_slab float[reuse_capacity][92] +
- * d_reuse_count int32[1] (relabelled records of the latest tick, compact; rows beyond the capacity only reach the ring). */
+ * d_reuse_count int32[1] (relabelled records of the latest tick, compact; rows beyond the capacity only reach the ring);
+ * d_ep_stats double[n][5], nullable: per environment the number of finished episodes and the sums of their length, reward,
+ * success flag and contact force (the quantities MoPARolloutRunner.run_episode reports, rl/mopa_rollouts.py:401-681). */
 int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
                         int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
-                        int64_t *d_counters, float *d_reuse_slab, int32_t *d_reuse_count, int32_t reuse_capacity, mopa_rollout **out);
+                        int64_t *d_counters, float *d_reuse_slab, int32_t *d_reuse_count, int32_t reuse_capacity, double *d_ep_stats,
+                        mopa_rollout **out);
 void mopa_rollout_destroy(mopa_rollout *r);
 /* wait_rrt != 0: block until the RRT batch in flight (if any) is done, then finalise it. */
 int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);

@@ -40,6 +40,8 @@ def build(force=False, verbose=False):
         flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
         if src in FMAD_ON and os.environ.get("MOPA_ENV_FMAD", "1") != "0":
             flags = [f for f in flags if f != "-fmad=false"]
+        if src in FMAD_ON and os.environ.get("MOPA_ENV_MAXREG"):
+            flags += ["-maxrregcount=" + os.environ["MOPA_ENV_MAXREG"]]
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
         procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

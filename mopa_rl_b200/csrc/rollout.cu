@@ -80,6 +80,8 @@ struct RoDev {   // everything the kernels need, passed by value
     double *rew_hist;            // [n][max_traj]      cumulative discounted reward after step i
     unsigned char *done_hist;    // [n][max_traj]
     float *xslab;                // caller-owned [xcap][92] relabelled records of this tick, compact
+    double *ep_stats;            // caller-owned [n][5], nullable: episodes finished, sum of ep_len, ep_rew, success, contact force
+    double *ep_cforce;           // [n] contact-force sum of the running episode (rl/mopa_rollouts.py:538-539, eval path)
     int *xcount;                 // caller-owned [1]: rows of xslab written by this tick (may exceed xcap: clamp)
     int xcap;
     int *plan_env;               // [n]
@@ -186,6 +188,11 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
             if (S.macro_done[e]) {
                 ro_count(S.counters, C_EPISODES);
                 if (B.success[e]) ro_count(S.counters, C_SUCCESS);
+                if (S.ep_stats) {   // per-environment episode statistics (what run_episode reports: len, rew, episode_success, contact_force)
+                    double *st = S.ep_stats + (size_t)e * 5;
+                    st[0] += 1.0; st[1] += (double)B.ep_len[e]; st[2] += B.ep_rew[e]; st[3] += B.success[e] ? 1.0 : 0.0; st[4] += S.ep_cforce[e];
+                }
+                S.ep_cforce[e] = 0.0;
                 const unsigned long long gid = (unsigned long long)(S.env_id_offset + e), ep = (unsigned long long)S.episode_idx[e];
                 double *q = B.qpos + (size_t)e * S.nq;
                 for (int k = 0; k < S.nq; k++) q[k] = S.qpos0[k];
@@ -530,6 +537,7 @@ __global__ void ro_post_kernel(RoDev S, mopa_env_buffers B) {
             S.done_hist[(size_t)e * S.max_traj + pos] = B.done[e];
         }
         S.executed[e] += 1;
+        if (B.cforce) S.ep_cforce[e] += B.cforce[e];
         S.traj_pos[e] = pos + 1;
         if (B.done[e]) { S.macro_done[e] = 1; S.traj_len[e] = pos + 1; }
     }
@@ -580,7 +588,8 @@ extern "C" {
 
 int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buffers *buf, const mopa_rollout_config *cfg,
                         int64_t *d_macro_index, float *d_slab, uint8_t *d_emit_flag, float *d_ring, int64_t ring_capacity,
-                        int64_t *d_counters, float *d_reuse_slab, int32_t *d_reuse_count, int32_t reuse_capacity, mopa_rollout **out) {
+                        int64_t *d_counters, float *d_reuse_slab, int32_t *d_reuse_count, int32_t reuse_capacity, double *d_ep_stats,
+                        mopa_rollout **out) {
     if (!env || !planner || !buf || !cfg || !d_macro_index || !d_slab || !d_emit_flag || !d_ring || ring_capacity <= 0 || !d_counters || !out) {
         mopa_set_error("mopa_rollout_create: bad argument");
         return MOPA_ERR_ARG;
@@ -612,6 +621,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.ring = d_ring; S.ring_cap = ring_capacity;
     S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_count && reuse_capacity > 0) ? 1 : 0;
     S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
+    S.ep_stats = d_ep_stats;
     S.seed_reuse = cfg->seed_reuse; S.xslab = d_reuse_slab; S.xcount = d_reuse_count; S.xcap = reuse_capacity;
     cudaError_t e = cudaSetDevice(env->device);
 #define A(ptr, count) if (e == cudaSuccess) e = ro_alloc(r, &ptr, (size_t)(count))
@@ -624,7 +634,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     A(S.kind, n); A(S.pending, n); A(S.macro_done, n); A(S.need, n); A(S.reset_flag, n); A(S.step_mode, n); A(S.step_mask, n);
     A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
     A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
-    A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n);
+    A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n); A(S.ep_cforce, n);
     if (S.reuse_data) { A(S.ob_hist, (size_t)n * S.max_traj * 40); A(S.rew_hist, (size_t)n * S.max_traj); A(S.done_hist, (size_t)n * S.max_traj); }
     A(S.plan_env, n); A(S.tgt64, (size_t)n * nq); A(S.c64, (size_t)n * nq); A(S.q32a, (size_t)n * row); A(S.res_a, n);
     A(S.back_of_plan, n); A(S.q32b, (size_t)n * S.num_trials * row); A(S.res_b, (size_t)n * S.num_trials);

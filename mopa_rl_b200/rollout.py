@@ -526,6 +526,7 @@ class NativeMoPARolloutRunner:
         self.emit_flag = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.transitions = torch.zeros(transition_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev)
         self._counters = torch.zeros(18, dtype=torch.int64, device=dev)
+        self.ep_stats = torch.zeros(n, 5, dtype=torch.float64, device=dev)   # per env: episodes, sum len, sum rew, sum success, sum contact force
         self.max_reuse = max(1, min(16, int(cfg.max_reuse_data)))
         self.reuse_capacity = 2 * n      # relabelled records per tick that take part in the replay exchange (steady state: ~0.4 n)
         self.reuse_slab = torch.zeros(self.reuse_capacity, TRANSITION_FLOATS, dtype=torch.float32, device=dev) if cfg.reuse_data else None
@@ -545,7 +546,7 @@ class NativeMoPARolloutRunner:
         c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
-                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.POINTER(_C.c_void_p)]
+                                          _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.c_void_p, _C.POINTER(_C.c_void_p)]
         L.mopa_rollout_destroy.argtypes = [_C.c_void_p]
         L.mopa_rollout_destroy.restype = None
         L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
@@ -560,7 +561,7 @@ class NativeMoPARolloutRunner:
         check(L.mopa_rollout_create(venv.h, self.planner.h, _C.byref(venv.buf), _C.byref(c), self.macro_index.data_ptr(), self.slab.data_ptr(),
                                     self.emit_flag.data_ptr(), self.transitions.data_ptr(), transition_capacity, self._counters.data_ptr(),
                                     self.reuse_slab.data_ptr() if cfg.reuse_data else None, self.reuse_count.data_ptr() if cfg.reuse_data else None,
-                                    self.reuse_capacity,
+                                    self.reuse_capacity, self.ep_stats.data_ptr(),
                                     _C.byref(h)))
         self.h = h
         self.ticks = 0
@@ -598,6 +599,13 @@ class NativeMoPARolloutRunner:
             if self.counter_values()["waiting"] == 0:
                 break
 
+    def episode_stats(self):
+        """Means over the finished episodes of all environments - what MoPARolloutRunner.run_episode reports per episode
+        (rl/mopa_rollouts.py:662-681): len, rew, episode_success, contact_force."""
+        s = self.ep_stats.sum(dim=0).cpu().numpy()
+        k = max(s[0], 1.0)
+        return dict(episodes=int(s[0]), len=s[1] / k, rew=s[2] / k, episode_success=s[3] / k, contact_force=s[4] / k)
+
     def counter_values(self):
         v = self._counters.cpu().numpy()
         return {k: int(v[i]) for i, k in enumerate(COUNTER_NAMES)}
@@ -630,3 +638,18 @@ class NativeMoPARolloutRunner:
         out = _C.c_double()
         self._check(self._L.mopa_rollout_env_ms(self.h, int(n_last), _C.byref(out)))
         return out.value
+
+
+def run_episodes(venv, config=None, policy=None, episodes_per_env=1, max_ticks=100000):
+    """Evaluation path (MoPARolloutRunner.run_episode, rl/mopa_rollouts.py:401-681, batched): run the collection loop
+    with the given (deterministic) policy until every environment has finished ``episodes_per_env`` episodes and return
+    the per-episode means the reference logs (len, rew, episode_success, contact_force) plus the planner counters."""
+    runner = NativeMoPARolloutRunner(venv, config, policy=policy, transition_capacity=1 << 16)
+    for t in range(max_ticks):
+        runner.tick()
+        if t % 16 == 15 and float(runner.ep_stats[:, 0].min()) >= episodes_per_env:
+            break
+    info = runner.episode_stats()
+    info.update({k: v for k, v in runner.counters.items() if k in ("mp", "rl", "interpolation", "mp_fail", "approximate", "invalid")})
+    runner.close()
+    return info

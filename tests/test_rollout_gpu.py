@@ -153,3 +153,22 @@ def test_native_runner_reuse_data_matches_scalar_reference_loop(push_model, orac
                 k += 1
     assert n_extra > n
     print("reuse_data: %d records (%d relabelled), worst |obs diff| %.2e" % (len(rec), c["reused"], worst))
+
+
+def test_run_episodes_reports_reference_episode_info(push_model, oracle_built):
+    """Evaluation path (run_episode, rl/mopa_rollouts.py:401-681): per-episode len / rew / success / contact_force."""
+    import torch
+
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, run_episodes
+
+    n, horizon = 8, 12
+    venv = VecSawyerPushObstacle(n, seed=11, max_episode_steps=horizon)
+    info = run_episodes(venv, MoPAConfig(max_iter=100, seed=2), policy=CounterPolicy(torch, venv.dev, 5), episodes_per_env=2)
+    assert info["episodes"] >= 2 * n
+    assert info["episode_success"] == 0.0 and abs(info["len"] - horizon) < 1e-9     # random actions never push the cube home
+    assert info["rew"] >= 0.0
+    # the cube rests on the bin floor in (almost) every step: contact force per step ~ its weight
+    weight = push_model.body_mass[push_model.body_name2id("cube")] * 9.81
+    assert 0.5 * weight * horizon < info["contact_force"] < 3.0 * weight * horizon, (info, weight)
+    assert info["mp"] + info["rl"] + info["interpolation"] + info["mp_fail"] > 0
