@@ -162,6 +162,85 @@ __device__ __noinline__ void w_factor_solve(const double *Msrc, const double *di
     __syncwarp();
 }
 
+// ---- box-box face contact, warp cooperative: same arithmetic per vertex as box_box_face (contact.cuh), with the
+// polygon distributed over the lanes (lane q = vertex q, at most 8).  Each Sutherland-Hodgman stage: every lane tests
+// its vertex and its successor's, emits 0-2 vertices, and the survivors are compacted in order through `tmp` (shared,
+// >= 8 x 3 doubles).  The <= 4 deepest points are written to out[] in vertex order; returns their number (all lanes).
+__device__ __noinline__ int box_box_face_warp(CPoint *out, const CGeom &g1, const CGeom &g2, int code, double margin, double (*tmp)[3], int lane) {
+    const CGeom &gr = code < 3 ? g1 : g2, &gi = code < 3 ? g2 : g1;
+    const int ax = code < 3 ? code : code - 3;
+    double n[3], dd[3] = {gi.c[0] - gr.c[0], gi.c[1] - gr.c[1], gi.c[2] - gr.c[2]};
+    c_colk(n, gr.R, ax);
+    if (d_dot(n, dd) < 0) for (int k = 0; k < 3; k++) n[k] = -n[k];
+    int iax = 0;
+    double mind = 1e30, isg = 1;
+    for (int k = 0; k < 3; k++) {
+        double a[3];
+        c_colk(a, gi.R, k);
+        const double dn = d_dot(a, n);
+        if (-fabs(dn) < mind) { mind = -fabs(dn); iax = k; isg = dn > 0 ? -1.0 : 1.0; }
+    }
+    const int u = (iax + 1) % 3, v = (iax + 2) % 3;
+    double P[3] = {0, 0, 0};
+    int np = 4;
+    if (lane < 4) {
+        double fa[3], ua[3], va[3];
+        c_colk(fa, gi.R, iax); c_colk(ua, gi.R, u); c_colk(va, gi.R, v);
+        const double su = (lane == 0 || lane == 3) ? 1.0 : -1.0, sv = lane < 2 ? 1.0 : -1.0;
+        for (int k = 0; k < 3; k++) P[k] = gi.c[k] + isg * gi.size[iax] * fa[k] + su * gi.size[u] * ua[k] + sv * gi.size[v] * va[k];
+    }
+    const int ru = (ax + 1) % 3, rv = (ax + 2) % 3;
+    for (int side = 0; side < 4 && np > 0; side++) {
+        double pa[3];
+        c_colk(pa, gr.R, side < 2 ? ru : rv);
+        const double sg = (side % 2) ? -1.0 : 1.0, lim = gr.size[side < 2 ? ru : rv];
+        const bool live = lane < np;
+        const double dp = sg * ((P[0] - gr.c[0]) * pa[0] + (P[1] - gr.c[1]) * pa[1] + (P[2] - gr.c[2]) * pa[2]) - lim;
+        const int nxt = live ? (lane + 1 == np ? 0 : lane + 1) : lane;
+        const double dq = shfl_d(dp, nxt), Q0 = shfl_d(P[0], nxt), Q1 = shfl_d(P[1], nxt), Q2 = shfl_d(P[2], nxt);
+        const bool keepP = live && dp <= 0, cross = live && ((dp <= 0) != (dq <= 0));
+        const int cnt = (keepP ? 1 : 0) + (cross ? 1 : 0);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        const int off = incl - cnt;
+        if (keepP) { tmp[off][0] = P[0]; tmp[off][1] = P[1]; tmp[off][2] = P[2]; }
+        if (cross) {
+            const double t = dp / (dp - dq);
+            const int o2 = off + (keepP ? 1 : 0);
+            tmp[o2][0] = P[0] + t * (Q0 - P[0]); tmp[o2][1] = P[1] + t * (Q1 - P[1]); tmp[o2][2] = P[2] + t * (Q2 - P[2]);
+        }
+        np = __shfl_sync(FULL, incl, 7);
+        __syncwarp();
+        if (lane < np) { P[0] = tmp[lane][0]; P[1] = tmp[lane][1]; P[2] = tmp[lane][2]; }
+        __syncwarp();
+    }
+    const double depth = (P[0] - gr.c[0]) * n[0] + (P[1] - gr.c[1]) * n[1] + (P[2] - gr.c[2]) * n[2] - gr.size[ax];
+    bool keep = lane < np && depth < margin;
+    unsigned km = __ballot_sync(FULL, keep);
+    while (__popc(km) > 4) {   // drop the shallowest point (first one on ties), like the serial selection
+        double bv = keep ? depth : -1e300;
+        int bi = lane;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        bi = __shfl_sync(FULL, bi, 0);
+        if (lane == bi) keep = false;
+        km = __ballot_sync(FULL, keep);
+    }
+    const double flip = (&gr == &g1) ? 1.0 : -1.0;
+    if (keep) {
+        const int slot = __popc(km & ((1u << lane) - 1));
+        out[slot].dist = depth;
+        for (int k = 0; k < 3; k++) { out[slot].n[k] = flip * n[k]; out[slot].pos[k] = P[k] - n[k] * 0.5 * depth; }
+    }
+    __syncwarp();
+    return __popc(km);
+}
+
 // Out-of-line wrappers keep one copy of the big routines in the instruction stream (the kernel is
 // instruction-cache bound otherwise: 9 warps per SM walk different phases of a long program).
 __device__ __noinline__ int pair_contacts_ni(CPoint *out, const CGeom &ga, const CGeom &gb, double margin) {
@@ -591,19 +670,22 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
                 const int l = __ffs(pending) - 1;
                 pending &= pending - 1;
                 int ncl = 0;
+                // clipper output + scratch: the last rows of W.Y (constraint rows are written after the narrow phase;
+                // the limit rows already there occupy at most the first nd <= 16 rows)
+                double *scr = W.Y + (WC - 6) * YS;
+                static_assert(6 * YS >= 28 + 24 && WC - 6 >= WD, "clipper scratch does not fit behind the limit rows");
+                CPoint *cout = reinterpret_cast<CPoint *>(scr);
+                const int code_l = __shfl_sync(FULL, clip_code, l);
+                int nclip = 0;
+                if (code_l >= 0) {   // box face contact of lane l's pair: all lanes clip the incident face together
+                    const int a_l = __shfl_sync(FULL, a, l), b_l = __shfl_sync(FULL, b, l);
+                    const double margin_l = shfl_d(margin, l);
+                    CGeom ga{W.gpos[a_l], geom_R(a_l), mg->g_size[a_l], 6}, gb{W.gpos[b_l], geom_R(b_l), mg->g_size[b_l], 6};
+                    nclip = box_box_face_warp(cout, ga, gb, code_l, margin_l, reinterpret_cast<double(*)[3]>(scr + 28), lane);
+                }
                 if (lane == l) {
                     const CPoint *src = cps;
-                    if (clip_code >= 0) {
-                        CGeom ga{W.gpos[a], geom_R(a), mg->g_size[a], 6}, gb{W.gpos[b], geom_R(b), mg->g_size[b], 6};
-                        // clipper output + scratch: the last rows of W.Y (constraint rows are written after the narrow phase;
-                        // the limit rows already there occupy at most the first nd <= 16 rows)
-                        double *scr = W.Y + (WC - 6) * YS;
-                        static_assert(6 * YS >= 28 + 24 + 24 + 8 + 4 && WC - 6 >= WD, "clipper scratch does not fit behind the limit rows");
-                        CPoint *cout = reinterpret_cast<CPoint *>(scr);
-                        nc = box_box_face(cout, ga, gb, clip_code, margin, reinterpret_cast<double(*)[3]>(scr + 28), reinterpret_cast<double(*)[3]>(scr + 52),
-                                          scr + 76, reinterpret_cast<int *>(scr + 84));
-                        src = cout;
-                    }
+                    if (clip_code >= 0) { nc = nclip; src = cout; }
                     const double fa = mg->g_friction[a][0], fb = mg->g_friction[b][0];
                     for (int qn = 0; qn < nc; qn++) {
                         const int slot = ncp + qn;
