@@ -766,8 +766,12 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             }
         }
         double jv = 0;
-        if (r < nc)
-            for (int k = 0; k < nd; k++) jv += W.Y[r * YS + k] * W.qd[k];
+        if (r < nc) {
+            double jw = 0;
+            for (int k = 0; k + 1 < nd; k += 2) { jv += W.Y[r * YS + k] * W.qd[k]; jw += W.Y[r * YS + k + 1] * W.qd[k + 1]; }
+            if (nd & 1) jv += W.Y[r * YS + nd - 1] * W.qd[nd - 1];
+            jv += jw;
+        }
         __syncwarp();   // every Jacobian row is complete: the kinematic arrays may now be overwritten (W.A aliases them)
         // ---- regulariser R = (1 - imp) / imp * (J M^-1 J^T)_rr with y = L^-1 J^T by forward substitution (lane = row)
         double aref = 0, Dr = 0;
@@ -780,8 +784,11 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             for (int k = k0; k < nd; k++) {
                 double s = jr[k];
                 const int j0 = W.blk[k] > k0 ? W.blk[k] : k0;   // L[k][j] = 0 outside k's tree
-                for (int j = j0; j < k; j++) s -= W.L[TRI(k, j)] * yr[j];
-                s = s * W.invd[k];
+                double s1 = 0;   // two accumulators: halves the dependent-add chain of the substitution
+                int j = j0;
+                for (; j + 1 < k; j += 2) { s -= W.L[TRI(k, j)] * yr[j]; s1 -= W.L[TRI(k, j + 1)] * yr[j + 1]; }
+                if (j < k) s -= W.L[TRI(k, j)] * yr[j];
+                s = (s + s1) * W.invd[k];
                 yr[k] = s;
                 diag += s * s;
             }
@@ -804,6 +811,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         trM = warp_sum(trM);
         const double scale = 1.0 / (trM > DYN_MINVAL ? trM : DYN_MINVAL);
         double cost = 0, x0 = 0, x1 = 0, x2 = 0, gsr = 0, h0 = 0, h1 = 0, h2 = 0;
+        const double Dm = Dr / (1 + mu * mu);   // middle-zone weight of this lane's contact
         // evaluates cost / gradient (W.rhs) / M a - tau (W.z) at W.a
         auto newton_eval = [&]() {
             double mat = 0, cq = 0;
@@ -838,11 +846,12 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
                     gsr = Dr * x; 
                     if (dirn == 0) { h0 = Dr; sc = 0.5 * Dr * (x0 * x0 + x1 * x1 + x2 * x2); } else if (dirn == 1) h1 = Dr; else h2 = Dr;
                 } else {                                                // middle zone: distance to the cone surface
-                    const double Dm = Dr / (1 + mu * mu), e = x0 - mu * t, u1 = -mu * x1 / t, u2 = -mu * x2 / t;
-                    const double c = -Dm * e * mu / t, t2 = t * t;
+                    // one reciprocal instead of six fp64 divisions (n1, n2 = unit tangential direction)
+                    const double it = 1.0 / t, n1 = x1 * it, n2 = x2 * it, e = x0 - mu * t, u1 = -mu * n1, u2 = -mu * n2;
+                    const double c = -Dm * e * mu * it;
                     if (dirn == 0) { gsr = Dm * e; h0 = Dm; h1 = Dm * u1; h2 = Dm * u2; sc = 0.5 * Dm * e * e; }
-                    else if (dirn == 1) { gsr = Dm * e * u1; h0 = Dm * u1; h1 = Dm * u1 * u1 + c * (1 - x1 * x1 / t2); h2 = Dm * u1 * u2 + c * (-x1 * x2 / t2); }
-                    else { gsr = Dm * e * u2; h0 = Dm * u2; h1 = Dm * u1 * u2 + c * (-x1 * x2 / t2); h2 = Dm * u2 * u2 + c * (1 - x2 * x2 / t2); }
+                    else if (dirn == 1) { gsr = Dm * e * u1; h0 = Dm * u1; h1 = Dm * u1 * u1 + c * (1 - n1 * n1); h2 = Dm * u1 * u2 + c * (-n1 * n2); }
+                    else { gsr = Dm * e * u2; h0 = Dm * u2; h1 = Dm * u1 * u2 + c * (-n1 * n2); h2 = Dm * u2 * u2 + c * (1 - n2 * n2); }
                 }
             }
             cost = warp_sum(cq + sc);
@@ -937,8 +946,8 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
                     if (a0 >= mu * t) { }
                     else if (mu * a0 + t <= 0) { d1 = Dr * (a0 * jp0 + a1 * jp1 + a2 * jp2); d2 = Dr * (jp0 * jp0 + jp1 * jp1 + jp2 * jp2); }
                     else {
-                        const double Dm = Dr / (1 + mu * mu), e = a0 - mu * t, u1 = -mu * a1 / t, u2 = -mu * a2 / t, c = -Dm * e * mu / t;
-                        const double uj = jp0 + u1 * jp1 + u2 * jp2, tj = (a1 * jp1 + a2 * jp2) / t;
+                        const double it = 1.0 / t, e = a0 - mu * t, u1 = -mu * a1 * it, u2 = -mu * a2 * it, c = -Dm * e * mu * it;
+                        const double uj = jp0 + u1 * jp1 + u2 * jp2, tj = (a1 * jp1 + a2 * jp2) * it;
                         d1 = Dm * e * uj;
                         d2 = Dm * uj * uj + c * (jp1 * jp1 + jp2 * jp2 - tj * tj);
                     }
