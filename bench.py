@@ -341,7 +341,7 @@ def run_rollout(args):
                     "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("r1_envwarp_v4_traffic.json") if args.task == "push" else None,
+                         "traffic": ncu_traffic("r1_envwarp_v5_traffic.json") if args.task == "push" else None,
                          "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
