@@ -53,6 +53,14 @@ typedef struct mopa_model_desc {
     const int32_t *site_bodyid;    /* [nsite] */
     const double  *site_pos;       /* [nsite][3] */
     const double  *site_quat;      /* [nsite][4] */
+    /* collision meshes: convex-hull vertices in the geom frame (mjModel mesh_vert of the hull;
+       MuJoCo 2.0 collides mesh geoms through their convex hull with libccd).  geom_dataid is the
+       mesh of a MOPA_GEOM_MESH geom, -1 otherwise. */
+    int32_t nmesh, nmeshvert;
+    const int32_t *geom_dataid;    /* [ngeom] */
+    const int32_t *mesh_vertadr;   /* [nmesh] */
+    const int32_t *mesh_vertnum;   /* [nmesh] */
+    const double  *mesh_vert;      /* [nmeshvert][3] */
 } mopa_model_desc;
 
 #ifdef __cplusplus

@@ -5,14 +5,16 @@
 // Analytic routines for plane-X, sphere-X, capsule-capsule and box-box (15-axis SAT); a
 // Minkowski portal refinement routine for the remaining cylinder / capsule / box pairs
 // (MuJoCo 2.0 delegates those to libccd's MPR with tolerance 1e-6, 50 iterations).
-// Geoms are ordered by kind (plane < sphere < capsule < cylinder < box) exactly as
+// Mesh geoms collide through the convex hull of their vertices (support = extreme hull vertex), always via MPR
+// (plane - mesh analytically), like mjc_Convex / mjc_PlaneConvex.
+// Geoms are ordered by kind (plane < sphere < capsule < cylinder < box < mesh) exactly as
 // mjtGeom orders them, so `a` is always the lower kind.
 #pragma once
 #include "mopa_math.cuh"
 
 namespace mopa {
 
-enum Kind : int { K_PLANE = 0, K_SPHERE = 1, K_CAPSULE = 2, K_CYLINDER = 3, K_BOX = 4 };
+enum Kind : int { K_PLANE = 0, K_SPHERE = 1, K_CAPSULE = 2, K_CYLINDER = 3, K_BOX = 4, K_MESH = 5 };
 #define MOPA_BIG 1.0e10f
 
 // A geom in world coordinates.  Capsules / cylinders only carry their axis in column 2 of R.
@@ -21,7 +23,26 @@ struct Geom {
     M3 R;
     V3 size;
     int kind;
+    const float *hull;   // K_MESH: hull vertices (xyz triplets, geom frame), count in nhull
+    int nhull;
 };
+
+// index of the hull vertex that is extreme along the LOCAL direction l (first maximum)
+static MOPA_HD_COLD int hull_extreme(const float *hull, int n, const V3 &l) {
+    int best = 0;
+    float bd = dot(V3{hull[0], hull[1], hull[2]}, l);
+    for (int i = 1; i < n; i++) {
+        float di = dot(V3{hull[3 * i], hull[3 * i + 1], hull[3 * i + 2]}, l);
+        if (di > bd) { bd = di; best = i; }
+    }
+    return best;
+}
+MOPA_HD float plane_mesh(const Geom &p, const Geom &g) {
+    V3 n = col(p.R, 2), d = g.c - p.c;
+    V3 l = mulMTV(g.R, n);
+    const float *v = g.hull + 3 * hull_extreme(g.hull, g.nhull, neg(l));
+    return dot(n, d) + dot(V3{v[0], v[1], v[2]}, l);
+}
 
 MOPA_HD float plane_sphere(const Geom &p, const Geom &s) { return dot(col(p.R, 2), s.c - p.c) - s.size.x; }
 MOPA_HD float plane_capsule(const Geom &p, const Geom &g) {
@@ -140,7 +161,16 @@ MOPA_HD float box_box(const Geom &g1, const Geom &g2) {
 }
 
 // ------------------------------------------------------------------ Minkowski portal refinement
+// MESH = false drops the hull / sphere branches at compile time: scenes without mesh colliders (push, assembly) run
+// exactly the code (and register budget) they ran before meshes existed.
+template <bool MESH>
 MOPA_HD V3 support(const Geom &g, const V3 &dir) {
+    if (MESH && g.kind == K_MESH) {
+        V3 l = mulMTV(g.R, dir);
+        const float *v = g.hull + 3 * hull_extreme(g.hull, g.nhull, l);
+        return g.c + mulMV(g.R, V3{v[0], v[1], v[2]});
+    }
+    if (MESH && g.kind == K_SPHERE) return V3{fmaf(dir.x, g.size.x, g.c.x), fmaf(dir.y, g.size.x, g.c.y), fmaf(dir.z, g.size.x, g.c.z)};
     if (g.kind == K_BOX) {
         V3 l = mulMTV(g.R, dir);
         V3 p{l.x >= 0 ? g.size.x : -g.size.x, l.y >= 0 ? g.size.y : -g.size.y, l.z >= 0 ? g.size.z : -g.size.z};
@@ -158,7 +188,8 @@ MOPA_HD V3 support(const Geom &g, const V3 &dir) {
     }
     return V3{fmaf(dir.x, g.size.x, base.x), fmaf(dir.y, g.size.x, base.y), fmaf(dir.z, g.size.x, base.z)};
 }
-MOPA_HD V3 msupport(const Geom &g1, const Geom &g2, const V3 &dir) { return support(g1, dir) - support(g2, neg(dir)); }
+template <bool MESH>
+MOPA_HD V3 msupport(const Geom &g1, const Geom &g2, const V3 &dir) { return support<MESH>(g1, dir) - support<MESH>(g2, neg(dir)); }
 MOPA_HD void normalize(V3 &v) {
     float n = len(v);
     if (n < 1e-30f) return;
@@ -205,13 +236,14 @@ MOPA_HD float origin_tri_dist2(const V3 &a, const V3 &b, const V3 &c) {
 }
 
 // true + depth when the two convex geoms intersect
+template <bool MESH>
 MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
     V3 v0 = g1.c - g2.c, v1, v2, v3, v4, dir, va;
     float d;
     if (v0.x == 0 && v0.y == 0 && v0.z == 0) v0.x = MPR_EPS * 10.0f;
     dir = neg(v0);
     normalize(dir);
-    v1 = msupport(g1, g2, dir);
+    v1 = msupport<MESH>(g1, g2, dir);
     d = dot(v1, dir);
     if (is_zero(d) || d < 0) return false;
     dir = cross(v0, v1);
@@ -221,7 +253,7 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
         return true;
     }
     normalize(dir);
-    v2 = msupport(g1, g2, dir);
+    v2 = msupport<MESH>(g1, g2, dir);
     d = dot(v2, dir);
     if (is_zero(d) || d < 0) return false;
     dir = cross(v1 - v0, v2 - v0);
@@ -234,7 +266,7 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
     int it = 0;
     for (;;) {
         if (++it > MPR_MAXIT) return false;
-        v3 = msupport(g1, g2, dir);
+        v3 = msupport<MESH>(g1, g2, dir);
         d = dot(v3, dir);
         if (is_zero(d) || d < 0) return false;
         bool cont = false;
@@ -258,7 +290,7 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
             d = dot(dir, v1);
             if (is_zero(d) || d > 0) inside = true;
         }
-        v4 = msupport(g1, g2, dir);
+        v4 = msupport<MESH>(g1, g2, dir);
         float dv4 = dot(v4, dir);
         float dmin = fminf(dv4 - dot(v1, dir), fminf(dv4 - dot(v2, dir), dv4 - dot(v3, dir)));
         bool reached = (dmin <= MPR_TOL);
@@ -287,6 +319,7 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
 // it only skips the expensive, badly diverging portal refinement for the many near-but-separate pairs.
 MOPA_HD bool mpr_certainly_separate(const Geom &a, const Geom &b) {
     const float eps = 1e-4f;
+    if (b.kind == K_MESH) return false;   // hulls: bounding spheres only
     if (b.kind == K_BOX) {   // a: capsule / cylinder.  Per box axis: gap between the slab and the projected segment
         const V3 ax = col(a.R, 2), d = a.c - b.c;
         const V3 l = mulMTV(b.R, d), al = mulMTV(b.R, ax);
@@ -313,16 +346,17 @@ MOPA_HD bool mpr_certainly_separate(const Geom &a, const Geom &b) {
 // dispatch classes (pair of kinds, a.kind <= b.kind)
 enum PairClass : int {
     PC_PLANE_SPHERE = 0, PC_PLANE_CAPSULE, PC_PLANE_CYLINDER, PC_PLANE_BOX, PC_SPHERE_SPHERE, PC_SPHERE_CAPSULE,
-    PC_SPHERE_CYLINDER, PC_SPHERE_BOX, PC_CAPSULE_CAPSULE, PC_BOX_BOX, PC_MPR, PC_NONE
+    PC_SPHERE_CYLINDER, PC_SPHERE_BOX, PC_CAPSULE_CAPSULE, PC_PLANE_MESH, PC_BOX_BOX, PC_MPR, PC_NONE
 };
 MOPA_HD int pair_class(int ka, int kb) {
-    if (ka == K_PLANE) return kb == K_SPHERE ? PC_PLANE_SPHERE : kb == K_CAPSULE ? PC_PLANE_CAPSULE : kb == K_CYLINDER ? PC_PLANE_CYLINDER : kb == K_BOX ? PC_PLANE_BOX : PC_NONE;
-    if (ka == K_SPHERE) return kb == K_SPHERE ? PC_SPHERE_SPHERE : kb == K_CAPSULE ? PC_SPHERE_CAPSULE : kb == K_CYLINDER ? PC_SPHERE_CYLINDER : PC_SPHERE_BOX;
+    if (ka == K_PLANE) return kb == K_SPHERE ? PC_PLANE_SPHERE : kb == K_CAPSULE ? PC_PLANE_CAPSULE : kb == K_CYLINDER ? PC_PLANE_CYLINDER : kb == K_BOX ? PC_PLANE_BOX : kb == K_MESH ? PC_PLANE_MESH : PC_NONE;
+    if (ka == K_SPHERE && kb != K_MESH) return kb == K_SPHERE ? PC_SPHERE_SPHERE : kb == K_CAPSULE ? PC_SPHERE_CAPSULE : kb == K_CYLINDER ? PC_SPHERE_CYLINDER : PC_SPHERE_BOX;
     if (ka == K_CAPSULE && kb == K_CAPSULE) return PC_CAPSULE_CAPSULE;
     if (ka == K_BOX && kb == K_BOX) return PC_BOX_BOX;
     return PC_MPR;
 }
 // cheap classes, evaluated inline by the owning thread
+template <bool MESH>
 MOPA_HD float cheap_dist(int cls, const Geom &a, const Geom &b) {
     switch (cls) {
     case PC_PLANE_SPHERE: return plane_sphere(a, b);
@@ -334,6 +368,7 @@ MOPA_HD float cheap_dist(int cls, const Geom &a, const Geom &b) {
     case PC_SPHERE_CYLINDER: return sphere_cylinder(a, b);
     case PC_SPHERE_BOX: return sphere_box(a, b);
     case PC_CAPSULE_CAPSULE: return capsule_capsule(a, b);
+    case PC_PLANE_MESH: return MESH ? plane_mesh(a, b) : MOPA_BIG;
     default: return MOPA_BIG;
     }
 }

@@ -11,8 +11,10 @@
 
 #if defined(__CUDACC__)
 #define MOPA_HD __host__ __device__ __forceinline__
+#define MOPA_HD_COLD __host__ __device__ __noinline__   // rare paths kept out of line (register pressure of the callers)
 #else
 #define MOPA_HD inline
+#define MOPA_HD_COLD inline
 #endif
 
 namespace mopa {

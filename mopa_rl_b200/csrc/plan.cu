@@ -130,6 +130,7 @@ struct WarpCtx {
 };
 
 // All `count` (<= PW_STATES) states valid?  Lane k < count holds state k in `mine`.
+template <bool MESH>
 __device__ __forceinline__ bool states_all_valid(const WarpCtx &W, const SpaceDev &sp, const float *baseq, const St &mine, int count) {
     const int lane = W.lane;
     if (lane < count) {
@@ -165,9 +166,9 @@ __device__ __forceinline__ bool states_all_valid(const WarpCtx &W, const SpaceDe
             }
             if (survive && pr.cls <= PC_MPR) {
                 Geom a, b;
-                load_geom(a, W.S.recs[pr.ga], W.frames, PW_STATES, k);
-                load_geom(b, W.S.recs[pr.gb], W.frames, PW_STATES, k);
-                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist(pr.cls, a, b) : cheap_dist(pr.cls, a, b);
+                load_geom<MESH>(a, W.S.recs[pr.ga], W.frames, PW_STATES, k);
+                load_geom<MESH>(b, W.S.recs[pr.gb], W.frames, PW_STATES, k);
+                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b);
                 if (dist <= thr) bad = true;
             }
         }
@@ -209,6 +210,7 @@ __device__ __forceinline__ int nearest(const SpaceDev &sp, const Tree &t, const 
     return bi;
 }
 
+template <bool MESH>
 __device__ __forceinline__ int grow(const WarpCtx &W, const SpaceDev &sp, const float *baseq, Tree &t, bool is_start,
                                     const St &target, St &xstate, int &added, int max_nodes) {
     const int lane = W.lane;
@@ -235,7 +237,7 @@ __device__ __forceinline__ int grow(const WarpCtx &W, const SpaceDev &sp, const 
         St mine = dstate;
         const int idx = base + lane;  // 0: dstate, m>=1: interior point m
         if (lane < cnt && idx >= 1) mine = interpolate(sp, s1, s2, (float)idx / (float)nd);
-        if (!states_all_valid(W, sp, baseq, mine, cnt)) return G_TRAPPED;
+        if (!states_all_valid<MESH>(W, sp, baseq, mine, cnt)) return G_TRAPPED;
     }
     if (t.n >= max_nodes) return G_TRAPPED;
     if (lane == 0) {
@@ -251,6 +253,7 @@ __device__ __forceinline__ int grow(const WarpCtx &W, const SpaceDev &sp, const 
     return reach ? G_REACHED : G_ADVANCED;
 }
 
+template <bool MESH>
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
 plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev sp, const float *__restrict__ start,
             const float *__restrict__ goal, int row_stride, const unsigned long long *__restrict__ keys, int n, int max_iter,
@@ -293,7 +296,7 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
             T[k].n = 0;
         }
         bool ok = true;
-        if (!states_all_valid(W, sp, baseq, g, 1)) { status = MOPA_PLAN_INVALID_GOAL_; ok = false; }
+        if (!states_all_valid<MESH>(W, sp, baseq, g, 1)) { status = MOPA_PLAN_INVALID_GOAL_; ok = false; }
         if (ok) {
             bool inb = true;
 #pragma unroll
@@ -302,7 +305,7 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
                     if (s.v[j] > sp.hi[j] || s.v[j] < sp.lo[j]) inb = false;
                     if (g.v[j] > sp.hi[j] || g.v[j] < sp.lo[j]) inb = false;
                 }
-            if (!inb || !states_all_valid(W, sp, baseq, s, 1)) ok = false;
+            if (!inb || !states_all_valid<MESH>(W, sp, baseq, s, 1)) ok = false;
         }
         if (ok) {
             if (lane == 0) {
@@ -327,11 +330,11 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
                 for (int j = 0; j < PLAN_MAXD; j++)
                     rstate.v[j] = j < sp.nd ? fmaf(sp.hi[j] - sp.lo[j], urand(sp.seed, key, (unsigned)it, (unsigned)j), sp.lo[j]) : 0.f;
                 int added = -1, oadded = -1;
-                int gs = grow(W, sp, baseq, T[ti], is_start, rstate, xstate, added, max_nodes);
+                int gs = grow<MESH>(W, sp, baseq, T[ti], is_start, rstate, xstate, added, max_nodes);
                 if (gs == G_TRAPPED) continue;
                 rstate = xstate;
-                int gsc = grow(W, sp, baseq, T[oi], start_tree, rstate, xstate, oadded, max_nodes);
-                while (gsc == G_ADVANCED) gsc = grow(W, sp, baseq, T[oi], start_tree, rstate, xstate, oadded, max_nodes);
+                int gsc = grow<MESH>(W, sp, baseq, T[oi], start_tree, rstate, xstate, oadded, max_nodes);
+                while (gsc == G_ADVANCED) gsc = grow<MESH>(W, sp, baseq, T[oi], start_tree, rstate, xstate, oadded, max_nodes);
                 if (gsc == G_REACHED) {
                     sm = start_tree ? oadded : added;
                     gm = start_tree ? added : oadded;
@@ -436,16 +439,18 @@ cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_go
     const SceneHeader &H = p->scene.hdr;
     size_t per_warp = ((size_t)PW_STATES * (H.nq + 1) + (size_t)H.frame_floats * PW_STATES + H.nq) * sizeof(float);
     size_t smem = (size_t)H.blob_bytes + per_warp * cta_warps + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static bool attr_set[2] = {false, false};
+    const int mesh = H.n_hull_vert > 0;   // scenes with mesh colliders: instantiation with the hull support function
+    auto kern = mesh ? plan_kernel<true> : plan_kernel<false>;
+    if (!attr_set[mesh]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[mesh] = true;
     }
     int grid = (n + cta_warps - 1) / cta_warps;
     int max_grid = cta_warps == 1 ? p->sm_count * 2 : p->sm_count * 4;
     if (grid > max_grid) grid = max_grid;
-    plan_kernel<<<grid, cta_warps * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
+    kern<<<grid, cta_warps * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
                                                         b->tree_x, b->tree_parent, b->max_nodes, d_path, d_node_ids, max_path,
                                                         d_path_len, d_status, d_iters, d_nodes, d_n);
     return cudaGetLastError();

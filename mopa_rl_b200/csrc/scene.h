@@ -42,7 +42,7 @@ struct ConstFrame {  // world frame of a static (world-welded) parent body
     float pad2[3];
 };
 struct GeomRec {  // every collidable geom that appears in at least one candidate pair
-    float sx, sy, sz;
+    float sx, sy, sz;   // geom_size; K_MESH: int bits of (byte offset from this record to the hull vertices, count)
     int kind;
     int slot;        // >= 0: moving geom, float offset in the frame store;  -1: static
     float px, py, pz;  // world frame when static
@@ -70,7 +70,8 @@ struct SceneHeader {
     float threshold;
     int off_body, off_joint, off_geom, off_const, off_rec, off_pair;  // byte offsets from blob start
     int blob_bytes;
-    int pad[2];
+    int off_hull;            // hull vertices of collision meshes (float xyz triplets)
+    int n_hull_vert;
 };
 
 struct HostScene {

@@ -24,6 +24,7 @@ static int kind_of(int mjtype) {
     case MOPA_GEOM_CAPSULE: return K_CAPSULE;
     case MOPA_GEOM_CYLINDER: return K_CYLINDER;
     case MOPA_GEOM_BOX: return K_BOX;
+    case MOPA_GEOM_MESH: return K_MESH;
     default: return -1;
     }
 }
@@ -68,7 +69,10 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
                 if (ignored[2 * k] == g1 && ignored[2 * k + 1] == g2) ign = true;
             if (ign) continue;
             if (kind_of(d->geom_type[g1]) < 0 || kind_of(d->geom_type[g2]) < 0)
-                throw std::runtime_error("collidable geom of unsupported type (mesh/ellipsoid/hfield) in a candidate pair");
+                throw std::runtime_error("collidable geom of unsupported type (ellipsoid/hfield) in a candidate pair");
+            for (int g : {g1, g2})
+                if (d->geom_type[g] == MOPA_GEOM_MESH && (d->geom_dataid[g] < 0 || d->geom_dataid[g] >= d->nmesh))
+                    throw std::runtime_error("collidable mesh geom without convex-hull vertices (recompile the scene)");
             out.canon_g1.push_back(g1);
             out.canon_g2.push_back(g2);
         }
@@ -185,7 +189,7 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
             memcpy(G.m, gm.m, sizeof(G.m));
             G.kind = kind_of(d->geom_type[g]);
             G.slot = frame_floats;
-            frame_floats += (G.kind == K_SPHERE) ? 3 : (G.kind == K_BOX ? 12 : 6);
+            frame_floats += (G.kind == K_SPHERE) ? 3 : (G.kind >= K_BOX ? 12 : 6);
             G.rec = (int)recs.size();
             GeomRec Rr;
             memset(&Rr, 0, sizeof(Rr));
@@ -266,6 +270,19 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     H.off_const = append(blob, consts);
     H.off_rec = append(blob, recs);
     H.off_pair = append(blob, pairs);
+    std::vector<float> hull(3 * (size_t)d->nmeshvert);
+    for (size_t k = 0; k < hull.size(); k++) hull[k] = (float)d->mesh_vert[k];
+    H.off_hull = append(blob, hull);
+    H.n_hull_vert = d->nmeshvert;
+    for (size_t r = 0; r < recs.size(); r++) {   // mesh records: locate their hull relative to the record itself
+        if (recs[r].kind != K_MESH) continue;
+        const int me = d->geom_dataid[recs[r].geom_id];
+        GeomRec *Rr = reinterpret_cast<GeomRec *>(blob.data() + H.off_rec) + r;
+        const int rel = (H.off_hull + 12 * d->mesh_vertadr[me]) - (H.off_rec + (int)(r * sizeof(GeomRec)));
+        const int cnt = d->mesh_vertnum[me];
+        memcpy(&Rr->sx, &rel, 4);
+        memcpy(&Rr->sy, &cnt, 4);
+    }
     while (blob.size() % 16) blob.push_back(0);
     H.blob_bytes = (int)blob.size();
     memcpy(blob.data(), &H, sizeof(H));

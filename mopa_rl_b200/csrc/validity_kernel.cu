@@ -19,7 +19,7 @@ struct RowQ {
     __device__ __forceinline__ float operator()(int i) const { return __ldg(row + i); }
 };
 
-template <int NQ, int QCAP>
+template <int NQ, int QCAP, bool MESH>
 __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
                                                       const float *__restrict__ qpos, int row_stride, int n,
                                                       uint32_t *__restrict__ out, int exact, const int *__restrict__ d_n, int d_n_mult) {
@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__res
                     if (idx < QCAP) { queue[k * QCAP + idx] = ((uint32_t)tid << 16) | (uint32_t)p; continue; }
                 }
                 Geom a, b;
-                load_geom(a, S.recs[pr.ga], frames, NQ, tid);
-                load_geom(b, S.recs[pr.gb], frames, NQ, tid);
-                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist(pr.cls, a, b) : cheap_dist(pr.cls, a, b);
+                load_geom<MESH>(a, S.recs[pr.ga], frames, NQ, tid);
+                load_geom<MESH>(b, S.recs[pr.gb], frames, NQ, tid);
+                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b);
                 if (dist <= thr) {
                     first = min(first, (uint32_t)pr.canon);
                     if (!exact) break;
@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__res
                 if (!exact && res[ql] != 0xFFFFFFFFu) continue;
                 const PairRec pr = S.pairs[p];
                 Geom a, b;
-                load_geom(a, S.recs[pr.ga], frames, NQ, ql);
-                load_geom(b, S.recs[pr.gb], frames, NQ, ql);
-                float dist = heavy_dist(pr.cls, a, b);
+                load_geom<MESH>(a, S.recs[pr.ga], frames, NQ, ql);
+                load_geom<MESH>(b, S.recs[pr.gb], frames, NQ, ql);
+                float dist = heavy_dist<MESH>(pr.cls, a, b);
                 if (dist <= thr) atomicMin(&res[ql], (uint32_t)pr.canon);
             }
         }
@@ -120,13 +120,14 @@ size_t validity_smem_bytes(const SceneHeader &H) {
 cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
                             uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
     if (n <= 0) return cudaSuccess;
-    static bool attr_set = false;
+    static bool attr_set[2] = {false, false};
     size_t smem = validity_smem_bytes(H);
-    auto kern = is_valid_kernel<VK_NQ, VK_QCAP>;
-    if (!attr_set) {
+    const int mesh = H.n_hull_vert > 0;   // scenes with mesh colliders run the instantiation that carries the hull support
+    auto kern = mesh ? is_valid_kernel<VK_NQ, VK_QCAP, true> : is_valid_kernel<VK_NQ, VK_QCAP, false>;
+    if (!attr_set[mesh]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[mesh] = true;
     }
     int ntile = (n + VK_NQ - 1) / VK_NQ;
     int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -88,7 +88,7 @@ __device__ __forceinline__ void fk_state(const SceneView &S, const QPos &q, floa
             V3 gp = cur.pos + mulMV(cur.mat, V3{G.px, G.py, G.pz});
             float *f = frames + (size_t)G.slot * stride + lane;
             f[0] = gp.x; f[stride] = gp.y; f[2 * stride] = gp.z;
-            if (G.kind == K_BOX) {
+            if (G.kind >= K_BOX) {   // boxes and mesh hulls need the full frame
                 M3 L;
 #pragma unroll
                 for (int k = 0; k < 9; k++) L.m[k] = G.m[k];
@@ -103,9 +103,15 @@ __device__ __forceinline__ void fk_state(const SceneView &S, const QPos &q, floa
     }
 }
 
+template <bool MESH>
 __device__ __forceinline__ void load_geom(Geom &g, const GeomRec &r, const float *frames, int stride, int lane) {
     g.kind = r.kind;
     g.size = V3{r.sx, r.sy, r.sz};
+    g.hull = nullptr; g.nhull = 0;
+    if (MESH && r.kind == K_MESH) {   // sx / sy carry (byte offset of the hull vertices from this record, vertex count)
+        g.hull = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(&r) + __float_as_int(r.sx));
+        g.nhull = __float_as_int(r.sy);
+    }
     if (r.slot < 0) {
         g.c = V3{r.px, r.py, r.pz};
 #pragma unroll
@@ -116,7 +122,7 @@ __device__ __forceinline__ void load_geom(Geom &g, const GeomRec &r, const float
     g.c = V3{f[0], f[stride], f[2 * stride]};
 #pragma unroll
     for (int k = 0; k < 9; k++) g.R.m[k] = 0.0f;
-    if (r.kind == K_BOX) {
+    if (r.kind >= K_BOX) {
 #pragma unroll
         for (int k = 0; k < 9; k++) g.R.m[k] = f[(3 + k) * stride];
     } else if (r.kind != K_SPHERE) {
@@ -125,11 +131,12 @@ __device__ __forceinline__ void load_geom(Geom &g, const GeomRec &r, const float
 }
 
 // signed distance of a deferred (box-box / MPR) pair
+template <bool MESH>
 __device__ __forceinline__ float heavy_dist(int cls, const Geom &a, const Geom &b) {
     if (cls == PC_BOX_BOX) return box_box(a, b);
     if (mpr_certainly_separate(a, b)) return MOPA_BIG;
     float depth;
-    if (mpr_penetration(a, b, &depth)) return -depth;
+    if (mpr_penetration<MESH>(a, b, &depth)) return -depth;
     return MOPA_BIG;
 }
 

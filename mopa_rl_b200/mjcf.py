@@ -155,6 +155,26 @@ def mesh_inertia_legacy(tri):
     return V, cen + com, I
 
 
+def mesh_hull_vertices(tri):
+    """Vertices of the convex hull of a triangle soup (float32 values, original vertex order).
+
+    MuJoCo collides mesh geoms through the convex hull of their vertices (qhull at compile
+    time, libccd support function = arg max of v . dir over the hull vertices).  The hull is
+    computed here with the same library family (scipy's qhull); vertices are de-duplicated on
+    their float32 values and kept in order of first appearance so that ties of the support
+    function resolve identically everywhere (lowest index wins).
+    """
+    from scipy.spatial import ConvexHull  # host-side scene compilation only
+
+    v = np.asarray(tri, dtype=np.float64).reshape(-1, 3).astype(np.float32)
+    _, first = np.unique(v, axis=0, return_index=True)
+    v = v[np.sort(first)].astype(np.float64)
+    hull = ConvexHull(v)
+    if not np.all(hull.equations[:, 3] < 0):
+        raise ValueError("mesh origin is not strictly inside its convex hull (needed as the MPR interior point)")
+    return v[np.sort(hull.vertices)]
+
+
 # --------------------------------------------------------------------------- defaults
 class _Defaults:
     def __init__(self, parent=None):
@@ -459,7 +479,7 @@ class _Compiler:
                 name = ma.get("name", os.path.splitext(os.path.basename(f))[0])
                 tri = read_stl(f, _vec(ma.get("scale"), default=[1, 1, 1]))
                 vol, com, I = mesh_inertia_legacy(tri)
-                self.meshes[name] = dict(vol=vol, com=com, I=I, ntri=len(tri), file=f)
+                self.meshes[name] = dict(vol=vol, com=com, I=I, ntri=len(tri), file=f, tri=tri, hull=None)
         for c in root.findall("contact"):
             for e in c.findall("exclude"):
                 self.excludes.append((e.attrib["body1"], e.attrib["body2"]))
@@ -595,10 +615,34 @@ class _Compiler:
             elif t == GEOM_ELLIPSOID:
                 rb.append(max(s))
             elif t == GEOM_MESH:
-                rb.append(-1.0)  # filled by the mesh collider when one is attached
+                rb.append(-1.0)  # collidable mesh geoms: filled below from the hull
             else:
                 rb.append(0.0)
         m.geom_rbound = np.array(rb)
+        # convex hulls of the meshes that collidable geoms reference (lift: "can").  The geom keeps the
+        # frame the XML gives it (MuJoCo re-expresses it in the mesh's inertial frame; the world-space
+        # hull is the same), the hull vertices are stored in that frame.
+        mesh_ids, vert_adr, vert_num, verts = {}, [], [], []
+        m.geom_dataid = np.full(len(G), -1, dtype=np.int32)
+        for gi, g in enumerate(G):
+            if g["type"] != GEOM_MESH or not (g["contype"] or g["conaffinity"]):
+                continue
+            name = g["mesh"]
+            if name not in mesh_ids:
+                me = self.meshes[name]
+                if me["hull"] is None:
+                    me["hull"] = mesh_hull_vertices(me["tri"])
+                mesh_ids[name] = len(vert_adr)
+                vert_adr.append(sum(vert_num))
+                vert_num.append(len(me["hull"]))
+                verts.append(me["hull"])
+            m.geom_dataid[gi] = mesh_ids[name]
+            m.geom_rbound[gi] = np.sqrt((self.meshes[name]["hull"] ** 2).sum(1).max())
+        m.nmesh = len(vert_adr)
+        m.mesh_vertadr = np.array(vert_adr, dtype=np.int32)
+        m.mesh_vertnum = np.array(vert_num, dtype=np.int32)
+        m.mesh_vert = np.concatenate(verts).reshape(-1, 3) if verts else np.zeros((0, 3))
+        m.collision_mesh_names = np.array(list(mesh_ids.keys())).astype(str)
 
         m.site_bodyid = np.array([s["body"] for s in S], dtype=np.int32)
         m.site_pos = np.array([s["pos"] for s in S]).reshape(-1, 3)

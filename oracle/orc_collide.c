@@ -33,6 +33,8 @@ typedef struct {
     R *jnt_pos, *jnt_axis, *jnt_range, *qpos0;
     int *geom_type, *geom_bodyid, *geom_contype, *geom_conaffinity;
     R *geom_pos, *geom_mat, *geom_size, *geom_margin, *geom_rbound;
+    int *geom_dataid, *mesh_vertadr, *mesh_vertnum; /* convex-hull vertices of collision meshes */
+    R *mesh_vert;
     int *site_bodyid;
     R *site_pos, *site_mat;
     int npair;
@@ -96,6 +98,10 @@ void *orc_scene_create(const mopa_model_desc *d, const int32_t *ignored_pairs, i
     s->geom_size = dupr(d->geom_size, 3 * d->ngeom);
     s->geom_margin = dupr(d->geom_margin, d->ngeom);
     s->geom_rbound = dupr(d->geom_rbound, d->ngeom);
+    s->geom_dataid = dupi(d->geom_dataid, d->ngeom);
+    s->mesh_vertadr = dupi(d->mesh_vertadr, d->nmesh);
+    s->mesh_vertnum = dupi(d->mesh_vertnum, d->nmesh);
+    s->mesh_vert = dupr(d->mesh_vert, 3 * d->nmeshvert);
     s->geom_mat = (R *)malloc(sizeof(R) * 9 * (d->ngeom + 1));
     for (int g = 0; g < d->ngeom; g++) {
         R q[4] = {(R)d->geom_quat[4 * g], (R)d->geom_quat[4 * g + 1], (R)d->geom_quat[4 * g + 2], (R)d->geom_quat[4 * g + 3]};
@@ -144,6 +150,7 @@ void orc_scene_destroy(void *h) {
     free(s->geom_type); free(s->geom_bodyid); free(s->geom_contype); free(s->geom_conaffinity);
     free(s->geom_pos); free(s->geom_mat); free(s->geom_size); free(s->geom_margin); free(s->geom_rbound);
     free(s->site_bodyid); free(s->site_pos); free(s->site_mat);
+    free(s->geom_dataid); free(s->mesh_vertadr); free(s->mesh_vertnum); free(s->mesh_vert);
     free(s->pair_g1); free(s->pair_g2); free(s->xpos); free(s->xquat); free(s->xmat); free(s->gpos); free(s->gmat);
     free(s);
 }
@@ -235,6 +242,26 @@ static R plane_box(const R *pp, const R *pm, const R *c, const R *m, const R *sz
     mulMTV(l, m, n); /* plane normal in box frame */
     R ext = MAD(FABS_(l[2]), sz[2], MAD(FABS_(l[1]), sz[1], FABS_(l[0]) * sz[0]));
     return dot3(n, d) - ext;
+}
+/* index of the hull vertex that is extreme along the LOCAL direction l (first maximum) */
+static int hull_extreme(const R *vert, int n, const R *l) {
+    int best = 0;
+    R bd = dot3(vert, l);
+    for (int i = 1; i < n; i++) {
+        R di = dot3(vert + 3 * i, l);
+        if (di > bd) { bd = di; best = i; }
+    }
+    return best;
+}
+
+/* plane - convex hull: lowest hull vertex along the plane normal */
+static R plane_mesh(const R *pp, const R *pm, const R *c, const R *m, const R *vert, int nvert) {
+    R n[3], d[3], l[3], nl[3];
+    col3(n, pm, 2);
+    sub3(d, c, pp);
+    mulMTV(l, m, n);
+    nl[0] = -l[0]; nl[1] = -l[1]; nl[2] = -l[2];
+    return dot3(n, d) + dot3(vert + 3 * hull_extreme(vert, nvert, nl), l);
 }
 static R sphere_sphere(const R *c1, R r1, const R *c2, R r2) {
     R d[3];
@@ -345,11 +372,24 @@ static R box_box(const R *c1, const R *m1, const R *sz1, const R *c2, const R *m
 }
 
 /* ---------------------------------------------------------------- generic convex: MPR */
-typedef struct { int type; const R *pos, *mat, *size; } cvx;
+typedef struct { int type; const R *pos, *mat, *size; const R *vert; int nvert; } cvx;
 
 /* support point of a convex geom in world direction dir (unit length).
    Capsules and cylinders only use their axis (z column of the frame). */
 static void support(R *out, const cvx *g, const R *dir) {
+    if (g->type == MOPA_GEOM_MESH) { /* convex hull of the mesh: extreme vertex (libccd support of mjc_Convex) */
+        R l[3], w[3];
+        mulMTV(l, g->mat, dir);
+        mulMV(w, g->mat, g->vert + 3 * hull_extreme(g->vert, g->nvert, l));
+        add3(out, g->pos, w);
+        return;
+    }
+    if (g->type == MOPA_GEOM_SPHERE) {
+        out[0] = MAD(dir[0], g->size[0], g->pos[0]);
+        out[1] = MAD(dir[1], g->size[0], g->pos[1]);
+        out[2] = MAD(dir[2], g->size[0], g->pos[2]);
+        return;
+    }
     if (g->type == MOPA_GEOM_BOX) {
         R l[3], p[3], w[3];
         mulMTV(l, g->mat, dir);
@@ -549,13 +589,18 @@ static R pair_dist(const orc_scene *s, int g1, int g2) {
         if (t2 == MOPA_GEOM_CAPSULE) return plane_capsule(c1, m1, c2, m2, z2);
         if (t2 == MOPA_GEOM_CYLINDER) return plane_cylinder(c1, m1, c2, m2, z2);
         if (t2 == MOPA_GEOM_BOX) return plane_box(c1, m1, c2, m2, z2);
+        if (t2 == MOPA_GEOM_MESH) {
+            int me = s->geom_dataid[g2];
+            return plane_mesh(c1, m1, c2, m2, s->mesh_vert + 3 * s->mesh_vertadr[me], s->mesh_vertnum[me]);
+        }
         return ORC_BIG;
     case MOPA_GEOM_SPHERE:
         if (t2 == MOPA_GEOM_SPHERE) return sphere_sphere(c1, z1[0], c2, z2[0]);
         if (t2 == MOPA_GEOM_CAPSULE) return sphere_capsule(c1, z1[0], c2, m2, z2);
         if (t2 == MOPA_GEOM_CYLINDER) return sphere_cylinder(c1, z1[0], c2, m2, z2);
         if (t2 == MOPA_GEOM_BOX) return sphere_box(c1, z1[0], c2, m2, z2);
-        return ORC_BIG;
+        if (t2 != MOPA_GEOM_MESH) return ORC_BIG;
+        break;
     case MOPA_GEOM_CAPSULE:
         if (t2 == MOPA_GEOM_CAPSULE) return capsule_capsule(c1, m1, z1, c2, m2, z2);
         break;
@@ -565,8 +610,10 @@ static R pair_dist(const orc_scene *s, int g1, int g2) {
     default:
         break;
     }
-    if (t2 == MOPA_GEOM_MESH || t1 == MOPA_GEOM_MESH) return ORC_BIG; /* mesh colliders: not yet restated */
-    cvx a = {t1, c1, m1, z1}, b = {t2, c2, m2, z2};
+    /* everything else, including every pair with a mesh geom (convex hull), goes through MPR */
+    cvx a = {t1, c1, m1, z1, 0, 0}, b = {t2, c2, m2, z2, 0, 0};
+    if (t1 == MOPA_GEOM_MESH) { int me = s->geom_dataid[g1]; a.vert = s->mesh_vert + 3 * s->mesh_vertadr[me]; a.nvert = s->mesh_vertnum[me]; }
+    if (t2 == MOPA_GEOM_MESH) { int me = s->geom_dataid[g2]; b.vert = s->mesh_vert + 3 * s->mesh_vertadr[me]; b.nvert = s->mesh_vertnum[me]; }
     R depth;
     if (mpr_penetration(&a, &b, &depth)) return -depth;
     return ORC_BIG;

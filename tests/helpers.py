@@ -25,3 +25,25 @@ def random_qpos(model, n, seed, ref, spread=1.0):
     q = np.tile(model.qpos0, (n, 1))
     q[:, ref] = rng.uniform(lo, hi, (n, len(ref)))
     return q.astype(np.float32).astype(np.float64)
+
+
+def lift_random_qpos(model, n, seed, ref, fk_scene=None, floating=0.5):
+    """SawyerLiftObstacle-v0 states: arm ~ U(joint range) and the can ("cube" free joint) either at its keyframe
+    pose in the bin or — for a `floating` fraction of the states — at a random orientation near the gripper
+    (grip_site + U(-0.1, 0.1)^3, through the oracle's FK when `fk_scene` is given) or anywhere in the arm's workspace,
+    so that the mesh collider decides.  All values fp32-representable."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q = random_qpos(model, n, seed + 1, ref)
+    a = model.get_joint_qpos_addr("cube")[0]
+    fl = rng.random(n) < floating
+    pos = np.stack([rng.uniform(0.3, 0.9, n), rng.uniform(-0.5, 0.5, n), rng.uniform(0.8, 1.4, n)], 1)
+    if fk_scene is not None:
+        site = model.names["site"].index("grip_site")
+        off = rng.uniform(-0.1, 0.1, (n, 3))
+        for i in np.nonzero(fl)[0][::2]:
+            pos[i] = fk_scene.fk(q[i])["site_xpos"][site] + off[i]
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    q[fl, a:a + 3] = pos[fl]
+    q[fl, a + 3:a + 7] = quat[fl]
+    return q.astype(np.float32).astype(np.float64)

@@ -142,3 +142,85 @@ def test_golden_validity_words(push_scene, push_model):
     assert np.array_equal(w64, g["valid_f64"])
     # fp32 arithmetic flips no boolean on this sample (report, target 0)
     assert int(((w & 1) != w64).sum()) == 0
+
+
+# ---------------------------------------------------------------------------- mesh collider (lift scene: the can)
+@pytest.fixture(scope="module")
+def lift_scene(oracle_built):
+    from helpers import planner_setup as ps
+    from mopa_rl_b200.model import load_model
+
+    m = load_model("SawyerLiftObstacle-v0")
+    ignored, passive, ref = ps(m)
+    return (m, oracle_built.OracleScene(m, ignored, -0.002, "f32"), oracle_built.OracleScene(m, ignored, -0.002, "f64"),
+            oracle_built.OracleScene(m, [], -0.002, "f64"), ref)
+
+
+def test_mesh_hull_compiled(lift_scene):
+    """The can's convex hull (env/assets/objects/meshes/can.stl, 956 triangles): 106 vertices that contain the geom
+    origin strictly (MPR's interior point), bounding radius = farthest hull vertex."""
+    m = lift_scene[0]
+    cube = m.geom_name2id("cube")
+    assert m.nmesh == 1 and int(m.mesh_vertnum[0]) == 106 and m.geom_dataid[cube] == 0
+    assert (m.geom_dataid >= 0).sum() == 1                                    # visual meshes carry no hull
+    v = m.mesh_vert
+    assert np.array_equal(v, v.astype(np.float32).astype(np.float64))         # fp32-representable on both sides
+    assert np.isclose(m.geom_rbound[cube], np.linalg.norm(v, axis=1).max())
+    assert v[:, 2].min() < -0.04 and v[:, 2].max() > 0.039 and np.abs(v[:, :2]).max() < 0.0252
+    from scipy.spatial import ConvexHull
+
+    h = ConvexHull(v)
+    assert len(h.vertices) == len(v) and (h.equations[:, 3] < 0).all()
+
+
+def test_mesh_known_answers(lift_scene):
+    """plane - hull analytically, box - hull through MPR: the upright can sunk 5 mm into the table top."""
+    m, s32, s64, s_all, ref = lift_scene
+    cube = m.geom_name2id("cube")
+    a = m.get_joint_qpos_addr("cube")[0]
+    g1, g2 = s_all.pairs()
+    zmin = m.mesh_vert[:, 2].min()
+    table = m.geom_name2id("table_collision")
+    plane = [g for g in range(m.ngeom) if m.geom_type[g] == 0 and (m.geom_contype[g] or m.geom_conaffinity[g])][0]
+    ip = [i for i in range(len(g1)) if {g1[i], g2[i]} == {plane, cube}][0]
+    it = [i for i in range(len(g1)) if {g1[i], g2[i]} == {table, cube}][0]
+    q = m.qpos0.copy()
+    q[a:a + 7] = [0.66, 0.5, 0.81 - zmin - 0.005, 1, 0, 0, 0]               # table top is at z = 0.40 + 0.41
+    d = s_all.pair_dists(q)
+    plane_z = m.geom_pos[plane][2] + m.body_pos[m.geom_bodyid[plane]][2]
+    assert abs(d[ip] - (q[a + 2] + zmin - plane_z)) < 1e-12
+    assert abs(d[it] + 0.005) < 2e-5
+    q[a + 2] += 0.006                                                         # 1 mm above the table: no penetration
+    assert s_all.pair_dists(q)[it] > 1e9
+    # tilted by 90 degrees about x: the can lies on its side, lowest point = hull radius in the (y, z) plane
+    q[a:a + 7] = [0.66, 0.5, 0.81 + 0.02, np.sqrt(0.5), np.sqrt(0.5), 0, 0]
+    d = s_all.pair_dists(q)
+    lowest = m.mesh_vert[:, 1].min()   # world z of a vertex = y_local after the rotation
+    assert abs(d[it] - (0.02 + lowest)) < 2e-5 and d[it] < 0
+
+
+def test_lift_scene_invariants_and_golden(lift_scene):
+    from helpers import lift_random_qpos
+
+    m, s32, s64, s_all, ref = lift_scene
+    cube = m.geom_name2id("cube")
+    assert s32.is_valid(m.qpos0)[0] == 1                                      # keyframe: can in the bin, ignored pairs
+    assert s_all.is_valid(m.qpos0)[0] & 1 in (0, 1)
+    g = np.load(os.path.join(GOLD, "lift_validity.npz"))
+    q = g["qpos"].astype(np.float64)
+    assert np.array_equal(q, lift_random_qpos(m, len(q), int(g["seed"]), ref, s64))
+    w, d = s32.is_valid(q, True)
+    assert np.array_equal(w, g["words_f32"])
+    assert np.allclose(d, g["min_dist_f32"], atol=1e-6)
+    assert np.array_equal(s64.is_valid(q) & 1, g["valid_f64"])
+    # the can decides some of the states: first offending pair involves the mesh geom
+    g1, g2 = s32.pairs()
+    first = (w[(w & 1) == 0] >> 8).astype(int) - 1
+    n_mesh = int(((g1[first] == cube) | (g2[first] == cube)).sum())
+    assert n_mesh >= 50, n_mesh
+    # moving only the can changes validity of states that were valid
+    a = m.get_joint_qpos_addr("cube")[0]
+    ok = q[(w & 1) == 1][:512].copy()
+    ok[:, a:a + 3] = np.float32(0.0)                                         # can inside the pedestal region at the arm's base
+    ok[:, a + 2] = np.float32(0.95)
+    assert (s32.is_valid(ok) & 1).mean() < 1.0

@@ -81,3 +81,37 @@ def test_passive_dims_frozen_and_key_dependence(planners, push_model):
         L = a["path_len"][i]
         if L:
             assert np.array_equal(a["path"][i, :L][:, passive], np.tile(start[i][passive].astype(np.float32), (L, 1)))
+
+
+def test_lift_plan_matches_oracle(oracle_built):
+    """RRT-Connect on the lift scene (mesh collider): the can floats next to the arm so that edges are checked
+    against the hull; status / iterations / node ids / waypoints bit-identical to the oracle."""
+    from helpers import lift_random_qpos
+    from mopa_rl_b200.capi import NativePlanner
+    from mopa_rl_b200.model import load_model
+
+    m = load_model("SawyerLiftObstacle-v0")
+    ignored, passive, ref = planner_setup(m)
+    native = NativePlanner(m, passive, ignored, -0.002, 0.1, seed=77)
+    scene = oracle_built.OracleScene(m, ignored, -0.002, "f32")
+    adr, lo, hi, so2 = oracle_built.space_from_model(m, passive)
+    orc = oracle_built.OraclePlanner(scene, adr, lo, hi, so2, 0.1, 0.005, seed=77, max_nodes=4096)
+    n = 32
+    q = random_qpos(m, 12 * n, 3, ref, spread=1.0)
+    a = m.get_joint_qpos_addr("cube")[0]
+    q[:, a:a + 7] = np.array([0.55, 0.1, 1.05, 0.8, 0.0, 0.6, 0.0], dtype=np.float32)   # can in the workspace, tilted
+    v = q[(scene.is_valid(q) & 1) == 1]
+    assert len(v) >= 2 * n
+    start, goal = v[:n], v[n:2 * n]
+    keys = np.arange(n, dtype=np.uint64) + 500
+    out = native.plan_host(start, goal, keys, max_iter=300, max_path=512)
+    n_ok = 0
+    for i in range(n):
+        r = orc.plan(start[i], goal[i], int(keys[i]), 300, 512)
+        assert out["status"][i] == r["status"] and out["iters"][i] == r["iters"], i
+        L = len(r["path"])
+        assert out["path_len"][i] == L
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.array_equal(out["node_ids"][i, :L], r["node_ids"]) and np.array_equal(out["path"][i, :L], r["path"])
+    assert n_ok >= n // 4

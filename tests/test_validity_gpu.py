@@ -68,3 +68,64 @@ def test_passive_dims_matter_only_where_they_should(push_pair, push_model):
     w3 = native.is_valid_host(q3, flags=1, return_words=True)[1]
     assert np.array_equal(w3, orc.is_valid(q3))
     assert (w3 & 1).mean() < base.mean()
+
+
+# ---------------------------------------------------------------------------- lift scene: mesh collider (hull of the can)
+@pytest.fixture(scope="module")
+def lift_pair(oracle_built):
+    from mopa_rl_b200.capi import NativePlanner
+    from mopa_rl_b200.model import load_model
+
+    m = load_model("SawyerLiftObstacle-v0")
+    ignored, passive, ref = planner_setup(m)
+    native = NativePlanner(m, passive, ignored, -0.002, 0.1, seed=1234)
+    orc = oracle_built.OracleScene(m, ignored, -0.002, "f32")
+    orc64 = oracle_built.OracleScene(m, ignored, -0.002, "f64")
+    return m, native, orc, orc64, ref, ignored, passive
+
+
+def test_lift_pair_list_and_golden(lift_pair):
+    import os
+
+    m, native, orc, orc64, ref, _, _ = lift_pair
+    g1, g2 = native.pairs()
+    o1, o2 = orc.pairs()
+    assert native.n_pairs == orc.npair and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    cube = m.geom_name2id("cube")
+    assert ((g1 == cube) | (g2 == cube)).sum() == 22
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lift_validity.npz"))
+    w = native.is_valid_host(g["qpos"].astype(np.float64), flags=1, return_words=True)[1]
+    assert np.array_equal(w, g["words_f32"])
+
+
+@pytest.mark.parametrize("seed,n", [(11, 60000), (12, 20000)])
+def test_lift_random_states_bit_exact(lift_pair, seed, n):
+    from helpers import lift_random_qpos
+
+    m, native, orc, orc64, ref, _, _ = lift_pair
+    q = lift_random_qpos(m, n, seed, ref, orc64 if n <= 20000 else None)
+    ow = orc.is_valid(q)
+    w = native.is_valid_host(q, flags=1, return_words=True)[1]
+    assert np.array_equal(w, ow), "first-offending-pair words differ at %d states" % (w != ow).sum()
+    assert np.array_equal(native.is_valid_host(q, flags=0), (ow & 1).astype(np.uint8))
+    assert 0.1 < (ow & 1).mean() < 0.7
+
+
+def test_lift_can_only_scene_bit_exact(lift_pair, oracle_built):
+    """Every pair that does not involve the can ignored: validity is decided by the mesh pairs alone
+    (plane / sphere / capsule / cylinder / box against the hull)."""
+    from helpers import lift_random_qpos
+    from mopa_rl_b200.capi import NativePlanner
+
+    m, _, orc, orc64, ref, ignored, passive = lift_pair
+    cube = m.geom_name2id("cube")
+    g1, g2 = orc.pairs()
+    others = [(int(a), int(b)) for a, b in zip(g1, g2) if a != cube and b != cube]
+    native = NativePlanner(m, passive, ignored + others, -0.002, 0.1, seed=1)
+    o = oracle_built.OracleScene(m, ignored + others, -0.002, "f32")
+    assert native.n_pairs == o.npair == 22
+    q = lift_random_qpos(m, 16384, 5, ref, orc64, floating=1.0)
+    ow = o.is_valid(q)
+    w = native.is_valid_host(q, flags=1, return_words=True)[1]
+    assert np.array_equal(w, ow), "mesh-pair words differ at %d states" % (w != ow).sum()
+    assert 0.02 < ((ow & 1) == 0).mean() < 0.9

@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import PUSH_INIT_QPOS, planner_setup, random_qpos  # noqa: E402
+from helpers import PUSH_INIT_QPOS, lift_random_qpos, planner_setup, random_qpos  # noqa: E402
 from mopa_rl_b200.dynmodel import DynModel  # noqa: E402
 from mopa_rl_b200.envs import push_reset_state  # noqa: E402
 from mopa_rl_b200.model import load_model  # noqa: E402
@@ -132,4 +132,14 @@ for _ in range(10):
     recs.append(runner.macro_step())
     recs.extend(runner.extra_records)
 np.savez_compressed(os.path.join(out, "push_rollout_reuse.npz"), records=np.array(recs, np.float32))
+
+# 7. lift scene (mesh collider: convex hull of the can): validity words for seeded states (arm + can pose)
+ml = load_model("SawyerLiftObstacle-v0")
+ign_l, passive_l, ref_l = planner_setup(ml)
+sl32 = oracle.OracleScene(ml, ign_l, -0.002, "f32")
+sl64 = oracle.OracleScene(ml, ign_l, -0.002, "f64")
+ql = lift_random_qpos(ml, 4096, 4321, ref_l, sl64)
+wl, dl = sl32.is_valid(ql, True)
+np.savez_compressed(os.path.join(out, "lift_validity.npz"), seed=4321, qpos=ql.astype(np.float32), words_f32=wl,
+                    valid_f64=(sl64.is_valid(ql) & 1).astype(np.uint8), min_dist_f32=dl.astype(np.float32))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
