@@ -115,3 +115,68 @@ def test_lift_plan_matches_oracle(oracle_built):
             n_ok += 1
             assert np.array_equal(out["node_ids"][i, :L], r["node_ids"]) and np.array_equal(out["path"][i, :L], r["path"])
     assert n_ok >= n // 4
+
+
+def _pusher_setup(m):
+    """PusherObstacle-v0 planner inputs as rl/trainer.py:62-75 derives them from env/pusher/pusher_obstacle.py:
+    manipulation geom `box` x static obstacle geoms ignored, joints 0-3 active (joint0 unlimited -> SO(2))."""
+    static = [m.geom_name2id("obstacle%d_geom" % i) for i in range(1, 8)]
+    box = m.geom_name2id("box")
+    ignored = [(min(box, g), max(box, g)) for g in static]
+    ref = [m.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+    passive = [i for i in range(m.nq) if i not in ref]
+    return ignored, passive, ref
+
+
+def _pusher_states(m, ref, n, seed, spread=1.0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    q = np.tile(m.qpos0, (n, 1))
+    q[:, ref[0]] = rng.uniform(-3.14, 3.14, n)          # unlimited hinge: the reference's +-3.14 convention
+    for k in (1, 2, 3):
+        j = list(m.jnt_qposadr).index(ref[k])
+        q[:, ref[k]] = rng.uniform(m.jnt_range[j, 0] * spread, m.jnt_range[j, 1] * spread, n)
+    return q.astype(np.float32).astype(np.float64)
+
+
+def test_pusher_validity_and_plan_match_oracle(oracle_built):
+    """BASELINE configs[0] scene (2-D pusher, 4 hinges, joint0 on SO(2)): validity words and RRT-Connect results
+    bit-identical to the oracle with the reference's Pusher settings (range 0.2, contact_threshold -0.0015)."""
+    from mopa_rl_b200.capi import NativePlanner
+    from mopa_rl_b200.model import load_model
+
+    m = load_model("PusherObstacle-v0")
+    ignored, passive, ref = _pusher_setup(m)
+    native = NativePlanner(m, passive, ignored, -0.0015, 0.2, seed=9)
+    scene = oracle_built.OracleScene(m, ignored, -0.0015, "f32")
+    g1, g2 = native.pairs()
+    o1, o2 = scene.pairs()
+    assert native.n_pairs == scene.npair == 80 and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+    q = _pusher_states(m, ref, 50000, 5)
+    ow = scene.is_valid(q)
+    assert np.array_equal(native.is_valid_host(q, flags=1, return_words=True)[1], ow)
+    assert 0.05 < (ow & 1).mean() < 0.5
+    adr, lo, hi, so2 = oracle_built.space_from_model(m, passive)
+    assert list(so2) == [1, 0, 0, 0]
+    orc = oracle_built.OraclePlanner(scene, adr, lo, hi, so2, 0.2, 0.005, seed=9, max_nodes=4096)
+    v = q[(ow & 1) == 1]
+    n = 48
+    start, goal = v[:n], v[n:2 * n]
+    keys = np.arange(n, dtype=np.uint64) + 100
+    out = native.plan_host(start, goal, keys, max_iter=400, max_path=512)
+    n_ok = n_long = 0
+    for i in range(n):
+        r = orc.plan(start[i], goal[i], int(keys[i]), 400, 512)
+        assert out["status"][i] == r["status"] and out["iters"][i] == r["iters"], i
+        L = len(r["path"])
+        assert out["path_len"][i] == L
+        if r["status"] == 0:
+            n_ok += 1
+            n_long += r["iters"] > 1
+            assert np.array_equal(out["node_ids"][i, :L], r["node_ids"]) and np.array_equal(out["path"][i, :L], r["path"])
+            # SO(2): joint0 stays in [-pi, pi] and hops are measured around the circle
+            p = r["path"][:, ref]
+            assert np.abs(p[:, 0]).max() <= np.float32(np.pi)
+            d0 = np.abs(np.diff(p[:, 0]))
+            hop = np.minimum(d0, 2 * np.pi - d0) + np.abs(np.diff(p[:, 1:], axis=0)).sum(1)
+            assert hop.max() <= 0.2 + 1e-5
+    assert n_ok >= 5 and n_long >= 2   # random 4-hinge states in the cluttered scene: most pairs are not connectable in 400 iterations
