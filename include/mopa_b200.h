@@ -185,6 +185,9 @@ typedef struct mopa_rollout_config {
     const double *qpos0;          /* host, nq: reset pose of everything else */
     int32_t reuse_data, max_reuse_data;   /* rl/mopa_rollouts.py:223-302: up to max_reuse_data (<= 16) relabelled records per executed plan */
     uint64_t seed_reuse;          /* seed of the (start, goal) draws, keyed by env id and macro-action index */
+    int32_t discrete_action;      /* config.discrete_action (rl/mopa_rollouts.py:86-88): ac_type picks planner / direct execution;
+                                     direct actions are not divided by omega; record slot 47 carries ac_type */
+    int32_t pad_;
 } mopa_rollout_config;
 /* Counter slots of d_counters (int64[16]). */
 #define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting,reused"
@@ -203,6 +206,8 @@ void mopa_rollout_destroy(mopa_rollout *r);
 int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
 /* d_actions: device float[n][7], the policy's action for every environment. */
 int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
+/* discrete_action handles: d_ac_type uint8[n] (0 = direct execution, 1 = motion planner), the policy's ac["ac_type"]. */
+int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const uint8_t *d_ac_type, void *stream);
 int mopa_rollout_busy(mopa_rollout *r);
 /* Diagnostics of the asynchronous planner: out4 = {device ms of the last finished RRT batch, batches finished, mean device
  * ms per batch, mean ticks between launch and finalisation}. */

@@ -75,6 +75,7 @@ struct RoDev {   // everything the kernels need, passed by value
     int heavy_work;              // Newton steps per env.step above which an environment counts as expensive
     // reuse_data (rl/mopa_rollouts.py:223-302): per-step history of the plan being executed, relabelled records
     int reuse_data, max_reuse;
+    int discrete;                // config.discrete_action: the policy's ac_type chooses planner / direct execution
     unsigned long long seed_reuse;
     float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
     double *rew_hist;            // [n][max_traj]      cumulative discounted reward after step i
@@ -171,7 +172,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     float xr[92];
                     for (int k = 0; k < 40; k++) xr[k] = oh[start * 40 + k];
                     for (int k = 0; k < 7; k++) xr[40 + k] = ia[k];
-                    xr[47] = 0.0f;
+                    xr[47] = S.discrete ? S.ac[(size_t)e * 8 + 7] : 0.0f;   // inter_subgoal_ac["ac_type"] = ac["ac_type"] (:266-267)
                     xr[48] = (float)((rh[goal] - rh[start]) * pow(S.discount, -(double)(start + 1)));
                     xr[49] = S.done_hist[(size_t)e * S.max_traj + goal] ? 1.0f : 0.0f;
                     xr[50] = (float)(goal - start - 1);
@@ -214,7 +215,8 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
 }
 
 // ---- 2. new macro actions: direct action, or planner target (SACAgent.convert2planner_displacement + target clip)
-__global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__restrict__ actions) {
+// config.discrete_action (rl/mopa_rollouts.py:86-88, 104-111): the branch is chosen by the policy's ac_type instead of |a| > omega.
+__global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__restrict__ actions, const unsigned char *__restrict__ ac_type) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n || !S.need[e]) return;
     float a32[7];
@@ -226,6 +228,7 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
         S.ac[(size_t)e * 8 + k] = a;
         if (fabs((double)a) > S.omega) is_mp = true;
     }
+    if (S.discrete) { is_mp = ac_type[e] != 0; S.ac[(size_t)e * 8 + 7] = is_mp ? 1.0f : 0.0f; }
     S.macro_index[e] += 1;
     for (int k = 0; k < 40; k++) S.prev_ob[(size_t)e * 40 + k] = B.obs[(size_t)e * 40 + k];
     S.meta_rew[e] = 0.0; S.executed[e] = 0; S.macro_done[e] = 0; S.pending[e] = 1;
@@ -514,7 +517,8 @@ __global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
     S.ids[heavy ? pos : S.n - 1 - pos] = e;
     float *sa = S.step_action + (size_t)e * 8;
     if (kind == 0) {
-        for (int k = 0; k < 7; k++) sa[k] = (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
+        // direct execution: ac / omega, or the raw action with discrete_action (rl/mopa_rollouts.py:347-352)
+        for (int k = 0; k < 7; k++) sa[k] = S.discrete ? S.ac[(size_t)e * 8 + k] : (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
     } else if (kind == 1) {
         int pos = S.traj_pos[e];
         if (pos > S.max_traj - 1) pos = S.max_traj - 1;
@@ -619,6 +623,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
+    S.discrete = cfg->discrete_action ? 1 : 0;
     S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_count && reuse_capacity > 0) ? 1 : 0;
     S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
     S.ep_stats = d_ep_stats;
@@ -725,15 +730,20 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
 
 /* Second half: d_actions [n][7] = the policy's output for every environment (used where a new macro
  * action starts).  Planning glue, RRT launch, env.step for every non-waiting environment, bookkeeping. */
-int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
+int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) { return mopa_rollout_step_discrete(r, d_actions, nullptr, stream); }
+
+/* Same with the policy's ac_type [n] (0 = direct execution, 1 = motion planner); required when the handle was created
+ * with discrete_action (scripts/3d/push/mopa_discrete.sh), ignored otherwise. */
+int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const uint8_t *d_ac_type, void *stream) {
     if (!r || !d_actions) return MOPA_ERR_ARG;
+    if (r->S.discrete && !d_ac_type) { mopa_set_error("mopa_rollout_step: the handle runs discrete_action, ac_type is required"); return MOPA_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     RoDev &S = r->S;
     mopa_planner *p = r->planner;
     RO_TRY(cudaSetDevice(r->env->device));
     const int blocks = (S.n + 127) / 128;
     RrtBatch &Q = r->batch[r->fill];
-    ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, d_actions);
+    ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, d_actions, d_ac_type);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32a, S.row, S.n, S.res_a, 0, p->sm_count, st, S.cnt_plan, 1));
     ro_backoff_kernel<<<(S.n * 32 + 127) / 128, 128, 0, st>>>(S, r->buf);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32b, S.row, S.n * S.num_trials, S.res_b, 0, p->sm_count, st, S.cnt_back, S.num_trials));

@@ -43,6 +43,7 @@ class MoPAConfig:
     seed = 1234
     reuse_data = False         # scripts/3d/push/mopa.sh sets True: relabel (start, goal) pairs of every executed plan
     max_reuse_data = 15
+    discrete_action = False    # scripts/3d/*/mopa_discrete.sh (with omega = 0): the policy's ac_type picks planner / direct
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -89,8 +90,8 @@ class CounterPolicy:
     """Uniform [-1,1]^7 actions that are a pure function of (seed, env id, macro-action index):
     the stand-in for random_exploration whose draws do not depend on batch composition."""
 
-    def __init__(self, torch, device, seed):
-        self.torch, self.device, self.seed = torch, device, int(seed)
+    def __init__(self, torch, device, seed, discrete=False):
+        self.torch, self.device, self.seed, self.discrete = torch, device, int(seed), discrete
 
     def __call__(self, obs, env_ids, macro_index):
         from . import rng
@@ -98,12 +99,20 @@ class CounterPolicy:
         e = env_ids.cpu().numpy().astype(np.uint64)[:, None]
         c = macro_index.cpu().numpy().astype(np.uint64)[:, None]
         u = rng.uniform01(self.seed, e, c, np.arange(7, dtype=np.uint64)[None, :])
-        return self.torch.as_tensor((2.0 * u - 1.0).astype(np.float32), device=self.device)
+        ac = self.torch.as_tensor((2.0 * u - 1.0).astype(np.float32), device=self.device)
+        if not self.discrete:
+            return ac
+        # discrete_action: ac_type ~ Discrete(2) from draw 7 of the same stream (ac_space.spaces["ac_type"], rl/trainer.py:90-91)
+        t = rng.uniform01(self.seed, e[:, 0], c[:, 0], np.uint64(7)) < 0.5
+        return ac, self.torch.as_tensor(t.astype(np.uint8), device=self.device)
 
 
 class VecMoPARolloutRunner:
     def __init__(self, venv, config=None, policy=None, transition_capacity=1 << 20):
         import torch
+
+        if config is not None and (config.discrete_action or config.reuse_data):
+            raise NotImplementedError("discrete_action / reuse_data are implemented by NativeMoPARolloutRunner only")
 
         self.torch = torch
         self.venv, self.cfg = venv, config or MoPAConfig()
@@ -496,7 +505,7 @@ class _RolloutConfig(_C.Structure):
                [(k, _C.c_double) for k in ("omega", "action_range", "ac_scale", "discount", "step_size", "joint_margin", "range")] + \
                [("seed_env", _C.c_uint64), ("env_id_offset", _C.c_int64), ("jnt_lo", _C.c_double * 7), ("jnt_hi", _C.c_double * 7),
                 ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p), ("reuse_data", _C.c_int32), ("max_reuse_data", _C.c_int32),
-                ("seed_reuse", _C.c_uint64)]
+                ("seed_reuse", _C.c_uint64), ("discrete_action", _C.c_int32), ("pad_", _C.c_int32)]
 
 
 class NativeMoPARolloutRunner:
@@ -504,7 +513,8 @@ class NativeMoPARolloutRunner:
     libmopa_b200 (csrc/rollout.cu): no host round trip inside a tick, the policy is evaluated once per
     tick on the observations of ALL environments (its output is used where a macro action starts).
 
-    ``policy(obs [n,40] f32, env_gid [n] i64, macro_index [n] i64) -> [n,7]`` actions in [-1, 1].
+    ``policy(obs [n,40] f32, env_gid [n] i64, macro_index [n] i64) -> [n,7]`` actions in [-1, 1]; with
+    ``config.discrete_action`` it returns ``(actions [n,7], ac_type [n])`` (1 = motion planner, 0 = direct execution).
     """
 
     def __init__(self, venv, config=None, policy=None, transition_capacity=1 << 20, rrt_capacity=1024):
@@ -544,6 +554,7 @@ class NativeMoPARolloutRunner:
         self._qpos0 = np.ascontiguousarray(m.qpos0, dtype=np.float64)
         c.qpos0 = self._qpos0.ctypes.data
         c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
+        c.discrete_action = int(cfg.discrete_action)
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
                                           _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.c_void_p, _C.POINTER(_C.c_void_p)]
@@ -551,6 +562,7 @@ class NativeMoPARolloutRunner:
         L.mopa_rollout_destroy.restype = None
         L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
         L.mopa_rollout_step.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.mopa_rollout_step_discrete.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p]
         L.mopa_rollout_busy.argtypes = [_C.c_void_p]
         L.mopa_rollout_launches.argtypes = [_C.c_void_p]
         L.mopa_rollout_launches.restype = _C.c_int64
@@ -584,9 +596,16 @@ class NativeMoPARolloutRunner:
     def tick(self, wait_rrt=False):
         self._check(self._L.mopa_rollout_pre(self.h, int(wait_rrt), self._stream()))
         ac = self.policy(self.venv.obs, self.env_gid, self.macro_index)
+        if self.cfg.discrete_action:   # policy -> (ac["default"] [n,7], ac["ac_type"] [n])
+            ac, ac_type = ac
+            ac_type = ac_type.to(device=self.dev, dtype=self.torch.uint8).contiguous()
         ac = ac.to(device=self.dev, dtype=self.torch.float32).contiguous()
-        self._check(self._L.mopa_rollout_step(self.h, ac.data_ptr(), self._stream()))
-        self._keep = ac
+        if self.cfg.discrete_action:
+            self._check(self._L.mopa_rollout_step_discrete(self.h, ac.data_ptr(), ac_type.data_ptr(), self._stream()))
+            self._keep = (ac, ac_type)
+        else:
+            self._check(self._L.mopa_rollout_step(self.h, ac.data_ptr(), self._stream()))
+            self._keep = ac
         self.ticks += 1
         self.last_emitted = (self.slab, self.emit_flag)
         # relabelled records of this tick: (slab [2n, 92], flags [2n]) - the first reuse_count rows are records

@@ -2,7 +2,7 @@
 environment, built on the CPU oracles (PushEnvOracle, OracleScene, OraclePlanner).  Follows:
 
   MoPARolloutRunner.run                 rl/mopa_rollouts.py:22-399   (train branch, every_steps=1,
-                                                                      no IK, no discrete action, no reuse_data)
+                                                                      no IK; discrete_action and reuse_data on request)
   SACAgent.is_planner_ac / convert2planner_displacement / plan / clip_qpos / simple_interpolate
                                         rl/sac_agent.py:148-318
   PlannerAgent.plan                     rl/planner_agent.py:42-52
@@ -117,18 +117,23 @@ class ScalarMoPARunner:
         if env.terminal:
             self.ob = self._reset()
         prev_ob = self.ob.copy()
-        ac = np.asarray(self.policy(self.gid, self.macro_index), np.float64)
-        ac = ac.astype(np.float32).astype(np.float64)
+        ac = self.policy(self.gid, self.macro_index)
+        discrete = bool(getattr(cfg, "discrete_action", False))
+        if discrete:                                               # ac = {"default": ..., "ac_type": ...}
+            ac, ac_type = ac
+        ac = np.asarray(ac, np.float64).astype(np.float32).astype(np.float64)
         self.macro_index += 1
         curr = env.qpos.copy()
-        is_mp = bool(np.any(np.abs(ac) > cfg.omega))
+        is_mp = bool(ac_type) if discrete else bool(np.any(np.abs(ac) > cfg.omega))   # rl/mopa_rollouts.py:86-88, 104-111
+        self._ac_type = float(is_mp) if discrete else 0.0
         steps = 0
         extra_src = None
         self.extra_records = []
         if is_mp:
             w = cfg.omega
-            disp = np.where(np.abs(ac) < w, ac / (w / cfg.ac_scale),
-                            np.sign(ac) * (cfg.ac_scale + (cfg.action_range - cfg.ac_scale) * ((np.abs(ac) - w) / (1 - w))))
+            with np.errstate(divide="ignore", invalid="ignore"):   # omega = 0 (discrete presets): the first branch is never selected
+                disp = np.where(np.abs(ac) < w, ac / (w / cfg.ac_scale),
+                                np.sign(ac) * (cfg.ac_scale + (cfg.action_range - cfg.ac_scale) * ((np.abs(ac) - w) / (1 - w))))
             target = curr.copy()
             target[:7] = np.clip(curr[:7] + disp, self.jlo, self.jhi)
             if cfg.invalid_target_handling and not self._valid(target):
@@ -167,7 +172,8 @@ class ScalarMoPARunner:
                 intra, steps = 0, 1
         else:
             self.counters["rl"] += 1
-            self.ob, rec_rew, done = env.step((ac / cfg.omega).astype(np.float32).astype(np.float64), is_planner=False)
+            direct = ac if discrete else (ac / cfg.omega).astype(np.float32).astype(np.float64)   # :347-352
+            self.ob, rec_rew, done = env.step(direct, is_planner=False)
             intra, steps = 0, 1
         env.prev_state = None                                       # env._reset_prev_state()
         self.env_steps += steps
@@ -176,6 +182,7 @@ class ScalarMoPARunner:
         rec = np.zeros(92, np.float32)
         no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
         rec[0:no], rec[40:47], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
+        rec[47] = self._ac_type
         return rec
 
     def _reuse(self, ob_list, rew_list, done_list, traj):
@@ -202,6 +209,7 @@ class ScalarMoPARunner:
             rec = np.zeros(92, np.float32)
             no = len(ob_list[start])
             rec[0:no], rec[40:47] = ob_list[start], a
+            rec[47] = self._ac_type                                                # inter_subgoal_ac["ac_type"] = ac["ac_type"]
             rec[48] = (rew_list[goal] - rew_list[start]) * cfg.discount_factor ** (-(start + 1))
             rec[49], rec[50], rec[52:52 + no] = float(done_list[goal]), goal - start - 1, ob_list[goal]
             self.extra_records.append(rec)

@@ -172,3 +172,56 @@ def test_run_episodes_reports_reference_episode_info(push_model, oracle_built):
     weight = push_model.body_mass[push_model.body_name2id("cube")] * 9.81
     assert 0.5 * weight * horizon < info["contact_force"] < 3.0 * weight * horizon, (info, weight)
     assert info["mp"] + info["rl"] + info["interpolation"] + info["mp_fail"] > 0
+
+
+def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model, oracle_built):
+    """config.discrete_action (scripts/3d/push/mopa_discrete.sh: omega = 0, reuse_data): the policy's ac_type picks
+    motion planner / direct execution (rl/mopa_rollouts.py:86-88, 104-111), direct actions are executed unscaled
+    (:347-352), relabelled records inherit ac_type (:266-267).  Record slot 47 carries ac_type."""
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    n, ticks, seed = 10, 50, 606
+    cfg = MoPAConfig(max_iter=150, seed=23, omega=0.0, discrete_action=True, reuse_data=True, max_reuse_data=15)
+    venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=30, env_id_offset=300)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 13, discrete=True))
+    for _ in range(ticks):
+        runner.tick()
+    runner.drain()
+    torch.cuda.synchronize()
+    c = runner.counters
+    rec = runner.transitions[:c["transitions"]].cpu().numpy()
+    assert c["rl"] > n and c["mp"] + c["interpolation"] > n
+
+    def policy(gid, k):
+        u = rng.uniform01(13, np.uint64(gid), np.uint64(k), np.arange(8, dtype=np.uint64))
+        return (2.0 * u[:7] - 1.0).astype(np.float32), bool(u[7] < 0.5)
+
+    ignored, passive, _ = planner_inputs(push_model)
+    dm = DynModel(push_model)
+    types, worst = set(), 0.0
+    for e in range(n):
+        gid = 300 + e
+        mine = list(rec[rec[:, 51] == gid])
+        ref = ScalarMoPARunner(push_model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=30)
+        k = 0
+        while k < len(mine):
+            for o in [ref.macro_step()] + list(ref.extra_records):
+                if k >= len(mine):
+                    break
+                r = mine[k]
+                assert np.allclose(r[40:47], o[40:47], atol=1e-6) and r[47] == o[47], (e, k, r[40:48], o[40:48])
+                assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])
+                assert abs(r[48] - o[48]) < 1e-5, (e, k)
+                d = max(np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+                worst = max(worst, d)
+                assert d < 1e-4, (e, k, d)
+                types.add(float(r[47]))
+                k += 1
+    assert types == {0.0, 1.0}
+    print("discrete_action: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
