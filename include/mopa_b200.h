@@ -112,7 +112,8 @@ int mopa_plan_host(mopa_planner *p, const double *start, const double *goal, con
 typedef struct mopa_env mopa_env;
 
 typedef struct mopa_sawyer_task {
-    int32_t kind;                 /* 0: SawyerPushObstacle-v0, 2: SawyerAssemblyObstacle-v0 (body_cube = peg, body_rclaw = the part that
+    int32_t kind;                 /* 0: SawyerPushObstacle-v0, 1: SawyerLiftObstacle-v0 (8-D action: 7 joints + gripper; body_cube = can),
+                                   * 2: SawyerAssemblyObstacle-v0 (body_cube = peg, body_rclaw = the part that
                                    * carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd) */
     int32_t arm_qadr[7], arm_vadr[7], arm_dof[7];   /* qpos / qvel addresses and simulated-dof indices of right_j0..6 */
     int32_t grip_qadr[2], grip_vadr[2];             /* rc_close, lc_close */
@@ -123,6 +124,10 @@ typedef struct mopa_sawyer_task {
     double target_base[3];                          /* body_pos of the target body */
     double ac_scale, distance_threshold, success_reward;
     double site_hole[3], site_hole_bottom[3];       /* assembly: sites "hole" / "hole_bottom" in their body frame */
+    /* lift (env/sawyer/sawyer_lift_obstacle.py:92-148): simulated-geom indices of the can and of the left / right finger geoms
+     * (l_finger_g0, l_finger_g1, l_fingertip_g0 / r_*; -1 = absent) whose contacts define has_grasp, and z of body bin1 */
+    int32_t geom_cube, geom_lfinger[3], geom_rfinger[3], pad_;
+    double bin_z;
 } mopa_sawyer_task;
 
 typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */

@@ -1039,6 +1039,14 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> 
         obs[o++] = 0.0f; obs[o++] = 0.0f;   // 38 observation floats, row padded to 40
         return;
     }
+    if (T.kind == 1) {   // SawyerLiftObstacleEnv._get_obs (:150-161): cube_pos, cube_quat (xyzw), gripper_to_cube = grip_site - cube
+        const double *cube = W.kxpos[1], *cq = W.kxquat[1];
+        for (int k = 0; k < 3; k++) obs[o++] = (float)cube[k];
+        obs[o++] = (float)cq[1]; obs[o++] = (float)cq[2]; obs[o++] = (float)cq[3]; obs[o++] = (float)cq[0];
+        for (int k = 0; k < 3; k++) obs[o++] = (float)(eef[k] - cube[k]);
+        while (o < 40) obs[o++] = 0.0f;   // 35 observation floats, row padded to 40
+        return;
+    }
     const double target[3] = {T.target_base[0] + W.q[T.target_qadr[0]], T.target_base[1] + W.q[T.target_qadr[1]], T.target_base[2]};
     for (int k = 0; k < 3; k++) obs[o++] = (float)target[k];
     const double *cube = W.kxpos[1], *cq = W.kxquat[1];
@@ -1095,6 +1103,8 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         a = a < -T.ac_scale ? -T.ac_scale : (a > T.ac_scale ? T.ac_scale : a);
         W.ctrl[lane] = prev + a;
     }
+    // lift: 8-D action, the last entry moves both finger actuators (SawyerEnv._gripper_format_action: gripper qpos + a)
+    if (T.kind == 1 && lane < 2 && mode != 2) W.ctrl[7 + lane] = W.q[T.grip_qadr[lane]] + (double)action[(size_t)e * action_stride + 7];
     __syncwarp();
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
@@ -1107,7 +1117,33 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
     // reward / success (frames of the last substep's start state)
     double reward = 0;
     bool success = false, terminal = false;
-    if (T.kind == 2) {   // SawyerAssemblyObstacleEnv.compute_reward (:32-51)
+    if (T.kind == 1) {   // SawyerLiftObstacleEnv.compute_reward (:92-148)
+        double grip[3], d = 0;
+        w_site(grip, W, 0, T.site_grip);
+        const double *cube = W.kxpos[1];
+        for (int k = 0; k < 3; k++) d += (cube[k] - grip[k]) * (cube[k] - grip[k]);
+        const double reach = (1 - tanh(10 * sqrt(d))) * 0.1;
+        // has_grasp: the contact list of the last mj_step holds can - left-finger and can - right-finger contacts
+        // (a planner-failure step has no fresh contact list: mode 2 runs no mj_step)
+        bool tl = false, tr = false;
+        const int nscan = mode != 2 ? ncon : 0;
+        for (int c = 0; c < nscan; c++) {
+            const int ga = W.cga[c], gb = W.cgb[c];
+            const int other = ga == T.geom_cube ? gb : (gb == T.geom_cube ? ga : -1);
+            if (other < 0) continue;
+            for (int k = 0; k < 3; k++) { if (other == T.geom_lfinger[k]) tl = true; if (other == T.geom_rfinger[k]) tr = true; }
+        }
+        const bool grasp = tl && tr;
+        const double r_grasp = grasp ? 0.35 : 0.0, z_target = T.bin_z + 0.45;
+        double r_lift = 0.0;
+        if (grasp) {
+            const double zd = z_target - cube[2] > 0.0 ? z_target - cube[2] : 0.0;
+            r_lift = 0.35 + (1 - tanh(15 * zd)) * (0.5 - 0.35);
+        }
+        reward = reach > r_grasp ? reach : r_grasp;
+        reward = reward > r_lift ? reward : r_lift;
+        if (grasp && fabs(cube[2] - z_target) < 0.05) { reward += T.success_reward; success = true; terminal = true; }
+    } else if (T.kind == 2) {   // SawyerAssemblyObstacleEnv.compute_reward (:32-51)
         double head[3], hole[3], bottom[3], d1 = 0, d2 = 0;
         w_site(head, W, 1, T.site_right_eef);
         w_site(hole, W, 2, T.site_hole);

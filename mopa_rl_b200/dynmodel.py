@@ -156,6 +156,22 @@ class DynModel:
                 g_quat[i] = quat_mul(squat[b], m.geom_quat[g])
         self.pairs = pairs
         self.geoms = used
+        # Collision meshes in the DYNAMICS: the contact generator works on primitives, so a mesh geom (lift: the can) is
+        # replaced by the bounding cylinder of its convex hull about the geom's z axis (can.stl: r = 25.1 mm, half height
+        # 40.0 mm, i.e. the can itself up to its bevels).  State validity / planning use the exact hull.
+        g_type, g_size, g_rbound = m.geom_type[used].astype(np.int32), np.array(m.geom_size[used]), np.array(m.geom_rbound[used])
+        for i, g in enumerate(used):
+            if g_type[i] != 7:
+                continue
+            me = int(m.geom_dataid[g])
+            v = m.mesh_vert[m.mesh_vertadr[me]:m.mesh_vertadr[me] + m.mesh_vertnum[me]]
+            r, zc, hh = np.sqrt((v[:, :2] ** 2).sum(1).max()), 0.5 * (v[:, 2].max() + v[:, 2].min()), 0.5 * (v[:, 2].max() - v[:, 2].min())
+            off = quat_to_mat(m.geom_quat[g]) @ np.array([0.0, 0.0, zc])
+            if g_body[i] >= 0:
+                g_pos[i] = g_pos[i] + off
+            else:
+                g_pos[i] = g_pos[i] + quat_to_mat(squat[int(m.geom_bodyid[g])]) @ off
+            g_type[i], g_size[i], g_rbound[i] = 5, [r, hh, 0.0], np.sqrt(r * r + hh * hh)
         arr = dict(
             b_parent=b_parent, b_bodyid=np.array(self.bodies, np.int32), b_pos=m.body_pos[self.bodies], b_quat=m.body_quat[self.bodies],
             b_rootpos=b_rootpos, b_rootquat=b_rootquat, b_jtype=b_jtype, b_qadr=b_qadr, b_vadr=b_vadr, b_dadr=b_dadr,
@@ -168,8 +184,8 @@ class DynModel:
             a_ctrllimited=m.actuator_ctrllimited[a_ids].astype(np.int32), a_forcelimited=m.actuator_forcelimited[a_ids].astype(np.int32),
             a_kp=m.actuator_kp[a_ids], a_kv=m.actuator_kv[a_ids], a_gear=m.actuator_gear[a_ids],
             a_ctrlrange=m.actuator_ctrlrange[a_ids].reshape(-1, 2), a_forcerange=m.actuator_forcerange[a_ids].reshape(-1, 2),
-            g_body=g_body, g_geomid=np.array(used, np.int32), g_type=m.geom_type[used].astype(np.int32), g_pos=g_pos, g_quat=g_quat,
-            g_size=m.geom_size[used], g_rbound=m.geom_rbound[used], g_margin=m.geom_margin[used], g_friction=m.geom_friction[used],
+            g_body=g_body, g_geomid=np.array(used, np.int32), g_type=g_type, g_pos=g_pos, g_quat=g_quat,
+            g_size=g_size, g_rbound=g_rbound, g_margin=m.geom_margin[used], g_friction=m.geom_friction[used],
             g_solref=m.geom_solref[used], g_solimp=m.geom_solimp[used], g_condim=m.geom_condim[used].astype(np.int32),
             p_g1=np.array([gidx[a] for a, _ in pairs], np.int32), p_g2=np.array([gidx[b] for _, b in pairs], np.int32),
         )

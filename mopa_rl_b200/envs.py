@@ -31,7 +31,9 @@ class SawyerTask(C.Structure):
                 ("max_episode_steps", C.c_int32), ("nsub", C.c_int32), ("site_right_eef", C.c_double * 3),
                 ("site_left_eef", C.c_double * 3), ("site_grip", C.c_double * 3), ("target_base", C.c_double * 3),
                 ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double),
-                ("site_hole", C.c_double * 3), ("site_hole_bottom", C.c_double * 3)]
+                ("site_hole", C.c_double * 3), ("site_hole_bottom", C.c_double * 3),
+                ("geom_cube", C.c_int32), ("geom_lfinger", C.c_int32 * 3), ("geom_rfinger", C.c_int32 * 3), ("pad_", C.c_int32),
+                ("bin_z", C.c_double)]
 
 
 class EnvBuffers(C.Structure):
@@ -39,7 +41,8 @@ class EnvBuffers(C.Structure):
                                            "reward", "done", "success", "ncon", "work", "cforce")]
 
 
-def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0):
+def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0,
+                   with_target=True):
     t = SawyerTask()
     t.kind = 0
     joints = ["right_j%d" % i for i in range(7)]
@@ -55,17 +58,20 @@ def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.
     t.body_cube = sim_body[model.body_name2id("cube")]
     t.body_rclaw = sim_body[model.body_name2id("rightclaw")]
     t.body_lclaw = sim_body[model.body_name2id("leftclaw")]
-    for k, j in enumerate(["target_x", "target_y"]):
+    for k, j in enumerate(["target_x", "target_y"] if with_target else []):
         t.target_qadr[k] = model.get_joint_qpos_addr(j)
     t.max_episode_steps = int(max_episode_steps)
     t.nsub = int(frame_dt / model.opt_timestep)
-    for name, field in (("right_eef", t.site_right_eef), ("left_eef", t.site_left_eef), ("grip_site", t.site_grip)):
+    for name, field in ((("right_eef", t.site_right_eef), ("left_eef", t.site_left_eef)) if with_target else ()) + (("grip_site", t.site_grip),):
         p = model.site_pos[model.site_name2id(name)]
         for k in range(3):
             field[k] = float(p[k])
-    tb = model.body_pos[model.body_name2id("target")]
+    tb = model.body_pos[model.body_name2id("target")] if with_target else np.zeros(3)
     for k in range(3):
         t.target_base[k] = float(tb[k])
+    t.geom_cube = -1
+    for k in range(3):
+        t.geom_lfinger[k] = t.geom_rfinger[k] = -1
     t.ac_scale, t.distance_threshold, t.success_reward = float(ac_scale), float(distance_threshold), float(success_reward)
     return t
 
@@ -102,6 +108,37 @@ def make_assembly_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scal
             field[k] = float(p[k])
     t.ac_scale, t.distance_threshold, t.success_reward = float(ac_scale), 0.0, float(success_reward)
     return t
+
+
+LIFT_INIT_QPOS = np.array([-0.0305, -0.7325, 0.03043, 1.16124, 1.87488, 0, 0])   # sawyer_lift_obstacle.py:13-14
+LIFT_LEFT_FINGER_GEOMS = ("l_finger_g0", "l_finger_g1", "l_fingertip_g0")      # :43-49
+LIFT_RIGHT_FINGER_GEOMS = ("r_finger_g0", "r_finger_g1", "r_fingertip_g0")
+
+
+def make_lift_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, **_):
+    """SawyerLiftObstacle-v0 (env/sawyer/sawyer_lift_obstacle.py): kind 1 of mopa_sawyer_task.  8-D action (7 joints +
+    gripper), reward = max(reach, grasp, lift) with has_grasp read from the contact list (both fingers touch the can)."""
+    t = make_push_task(model, dyn, max_episode_steps, frame_dt, ac_scale, 0.0, success_reward, with_target=False)
+    t.kind = 1
+    sim_geom = {g: i for i, g in enumerate(dyn.geoms)}
+    t.geom_cube = sim_geom[model.geom_name2id("cube")]
+    for k in range(3):
+        t.geom_lfinger[k] = sim_geom.get(model.geom_name2id(LIFT_LEFT_FINGER_GEOMS[k]), -1)
+        t.geom_rfinger[k] = sim_geom.get(model.geom_name2id(LIFT_RIGHT_FINGER_GEOMS[k]), -1)
+    t.bin_z = float(model.body_pos[model.body_name2id("bin1")][2])
+    return t
+
+
+def lift_reset_state(model, seed, env_ids, episode_idx):
+    """Reset distribution of SawyerLiftObstacleEnv._reset (:23-32): arm = init_qpos + N(0, 0.02^2), the can at its keyframe pose."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64).reshape(-1)
+    ep = np.broadcast_to(np.asarray(episode_idx, dtype=np.uint64), env_ids.shape)
+    n = len(env_ids)
+    qpos = np.tile(model.qpos0, (n, 1))
+    ref = [model.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+    dims = np.arange(7, dtype=np.uint64)
+    qpos[:, ref] = LIFT_INIT_QPOS + 0.02 * rng.normal(seed, env_ids[:, None], ep[:, None], dims[None, :])
+    return qpos, np.zeros((n, model.nv))
 
 
 def assembly_reset_state(model, seed, env_ids, episode_idx):
@@ -266,3 +303,17 @@ class VecSawyerAssemblyObstacle(VecSawyerPushObstacle):
     MANIPULATION_BODIES = ("furniture", "0_part0", "1_part1", "4_part4", "2_part2")
     make_task = staticmethod(make_assembly_task)
     reset_state = staticmethod(assembly_reset_state)
+
+
+class VecSawyerLiftObstacle(VecSawyerPushObstacle):
+    """N device-resident SawyerLiftObstacle-v0 environments (BASELINE configs[2]).  Actions are 8-D (7 joint entries +
+    gripper); the observation row keeps the 40-float stride, its first 35 floats are joint_pos7, joint_vel7, gripper_qpos2,
+    gripper_qvel2, eef_pos3, eef_quat4, cube_pos3, cube_quat4, gripper_to_cube3 (env/sawyer/sawyer_lift_obstacle.py:150-161)."""
+    ENV_ID = "SawyerLiftObstacle-v0"
+    OBS_DIM = 35
+    ACTION_DIM = 8
+    INIT_QPOS = LIFT_INIT_QPOS
+    STATIC_BODIES = ("table", "bin1")          # sawyer_lift_obstacle.py:163-165
+    MANIPULATION_BODIES = ("cube",)
+    make_task = staticmethod(make_lift_task)
+    reset_state = staticmethod(lift_reset_state)

@@ -164,3 +164,89 @@ class AssemblyEnvOracle(PushEnvOracle):
             reward += self.succ_rew
             self.success, terminal = True, True
         return reward, terminal
+
+
+class LiftEnvOracle(PushEnvOracle):
+    """SawyerLiftObstacle-v0 (env/sawyer/sawyer_lift_obstacle.py): 8-D action (7 joints + gripper, _step :191-240 with
+    SawyerEnv._gripper_format_action :340-342), reward = max(reach, grasp, lift) with has_grasp read from the contact
+    list of the last mj_step (:92-148), 35-float observation (:150-161)."""
+    LEFT = ("l_finger_g0", "l_finger_g1", "l_fingertip_g0")
+    RIGHT = ("r_finger_g0", "r_finger_g1", "r_fingertip_g0")
+
+    def __init__(self, model, dynmodel, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, contacts=True):
+        self.m, self.dm = model, dynmodel
+        self.dyn = OracleDyn(dynmodel)
+        self.dyn.enable_contacts(contacts)
+        m = model
+        self.ref_q = [m.get_joint_qpos_addr("right_j%d" % i) for i in range(7)]
+        self.ref_v = [m.get_joint_qvel_addr("right_j%d" % i) for i in range(7)]
+        self.grip_q = [m.get_joint_qpos_addr(j) for j in ("rc_close", "lc_close")]
+        self.grip_v = [m.get_joint_qvel_addr(j) for j in ("rc_close", "lc_close")]
+        sim = {b: i for i, b in enumerate(dynmodel.bodies)}
+        self.b_ee, self.b_cube = sim[m.body_name2id("right_ee_attchment")], sim[m.body_name2id("cube")]
+        self.s_grip = m.site_pos[m.site_name2id("grip_site")]
+        self.g_cube = m.geom_name2id("cube")
+        self.g_left, self.g_right = [m.geom_name2id(n) for n in self.LEFT], [m.geom_name2id(n) for n in self.RIGHT]
+        self.bin_z = float(m.body_pos[m.body_name2id("bin1")][2])
+        self.comp = np.zeros(dynmodel.nd, np.int32)
+        self.comp[[list(dynmodel.dof_vadr).index(v) for v in self.ref_v]] = 1
+        self.nsub = int(frame_dt / m.opt_timestep)
+        self.ac_scale, self.succ_rew, self.max_steps = ac_scale, success_reward, max_episode_steps
+        self.lim = [(int(q), dynmodel._arr["d_range"][k]) for k, q in enumerate(dynmodel.dof_qadr) if q >= 0 and dynmodel._arr["d_limited"][k]]
+        self.contacts = []
+
+    def obs(self):
+        q, v = self.qpos, self.qvel
+        eef, eq = self._site(self.b_ee, self.s_grip), self.xquat[self.b_ee]
+        cube, cq = self.xpos[self.b_cube], self.xquat[self.b_cube]
+        return np.concatenate([q[self.ref_q], v[self.ref_v], q[self.grip_q], v[self.grip_v], eef, eq[[1, 2, 3, 0]], cube, cq[[1, 2, 3, 0]],
+                               eef - cube])
+
+    def _reward(self):
+        grip, cube = self._site(self.b_ee, self.s_grip), self.xpos[self.b_cube]
+        reach = (1 - np.tanh(10 * np.linalg.norm(cube - grip))) * 0.1
+        tl = tr = False
+        for g1, g2 in self.contacts:
+            other = g2 if g1 == self.g_cube else (g1 if g2 == self.g_cube else None)
+            tl, tr = tl or other in self.g_left, tr or other in self.g_right
+        self.has_grasp = tl and tr
+        grasp = 0.35 if self.has_grasp else 0.0
+        z_target = self.bin_z + 0.45
+        lift = 0.35 + (1 - np.tanh(15 * max(z_target - cube[2], 0.0))) * (0.5 - 0.35) if self.has_grasp else 0.0
+        reward, terminal = max(reach, grasp, lift), False
+        if self.has_grasp and abs(cube[2] - z_target) < 0.05:
+            reward += self.succ_rew
+            self.success, terminal = True, True
+        return reward, terminal
+
+    def step(self, action, is_planner=False):
+        action = np.asarray(action, np.float64)
+        assert len(action) == 8
+        if not is_planner or self.prev_state is None:
+            self.prev_state = self.qpos[self.ref_q].copy()
+        a = action[:7] if is_planner else action[:7] * self.ac_scale
+        desired = self.prev_state + np.clip(a, -self.ac_scale, self.ac_scale)
+        ctrl = np.concatenate([desired, self.qpos[self.grip_q] + action[7]])
+        self.qpos, self.qvel, self.bias_prev, self.xpos, self.xquat, self.ncon = self.dyn.step(
+            self.qpos, self.qvel, ctrl, self.comp, self.bias_prev, self.nsub)
+        self.contact_force, self.contacts = self.dyn.contact_force, self.dyn.contacts
+        self.prev_state = desired.copy()
+        reward, terminal = self._reward()
+        ob = self.obs()
+        clipped = False
+        for qa, (lo, hi) in self.lim:
+            if self.qpos[qa] < lo or self.qpos[qa] > hi:
+                self.qpos[qa] = min(max(self.qpos[qa], lo), hi)
+                clipped = True
+        if clipped:
+            self.set_state(self.qpos, self.qvel)
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return ob, reward, terminal
+
+    def null_step(self):
+        self.contacts = []   # no mj_step ran: no fresh contact list (the device path does the same)
+        return super().null_step()

@@ -171,6 +171,7 @@ class OracleDyn:
         L.orc_dyn_enable_contacts.argtypes = [C.c_void_p, C.c_int]
         L.orc_dyn_set_max_rows.argtypes = [C.c_void_p, C.c_int]
         L.orc_dyn_last_contact_force.restype = C.c_double
+        L.orc_dyn_last_contacts.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_dyn_step.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
         L.orc_dyn_forward.argtypes = [C.c_void_p] * 6
         L.orc_dyn_mass_bias.argtypes = [C.c_void_p] * 6
@@ -207,6 +208,9 @@ class OracleDyn:
         ncon = C.c_int32()
         self.L.orc_dyn_step(self.h, _p(q), _p(v), _p(c), _p(cm), _p(b), int(nsub), _p(xpos), _p(xquat), C.byref(ncon))
         self.contact_force = float(self.L.orc_dyn_last_contact_force())   # BaseEnv.get_contact_force() after this step
+        g1, g2 = np.zeros(16, np.int32), np.zeros(16, np.int32)
+        k = self.L.orc_dyn_last_contacts(_p(g1), _p(g2))
+        self.contacts = [(int(self.dm.geoms[g1[i]]), int(self.dm.geoms[g2[i]])) for i in range(k)]   # (geom1, geom2) model ids
         return q, v, b, xpos, xquat, ncon.value
 
     def mass_bias(self, qpos, qvel):

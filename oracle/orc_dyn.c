@@ -129,6 +129,7 @@ void orc_dyn_destroy(void *h) {
     free(m->p_g1); free(m->p_g2); free(m);
 }
 static long g_pgs_calls = 0, g_pgs_sweeps = 0;
+static int g_last_ncon = 0, g_last_g1[DMAXC / 3], g_last_g2[DMAXC / 3]; /* contact list (simulated-geom indices) of the same call */
 static double g_last_cforce = 0; /* contact-force metric of the latest orc_dyn_step call (single-threaded test use) */
 void orc_pgs_stats(long *out, int reset) { out[0] = g_pgs_calls; out[1] = g_pgs_sweeps; if (reset) g_pgs_calls = g_pgs_sweeps = 0; }
 void orc_dyn_enable_contacts(void *h, int on) { ((dyn_model *)h)->enable_contacts = on; }
@@ -352,6 +353,7 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
         int n0 = nc;
         nc += orc_contact_rows(m, D, S, rows + nc, maxrows - nc);
         D->ncon = (nc - n0) / 3;
+        for (int c = 0; c < D->ncon && c < DMAXC / 3; c++) D->con_pair[c] = rows[n0 + 3 * c].sig / 16; /* sig = pair*16 + point*4 + dir */
     }
     double fc[DMAXD];
     memset(fc, 0, sizeof(fc));
@@ -528,9 +530,17 @@ int orc_dyn_step(void *h, double *qpos, double *qvel, const double *ctrl, const 
     if (xquat) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 4; k++) xquat[4 * i + k] = D.xquat[i][k];
     if (ncon) *ncon = D.ncon;
     g_last_cforce = D.cforce;
+    g_last_ncon = D.ncon < DMAXC / 3 ? D.ncon : DMAXC / 3;
+    for (int c = 0; c < g_last_ncon; c++) { g_last_g1[c] = m->p_g1[D.con_pair[c]]; g_last_g2[c] = m->p_g2[D.con_pair[c]]; }
     return 0;
 }
 double orc_dyn_last_contact_force(void) { return g_last_cforce; }
+/* mjData.contact[i].geom1 / geom2 after the step (sim.data.ncon entries; the lift reward scans them,
+   env/sawyer/sawyer_lift_obstacle.py:109-123), as indices into the simulated-geom list */
+int orc_dyn_last_contacts(int32_t *g1, int32_t *g2) {
+    for (int c = 0; c < g_last_ncon; c++) { g1[c] = g_last_g1[c]; g2[c] = g_last_g2[c]; }
+    return g_last_ncon;
+}
 
 /* mj_forward's part that the env reads: kinematics + bias at the current state (no integration) */
 int orc_dyn_forward(void *h, const double *qpos, const double *qvel, double *bias, double *xpos, double *xquat) {

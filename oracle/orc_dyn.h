@@ -37,6 +37,7 @@ typedef struct {
     double xpos[DMAXB][3], xquat[DMAXB][4], xmat[DMAXB][9];
     double bias[DMAXD];
     int ncon;
+    int con_pair[DMAXC / 3 + 1]; /* candidate-pair index of every contact of the last mj_step */
     double cforce; /* sum over contacts of |f_n| + |f_t1| + |f_t2| of the last mj_step (BaseEnv.get_contact_force) */
     double M[DMAXD * DMAXD], com[DMAXB][3]; /* debug / unit tests */
 } dyn_data;

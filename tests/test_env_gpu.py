@@ -101,3 +101,94 @@ def test_assembly_env_step_matches_oracle(oracle_built):
     assert worst["qpos"] < TOL and worst["qvel"] < TOL, worst
     assert worst["obs"] < 1e-4 and worst["rew"] < 1e-6, worst
     print("assembly max abs error:", worst)
+
+
+def _lift_fingertip_frame(model, dm, e):
+    """Midpoint of the fingertip geoms, closing direction, and a can orientation whose axis is perpendicular to it."""
+    from mopa_rl_b200.mjcf import mat_to_quat
+    from oracle.env_oracle import _q2m
+
+    tips = []
+    for name in ("l_fingertip_g0", "r_fingertip_g0"):
+        g = model.geom_name2id(name)
+        sb = dm.bodies.index(int(model.geom_bodyid[g]))
+        tips.append(e.xpos[sb] + _q2m(e.xquat[sb]) @ model.geom_pos[g])
+    mid, cdir = 0.5 * (tips[0] + tips[1]), (tips[0] - tips[1]) / np.linalg.norm(tips[0] - tips[1])
+    R = _q2m(e.xquat[e.b_ee])
+    ax = R[:, 1] - (R[:, 1] @ cdir) * cdir
+    ax /= np.linalg.norm(ax)
+    return mid, mat_to_quat(np.stack([cdir, np.cross(ax, cdir), ax], 1))
+
+
+def test_lift_env_step_matches_oracle(oracle_built):
+    """SawyerLiftObstacle-v0 (BASELINE configs[2]): 8-D action with the gripper entry, 35-float observation, reward =
+    max(reach, grasp, lift) with has_grasp from the contact list, success at the lift height.  The gripper is closed,
+    the can is placed between the fingers, then the arm moves: grasp / lift / success rewards are all exercised."""
+    import torch
+
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerLiftObstacle, lift_reset_state
+    from mopa_rl_b200.model import load_model
+    from oracle.env_oracle import LiftEnvOracle
+
+    model = load_model("SawyerLiftObstacle-v0")
+    n = 16
+    venv = VecSawyerLiftObstacle(n, seed=13, max_episode_steps=7)
+    venv.reset()
+    dm = DynModel(model)
+    q0, v0 = lift_reset_state(model, 13, np.arange(n), np.zeros(n, dtype=np.int64))
+    assert np.array_equal(venv.qpos.cpu().numpy(), q0)
+    j1 = model.get_joint_qpos_addr("right_j1")
+    q0[1::4, j1] = -0.6                                   # arm lowered: the fingertips sit at the success height (bin z + 0.45)
+    venv.set_state(np.arange(n), q0, v0)
+    envs = [LiftEnvOracle(model, dm, max_episode_steps=7) for _ in range(n)]
+    obs0 = np.stack([e.reset_to(q0[i], v0[i]) for i, e in enumerate(envs)])
+    assert np.abs(venv.obs.cpu().numpy()[:, :35] - obs0).max() < 1e-5 and np.all(venv.obs.cpu().numpy()[:, 35:] == 0)
+    rng = np.random.default_rng(4)
+    worst = dict(qpos=0.0, qvel=0.0, obs=0.0, rew=0.0)
+    kinds = set()
+    a = model.get_joint_qpos_addr("cube")[0]
+    va = model.get_joint_qvel_addr("cube")[0]
+
+    def step(act, isp):
+        venv.step(torch.as_tensor(act, device="cuda"), torch.as_tensor(isp, device="cuda"))
+        torch.cuda.synchronize()
+        gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
+        gobs, grew, gdone, gsucc = venv.obs.cpu().numpy(), venv.reward.cpu().numpy(), venv.done.cpu().numpy(), venv.success.cpu().numpy()
+        for i, e in enumerate(envs):
+            if e.terminal:
+                continue                                   # finished episodes are not stepped by the reference loop
+            ob, r, d = e.step(act[i].astype(np.float64), bool(isp[i]))
+            worst["qpos"] = max(worst["qpos"], np.abs(gq[i] - e.qpos).max())
+            worst["qvel"] = max(worst["qvel"], np.abs(gv[i] - e.qvel).max())
+            worst["obs"] = max(worst["obs"], np.abs(gobs[i, :35] - ob).max())
+            worst["rew"] = max(worst["rew"], abs(grew[i] - r))
+            assert bool(gdone[i]) == d and bool(gsucc[i]) == (e.success and d), (i, gdone[i], d, gsucc[i], e.success)
+            kinds.add("success" if r > 100 else ("lift" if r > 0.35 + 1e-9 else ("grasp" if abs(r - 0.35) < 1e-9 else "reach")))
+
+    for s in range(3):                                     # close the gripper (positive gripper action closes it)
+        act = np.zeros((n, 8), np.float32)
+        act[:, :7] = rng.uniform(-0.2, 0.2, (n, 7))
+        act[:, 7] = 1.0
+        step(act, np.zeros(n, np.uint8))
+    q, v = np.stack([e.qpos for e in envs]), np.stack([e.qvel for e in envs])
+    for i, e in enumerate(envs):                           # the can appears between the closed fingers of every other env
+        if i % 2 == 0 or i % 4 == 1:
+            mid, quat = _lift_fingertip_frame(model, dm, e)
+            q[i, a:a + 3], q[i, a + 3:a + 7], v[i, va:va + 6] = mid, quat, 0.0
+        e.set_state(q[i], v[i])
+        e.prev_state = None
+    venv.set_state(np.arange(n), q, v)
+    venv.reset_prev_state()
+    for s in range(3):
+        act = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
+        act[:, 7] = rng.uniform(-0.3, 0.1, n)
+        isp = np.zeros(n, np.uint8)
+        if s >= 1:
+            isp[::2] = 1
+            act[::2, :7] *= 0.08
+        step(act, isp)
+    assert worst["qpos"] < TOL and worst["qvel"] < TOL, worst
+    assert worst["obs"] < 1e-4 and worst["rew"] < 1e-6, worst
+    assert {"reach", "lift", "success"} <= kinds, kinds
+    print("lift max abs error:", worst, sorted(kinds))
