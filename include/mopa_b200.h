@@ -209,7 +209,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
 void mopa_rollout_destroy(mopa_rollout *r);
 /* wait_rrt != 0: block until the RRT batch in flight (if any) is done, then finalise it. */
 int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
-/* d_actions: device float[n][7], the policy's action for every environment. */
+/* d_actions: device float[n][7] (float[n][8] for the lift task: 7 joint entries + gripper), the policy's action for every environment. */
 int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
 /* discrete_action handles: d_ac_type uint8[n] (0 = direct execution, 1 = motion planner), the policy's ac["ac_type"]. */
 int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const uint8_t *d_ac_type, void *stream);

@@ -92,7 +92,8 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
         mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
         return MOPA_ERR_MODEL;
     }
-    if (task->kind != 0 && task->kind != 2) { mopa_set_error("mopa_env_create: only the SawyerPushObstacle (0) and SawyerAssemblyObstacle (2) tasks are built"); return MOPA_ERR_MODEL; }
+    if (task->kind < 0 || task->kind > 2) { mopa_set_error("mopa_env_create: task kind must be 0 (push), 1 (lift) or 2 (assembly)"); return MOPA_ERR_MODEL; }
+    if (task->kind == 1 && (task->geom_cube < 0 || task->geom_cube >= dyn->ngeom)) { mopa_set_error("mopa_env_create: lift task without the can's contact geom"); return MOPA_ERR_MODEL; }
     mopa_env *e = new mopa_env();
     e->device = device;
     e->task = *task;

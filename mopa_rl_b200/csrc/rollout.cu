@@ -75,6 +75,8 @@ struct RoDev {   // everything the kernels need, passed by value
     int heavy_work;              // Newton steps per env.step above which an environment counts as expensive
     // reuse_data (rl/mopa_rollouts.py:223-302): per-step history of the plan being executed, relabelled records
     int reuse_data, max_reuse;
+    int adim, grip_qadr0;        // action entries per environment (7; 8 for the lift task: + gripper), qpos address of rc_close
+    double *grip0;               // [n] gripper qpos when the current plan was made (SawyerEnv.form_action with dof == 8, :290-296)
     int discrete;                // config.discrete_action: the policy's ac_type chooses planner / direct execution
     unsigned long long seed_reuse;
     float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
@@ -222,13 +224,18 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
     float a32[7];
     bool is_mp = false;
     for (int k = 0; k < 7; k++) {
-        float a = actions[(size_t)e * 7 + k];
+        float a = actions[(size_t)e * S.adim + k];
         a = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
         a32[k] = a;
         S.ac[(size_t)e * 8 + k] = a;
         if (fabs((double)a) > S.omega) is_mp = true;
     }
     if (S.discrete) { is_mp = ac_type[e] != 0; S.ac[(size_t)e * 8 + 7] = is_mp ? 1.0f : 0.0f; }
+    if (S.adim == 8) {   // lift: the gripper entry rides along (executed with direct actions and with the last waypoint of a plan)
+        float g = actions[(size_t)e * 8 + 7];
+        S.ac[(size_t)e * 8 + 7] = g < -1.0f ? -1.0f : (g > 1.0f ? 1.0f : g);
+        S.grip0[e] = B.qpos[(size_t)e * S.nq + S.grip_qadr0];
+    }
     S.macro_index[e] += 1;
     for (int k = 0; k < 40; k++) S.prev_ob[(size_t)e * 40 + k] = B.obs[(size_t)e * 40 + k];
     S.meta_rew[e] = 0.0; S.executed[e] = 0; S.macro_done[e] = 0; S.pending[e] = 1;
@@ -519,11 +526,15 @@ __global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
     if (kind == 0) {
         // direct execution: ac / omega, or the raw action with discrete_action (rl/mopa_rollouts.py:347-352)
         for (int k = 0; k < 7; k++) sa[k] = S.discrete ? S.ac[(size_t)e * 8 + k] : (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
+        if (S.adim == 8) sa[7] = S.ac[(size_t)e * 8 + 7];   // rescaled_ac: only the joint entries are divided by omega (:349-352)
     } else if (kind == 1) {
         int pos = S.traj_pos[e];
         if (pos > S.max_traj - 1) pos = S.max_traj - 1;
         const double *nx = S.traj + ((size_t)e * S.max_traj + pos) * 7;
         for (int k = 0; k < 7; k++) sa[k] = (float)(nx[k] - B.qpos[(size_t)e * S.nq + S.arm_qadr[k]]);
+        // lift: form_action's gripper entry = (gripper qpos of the waypoint = of the plan's start state) - current one; the
+        // policy's gripper action replaces it on the last waypoint (rl/mopa_rollouts.py:170-175)
+        if (S.adim == 8) sa[7] = (S.traj_pos[e] >= S.traj_len[e] - 1) ? S.ac[(size_t)e * 8 + 7] : (float)(S.grip0[e] - B.qpos[(size_t)e * S.nq + S.grip_qadr0]);
     }
 }
 // ---- 8. after env.step: discounted macro reward, counters, termination
@@ -624,6 +635,9 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
     S.discrete = cfg->discrete_action ? 1 : 0;
+    S.adim = env->task.kind == 1 ? 8 : 7;
+    S.grip_qadr0 = env->task.grip_qadr[0];
+    if (S.adim == 8 && S.discrete) { mopa_set_error("mopa_rollout_create: discrete_action is not built for the 8-D lift action (record slot 47 is taken)"); delete r; return MOPA_ERR_ARG; }
     S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_count && reuse_capacity > 0) ? 1 : 0;
     S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
     S.ep_stats = d_ep_stats;
@@ -639,7 +653,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     A(S.kind, n); A(S.pending, n); A(S.macro_done, n); A(S.need, n); A(S.reset_flag, n); A(S.step_mode, n); A(S.step_mask, n);
     A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
     A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
-    A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n); A(S.ep_cforce, n);
+    A(S.grip0, n); A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n); A(S.ep_cforce, n);
     if (S.reuse_data) { A(S.ob_hist, (size_t)n * S.max_traj * 40); A(S.rew_hist, (size_t)n * S.max_traj); A(S.done_hist, (size_t)n * S.max_traj); }
     A(S.plan_env, n); A(S.tgt64, (size_t)n * nq); A(S.c64, (size_t)n * nq); A(S.q32a, (size_t)n * row); A(S.res_a, n);
     A(S.back_of_plan, n); A(S.q32b, (size_t)n * S.num_trials * row); A(S.res_b, (size_t)n * S.num_trials);

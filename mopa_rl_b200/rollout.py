@@ -77,28 +77,28 @@ def env_planner_inputs(venv_cls, model):
 class UniformPolicy:
     """random_exploration=True: ac_space.sample(), uniform in [-1, 1]^7 (rl/base_agent.py:15-22)."""
 
-    def __init__(self, torch, device, seed):
+    def __init__(self, torch, device, seed, action_dim=7):
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(int(seed))
-        self.torch, self.device = torch, device
+        self.torch, self.device, self.adim = torch, device, int(action_dim)
 
     def __call__(self, obs, env_ids=None, macro_index=None):
-        return self.torch.rand(obs.shape[0], 7, generator=self.gen, device=self.device) * 2 - 1
+        return self.torch.rand(obs.shape[0], self.adim, generator=self.gen, device=self.device) * 2 - 1
 
 
 class CounterPolicy:
     """Uniform [-1,1]^7 actions that are a pure function of (seed, env id, macro-action index):
     the stand-in for random_exploration whose draws do not depend on batch composition."""
 
-    def __init__(self, torch, device, seed, discrete=False):
-        self.torch, self.device, self.seed, self.discrete = torch, device, int(seed), discrete
+    def __init__(self, torch, device, seed, discrete=False, action_dim=7):
+        self.torch, self.device, self.seed, self.discrete, self.adim = torch, device, int(seed), discrete, int(action_dim)
 
     def __call__(self, obs, env_ids, macro_index):
         from . import rng
 
         e = env_ids.cpu().numpy().astype(np.uint64)[:, None]
         c = macro_index.cpu().numpy().astype(np.uint64)[:, None]
-        u = rng.uniform01(self.seed, e, c, np.arange(7, dtype=np.uint64)[None, :])
+        u = rng.uniform01(self.seed, e, c, np.arange(self.adim, dtype=np.uint64)[None, :])
         ac = self.torch.as_tensor((2.0 * u - 1.0).astype(np.float32), device=self.device)
         if not self.discrete:
             return ac
@@ -527,7 +527,8 @@ class NativeMoPARolloutRunner:
         self.dev = dev
         ignored, passive, ref = env_planner_inputs(type(venv), m)
         self.planner = NativePlanner(m, passive, ignored, cfg.contact_threshold, cfg.range, 0.005, cfg.seed, venv.device_index)
-        self.policy = policy or UniformPolicy(torch, dev, cfg.seed + 17 * int(venv.env_ids[0]))
+        self.action_dim = int(getattr(venv, "ACTION_DIM", 7))   # 8 for the lift task (7 joint entries + gripper)
+        self.policy = policy or UniformPolicy(torch, dev, cfg.seed + 17 * int(venv.env_ids[0]), self.action_dim)
         n = venv.n
         self.n = n
         self.env_gid = torch.as_tensor(venv.env_ids, dtype=torch.int64, device=dev)
@@ -600,6 +601,8 @@ class NativeMoPARolloutRunner:
             ac, ac_type = ac
             ac_type = ac_type.to(device=self.dev, dtype=self.torch.uint8).contiguous()
         ac = ac.to(device=self.dev, dtype=self.torch.float32).contiguous()
+        if tuple(ac.shape) != (self.n, self.action_dim):
+            raise ValueError("policy returned actions of shape %s, expected (%d, %d)" % (tuple(ac.shape), self.n, self.action_dim))
         if self.cfg.discrete_action:
             self._check(self._L.mopa_rollout_step_discrete(self.h, ac.data_ptr(), ac_type.data_ptr(), self._stream()))
             self._keep = (ac, ac_type)

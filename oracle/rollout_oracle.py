@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .env_oracle import AssemblyEnvOracle, PushEnvOracle
+from .env_oracle import AssemblyEnvOracle, LiftEnvOracle, PushEnvOracle
 from .oracle import OraclePlanner, OracleScene, space_from_model
 
 
@@ -24,7 +24,7 @@ class ScalarMoPARunner:
         """policy(env_gid, macro_index) -> action (7,) in [-1, 1]."""
         self.m, self.cfg, self.gid, self.policy = model, cfg, int(env_gid), policy
         self.task = task
-        env_cls = AssemblyEnvOracle if task == "assembly" else PushEnvOracle
+        env_cls = {"assembly": AssemblyEnvOracle, "lift": LiftEnvOracle}.get(task, PushEnvOracle)
         self.env = env_cls(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
         self.scene = OracleScene(model, ignored, cfg.contact_threshold, "f32")
         adr, lo, hi, so2 = space_from_model(model, passive)
@@ -42,9 +42,10 @@ class ScalarMoPARunner:
         self.ob = self._reset()
 
     def _reset(self):
-        from mopa_rl_b200.envs import assembly_reset_state, push_reset_state  # reset draws are input data shared with the product
+        from mopa_rl_b200.envs import assembly_reset_state, lift_reset_state, push_reset_state  # reset draws are input data shared with the product
 
-        q, v = (assembly_reset_state if self.task == "assembly" else push_reset_state)(self.m, self.seed_env, [self.gid], [self.episode])
+        fn = {"assembly": assembly_reset_state, "lift": lift_reset_state}.get(self.task, push_reset_state)
+        q, v = fn(self.m, self.seed_env, [self.gid], [self.episode])
         self.episode += 1
         return self.env.reset_to(q[0], v[0])
 
@@ -122,6 +123,9 @@ class ScalarMoPARunner:
         if discrete:                                               # ac = {"default": ..., "ac_type": ...}
             ac, ac_type = ac
         ac = np.asarray(ac, np.float64).astype(np.float32).astype(np.float64)
+        lift = self.task == "lift"                                 # 8-D action: 7 joint entries + gripper
+        grip_ac = float(ac[7]) if lift else None
+        ac = ac[:7]
         self.macro_index += 1
         curr = env.qpos.copy()
         is_mp = bool(ac_type) if discrete else bool(np.any(np.abs(ac) > cfg.omega))   # rl/mopa_rollouts.py:86-88, 104-111
@@ -151,8 +155,12 @@ class ScalarMoPARunner:
                 self.counters["interpolation" if interpolation else "mp"] += 1
                 meta, done = 0.0, False
                 ob_list, rew_list, done_list = [], [], []
+                grip_q0 = env.qpos[env.grip_q[0]] if lift else 0.0
                 for i, nq in enumerate(traj):
                     a = np.asarray(nq[:7] - env.qpos[:7], np.float32).astype(np.float64)   # form_action (fp32 action row)
+                    if lift:   # form_action's gripper entry (waypoints carry the start state's passive dims), policy's on the last one
+                        g = grip_ac if i == len(traj) - 1 else grip_q0 - env.qpos[env.grip_q[0]]
+                        a = np.concatenate([a, [np.float64(np.float32(g))]])
                     self.ob, rew, done = env.step(a, is_planner=True)
                     meta += cfg.discount_factor ** i * rew
                     ob_list.append(self.ob.copy()), rew_list.append(meta), done_list.append(done)
@@ -173,6 +181,8 @@ class ScalarMoPARunner:
         else:
             self.counters["rl"] += 1
             direct = ac if discrete else (ac / cfg.omega).astype(np.float32).astype(np.float64)   # :347-352
+            if lift:
+                direct = np.concatenate([direct, [grip_ac]])
             self.ob, rec_rew, done = env.step(direct, is_planner=False)
             intra, steps = 0, 1
         env.prev_state = None                                       # env._reset_prev_state()
@@ -182,7 +192,7 @@ class ScalarMoPARunner:
         rec = np.zeros(92, np.float32)
         no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
         rec[0:no], rec[40:47], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
-        rec[47] = self._ac_type
+        rec[47] = grip_ac if lift else self._ac_type
         return rec
 
     def _reuse(self, ob_list, rew_list, done_list, traj):

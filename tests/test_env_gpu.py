@@ -122,8 +122,8 @@ def _lift_fingertip_frame(model, dm, e):
 
 def test_lift_env_step_matches_oracle(oracle_built):
     """SawyerLiftObstacle-v0 (BASELINE configs[2]): 8-D action with the gripper entry, 35-float observation, reward =
-    max(reach, grasp, lift) with has_grasp from the contact list, success at the lift height.  The gripper is closed,
-    the can is placed between the fingers, then the arm moves: grasp / lift / success rewards are all exercised."""
+    max(reach, grasp, lift) with has_grasp from the contact list, success at the lift height.  The gripper is opened,
+    the can is placed between the fingers, the gripper closes on it, then the arm moves: grasp / lift / success rewards are all exercised."""
     import torch
 
     from mopa_rl_b200.dynmodel import DynModel
@@ -166,13 +166,13 @@ def test_lift_env_step_matches_oracle(oracle_built):
             assert bool(gdone[i]) == d and bool(gsucc[i]) == (e.success and d), (i, gdone[i], d, gsucc[i], e.success)
             kinds.add("success" if r > 100 else ("lift" if r > 0.35 + 1e-9 else ("grasp" if abs(r - 0.35) < 1e-9 else "reach")))
 
-    for s in range(3):                                     # close the gripper (positive gripper action closes it)
+    for s in range(2):                                     # open the gripper (negative gripper action opens it)
         act = np.zeros((n, 8), np.float32)
         act[:, :7] = rng.uniform(-0.2, 0.2, (n, 7))
-        act[:, 7] = 1.0
+        act[:, 7] = -1.0
         step(act, np.zeros(n, np.uint8))
     q, v = np.stack([e.qpos for e in envs]), np.stack([e.qvel for e in envs])
-    for i, e in enumerate(envs):                           # the can appears between the closed fingers of every other env
+    for i, e in enumerate(envs):                           # the can appears between the open fingers of most envs
         if i % 2 == 0 or i % 4 == 1:
             mid, quat = _lift_fingertip_frame(model, dm, e)
             q[i, a:a + 3], q[i, a + 3:a + 7], v[i, va:va + 6] = mid, quat, 0.0
@@ -180,11 +180,11 @@ def test_lift_env_step_matches_oracle(oracle_built):
         e.prev_state = None
     venv.set_state(np.arange(n), q, v)
     venv.reset_prev_state()
-    for s in range(3):
-        act = rng.uniform(-1, 1, (n, 8)).astype(np.float32)
-        act[:, 7] = rng.uniform(-0.3, 0.1, n)
+    for s in range(5):                                     # close gently (40 N), then move the arm with the can in hand
+        act = rng.uniform(-1, 1, (n, 8)).astype(np.float32) if s >= 2 else np.zeros((n, 8), np.float32)
+        act[:, 7] = 0.004
         isp = np.zeros(n, np.uint8)
-        if s >= 1:
+        if s >= 3:
             isp[::2] = 1
             act[::2, :7] *= 0.08
         step(act, isp)

@@ -225,3 +225,58 @@ def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model,
                 k += 1
     assert types == {0.0, 1.0}
     print("discrete_action: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
+
+
+def test_native_runner_lift_matches_scalar_reference_loop(oracle_built):
+    """SawyerLiftObstacle-v0 (BASELINE configs[2] scene): mesh collider in the planner, 8-D actions whose gripper entry
+    is executed with direct actions and with the last waypoint of a plan (rl/mopa_rollouts.py:170-175), form_action's
+    gripper entry in between (env/sawyer/sawyer.py:290-296), reuse_data on."""
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerLiftObstacle
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, env_planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    model = load_model("SawyerLiftObstacle-v0")
+    n, ticks, seed = 8, 40, 515
+    cfg = MoPAConfig(max_iter=150, seed=31, reuse_data=True, max_reuse_data=15)
+    venv = VecSawyerLiftObstacle(n, seed=seed, max_episode_steps=20, env_id_offset=60)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 19, action_dim=8))
+    for _ in range(ticks):
+        runner.tick()
+    runner.drain()
+    torch.cuda.synchronize()
+    c = runner.counters
+    rec = runner.transitions[:c["transitions"]].cpu().numpy()
+    assert len(rec) > n
+
+    def policy(gid, k):
+        u = rng.uniform01(19, np.uint64(gid), np.uint64(k), np.arange(8, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ignored, passive, _ = env_planner_inputs(VecSawyerLiftObstacle, model)
+    dm = DynModel(model)
+    worst, n_plan = 0.0, 0
+    for e in range(n):
+        gid = 60 + e
+        mine = list(rec[rec[:, 51] == gid])
+        ref = ScalarMoPARunner(model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=20, task="lift")
+        k = 0
+        while k < len(mine):
+            for o in [ref.macro_step()] + list(ref.extra_records):
+                if k >= len(mine):
+                    break
+                r = mine[k]
+                assert np.allclose(r[40:48], o[40:48], atol=1e-6), (e, k, r[40:48], o[40:48])
+                assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])
+                assert abs(r[48] - o[48]) < 1e-5, (e, k)
+                d = max(np.abs(r[0:35] - o[0:35]).max(), np.abs(r[52:87] - o[52:87]).max())
+                worst = max(worst, d)
+                assert d < 1e-4, (e, k, d)
+                n_plan += r[50] > 0
+                k += 1
+    assert n_plan > n
+    print("lift: native vs scalar runner: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
