@@ -30,6 +30,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "env-steps/sec (incl. planner) SawyerPushObstacle-v0"
 METRIC_ASSEMBLY = "env-steps/sec (incl. planner) SawyerAssemblyObstacle-v0"
+TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0"}
+
+
+def task_metric(task):
+    return METRIC.replace("SawyerPushObstacle-v0", TASK_ENV[task])
 WORKLOADS = {
     "rollout": "SawyerPushObstacle-v0 MoPA (omega 0.7, action_range 0.5, RRT-Connect range 0.1), %d vectorised envs per GPU, uniform random-exploration policy",
     "validity": "config5 collision-check microbench: SawyerPushObstacle-v0, %d random 7-DoF qpos state-validity queries per GPU, contact_threshold -0.002, cube x {table,bin1} ignored",
@@ -131,16 +136,17 @@ def _cpu_rollout_worker(args):
     from mopa_rl_b200 import rng
     from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.model import load_model
-    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerPushObstacle
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerLiftObstacle, VecSawyerPushObstacle
     from mopa_rl_b200.rollout import MoPAConfig, env_planner_inputs
     from oracle.rollout_oracle import ScalarMoPARunner
 
-    cls = VecSawyerAssemblyObstacle if task == "assembly" else VecSawyerPushObstacle
+    cls = {"assembly": VecSawyerAssemblyObstacle, "lift": VecSawyerLiftObstacle}.get(task, VecSawyerPushObstacle)
     model = load_model(cls.ENV_ID)
     ignored, passive, _ = env_planner_inputs(cls, model)
+    adim = 8 if task == "lift" else 7
 
     def policy(g, k):
-        u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
+        u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(adim, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
     r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15), ignored, passive, gid, seed, policy, task=task)
@@ -206,10 +212,10 @@ def run_reference_arm(args):
             if step >= args.warmup:
                 rates.append((rate, busy))
         value, ms = float(np.mean([r for r, _ in rates])), float(np.mean([d for _, d in rates]) * 1e3)
-        metric, unit = (METRIC if args.task == "push" else METRIC_ASSEMBLY), "env-steps/s"
+        metric, unit = task_metric(args.task), "env-steps/s"
         sample = "%d macro actions per scalar runner per step, one runner (env + planner) per host core" % args.ref_macros
         wl = WORKLOADS["rollout"] % args.envs
-        cfg = {"workload": wl if args.task == "push" else wl.replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "max_iter": args.max_iter}
+        cfg = {"workload": wl.replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "max_iter": args.max_iter}
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -223,18 +229,18 @@ class HostLoopPolicy:
     """End-to-end arm: the policy lives on the host (as the reference's actor loop does): every tick the
     observations of all environments come back to pinned host memory and the actions go up from pinned memory."""
 
-    def __init__(self, torch, device, seed, n):
-        self.torch, self.device, self.n = torch, device, n
+    def __init__(self, torch, device, seed, n, adim=7):
+        self.torch, self.device, self.n, self.adim = torch, device, n, adim
         self.rng = np.random.Generator(np.random.PCG64(seed))
         self.h_obs = torch.zeros(n, 40, dtype=torch.float32).pin_memory()
-        self.h_act = torch.zeros(n, 7, dtype=torch.float32).pin_memory()
+        self.h_act = torch.zeros(n, adim, dtype=torch.float32).pin_memory()
         self.h2d = self.d2h = 0
 
     def __call__(self, obs, env_ids=None, macro_index=None):
         self.h_obs.copy_(obs, non_blocking=False)
-        self.h_act.copy_(self.torch.from_numpy(self.rng.uniform(-1, 1, (self.n, 7)).astype(np.float32)))
+        self.h_act.copy_(self.torch.from_numpy(self.rng.uniform(-1, 1, (self.n, self.adim)).astype(np.float32)))
         self.d2h += self.n * 40 * 4
-        self.h2d += self.n * 7 * 4
+        self.h2d += self.n * self.adim * 4
         return self.h_act.to(self.device, non_blocking=True)
 
 
@@ -242,11 +248,11 @@ def run_rollout(args):
     import torch
     import torch.distributed as dist
 
-    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerPushObstacle
+    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerLiftObstacle, VecSawyerPushObstacle
     from mopa_rl_b200.replay import ReplicatedReplay
     from mopa_rl_b200.rollout import MoPAConfig, NativeMoPARolloutRunner
 
-    env_cls = VecSawyerAssemblyObstacle if args.task == "assembly" else VecSawyerPushObstacle
+    env_cls = {"assembly": VecSawyerAssemblyObstacle, "lift": VecSawyerLiftObstacle}.get(args.task, VecSawyerPushObstacle)
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -305,7 +311,7 @@ def run_rollout(args):
     clocks = sampler.stop() if rank == 0 else None
     counters = dict(runner.counters)
     # end-to-end arm: host-side policy loop + transition records read back to pinned host memory every tick
-    hp = HostLoopPolicy(torch, dev, 99 + rank, n)
+    hp = HostLoopPolicy(torch, dev, 99 + rank, n, 8 if args.task == "lift" else 7)
     runner2 = make(policy=hp)
     replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20)
     h_trans = torch.zeros(n + runner2.reuse_capacity, 92, dtype=torch.float32).pin_memory()
@@ -329,10 +335,10 @@ def run_rollout(args):
         cores = os.cpu_count() or 1
         cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter, task=args.task)
         line = {
-            "metric": METRIC if args.task == "push" else METRIC_ASSEMBLY, "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "metric": task_metric(args.task), "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 collision", "data": "synthetic",
-            "config": {"reuse_data": True, "max_reuse_data": 15, "workload": (WORKLOADS["rollout"] % n) if args.task == "push" else (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", "SawyerAssemblyObstacle-v0"), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
+            "config": {"reuse_data": True, "max_reuse_data": 15, "workload": (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
                        "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
                        "device_ms_per_step": dev_ms / args.steps, "counters": counters},
             "clocks": clocks,
@@ -450,8 +456,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
-    ap.add_argument("--task", default="push", choices=["push", "assembly"],
-                    help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3])")
+    ap.add_argument("--task", default="push", choices=["push", "assembly", "lift"],
+                    help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3]), "
+                         "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there)")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
     ap.add_argument("--cpu-macros", type=int, default=24, help="macro actions per scalar runner in the cpu_baseline leg")
     ap.add_argument("--ref-macros", type=int, default=16, help="macro actions per scalar runner per step of --impl reference")
