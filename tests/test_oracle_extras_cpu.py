@@ -110,3 +110,60 @@ def test_reuse_data_rollout_golden(push_model, push_dyn):
     extra = recs[np.abs(recs[:, 40:47]).max(axis=1) > cfg.omega]
     assert len(extra) > 0 and np.all(np.abs(recs[:, 40:47]) <= 1.0) and np.all(recs[:, 50] >= 0)
     assert r.counters["reused"] == len(recs) - 10
+
+
+def test_lift_env_golden_and_known_answers(oracle_built):
+    """SawyerLiftObstacle-v0 oracle: (i) the can at rest on the bin floor is carried by a contact force equal to its
+    weight, reward = reach term only; (ii) golden open -> insert can -> close -> lift sequence: has_grasp from the
+    contact list, reward 0.5 = grasp_mult + (lift_mult - grasp_mult) above the lift height, + 150 inside the success
+    band (env/sawyer/sawyer_lift_obstacle.py:92-148)."""
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import lift_reset_state
+    from mopa_rl_b200.mjcf import mat_to_quat
+    from mopa_rl_b200.model import load_model
+    from oracle.env_oracle import LiftEnvOracle, _q2m
+
+    m = load_model("SawyerLiftObstacle-v0")
+    dm = DynModel(m)
+    cube = dm.geoms.index(m.geom_name2id("cube"))
+    assert dm._arr["g_type"][cube] == 5 and abs(dm._arr["g_size"][cube][0] - 0.0251) < 1e-4 and abs(dm._arr["g_size"][cube][1] - 0.04) < 1e-6
+    g = np.load(os.path.join(GOLD, "lift_env_steps.npz"))
+    n = g["qpos"].shape[1]
+    q0, v0 = lift_reset_state(m, int(g["seed"]), np.arange(n), np.zeros(n, dtype=np.int64))
+    q0[1, m.get_joint_qpos_addr("right_j1")] = -0.6
+    ca, cva = m.get_joint_qpos_addr("cube")[0], m.get_joint_qvel_addr("cube")[0]
+    weight = m.body_mass[m.body_name2id("cube")] * 9.81
+    for e in range(n):
+        env = LiftEnvOracle(m, dm, max_episode_steps=50)
+        ob0 = env.reset_to(q0[e], v0[e])
+        assert ob0.shape == (35,)
+        for s in range(g["qpos"].shape[0]):
+            if s == 2:   # the can appears between the open fingers, axis perpendicular to the closing direction
+                tips = []
+                for name in ("l_fingertip_g0", "r_fingertip_g0"):
+                    gi = m.geom_name2id(name)
+                    sb = dm.bodies.index(int(m.geom_bodyid[gi]))
+                    tips.append(env.xpos[sb] + _q2m(env.xquat[sb]) @ m.geom_pos[gi])
+                mid, cdir = 0.5 * (tips[0] + tips[1]), (tips[0] - tips[1]) / np.linalg.norm(tips[0] - tips[1])
+                R = _q2m(env.xquat[env.b_ee])
+                ax = R[:, 1] - (R[:, 1] @ cdir) * cdir
+                ax /= np.linalg.norm(ax)
+                q, v = env.qpos.copy(), env.qvel.copy()
+                q[ca:ca + 3], q[ca + 3:ca + 7], v[cva:cva + 6] = mid, mat_to_quat(np.stack([cdir, np.cross(ax, cdir), ax], 1)), 0.0
+                env.set_state(q, v)
+                env.prev_state = None
+            if env.terminal:
+                break
+            ob, r, d = env.step(g["actions"][s, e].astype(np.float64))
+            assert np.abs(env.qpos - g["qpos"][s, e]).max() < 1e-9 and np.abs(env.qvel - g["qvel"][s, e]).max() < 1e-9
+            assert np.abs(ob - g["obs"][s, e]).max() < 1e-9 and abs(r - g["reward"][s, e]) < 1e-12
+            assert env.has_grasp == bool(g["grasp"][s, e])
+            if s < 2:    # can at rest on the bin floor, gripper far away
+                assert abs(env.contact_force - weight) < 0.02 * weight and len(env.contacts) == 1 and m.geom_name2id("cube") in env.contacts[0]
+                assert r < 1e-3 and not env.has_grasp
+            if env.has_grasp:
+                z = ob[27]
+                zt = m.body_pos[m.body_name2id("bin1")][2] + 0.45
+                expect = 0.35 + (1 - np.tanh(15 * max(zt - z, 0.0))) * 0.15 + (150.0 if abs(z - zt) < 0.05 else 0.0)
+                assert abs(r - expect) < 1e-9 and d == (abs(z - zt) < 0.05)
+    assert g["grasp"].sum() >= 4 and (g["reward"] > 100).sum() == 1

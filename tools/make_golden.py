@@ -142,4 +142,53 @@ ql = lift_random_qpos(ml, 4096, 4321, ref_l, sl64)
 wl, dl = sl32.is_valid(ql, True)
 np.savez_compressed(os.path.join(out, "lift_validity.npz"), seed=4321, qpos=ql.astype(np.float32), words_f32=wl,
                     valid_f64=(sl64.is_valid(ql) & 1).astype(np.uint8), min_dist_f32=dl.astype(np.float32))
+
+# 8. lift env (SawyerLiftObstacle-v0): open the gripper, place the can between the fingers, close, lift - grasp / lift /
+#    success rewards, contact list and the 8-D action with the gripper entry
+from mopa_rl_b200.envs import lift_reset_state  # noqa: E402
+from oracle.env_oracle import LiftEnvOracle, _q2m  # noqa: E402
+from mopa_rl_b200.mjcf import mat_to_quat  # noqa: E402
+
+
+def lift_can_between_fingers(model, dm, e):
+    tips = []
+    for name in ("l_fingertip_g0", "r_fingertip_g0"):
+        g = model.geom_name2id(name)
+        sb = dm.bodies.index(int(model.geom_bodyid[g]))
+        tips.append(e.xpos[sb] + _q2m(e.xquat[sb]) @ model.geom_pos[g])
+    mid, cdir = 0.5 * (tips[0] + tips[1]), (tips[0] - tips[1]) / np.linalg.norm(tips[0] - tips[1])
+    R = _q2m(e.xquat[e.b_ee])
+    ax = R[:, 1] - (R[:, 1] @ cdir) * cdir
+    ax /= np.linalg.norm(ax)
+    return mid, mat_to_quat(np.stack([cdir, np.cross(ax, cdir), ax], 1))
+
+
+dml = DynModel(ml)
+nl = 2
+ql0, vl0 = lift_reset_state(ml, 13, np.arange(nl), np.zeros(nl, dtype=np.int64))
+ql0[1, ml.get_joint_qpos_addr("right_j1")] = -0.6           # second env: fingertips at the success height
+rngl = np.random.default_rng(4)
+acts_l = np.zeros((7, nl, 8), np.float32)
+acts_l[:2, :, :7] = rngl.uniform(-0.2, 0.2, (2, nl, 7))
+acts_l[:2, :, 7] = -1.0                                      # open
+acts_l[2:, :, 7] = 0.004                                     # close gently
+acts_l[4:, :, :7] = rngl.uniform(-1, 1, (3, nl, 7))          # move the arm with the can in hand
+Ql, Vl, Rl, Ol, Gl = np.zeros((7, nl, ml.nq)), np.zeros((7, nl, ml.nv)), np.zeros((7, nl)), np.zeros((7, nl, 35)), np.zeros((7, nl), np.uint8)
+ca, cva = ml.get_joint_qpos_addr("cube")[0], ml.get_joint_qvel_addr("cube")[0]
+for e in range(nl):
+    env = LiftEnvOracle(ml, dml, max_episode_steps=50)
+    env.reset_to(ql0[e], vl0[e])
+    for s in range(7):
+        if s == 2:
+            mid, quat = lift_can_between_fingers(ml, dml, env)
+            q, v = env.qpos.copy(), env.qvel.copy()
+            q[ca:ca + 3], q[ca + 3:ca + 7], v[cva:cva + 6] = mid, quat, 0.0
+            env.set_state(q, v)
+            env.prev_state = None
+        if env.terminal:
+            break
+        Ol[s, e], Rl[s, e], _ = env.step(acts_l[s, e].astype(np.float64))
+        Ql[s, e], Vl[s, e], Gl[s, e] = env.qpos, env.qvel, env.has_grasp
+np.savez_compressed(os.path.join(out, "lift_env_steps.npz"), seed=13, actions=acts_l, qpos=Ql, qvel=Vl, reward=Rl, obs=Ol, grasp=Gl)
+print("lift env golden: rewards", Rl.round(3).tolist(), "grasp", Gl.tolist())
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
