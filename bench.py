@@ -109,11 +109,11 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def push_setup():
+def push_setup(task="push"):
     from mopa_rl_b200.model import load_model
     from mopa_rl_b200.rollout import planner_inputs
 
-    model = load_model("SawyerPushObstacle-v0")
+    model = load_model(TASK_ENV[task])
     ignored, passive, ref = planner_inputs(model)
     return model, ignored, passive, ref
 
@@ -371,7 +371,9 @@ def run_validity(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model, ignored, passive, ref = push_setup()
+    if args.task == "assembly":
+        raise SystemExit("--workload validity runs on the push (BASELINE config 5) or lift (mesh collider) scene")
+    model, ignored, passive, ref = push_setup(args.task)
     planner = NativePlanner(model, passive, ignored, -0.002, 0.1, seed=1234, device=local_rank)
     n = args.queries
     row = ((model.nq + 3) // 4) * 4
@@ -433,14 +435,14 @@ def run_validity(args):
             "metric": "state-validity queries/sec (collision-check microbench)", "value": world * n / (ms_step * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS["validity"] % n, "queries_per_gpu": n, "row_bytes": row * 4,
+            "config": {"workload": (WORKLOADS["validity"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "queries_per_gpu": n, "row_bytes": row * 4,
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % (n * row * 4 / 1e9), "valid_fraction": float((words & 1).mean())},
             "clocks": clocks,
             "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * row * 4, "d2h_bytes_per_step": n * 4,
                     "api": "mopa_is_valid_host_f32 (pinned host rows in, result words out)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v4_traffic.json")),
+                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v4_traffic.json") if args.task == "push" else None),
                          "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query},
             "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism}}))

@@ -37,8 +37,11 @@ static MOPA_HD_COLD int hull_extreme(const float *hull, int n, const V3 &l) {
     }
     return best;
 }
-MOPA_HD float plane_mesh(const Geom &p, const Geom &g) {
+// `thr`: distances above it are never looked at by the validity predicate, so when the hull's bounding sphere (radius in
+// g.size.z, inflated by 1e-6 against rounding) clears the plane by more than thr the 100-odd vertices are not scanned.
+MOPA_HD float plane_mesh(const Geom &p, const Geom &g, float thr) {
     V3 n = col(p.R, 2), d = g.c - p.c;
+    if (dot(n, d) - g.size.z * 1.000001f > thr) return MOPA_BIG;
     V3 l = mulMTV(g.R, n);
     const float *v = g.hull + 3 * hull_extreme(g.hull, g.nhull, neg(l));
     return dot(n, d) + dot(V3{v[0], v[1], v[2]}, l);
@@ -357,7 +360,7 @@ MOPA_HD int pair_class(int ka, int kb) {
 }
 // cheap classes, evaluated inline by the owning thread
 template <bool MESH>
-MOPA_HD float cheap_dist(int cls, const Geom &a, const Geom &b) {
+MOPA_HD float cheap_dist(int cls, const Geom &a, const Geom &b, float thr) {
     switch (cls) {
     case PC_PLANE_SPHERE: return plane_sphere(a, b);
     case PC_PLANE_CAPSULE: return plane_capsule(a, b);
@@ -368,7 +371,7 @@ MOPA_HD float cheap_dist(int cls, const Geom &a, const Geom &b) {
     case PC_SPHERE_CYLINDER: return sphere_cylinder(a, b);
     case PC_SPHERE_BOX: return sphere_box(a, b);
     case PC_CAPSULE_CAPSULE: return capsule_capsule(a, b);
-    case PC_PLANE_MESH: return MESH ? plane_mesh(a, b) : MOPA_BIG;
+    case PC_PLANE_MESH: return MESH ? plane_mesh(a, b, thr) : MOPA_BIG;
     default: return MOPA_BIG;
     }
 }

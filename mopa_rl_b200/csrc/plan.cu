@@ -168,7 +168,7 @@ __device__ __forceinline__ bool states_all_valid(const WarpCtx &W, const SpaceDe
                 Geom a, b;
                 load_geom<MESH>(a, W.S.recs[pr.ga], W.frames, PW_STATES, k);
                 load_geom<MESH>(b, W.S.recs[pr.gb], W.frames, PW_STATES, k);
-                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b);
+                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
                 if (dist <= thr) bad = true;
             }
         }

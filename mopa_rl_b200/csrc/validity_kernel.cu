@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__res
                 Geom a, b;
                 load_geom<MESH>(a, S.recs[pr.ga], frames, NQ, tid);
                 load_geom<MESH>(b, S.recs[pr.gb], frames, NQ, tid);
-                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b);
+                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
                 if (dist <= thr) {
                     first = min(first, (uint32_t)pr.canon);
                     if (!exact) break;

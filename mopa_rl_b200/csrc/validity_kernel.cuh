@@ -111,6 +111,7 @@ __device__ __forceinline__ void load_geom(Geom &g, const GeomRec &r, const float
     if (MESH && r.kind == K_MESH) {   // sx / sy carry (byte offset of the hull vertices from this record, vertex count)
         g.hull = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(&r) + __float_as_int(r.sx));
         g.nhull = __float_as_int(r.sy);
+        g.size.z = r.rbound;   // bounding radius of the hull (plane - hull cull)
     }
     if (r.slot < 0) {
         g.c = V3{r.px, r.py, r.pz};
