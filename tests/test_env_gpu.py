@@ -1,5 +1,7 @@
 """GPU <-> oracle parity of the vectorised env.step (physics + env logic), through the C ABI.
 Tolerance stated by BASELINE.json north_star: qpos / qvel within 1e-5 absolute."""
+from collections import OrderedDict
+
 import numpy as np
 import pytest
 
@@ -192,3 +194,63 @@ def test_lift_env_step_matches_oracle(oracle_built):
     assert worst["obs"] < 1e-4 and worst["rew"] < 1e-6, worst
     assert {"reach", "lift", "success"} <= kinds, kinds
     print("lift max abs error:", worst, sorted(kinds))
+
+
+def test_gym_env_view_drop_in_loop(push_model, oracle_built):
+    """The reference-facing N = 1 view (gym_env.make, env/__init__.py:7-32 + BaseEnv API) driven the way
+    rl/trainer.py:62-75 and rl/mopa_rollouts.py drive the reference env - trainer-style planner set-up from the env's
+    attributes, a direct step, planner steps through form_action, the planner-failure pair compute_reward /
+    _after_step - against the env oracle."""
+    import types
+
+    from mopa_rl_b200 import gym_env
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import push_reset_state
+    from mopa_rl_b200.motion_planners import SamplingBasedPlanner
+    from oracle.env_oracle import PushEnvOracle
+
+    env = gym_env.make("SawyerPushObstacle-v0", seed=77, max_episode_steps=12)
+    ob = env.reset()
+    q0, v0 = push_reset_state(push_model, 77, [0], [0])
+    orc = PushEnvOracle(push_model, DynModel(push_model), max_episode_steps=12)
+    ob0 = orc.reset_to(q0[0], v0[0])
+    cat = lambda o: np.concatenate(list(o.values()))
+    assert list(ob.keys())[:3] == ["joint_pos", "joint_vel", "gripper_qpos"] and np.abs(cat(ob) - ob0).max() < 1e-5
+    # rl/trainer.py:62-75: ignored contacts and passive joints from the env's attributes
+    ignored = [(min(a, b), max(a, b)) for a in env.manipulation_geom_ids for b in env.static_geom_ids]
+    passive = [i for i in range(len(env.sim.data.qpos)) if i not in env.ref_joint_pos_indexes]
+    cfg = types.SimpleNamespace(planner_type="rrt_connect", range=0.1, planner_objective="path_length", threshold=0.0, seed=1234)
+    planner = SamplingBasedPlanner(cfg, env.xml_path, env.sim.model.nu, [], passive_joint_idx=passive, ignored_contacts=ignored,
+                                   contact_threshold=-0.002)
+    assert planner.isValidState(env.sim.data.qpos)
+    # direct step
+    a = np.random.default_rng(1).uniform(-1, 1, 7).astype(np.float32)
+    ob, r, d, info = env.step(OrderedDict([("default", a)]))
+    o2, r2, d2 = orc.step(a.astype(np.float64))
+    assert np.abs(cat(ob) - o2).max() < 1e-4 and abs(r - r2) < 1e-9 and d == d2 and info == {}
+    assert np.abs(env.sim.data.qpos - orc.qpos).max() < 1e-5 and env.sim.data.ncon == orc.ncon
+    assert abs(env.get_contact_force() - orc.contact_force) < 1e-6 * max(1.0, orc.contact_force)
+    # a short plan executed waypoint by waypoint (rl/mopa_rollouts.py:166-199)
+    curr = env.sim.data.qpos.copy()
+    target = curr.copy()
+    target[env.ref_joint_pos_indexes] += 0.03
+    traj, _, valid, exact = planner.plan(curr, target, timelimit=0.3)
+    assert valid and (not exact or len(traj) >= 2)
+    for nq in (traj[1:] if exact else []):
+        ac = env.form_action(nq)
+        ob, r, d, info = env.step(ac, is_planner=True)
+        o2, r2, d2 = orc.step(np.asarray(ac["default"], np.float32).astype(np.float64), True)
+        assert np.abs(cat(ob) - o2).max() < 1e-4 and abs(r - r2) < 1e-9 and d == d2
+        if d:
+            break
+    env._reset_prev_state()
+    orc.prev_state = None
+    # planner failure: compute_reward(zeros) + _after_step (rl/mopa_rollouts.py:304-327)
+    if not env._terminal:
+        reward, info = env.compute_reward(np.zeros(env.sim.model.nu))
+        done, info, _ = env._after_step(reward, False, info)
+        r2, d2 = orc.null_step()
+        assert abs(reward - r2) < 1e-9 and done == d2 and env._episode_length == orc.ep_len
+    grip = env.sim.data.get_site_xpos("grip_site")
+    assert np.abs(grip - (orc._site(orc.b_ee, orc.s_grip))).max() < 1e-3      # frames of the last substep vs current qpos
+    env.close()
