@@ -81,3 +81,50 @@ def test_sentinel_statuses(setup, push_model):
     oob[ref[0]] = 3.2                                         # outside jnt_range of right_j0 (+-3.0503)
     assert pl.plan(q0, oob, 1, 50)["status"] in (-4, -5)
     assert pl.plan(q0, cand[(scene.is_valid(cand) & 1) == 1][0], 3, 0)["status"] == -4   # zero iterations: no solution
+
+
+def test_pusher_scene_golden_and_so2_invariants(oracle_built):
+    """PusherObstacle-v0 (BASELINE configs[0]): joint0 is an unlimited hinge -> SO(2) sub-space
+    (mujoco_ompl_interface.cpp:149-281), the other three hinges are bounded; reference Pusher settings
+    (config/pusher.py: range 0.2, contact_threshold -0.0015).  Validity words and RRT-Connect traces against the golden
+    file; waypoints stay in [-pi, pi] on joint0 and hops are measured around the circle."""
+    import os
+
+    from mopa_rl_b200.model import load_model
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pusher_validity_rrt.npz"))
+    m = load_model("PusherObstacle-v0")
+    static = [m.geom_name2id("obstacle%d_geom" % i) for i in range(1, 8)]
+    box = m.geom_name2id("box")
+    ignored = [(min(box, s), max(box, s)) for s in static]
+    ref = [m.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+    passive = [i for i in range(m.nq) if i not in ref]
+    s32 = oracle_built.OracleScene(m, ignored, -0.0015, "f32")
+    s64 = oracle_built.OracleScene(m, ignored, -0.0015, "f64")
+    assert s32.npair == 80
+    q = np.tile(m.qpos0, (len(g["active"]), 1))
+    q[:, ref] = g["active"].astype(np.float64)
+    w = s32.is_valid(q)
+    assert np.array_equal(w, g["words_f32"]) and np.array_equal(s64.is_valid(q) & 1, g["valid_f64"])
+    assert int(((w & 1) != g["valid_f64"]).sum()) <= 2                      # fp32 vs fp64 flips (report; 0-2 on 4096 states)
+    adr, lo, hi, so2 = oracle_built.space_from_model(m, passive)
+    assert list(so2) == [1, 0, 0, 0] and abs(hi[0] - np.pi) < 1e-12 and lo[1] == -3.0
+    pl = oracle_built.OraclePlanner(s32, adr, lo, hi, so2, 0.2, 0.005, seed=9)
+    v = q[(w & 1) == 1]
+    n = int(g["n_plans"])
+    n_ok = 0
+    for i in range(n):
+        r = pl.plan(v[i], v[n + i], int(g["keys"][i]), int(g["max_iter"]), 512)
+        L = len(r["path"])
+        assert r["status"] == g["status"][i] and r["iters"] == g["iters"][i] and L == g["path_len"][i]
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.array_equal(r["node_ids"], g["node_ids"][i, :L])
+            p = r["path"][:, ref]
+            assert np.array_equal(p.astype(np.float32), g["paths"][i, :L])
+            assert np.abs(p[:, 0]).max() <= np.float32(np.pi)
+            d0 = np.abs(np.diff(p[:, 0]))
+            hop = np.minimum(d0, 2 * np.pi - d0) + np.abs(np.diff(p[:, 1:], axis=0)).sum(1)
+            assert len(hop) == 0 or hop.max() <= 0.2 + 1e-5
+            assert (s32.is_valid(r["path"]) & 1).all()
+    assert n_ok >= 3

@@ -191,4 +191,40 @@ for e in range(nl):
         Ql[s, e], Vl[s, e], Gl[s, e] = env.qpos, env.qvel, env.has_grasp
 np.savez_compressed(os.path.join(out, "lift_env_steps.npz"), seed=13, actions=acts_l, qpos=Ql, qvel=Vl, reward=Rl, obs=Ol, grasp=Gl)
 print("lift env golden: rewards", Rl.round(3).tolist(), "grasp", Gl.tolist())
+
+# 9. Pusher scene (BASELINE configs[0]: 2-D pusher, joint0 on SO(2), range 0.2, contact_threshold -0.0015):
+#    validity words and RRT-Connect traces
+mp = load_model("PusherObstacle-v0")
+static_p = [mp.geom_name2id("obstacle%d_geom" % i) for i in range(1, 8)]
+box_p = mp.geom_name2id("box")
+ign_p = [(min(box_p, g), max(box_p, g)) for g in static_p]
+ref_p = [mp.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+pas_p = [i for i in range(mp.nq) if i not in ref_p]
+sp32 = oracle.OracleScene(mp, ign_p, -0.0015, "f32")
+sp64 = oracle.OracleScene(mp, ign_p, -0.0015, "f64")
+rngp = np.random.Generator(np.random.PCG64(5))
+qp = np.tile(mp.qpos0, (4096, 1))
+qp[:, ref_p[0]] = rngp.uniform(-3.14, 3.14, 4096)
+for k in (1, 2, 3):
+    jp = list(mp.jnt_qposadr).index(ref_p[k])
+    qp[:, ref_p[k]] = rngp.uniform(mp.jnt_range[jp, 0], mp.jnt_range[jp, 1], 4096)
+qp = qp.astype(np.float32).astype(np.float64)
+wp = sp32.is_valid(qp)
+adr_p, lo_p, hi_p, so2_p = oracle.space_from_model(mp, pas_p)
+plp = oracle.OraclePlanner(sp32, adr_p, lo_p, hi_p, so2_p, 0.2, 0.005, seed=9)
+vp = qp[(wp & 1) == 1]
+st_p, it_p, len_p, ids_p, paths_p = [], [], [], [], []
+for i in range(24):
+    r = plp.plan(vp[i], vp[24 + i], 100 + i, 400, 512)
+    st_p.append(r["status"]), it_p.append(r["iters"]), len_p.append(len(r["path"]))
+    pid = np.full(512, -1, np.int32)
+    pid[: len(r["node_ids"])] = r["node_ids"]
+    ids_p.append(pid)
+    pp = np.zeros((512, 4), np.float32)
+    pp[: len(r["path"])] = r["path"][:, ref_p]
+    paths_p.append(pp)
+np.savez_compressed(os.path.join(out, "pusher_validity_rrt.npz"), active=qp[:, ref_p].astype(np.float32), words_f32=wp,
+                    valid_f64=(sp64.is_valid(qp) & 1).astype(np.uint8), n_plans=24, keys=np.arange(24) + 100, max_iter=400,
+                    status=np.array(st_p), iters=np.array(it_p), path_len=np.array(len_p), node_ids=np.array(ids_p), paths=np.array(paths_p))
+print("pusher golden: valid fraction %.3f, plan status %s" % ((wp & 1).mean(), st_p))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
