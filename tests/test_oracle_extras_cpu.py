@@ -167,3 +167,53 @@ def test_lift_env_golden_and_known_answers(oracle_built):
                 expect = 0.35 + (1 - np.tanh(15 * max(zt - z, 0.0))) * 0.15 + (150.0 if abs(z - zt) < 0.05 else 0.0)
                 assert abs(r - expect) < 1e-9 and d == (abs(z - zt) < 0.05)
     assert g["grasp"].sum() >= 4 and (g["reward"] > 100).sum() == 1
+
+
+def test_scalar_loop_discrete_and_lift_goldens(push_model, push_dyn, oracle_built):
+    """Scalar restatement of MoPARolloutRunner.run with (i) config.discrete_action (omega = 0; ac_type in record slot 47,
+    direct actions unscaled, relabelled records inherit ac_type) and (ii) the lift task (8-D actions, gripper entry in
+    slot 47): records of one environment against the golden file."""
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerLiftObstacle
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import MoPAConfig, env_planner_inputs, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    g = np.load(os.path.join(GOLD, "rollout_discrete_lift.npz"))
+
+    def pol_d(gid, k):
+        u = rng.uniform01(13, np.uint64(gid), np.uint64(k), np.arange(8, dtype=np.uint64))
+        return (2.0 * u[:7] - 1.0).astype(np.float32), bool(u[7] < 0.5)
+
+    ign, pas, _ = planner_inputs(push_model)
+    cfg = MoPAConfig(max_iter=150, seed=23, omega=0.0, discrete_action=True, reuse_data=True, max_reuse_data=15)
+    run = ScalarMoPARunner(push_model, push_dyn, cfg, ign, pas, 300, 606, pol_d, max_episode_steps=30)
+    recs = []
+    for _ in range(12):
+        recs.append(run.macro_step())
+        recs.extend(run.extra_records)
+    recs = np.array(recs, np.float32)
+    assert recs.shape == g["discrete"].shape and np.abs(recs - g["discrete"]).max() < 1e-6
+    assert set(np.unique(recs[:, 47])) == {0.0, 1.0}
+    direct = recs[(recs[:, 47] == 0)]
+    assert np.all(direct[:, 50] == 0)                                          # direct actions are single env.steps
+    assert run.counters["rl"] == len(direct) and run.counters["reused"] > 0
+
+    def pol_l(gid, k):
+        u = rng.uniform01(19, np.uint64(gid), np.uint64(k), np.arange(8, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ml = load_model("SawyerLiftObstacle-v0")
+    ign_l, pas_l, _ = env_planner_inputs(VecSawyerLiftObstacle, ml)
+    cfg_l = MoPAConfig(max_iter=150, seed=31, reuse_data=True, max_reuse_data=15)
+    run_l = ScalarMoPARunner(ml, DynModel(ml), cfg_l, ign_l, pas_l, 60, 515, pol_l, max_episode_steps=20, task="lift")
+    recs_l = []
+    for _ in range(8):
+        recs_l.append(run_l.macro_step())
+        recs_l.extend(run_l.extra_records)
+    recs_l = np.array(recs_l, np.float32)
+    assert recs_l.shape == g["lift"].shape and np.abs(recs_l - g["lift"]).max() < 1e-6
+    assert np.all(recs_l[:, 35:40] == 0) and np.all(recs_l[:, 87:92] == 0)      # 35-float observations in 40-float rows
+    main = recs_l[recs_l[:, 47] != 0]
+    assert len(main) == 8                                                      # main records carry the policy's gripper entry, relabelled ones 0

@@ -86,7 +86,6 @@ def test_passive_dims_frozen_and_key_dependence(planners, push_model):
 def test_lift_plan_matches_oracle(oracle_built):
     """RRT-Connect on the lift scene (mesh collider): the can floats next to the arm so that edges are checked
     against the hull; status / iterations / node ids / waypoints bit-identical to the oracle."""
-    from helpers import lift_random_qpos
     from mopa_rl_b200.capi import NativePlanner
     from mopa_rl_b200.model import load_model
 

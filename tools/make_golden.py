@@ -227,4 +227,38 @@ np.savez_compressed(os.path.join(out, "pusher_validity_rrt.npz"), active=qp[:, r
                     valid_f64=(sp64.is_valid(qp) & 1).astype(np.uint8), n_plans=24, keys=np.arange(24) + 100, max_iter=400,
                     status=np.array(st_p), iters=np.array(it_p), path_len=np.array(len_p), node_ids=np.array(ids_p), paths=np.array(paths_p))
 print("pusher golden: valid fraction %.3f, plan status %s" % ((wp & 1).mean(), st_p))
+
+# 10. scalar rollout loop, discrete_action (omega = 0, ac_type picks the branch) and the lift task (8-D actions): records of one env
+cfg_d = MoPAConfig(max_iter=150, seed=23, omega=0.0, discrete_action=True, reuse_data=True, max_reuse_data=15)
+
+
+def _policy_d(g, k):
+    u = crng.uniform01(13, np.uint64(g), np.uint64(k), np.arange(8, dtype=np.uint64))
+    return (2.0 * u[:7] - 1.0).astype(np.float32), bool(u[7] < 0.5)
+
+
+run_d = ScalarMoPARunner(m, dm, cfg_d, ign2, pas2, 300, 606, _policy_d, max_episode_steps=30)
+recs_d = []
+for _ in range(12):
+    recs_d.append(run_d.macro_step())
+    recs_d.extend(run_d.extra_records)
+from mopa_rl_b200.envs import VecSawyerLiftObstacle  # noqa: E402
+from mopa_rl_b200.rollout import env_planner_inputs  # noqa: E402
+
+cfg_l = MoPAConfig(max_iter=150, seed=31, reuse_data=True, max_reuse_data=15)
+
+
+def _policy_l(g, k):
+    u = crng.uniform01(19, np.uint64(g), np.uint64(k), np.arange(8, dtype=np.uint64))
+    return (2.0 * u - 1.0).astype(np.float32)
+
+
+ign_l2, pas_l2, _ = env_planner_inputs(VecSawyerLiftObstacle, ml)
+run_l = ScalarMoPARunner(ml, DynModel(ml), cfg_l, ign_l2, pas_l2, 60, 515, _policy_l, max_episode_steps=20, task="lift")
+recs_l = []
+for _ in range(8):
+    recs_l.append(run_l.macro_step())
+    recs_l.extend(run_l.extra_records)
+np.savez_compressed(os.path.join(out, "rollout_discrete_lift.npz"), discrete=np.array(recs_d, np.float32), lift=np.array(recs_l, np.float32))
+print("rollout goldens: discrete %d records, lift %d records" % (len(recs_d), len(recs_l)))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
