@@ -192,7 +192,8 @@ typedef struct mopa_rollout_config {
     uint64_t seed_reuse;          /* seed of the (start, goal) draws, keyed by env id and macro-action index */
     int32_t discrete_action;      /* config.discrete_action (rl/mopa_rollouts.py:86-88): ac_type picks planner / direct execution;
                                      direct actions are not divided by omega; record slot 47 carries ac_type */
-    int32_t pad_;
+    int32_t ac_space_normal;      /* config.ac_space_type == "normal" (scripts/3d/{lift,assembly}/mopa_discrete.sh): planner displacement =
+                                     a * action_range and relabelled action = d / action_range (rl/sac_agent.py:160-163, 180-181); 0 = piecewise */
 } mopa_rollout_config;
 /* Counter slots of d_counters (int64[16]). */
 #define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting,reused"

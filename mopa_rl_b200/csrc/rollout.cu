@@ -77,6 +77,7 @@ struct RoDev {   // everything the kernels need, passed by value
     int reuse_data, max_reuse;
     int adim, grip_qadr0;        // action entries per environment (7; 8 for the lift task: + gripper), qpos address of rc_close
     double *grip0;               // [n] gripper qpos when the current plan was made (SawyerEnv.form_action with dof == 8, :290-296)
+    int ac_normal;               // config.ac_space_type == "normal": displacement = a * action_range (rl/sac_agent.py:160-163, 180-181)
     int discrete;                // config.discrete_action: the policy's ac_type chooses planner / direct execution
     unsigned long long seed_reuse;
     float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
@@ -163,9 +164,10 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     bool planner_ac = false, valid_ac = true;
                     for (int k = 0; k < 7; k++) {
                         const double d = tr[goal * 7 + k] - tr[start * 7 + k], ad = fabs(d);
-                        const double a = ad < S.ac_scale ? d * (S.omega / S.ac_scale)
-                                                         : (d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0)) *
-                                                               ((ad - S.ac_scale) / ((S.action_range - S.ac_scale) / (1.0 - S.ac_scale)) / ((1.0 - S.ac_scale) / (1.0 - S.omega)) + S.omega);
+                        const double a = S.ac_normal ? d / S.action_range
+                                         : ad < S.ac_scale ? d * (S.omega / S.ac_scale)
+                                                           : (d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0)) *
+                                                                 ((ad - S.ac_scale) / ((S.action_range - S.ac_scale) / (1.0 - S.ac_scale)) / ((1.0 - S.ac_scale) / (1.0 - S.omega)) + S.omega);
                         if (a < -S.omega || a > S.omega) planner_ac = true;
                         if (a < -1.0 || a > 1.0) valid_ac = false;
                         ia[k] = (float)a;
@@ -251,8 +253,9 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
     const double w = S.omega;
     for (int k = 0; k < 7; k++) {
         const double a = (double)a32[k], aa = fabs(a);
-        const double disp = aa < w ? a / (w / S.ac_scale)
-                                   : (a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0)) * (S.ac_scale + (S.action_range - S.ac_scale) * ((aa - w) / (1 - w)));
+        const double disp = S.ac_normal ? a * S.action_range
+                            : aa < w ? a / (w / S.ac_scale)
+                                     : (a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0)) * (S.ac_scale + (S.action_range - S.ac_scale) * ((aa - w) / (1 - w)));
         double t = curr[S.arm_qadr[k]] + disp;
         t = t < S.jlo[k] ? S.jlo[k] : t;
         t = t > S.jhi[k] ? S.jhi[k] : t;
@@ -635,6 +638,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
     S.discrete = cfg->discrete_action ? 1 : 0;
+    S.ac_normal = cfg->ac_space_normal ? 1 : 0;
     S.adim = env->task.kind == 1 ? 8 : 7;
     S.grip_qadr0 = env->task.grip_qadr[0];
     if (S.adim == 8 && S.discrete) { mopa_set_error("mopa_rollout_create: discrete_action is not built for the 8-D lift action (record slot 47 is taken)"); delete r; return MOPA_ERR_ARG; }

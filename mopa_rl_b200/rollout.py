@@ -43,6 +43,7 @@ class MoPAConfig:
     seed = 1234
     reuse_data = False         # scripts/3d/push/mopa.sh sets True: relabel (start, goal) pairs of every executed plan
     max_reuse_data = 15
+    ac_space_type = "piecewise"  # "normal" (lift / assembly / 2d mopa_discrete.sh): displacement = a * action_range
     discrete_action = False    # scripts/3d/*/mopa_discrete.sh (with omega = 0): the policy's ac_type picks planner / direct
 
     def __init__(self, **kw):
@@ -111,8 +112,8 @@ class VecMoPARolloutRunner:
     def __init__(self, venv, config=None, policy=None, transition_capacity=1 << 20):
         import torch
 
-        if config is not None and (config.discrete_action or config.reuse_data):
-            raise NotImplementedError("discrete_action / reuse_data are implemented by NativeMoPARolloutRunner only")
+        if config is not None and (config.discrete_action or config.reuse_data or config.ac_space_type != "piecewise"):
+            raise NotImplementedError("discrete_action / reuse_data / ac_space_type 'normal' are implemented by NativeMoPARolloutRunner only")
 
         self.torch = torch
         self.venv, self.cfg = venv, config or MoPAConfig()
@@ -505,7 +506,7 @@ class _RolloutConfig(_C.Structure):
                [(k, _C.c_double) for k in ("omega", "action_range", "ac_scale", "discount", "step_size", "joint_margin", "range")] + \
                [("seed_env", _C.c_uint64), ("env_id_offset", _C.c_int64), ("jnt_lo", _C.c_double * 7), ("jnt_hi", _C.c_double * 7),
                 ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p), ("reuse_data", _C.c_int32), ("max_reuse_data", _C.c_int32),
-                ("seed_reuse", _C.c_uint64), ("discrete_action", _C.c_int32), ("pad_", _C.c_int32)]
+                ("seed_reuse", _C.c_uint64), ("discrete_action", _C.c_int32), ("ac_space_normal", _C.c_int32)]
 
 
 class NativeMoPARolloutRunner:
@@ -556,6 +557,9 @@ class NativeMoPARolloutRunner:
         c.qpos0 = self._qpos0.ctypes.data
         c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
         c.discrete_action = int(cfg.discrete_action)
+        if cfg.ac_space_type not in ("piecewise", "normal"):
+            raise NotImplementedError("ac_space_type %r" % (cfg.ac_space_type,))   # rl/sac_agent.py:174-175 raises as well
+        c.ac_space_normal = int(cfg.ac_space_type == "normal")
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
                                           _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.c_void_p, _C.POINTER(_C.c_void_p)]

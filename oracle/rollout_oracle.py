@@ -138,6 +138,8 @@ class ScalarMoPARunner:
             with np.errstate(divide="ignore", invalid="ignore"):   # omega = 0 (discrete presets): the first branch is never selected
                 disp = np.where(np.abs(ac) < w, ac / (w / cfg.ac_scale),
                                 np.sign(ac) * (cfg.ac_scale + (cfg.action_range - cfg.ac_scale) * ((np.abs(ac) - w) / (1 - w))))
+            if getattr(cfg, "ac_space_type", "piecewise") == "normal":   # rl/sac_agent.py:160-163
+                disp = ac * cfg.action_range
             target = curr.copy()
             target[:7] = np.clip(curr[:7] + disp, self.jlo, self.jhi)
             if cfg.invalid_target_handling and not self._valid(target):
@@ -214,6 +216,8 @@ class ScalarMoPARunner:
             d = traj[goal][:7] - traj[start][:7]                                  # env.form_action(traj[goal], traj[start])
             s, w, ar = cfg.ac_scale, cfg.omega, cfg.action_range                  # SACAgent.invert_displacement, piecewise
             a = np.where(np.abs(d) < s, d * (w / s), np.sign(d) * ((np.abs(d) - s) / ((ar - s) / (1.0 - s)) / ((1.0 - s) / (1.0 - w)) + w))
+            if getattr(cfg, "ac_space_type", "piecewise") == "normal":            # rl/sac_agent.py:180-181
+                a = d / ar
             if not (np.any(a < -w) or np.any(a > w)) or not (np.all(a >= -1.0) and np.all(a <= 1.0)):
                 continue
             rec = np.zeros(92, np.float32)

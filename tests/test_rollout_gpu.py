@@ -174,10 +174,12 @@ def test_run_episodes_reports_reference_episode_info(push_model, oracle_built):
     assert info["mp"] + info["rl"] + info["interpolation"] + info["mp_fail"] > 0
 
 
-def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model, oracle_built):
+@pytest.mark.parametrize("ac_space_type", ["piecewise", "normal"])
+def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model, oracle_built, ac_space_type):
     """config.discrete_action (scripts/3d/push/mopa_discrete.sh: omega = 0, reuse_data): the policy's ac_type picks
     motion planner / direct execution (rl/mopa_rollouts.py:86-88, 104-111), direct actions are executed unscaled
-    (:347-352), relabelled records inherit ac_type (:266-267).  Record slot 47 carries ac_type."""
+    (:347-352), relabelled records inherit ac_type (:266-267).  Record slot 47 carries ac_type.  ac_space_type "normal"
+    (the lift / assembly / 2-D discrete presets): displacement = a * action_range, relabelled action = d / action_range."""
     import torch
 
     from mopa_rl_b200 import rng
@@ -187,7 +189,7 @@ def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model,
     from oracle.rollout_oracle import ScalarMoPARunner
 
     n, ticks, seed = 10, 50, 606
-    cfg = MoPAConfig(max_iter=150, seed=23, omega=0.0, discrete_action=True, reuse_data=True, max_reuse_data=15)
+    cfg = MoPAConfig(max_iter=150, seed=23, omega=0.0, discrete_action=True, reuse_data=True, max_reuse_data=15, ac_space_type=ac_space_type)
     venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=30, env_id_offset=300)
     runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 13, discrete=True))
     for _ in range(ticks):
@@ -224,7 +226,7 @@ def test_native_runner_discrete_action_matches_scalar_reference_loop(push_model,
                 types.add(float(r[47]))
                 k += 1
     assert types == {0.0, 1.0}
-    print("discrete_action: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
+    print("discrete_action (%s): %d records, worst |obs diff| %.2e, counters %s" % (ac_space_type, len(rec), worst, c))
 
 
 def test_native_runner_lift_matches_scalar_reference_loop(oracle_built):
