@@ -91,27 +91,48 @@ class DynModel:
                 live_roots.add(int(root[m.geom_bodyid[g]]))
         for b in acted:
             live_roots.add(int(root[b]))
-        self.bodies = [b for b in range(1, nb) if root[b] in live_roots]
-        idx = {b: i for i, b in enumerate(self.bodies)}
+        # A body with several joints (Pusher: the box and the target carry two slide joints each) becomes a chain of
+        # simulated bodies, one joint each: massless virtual bodies for all joints but the last, which stays on the
+        # body itself.  Virtual entries are listed as -1 - body id so that look-ups by body id find the real one.
+        entries = []   # (model body, joint id or -1, first of its chain, last of its chain)
+        for b in range(1, nb):
+            if root[b] not in live_roots:
+                continue
+            nj = int(m.body_jntnum[b])
+            if nj <= 1:
+                entries.append((b, int(m.body_jntadr[b]) if nj == 1 else -1, True, True))
+            else:
+                js = [int(m.body_jntadr[b]) + k for k in range(nj)]
+                if any(int(m.jnt_type[j]) != JNT_SLIDE for j in js):
+                    raise NotImplementedError("simulated body %s has several joints that are not all slides" % m.names["body"][b])
+                for k, j in enumerate(js):
+                    entries.append((b, j, k == 0, k == nj - 1))
+        self.bodies = [b if last else -1 - b for b, _, _, last in entries]
+        idx = {b: i for i, (b, _, _, last) in enumerate(entries) if last}
         spos, squat = static_frames(m)
         A = lambda *shape: np.zeros(shape)
-        n = len(self.bodies)
+        n = len(entries)
         b_parent = np.full(n, -1, np.int32)
         b_jtype = np.full(n, -1, np.int32)
         b_qadr, b_vadr, b_dadr = np.full(n, -1, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32)
         b_rootpos, b_rootquat = A(n, 3), np.tile(np.array([1.0, 0, 0, 0]), (n, 1))
         b_jaxis, b_jpos, b_qpos0 = A(n, 3), A(n, 3), A(n)
+        b_pos, b_quat = A(n, 3), np.tile(np.array([1.0, 0, 0, 0]), (n, 1))
+        b_mass, b_ipos, b_iquat, b_inertia = A(n), A(n, 3), np.tile(np.array([1.0, 0, 0, 0]), (n, 1)), A(n, 3)
         d_body, d_qadr, d_vadr, d_arm, d_damp, d_lim, d_range, d_solref, d_solimp, d_margin = [], [], [], [], [], [], [], [], [], []
-        for i, b in enumerate(self.bodies):
+        for i, (b, j, first, last) in enumerate(entries):
             p = int(m.body_parentid[b])
-            if p in idx:
-                b_parent[i] = idx[p]
+            if not first:
+                b_parent[i] = i - 1                      # previous joint of the same body; identity offset
             else:
-                b_rootpos[i], b_rootquat[i] = spos[p], squat[p]
-            if m.body_jntnum[b] > 1:
-                raise NotImplementedError("simulated body %s has more than one joint" % m.names["body"][b])
-            if m.body_jntnum[b] == 1:
-                j = int(m.body_jntadr[b])
+                b_pos[i], b_quat[i] = m.body_pos[b], m.body_quat[b]
+                if p in idx:
+                    b_parent[i] = idx[p]
+                else:
+                    b_rootpos[i], b_rootquat[i] = spos[p], squat[p]
+            if last:
+                b_mass[i], b_ipos[i], b_iquat[i], b_inertia[i] = m.body_mass[b], m.body_ipos[b], m.body_iquat[b], m.body_inertia[b]
+            if j >= 0:
                 t = int(m.jnt_type[j])
                 if t not in (JNT_FREE, JNT_SLIDE, JNT_HINGE):
                     raise NotImplementedError("ball joints")
@@ -173,10 +194,9 @@ class DynModel:
                 g_pos[i] = g_pos[i] + quat_to_mat(squat[int(m.geom_bodyid[g])]) @ off
             g_type[i], g_size[i], g_rbound[i] = 5, [r, hh, 0.0], np.sqrt(r * r + hh * hh)
         arr = dict(
-            b_parent=b_parent, b_bodyid=np.array(self.bodies, np.int32), b_pos=m.body_pos[self.bodies], b_quat=m.body_quat[self.bodies],
+            b_parent=b_parent, b_bodyid=np.array(self.bodies, np.int32), b_pos=b_pos, b_quat=b_quat,
             b_rootpos=b_rootpos, b_rootquat=b_rootquat, b_jtype=b_jtype, b_qadr=b_qadr, b_vadr=b_vadr, b_dadr=b_dadr,
-            b_jaxis=b_jaxis, b_jpos=b_jpos, b_qpos0=b_qpos0, b_mass=m.body_mass[self.bodies], b_ipos=m.body_ipos[self.bodies],
-            b_iquat=m.body_iquat[self.bodies], b_inertia=m.body_inertia[self.bodies],
+            b_jaxis=b_jaxis, b_jpos=b_jpos, b_qpos0=b_qpos0, b_mass=b_mass, b_ipos=b_ipos, b_iquat=b_iquat, b_inertia=b_inertia,
             d_body=np.array(d_body, np.int32), d_qadr=self.dof_qadr, d_vadr=self.dof_vadr, d_armature=np.array(d_arm),
             d_damping=np.array(d_damp), d_limited=np.array(d_lim, np.int32), d_range=np.array(d_range).reshape(-1, 2),
             d_solref=np.array(d_solref).reshape(-1, 2), d_solimp=np.array(d_solimp).reshape(-1, 5), d_margin=np.array(d_margin),

@@ -250,3 +250,126 @@ class LiftEnvOracle(PushEnvOracle):
     def null_step(self):
         self.contacts = []   # no mj_step ran: no fresh contact list (the device path does the same)
         return super().null_step()
+
+
+def pusher_reset_state(model, seed, env_id, episode):
+    """PusherObstacleEnv._reset (env/pusher/pusher_obstacle.py:40-67) with counter-based draws keyed by (seed, env id,
+    episode, attempt): goal / box ~ U([-0.35, 0.13], [-0.24, 0.2]), qpos0 + U(+-0.02), qvel ~ U(+-0.005) with the goal /
+    box velocities zero.  The acceptance test (no contact, box farther than 0.1 from the target, goal[0] <= box[0]) needs
+    the collision oracle and is applied by the caller (PusherEnvOracle.reset)."""
+    from mopa_rl_b200 import rng
+
+    def draw(attempt):
+        s = np.uint64(env_id) * np.uint64(1000003) + np.uint64(attempt)
+        u = rng.uniform01(seed, s, np.uint64(episode), np.arange(4 + model.nq + model.nv, dtype=np.uint64))
+        lo, hi = np.array([-0.35, 0.13]), np.array([-0.24, 0.2])
+        goal, box = lo + (hi - lo) * u[0:2], lo + (hi - lo) * u[2:4]
+        qpos = model.qpos0 + (-0.02 + 0.04 * u[4:4 + model.nq])
+        qpos[-4:-2], qpos[-2:] = goal, box
+        qvel = -0.005 + 0.01 * u[4 + model.nq:]
+        qvel[-4:] = 0.0
+        return qpos, qvel, goal, box
+
+    return draw
+
+
+class PusherEnvOracle:
+    """PusherObstacle-v0 (BASELINE configs[0], the reference's CPU-runnable case): 4 hinge joints driven through velocity
+    actuators (gear 10) by the PID law of BaseEnv._get_control (env/base.py:200-209: kp 150, kd 20, ki 0.1, leak 0.95),
+    RK4 with dt = 0.01, int(frame_dt / dt) = 100 mj_steps per env.step (env/pusher/pusher_obstacle.py:240-284), reward
+    :223-238, observation :185-205, BaseEnv._after_step.  `desired_state = prev_state + action` - the clipped / scaled
+    variants computed before it are dead code in the reference and are not applied here either."""
+
+    def __init__(self, model, dynmodel, max_episode_steps=150, frame_dt=1.0, distance_threshold=0.05, success_reward=150.0,
+                 kp=150.0, kd=20.0, ki=0.1, contacts=True):
+        self.m, self.dm = model, dynmodel
+        self.dyn = OracleDyn(dynmodel)
+        self.dyn.enable_contacts(contacts)
+        m = model
+        self.ref_q = [m.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+        self.ref_v = [m.get_joint_qvel_addr("joint%d" % i) for i in range(4)]
+        sim = {b: i for i, b in enumerate(dynmodel.bodies) if b >= 0}
+        self.b_tip, self.b_box, self.b_target = (sim[m.body_name2id(n)] for n in ("fingertip", "box", "target"))
+        self.s_tip = m.site_pos[m.site_name2id("fingertip")]
+        self.nsub = int(frame_dt / m.opt_timestep)
+        self.kp, self.kd, self.ki = kp, kd, ki
+        self.dthr, self.succ_rew, self.max_steps, self.ac_scale = distance_threshold, success_reward, max_episode_steps, 0.1
+        self.lim = [(int(q), dynmodel._arr["d_range"][k]) for k, q in enumerate(dynmodel.dof_qadr) if q >= 0 and dynmodel._arr["d_limited"][k]]
+        self.zero_comp = np.zeros(dynmodel.nd, np.int32)
+
+    def set_state(self, qpos, qvel):
+        self.qpos, self.qvel = np.array(qpos, np.float64), np.array(qvel, np.float64)
+        _, self.xpos, self.xquat = self.dyn.forward(self.qpos, self.qvel)
+
+    def ncon_at(self, qpos):
+        """sim.data.ncon after set_state: contacts at this configuration (one zero-length look through the physics oracle)."""
+        q, v = np.array(qpos, np.float64), np.zeros(self.m.nv)
+        *_, ncon = self.dyn.step(q, v, np.zeros(4), self.zero_comp, np.zeros(self.dm.nd), 1)
+        return ncon
+
+    def reset(self, seed, env_id, episode):
+        draw = pusher_reset_state(self.m, seed, env_id, episode)
+        for attempt in range(1000):
+            qpos, qvel, goal, box = draw(attempt)
+            self.set_state(qpos, qvel)
+            d = np.linalg.norm(self.xpos[self.b_box] - self.xpos[self.b_target])
+            if self.ncon_at(qpos) == 0 and d > 0.1 and goal[0] <= box[0]:
+                break
+        else:
+            raise RuntimeError("no admissible reset state in 1000 draws")
+        return self.reset_to(qpos, qvel)
+
+    def reset_to(self, qpos, qvel):
+        self.set_state(qpos, qvel)
+        self.prev_state, self.i_term = None, np.zeros(4)
+        self.ep_len, self.ep_rew, self.terminal, self.success = 0, 0.0, False, False
+        return self.obs()
+
+    def obs(self):
+        th = self.qpos[self.ref_q]
+        tip = self.xpos[self.b_tip] + _q2m(self.xquat[self.b_tip]) @ self.s_tip
+        return np.concatenate([np.cos(th), np.sin(th), self.qpos[-2:], self.qvel[self.ref_v], self.qvel[-2:], tip[:2], self.qpos[-4:-2]])
+
+    def _reward(self):
+        tip = self.xpos[self.b_tip] + _q2m(self.xquat[self.b_tip]) @ self.s_tip
+        d_bg = np.linalg.norm(self.xpos[self.b_box] - tip)
+        d_bt = np.linalg.norm(self.xpos[self.b_box] - self.xpos[self.b_target])
+        reward = 0.0
+        if d_bg < 0.1:
+            reward += 0.1 * (1 - np.tanh(5 * d_bg))
+        if d_bt < 0.1:
+            reward += 0.3 * (1 - np.tanh(5 * d_bt))
+        terminal = False
+        if d_bt < self.dthr:
+            self.success, terminal = True, True
+            reward += self.succ_rew
+        return reward, terminal
+
+    def step(self, action, is_planner=False):
+        action = np.asarray(action, np.float64)
+        if not is_planner or self.prev_state is None:
+            self.prev_state = self.qpos[self.ref_q].copy()
+        desired = self.prev_state + action
+        bias = np.zeros(self.dm.nd)
+        for _ in range(self.nsub):   # the PID law is re-evaluated before every mj_step
+            p = self.kp * (desired - self.qpos[self.ref_q])
+            d = self.kd * (0.0 - self.qvel[self.ref_v])
+            self.i_term = 0.95 * self.i_term + self.ki * (self.prev_state - self.qpos[self.ref_q])
+            self.qpos, self.qvel, bias, self.xpos, self.xquat, self.ncon = self.dyn.step(
+                self.qpos, self.qvel, p + d + self.i_term, self.zero_comp, bias, 1)
+        self.prev_state = desired.copy()
+        reward, terminal = self._reward()
+        ob = self.obs()
+        clipped = False
+        for qa, (lo, hi) in self.lim:
+            if self.qpos[qa] < lo or self.qpos[qa] > hi:
+                self.qpos[qa] = min(max(self.qpos[qa], lo), hi)
+                clipped = True
+        if clipped:
+            self.set_state(self.qpos, self.qvel)
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return ob, reward, terminal

@@ -180,6 +180,8 @@ class OracleDyn:
             raise RuntimeError("scene too large for the dynamics oracle")
         self.nd, self.nb = dynmodel.nd, dynmodel.nb
         L.orc_dyn_set_max_rows(self.h, int(getattr(dynmodel, "max_rows", 36)))
+        L.orc_dyn_set_integrator.argtypes = [C.c_void_p, C.c_int]
+        L.orc_dyn_set_integrator(self.h, int(getattr(dynmodel.model, "opt_integrator", 0)))   # <option integrator="RK4"> (Pusher)
 
     def __del__(self):
         try:

@@ -134,6 +134,8 @@ static double g_last_cforce = 0; /* contact-force metric of the latest orc_dyn_s
 void orc_pgs_stats(long *out, int reset) { out[0] = g_pgs_calls; out[1] = g_pgs_sweeps; if (reset) g_pgs_calls = g_pgs_sweeps = 0; }
 void orc_dyn_enable_contacts(void *h, int on) { ((dyn_model *)h)->enable_contacts = on; }
 /* constraint-row capacity (the env kernel keeps 24 rows for small scenes, 32 for large ones; excess contacts are dropped in pair order) */
+/* 0 = semi-implicit Euler (Sawyer scenes), 1 = RK4 (Pusher: <option integrator="RK4">) */
+void orc_dyn_set_integrator(void *h, int rk4) { ((dyn_model *)h)->integrator = rk4 ? 1 : 0; }
 void orc_dyn_set_max_rows(void *h, int n) { ((dyn_model *)h)->max_rows = n < 3 ? 3 : (n > DMAXC ? DMAXC : n); }
 
 /* impedance / reference parameters of one constraint row (mj_makeImpedance semantics) */
@@ -179,7 +181,28 @@ static double orc_cone(double mu, double D, const double *x, double *grad, doubl
 
 /* one mj_step.  qpos[nq], qvel[nv] updated in place; ctrl[nact]; applied[nd] = qfrc_applied on the
    simulated dofs; data receives the kinematics / bias of this step. */
-static void substep(const dyn_model *m, double *qpos, double *qvel, const double *ctrl, const double *applied, dyn_data *D, warm_t *warm) {
+/* mj_integratePos for the simulated joints: hinge / slide linear, free joints by the exponential map of the angular velocity */
+static void integrate_pos(const dyn_model *m, double *qpos, const double *qd, double h) {
+    for (int i = 0; i < m->nb; i++) {
+        int jt = m->b_jtype[i], da = m->b_dadr[i], a = m->b_qadr[i];
+        if (jt == 2 || jt == 3) qpos[a] += h * qd[da];
+        else if (jt == 0) {
+            for (int k = 0; k < 3; k++) qpos[a + k] += h * qd[da + k];
+            double w[3] = {qd[da + 3], qd[da + 4], qd[da + 5]}, n = sqrt(dot(w, w)), ang = n * h;
+            if (ang > 0) {
+                double sn = sin(0.5 * ang) / n, dq[4] = {cos(0.5 * ang), w[0] * sn, w[1] * sn, w[2] * sn}, qn[4];
+                qmul(qn, qpos + a + 3, dq);
+                double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+                for (int k = 0; k < 4; k++) qpos[a + 3 + k] = qn[k] / nn;
+            }
+        }
+    }
+}
+
+/* acc_out != NULL: forward dynamics only - write qacc = M^-1 (tau + J^T f) of the simulated dofs and leave the state alone
+   (one stage of the Runge-Kutta integrator); NULL: one semi-implicit Euler mj_step. */
+static void substep(const dyn_model *m, double *qpos, double *qvel, const double *ctrl, const double *applied, dyn_data *D, warm_t *warm,
+                    double *acc_out) {
     const int nb = m->nb, nd = m->nd;
     sv6 S[DMAXD], vel[DMAXB], acc[DMAXB], frc[DMAXB];
     sinert I[DMAXB], Ic[DMAXB];
@@ -480,6 +503,12 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
     }
     else if (warm) warm->have_a = 0;
     free(rows);
+    if (acc_out) { /* explicit stage: qacc = M^-1 (tau + J^T f), damping is part of tau */
+        for (int k = 0; k < nd; k++) acc_out[k] = tau[k] + fc[k];
+        CHOL_SOLVE(L, acc_out);
+        memcpy(D->bias, bias, sizeof(double) * nd);
+        return;
+    }
     /* ---- semi-implicit Euler with implicit joint damping: (M + h D) qacc = tau + J^T f */
     double Lh[DMAXD][DMAXD], rhs[DMAXD];
     memset(Lh, 0, sizeof(Lh));
@@ -492,21 +521,40 @@ static void substep(const dyn_model *m, double *qpos, double *qvel, const double
     for (int k = 0; k < nd; k++) rhs[k] = tau[k] + fc[k];
     CHOL_SOLVE(Lh, rhs);
     for (int k = 0; k < nd; k++) { qd[k] += m->h * rhs[k]; qvel[m->d_vadr[k]] = qd[k]; }
-    for (int i = 0; i < nb; i++) {
-        int jt = m->b_jtype[i], da = m->b_dadr[i], a = m->b_qadr[i];
-        if (jt == 2 || jt == 3) qpos[a] += m->h * qd[da];
-        else if (jt == 0) {
-            for (int k = 0; k < 3; k++) qpos[a + k] += m->h * qd[da + k];
-            double w[3] = {qd[da + 3], qd[da + 4], qd[da + 5]}, n = sqrt(dot(w, w)), ang = n * m->h;
-            if (ang > 0) {
-                double sn = sin(0.5 * ang) / n, dq[4] = {cos(0.5 * ang), w[0] * sn, w[1] * sn, w[2] * sn}, qn[4];
-                qmul(qn, qpos + a + 3, dq);
-                double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-                for (int k = 0; k < 4; k++) qpos[a + 3 + k] = qn[k] / nn;
-            }
-        }
-    }
+    integrate_pos(m, qpos, qd, m->h);
     memcpy(D->bias, bias, sizeof(double) * nd);
+}
+
+/* One mj_step with the 4th-order Runge-Kutta integrator (mj_RungeKutta, N = 4: A = [[1/2], [0, 1/2], [0, 0, 1]],
+   B = [1/6, 1/3, 1/3, 1/6]); every stage runs the full forward dynamics incl. collision and the constraint solver. */
+static void rk4_step(const dyn_model *m, double *qpos, double *qvel, const double *ctrl, const double *applied, dyn_data *D, warm_t *warm) {
+    static const double A[3][3] = {{0.5, 0, 0}, {0, 0.5, 0}, {0, 0, 1.0}}, B[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    const int nd = m->nd;
+    double q0[64], v0[64], Fv[4][DMAXD], Fa[4][DMAXD], dv[DMAXD], da[DMAXD];
+    memcpy(q0, qpos, sizeof(double) * m->nq);
+    memcpy(v0, qvel, sizeof(double) * m->nv);
+    for (int i = 0; i < 4; i++) {
+        if (i > 0) { /* X[i] = X[0] + h * sum_j A[i-1][j] F[j] */
+            for (int k = 0; k < nd; k++) {
+                dv[k] = da[k] = 0;
+                for (int j = 0; j < i; j++) { dv[k] += A[i - 1][j] * Fv[j][k]; da[k] += A[i - 1][j] * Fa[j][k]; }
+            }
+            memcpy(qpos, q0, sizeof(double) * m->nq);
+            memcpy(qvel, v0, sizeof(double) * m->nv);
+            integrate_pos(m, qpos, dv, m->h);
+            for (int k = 0; k < nd; k++) qvel[m->d_vadr[k]] = v0[m->d_vadr[k]] + m->h * da[k];
+        }
+        for (int k = 0; k < nd; k++) Fv[i][k] = qvel[m->d_vadr[k]];
+        substep(m, qpos, qvel, ctrl, applied, D, warm, Fa[i]);   /* mjData keeps the frames / contacts of the LAST stage */
+    }
+    for (int k = 0; k < nd; k++) {
+        dv[k] = da[k] = 0;
+        for (int j = 0; j < 4; j++) { dv[k] += B[j] * Fv[j][k]; da[k] += B[j] * Fa[j][k]; }
+    }
+    memcpy(qpos, q0, sizeof(double) * m->nq);
+    memcpy(qvel, v0, sizeof(double) * m->nv);
+    integrate_pos(m, qpos, dv, m->h);
+    for (int k = 0; k < nd; k++) qvel[m->d_vadr[k]] = v0[m->d_vadr[k]] + m->h * da[k];
 }
 
 /* n mj_step calls with constant ctrl.  comp[nd]: 1 where qfrc_applied tracks the previous step's
@@ -523,7 +571,8 @@ int orc_dyn_step(void *h, double *qpos, double *qvel, const double *ctrl, const 
     warm.have_a = 0; /* the warm start lives for the substeps of one call (one env.step) */
     for (int s = 0; s < nsub; s++) {
         for (int k = 0; k < m->nd; k++) applied[k] = comp[k] ? bias_prev[k] : 0.0;
-        substep(m, qpos, qvel, ctrl, applied, &D, &warm);
+        if (m->integrator == 1) rk4_step(m, qpos, qvel, ctrl, applied, &D, &warm);
+        else substep(m, qpos, qvel, ctrl, applied, &D, &warm, NULL);
         memcpy(bias_prev, D.bias, sizeof(double) * m->nd);
     }
     if (xpos) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 3; k++) xpos[3 * i + k] = D.xpos[i][k];
@@ -551,7 +600,7 @@ int orc_dyn_forward(void *h, const double *qpos, const double *qvel, double *bia
     memcpy(q, qpos, sizeof(double) * m->nq); memcpy(v, qvel, sizeof(double) * m->nv);
     int ec = m->enable_contacts;
     m->enable_contacts = 0;
-    substep(m, q, v, ctrl, zero, &D, NULL);
+    substep(m, q, v, ctrl, zero, &D, NULL, NULL);
     m->enable_contacts = ec;
     if (bias) memcpy(bias, D.bias, sizeof(double) * m->nd);
     if (xpos) for (int i = 0; i < m->nb; i++) for (int k = 0; k < 3; k++) xpos[3 * i + k] = D.xpos[i][k];
@@ -567,7 +616,7 @@ int orc_dyn_mass_bias(void *h, const double *qpos, const double *qvel, double *M
     memcpy(q, qpos, sizeof(double) * m->nq); memcpy(v, qvel, sizeof(double) * m->nv);
     int ec = m->enable_contacts;
     m->enable_contacts = 0;
-    substep(m, q, v, ctrl, zero, D, NULL);
+    substep(m, q, v, ctrl, zero, D, NULL, NULL);
     m->enable_contacts = ec;
     memcpy(M, D->M, sizeof(double) * m->nd * m->nd);
     memcpy(bias, D->bias, sizeof(double) * m->nd);

@@ -23,7 +23,7 @@ typedef struct {
     double d_armature[DMAXD], d_damping[DMAXD], d_range[DMAXD][2], d_solref[DMAXD][2], d_solimp[DMAXD][5], d_margin[DMAXD];
     int a_dof[DMAXA], a_kind[DMAXA], a_ctrllimited[DMAXA], a_forcelimited[DMAXA];
     double a_kp[DMAXA], a_kv[DMAXA], a_gear[DMAXA], a_ctrlrange[DMAXA][2], a_forcerange[DMAXA][2];
-    int enable_contacts, max_rows;
+    int enable_contacts, max_rows, integrator; /* integrator: 0 semi-implicit Euler, 1 RK4 (oracle-side switch, orc_dyn_set_integrator) */
     /* contact geoms (orc_contact.c) */
     int g_body[DMAXG], g_type[DMAXG], g_condim[DMAXG];
     double g_pos[DMAXG][3], g_quat[DMAXG][4], g_size[DMAXG][3], g_rbound[DMAXG], g_margin[DMAXG], g_friction[DMAXG][3],

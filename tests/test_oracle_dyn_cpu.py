@@ -186,3 +186,79 @@ def test_env_logic(dyn, push_model):
     env2.reset_to(q, v0[0])
     _, r, done = env2.step(np.zeros(7))
     assert done and env2.success and r > 150
+
+
+# ---------------------------------------------------------------------------- Pusher (BASELINE configs[0]): RK4, velocity actuators
+@pytest.fixture(scope="module")
+def pusher(oracle_built):
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.model import load_model
+
+    m = load_model("PusherObstacle-v0")
+    return m, DynModel(m)
+
+
+def test_pusher_dynmodel_splits_multi_joint_bodies(pusher):
+    """The box and the target carry two slide joints each: one simulated body per joint, massless virtual bodies first."""
+    m, dm = pusher
+    assert dm.nb == 9 and dm.nd == 8 and dm.nact == 4 and m.opt_integrator == 1
+    A = dm._arr
+    virt = [i for i, b in enumerate(dm.bodies) if b < 0]
+    assert len(virt) == 2 and all(A["b_mass"][i] == 0 and A["b_jtype"][i] == 2 for i in virt)
+    for i in virt:                                   # the real body hangs off its virtual parent with an identity offset
+        assert A["b_parent"][i + 1] == i and np.all(A["b_pos"][i + 1] == 0) and dm.bodies[i + 1] == -1 - dm.bodies[i]
+    from oracle.oracle import OracleDyn
+
+    M, bias, _ = OracleDyn(dm).mass_bias(m.qpos0, np.zeros(m.nv))
+    box_mass = 1000.0 * 0.02 ** 3                    # inertiafromgeom="true": the <inertial> element of the box is overridden
+    assert np.allclose(np.diag(M)[-2:], box_mass) and np.all(np.abs(bias) < 1e-12)   # planar arm, gravity along the hinge axes
+    assert np.all(np.diag(M)[:4] > 1.0)              # armature 1 + link inertias
+
+
+def test_pusher_rk4_step_is_the_rk4_polynomial_of_the_linearised_system(pusher):
+    """Known answer for mj_RungeKutta (N = 4): with tiny velocities the arm is the linear system M qdd = -(d + kv gear^2) qd
+    (joint damping 1, velocity actuators kv 1 x gear 10 with ctrl 0), for which one RK4 step multiplies qd by
+    I + Z + Z^2/2 + Z^3/6 + Z^4/24, Z = h M^-1 (-(d + kv gear^2))."""
+    from oracle.oracle import OracleDyn
+
+    m, dm = pusher
+    o = OracleDyn(dm)
+    q, v = m.qpos0.copy(), np.zeros(m.nv)
+    v[:4] = [1e-6, -2e-6, 3e-6, -1e-6]
+    M, _, _ = o.mass_bias(q, v)
+    Z = -np.linalg.solve(M[:4, :4], np.eye(4) * (1.0 + 1.0 * 10.0 ** 2)) * m.opt_timestep
+    P = np.eye(4) + Z + Z @ Z / 2 + Z @ Z @ Z / 6 + Z @ Z @ Z @ Z / 24
+    v1 = o.step(q, v, np.zeros(4), np.zeros(dm.nd, np.int32), np.zeros(dm.nd), 1)[1]
+    assert np.abs(v1[:4] - P @ v[:4]).max() < 1e-15 * 1e3 * np.abs(v[:4]).max() + 1e-20
+    assert np.all(v1[4:] == 0)
+
+
+def test_pusher_env_oracle_tracks_pushes_and_matches_golden(pusher):
+    import os
+
+    from oracle.env_oracle import PusherEnvOracle
+
+    m, dm = pusher
+    env = PusherEnvOracle(m, dm)
+    # reset: the acceptance test of PusherObstacleEnv._reset holds for the accepted draw
+    ob = env.reset(7, 0, 0)
+    assert ob.shape == (20,) and env.ncon_at(env.qpos) == 0
+    goal, box = env.qpos[-4:-2], env.qpos[-2:]
+    assert goal[0] <= box[0] and np.linalg.norm(env.xpos[env.b_box] - env.xpos[env.b_target]) > 0.1
+    assert np.allclose(ob[:4] ** 2 + ob[4:8] ** 2, 1.0) and np.allclose(ob[18:20], goal)
+    # free motion: the PID + velocity-actuator loop tracks prev_state + action within a few hundredths of a radian per 1 s step
+    a = np.array([0.05, -0.08, 0.1, -0.03])
+    start = env.qpos[env.ref_q].copy()
+    env.step(a)
+    assert env.ncon == 0 and np.abs(env.qpos[env.ref_q] - (start + a)).max() < 0.03 and np.allclose(env.qpos[-2:], box)
+    # pushing: the stretched arm sweeps into the box, the box moves, reward_reach is paid (fingertip within 0.1 of the box)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pusher_env_steps.npz"))
+    env.reset_to(g["qpos0"], np.zeros(m.nv))
+    moved = False
+    for s in range(len(g["actions"])):
+        ob, r, d = env.step(g["actions"][s])
+        assert np.abs(env.qpos - g["qpos"][s]).max() < 1e-9 and np.abs(env.qvel - g["qvel"][s]).max() < 1e-8
+        assert np.abs(ob - g["obs"][s]).max() < 1e-9 and abs(r - g["reward"][s]) < 1e-12 and env.ncon == g["ncon"][s]
+        moved = moved or np.abs(env.qpos[-2:] - g["qpos0"][-2:]).max() > 0.01
+        assert 0.0 < r < 0.1 and not d
+    assert moved and g["ncon"].max() >= 1

@@ -261,4 +261,22 @@ for _ in range(8):
     recs_l.extend(run_l.extra_records)
 np.savez_compressed(os.path.join(out, "rollout_discrete_lift.npz"), discrete=np.array(recs_d, np.float32), lift=np.array(recs_l, np.float32))
 print("rollout goldens: discrete %d records, lift %d records" % (len(recs_d), len(recs_l)))
+
+# 11. Pusher env (RK4 + PID + velocity actuators): the stretched arm sweeps into the box
+from oracle.env_oracle import PusherEnvOracle  # noqa: E402
+
+dmp = DynModel(mp)
+envp = PusherEnvOracle(mp, dmp)
+qp0 = mp.qpos0.copy()
+qp0[-2:], qp0[-4:-2] = [0.36, 0.06], [-0.3, 0.15]
+envp.reset_to(qp0, np.zeros(mp.nv))
+acts_p = np.tile(np.array([0.1, 0.0, 0.0, 0.0]), (4, 1))
+acts_p[2:, 1] = -0.05
+Qp, Vp, Rp, Op, Np = [], [], [], [], []
+for s in range(4):
+    ob, r, _ = envp.step(acts_p[s])
+    Qp.append(envp.qpos.copy()), Vp.append(envp.qvel.copy()), Rp.append(r), Op.append(ob), Np.append(envp.ncon)
+np.savez_compressed(os.path.join(out, "pusher_env_steps.npz"), qpos0=qp0, actions=acts_p, qpos=np.array(Qp), qvel=np.array(Vp),
+                    reward=np.array(Rp), obs=np.array(Op), ncon=np.array(Np))
+print("pusher env golden: box", Qp[-1][-2:], "ncon", Np, "rewards", np.round(Rp, 4))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
