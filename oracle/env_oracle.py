@@ -373,3 +373,14 @@ class PusherEnvOracle:
             terminal = True
         self.terminal = terminal
         return ob, reward, terminal
+
+    def null_step(self):
+        """Planner failure (rl/mopa_rollouts.py:304-327): compute_reward + _after_step, no simulation; frames refreshed first."""
+        self.set_state(self.qpos, self.qvel)
+        reward, terminal = self._reward()
+        self.ep_rew += reward
+        self.ep_len += 1
+        if self.ep_len == self.max_steps:
+            terminal = True
+        self.terminal = terminal
+        return reward, terminal

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .env_oracle import AssemblyEnvOracle, LiftEnvOracle, PushEnvOracle
+from .env_oracle import AssemblyEnvOracle, LiftEnvOracle, PusherEnvOracle, PushEnvOracle
 from .oracle import OraclePlanner, OracleScene, space_from_model
 
 
@@ -24,14 +24,22 @@ class ScalarMoPARunner:
         """policy(env_gid, macro_index) -> action (7,) in [-1, 1]."""
         self.m, self.cfg, self.gid, self.policy = model, cfg, int(env_gid), policy
         self.task = task
-        env_cls = {"assembly": AssemblyEnvOracle, "lift": LiftEnvOracle}.get(task, PushEnvOracle)
-        self.env = env_cls(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
+        env_cls = {"assembly": AssemblyEnvOracle, "lift": LiftEnvOracle, "pusher": PusherEnvOracle}.get(task, PushEnvOracle)
+        if task == "pusher":   # BASELINE configs[0]: 4 hinges (joint0 unlimited -> SO(2)), env._ac_scale = 0.1 (pusher_obstacle.py:33)
+            self.env = env_cls(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts)
+        else:
+            self.env = env_cls(model, dynmodel, max_episode_steps=max_episode_steps, contacts=contacts, ac_scale=cfg.ac_scale)
         self.scene = OracleScene(model, ignored, cfg.contact_threshold, "f32")
         adr, lo, hi, so2 = space_from_model(model, passive)
         self.planner = OraclePlanner(self.scene, adr, lo, hi, so2, cfg.range, 0.005, cfg.seed, max_nodes=4096)
         self.ref = adr
+        self.na = len(adr)                                          # arm joints (7 Sawyer, 4 Pusher), qpos addresses 0 .. na-1
+        assert list(adr) == list(range(self.na))
         jid = [list(model.jnt_qposadr).index(a) for a in adr]
-        self.jlo, self.jhi = model.jnt_range[jid, 0], model.jnt_range[jid, 1]
+        self.limited = np.asarray(model.jnt_limited)[jid].astype(bool)
+        # unlimited joints (Pusher joint0): never clipped (rl/mopa_rollouts.py:121-131, sac_agent.clip_qpos), wrapped for the planner
+        self.jlo = np.where(self.limited, model.jnt_range[jid, 0], -np.inf)
+        self.jhi = np.where(self.limited, model.jnt_range[jid, 1], np.inf)
         self.seed_env = seed_env
         self.episode = 0
         self.plan_count = 0
@@ -45,6 +53,9 @@ class ScalarMoPARunner:
         from mopa_rl_b200.envs import assembly_reset_state, lift_reset_state, push_reset_state  # reset draws are input data shared with the product
 
         fn = {"assembly": assembly_reset_state, "lift": lift_reset_state}.get(self.task, push_reset_state)
+        if self.task == "pusher":
+            self.episode += 1
+            return self.env.reset(self.seed_env, self.gid, self.episode - 1)
         q, v = fn(self.m, self.seed_env, [self.gid], [self.episode])
         self.episode += 1
         return self.env.reset_to(q[0], v[0])
@@ -52,23 +63,34 @@ class ScalarMoPARunner:
     def _valid(self, q):
         return bool(self.scene.is_valid(np.asarray(q, np.float64).astype(np.float32).astype(np.float64))[0] & 1)
 
+    def _wrap(self, q):
+        """util/env.py:15-25 joint_convert on the unlimited joints (period 3.14, sign preserving); identity for the Sawyer scenes."""
+        q = np.array(q, np.float64)
+        for k in np.nonzero(~self.limited)[0]:
+            period = 3.14 if q[k] > 0 else -3.14
+            w = q[k] % period
+            if (q[k] // period) % 2 != 0:
+                w -= period
+            q[k] = w
+        return q
+
     def _clip_qpos(self, q):
-        arm = q[:7]
+        arm = q[:self.na]
         if np.any(arm < self.jlo) or np.any(arm > self.jhi):
             q = q.copy()
-            q[:7] = np.clip(arm, self.jlo + self.cfg.joint_margin, self.jhi - self.cfg.joint_margin)
+            q[:self.na] = np.clip(arm, self.jlo + self.cfg.joint_margin, self.jhi - self.cfg.joint_margin)
         return q
 
     def _simple_interpolate(self, curr, target):
         """rl/sac_agent.py:262-318 with use_planner=False.  Returns (traj, valid)."""
         lim = self.cfg.ac_scale * 0.8
         curr = self._clip_qpos(curr)
-        diff = target[:7] - curr[:7]
+        diff = target[:self.na] - curr[:self.na]
         sf = max(np.max(np.abs(diff) / lim), 1.0)
         scaled = diff / sf
         traj, interp = [], curr.copy()
         for _ in range(int(sf)):
-            interp[:7] += scaled
+            interp[:self.na] += scaled
             if not self._valid(interp):
                 return traj, False
             traj.append(interp.copy())
@@ -84,21 +106,34 @@ class ScalarMoPARunner:
             return traj, True, True, True
         key = (self.gid << 32) + self.plan_count
         self.plan_count += 1
-        r = self.planner.plan(curr.astype(np.float32).astype(np.float64), target.astype(np.float32).astype(np.float64), key, cfg.max_iter, cfg.max_path)
+        ws, wg = self._wrap(curr), self._wrap(target)               # SamplingBasedPlanner.plan: convert_nonlimited on copies (:63-66)
+        r = self.planner.plan(ws.astype(np.float32).astype(np.float64), wg.astype(np.float32).astype(np.float64), key, cfg.max_iter, cfg.max_path)
         if r["status"] != 0:
             return None, False, False, r["status"] != -4
         states = r["path"]
-        path = [curr + (s - states[0]) for s in states][1:]       # re-based on start, first row dropped
+        if self.limited.all():
+            path = [curr + (s - states[0]) for s in states][1:]   # re-based on start, first row dropped
+        else:   # :81-101: accumulate waypoint deltas on the un-wrapped start, going the short way round across +-3.14
+            path, prev_s, acc = [], states[0], curr.copy()
+            for st in states[1:]:
+                delta = st - prev_s
+                for k in np.nonzero(~self.limited)[0]:
+                    if abs(st[k] - prev_s[k]) > 3.14:
+                        delta[k] = (3.14 - prev_s[k] + st[k] + 3.14) if prev_s[k] > 0 and st[k] <= 0 else (
+                            -(3.14 - st[k] + prev_s[k] + 3.14) if prev_s[k] < 0 and st[k] > 0 else delta[k])
+                acc = acc + delta
+                path.append(acc.copy())
+                prev_s = st
         if cfg.interpolation:
             new, start = [], curr
             for p in path:
-                d = p[:7] - start[:7]
+                d = p[:self.na] - start[:self.na]
                 if np.any(np.abs(d) > cfg.ac_scale):
                     lim = cfg.ac_scale * 0.8
                     sf = max(np.max(np.abs(d) / lim), 1.0)
                     inner, interp, good = [], start.copy(), True
                     for _ in range(min(int(sf), int(cfg.range / lim) + 1)):
-                        interp[:7] += d / sf
+                        interp[:self.na] += d / sf
                         if not self._valid(interp):
                             good = False
                             break
@@ -125,7 +160,7 @@ class ScalarMoPARunner:
         ac = np.asarray(ac, np.float64).astype(np.float32).astype(np.float64)
         lift = self.task == "lift"                                 # 8-D action: 7 joint entries + gripper
         grip_ac = float(ac[7]) if lift else None
-        ac = ac[:7]
+        ac = ac[:self.na]
         self.macro_index += 1
         curr = env.qpos.copy()
         is_mp = bool(ac_type) if discrete else bool(np.any(np.abs(ac) > cfg.omega))   # rl/mopa_rollouts.py:86-88, 104-111
@@ -141,7 +176,7 @@ class ScalarMoPARunner:
             if getattr(cfg, "ac_space_type", "piecewise") == "normal":   # rl/sac_agent.py:160-163
                 disp = ac * cfg.action_range
             target = curr.copy()
-            target[:7] = np.clip(curr[:7] + disp, self.jlo, self.jhi)
+            target[:self.na] = np.clip(curr[:self.na] + disp, self.jlo, self.jhi)
             if cfg.invalid_target_handling and not self._valid(target):
                 trial = 0
                 while not self._valid(target) and trial < cfg.num_trials:
@@ -159,7 +194,7 @@ class ScalarMoPARunner:
                 ob_list, rew_list, done_list = [], [], []
                 grip_q0 = env.qpos[env.grip_q[0]] if lift else 0.0
                 for i, nq in enumerate(traj):
-                    a = np.asarray(nq[:7] - env.qpos[:7], np.float32).astype(np.float64)   # form_action (fp32 action row)
+                    a = np.asarray(nq[:self.na] - env.qpos[:self.na], np.float32).astype(np.float64)   # form_action (fp32 action row)
                     if lift:   # form_action's gripper entry (waypoints carry the start state's passive dims), policy's on the last one
                         g = grip_ac if i == len(traj) - 1 else grip_q0 - env.qpos[env.grip_q[0]]
                         a = np.concatenate([a, [np.float64(np.float32(g))]])
@@ -193,7 +228,7 @@ class ScalarMoPARunner:
             self._reuse(*extra_src)
         rec = np.zeros(92, np.float32)
         no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
-        rec[0:no], rec[40:47], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
+        rec[0:no], rec[40:40 + self.na], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
         rec[47] = grip_ac if lift else self._ac_type
         return rec
 
@@ -213,7 +248,7 @@ class ScalarMoPARunner:
             if (start, goal) in pairs:
                 continue
             pairs.append((start, goal))
-            d = traj[goal][:7] - traj[start][:7]                                  # env.form_action(traj[goal], traj[start])
+            d = traj[goal][:self.na] - traj[start][:self.na]                                  # env.form_action(traj[goal], traj[start])
             s, w, ar = cfg.ac_scale, cfg.omega, cfg.action_range                  # SACAgent.invert_displacement, piecewise
             a = np.where(np.abs(d) < s, d * (w / s), np.sign(d) * ((np.abs(d) - s) / ((ar - s) / (1.0 - s)) / ((1.0 - s) / (1.0 - w)) + w))
             if getattr(cfg, "ac_space_type", "piecewise") == "normal":            # rl/sac_agent.py:180-181
@@ -222,7 +257,7 @@ class ScalarMoPARunner:
                 continue
             rec = np.zeros(92, np.float32)
             no = len(ob_list[start])
-            rec[0:no], rec[40:47] = ob_list[start], a
+            rec[0:no], rec[40:40 + self.na] = ob_list[start], a
             rec[47] = self._ac_type                                                # inter_subgoal_ac["ac_type"] = ac["ac_type"]
             rec[48] = (rew_list[goal] - rew_list[start]) * cfg.discount_factor ** (-(start + 1))
             rec[49], rec[50], rec[52:52 + no] = float(done_list[goal]), goal - start - 1, ob_list[goal]

@@ -217,3 +217,42 @@ def test_scalar_loop_discrete_and_lift_goldens(push_model, push_dyn, oracle_buil
     assert np.all(recs_l[:, 35:40] == 0) and np.all(recs_l[:, 87:92] == 0)      # 35-float observations in 40-float rows
     main = recs_l[recs_l[:, 47] != 0]
     assert len(main) == 8                                                      # main records carry the policy's gripper entry, relabelled ones 0
+
+
+def test_scalar_loop_on_the_pusher_golden(oracle_built):
+    """BASELINE configs[0] on the CPU restatement: PusherObstacle-v0 MoPA-SAC loop (scripts/2d/mopa.sh: omega 0.5,
+    action_range 1.0, reuse_data, max_reuse_data 30; config/pusher.py: range 0.2, contact_threshold -0.0015, step_size
+    0.04) over the RK4 / PID env oracle and the SO(2) planner oracle; 4-float actions, 20-float observations."""
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import MoPAConfig
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    g = np.load(os.path.join(GOLD, "pusher_rollout.npz"))["records"]
+    m = load_model("PusherObstacle-v0")
+    static = [m.geom_name2id("obstacle%d_geom" % i) for i in range(1, 8)]
+    box = m.geom_name2id("box")
+    ignored = [(min(box, s), max(box, s)) for s in static]
+    ref = [m.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+    passive = [i for i in range(m.nq) if i not in ref]
+    cfg = MoPAConfig(omega=0.5, action_range=1.0, ac_scale=0.1, step_size=0.04, joint_margin=0.0, contact_threshold=-0.0015, range=0.2,
+                     max_iter=1000, reuse_data=True, max_reuse_data=30, seed=5)
+
+    def policy(gid, k):
+        u = rng.uniform01(3, np.uint64(gid), np.uint64(k), np.arange(4, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    run = ScalarMoPARunner(m, DynModel(m), cfg, ignored, passive, 0, 11, policy, max_episode_steps=400, task="pusher")
+    recs = []
+    for _ in range(12):
+        recs.append(run.macro_step())
+        recs.extend(run.extra_records)
+    recs = np.array(recs, np.float32)
+    assert recs.shape == g.shape and np.abs(recs - g).max() < 1e-6
+    assert np.all(recs[:, 44:48] == 0) and np.all(recs[:, 20:40] == 0)         # 4-float actions, 20-float observations
+    assert np.allclose(recs[:, 0:4] ** 2 + recs[:, 4:8] ** 2, 1.0, atol=1e-6)   # cos / sin of the joint angles
+    assert run.counters["interpolation"] + run.counters["mp"] > 0 and run.counters["reused"] > 0
+    # the unlimited joint is wrapped for the planner only: joint_convert is the identity inside (-3.14, 3.14) and maps beyond
+    assert abs(run._wrap(np.array([3.5, 0, 0, 0] + [0.0] * 12))[0] - (3.5 - 3.14 - 3.14)) < 1e-12
+    assert run._wrap(np.array([1.0, 5.0, 0, 0] + [0.0] * 12))[1] == 5.0         # limited joints untouched

@@ -279,4 +279,23 @@ for s in range(4):
 np.savez_compressed(os.path.join(out, "pusher_env_steps.npz"), qpos0=qp0, actions=acts_p, qpos=np.array(Qp), qvel=np.array(Vp),
                     reward=np.array(Rp), obs=np.array(Op), ncon=np.array(Np))
 print("pusher env golden: box", Qp[-1][-2:], "ncon", Np, "rewards", np.round(Rp, 4))
+
+# 12. scalar MoPA loop on the Pusher (BASELINE configs[0], scripts/2d/mopa.sh: omega 0.5, action_range 1.0, reuse_data)
+ign_pp = [(min(box_p, g), max(box_p, g)) for g in static_p]
+cfg_p = MoPAConfig(omega=0.5, action_range=1.0, ac_scale=0.1, step_size=0.04, joint_margin=0.0, contact_threshold=-0.0015, range=0.2,
+                   max_iter=1000, reuse_data=True, max_reuse_data=30, seed=5)
+
+
+def _policy_p(g, k):
+    u = crng.uniform01(3, np.uint64(g), np.uint64(k), np.arange(4, dtype=np.uint64))
+    return (2.0 * u - 1.0).astype(np.float32)
+
+
+run_p = ScalarMoPARunner(mp, DynModel(mp), cfg_p, ign_pp, pas_p, 0, 11, _policy_p, max_episode_steps=400, task="pusher")
+recs_p = []
+for _ in range(12):
+    recs_p.append(run_p.macro_step())
+    recs_p.extend(run_p.extra_records)
+np.savez_compressed(os.path.join(out, "pusher_rollout.npz"), records=np.array(recs_p, np.float32))
+print("pusher rollout golden: %d records, counters %s" % (len(recs_p), run_p.counters))
 print("golden fixtures written to", out, [f for f in os.listdir(out)])
