@@ -462,7 +462,7 @@ def main():
                     help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3]), "
                          "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there)")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
-    ap.add_argument("--cpu-macros", type=int, default=24, help="macro actions per scalar runner in the cpu_baseline leg")
+    ap.add_argument("--cpu-macros", type=int, default=600, help="macro actions per scalar runner in the cpu_baseline leg (~10 s of CPU work on a 16-core host)")
     ap.add_argument("--ref-macros", type=int, default=16, help="macro actions per scalar runner per step of --impl reference")
     ap.add_argument("--queries", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
