@@ -47,6 +47,7 @@ def test_struct_layouts_match_the_headers(tmp_path):
     from mopa_rl_b200.dynmodel import DynDesc
     from mopa_rl_b200.envs import EnvBuffers, SawyerTask
     from mopa_rl_b200.model import ModelDesc
+    from mopa_rl_b200.rollout import _RolloutConfig
 
     prog = r'''
 #include <stdio.h>
@@ -55,15 +56,21 @@ def test_struct_layouts_match_the_headers(tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu\n", sizeof(mopa_model_desc), sizeof(mopa_dyn_desc), sizeof(mopa_sawyer_task), sizeof(mopa_env_buffers));
   printf("%zu %zu %zu %zu\n", offsetof(mopa_model_desc, site_quat), offsetof(mopa_dyn_desc, p_g2), offsetof(mopa_sawyer_task, success_reward), offsetof(mopa_env_buffers, ncon));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mopa_rollout_config), offsetof(mopa_rollout_config, qpos0), offsetof(mopa_rollout_config, seed_reuse),
+         offsetof(mopa_rollout_config, ac_space_normal), offsetof(mopa_sawyer_task, geom_cube), offsetof(mopa_sawyer_task, bin_z),
+         offsetof(mopa_model_desc, mesh_vert));
   return 0; }'''
     src = tmp_path / "layout.c"
     src.write_text(prog)
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     out = subprocess.check_output([str(exe)], text=True).split()
-    sizes, offs = list(map(int, out[:4])), list(map(int, out[4:]))
+    sizes, offs, more = list(map(int, out[:4])), list(map(int, out[4:8])), list(map(int, out[8:]))
     assert sizes == [C.sizeof(ModelDesc), C.sizeof(DynDesc), C.sizeof(SawyerTask), C.sizeof(EnvBuffers)]
     assert offs == [ModelDesc.site_quat.offset, DynDesc.p_g2.offset, SawyerTask.success_reward.offset, EnvBuffers.ncon.offset]
+    # the rollout configuration and the fields added for the lift task / mesh collider (a mismatch here would only show on a GPU)
+    assert more == [C.sizeof(_RolloutConfig), _RolloutConfig.qpos0.offset, _RolloutConfig.seed_reuse.offset, _RolloutConfig.ac_space_normal.offset,
+                    SawyerTask.geom_cube.offset, SawyerTask.bin_z.offset, ModelDesc.mesh_vert.offset]
 
 
 def test_product_never_imports_the_oracle():
