@@ -200,7 +200,7 @@ _OBS_KEYS = {
     "lift": (("joint_pos", 7), ("joint_vel", 7), ("gripper_qpos", 2), ("gripper_qvel", 2), ("eef_pos", 3), ("eef_quat", 4),
              ("cube_pos", 3), ("cube_quat", 4), ("gripper_to_cube", 3)),
     "assembly": (("joint_pos", 7), ("joint_vel", 7), ("gripper_qpos", 2), ("gripper_qvel", 2), ("eef_pos", 3), ("eef_quat", 4),
-                 ("hole", 3), ("head", 3), ("end", 3), ("peg_quat", 4)),
+                 ("hole", 3), ("pegHead", 3), ("pegEnd", 3), ("peg_quat", 4)),   # sawyer_assembly_obstacle.py:52-58
 }
 
 

@@ -79,6 +79,11 @@ def test_env_view_spaces_and_tables(cls_name, scene, dof, obs_dim):
     assert sum(s.shape[0] for s in env.observation_space.spaces.values()) == obs_dim
     ob = env.reset()
     assert isinstance(ob, OrderedDict) and np.array_equal(np.concatenate(list(ob.values())), np.arange(obs_dim))
+    # observation keys in the reference's order (env/sawyer/sawyer.py:317-338 + the task's _get_obs)
+    tail = {"SawyerPushObstacleEnv": ["target_pos", "cube_pos", "cube_quat", "gripper_to_cube", "cube_to_target"],
+            "SawyerLiftObstacleEnv": ["cube_pos", "cube_quat", "gripper_to_cube"],
+            "SawyerAssemblyObstacleEnv": ["hole", "pegHead", "pegEnd", "peg_quat"]}[cls_name]
+    assert list(ob.keys()) == ["joint_pos", "joint_vel", "gripper_qpos", "gripper_qvel", "eef_pos", "eef_quat"] + tail
     # env/base.py:67-99: one jnt_indices entry per qpos element, free joints count 7 times; unlimited joints +-3.14
     assert len(env.jnt_indices) == m.nq and env.sim.model.nq == m.nq
     lim = np.asarray(m.jnt_limited).astype(bool)
