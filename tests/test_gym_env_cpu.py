@@ -156,3 +156,28 @@ def test_site_kinematics_match_oracle_fk(push_model, oracle_built):
             sid = push_model.site_name2id(name)
             assert np.abs(env.sim.data.get_site_xpos(name) - fk["site_xpos"][sid]).max() < 1e-12
             assert np.abs(env.sim.data.get_site_xmat(name).ravel() - fk["site_xmat"][sid]).max() < 1e-12
+
+
+@pytest.mark.parametrize("scene", ["SawyerLiftObstacle-v0", "SawyerAssemblyObstacle-v0", "PusherObstacle-v0"])
+def test_host_kinematics_match_oracle_fk_on_every_scene(scene, oracle_built):
+    """gym_env.body_frames (hinge / slide / free joints, bodies with several joints: the Pusher's box and target) against
+    the oracle's mj_kinematics restatement: body and site frames of random states."""
+    from mopa_rl_b200 import gym_env as G
+    from mopa_rl_b200.mjcf import quat_to_mat
+    from mopa_rl_b200.model import load_model
+
+    m = load_model(scene)
+    scn = oracle_built.OracleScene(m, [], 0.0, "f64")
+    rng = np.random.default_rng(8)
+    for _ in range(4):
+        q = m.qpos0 + rng.uniform(-0.3, 0.3, m.nq)
+        for j in range(m.njnt):                      # free joints: a proper pose
+            if m.jnt_type[j] == 0:
+                a = int(m.jnt_qposadr[j])
+                quat = rng.normal(size=4)
+                q[a + 3:a + 7] = quat / np.linalg.norm(quat)
+        pos, quat = G.body_frames(m, q)
+        fk = scn.fk(q)
+        assert np.abs(pos - fk["body_xpos"]).max() < 1e-12
+        R = np.stack([quat_to_mat(x).ravel() for x in quat])
+        assert np.abs(R - fk["body_xmat"]).max() < 1e-12
