@@ -33,10 +33,20 @@ METRIC_ASSEMBLY = "env-steps/sec (incl. planner) SawyerAssemblyObstacle-v0"
 TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0"}
 
 
+# scripts/3d/{push,assembly,lift}/mopa.sh: omega per task (action_range 0.5, reuse_data, max_reuse_data 15 in all three)
+TASK_OMEGA = {"push": 0.7, "assembly": 0.7, "lift": 0.5}
+
+
+def task_config(task, max_iter):
+    from mopa_rl_b200.rollout import MoPAConfig
+
+    return MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15, omega=TASK_OMEGA[task])
+
+
 def task_metric(task):
     return METRIC.replace("SawyerPushObstacle-v0", TASK_ENV[task])
 WORKLOADS = {
-    "rollout": "SawyerPushObstacle-v0 MoPA (omega 0.7, action_range 0.5, RRT-Connect range 0.1), %d vectorised envs per GPU, uniform random-exploration policy",
+    "rollout": "SawyerPushObstacle-v0 MoPA (omega OMEGA, action_range 0.5, RRT-Connect range 0.1), %d vectorised envs per GPU, uniform random-exploration policy",
     "validity": "config5 collision-check microbench: SawyerPushObstacle-v0, %d random 7-DoF qpos state-validity queries per GPU, contact_threshold -0.002, cube x {table,bin1} ignored",
 }
 
@@ -149,7 +159,7 @@ def _cpu_rollout_worker(args):
         u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(adim, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15), ignored, passive, gid, seed, policy, task=task)
+    r = ScalarMoPARunner(model, DynModel(model), task_config(task, max_iter), ignored, passive, gid, seed, policy, task=task)
     t0 = time.perf_counter()
     for _ in range(macros):
         r.macro_step()
@@ -208,14 +218,13 @@ def run_reference_arm(args):
     else:
         rates = []
         for step in range(args.warmup + args.steps):
-            rate, steps, busy, wall = cpu_rollout_rate(cores, args.ref_macros, 1234, args.max_iter, base_gid=1000 * step, task=args.task)
+            rate, steps, busy, wall = cpu_rollout_rate(cores, args.cpu_macros, 1234, args.max_iter, base_gid=1000 * step, task=args.task)
             if step >= args.warmup:
                 rates.append((rate, busy))
         value, ms = float(np.mean([r for r, _ in rates])), float(np.mean([d for _, d in rates]) * 1e3)
         metric, unit = task_metric(args.task), "env-steps/s"
-        sample = "%d macro actions per scalar runner per step, one runner (env + planner) per host core" % args.ref_macros
-        wl = WORKLOADS["rollout"] % args.envs
-        cfg = {"workload": wl.replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "max_iter": args.max_iter}
+        sample = "%d macro actions per scalar runner per step, one runner (env + planner) per host core" % args.cpu_macros
+        cfg = rollout_config(args, args.envs)
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -250,7 +259,7 @@ def run_rollout(args):
 
     from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerLiftObstacle, VecSawyerPushObstacle
     from mopa_rl_b200.replay import ReplicatedReplay
-    from mopa_rl_b200.rollout import MoPAConfig, NativeMoPARolloutRunner
+    from mopa_rl_b200.rollout import NativeMoPARolloutRunner
 
     env_cls = {"assembly": VecSawyerAssemblyObstacle, "lift": VecSawyerLiftObstacle}.get(args.task, VecSawyerPushObstacle)
 
@@ -260,7 +269,8 @@ def run_rollout(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
-    cfg = MoPAConfig(max_iter=args.max_iter, reuse_data=True, max_reuse_data=15)   # scripts/3d/push/mopa.sh
+    cfg = task_config(args.task, args.max_iter)   # scripts/3d/<task>/mopa.sh
+    slab = args.slab or n
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,13 +282,13 @@ def run_rollout(args):
         venv = env_cls(n, seed=1234, device=local_rank, env_id_offset=rank * n)
         return NativeMoPARolloutRunner(venv, cfg, policy=policy)
 
-    def timed(runner, replay, h_trans=None, h_flags=None):
-        """W warm-up ticks, then K timed ticks.  Returns (device ms, wall ms, env_steps, launches, env-kernel ms, d2h bytes)."""
+    def timed(runner, replay, h_block=None):
+        """`settle` untimed ticks (start-up transient: every env plans at tick 0), W warm-up ticks, then K timed ticks.
+        Returns (device ms, wall ms, env_steps, launches, env-kernel ms, d2h bytes)."""
         d2h = 0
-        for _ in range(args.warmup):
+        for _ in range(args.settle + args.warmup):
             runner.tick()
-            replay.exchange_slab(*runner.last_emitted)
-            replay.exchange_slab(*runner.last_reused)
+            replay.exchange(runner)
         barrier()
         l0, s0 = runner.launches, runner.env_steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -286,41 +296,36 @@ def run_rollout(args):
         e0.record()
         for _ in range(args.steps):
             runner.tick()
-            replay.exchange_slab(*runner.last_emitted)
-            replay.exchange_slab(*runner.last_reused)
-            if h_trans is not None:   # end-to-end arm: this tick's transition records (main + relabelled) back to pinned host memory
-                h_trans[:n].copy_(runner.slab, non_blocking=True)
-                h_trans[n:].copy_(runner.reuse_slab, non_blocking=True)
-                h_flags[:n].copy_(runner.emit_flag, non_blocking=True)
-                h_flags[n:].copy_(runner.last_reused[1], non_blocking=False)
-                d2h += (n + runner.reuse_capacity) * (92 * 4 + 1)
+            replay.exchange(runner)
+            if h_block is not None:   # end-to-end arm: this tick's transition records (header row + records) back to pinned host memory
+                h_block.copy_(replay.last_block, non_blocking=True)
+                d2h += h_block.numel() * 4
+        replay.sync()
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         dev_ms = e0.elapsed_time(e1)
         k_ms = runner.env_kernel_ms(args.steps)
-        return max(dev_ms, 0.0), wall_ms, runner.env_steps - s0, runner.launches - l0, k_ms, d2h
+        return max(dev_ms, 0.0), wall_ms, runner.env_steps - s0, runner.launches - l0 + 2 * args.steps, k_ms, d2h
 
     # device-resident arm
     runner = make()
-    replay = ReplicatedReplay(torch, dev, capacity=1 << 20)
+    replay = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=slab)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     dev_ms, wall_ms, steps, launches, k_ms, _ = timed(runner, replay)
     clocks = sampler.stop() if rank == 0 else None
     counters = dict(runner.counters)
+    replay_size = replay.device_size()
+    xbytes = replay.bytes_exchanged / max(1, args.settle + args.warmup + args.steps)
     # end-to-end arm: host-side policy loop + transition records read back to pinned host memory every tick
     hp = HostLoopPolicy(torch, dev, 99 + rank, n, 8 if args.task == "lift" else 7)
     runner2 = make(policy=hp)
-    replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20)
-    h_trans = torch.zeros(n + runner2.reuse_capacity, 92, dtype=torch.float32).pin_memory()
-    h_flags = torch.zeros(n + runner2.reuse_capacity, dtype=torch.uint8).pin_memory()
-    for _ in range(args.warmup):
-        runner2.tick()
-    hp.h2d = hp.d2h = 0
-    _, wall2_ms, steps2, _, _, d2h_tr = timed(runner2, replay2, h_trans, h_flags)
-    e2e_ticks = args.warmup + args.steps   # hp counts the warm-up ticks of timed() as well
+    replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=slab)
+    h_block = torch.zeros(1 + slab, 92, dtype=torch.float32).pin_memory()
+    _, wall2_ms, steps2, _, _, d2h_tr = timed(runner2, replay2, h_block)
+    e2e_ticks = args.settle + args.warmup + args.steps   # hp counts every tick of timed()
     t = torch.tensor([wall_ms, wall2_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([steps, steps2], dtype=torch.float64, device=dev)
     if world > 1:
@@ -333,24 +338,25 @@ def run_rollout(args):
         bytes_per_env_step = 816  # 352 B state/action in + 464 B state/obs out
         achieved = bytes_per_env_step * n / (k_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        # the full ~10 s sample at N = 1 (where the contract asks for the baseline); a short one when other ranks are waiting
+        # same protocol as `--impl reference` (one scalar runner per host core, args.cpu_macros macro actions each, rate = env-steps /
+        # busy time of the slowest runner); a short sample when other ranks are waiting
         cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros if world == 1 else min(args.cpu_macros, 24), 1234, args.max_iter, task=args.task)
         line = {
             "metric": task_metric(args.task), "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 collision", "data": "synthetic",
-            "config": {"reuse_data": True, "max_reuse_data": 15, "workload": (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter,
-                       "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
-                       "device_ms_per_step": dev_ms / args.steps, "counters": counters},
+            "config": rollout_config(args, n, dev_ms=dev_ms, counters=counters, replay_size=replay_size, xbytes=xbytes, slab=slab),
             "clocks": clocks,
             "e2e": {"value": tot_steps2 / (wall2_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": hp.h2d / e2e_ticks,
                     "d2h_bytes_per_step": hp.d2h / e2e_ticks + d2h_tr / args.steps,
-                    "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) and the tick's transition records read back to pinned host memory"},
+                    "api": "NativeMoPARolloutRunner.tick() with a host-side policy loop (observations D2H, actions H2D, pinned memory) + "
+                           "ReplicatedReplay.exchange(); the tick's transition block is read back to pinned host memory"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("r1_envwarp_v5_traffic.json") if args.task == "push" else None,
+                         "traffic": ncu_traffic(args.traffic_file) if args.task == "push" else None,
                          "peak_source": peak_kind, "kernel": "env_step_warp_kernel", "algorithmic_bytes_per_env_step": bytes_per_env_step,
                          "kernel_ms_per_launch": k_ms, "kernel_share_of_step": k_ms * args.steps / max(dev_ms, 1e-9),
+                         "second_bound": ncu_pipe(args.traffic_file),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d macro actions on each of %d scalar runners (%d env-steps, %.1f s)" % (args.cpu_macros, cores, cpu_steps, cpu_busy)},
@@ -358,6 +364,30 @@ def run_rollout(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def rollout_config(args, n, **extra):
+    """The `config` object of the rollout line; both arms print the same workload keys."""
+    wl = (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]).replace("OMEGA", str(TASK_OMEGA[args.task]))
+    cfg = {"workload": wl, "reuse_data": True, "max_reuse_data": 15, "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter}
+    if extra:
+        cfg.update({
+            "settle_ticks": args.settle,
+            "settle": "untimed ticks before the W warm-up ticks: every env starts a macro action at tick 0, the planning burst has decayed by tick ~40",
+            "l2": "per-tick working set (env state + planner trees) is rewritten every tick; kernels are compute/latency bound",
+            "device_ms_per_step": extra["dev_ms"] / args.steps, "counters": extra["counters"],
+            "replay": {"records": extra["replay_size"], "slab_rows": extra["slab"], "allgather_bytes_landed_per_tick": extra["xbytes"]}})
+    return cfg
+
+
+def ncu_pipe(name):
+    """fp64 / issue utilisation of the env-step kernel from the committed ncu capture (the honest second bound next to HBM)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.load(f)
+        return {k: d[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct") if k in d} or None
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------- GPU arm: validity microbench
@@ -455,7 +485,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=30, help="untimed ticks (the first ~25 ticks carry the start-up burst: every env plans at tick 0)")
+    ap.add_argument("--warmup", type=int, default=10, help="untimed warm-up ticks (after the settle phase)")
+    ap.add_argument("--settle", type=int, default=40, help="untimed ticks before the warm-up: lets the start-up planning burst (every env plans at tick 0) decay")
+    ap.add_argument("--slab", type=int, default=0, help="rows of the per-tick replay exchange block (0 = envs per GPU)")
+    ap.add_argument("--traffic-file", default="r2_envwarp_traffic.json", help="profiles/<file>: dram bytes per launch + pipe utilisation from the ncu capture")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
@@ -463,8 +496,8 @@ def main():
                     help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3]), "
                          "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there)")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
-    ap.add_argument("--cpu-macros", type=int, default=600, help="macro actions per scalar runner in the cpu_baseline leg (~10 s of CPU work on a 16-core host)")
-    ap.add_argument("--ref-macros", type=int, default=16, help="macro actions per scalar runner per step of --impl reference")
+    ap.add_argument("--cpu-macros", type=int, default=150, help="macro actions per scalar runner in the cpu_baseline leg and per step of --impl reference "
+                                                                   "(one protocol for both: ~2.5 s of CPU work per runner)")
     ap.add_argument("--queries", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=1_000_000)

@@ -26,6 +26,7 @@ typedef struct mopa_planner mopa_planner;
 #define MOPA_ERR_ARG (-1)
 #define MOPA_ERR_CUDA (-2)
 #define MOPA_ERR_MODEL (-3)
+#define MOPA_ERR_OVERFLOW (-6)   /* a fixed-capacity queue lost data (see mopa_rollout_pack) */
 
 /* mopa_is_valid_* flags */
 #define MOPA_VALID_FAST 0        /* result word: bit0 = valid; other bits 0 */
@@ -128,6 +129,8 @@ typedef struct mopa_sawyer_task {
      * (l_finger_g0, l_finger_g1, l_fingertip_g0 / r_*; -1 = absent) whose contacts define has_grasp, and z of body bin1 */
     int32_t geom_cube, geom_lfinger[3], geom_rfinger[3], pad_;
     double bin_z;
+    double unstable_penalty;      /* env_config["unstable_penalty"] (env/base.py:36, default 0): subtracted from the reward of a step whose
+                                   * simulation diverged (BaseEnv._do_simulation / _after_step, env/base.py:300-304, 388-400) */
 } mopa_sawyer_task;
 
 typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
@@ -147,7 +150,17 @@ typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
                           *         expensive environments into the same CTAs, see mopa_rollout_step) */
     double *cforce;      /* [n]     nullable: BaseEnv.get_contact_force() after the step (env/base.py:568-581): sum over the
                           *         contacts of the last substep of |f_normal| + |f_tangent1| + |f_tangent2| */
+    uint8_t *grasp;      /* [n]     nullable (lift): bit 0 / 1 = the can touched a left / right finger geom in the contact list of the
+                          *         latest simulated step; a planner-failure step (no mj_step) evaluates compute_reward on this stale
+                          *         list exactly as the reference reads mjData.contact there (rl/mopa_rollouts.py:312) */
+    uint8_t *unstable;   /* [n]     nullable: 1 when the latest step produced a non-finite / huge (> 1e10, mjMAXVAL) state: the step is
+                          *         discarded (state row untouched), the episode terminates with -unstable_penalty, and the caller
+                          *         resets the environment (BaseEnv._do_simulation: reset() + _fail, env/base.py:388-400) */
 } mopa_env_buffers;
+
+/* sizeof() of the ABI structs as this library was compiled (bindings compare them with their own layout at load time):
+ * out[0..4] = mopa_model_desc, mopa_dyn_desc, mopa_sawyer_task, mopa_env_buffers, mopa_rollout_config. */
+int mopa_abi_sizes(int32_t *out5);
 
 int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int32_t device, mopa_env **out);
 void mopa_env_destroy(mopa_env *e);
@@ -188,18 +201,26 @@ typedef struct mopa_rollout_config {
     double jnt_lo[7], jnt_hi[7];  /* joint ranges of the arm */
     double init_qpos[7];          /* arm pose the reset noise is added to */
     const double *qpos0;          /* host, nq: reset pose of everything else */
-    int32_t reuse_data, max_reuse_data;   /* rl/mopa_rollouts.py:223-302: up to max_reuse_data (<= 16) relabelled records per executed plan */
+    int32_t reuse_data, max_reuse_data;   /* rl/mopa_rollouts.py:223-302: up to max_reuse_data (<= 32) relabelled records per executed plan */
     uint64_t seed_reuse;          /* seed of the (start, goal) draws, keyed by env id and macro-action index */
     int32_t discrete_action;      /* config.discrete_action (rl/mopa_rollouts.py:86-88): ac_type picks planner / direct execution;
                                      direct actions are not divided by omega; record slot 47 carries ac_type */
     int32_t ac_space_normal;      /* config.ac_space_type == "normal" (scripts/3d/{lift,assembly}/mopa_discrete.sh): planner displacement =
                                      a * action_range and relabelled action = d / action_range (rl/sac_agent.py:160-163, 180-181); 0 = piecewise */
+    /* SACAgent._simple_planner (rl/sac_agent.py:98-110, used by simple_interpolate(use_planner=True), :300-311): a densification hop
+     * whose interior is blocked is re-planned with RRT-Connect at `simple_planner_range` for `simple_max_iter` iterations (the cap that
+     * stands in for simple_planner_timelimit), then with the main planner (`range`, `max_iter`), else only its end point is kept. */
+    double simple_planner_range;
+    int32_t simple_max_iter;
+    int32_t debug_block_mod;      /* test hook, 0 = off: treat the interior of densification hop i of a problem as blocked when
+                                     (problem key + i) % debug_block_mod == 0, so that conformance tests reach the fallback planners
+                                     (naturally ~0.3 % of the RRT plans have such a hop) */
 } mopa_rollout_config;
-/* Counter slots of d_counters (int64[16]). */
-#define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting,reused"
+/* Counter slots of d_counters (int64[24]; the named ones below, the rest reserved). */
+#define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting,reused,unstable,fb_simple,fb_main"
 /* Caller-owned device buffers: d_macro_index int64[n] (policy calls per env), d_slab float[n][92] + d_emit_flag
  * uint8[n] (records emitted by the latest tick, dense by environment), d_ring float[ring_capacity][92] (all
- * records, slot = running count % capacity), d_counters int64[18]; with reuse_data: d_reuse_slab float[reuse_capacity][92] +
+ * records, slot = running count % capacity), d_counters int64[24]; with reuse_data: d_reuse_slab float[reuse_capacity][92] +
  * d_reuse_count int32[1] (relabelled records of the latest tick, compact; rows beyond the capacity only reach the ring);
  * d_ep_stats double[n][5], nullable: per environment the number of finished episodes and the sums of their length, reward,
  * success flag and contact force (the quantities MoPARolloutRunner.run_episode reports, rl/mopa_rollouts.py:401-681). */
@@ -214,6 +235,16 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
 int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
 /* discrete_action handles: d_ac_type uint8[n] (0 = direct execution, 1 = motion planner), the policy's ac["ac_type"]. */
 int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const uint8_t *d_ac_type, void *stream);
+/* Replicated replay (the consumer rl/dataset.py:7-37 replaces): step 1 of the per-tick exchange.  Copies the records emitted
+ * since the previous call - at most `cap`, the rest stays queued in the ring - to d_send float[1 + cap][92]: row 0 is a header whose
+ * first word holds the record count (int32 bits), rows 1.. the records.  The caller all-gathers d_send across ranks (NCCL) and hands
+ * the result to mopa_replay_append.  Returns MOPA_ERR_OVERFLOW when queued records were overwritten in the ring before they left. */
+int mopa_rollout_pack(mopa_rollout *r, float *d_send, int32_t cap, void *stream);
+/* Step 2: d_recv float[world][1 + cap][92] (the gathered blocks; world = 1: the send buffer itself) -> rows appended to the replicated
+ * ring d_ring float[ring_capacity][92] in rank-major order (identical on every rank).  d_size2 int64[2]: running record count, read
+ * from [parity] and written to [1 - parity] (the caller alternates parity = 0, 1, 0, ... so that one launch suffices). */
+int mopa_replay_append(const float *d_recv, int32_t world, int32_t cap, float *d_ring, int64_t ring_capacity, int64_t *d_size2, int32_t parity,
+                       void *stream);
 int mopa_rollout_busy(mopa_rollout *r);
 /* Diagnostics of the asynchronous planner: out4 = {device ms of the last finished RRT batch, batches finished, mean device
  * ms per batch, mean ticks between launch and finalisation}. */

@@ -28,6 +28,7 @@ def lib():
         if not os.path.exists(path):
             _build.build()
         L = C.CDLL(path)
+        _check_abi(L)
         L.mopa_last_error.restype = C.c_char_p
         L.mopa_device_count.restype = C.c_int
         L.mopa_planner_create.restype = C.c_int
@@ -47,6 +48,26 @@ def lib():
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def _check_abi(L):
+    """A library built from older headers would read mis-laid-out structs (silent memory corruption): compare the struct
+    sizes it was compiled with against the ctypes mirrors and refuse to run on a mismatch."""
+    if not hasattr(L, "mopa_abi_sizes"):
+        raise MopaError("libmopa_b200.so predates the current headers (no mopa_abi_sizes): rebuild with `python -m mopa_rl_b200.build --force`")
+    from .dynmodel import DynDesc
+    from .envs import EnvBuffers, SawyerTask
+    from .model import ModelDesc
+    from .rollout import _RolloutConfig
+
+    got = (C.c_int32 * 5)()
+    L.mopa_abi_sizes.argtypes = [C.c_void_p]
+    if L.mopa_abi_sizes(got) != 0:
+        raise MopaError("mopa_abi_sizes failed")
+    want = [C.sizeof(t) for t in (ModelDesc, DynDesc, SawyerTask, EnvBuffers, _RolloutConfig)]
+    if list(got) != want:
+        raise MopaError("libmopa_b200.so is stale: struct sizes %s (library) != %s (bindings); rebuild with "
+                        "`python -m mopa_rl_b200.build --force`" % (list(got), want))
 
 
 def check(rc):

@@ -30,6 +30,13 @@ extern "C" {
 
 const char *mopa_last_error(void) { return g_err.c_str(); }
 
+int mopa_abi_sizes(int32_t *out5) {
+    if (!out5) { g_err = "mopa_abi_sizes: bad argument"; return MOPA_ERR_ARG; }
+    out5[0] = (int32_t)sizeof(mopa_model_desc); out5[1] = (int32_t)sizeof(mopa_dyn_desc); out5[2] = (int32_t)sizeof(mopa_sawyer_task);
+    out5[3] = (int32_t)sizeof(mopa_env_buffers); out5[4] = (int32_t)sizeof(mopa_rollout_config);
+    return MOPA_OK;
+}
+
 int mopa_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);

@@ -104,7 +104,8 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     if (err == cudaSuccess) err = cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice);
     static int next_slot = 0;
     e->model_slot = (next_slot++) % 2;   // up to 2 live scenes per process share the constant bank round-robin
-    if (err == cudaSuccess) err = mopa::upload_env_model(e->model_slot, e->h_model);
+    if (err == cudaSuccess) err = mopa::env_slot_claim(e, nullptr, true);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err == cudaSuccess) {   // tuning / profiling hooks of the warp kernel (defaults: no profiling, all stage barriers)
         const char *pf = getenv("MOPA_ENV_PROF"), *sm = getenv("MOPA_ENV_SYNC_MASK");
         err = mopa::env_tune_set(pf ? atoi(pf) : 0, sm ? (int)strtol(sm, nullptr, 0) : 0xFE);
@@ -121,6 +122,8 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
 void mopa_env_destroy(mopa_env *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    mopa::env_slot_release(e);
     if (e->d_model) cudaFree(e->d_model);
     delete e;
 }
@@ -130,7 +133,8 @@ int mopa_env_enable_contacts(mopa_env *e, int32_t on) {
     e->h_model.enable_contacts = on ? 1 : 0;
     ENV_TRY(cudaSetDevice(e->device));
     ENV_TRY(cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice));
-    ENV_TRY(mopa::upload_env_model(e->model_slot, e->h_model));
+    ENV_TRY(mopa::env_slot_claim(e, nullptr, true));
+    ENV_TRY(cudaDeviceSynchronize());
     return MOPA_OK;
 }
 
@@ -146,7 +150,7 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
     if (!e || !buf || n < 0) { mopa_set_error("mopa_env_forward: bad argument"); return MOPA_ERR_ARG; }
     if (n == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->h_model.ngm, e->task, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
+    ENV_TRY(mopa::launch_env_warp(e, *buf, nullptr, 0, nullptr, nullptr, n, 1, d_ids, (cudaStream_t)stream));
     return MOPA_OK;
 }
 
@@ -155,8 +159,7 @@ int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_actio
     if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
     if (n_envs == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
-    ENV_TRY(mopa::launch_env_warp(e->model_slot, e->d_model, e->h_model.nb, e->h_model.ngeom, e->h_model.ngm, e->task, *buf, d_action, action_stride, d_is_planner,
-                                  d_mask, n_envs, 0, nullptr, (cudaStream_t)stream));
+    ENV_TRY(mopa::launch_env_warp(e, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr, (cudaStream_t)stream));
     return MOPA_OK;
 }
 

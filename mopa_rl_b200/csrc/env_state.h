@@ -7,12 +7,8 @@
 
 namespace mopa {
 struct DynDev;
-cudaError_t upload_env_model(int slot, const DynDev &h_model);
 cudaError_t env_tune_set(int prof, int sync_mask);
 cudaError_t env_prof_read(unsigned long long *out);
-cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, int ngm, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
-                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
-                            const int32_t *ids, cudaStream_t stream);
 }
 
 struct mopa_env {
@@ -22,3 +18,11 @@ struct mopa_env {
     mopa::DynDev h_model;
     mopa_sawyer_task task;
 };
+
+namespace mopa {
+// env.step / sim.forward launch for the handle's scene (refreshes its constant-memory slot when another handle used it)
+cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const float *action, int action_stride, const uint8_t *is_planner,
+                            const uint8_t *mask, int n, int forward_only, const int32_t *ids, cudaStream_t stream);
+cudaError_t env_slot_claim(mopa_env *env, cudaStream_t stream, bool force);
+void env_slot_release(const mopa_env *env);
+}

@@ -25,6 +25,7 @@
 #include "../../include/mopa_b200.h"
 #include "dyn.cuh"
 #include "contact.cuh"
+#include "env_state.h"
 
 namespace mopa {
 
@@ -74,6 +75,9 @@ struct WarpWS {
 // scene constants: uniform reads go through the constant cache instead of global loads
 constexpr int ENV_MODEL_SLOTS = 2;
 __constant__ DynDev c_models[ENV_MODEL_SLOTS];
+// Task tables live in the constant bank too: a kernel parameter struct that is indexed with a lane id gets copied to
+// local memory by every thread (1.2 KB x 131 k threads = 150 MB of writes per launch in round 1's ncu capture).
+__constant__ mopa_sawyer_task c_tasks[ENV_MODEL_SLOTS];
 struct EnvTune { int prof, sync_mask; };
 __constant__ EnvTune c_tune;
 __device__ unsigned long long g_prof[32];   // [2k] work before stage barrier k, [2k+1] wait at it; 20 = PGS sweeps, 21 = rows, 22 = substeps
@@ -1059,13 +1063,14 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> 
 
 template <int WB, int WG, int WC, int ENV_WARPS>
 __global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 ? 2 : 1))
-env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_task T, mopa_env_buffers B, const float *__restrict__ action,
+env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpWS<WB, WG, WC> &W = reinterpret_cast<WarpWS<WB, WG, WC> *>(smem_raw)[warp];
     const DynDev &m = c_models[model_slot];
+    const mopa_sawyer_task &T = c_tasks[model_slot];
     const int t = blockIdx.x * ENV_WARPS + warp;
     const int e = t < n ? (ids ? ids[t] : t) : 0;
     const bool live = t < n && (!mask || mask[e]);
@@ -1114,9 +1119,31 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
+    // ---- instability guard (BaseEnv._do_simulation, env/base.py:388-400: MuJoCo flags NaN / values beyond mjMAXVAL = 1e10 in
+    // qpos / qvel / qacc, mujoco-py raises, the env resets and _after_step terminates the episode with -unstable_penalty).
+    // Here: the diverged step is discarded (the state row in HBM is left as it was), the episode terminates, the caller
+    // resets the environment (the rollout does so on `done`); observation and frames are those of the untouched state.
+    bool unstable = false, corrupt = false;
+    if (mode != 2) {
+        bool bad = false;
+        for (int k = lane; k < m.nq; k += 32) { const double x = W.q[k]; if (!(fabs(x) <= 1e10)) bad = true; }
+        for (int k = lane; k < m.nv; k += 32) { const double x = W.v[k]; if (!(fabs(x) <= 1e10)) bad = true; }
+        unstable = __any_sync(FULL, bad);
+        if (unstable) {
+            bool bad2 = false;   // the stored row itself is corrupt (only possible through an external write): nothing to show
+            for (int k = lane; k < m.nq; k += 32) { const double x = B.qpos[(size_t)e * m.nq + k]; W.q[k] = x; if (!(fabs(x) <= 1e10)) bad2 = true; }
+            for (int k = lane; k < m.nv; k += 32) { const double x = B.qvel[(size_t)e * m.nv + k]; W.v[k] = x; if (!(fabs(x) <= 1e10)) bad2 = true; }
+            corrupt = __any_sync(FULL, bad2);
+            if (lane == 0) W.wn = 0;
+            __syncwarp();
+            if (!corrupt) w_substep(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
+            ncon = 0; cforce = 0.0;
+        }
+    }
     // reward / success (frames of the last substep's start state)
     double reward = 0;
     bool success = false, terminal = false;
+    int grasp_bits = 0;
     if (T.kind == 1) {   // SawyerLiftObstacleEnv.compute_reward (:92-148)
         double grip[3], d = 0;
         w_site(grip, W, 0, T.site_grip);
@@ -1126,12 +1153,19 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         // has_grasp: the contact list of the last mj_step holds can - left-finger and can - right-finger contacts
         // (a planner-failure step has no fresh contact list: mode 2 runs no mj_step)
         bool tl = false, tr = false;
-        const int nscan = mode != 2 ? ncon : 0;
-        for (int c = 0; c < nscan; c++) {
-            const int ga = W.cga[c], gb = W.cgb[c];
-            const int other = ga == T.geom_cube ? gb : (gb == T.geom_cube ? ga : -1);
-            if (other < 0) continue;
-            for (int k = 0; k < 3; k++) { if (other == T.geom_lfinger[k]) tl = true; if (other == T.geom_rfinger[k]) tr = true; }
+        if (mode != 2) {
+            for (int c = 0; c < ncon; c++) {
+                const int ga = W.cga[c], gb = W.cgb[c];
+                const int other = ga == T.geom_cube ? gb : (gb == T.geom_cube ? ga : -1);
+                if (other < 0) continue;
+                for (int k = 0; k < 3; k++) { if (other == T.geom_lfinger[k]) tl = true; if (other == T.geom_rfinger[k]) tr = true; }
+            }
+            grasp_bits = (tl ? 1 : 0) | (tr ? 2 : 0);
+        } else if (B.grasp) {
+            // planner failure: compute_reward runs without an mj_step and reads the contact list the previous step left in
+            // mjData (rl/mopa_rollouts.py:312) - the touch flags of that list are kept per environment
+            const int gb = B.grasp[e];
+            tl = (gb & 1) != 0; tr = (gb & 2) != 0;
         }
         const bool grasp = tl && tr;
         const double r_grasp = grasp ? 0.35 : 0.0, z_target = T.bin_z + 0.45;
@@ -1166,7 +1200,9 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         if (dgc < 0.1) reward += 0.1 * (1 - tanh(10 * dgc));
         if (dct < T.distance_threshold) { reward += T.success_reward; success = true; terminal = true; }
     }
-    if (mode != 2) w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+    if (unstable) { reward = -T.unstable_penalty; success = false; terminal = true; grasp_bits = 0; }
+    if (corrupt) { for (int k = lane; k < 40; k += 32) B.obs[(size_t)e * 40 + k] = 0.0f; }
+    else if (mode != 2) w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
     __syncwarp();
     // _after_step: joint-limit projection (set_state + forward), episode accounting
     bool clipped = false;
@@ -1175,17 +1211,19 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         if (x < m.d_range[lane][0]) { x = m.d_range[lane][0]; clipped = true; }
         else if (x > m.d_range[lane][1]) { x = m.d_range[lane][1]; clipped = true; }
     }
-    clipped = __any_sync(FULL, clipped);
+    clipped = __any_sync(FULL, clipped) && !unstable;
     __syncwarp();
     if (clipped) {
         w_substep(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
         if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
-    for (int k = lane; k < m.nq; k += 32) B.qpos[(size_t)e * m.nq + k] = W.q[k];
-    for (int k = lane; k < m.nv; k += 32) B.qvel[(size_t)e * m.nv + k] = W.v[k];
-    if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias_prev[lane] : 0.0;
-    if (mode != 2 && lane < 7) B.prev_state[(size_t)e * 7 + lane] = W.ctrl[lane];
+    if (!unstable) {
+        for (int k = lane; k < m.nq; k += 32) B.qpos[(size_t)e * m.nq + k] = W.q[k];
+        for (int k = lane; k < m.nv; k += 32) B.qvel[(size_t)e * m.nv + k] = W.v[k];
+        if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias_prev[lane] : 0.0;
+        if (mode != 2 && lane < 7) B.prev_state[(size_t)e * 7 + lane] = W.ctrl[lane];
+    }
     if (lane == 0) {
         if (mode != 2) B.has_prev[e] = 1;
         const int len = B.ep_len[e] + 1;
@@ -1198,6 +1236,8 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_sawyer_
         if (B.ncon) B.ncon[e] = ncon;
         if (B.work && mode != 2) B.work[e] = nwt;
         if (B.cforce) B.cforce[e] = mode != 2 ? cforce : 0.0;
+        if (B.grasp && mode != 2) B.grasp[e] = (uint8_t)grasp_bits;
+        if (B.unstable) B.unstable[e] = unstable ? 1 : 0;
     }
 }
 
@@ -1210,13 +1250,8 @@ cudaError_t env_tune_set(int prof, int sync_mask) {
 }
 cudaError_t env_prof_read(unsigned long long *out) { return cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32); }
 
-cudaError_t upload_env_model(int slot, const DynDev &h_model) {
-    if (slot < 0 || slot >= ENV_MODEL_SLOTS) return cudaErrorInvalidValue;
-    return cudaMemcpyToSymbol(c_models, &h_model, sizeof(DynDev), sizeof(DynDev) * slot);
-}
-
 template <int WB, int WG, int WC, int ENV_WARPS>
-static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
+static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_env_buffers &B, const float *action,
                                      int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                                      const int32_t *ids, cudaStream_t stream) {
     static bool attr_set = false;
@@ -1228,22 +1263,43 @@ static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n,
+    kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, d_model, B, action, action_stride, is_planner, mask, n,
                                                                             forward_only, ids);
     return cudaGetLastError();
 }
 
-cudaError_t launch_env_warp(int model_slot, const DynDev *d_model, int nb, int ngeom, int ngm, const mopa_sawyer_task &T, const mopa_env_buffers &B, const float *action,
-                            int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
-                            const int32_t *ids, cudaStream_t stream) {
+// The constant bank holds ENV_MODEL_SLOTS scenes; handles are assigned to slots round-robin.  A slot whose tables
+// belong to another (older) handle is refreshed before the launch, ordered on the launch stream.
+constexpr int ENV_MAX_DEVICES = 16;   // constant banks are per device
+static const mopa_env *g_slot_owner[ENV_MAX_DEVICES][ENV_MODEL_SLOTS] = {};
+void env_slot_release(const mopa_env *env) {
+    for (int d = 0; d < ENV_MAX_DEVICES; d++)
+        for (int k = 0; k < ENV_MODEL_SLOTS; k++) if (g_slot_owner[d][k] == env) g_slot_owner[d][k] = nullptr;
+}
+cudaError_t env_slot_claim(mopa_env *env, cudaStream_t stream, bool force) {
+    const int slot = env->model_slot;
+    if (slot < 0 || slot >= ENV_MODEL_SLOTS || env->device < 0 || env->device >= ENV_MAX_DEVICES) return cudaErrorInvalidValue;
+    if (g_slot_owner[env->device][slot] == env && !force) return cudaSuccess;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_models, &env->h_model, sizeof(DynDev), sizeof(DynDev) * slot, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_tasks, &env->task, sizeof(mopa_sawyer_task), sizeof(mopa_sawyer_task) * slot, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) g_slot_owner[env->device][slot] = env;
+    return e;
+}
+
+cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const float *action, int action_stride, const uint8_t *is_planner,
+                            const uint8_t *mask, int n, int forward_only, const int32_t *ids, cudaStream_t stream) {
     static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
     if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
+    cudaError_t e = env_slot_claim(env, stream, false);
+    if (e != cudaSuccess) return e;
+    const int model_slot = env->model_slot, nb = env->h_model.nb, ngeom = env->h_model.ngeom, ngm = env->h_model.ngm;
+    const DynDev *d_model = env->d_model;
     const bool small = nb <= 14 && ngeom <= 32 && ngm <= WarpWS<14, 32, 24>::WGM;
     if (small && small_warps)
-        return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     if (small)
-        return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
-    return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, T, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+    return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
 }
 
 // 14 workspaces + one 1-warp planner CTA (<= 18 KB + 1 KB reserved each) must fit the 228 KB of an SM together

@@ -259,7 +259,8 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
             const float *__restrict__ goal, int row_stride, const unsigned long long *__restrict__ keys, int n, int max_iter,
             float *__restrict__ tree_x, int *__restrict__ tree_parent, int max_nodes, float *__restrict__ path,
             int *__restrict__ node_ids, int max_path, int *__restrict__ path_len, int *__restrict__ status_out,
-            int *__restrict__ iters_out, int *__restrict__ nodes_out, const int *__restrict__ d_n) {
+            int *__restrict__ iters_out, int *__restrict__ nodes_out, const int *__restrict__ d_n, int only_failed,
+            unsigned long long key_xor) {
     extern __shared__ __align__(16) unsigned char smem[];
     if (d_n) { const int m = *d_n; if (m < n) n = m; if (n <= 0) return; }   // problem count produced on the device
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,6 +279,7 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
 
     const int cta_warps = blockDim.x >> 5;   // 8 for stand-alone batches; 1 when the CTAs are meant to co-reside with the env-step kernel
     for (int prob = blockIdx.x * cta_warps + warp; prob < n; prob += gridDim.x * cta_warps) {
+        if (only_failed && status_out[prob] == 0) continue;   // retry pass: problems an earlier planner already solved keep their path
         const float *srow = start + (size_t)prob * row_stride, *grow_ = goal + (size_t)prob * row_stride;
         for (int i = lane; i < sp.nq; i += 32) baseq[i] = srow[i];  // passive dims frozen at the start values
         __syncwarp();
@@ -287,7 +289,7 @@ plan_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes, SpaceDev s
             s.v[j] = j < sp.nd ? srow[sp.adr[j]] : 0.f;
             g.v[j] = j < sp.nd ? grow_[sp.adr[j]] : 0.f;
         }
-        const unsigned long long key = keys[prob];
+        const unsigned long long key = keys[prob] ^ key_xor;
         int status = MOPA_PLAN_NOT_EXACT_, it = 0, sm = -1, gm = -1;
         Tree T[2];
         for (int k = 0; k < 2; k++) {
@@ -421,7 +423,8 @@ static cudaError_t ensure_trees(mopa_planner *p, size_t n, int max_nodes) {
 
 cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_goal, int row_stride, const unsigned long long *d_keys,
                         int n, int max_iter, float *d_path, int *d_node_ids, int max_path, int *d_path_len, int *d_status,
-                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n, int cta_warps) {
+                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n, int cta_warps, float range_override, int only_failed,
+                        unsigned long long key_xor) {
     if (n <= 0) return cudaSuccess;
     if (cta_warps < 1 || cta_warps > PLAN_WARPS) cta_warps = PLAN_WARPS;
     cudaError_t e = ensure_trees(p, (size_t)n, p->max_nodes);
@@ -429,7 +432,7 @@ cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_go
     PlanBuffers *b = (PlanBuffers *)p->plan_buffers;
     SpaceDev sp;
     memset(&sp, 0, sizeof(sp));
-    sp.nd = p->space.n_active; sp.nq = p->space.nq; sp.range = p->space.range; sp.seed = p->space.seed;
+    sp.nd = p->space.n_active; sp.nq = p->space.nq; sp.range = range_override > 0.f ? range_override : p->space.range; sp.seed = p->space.seed;
     for (int j = 0; j < sp.nd; j++) {
         sp.adr[j] = p->space.active_qadr[j]; sp.so2[j] = p->space.is_so2[j];
         sp.lo[j] = p->space.lo[j]; sp.hi[j] = p->space.hi[j];
@@ -452,7 +455,7 @@ cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_go
     if (grid > max_grid) grid = max_grid;
     kern<<<grid, cta_warps * 32, smem, stream>>>(p->d_blob, H.blob_bytes, sp, d_start, d_goal, row_stride, d_keys, n, max_iter,
                                                         b->tree_x, b->tree_parent, b->max_nodes, d_path, d_node_ids, max_path,
-                                                        d_path_len, d_status, d_iters, d_nodes, d_n);
+                                                        d_path_len, d_status, d_iters, d_nodes, d_n, only_failed, key_xor);
     return cudaGetLastError();
 }
 

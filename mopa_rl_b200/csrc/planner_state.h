@@ -56,7 +56,11 @@ namespace mopa {
 void free_plan_buffers(mopa_planner *p);
 cudaError_t launch_plan(mopa_planner *p, const float *d_start, const float *d_goal, int row_stride, const unsigned long long *d_keys,
                         int n, int max_iter, float *d_path, int *d_node_ids, int max_path, int *d_path_len, int *d_status,
-                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n = nullptr, int cta_warps = 8);
+                        int *d_iters, int *d_nodes, cudaStream_t stream, const int *d_n = nullptr, int cta_warps = 8, float range_override = 0.f,
+                        int only_failed = 0, unsigned long long key_xor = 0ULL);
+// range_override > 0: extension range of this launch (the "simple" planner of SACAgent, rl/sac_agent.py:98-110, shares the scene
+// and state space of the main one); only_failed: skip problems whose d_status is already MOPA_PLAN_OK (retry pass);
+// key_xor: mixed into every problem key (independent sample streams for the retry).
 int plan_host(mopa_planner *p, const double *start, const double *goal, const uint64_t *keys, int n, int max_iter, double *path,
               int32_t *node_ids, int max_path, int32_t *path_len, int32_t *status, int32_t *iters, std::string &err);
 }

@@ -31,7 +31,7 @@ cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, c
 constexpr int RO_JMAX = 16;     // interpolation points checked per straight-line plan
 constexpr int RO_NQ = 40;       // qpos capacity (same as the env kernel)
 enum { C_MP = 0, C_RL, C_INTERP, C_MP_FAIL, C_APPROX, C_INVALID, C_DENSIFY_FALLBACK, C_EPISODES, C_SUCCESS, C_MP_PATH_LEN,
-       C_INTERP_PATH_LEN, C_ENV_STEPS, C_TRANSITIONS, C_RRT_DROPPED, C_RRT_PROBLEMS, C_WAITING, C_REUSED, C_COUNT = 18 };
+       C_INTERP_PATH_LEN, C_ENV_STEPS, C_TRANSITIONS, C_RRT_DROPPED, C_RRT_PROBLEMS, C_WAITING, C_REUSED, C_UNSTABLE, C_FB_SIMPLE, C_FB_MAIN, C_COUNT = 24 };
 
 struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being filled / in flight)
     int *cnt;                    // problems queued (may exceed the capacity: clamp)
@@ -44,12 +44,24 @@ struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being fil
     // densification
     float *dens32;               // [cap][max_path - 1][kmax][row]
     uint32_t *dens_res;          // [cap][max_path - 1][kmax]
-    int *nst;                    // [cap][max_path - 1]
+    int *nst;                    // [cap][max_path - 1]  > 0 interior states of the hop, 0 end point only, -(1 + s) fallback path s
     int *ok;                     // [cap]
+    // blocked hops -> "simple" planner, then the main planner (SACAgent.simple_interpolate with use_planner, rl/sac_agent.py:300-311)
+    int *fb_cnt;                 // hops queued (may exceed the capacity: clamp)
+    int *fb_prob, *fb_hop;       // [fb_cap]
+    float *fb_start32, *fb_goal32;   // [fb_cap][row]
+    unsigned long long *fb_keys; // [fb_cap]
+    float *fb_path;              // [fb_cap][fb_max_path][row]
+    int *fb_ids, *fb_plen, *fb_status, *fb_status1;   // [fb_cap][fb_max_path], [fb_cap] x 3 (status1: after the simple planner only)
+    int *hop_fb;                 // [cap][max_path - 1] fallback slot of a blocked hop, -1 none, -2 dropped (capacity)
 };
 
 struct RoDev {   // everything the kernels need, passed by value
     int n, nq, row, max_traj, max_path, kmax, rrt_cap, num_trials, invalid_target_handling, interpolation, task_kind;
+    int fb_cap, fb_max_path;     // blocked-hop fallback problems per RRT batch, waypoints per fallback path
+    int debug_block_mod;         // test hook, see mopa_rollout_config
+    long long *sent;             // [2] records already handed to the replay exchange (ping-pong: read [parity], write [1 - parity])
+    int *xfer_overflow;          // mapped host flag: records were overwritten in the ring before they were exchanged
     double omega, action_range, ac_scale, discount, step_size, joint_margin, range;
     unsigned long long seed_env;
     long long env_id_offset;
@@ -145,7 +157,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
             if (S.reuse_data && S.kind[e] == 1 && L > 3) {
                 const unsigned long long gid = (unsigned long long)(S.env_id_offset + e), mi = (unsigned long long)(S.macro_index[e] - 1);
                 const int tries = L < S.max_reuse ? L : S.max_reuse;
-                int ps[16], pg[16], np_ = 0;
+                int ps[32], pg[32], np_ = 0;
                 const double *tr = S.traj + (size_t)e * S.max_traj * 7;
                 const float *oh = S.ob_hist + (size_t)e * S.max_traj * 40;
                 const double *rh = S.rew_hist + (size_t)e * S.max_traj;
@@ -182,8 +194,10 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     xr[50] = (float)(goal - start - 1);
                     xr[51] = (float)(S.env_id_offset + e);
                     for (int k = 0; k < 40; k++) xr[52 + k] = oh[goal * 40 + k];
-                    const int xs = atomicAdd(S.xcount, 1);   // compact per-tick slab for the multi-GPU exchange (overflow: ring only)
-                    if (xs < S.xcap) { float *xo = S.xslab + (size_t)xs * 92; for (int k = 0; k < 92; k++) xo[k] = xr[k]; }
+                    if (S.xslab) {   // optional compact per-tick copy of the relabelled records (diagnostics; the exchange reads the ring)
+                        const int xs = atomicAdd(S.xcount, 1);
+                        if (xs < S.xcap) { float *xo = S.xslab + (size_t)xs * 92; for (int k = 0; k < 92; k++) xo[k] = xr[k]; }
+                    }
                     const unsigned long long xslot = atomicAdd((unsigned long long *)(S.counters + C_TRANSITIONS), 1ULL) % (unsigned long long)S.ring_cap;
                     float *xd = S.ring + xslot * 92;
                     for (int k = 0; k < 92; k++) xd[k] = xr[k];
@@ -207,6 +221,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                 for (int k = 0; k < nv; k++) B.qvel[(size_t)e * nv + k] = 0.0;
                 S.episode_idx[e] += 1;
                 B.ep_len[e] = 0; B.ep_rew[e] = 0.0; B.done[e] = 0; B.success[e] = 0;
+                if (B.grasp) B.grasp[e] = 0;
                 reset = 1;
             }
         }
@@ -401,12 +416,10 @@ __global__ void ro_rrt_densify_kernel(RoDev S, RrtBatch Q) {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int cnt = min(*Q.cnt, S.rrt_cap);
     if (r >= cnt) return;
-    const int e = Q.env[r];
     const int H = S.max_path - 1;
-    if (Q.status[r] != 0) {
-        if (lane == 0) { Q.ok[r] = 0; S.kind[e] = 2; S.traj_len[e] = 1; S.traj_pos[e] = 0; ro_count(S.counters, C_APPROX); ro_count(S.counters, C_MP_FAIL); }
-        return;
-    }
+    // runs on the planner stream: only the batch's own buffers are written here, the environments adopt the result in
+    // ro_rrt_finish_kernel (main stream)
+    if (Q.status[r] != 0) { if (lane == 0) Q.ok[r] = 0; return; }
     if (lane == 0) Q.ok[r] = 1;
     const int L = Q.plen[r];
     const float *path = Q.path + (size_t)r * S.max_path * S.row;
@@ -444,32 +457,92 @@ __global__ void ro_rrt_densify_kernel(RoDev S, RrtBatch Q) {
         Q.nst[(size_t)r * H + i] = nst;
     }
 }
+// hop i of problem r, re-based on the (clipped, f64) start state as SamplingBasedPlanner.plan does: start / end / difference
+__device__ __forceinline__ void ro_hop(const RoDev &S, const float *path, const double *st, int i, double *hs, double *he, double *diff, double &sf) {
+    const double lim = S.ac_scale * 0.8;
+    sf = 1.0;
+    for (int k = 0; k < 7; k++) {
+        const int a = S.arm_qadr[k];
+        const double p0 = (double)path[a];
+        he[k] = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
+        hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
+        diff[k] = he[k] - hs[k];
+        const double s = fabs(diff[k]) / lim;
+        if (s > sf) sf = s;
+    }
+}
+// Hops whose interior states are invalid become planning problems of their own (simple_interpolate with use_planner=True,
+// rl/sac_agent.py:300-311): first the "simple" planner (range simple_planner_range, goal_bias is not used by RRT-Connect),
+// then the main planner, else the hop keeps only its end point.  One warp per problem, lanes stride the hops.
+__global__ void ro_fb_collect_kernel(RoDev S, RrtBatch Q) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int cnt = min(*Q.cnt, S.rrt_cap);
+    if (r >= cnt) return;
+    const int H = S.max_path - 1, L = Q.ok[r] ? Q.plen[r] : 0;
+    const float *path = Q.path + (size_t)r * S.max_path * S.row;
+    const double *st = Q.start64 + (size_t)r * S.nq;
+    for (int i = lane; i < H; i += 32) {
+        int slot = -1;
+        if (i < L - 1) {
+            const int nst = Q.nst[(size_t)r * H + i];
+            bool bad = false;
+            for (int j = 0; j < nst; j++) if (!(Q.dens_res[((size_t)r * H + i) * S.kmax + j] & 1u)) bad = true;
+            if (S.debug_block_mod > 0 && nst > 0 && (Q.keys[r] + (unsigned long long)i) % (unsigned long long)S.debug_block_mod == 0) bad = true;
+            if (bad) {
+                slot = atomicAdd(Q.fb_cnt, 1);
+                if (slot >= S.fb_cap) slot = -2;
+                else {
+                    double hs[7], he[7], diff[7], sf;
+                    ro_hop(S, path, st, i, hs, he, diff, sf);
+                    float *s32 = Q.fb_start32 + (size_t)slot * S.row, *g32 = Q.fb_goal32 + (size_t)slot * S.row;
+                    for (int k = 0; k < S.row; k++) { const float v = k < S.nq ? (float)st[k] : 0.0f; s32[k] = v; g32[k] = v; }
+                    for (int k = 0; k < 7; k++) { s32[S.arm_qadr[k]] = (float)hs[k]; g32[S.arm_qadr[k]] = (float)he[k]; }
+                    Q.fb_prob[slot] = r; Q.fb_hop[slot] = i;
+                    Q.fb_keys[slot] = (Q.keys[r] * 0x9E3779B97F4A7C15ULL) ^ (unsigned long long)(i + 1);
+                }
+            }
+        }
+        Q.hop_fb[(size_t)r * H + i] = slot;
+    }
+}
 __global__ void ro_rrt_finish_kernel(RoDev S, RrtBatch Q) {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int cnt = min(*Q.cnt, S.rrt_cap);
-    if (r >= cnt || !Q.ok[r]) return;
+    if (r >= cnt) return;
     const int e = Q.env[r], H = S.max_path - 1, L = Q.plen[r];
+    if (!Q.ok[r]) {   // no exact solution within max_iter (sentinel -4): the plan fails
+        if (lane == 0) { S.kind[e] = 2; S.traj_len[e] = 1; S.traj_pos[e] = 0; ro_count(S.counters, C_APPROX); ro_count(S.counters, C_MP_FAIL); }
+        return;
+    }
     const float *path = Q.path + (size_t)r * S.max_path * S.row;
     const double *st = Q.start64 + (size_t)r * S.nq;
-    const double lim = S.ac_scale * 0.8;
-    // pass 1: hops whose interior states are invalid keep only their end point; total length
-    int total = 0, fallback = 0;
+    // pass 1: per hop, what is executed: its interior states + end point, the fallback planner's path, or the end point only
+    int total = 0, fallback = 0, fb_simple = 0, fb_main = 0;
     for (int base = 0; base < H; base += 32) {
         const int i = base + lane;
         int c = 0;
         if (i < L - 1) {
             int nst = Q.nst[(size_t)r * H + i];
-            bool bad = false;
-            for (int j = 0; j < nst; j++) if (!(Q.dens_res[((size_t)r * H + i) * S.kmax + j] & 1u)) bad = true;
-            if (bad) { nst = 0; Q.nst[(size_t)r * H + i] = 0; fallback++; }
-            c = nst + 1;
+            const int slot = Q.hop_fb[(size_t)r * H + i];
+            if (slot != -1) {   // blocked hop
+                if (slot >= 0 && Q.fb_status[slot] == 0 && Q.fb_plen[slot] >= 2) {
+                    nst = -(1 + slot);
+                    c = Q.fb_plen[slot] - 1;
+                    if (Q.fb_status1[slot] == 0) fb_simple++; else fb_main++;
+                } else { nst = 0; c = 1; fallback++; }
+                Q.nst[(size_t)r * H + i] = nst;
+            } else c = nst + 1;
         }
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         total += c;
     }
-    for (int o = 16; o > 0; o >>= 1) fallback += __shfl_xor_sync(0xffffffffu, fallback, o);
+    for (int o = 16; o > 0; o >>= 1) { fallback += __shfl_xor_sync(0xffffffffu, fallback, o); fb_simple += __shfl_xor_sync(0xffffffffu, fb_simple, o); fb_main += __shfl_xor_sync(0xffffffffu, fb_main, o); }
     __syncwarp();
-    if (lane == 0 && fallback) ro_count(S.counters, C_DENSIFY_FALLBACK, fallback);
+    if (lane == 0) {
+        if (fallback) ro_count(S.counters, C_DENSIFY_FALLBACK, fallback);
+        if (fb_simple) ro_count(S.counters, C_FB_SIMPLE, fb_simple);
+        if (fb_main) ro_count(S.counters, C_FB_MAIN, fb_main);
+    }
     if (total > S.max_traj) {
         if (lane == 0) { S.kind[e] = 2; S.traj_len[e] = 1; S.traj_pos[e] = 0; ro_count(S.counters, C_MP_FAIL); ro_count(S.counters, C_MP); }
         return;
@@ -481,26 +554,28 @@ __global__ void ro_rrt_finish_kernel(RoDev S, RrtBatch Q) {
         const int i = base + lane;
         const bool live = i < L - 1;
         const int nst = live ? Q.nst[(size_t)r * H + i] : 0;
-        const int c = live ? nst + 1 : 0;
+        const int slot = nst < 0 ? -nst - 1 : -1;
+        const int c = live ? (slot >= 0 ? Q.fb_plen[slot] - 1 : nst + 1) : 0;
         int incl = c;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const int off = carry + incl - c;
         if (live) {
-            double hs[7], diff[7], sf = 1.0, he[7];
-            for (int k = 0; k < 7; k++) {
-                const int a = S.arm_qadr[k];
-                const double p0 = (double)path[a];
-                he[k] = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
-                hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
-                diff[k] = he[k] - hs[k];
-                const double s = fabs(diff[k]) / lim;
-                if (s > sf) sf = s;
+            double hs[7], he[7], diff[7], sf;
+            ro_hop(S, path, st, i, hs, he, diff, sf);
+            if (slot >= 0) {   // the fallback planner's waypoints, re-based on the hop's start (first row dropped: PlannerAgent.plan)
+                const float *fp = Q.fb_path + (size_t)slot * S.fb_max_path * S.row;
+                for (int j = 1; j <= c; j++)
+                    for (int k = 0; k < 7; k++) {
+                        const int a = S.arm_qadr[k];
+                        tr[(size_t)(off + j - 1) * 7 + k] = hs[k] + ((double)fp[(size_t)j * S.row + a] - (double)fp[a]);
+                    }
+            } else {
+                double run[7];
+                for (int k = 0; k < 7; k++) run[k] = hs[k];
+                for (int j = 0; j < nst; j++)
+                    for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[(size_t)(off + j) * 7 + k] = run[k]; }
+                for (int k = 0; k < 7; k++) tr[(size_t)(off + nst) * 7 + k] = he[k];
             }
-            double run[7];
-            for (int k = 0; k < 7; k++) run[k] = hs[k];
-            for (int j = 0; j < nst; j++)
-                for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[(size_t)(off + j) * 7 + k] = run[k]; }
-            for (int k = 0; k < 7; k++) tr[(size_t)(off + nst) * 7 + k] = he[k];
         }
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
@@ -509,6 +584,46 @@ __global__ void ro_rrt_finish_kernel(RoDev S, RrtBatch Q) {
         ro_count(S.counters, C_MP);
         ro_count(S.counters, C_MP_PATH_LEN, total);
     }
+}
+
+// ---- replay exchange: the records emitted since the previous call, compact, behind a one-row header (row 0, word 0 = count).
+// The local ring is the queue: records [sent, transitions) are pending; at most `cap` leave per call, the rest waits.
+__global__ void ro_pack_kernel(RoDev S, float *__restrict__ send, int cap, int parity) {
+    const long long total = S.counters[C_TRANSITIONS], sent = S.sent[parity];
+    long long pending = total - sent;
+    const int k = (int)(pending < (long long)cap ? pending : (long long)cap);
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int i = gt; i < k * 23; i += nt) {   // 92 floats = 23 float4 per record
+        const int rec = i / 23, c = i - rec * 23;
+        const float4 v = reinterpret_cast<const float4 *>(S.ring + (size_t)((sent + rec) % S.ring_cap) * 92)[c];
+        reinterpret_cast<float4 *>(send + (size_t)(1 + rec) * 92)[c] = v;
+    }
+    if (gt == 0) {
+        for (int c = 1; c < 92; c++) send[c] = 0.0f;
+        send[0] = __int_as_float(k);
+        S.sent[1 - parity] = sent + k;
+        if (pending - k > S.ring_cap / 2) *S.xfer_overflow = 1;
+    }
+}
+// Appends the gathered per-rank blocks ([world][1 + cap][92], header row first) to the replicated ring, rank-major: the same
+// order on every rank.  One launch; every thread recomputes the (tiny) prefix over the rank counts.
+__global__ void replay_append_kernel(const float *__restrict__ recv, int world, int cap, float *__restrict__ ring, long long ring_cap,
+                                     long long *__restrict__ size_io, int parity) {
+    const long long size0 = size_io[parity];
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    long long off = 0;
+    for (int rk = 0; rk < world; rk++) {
+        const float *blk = recv + (size_t)rk * (1 + cap) * 92;
+        int k = __float_as_int(blk[0]);
+        k = k < 0 ? 0 : (k > cap ? cap : k);
+        for (int i = gt; i < k * 23; i += nt) {
+            const int rec = i / 23, c = i - rec * 23;
+            reinterpret_cast<float4 *>(ring + (size_t)((size0 + off + rec) % ring_cap) * 92)[c] =
+                reinterpret_cast<const float4 *>(blk + (size_t)(1 + rec) * 92)[c];
+        }
+        off += k;
+    }
+    if (gt == 0) size_io[1 - parity] = size0 + off;
 }
 
 // ---- 7. stage the action of every environment (direct: ac / omega, plan: env.form_action(next_qpos))
@@ -556,6 +671,7 @@ __global__ void ro_post_kernel(RoDev S, mopa_env_buffers B) {
         }
         S.executed[e] += 1;
         if (B.cforce) S.ep_cforce[e] += B.cforce[e];
+        if (B.unstable && B.unstable[e]) ro_count(S.counters, C_UNSTABLE);
         S.traj_pos[e] = pos + 1;
         if (B.done[e]) { S.macro_done[e] = 1; S.traj_len[e] = pos + 1; }
     }
@@ -576,6 +692,10 @@ struct mopa_rollout {
     int fill = 0;                // batch being filled; the other one may be in flight
     bool inflight = false;
     int max_iter = 1000;
+    int simple_max_iter = 25;    // iteration cap of the "simple" planner (stands in for simple_planner_timelimit)
+    float simple_range = 0.05f;  // config.simple_planner_range
+    int pack_parity = 0;
+    int *h_overflow = nullptr;   // mapped host memory: see RoDev::xfer_overflow
     int plan_cta_warps = 1;      // tuning hook: MOPA_PLAN_CTA_WARPS
     cudaStream_t plan_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_plan0 = nullptr;
@@ -618,8 +738,21 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
         mopa_set_error("mopa_rollout_create: configuration outside the compiled limits");
         return MOPA_ERR_ARG;
     }
+    {   // limits of the straight-line planner and of the relabelling kernel: refuse, do not clamp
+        const double steps = cfg->action_range / (cfg->ac_scale * 0.8);
+        if (!(cfg->ac_scale > 0) || steps > (double)RO_JMAX || cfg->max_traj < RO_JMAX + 1) {
+            mopa_set_error("mopa_rollout_create: action_range / (0.8 * ac_scale) exceeds the 16 interpolation points of the straight-line planner, or max_traj < 17");
+            return MOPA_ERR_ARG;
+        }
+        if (cfg->reuse_data && (cfg->max_reuse_data < 1 || cfg->max_reuse_data > 32)) {
+            mopa_set_error("mopa_rollout_create: max_reuse_data must be in 1..32");
+            return MOPA_ERR_ARG;
+        }
+    }
     mopa_rollout *r = new mopa_rollout();
     r->env = env; r->planner = planner; r->buf = *buf; r->max_iter = cfg->max_iter;
+    r->simple_max_iter = cfg->simple_max_iter > 0 ? cfg->simple_max_iter : 1;
+    r->simple_range = (float)cfg->simple_planner_range;
     if (const char *w = getenv("MOPA_PLAN_CTA_WARPS")) r->plan_cta_warps = atoi(w);
     RoDev &S = r->S;
     memset(&S, 0, sizeof(S));
@@ -628,6 +761,8 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.n = n; S.nq = nq; S.row = row; S.max_traj = cfg->max_traj; S.max_path = cfg->max_path; S.kmax = (int)(cfg->range / lim) + 1;
     S.rrt_cap = cfg->rrt_capacity; S.num_trials = cfg->num_trials; S.invalid_target_handling = cfg->invalid_target_handling;
     S.interpolation = cfg->interpolation;
+    S.fb_cap = cfg->rrt_capacity < 256 ? cfg->rrt_capacity : 256; S.fb_max_path = 64;
+    S.debug_block_mod = cfg->debug_block_mod;
     S.task_kind = env->task.kind;
     S.omega = cfg->omega; S.action_range = cfg->action_range; S.ac_scale = cfg->ac_scale; S.discount = cfg->discount;
     S.step_size = cfg->step_size; S.joint_margin = cfg->joint_margin; S.range = cfg->range;
@@ -642,10 +777,11 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.adim = env->task.kind == 1 ? 8 : 7;
     S.grip_qadr0 = env->task.grip_qadr[0];
     if (S.adim == 8 && S.discrete) { mopa_set_error("mopa_rollout_create: discrete_action is not built for the 8-D lift action (record slot 47 is taken)"); delete r; return MOPA_ERR_ARG; }
-    S.reuse_data = (cfg->reuse_data && d_reuse_slab && d_reuse_count && reuse_capacity > 0) ? 1 : 0;
-    S.max_reuse = cfg->max_reuse_data < 1 ? 1 : (cfg->max_reuse_data > 16 ? 16 : cfg->max_reuse_data);
+    S.reuse_data = cfg->reuse_data ? 1 : 0;
+    S.max_reuse = cfg->max_reuse_data < 1 ? 1 : cfg->max_reuse_data;
     S.ep_stats = d_ep_stats;
-    S.seed_reuse = cfg->seed_reuse; S.xslab = d_reuse_slab; S.xcount = d_reuse_count; S.xcap = reuse_capacity;
+    S.seed_reuse = cfg->seed_reuse;
+    if (d_reuse_slab && d_reuse_count && reuse_capacity > 0) { S.xslab = d_reuse_slab; S.xcount = d_reuse_count; S.xcap = reuse_capacity; }
     cudaError_t e = cudaSetDevice(env->device);
 #define A(ptr, count) if (e == cudaSuccess) e = ro_alloc(r, &ptr, (size_t)(count))
     double *qpos0 = nullptr;
@@ -668,9 +804,19 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
         A(Q.cnt, 1); A(Q.env, cap); A(Q.start32, cap * row); A(Q.goal32, cap * row); A(Q.start64, cap * nq); A(Q.keys, cap);
         A(Q.path, cap * S.max_path * row); A(Q.ids, cap * S.max_path); A(Q.plen, cap); A(Q.status, cap);
         A(Q.dens32, cap * H * S.kmax * row); A(Q.dens_res, cap * H * S.kmax); A(Q.nst, cap * H); A(Q.ok, cap);
+        const size_t fc = S.fb_cap, fp = S.fb_max_path;
+        A(Q.fb_cnt, 1); A(Q.fb_prob, fc); A(Q.fb_hop, fc); A(Q.fb_start32, fc * row); A(Q.fb_goal32, fc * row); A(Q.fb_keys, fc);
+        A(Q.fb_path, fc * fp * row); A(Q.fb_ids, fc * fp); A(Q.fb_plen, fc); A(Q.fb_status, fc); A(Q.fb_status1, fc); A(Q.hop_fb, cap * H);
     }
+    A(S.sent, 2);
 #undef A
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->plan_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&r->h_overflow, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *r->h_overflow = 0; e = cudaHostGetDevicePointer((void **)&S.xfer_overflow, r->h_overflow, 0); }
+    if (e == cudaSuccess) {   // the planner stream outranks the env-step kernel: its small CTAs take the first SM slots that free up
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&r->plan_stream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_done);
     if (e == cudaSuccess) e = cudaEventCreate(&r->ev_plan0);
@@ -694,6 +840,7 @@ void mopa_rollout_destroy(mopa_rollout *r) {
     cudaSetDevice(r->env->device);
     cudaDeviceSynchronize();
     for (void *p : r->allocs) cudaFree(p);
+    if (r->h_overflow) cudaFreeHost(r->h_overflow);
     if (r->plan_stream) cudaStreamDestroy(r->plan_stream);
     if (r->ev_ready) cudaEventDestroy(r->ev_ready);
     if (r->ev_done) cudaEventDestroy(r->ev_done);
@@ -705,19 +852,39 @@ void mopa_rollout_destroy(mopa_rollout *r) {
 static int ro_finalize_rrt(mopa_rollout *r, cudaStream_t st) {
     RoDev &S = r->S;
     RrtBatch &Q = r->batch[1 - r->fill];
-    const int warps_blocks = (S.rrt_cap * 32 + 127) / 128, H = S.max_path - 1;
+    const int warps_blocks = (S.rrt_cap * 32 + 127) / 128;
     RO_TRY(cudaStreamWaitEvent(st, r->ev_done, 0));
     {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, r->ev_plan0, r->ev_done) == cudaSuccess) { r->rrt_last_ms = ms; r->rrt_sum_ms += ms; r->rrt_batches += 1; r->rrt_sum_ticks += r->ticks - r->tick_launched; }
     }
-    ro_rrt_densify_kernel<<<warps_blocks, 128, 0, st>>>(S, Q);
-    RO_TRY(launch_is_valid(r->planner->d_blob, r->planner->scene.hdr, Q.dens32, S.row, S.rrt_cap * H * S.kmax, Q.dens_res, 0,
-                           r->planner->sm_count, st, Q.cnt, H * S.kmax));
     ro_rrt_finish_kernel<<<warps_blocks, 128, 0, st>>>(S, Q);
     RO_TRY(cudaGetLastError());
     r->inflight = false;
-    r->launches += 3;
+    r->launches += 1;
+    return MOPA_OK;
+}
+
+/* The whole planning pipeline of a batch, on the planner stream (under the env-step kernels of the following ticks):
+ * RRT-Connect -> densification states -> their validity -> blocked hops -> simple planner -> main planner on what is left. */
+static int ro_launch_rrt(mopa_rollout *r, RrtBatch &Q) {
+    RoDev &S = r->S;
+    mopa_planner *p = r->planner;
+    cudaStream_t ps = r->plan_stream;
+    const int warps_blocks = (S.rrt_cap * 32 + 127) / 128, H = S.max_path - 1;
+    RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
+                       ps, Q.cnt, r->plan_cta_warps));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
+    ro_rrt_densify_kernel<<<warps_blocks, 128, 0, ps>>>(S, Q);
+    RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, Q.dens32, S.row, S.rrt_cap * H * S.kmax, Q.dens_res, 0, p->sm_count, ps, Q.cnt, H * S.kmax));
+    RO_TRY(cudaMemsetAsync(Q.fb_cnt, 0, sizeof(int), ps));
+    ro_fb_collect_kernel<<<warps_blocks, 128, 0, ps>>>(S, Q);
+    RO_TRY(cudaGetLastError());
+    RO_TRY(launch_plan(p, Q.fb_start32, Q.fb_goal32, S.row, Q.fb_keys, S.fb_cap, r->simple_max_iter, Q.fb_path, Q.fb_ids, S.fb_max_path, Q.fb_plen,
+                       Q.fb_status, nullptr, nullptr, ps, Q.fb_cnt, r->plan_cta_warps, r->simple_range, 0, 0ULL));
+    RO_TRY(cudaMemcpyAsync(Q.fb_status1, Q.fb_status, sizeof(int) * S.fb_cap, cudaMemcpyDeviceToDevice, ps));
+    RO_TRY(launch_plan(p, Q.fb_start32, Q.fb_goal32, S.row, Q.fb_keys, S.fb_cap, r->max_iter, Q.fb_path, Q.fb_ids, S.fb_max_path, Q.fb_plen,
+                       Q.fb_status, nullptr, nullptr, ps, Q.fb_cnt, r->plan_cta_warps, 0.f, 1, 0xA5A5A5A5A5A5A5A5ULL));
+    r->launches += 6;
     return MOPA_OK;
 }
 
@@ -737,11 +904,10 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
         else if (q != cudaErrorNotReady) RO_TRY(q);
     }
     const int blocks = (S.n + 127) / 128;
-    if (S.reuse_data) RO_TRY(cudaMemsetAsync(S.xcount, 0, sizeof(int), st));
+    if (S.xslab) RO_TRY(cudaMemsetAsync(S.xcount, 0, sizeof(int), st));
     ro_pre_kernel<<<blocks, 128, 0, st>>>(S, r->buf, r->env->h_model.nv);
     RO_TRY(cudaGetLastError());
-    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->h_model.ngm, r->env->task, r->buf, nullptr, 0, nullptr,
-                           S.reset_flag, S.n, 1, nullptr, st));
+    RO_TRY(launch_env_warp(r->env, r->buf, nullptr, 0, nullptr, S.reset_flag, S.n, 1, nullptr, st));
     r->launches += 2;
     return MOPA_OK;
 }
@@ -775,11 +941,9 @@ int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const ui
         RO_TRY(cudaStreamWaitEvent(r->plan_stream, r->ev_ready, 0));
         RO_TRY(cudaEventRecord(r->ev_plan0, r->plan_stream));
         r->tick_launched = r->ticks;
-        RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
-                           r->plan_stream, Q.cnt, r->plan_cta_warps));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
+        { const int rc = ro_launch_rrt(r, Q); if (rc) return rc; }
         RO_TRY(cudaEventRecord(r->ev_done, r->plan_stream));
         r->inflight = true;
-        r->launches += 1;
         r->fill = 1 - r->fill;
         RO_TRY(cudaMemsetAsync(r->batch[r->fill].cnt, 0, sizeof(int), st));
     }
@@ -787,13 +951,41 @@ int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const ui
     RO_TRY(cudaGetLastError());
     const int ev = (int)(r->ticks % mopa_rollout::EV_RING);
     RO_TRY(cudaEventRecord(r->ev_env0[ev], st));
-    RO_TRY(launch_env_warp(r->env->model_slot, r->env->d_model, r->env->h_model.nb, r->env->h_model.ngeom, r->env->h_model.ngm, r->env->task, r->buf, S.step_action, 8, S.step_mode,
-                           S.step_mask, S.n, 0, S.ids, st));
+    RO_TRY(launch_env_warp(r->env, r->buf, S.step_action, 8, S.step_mode, S.step_mask, S.n, 0, S.ids, st));
     RO_TRY(cudaEventRecord(r->ev_env1[ev], st));
     ro_post_kernel<<<blocks, 128, 0, st>>>(S, r->buf);
     RO_TRY(cudaGetLastError());
     r->launches += 10;   // begin, 3 x validity, back-off, interpolation, interpolation finish, stage, env step, post
     r->ticks += 1;
+    return MOPA_OK;
+}
+
+/* Replay exchange, step 1 (see include/mopa_b200.h). */
+int mopa_rollout_pack(mopa_rollout *r, float *d_send, int32_t cap, void *stream) {
+    if (!r || !d_send || cap <= 0) { mopa_set_error("mopa_rollout_pack: bad argument"); return MOPA_ERR_ARG; }
+    if (*r->h_overflow) {
+        mopa_set_error("mopa_rollout_pack: transition records were overwritten before they were exchanged (the slab capacity is too small for the emission rate)");
+        return MOPA_ERR_OVERFLOW;
+    }
+    RO_TRY(cudaSetDevice(r->env->device));
+    const int blocks = (cap * 23 + 255) / 256 < 296 ? (cap * 23 + 255) / 256 : 296;
+    ro_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(r->S, d_send, cap, r->pack_parity);
+    RO_TRY(cudaGetLastError());
+    r->pack_parity ^= 1;
+    r->launches += 1;
+    return MOPA_OK;
+}
+
+/* Replay exchange, step 2: gathered blocks -> replicated ring. */
+int mopa_replay_append(const float *d_recv, int32_t world, int32_t cap, float *d_ring, int64_t ring_capacity, int64_t *d_size2, int32_t parity,
+                       void *stream) {
+    if (!d_recv || world <= 0 || cap <= 0 || !d_ring || ring_capacity <= 0 || !d_size2 || (parity != 0 && parity != 1)) {
+        mopa_set_error("mopa_replay_append: bad argument");
+        return MOPA_ERR_ARG;
+    }
+    const int blocks = (cap * 23 + 255) / 256 < 296 ? (cap * 23 + 255) / 256 : 296;
+    replay_append_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_recv, world, cap, d_ring, (long long)ring_capacity, (long long *)d_size2, parity);
+    RO_TRY(cudaGetLastError());
     return MOPA_OK;
 }
 

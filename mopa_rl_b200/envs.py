@@ -33,17 +33,18 @@ class SawyerTask(C.Structure):
                 ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double),
                 ("site_hole", C.c_double * 3), ("site_hole_bottom", C.c_double * 3),
                 ("geom_cube", C.c_int32), ("geom_lfinger", C.c_int32 * 3), ("geom_rfinger", C.c_int32 * 3), ("pad_", C.c_int32),
-                ("bin_z", C.c_double)]
+                ("bin_z", C.c_double), ("unstable_penalty", C.c_double)]
 
 
 class EnvBuffers(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("qpos", "qvel", "prev_state", "bias_prev", "has_prev", "ep_len", "ep_rew", "obs",
-                                           "reward", "done", "success", "ncon", "work", "cforce")]
+                                           "reward", "done", "success", "ncon", "work", "cforce", "grasp", "unstable")]
 
 
 def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0,
-                   with_target=True):
+                   with_target=True, unstable_penalty=0.0):
     t = SawyerTask()
+    t.unstable_penalty = float(unstable_penalty)
     t.kind = 0
     joints = ["right_j%d" % i for i in range(7)]
     sim_body = {b: i for i, b in enumerate(dyn.bodies)}
@@ -79,11 +80,12 @@ def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.
 ASSEMBLY_INIT_QPOS = np.array([0.427, 0.13, 0.0557, 0.114, -0.0622, 0.0276, 0.00356])   # sawyer_assembly_obstacle.py:19-20
 
 
-def make_assembly_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, **_):
+def make_assembly_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, unstable_penalty=0.0, **_):
     """SawyerAssemblyObstacle-v0: peg rigidly attached to the gripper, hole sites on the furniture part `4_part4`
     (env/sawyer/sawyer_assembly_obstacle.py).  kind 2 of mopa_sawyer_task: body_cube = peg, body_rclaw / body_lclaw =
     the body that carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd."""
     t = SawyerTask()
+    t.unstable_penalty = float(unstable_penalty)
     t.kind = 2
     sim_body = {b: i for i, b in enumerate(dyn.bodies)}
     for k in range(7):
@@ -115,10 +117,10 @@ LIFT_LEFT_FINGER_GEOMS = ("l_finger_g0", "l_finger_g1", "l_fingertip_g0")      #
 LIFT_RIGHT_FINGER_GEOMS = ("r_finger_g0", "r_finger_g1", "r_fingertip_g0")
 
 
-def make_lift_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, **_):
+def make_lift_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, success_reward=150.0, unstable_penalty=0.0, **_):
     """SawyerLiftObstacle-v0 (env/sawyer/sawyer_lift_obstacle.py): kind 1 of mopa_sawyer_task.  8-D action (7 joints +
     gripper), reward = max(reach, grasp, lift) with has_grasp read from the contact list (both fingers touch the can)."""
-    t = make_push_task(model, dyn, max_episode_steps, frame_dt, ac_scale, 0.0, success_reward, with_target=False)
+    t = make_push_task(model, dyn, max_episode_steps, frame_dt, ac_scale, 0.0, success_reward, with_target=False, unstable_penalty=unstable_penalty)
     t.kind = 1
     sim_geom = {g: i for i, g in enumerate(dyn.geoms)}
     t.geom_cube = sim_geom[model.geom_name2id("cube")]
@@ -218,6 +220,8 @@ class VecSawyerPushObstacle:
         self.ncon = torch.zeros(n, dtype=torch.int32, device=dev)
         self.work = torch.zeros(n, dtype=torch.int32, device=dev)
         self.cforce = torch.zeros(n, dtype=f64, device=dev)   # get_contact_force() of every env after the latest step
+        self.grasp = torch.zeros(n, dtype=torch.uint8, device=dev)      # lift: finger-touch flags of the latest simulated step
+        self.unstable = torch.zeros(n, dtype=torch.uint8, device=dev)   # 1 = the latest step diverged and was discarded (episode ends)
         self.buf = EnvBuffers(*[getattr(self, k).data_ptr() for k, _ in EnvBuffers._fields_])
         self.env_ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
         self.episode_idx = np.zeros(n, dtype=np.int64)
@@ -262,6 +266,8 @@ class VecSawyerPushObstacle:
         self.ep_rew[t_ids] = 0
         self.done[t_ids] = 0
         self.success[t_ids] = 0
+        self.grasp[t_ids] = 0
+        self.unstable[t_ids] = 0
         self.forward(t_ids)
         return self.obs
 

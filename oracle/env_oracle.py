@@ -247,8 +247,12 @@ class LiftEnvOracle(PushEnvOracle):
         self.terminal = terminal
         return ob, reward, terminal
 
+    def reset_to(self, qpos, qvel):
+        self.contacts = []   # sim.forward() of the reset state: the can rests in the bin, no finger touches it
+        return super().reset_to(qpos, qvel)
+
     def null_step(self):
-        self.contacts = []   # no mj_step ran: no fresh contact list (the device path does the same)
+        # no mj_step ran: compute_reward(zeros) reads the contact list the previous step left in mjData (rl/mopa_rollouts.py:312)
         return super().null_step()
 
 

@@ -32,6 +32,8 @@ class ScalarMoPARunner:
         self.scene = OracleScene(model, ignored, cfg.contact_threshold, "f32")
         adr, lo, hi, so2 = space_from_model(model, passive)
         self.planner = OraclePlanner(self.scene, adr, lo, hi, so2, cfg.range, 0.005, cfg.seed, max_nodes=4096)
+        # SACAgent._simple_planner (rl/sac_agent.py:98-110): same scene and space, range = simple_planner_range
+        self.simple_planner = OraclePlanner(self.scene, adr, lo, hi, so2, cfg.simple_planner_range, 0.005, cfg.seed, max_nodes=4096)
         self.ref = adr
         self.na = len(adr)                                          # arm joints (7 Sawyer, 4 Pusher), qpos addresses 0 .. na-1
         assert list(adr) == list(range(self.na))
@@ -45,7 +47,7 @@ class ScalarMoPARunner:
         self.plan_count = 0
         self.macro_index = 0
         self.env_steps = 0
-        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, reused=0)
+        self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, reused=0, fb_simple=0, fb_main=0, densify_fallback=0)
         self.extra_records = []   # relabelled records (reuse_data) of the latest macro step
         self.ob = self._reset()
 
@@ -97,6 +99,24 @@ class ScalarMoPARunner:
         traj.append(target)
         return traj, True
 
+    def _rebase(self, curr, states):
+        """SamplingBasedPlanner.plan (:72-101) + PlannerAgent.plan (:47-48): the planner's states re-based on the (un-wrapped)
+        start, first row dropped."""
+        if self.limited.all():
+            return [curr + (s - states[0]) for s in states][1:]
+        # accumulate waypoint deltas on the un-wrapped start, going the short way round across +-3.14
+        path, prev_s, acc = [], states[0], curr.copy()
+        for st in states[1:]:
+            delta = st - prev_s
+            for k in np.nonzero(~self.limited)[0]:
+                if abs(st[k] - prev_s[k]) > 3.14:
+                    delta[k] = (3.14 - prev_s[k] + st[k] + 3.14) if prev_s[k] > 0 and st[k] <= 0 else (
+                        -(3.14 - st[k] + prev_s[k] + 3.14) if prev_s[k] < 0 and st[k] > 0 else delta[k])
+            acc = acc + delta
+            path.append(acc.copy())
+            prev_s = st
+        return path
+
     def _plan(self, curr, target):
         """SACAgent.plan: interpolation first, RRT-Connect when the straight line is blocked, densify."""
         cfg = self.cfg
@@ -110,23 +130,10 @@ class ScalarMoPARunner:
         r = self.planner.plan(ws.astype(np.float32).astype(np.float64), wg.astype(np.float32).astype(np.float64), key, cfg.max_iter, cfg.max_path)
         if r["status"] != 0:
             return None, False, False, r["status"] != -4
-        states = r["path"]
-        if self.limited.all():
-            path = [curr + (s - states[0]) for s in states][1:]   # re-based on start, first row dropped
-        else:   # :81-101: accumulate waypoint deltas on the un-wrapped start, going the short way round across +-3.14
-            path, prev_s, acc = [], states[0], curr.copy()
-            for st in states[1:]:
-                delta = st - prev_s
-                for k in np.nonzero(~self.limited)[0]:
-                    if abs(st[k] - prev_s[k]) > 3.14:
-                        delta[k] = (3.14 - prev_s[k] + st[k] + 3.14) if prev_s[k] > 0 and st[k] <= 0 else (
-                            -(3.14 - st[k] + prev_s[k] + 3.14) if prev_s[k] < 0 and st[k] > 0 else delta[k])
-                acc = acc + delta
-                path.append(acc.copy())
-                prev_s = st
+        path = self._rebase(curr, r["path"])
         if cfg.interpolation:
             new, start = [], curr
-            for p in path:
+            for hop, p in enumerate(path):
                 d = p[:self.na] - start[:self.na]
                 if np.any(np.abs(d) > cfg.ac_scale):
                     lim = cfg.ac_scale * 0.8
@@ -138,7 +145,13 @@ class ScalarMoPARunner:
                             good = False
                             break
                         inner.append(interp.copy())
-                    new.extend((inner if good else []) + [p])
+                    mod = int(getattr(cfg, "debug_block_mod", 0))
+                    if mod > 0 and min(int(sf), int(cfg.range / lim) + 1) > 0 and (key + hop) % mod == 0:
+                        good = False
+                    if good:
+                        new.extend(inner + [p])
+                    else:
+                        new.extend(self._replan_hop(start, p, key, hop))
                 else:
                     new.append(p)
                 start = p
@@ -146,6 +159,24 @@ class ScalarMoPARunner:
         if len(path) > cfg.max_traj:
             return None, False, False, True
         return path, True, False, True
+
+    def _replan_hop(self, start, target, key, hop):
+        """simple_interpolate(..., use_planner=True) on a blocked hop (rl/sac_agent.py:300-311): the simple planner
+        (simple_planner_timelimit -> cfg.simple_max_iter iterations), then the main planner, else [target]."""
+        cfg = self.cfg
+        fbkey = ((int(key) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) ^ (hop + 1)
+        s32 = self._wrap(start).astype(np.float32).astype(np.float64)
+        g32 = self._wrap(target).astype(np.float32).astype(np.float64)
+        r = self.simple_planner.plan(s32, g32, fbkey, cfg.simple_max_iter, 64)
+        which = "fb_simple"
+        if r["status"] != 0:
+            r = self.planner.plan(s32, g32, fbkey ^ 0xA5A5A5A5A5A5A5A5, cfg.max_iter, 64)
+            which = "fb_main"
+        if r["status"] != 0 or len(r["path"]) < 2:
+            self.counters["densify_fallback"] += 1
+            return [target]
+        self.counters[which] += 1
+        return self._rebase(start, r["path"])
 
     def macro_step(self):
         """One iteration of the `while not done` loop of run(); returns the 92-float transition record."""

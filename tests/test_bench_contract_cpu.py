@@ -17,7 +17,7 @@ def _run(*args):
 
 
 def test_reference_arm_line(oracle_built):
-    d = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-macros", "2")
+    d = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-macros", "2")
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("env-steps/sec (incl. planner) SawyerPushObstacle-v0")
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1

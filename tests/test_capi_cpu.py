@@ -59,18 +59,28 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mopa_rollout_config), offsetof(mopa_rollout_config, qpos0), offsetof(mopa_rollout_config, seed_reuse),
          offsetof(mopa_rollout_config, ac_space_normal), offsetof(mopa_sawyer_task, geom_cube), offsetof(mopa_sawyer_task, bin_z),
          offsetof(mopa_model_desc, mesh_vert));
+  printf("%zu %zu %zu %zu\n", offsetof(mopa_sawyer_task, unstable_penalty), offsetof(mopa_env_buffers, grasp), offsetof(mopa_env_buffers, unstable),
+         offsetof(mopa_rollout_config, debug_block_mod));
   return 0; }'''
     src = tmp_path / "layout.c"
     src.write_text(prog)
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     out = subprocess.check_output([str(exe)], text=True).split()
-    sizes, offs, more = list(map(int, out[:4])), list(map(int, out[4:8])), list(map(int, out[8:]))
+    sizes, offs, more, r2 = list(map(int, out[:4])), list(map(int, out[4:8])), list(map(int, out[8:15])), list(map(int, out[15:]))
     assert sizes == [C.sizeof(ModelDesc), C.sizeof(DynDesc), C.sizeof(SawyerTask), C.sizeof(EnvBuffers)]
     assert offs == [ModelDesc.site_quat.offset, DynDesc.p_g2.offset, SawyerTask.success_reward.offset, EnvBuffers.ncon.offset]
     # the rollout configuration and the fields added for the lift task / mesh collider (a mismatch here would only show on a GPU)
     assert more == [C.sizeof(_RolloutConfig), _RolloutConfig.qpos0.offset, _RolloutConfig.seed_reuse.offset, _RolloutConfig.ac_space_normal.offset,
                     SawyerTask.geom_cube.offset, SawyerTask.bin_z.offset, ModelDesc.mesh_vert.offset]
+    # round 2: instability guard, persistent grasp flags, fallback planners
+    assert r2 == [SawyerTask.unstable_penalty.offset, EnvBuffers.grasp.offset, EnvBuffers.unstable.offset, _RolloutConfig.debug_block_mod.offset]
+    # the library reports the sizes it was compiled with; the binding refuses a stale build (capi._check_abi)
+    from mopa_rl_b200 import capi
+
+    got = (C.c_int32 * 5)()
+    assert capi.lib().mopa_abi_sizes(got) == 0
+    assert list(got) == sizes + [C.sizeof(_RolloutConfig)]
 
 
 def test_product_never_imports_the_oracle():

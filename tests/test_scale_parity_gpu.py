@@ -1,0 +1,265 @@
+"""Parity at the benchmarked scale and horizon:
+
+  * the 4096-env SawyerPushObstacle-v0 bench configuration (push preset incl. reuse_data), a seeded 64-env subset followed
+    through a full 250-step episode against the scalar restatement: state after every env.step, every record;
+  * >= 10^6 state-validity queries against the f32 oracle (bit exact) and the f64 oracle (flips counted);
+  * physics invariants that do not involve the oracle or its shared front end (mjcf.py / dynmodel.py): analytic free
+    fall, torque-free spin, static contact force = weight, Coulomb deceleration.
+"""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import planner_setup, random_qpos
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BENCH_SEED_ENV, BENCH_SEED_POLICY, BENCH_SEED_CFG = 1234, 1241, 1234   # bench.py: venv seed 1234, policy seed + 7, MoPAConfig.seed
+
+
+def _scalar_episode(args):
+    """Worker: the scalar loop of one environment until its first episode ends; logs the state after every env.step."""
+    gid, horizon = args
+    sys.path.insert(0, ROOT)
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import MoPAConfig, planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    model = load_model("SawyerPushObstacle-v0")
+    ignored, passive, _ = planner_inputs(model)
+    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG)
+
+    def policy(g, k):
+        u = rng.uniform01(BENCH_SEED_POLICY, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    r = ScalarMoPARunner(model, DynModel(model), cfg, ignored, passive, gid, BENCH_SEED_ENV, policy, max_episode_steps=horizon)
+    states, env = {}, r.env
+    step0, null0 = env.step, env.null_step
+
+    def step(a, is_planner=False):
+        out = step0(a, is_planner)
+        states[env.ep_len] = (env.qpos.copy(), env.qvel.copy())
+        return out
+
+    def null_step():
+        out = null0()
+        states[env.ep_len] = (env.qpos.copy(), env.qvel.copy())
+        return out
+
+    env.step, env.null_step = step, null_step
+    records = []
+    while True:
+        rec = r.macro_step()
+        records.append(rec)
+        records.extend(r.extra_records)
+        if rec[49] == 1.0:
+            break
+    n = max(states)
+    return gid, np.stack([states[k][0] for k in range(1, n + 1)]), np.stack([states[k][1] for k in range(1, n + 1)]), np.stack(records)
+
+
+def test_bench_config_subset_matches_scalar_loop_over_a_full_episode(oracle_built):
+    import torch
+
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner
+
+    n, horizon, nsub = 4096, 250, 64
+    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG)
+    venv = VecSawyerPushObstacle(n, seed=BENCH_SEED_ENV, max_episode_steps=horizon)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, BENCH_SEED_POLICY))
+    subset = np.sort(np.random.default_rng(2026).choice(n, nsub, replace=False))
+    sub_t = torch.as_tensor(subset, device=venv.dev)
+    with mp.get_context("fork").Pool(min(nsub, os.cpu_count() or 1)) as pool:
+        job = pool.map_async(_scalar_episode, [(int(g), horizon) for g in subset])
+        # device side: tick until every subset env has finished its first episode; log (episode, ep_len, qpos, qvel) per tick
+        logs = {int(g): {} for g in subset}
+        episode = np.zeros(nsub, np.int64)
+        prev_len = np.zeros(nsub, np.int64)
+        for t in range(horizon * 2):
+            runner.tick()
+            ep_len = venv.ep_len[sub_t].cpu().numpy()
+            q, v = venv.qpos[sub_t].cpu().numpy(), venv.qvel[sub_t].cpu().numpy()
+            for i, g in enumerate(subset):
+                if ep_len[i] < prev_len[i]:
+                    episode[i] += 1
+                prev_len[i] = ep_len[i]
+                if episode[i] == 0 and ep_len[i] > 0:
+                    logs[int(g)][int(ep_len[i])] = (q[i], v[i])
+            if (episode >= 1).all():
+                break
+        assert (episode >= 1).all(), "some environments did not finish an episode in %d ticks" % (horizon * 2)
+        runner.drain()
+        torch.cuda.synchronize()
+        c = runner.counters
+        rec = runner.transitions[:c["transitions"]].cpu().numpy()
+        scalar = job.get(timeout=1200)
+    err_at = {1: 0.0, 75: 0.0, 250: 0.0}
+    worst_q = worst_v = worst_obs = 0.0
+    per_env = []
+    n_rec = 0
+    for gid, sq, sv, srec in scalar:
+        log = logs[gid]
+        # the last env.step of an episode is overwritten by the reset before the tick ends: compare what was logged
+        ks = sorted(k for k in log if k <= len(sq))
+        assert len(ks) >= len(sq) - 1, (gid, len(ks), len(sq))
+        eq = np.array([np.abs(log[k][0] - sq[k - 1]).max() for k in ks])
+        ev = np.array([np.abs(log[k][1] - sv[k - 1]).max() for k in ks])
+        per_env.append((gid, eq.max(), ev.max()))
+        worst_q, worst_v = max(worst_q, eq.max()), max(worst_v, ev.max())
+        for k in err_at:
+            if k in log and k <= len(sq):
+                err_at[k] = max(err_at[k], np.abs(log[k][0] - sq[k - 1]).max())
+        mine = rec[rec[:, 51] == gid][:len(srec)]
+        assert len(mine) == len(srec), (gid, len(mine), len(srec))
+        for k, (r, o) in enumerate(zip(mine, srec)):
+            assert np.allclose(r[40:47], o[40:47], atol=1e-6), (gid, k)
+            assert r[49] == o[49] and r[50] == o[50], (gid, k, r[48:51], o[48:51])
+            assert abs(r[48] - o[48]) < 1e-4, (gid, k, r[48], o[48])
+            worst_obs = max(worst_obs, np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+        n_rec += len(srec)
+    print("bench-config parity: %d envs x %d env.steps, %d records; max |dqpos| %.3e, max |dqvel| %.3e, max |dobs| %.3e; "
+          "max |dqpos| after 1 / 75 / 250 env.steps: %.3e / %.3e / %.3e; counters %s"
+          % (nsub, horizon, n_rec, worst_q, worst_v, worst_obs, err_at[1], err_at[75], err_at[250], {k: c[k] for k in ("mp", "rl", "interpolation", "mp_fail", "reused", "fb_simple", "fb_main", "unstable")}))
+    assert worst_q < 1e-5 and worst_v < 1e-5, sorted(per_env, key=lambda x: -x[1])[:5]
+    assert worst_obs < 1e-4
+
+
+def test_single_substep_matches_oracle(push_model, oracle_built):
+    """One mj_step (frame_dt = timestep): the '1 substep' point of BASELINE.md section 3, 256 envs."""
+    import torch
+
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerPushObstacle, push_reset_state
+    from oracle.env_oracle import PushEnvOracle
+
+    n = 256
+    venv = VecSawyerPushObstacle(n, seed=5, frame_dt=0.002)
+    venv.reset()
+    dm = DynModel(push_model)
+    q0, v0 = push_reset_state(push_model, 5, np.arange(n), np.zeros(n, dtype=np.int64))
+    act = np.random.default_rng(1).uniform(-1, 1, (n, 8)).astype(np.float32)
+    venv.step(torch.as_tensor(act, device="cuda"))
+    torch.cuda.synchronize()
+    gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
+    worst = 0.0
+    for i in range(n):
+        e = PushEnvOracle(push_model, dm, frame_dt=0.002)
+        e.reset_to(q0[i], v0[i])
+        e.step(act[i].astype(np.float64), False)
+        worst = max(worst, np.abs(gq[i] - e.qpos).max(), np.abs(gv[i] - e.qvel).max())
+    print("one substep, %d envs: max |dq|, |dv| = %.3e" % (n, worst))
+    assert worst < 1e-9
+
+
+def test_million_states_bit_exact_and_f64_flips(push_model, oracle_built):
+    """>= 10^6 validity queries: words bit-identical to the f32 oracle; against the f64 oracle (the
+    reference computes in double) the number of flipped booleans is counted and bounded."""
+    import threading
+
+    from mopa_rl_b200.capi import NativePlanner
+
+    ignored, passive, ref = planner_setup(push_model)
+    native = NativePlanner(push_model, passive, ignored, -0.002, 0.1, seed=1234)
+    n = 1_048_576
+    q = random_qpos(push_model, n, 4242, ref)
+    _, w = native.is_valid_host(q, flags=1, return_words=True)
+    threads = min(os.cpu_count() or 1, 32)
+    parts = np.array_split(np.arange(n), threads)
+    out32, out64 = [None] * threads, [None] * threads
+
+    def work(i):
+        out32[i] = oracle_built.OracleScene(push_model, ignored, -0.002, "f32").is_valid(q[parts[i]])
+        out64[i] = oracle_built.OracleScene(push_model, ignored, -0.002, "f64").is_valid(q[parts[i]])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    o32, o64 = np.concatenate(out32), np.concatenate(out64)
+    assert np.array_equal(w, o32), "%d of %d words differ from the f32 oracle" % ((w != o32).sum(), n)
+    flips = int(((w & 1) != (o64 & 1)).sum())
+    print("validity: %d states, valid fraction %.4f, f32 words bit-exact, booleans flipped against the f64 oracle: %d" % (n, (w & 1).mean(), flips))
+    assert flips <= 8, flips   # states within fp32 rounding of the contact threshold
+
+
+# ----------------------------------------------------------------------------- oracle-independent physics invariants
+def _cube_env(n, push_model, **kw):
+    import torch
+
+    from mopa_rl_b200.envs import VecSawyerPushObstacle
+
+    venv = VecSawyerPushObstacle(n, seed=1, max_episode_steps=10 ** 6, **kw)
+    venv.reset()
+    a = push_model.get_joint_qpos_addr("cube")[0]
+    va = push_model.get_joint_qvel_addr("cube")[0]
+    return venv, a, va, torch
+
+
+def test_free_fall_is_the_semi_implicit_euler_parabola(push_model):
+    """A cube released in mid air: v_k = -g h k, z_k = z0 - g h^2 k (k + 1) / 2 exactly (semi-implicit Euler); the
+    quaternion of a torque-free spinning cube keeps |q| = 1 and, for a cube (isotropic inertia), a constant spin."""
+    venv, a, va, torch = _cube_env(4, push_model)
+    q, v = venv.qpos.clone(), venv.qvel.clone()
+    z0 = 1.6
+    q[:, a:a + 3] = torch.tensor([0.6, 0.3, z0], dtype=torch.float64, device=venv.dev)
+    w0 = torch.tensor([[0, 0, 0], [3.0, 0, 0], [1.0, -2.0, 0.5], [0, 0, 7.0]], dtype=torch.float64, device=venv.dev)
+    v[:, va + 3:va + 6] = w0
+    venv.set_state(np.arange(4), q.cpu().numpy(), v.cpu().numpy())
+    h, g, nsub = 0.002, 9.81, 75
+    for step in range(1, 3):
+        venv.step(torch.zeros(4, 8, device=venv.dev))
+        torch.cuda.synchronize()
+        k = nsub * step
+        z = venv.qpos[:, a + 2].cpu().numpy()
+        vz = venv.qvel[:, va + 2].cpu().numpy()
+        assert np.abs(vz + g * h * k).max() < 1e-9, vz
+        assert np.abs(z - (z0 - g * h * h * k * (k + 1) / 2)).max() < 1e-9, z
+        quat = venv.qpos[:, a + 3:a + 7].cpu().numpy()
+        assert np.abs(np.linalg.norm(quat, axis=1) - 1).max() < 1e-12
+        w = venv.qvel[:, va + 3:va + 6].cpu().numpy()
+        assert np.abs(w - w0.cpu().numpy()).max() < 1e-9, w           # isotropic inertia: no precession, no damping on the free joint
+        assert np.abs(venv.qvel[:, va:va + 2].cpu().numpy()).max() < 1e-12
+    assert int(venv.ncon.max()) == 0
+
+
+def test_resting_cube_is_carried_by_its_weight(push_model):
+    """Static equilibrium on the bin floor: contact complementarity (no penetration velocity, contacts active) and the
+    sum of the normal forces = m g; friction idle."""
+    venv, a, va, torch = _cube_env(8, push_model)
+    for _ in range(6):                                   # let the soft contact settle (0.9 s)
+        venv.step(torch.zeros(8, 8, device=venv.dev))
+    torch.cuda.synchronize()
+    weight = float(push_model.body_mass[push_model.body_name2id("cube")]) * 9.81
+    cf = venv.cforce.cpu().numpy()
+    assert int(venv.ncon.min()) >= 1
+    assert np.abs(venv.qvel[:, va:va + 6].cpu().numpy()).max() < 1e-6
+    assert np.abs(cf - weight).max() < 1e-3 * weight, (cf, weight)
+
+
+def test_sliding_cube_decelerates_at_mu_g(push_model):
+    """Coulomb friction: a cube sliding on the bin floor loses speed at mu g while it slides (mu = max of the two geoms'
+    friction coefficients, as MuJoCo combines them)."""
+    venv, a, va, torch = _cube_env(2, push_model, frame_dt=0.05)   # 25 mj_steps per env.step
+    for _ in range(20):
+        venv.step(torch.zeros(2, 8, device=venv.dev))
+    v = venv.qvel.clone()
+    v0 = 1.0
+    v[0, va] = v0                                        # env 0 slides along x, env 1 stays
+    venv.set_state(np.arange(2), venv.qpos.cpu().numpy(), v.cpu().numpy())
+    venv.step(torch.zeros(2, 8, device=venv.dev))
+    torch.cuda.synchronize()
+    gi = push_model.geom_name2id("cube")
+    floor_mu = max(float(push_model.geom_friction[g][0]) for g in range(push_model.ngeom) if push_model.names["body"][push_model.geom_bodyid[g]] == "bin1")
+    mu = max(float(push_model.geom_friction[gi][0]), floor_mu)
+    vx = float(venv.qvel[0, va])
+    expect = v0 - mu * 9.81 * 0.05
+    print("sliding cube: v after 0.05 s = %.4f, Coulomb prediction %.4f (mu = %.2f)" % (vx, expect, mu))
+    assert abs(vx - expect) < 0.05 * v0, (vx, expect, mu)
+    assert abs(float(venv.qvel[1, va])) < 1e-6
