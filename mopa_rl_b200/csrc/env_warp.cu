@@ -893,16 +893,45 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
             }
             __syncwarp();
         };
-        // warm start: the previous substep's acceleration when there is one (the oracle, like MuJoCo, first
-        // compares its cost with the unconstrained acceleration's; the minimiser is the same either way).
-        // One evaluation site; the Hessian is only assembled once it is known that a Newton step follows.
-        if (lane < nd) W.a[lane] = W.wn ? W.wa[lane] : W.qacc0[lane];
-        __syncwarp();
+        // warm start (mj_solNewton / mj_warmstart): the previous substep's acceleration unless the unconstrained one costs
+        // less.  Both candidates converge to the same minimiser, but only to within the solver tolerance: starting where
+        // the reference starts keeps kernel and oracle on the same iteration path over long horizons.
+        // The Hessian is only assembled once it is known that a Newton step follows.
+        bool have_eval = false;
+        if (W.wn) {
+            // cost at the unconstrained acceleration, cheaply: M qacc0 = tau, so only the constraint penalties remain
+            double xq = 0;
+            if (r < nc) {
+                double xb = 0;
+                for (int k = 0; k + 1 < nd; k += 2) { xq += W.Y[r * YS + k] * W.qacc0[k]; xb += W.Y[r * YS + k + 1] * W.qacc0[k + 1]; }
+                if (nd & 1) xq += W.Y[r * YS + nd - 1] * W.qacc0[nd - 1];
+                xq = (xq + xb) - aref;
+            }
+            const double q0 = shfl_d(xq, base & 31), q1 = shfl_d(xq, (base + 1) & 31), q2 = shfl_d(xq, (base + 2) & 31);
+            double sc0 = 0;
+            if (type == 0) { if (xq < 0) sc0 = 0.5 * Dr * xq * xq; }
+            else if (type == 1) {
+                const double t = sqrt(q1 * q1 + q2 * q2);
+                if (q0 >= mu * t) { }
+                else if (mu * q0 + t <= 0) sc0 = 0.5 * Dr * (q0 * q0 + q1 * q1 + q2 * q2);
+                else { const double e = q0 - mu * t; sc0 = 0.5 * Dm * e * e; }
+            }
+            const double c0 = warp_sum(sc0);
+            if (lane < nd) W.a[lane] = W.wa[lane];
+            __syncwarp();
+            newton_eval();
+            if (cost < c0) have_eval = true;
+            else { if (lane < nd) W.a[lane] = W.qacc0[lane]; __syncwarp(); }
+        } else {
+            if (lane < nd) W.a[lane] = W.qacc0[lane];
+            __syncwarp();
+        }
         int it = 0;
         bool first = true;
         double old = 0;
         for (;;) {
-            newton_eval();
+            if (!have_eval) newton_eval();
+            have_eval = false;
             if (!first && scale * (old - cost) < m.tolerance) break;
             first = false;
             if (it++ >= m.iterations) break;

@@ -751,7 +751,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     }
     mopa_rollout *r = new mopa_rollout();
     r->env = env; r->planner = planner; r->buf = *buf; r->max_iter = cfg->max_iter;
-    r->simple_max_iter = cfg->simple_max_iter > 0 ? cfg->simple_max_iter : 1;
+    r->simple_max_iter = cfg->simple_max_iter > 0 ? cfg->simple_max_iter : 0;   // 0: the simple planner gives up at once (tests of the main-planner retry)
     r->simple_range = (float)cfg->simple_planner_range;
     if (const char *w = getenv("MOPA_PLAN_CTA_WARPS")) r->plan_cta_warps = atoi(w);
     RoDev &S = r->S;

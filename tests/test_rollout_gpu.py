@@ -281,7 +281,8 @@ def test_native_runner_lift_matches_scalar_reference_loop(oracle_built):
     print("lift: native vs scalar runner: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
 
 
-def test_blocked_hops_go_through_the_simple_and_the_main_planner(push_model, oracle_built):
+@pytest.mark.parametrize("simple_max_iter", [3, 0], ids=["simple-planner", "main-planner-retry"])
+def test_blocked_hops_go_through_the_simple_and_the_main_planner(push_model, oracle_built, simple_max_iter):
     """SACAgent.simple_interpolate(use_planner=True) (rl/sac_agent.py:300-311): a densification hop whose interior is blocked is
     re-planned with the simple planner (range 0.05), then with the main planner, else only its end point is kept.  Such hops
     are rare (~0.3 % of the RRT plans), so the test hook `debug_block_mod` forces every third hop down that path, in the
@@ -295,8 +296,8 @@ def test_blocked_hops_go_through_the_simple_and_the_main_planner(push_model, ora
     from oracle.rollout_oracle import ScalarMoPARunner
 
     n, ticks, seed = 256, 60, 811
-    # simple_max_iter = 3: some hops are solved by the simple planner, the others need the main one
-    cfg = MoPAConfig(max_iter=150, seed=41, debug_block_mod=3, simple_max_iter=3)
+    # simple_max_iter = 3: the simple planner (range 0.05) solves the hops; 0: it gives up at once and the main planner is retried
+    cfg = MoPAConfig(max_iter=150, seed=41, debug_block_mod=3, simple_max_iter=simple_max_iter)
     venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=40, env_id_offset=500)
     runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, 29))
     for _ in range(ticks):
@@ -305,7 +306,7 @@ def test_blocked_hops_go_through_the_simple_and_the_main_planner(push_model, ora
     torch.cuda.synchronize()
     c = runner.counters
     rec = runner.transitions[:c["transitions"]].cpu().numpy()
-    assert c["fb_simple"] > 0 and c["fb_simple"] + c["fb_main"] + c["densify_fallback"] >= 5, c
+    assert c["fb_simple" if simple_max_iter else "fb_main"] >= 5 and c["fb_main" if simple_max_iter else "fb_simple"] == 0, c
 
     def policy(gid, k):
         u = rng.uniform01(29, np.uint64(gid), np.uint64(k), np.arange(7, dtype=np.uint64))

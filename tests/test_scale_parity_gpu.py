@@ -202,31 +202,43 @@ def _cube_env(n, push_model, **kw):
     return venv, a, va, torch
 
 
-def test_free_fall_is_the_semi_implicit_euler_parabola(push_model):
-    """A cube released in mid air: v_k = -g h k, z_k = z0 - g h^2 k (k + 1) / 2 exactly (semi-implicit Euler); the
-    quaternion of a torque-free spinning cube keeps |q| = 1 and, for a cube (isotropic inertia), a constant spin."""
+# constants read by hand from env/assets/xml/sawyer_push_obstacle.xml:46-48 (not through mjcf.py / dynmodel.py):
+#   <geom name="cube" type="box" size="0.03 0.03 0.03" density="300" friction="0.95 ..."/>  <joint name="cube" type="free" damping="0.0005"/>
+CUBE_MASS = 300.0 * 0.06 ** 3
+CUBE_INERTIA = CUBE_MASS * 0.06 ** 2 / 6.0
+CUBE_DAMPING = 0.0005
+
+
+def test_free_fall_is_the_semi_implicit_euler_recurrence(push_model):
+    """A cube released in mid air.  mj_Euler with implicit joint damping: (m + h d) v' = m v - h m g, z' = z + h v' - the closed
+    recurrence is evaluated here from the XML's numbers; a torque-free spinning cube (isotropic inertia: no precession)
+    keeps its axis, loses spin at I / (I + h d) per step, and its quaternion stays normalised."""
     venv, a, va, torch = _cube_env(4, push_model)
     q, v = venv.qpos.clone(), venv.qvel.clone()
     z0 = 1.6
     q[:, a:a + 3] = torch.tensor([0.6, 0.3, z0], dtype=torch.float64, device=venv.dev)
-    w0 = torch.tensor([[0, 0, 0], [3.0, 0, 0], [1.0, -2.0, 0.5], [0, 0, 7.0]], dtype=torch.float64, device=venv.dev)
-    v[:, va + 3:va + 6] = w0
+    w0 = np.array([[0, 0, 0], [3.0, 0, 0], [1.0, -2.0, 0.5], [0, 0, 7.0]])
+    v[:, va + 3:va + 6] = torch.as_tensor(w0, device=venv.dev)
     venv.set_state(np.arange(4), q.cpu().numpy(), v.cpu().numpy())
     h, g, nsub = 0.002, 9.81, 75
+    z, vz, spin = z0, 0.0, 1.0
     for step in range(1, 3):
         venv.step(torch.zeros(4, 8, device=venv.dev))
         torch.cuda.synchronize()
-        k = nsub * step
-        z = venv.qpos[:, a + 2].cpu().numpy()
-        vz = venv.qvel[:, va + 2].cpu().numpy()
-        assert np.abs(vz + g * h * k).max() < 1e-9, vz
-        assert np.abs(z - (z0 - g * h * h * k * (k + 1) / 2)).max() < 1e-9, z
+        for _ in range(nsub):
+            vz = (CUBE_MASS * vz - h * CUBE_MASS * g) / (CUBE_MASS + h * CUBE_DAMPING)
+            z += h * vz
+            spin *= CUBE_INERTIA / (CUBE_INERTIA + h * CUBE_DAMPING)
+        gz, gvz = venv.qpos[:, a + 2].cpu().numpy(), venv.qvel[:, va + 2].cpu().numpy()
+        assert np.abs(gvz - vz).max() < 1e-10, (gvz, vz)
+        assert np.abs(gz - z).max() < 1e-10, (gz, z)
         quat = venv.qpos[:, a + 3:a + 7].cpu().numpy()
         assert np.abs(np.linalg.norm(quat, axis=1) - 1).max() < 1e-12
         w = venv.qvel[:, va + 3:va + 6].cpu().numpy()
-        assert np.abs(w - w0.cpu().numpy()).max() < 1e-9, w           # isotropic inertia: no precession, no damping on the free joint
+        assert np.abs(w - spin * w0).max() < 1e-9, (w, spin * w0)
         assert np.abs(venv.qvel[:, va:va + 2].cpu().numpy()).max() < 1e-12
     assert int(venv.ncon.max()) == 0
+    print("free fall: z, vz after 150 mj_steps match the closed recurrence to %.1e / %.1e" % (np.abs(gz - z).max(), np.abs(gvz - vz).max()))
 
 
 def test_resting_cube_is_carried_by_its_weight(push_model):
@@ -236,7 +248,7 @@ def test_resting_cube_is_carried_by_its_weight(push_model):
     for _ in range(6):                                   # let the soft contact settle (0.9 s)
         venv.step(torch.zeros(8, 8, device=venv.dev))
     torch.cuda.synchronize()
-    weight = float(push_model.body_mass[push_model.body_name2id("cube")]) * 9.81
+    weight = CUBE_MASS * 9.81
     cf = venv.cforce.cpu().numpy()
     assert int(venv.ncon.min()) >= 1
     assert np.abs(venv.qvel[:, va:va + 6].cpu().numpy()).max() < 1e-6
@@ -244,8 +256,8 @@ def test_resting_cube_is_carried_by_its_weight(push_model):
 
 
 def test_sliding_cube_decelerates_at_mu_g(push_model):
-    """Coulomb friction: a cube sliding on the bin floor loses speed at mu g while it slides (mu = max of the two geoms'
-    friction coefficients, as MuJoCo combines them)."""
+    """Coulomb friction: a cube sliding on the bin floor loses speed at about mu g while it slides (mu = max of the two
+    geoms' friction coefficients, as MuJoCo combines them)."""
     venv, a, va, torch = _cube_env(2, push_model, frame_dt=0.05)   # 25 mj_steps per env.step
     for _ in range(20):
         venv.step(torch.zeros(2, 8, device=venv.dev))
@@ -255,11 +267,11 @@ def test_sliding_cube_decelerates_at_mu_g(push_model):
     venv.set_state(np.arange(2), venv.qpos.cpu().numpy(), v.cpu().numpy())
     venv.step(torch.zeros(2, 8, device=venv.dev))
     torch.cuda.synchronize()
-    gi = push_model.geom_name2id("cube")
-    floor_mu = max(float(push_model.geom_friction[g][0]) for g in range(push_model.ngeom) if push_model.names["body"][push_model.geom_bodyid[g]] == "bin1")
-    mu = max(float(push_model.geom_friction[gi][0]), floor_mu)
+    mu = 1.0   # max(cube 0.95, bin floor 1.0 - MuJoCo's default friction, the bin geoms set none)
     vx = float(venv.qvel[0, va])
-    expect = v0 - mu * 9.81 * 0.05
-    print("sliding cube: v after 0.05 s = %.4f, Coulomb prediction %.4f (mu = %.2f)" % (vx, expect, mu))
-    assert abs(vx - expect) < 0.05 * v0, (vx, expect, mu)
+    decel = (v0 - vx) / 0.05
+    print("sliding cube: v after 0.05 s = %.4f, deceleration %.2f m/s^2 (Coulomb: mu g = %.2f)" % (vx, decel, mu * 9.81))
+    # mu = 1 on a cube is the tipping limit (friction torque = restoring torque): the load shifts to the leading edge and the
+    # normal force overshoots m g while the cube pitches, so the deceleration is only required to be mu g within 25 %
+    assert 0.75 * mu * 9.81 < decel < 1.25 * mu * 9.81, (vx, decel)
     assert abs(float(venv.qvel[1, va])) < 1e-6
