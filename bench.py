@@ -385,7 +385,7 @@ def ncu_pipe(name):
     try:
         with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
-        return {k: d[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct") if k in d} or None
+        return {k: d[k] for k in ("fp64_pipe_pct", "fp32_issue_frac", "issue_active_pct", "threads_per_instruction", "warps_active_pct") if k in d} or None
     except Exception:
         return None
 
@@ -473,8 +473,10 @@ def run_validity(args):
                     "api": "mopa_is_valid_host_f32 (pinned host rows in, result words out)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r1_validity_v4_traffic.json") if args.task == "push" else None),
-                         "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query},
+                         "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r2_validity_traffic.json") if args.task == "push" else None),
+                         "peak_source": peak_kind, "kernel": "is_valid_kernel", "algorithmic_bytes_per_query": bytes_per_query,
+                         "second_bound": ncu_pipe("r2_validity_traffic.json") if args.task == "push" else None,
+                         "note": "FP32 issue / latency bound, not HBM bound: second_bound.fp32_issue_frac = issue-active x active lanes / 32 from the committed ncu capture"},
             "cpu_baseline": {"value": rate, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": "%d of the same queries, one oracle scene per host thread" % ns, "gpu_bit_mismatches": mism}}))
     if world > 1:

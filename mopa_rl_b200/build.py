@@ -40,6 +40,8 @@ def build(force=False, verbose=False):
         flags = [f for f in NVCC_FLAGS if f not in ("--shared",)]
         if src in FMAD_ON and os.environ.get("MOPA_ENV_FMAD", "1") != "0":
             flags = [f for f in flags if f != "-fmad=false"]
+        if os.environ.get("MOPA_EXTRA_NVCC"):   # diagnostics builds, e.g. MOPA_EXTRA_NVCC=-DMOPA_VK_STATS
+            flags += os.environ["MOPA_EXTRA_NVCC"].split()
         if src in FMAD_ON and os.environ.get("MOPA_ENV_MAXREG"):
             flags += ["-maxrregcount=" + os.environ["MOPA_ENV_MAXREG"]]
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

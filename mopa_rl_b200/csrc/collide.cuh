@@ -315,6 +315,114 @@ MOPA_HD bool mpr_penetration(const Geom &g1, const Geom &g2, float *depth) {
     }
 }
 
+// The same routine as a resumable state machine: one Minkowski support evaluation per trip, then the bookkeeping of the
+// phase the item is in.  Every arithmetic expression is the one mpr_penetration evaluates, in the same order, so the
+// verdict and the depth are bit-identical; only the control flow is unrolled so that the lanes of a warp can work on
+// different items that are at different iterations (the iteration count has a heavy tail: most items finish within a
+// few trips, a few run to MPR_MAXIT) and pick up a new item as soon as theirs is finished.
+enum { MPR_RUNNING = 0, MPR_SEPARATE = 1, MPR_PENETRATING = 2 };
+struct MprSM {
+    V3 v0, v1, v2, v3, dir;
+    int phase, it;   // phase 0..3: the support point being computed is v1 / v2 / v3 (portal discovery) / v4 (refinement)
+    bool inside;
+};
+MOPA_HD void mpr_begin(MprSM &m, const Geom &g1, const Geom &g2) {
+    m.v0 = g1.c - g2.c;
+    if (m.v0.x == 0 && m.v0.y == 0 && m.v0.z == 0) m.v0.x = MPR_EPS * 10.0f;
+    m.dir = neg(m.v0);
+    normalize(m.dir);
+    m.phase = 0; m.it = 0; m.inside = false;
+    m.v1 = m.v2 = m.v3 = V3{0, 0, 0};
+}
+MOPA_HD void mpr_refine_dir(MprSM &m) {   // head of a refinement iteration: portal normal, inside test
+    m.dir = cross(m.v2 - m.v1, m.v3 - m.v1);
+    normalize(m.dir);
+    if (!m.inside) {
+        const float d = dot(m.dir, m.v1);
+        if (is_zero(d) || d > 0) m.inside = true;
+    }
+}
+template <bool MESH>
+MOPA_HD int mpr_trip(MprSM &m, const Geom &g1, const Geom &g2, float *depth) {
+    const V3 s = msupport<MESH>(g1, g2, m.dir);
+    float d;
+    if (m.phase == 0) {
+        m.v1 = s;
+        d = dot(m.v1, m.dir);
+        if (is_zero(d) || d < 0) return MPR_SEPARATE;
+        m.dir = cross(m.v0, m.v1);
+        if (is_zero(dot(m.dir, m.dir))) {
+            *depth = (m.v1.x == 0 && m.v1.y == 0 && m.v1.z == 0) ? 0.0f : len(m.v1);
+            return MPR_PENETRATING;
+        }
+        normalize(m.dir);
+        m.phase = 1;
+        return MPR_RUNNING;
+    }
+    if (m.phase == 1) {
+        m.v2 = s;
+        d = dot(m.v2, m.dir);
+        if (is_zero(d) || d < 0) return MPR_SEPARATE;
+        m.dir = cross(m.v1 - m.v0, m.v2 - m.v0);
+        normalize(m.dir);
+        d = dot(m.dir, m.v0);
+        if (d > 0) {
+            const V3 t = m.v1; m.v1 = m.v2; m.v2 = t;
+            m.dir = neg(m.dir);
+        }
+        m.it = 0;
+        m.phase = 2;
+        return MPR_RUNNING;
+    }
+    if (m.phase == 2) {
+        if (++m.it > MPR_MAXIT) return MPR_SEPARATE;
+        m.v3 = s;
+        d = dot(m.v3, m.dir);
+        if (is_zero(d) || d < 0) return MPR_SEPARATE;
+        bool cont = false;
+        V3 va = cross(m.v1, m.v3);
+        d = dot(va, m.v0);
+        if (d < 0 && !is_zero(d)) { m.v2 = m.v3; cont = true; }
+        if (!cont) {
+            va = cross(m.v3, m.v2);
+            d = dot(va, m.v0);
+            if (d < 0 && !is_zero(d)) { m.v1 = m.v3; cont = true; }
+        }
+        if (cont) {
+            m.dir = cross(m.v1 - m.v0, m.v2 - m.v0);
+            normalize(m.dir);
+            return MPR_RUNNING;
+        }
+        m.inside = false;
+        m.it = 0;
+        m.phase = 3;
+        mpr_refine_dir(m);
+        return MPR_RUNNING;
+    }
+    const V3 v4 = s;
+    const float dv4 = dot(v4, m.dir);
+    const float dmin = fminf(dv4 - dot(m.v1, m.dir), fminf(dv4 - dot(m.v2, m.dir), dv4 - dot(m.v3, m.dir)));
+    const bool reached = (dmin <= MPR_TOL);
+    if (!m.inside) {
+        if (!(is_zero(dv4) || dv4 > 0) || reached || m.it >= MPR_MAXIT) return MPR_SEPARATE;
+    } else if (reached || m.it >= MPR_MAXIT) {
+        *depth = sqrtf(origin_tri_dist2(m.v1, m.v2, m.v3));
+        return MPR_PENETRATING;
+    }
+    const V3 va = cross(v4, m.v0);
+    d = dot(m.v1, va);
+    if (d > 0) {
+        d = dot(m.v2, va);
+        if (d > 0) m.v1 = v4; else m.v3 = v4;
+    } else {
+        d = dot(m.v3, va);
+        if (d > 0) m.v2 = v4; else m.v1 = v4;
+    }
+    m.it++;
+    mpr_refine_dir(m);
+    return MPR_RUNNING;
+}
+
 // Conservative pre-test for the pairs that go to MPR (capsule / cylinder against capsule / cylinder / box): true when
 // the shapes are certainly more than 1e-4 apart, in which case MPR cannot report a penetration at all (the validity
 // predicate needs dist <= contact_threshold <= 0).  A cylinder lies inside the capsule with the same axis, radius and

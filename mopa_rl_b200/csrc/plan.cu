@@ -152,18 +152,7 @@ __device__ __forceinline__ bool states_all_valid(const WarpCtx &W, const SpaceDe
         if (i < total) {
             const int k = i / npair, p = i - k * npair;
             const PairRec pr = W.S.pairs[p];
-            bool survive = true;
-            if (pr.bound2 >= 0.0f) {
-                const float *fa = W.frames + (size_t)pr.anchor_slot * PW_STATES + k;
-                V3 ac{fa[0], fa[PW_STATES], fa[2 * PW_STATES]};
-                V3 pc{pr.px, pr.py, pr.pz};
-                if (pr.partner_slot != 0xFFFF) {
-                    const float *fp = W.frames + (size_t)pr.partner_slot * PW_STATES + k;
-                    pc = V3{fp[0], fp[PW_STATES], fp[2 * PW_STATES]};
-                }
-                V3 d = pc - ac;
-                survive = !(dot(d, d) > pr.bound2);
-            }
+            const bool survive = cull_survives(pr, W.S.cull[p], W.frames, PW_STATES, k);
             if (survive && pr.cls <= PC_MPR) {
                 Geom a, b;
                 load_geom<MESH>(a, W.S.recs[pr.ga], W.frames, PW_STATES, k);

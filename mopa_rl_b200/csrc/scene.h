@@ -51,16 +51,26 @@ struct GeomRec {  // every collidable geom that appears in at least one candidat
     int geom_id;     // mjModel geom id
     int pad;
 };
-struct PairRec {  // 32 bytes; candidate pair in kernel order (grouped by anchor = first moving geom)
-    float px, py, pz;   // centre of the partner when it is static
-    float bound2;       // squared bounding-sphere cull distance; < 0: no sphere test (plane pair)
+// Candidate pairs, in kernel order: sorted by the kind of cull test, then by anchor (the first moving geom); runs are padded
+// to multiples of four with dummy pairs (cls = PC_NONE) that never survive the cull.  Two parallel arrays, 16 bytes per pair each: what the narrow
+// phase needs (PairRec) and what the cull sweep needs (CullEntry); runs of pairs with the same (cull kind, anchor) are
+// described by CullGroup records so that the sweep loads the anchor centre once per run and has branch-free inner loops.
+struct PairRec {
     uint16_t anchor_slot, partner_slot;  // frame-store offsets; partner_slot == 0xFFFF: static partner
     uint16_t ga, gb;    // GeomRec indices, kind(ga) <= kind(gb)  (the order the narrowphase expects)
     uint16_t canon;     // index in the canonical (g1<g2 lexicographic) candidate list
     uint8_t cls;        // PairClass
-    uint8_t flags;
+    uint8_t ckind;      // CullKind
     uint32_t pad;
 };
+enum CullKind : int {
+    CK_SPHERE_STATIC = 0,   // e = (partner centre, squared cull distance): cull when |centre - anchor centre|^2 > e.w
+    CK_SPHERE_MOVING = 1,   // e.x = int bits of the partner's frame-store offset, e.w = squared cull distance
+    CK_PLANE = 2,           // e = (unit normal of the static plane, offset): cull when dot(normal, anchor centre) > e.w
+    CK_NONE = 3             // always passed to the narrow phase
+};
+struct CullEntry { float x, y, z, w; };
+struct CullGroup { uint16_t anchor_slot, kind, count, pad; };
 
 struct SceneHeader {
     int nq, nq4;             // qpos row length, and in float4 units (row stride = 4*nq4 floats)
@@ -72,6 +82,7 @@ struct SceneHeader {
     int blob_bytes;
     int off_hull;            // hull vertices of collision meshes (float xyz triplets)
     int n_hull_vert;
+    int off_cull, off_group, n_group;   // CullEntry[n_pair] (parallel to the pair records), CullGroup[n_group]
 };
 
 struct HostScene {

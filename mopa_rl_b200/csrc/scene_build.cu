@@ -220,39 +220,79 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
         rec_of_geom[g] = (int)recs.size();
         recs.push_back(Rr);
     }
-    // ---- pair records
-    std::vector<PairRec> pairs;
+    // ---- pair records + cull entries
+    struct PairBuild { PairRec P; CullEntry E; int list; };
+    std::vector<PairBuild> pb;
     for (int p = 0; p < npair; p++) {
         int g1 = out.canon_g1[p], g2 = out.canon_g2[p];
         if (d->geom_type[g1] > d->geom_type[g2]) std::swap(g1, g2);  // lower mjtGeom first, ties keep g1<g2
         const GeomRec &A = recs[rec_of_geom[g1]], &B = recs[rec_of_geom[g2]];
-        PairRec P;
-        memset(&P, 0, sizeof(P));
+        PairBuild X;
+        memset(&X, 0, sizeof(X));
+        PairRec &P = X.P;
+        CullEntry &E = X.E;
         P.ga = (uint16_t)rec_of_geom[g1];
         P.gb = (uint16_t)rec_of_geom[g2];
         P.canon = (uint16_t)p;
         P.cls = (uint8_t)pair_class(A.kind, B.kind);
+        X.list = P.cls < PC_BOX_BOX ? 0 : (P.cls == PC_BOX_BOX ? 1 : (P.cls == PC_MPR ? 2 : 3));
         float margin = fmaxf((float)d->geom_margin[g1], (float)d->geom_margin[g2]);
-        if (A.kind == K_PLANE) P.bound2 = -1.0f;
-        else {
-            float bound = (A.rbound + B.rbound) + margin;
-            P.bound2 = bound * bound;
-        }
         const GeomRec *anchor = &A, *partner = &B;
         if (A.slot < 0 || (B.slot >= 0 && B.geom_id < A.geom_id)) { anchor = &B; partner = &A; }
         if (anchor->slot < 0) throw std::runtime_error("candidate pair without a moving geom");
         P.anchor_slot = (uint16_t)anchor->slot;
-        if (partner->slot < 0) {
-            P.partner_slot = 0xFFFF;
-            P.px = partner->px; P.py = partner->py; P.pz = partner->pz;
-        } else
-            P.partner_slot = (uint16_t)partner->slot;
-        pairs.push_back(P);
+        P.partner_slot = partner->slot < 0 ? 0xFFFF : (uint16_t)partner->slot;
+        if (A.kind == K_PLANE) {
+            P.ckind = CK_NONE;
+            if (A.slot < 0 && anchor == &B) {
+                // static plane against a moving geom: nothing of the geom is closer to the plane than its centre height minus
+                // its bounding radius.  The kernels skip the pair when that lower bound is clearly positive (1e-4 of slack
+                // against rounding; the validity predicate needs dist <= contact_threshold).  Conservative: never changes a result.
+                const V3 nrm{A.m[2], A.m[5], A.m[8]};
+                E.x = nrm.x; E.y = nrm.y; E.z = nrm.z;
+                E.w = dot(nrm, V3{A.px, A.py, A.pz}) + B.rbound + 1e-4f + fmaxf((float)threshold, 0.0f);
+                P.ckind = CK_PLANE;
+            }
+        } else {   // bounding spheres + margin, exactly MuJoCo's (and the oracle's) filter
+            float bound = (A.rbound + B.rbound) + margin;
+            E.w = bound * bound;
+            if (partner->slot < 0) { P.ckind = CK_SPHERE_STATIC; E.x = partner->px; E.y = partner->py; E.z = partner->pz; }
+            else { P.ckind = CK_SPHERE_MOVING; const int off = partner->slot; memcpy(&E.x, &off, 4); }
+        }
+        if (X.list < 3) pb.push_back(X);   // pairs of classes the narrow phase does not know never collide (PC_NONE)
     }
-    std::stable_sort(pairs.begin(), pairs.end(), [](const PairRec &a, const PairRec &b) {
-        if (a.anchor_slot != b.anchor_slot) return a.anchor_slot < b.anchor_slot;
-        return a.canon < b.canon;
+    // kernel order: runs of (cull kind, anchor); every run is padded to a multiple of four entries with dummy pairs that never
+    // survive the cull (the sweep tests four entries per trip without bounds checks)
+    std::stable_sort(pb.begin(), pb.end(), [](const PairBuild &a, const PairBuild &b) {
+        if (a.P.ckind != b.P.ckind) return a.P.ckind < b.P.ckind;
+        if (a.P.anchor_slot != b.P.anchor_slot) return a.P.anchor_slot < b.P.anchor_slot;
+        return a.P.canon < b.P.canon;
     });
+    std::vector<PairRec> pairs;
+    std::vector<CullEntry> cull;
+    std::vector<CullGroup> groups;
+    auto pad_group = [&]() {
+        if (groups.empty() || groups.back().kind == CK_NONE) return;
+        while (groups.back().count % 4) {
+            PairRec D;
+            memset(&D, 0, sizeof(D));
+            D.cls = PC_NONE; D.ckind = (uint8_t)groups.back().kind; D.anchor_slot = groups.back().anchor_slot; D.partner_slot = groups.back().anchor_slot;
+            D.canon = 0xFFFF;
+            CullEntry E{0.0f, 0.0f, 0.0f, -1.0f};   // |d|^2 > -1 and 0 > -1: culled by every kind of test
+            if (groups.back().kind == CK_SPHERE_MOVING) { const int off = groups.back().anchor_slot; memcpy(&E.x, &off, 4); }
+            pairs.push_back(D); cull.push_back(E);
+            groups.back().count++;
+        }
+    };
+    for (size_t i = 0; i < pb.size(); i++) {
+        const bool fresh = i == 0 || pb[i].P.ckind != pb[i - 1].P.ckind || pb[i].P.anchor_slot != pb[i - 1].P.anchor_slot;
+        if (fresh) { pad_group(); groups.push_back(CullGroup{pb[i].P.anchor_slot, pb[i].P.ckind, 0, 0}); }
+        pairs.push_back(pb[i].P);
+        cull.push_back(pb[i].E);
+        groups.back().count++;
+    }
+    pad_group();
+    if (pairs.size() >= 65535) throw std::runtime_error("too many candidate pairs");
 
     // ---- pack
     SceneHeader H;
@@ -270,6 +310,9 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     H.off_const = append(blob, consts);
     H.off_rec = append(blob, recs);
     H.off_pair = append(blob, pairs);
+    H.off_cull = append(blob, cull);
+    H.off_group = append(blob, groups);
+    H.n_group = (int)groups.size();
     std::vector<float> hull(3 * (size_t)d->nmeshvert);
     for (size_t k = 0; k < hull.size(); k++) hull[k] = (float)d->mesh_vert[k];
     H.off_hull = append(blob, hull);

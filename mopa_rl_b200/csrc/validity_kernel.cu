@@ -1,14 +1,11 @@
-// mopa_is_valid_batch: batched state-validity checks on sm_100a.
-//
-// Layout per CTA (NQ threads = NQ queries per tile, persistent over tiles):
-//   shared: [scene blob][frame store: frame_floats x NQ][result word x NQ][two work queues]
-//   phase A  thread-per-query FK (registers), moving-geom frames -> shared (stride NQ, conflict free)
-//   phase B  thread-per-query loop over candidate pairs: bounding-sphere cull, cheap analytic
-//            pairs evaluated inline, box-box / MPR survivors pushed to CTA-wide queues
-//   phase C  the whole CTA drains the queues (one item per thread) so that the expensive,
-//            rarely-needed routines run with full lanes instead of one lane per warp
+// mopa_is_valid_batch: batched state-validity checks on sm_100a (replaces MujocoStateValidityChecker::isValid,
+// motion_planners/src/mujoco_ompl_interface.cpp:909-978).  See the kernel comment below for the mapping.
 // HBM traffic is the qpos row in and one 32-bit word out per query.
 #include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "validity_kernel.cuh"
 
@@ -19,10 +16,59 @@ struct RowQ {
     __device__ __forceinline__ float operator()(int i) const { return __ldg(row + i); }
 };
 
-template <int NQ, int QCAP, bool MESH>
-__global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
+// ---- the flattened checker (round 2).  Round 1 swept the candidate pairs with one thread per query and evaluated the
+// narrow phase where it stood: ~25 of the 241 (query, pair) items survive the bounding-sphere cull (14 of them plane pairs
+// that had no cull at all), 0.8 per query end in the portal refinement whose iteration count has a heavy tail, and the
+// warp waited for its slowest lane everywhere (ncu: 11.9 of 32 threads per instruction).  Now every kind of work runs in
+// the shape that suits it:
+//   phase A  thread = query   forward kinematics (serial chain, in registers); world frames of the moving geoms go to shared
+//                             memory ([frame float][query]: conflict-free for thread = query access)
+//   phase B  thread = query   a pure cull sweep over the candidate pairs, no narrow phase inside: pair records are broadcast
+//                             reads, the control flow is uniform (bounding spheres; plane pairs by centre height - bounding
+//                             radius), survivors are kept as a bit mask in registers and then appended to one of three
+//                             CTA-wide work lists (analytic pairs / box-box / portal-refinement candidates)
+//   phase C  thread = item    the CTA drains the lists one at a time: the lanes of a warp run the same routine on different
+//                             items.  Portal-refinement candidates first pass the conservative segment / slab pre-test;
+//                             what is left is queued (with the two world frames) in a per-CTA slab in global memory
+//   phase D  lane = item, refilled   once ~8 items per thread are queued (or the CTA runs out of tiles) the refinement runs
+//                             as a state machine, one support evaluation per trip; a lane whose item is finished takes the
+//                             next one, so the tail of long-running items no longer idles the other 31 lanes
+// During the kernel out[] holds the raw verdict (smallest canonical index of an offending pair, or ~0); the CTA converts
+// its own rows to the result-word format at the end.  Cull and narrow-phase arithmetic are round 1's, on the same inputs:
+// the result words are unchanged (bit-identical to the f32 oracle).  A full list / queue makes the pushing lane evaluate
+// its item in place.
+enum { WL_CHEAP = 0, WL_BOX = 1, WL_MPR = 2, WL_COUNT = 3 };
+#ifdef MOPA_VK_STATS   // diagnostics build (tools/vk_stats.py): per pair class, pairs tested / cull survivors / offending / refined
+__device__ unsigned long long g_vk_stats[16][4];
+#define VK_STAT(cls, k) atomicAdd(&g_vk_stats[cls][k], 1ULL)
+#else
+#define VK_STAT(cls, k)
+#endif
+
+struct MprItem { int q, p; float ca[3], Ra[9], cb[3], Rb[9]; };   // 104 bytes: global query row, pair, the two world frames
+
+// one (query, pair) item of the analytic / box-box classes: distance against the threshold
+template <bool MESH>
+__device__ __forceinline__ void eval_item(const SceneView &S, const float *frames, int stride, int ql, const PairRec &pr, float thr, uint32_t *res_q) {
+    Geom a, b;
+    load_geom<MESH>(a, S.recs[pr.ga], frames, stride, ql);
+    load_geom<MESH>(b, S.recs[pr.gb], frames, stride, ql);
+    const float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
+    if (dist <= thr) { atomicMin(res_q, (uint32_t)pr.canon); VK_STAT(pr.cls, 2); }
+}
+// the same for any class, out of line: a work list / queue that is full makes the pushing lane evaluate its item in place (rare)
+template <bool MESH>
+__device__ __noinline__ void eval_item_overflow(const unsigned char *blob, const float *frames, int stride, int ql, int p, float thr, uint32_t *res_q) {
+    const SceneView S = view_scene(blob);
+    eval_item<MESH>(S, frames, stride, ql, S.pairs[p], thr, res_q);
+}
+
+template <int NQ, bool MESH>
+__global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
                                                       const float *__restrict__ qpos, int row_stride, int n,
-                                                      uint32_t *__restrict__ out, int exact, const int *__restrict__ d_n, int d_n_mult) {
+                                                      uint32_t *__restrict__ out, int exact, const int *__restrict__ d_n, int d_n_mult,
+                                                      int ffs, int cap_cheap, int cap_box, int cap_mpr, MprItem *__restrict__ mq_all,
+                                                      int mq_cap, int mq_run) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     if (d_n) {   // row count produced on the device (no host round trip): n is the capacity
@@ -33,110 +79,292 @@ __global__ void __launch_bounds__(NQ) is_valid_kernel(const unsigned char *__res
     for (int i = tid; i < blob_bytes / 16; i += NQ) reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(blob_g)[i];
     __syncthreads();
     const SceneView S = view_scene(smem);
-    float *frames = reinterpret_cast<float *>(smem + blob_bytes);
-    uint32_t *res = reinterpret_cast<uint32_t *>(frames + (size_t)S.H->frame_floats * NQ);
-    uint32_t *queue = res + NQ;          // [2][QCAP]
-    int *qcount = reinterpret_cast<int *>(queue + 2 * QCAP);  // [2]
+    float *frames = reinterpret_cast<float *>(smem + blob_bytes);         // [ffs][NQ]
+    uint32_t *res = reinterpret_cast<uint32_t *>(frames + (size_t)ffs * NQ);
+    int *wcount = reinterpret_cast<int *>(res + NQ);                        // [0..2] work lists, [4] queue length, [5] queue cursor, [8..10] list offsets, [12..14] capacities
+    uint32_t *wl0 = reinterpret_cast<uint32_t *>(wcount + 16);              // the three lists, back to back
+    auto wl_base = [&](int list) { return wl0 + wcount[8 + list]; };
+    auto wl_cap = [&](int list) { return wcount[12 + list]; };
+    MprItem *mq = mq_all + (size_t)blockIdx.x * mq_cap;
+    if (tid == 0) {
+        wcount[4] = 0; wcount[5] = 0;
+        wcount[8] = 0; wcount[9] = cap_cheap; wcount[10] = cap_cheap + cap_box;
+        wcount[12] = cap_cheap; wcount[13] = cap_box; wcount[14] = cap_mpr;
+    }
+    __syncthreads();
     const float thr = S.H->threshold;
     const int npair = S.H->n_pair;
     const int ntile = (n + NQ - 1) / NQ;
 
+    // ---- phase D: the queued portal refinements, lanes refilled from the queue
+    auto run_queue = [&]() {
+        const int cnt = min(wcount[4], mq_cap);
+        __syncthreads();
+        if (cnt > 0) {
+            MprSM m;
+            Geom a, b;
+            int iq = 0;
+            uint32_t canon = 0;
+            bool active = false, exhausted = false;
+            for (;;) {
+                const unsigned act = __ballot_sync(0xffffffffu, active);
+                if (__popc(act) <= 24 && !active && !exhausted) {   // refill once a quarter of the warp is idle
+                    const int idx = atomicAdd(&wcount[5], 1);
+                    if (idx >= cnt) exhausted = true;
+                    else {
+                        const MprItem &it = mq[idx];
+                        iq = it.q;
+                        if (exact || out[iq] == 0xFFFFFFFFu) {   // fast mode: nothing to learn about a state already known to be invalid
+                            const PairRec pr = S.pairs[it.p];
+                            canon = pr.canon;
+                            const GeomRec &ra = S.recs[pr.ga], &rb = S.recs[pr.gb];
+                            a.kind = ra.kind; a.size = V3{ra.sx, ra.sy, ra.sz}; a.hull = nullptr; a.nhull = 0;
+                            b.kind = rb.kind; b.size = V3{rb.sx, rb.sy, rb.sz}; b.hull = nullptr; b.nhull = 0;
+                            if (MESH && ra.kind == K_MESH) { a.hull = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(&ra) + __float_as_int(ra.sx)); a.nhull = __float_as_int(ra.sy); a.size.z = ra.rbound; }
+                            if (MESH && rb.kind == K_MESH) { b.hull = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(&rb) + __float_as_int(rb.sx)); b.nhull = __float_as_int(rb.sy); b.size.z = rb.rbound; }
+                            a.c = V3{it.ca[0], it.ca[1], it.ca[2]}; b.c = V3{it.cb[0], it.cb[1], it.cb[2]};
+#pragma unroll
+                            for (int k = 0; k < 9; k++) { a.R.m[k] = it.Ra[k]; b.R.m[k] = it.Rb[k]; }
+                            mpr_begin(m, a, b);
+                            active = true;
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, active)) {
+                    if (__all_sync(0xffffffffu, exhausted)) break;
+                    continue;
+                }
+                if (active) {
+                    float depth = 0.0f;
+                    const int r = mpr_trip<MESH>(m, a, b, &depth);
+                    if (r != MPR_RUNNING) {
+                        if (r == MPR_PENETRATING && -depth <= thr) { atomicMin(&out[iq], canon); VK_STAT(PC_MPR, 2); }
+                        active = false;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { wcount[4] = 0; wcount[5] = 0; }
+        __syncthreads();
+    };
+
     for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const int q = tile * NQ + tid;
-        const bool active = q < n;
-        if (tid < 2) qcount[tid] = 0;
-        uint32_t first = 0xFFFFFFFFu;
-        if (active) {
+        if (tid < 3) wcount[tid] = 0;
+        res[tid] = 0xFFFFFFFFu;
+        if (q < n) {
             RowQ rq{qpos + (size_t)q * row_stride};
             fk_state(S, rq, frames, NQ, tid);
         }
         __syncthreads();
-        if (active) {
-            int cur_anchor = -1;
-            V3 ac{0, 0, 0};
-            for (int p = 0; p < npair; p++) {
-                const PairRec pr = S.pairs[p];
-                if (pr.anchor_slot != cur_anchor) {
-                    cur_anchor = pr.anchor_slot;
-                    const float *f = frames + (size_t)cur_anchor * NQ + tid;
-                    ac = V3{f[0], f[NQ], f[2 * NQ]};
+        // ---- phase B.  Every lane sweeps (rows beyond n hold stale frames and push nothing) so that the warp can be
+        // re-converged explicitly after the divergent push loop.  Runs of pairs with the same cull kind and anchor share
+        // the anchor centre; survivors are collected 32 pairs at a time in a register mask.
+        {
+            const uint32_t live = q < n ? 0xFFFFFFFFu : 0u;
+            uint32_t mw = 0u;
+            int cnt = 0, e = 0;              // bits collected in mw; next pair (uniform)
+            auto flush = [&](int base) {      // pairs base .. base + 31 <-> bits of mw
+                mw &= live;
+                while (mw) {
+                    const int p = base + __ffs(mw) - 1;
+                    mw &= mw - 1;
+                    const int cls = S.pairs[p].cls;
+                    VK_STAT(cls, 1);
+                    const int list = cls < PC_BOX_BOX ? WL_CHEAP : (cls == PC_BOX_BOX ? WL_BOX : WL_MPR);
+                    const int idx = atomicAdd(&wcount[list], 1);
+                    if (idx < wl_cap(list)) wl_base(list)[idx] = ((uint32_t)tid << 16) | (uint32_t)p;
+                    else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
                 }
-                if (pr.bound2 >= 0.0f) {
-                    V3 pc{pr.px, pr.py, pr.pz};
-                    if (pr.partner_slot != 0xFFFF) {
-                        const float *f = frames + (size_t)pr.partner_slot * NQ + tid;
-                        pc = V3{f[0], f[NQ], f[2 * NQ]};
-                    }
-                    V3 d = pc - ac;
-                    if (dot(d, d) > pr.bound2) continue;
-                }
-                if (pr.cls >= PC_BOX_BOX) {
-                    if (pr.cls > PC_MPR) continue;
-                    const int k = pr.cls - PC_BOX_BOX;
-                    int idx = atomicAdd(&qcount[k], 1);
-                    if (idx < QCAP) { queue[k * QCAP + idx] = ((uint32_t)tid << 16) | (uint32_t)p; continue; }
-                }
-                Geom a, b;
-                load_geom<MESH>(a, S.recs[pr.ga], frames, NQ, tid);
-                load_geom<MESH>(b, S.recs[pr.gb], frames, NQ, tid);
-                float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
-                if (dist <= thr) {
-                    first = min(first, (uint32_t)pr.canon);
-                    if (!exact) break;
+                __syncwarp();
+                cnt = 0;
+            };
+            const int ngroup = S.H->n_group;
+#pragma unroll 1
+            for (int g = 0; g < ngroup; g++) {
+                const CullGroup G = S.groups[g];
+                const float *fa = frames + (int)G.anchor_slot * NQ + tid;
+                const V3 ac{fa[0], fa[NQ], fa[2 * NQ]};
+                int rem = G.count;
+                while (rem > 0) {
+                    const int m = min(rem, 32 - cnt);
+                    // four independent tests per trip (the tests are short dependent chains: instruction-level parallelism
+                    // is what hides their latency at 12 resident warps); runs are padded to multiples of four, and a trip that
+                    // reaches past m only reads entries of the same run, which are masked out
+                    const uint32_t mmask = m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+                    uint32_t got = 0u;
+                    if (G.kind == CK_SPHERE_STATIC) {
+                        for (int j = 0; j < m; j += 4) {
+                            uint32_t b[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const CullEntry E = S.cull[e + j + u];
+                                const V3 d = V3{E.x, E.y, E.z} - ac;
+                                b[u] = !(dot(d, d) > E.w);
+                            }
+                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        }
+                    } else if (G.kind == CK_SPHERE_MOVING) {
+                        for (int j = 0; j < m; j += 4) {
+                            uint32_t b[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const CullEntry E = S.cull[e + j + u];
+                                const float *fp = frames + __float_as_int(E.x) * NQ + tid;
+                                const V3 d = V3{fp[0], fp[NQ], fp[2 * NQ]} - ac;
+                                b[u] = !(dot(d, d) > E.w);
+                            }
+                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        }
+                    } else if (G.kind == CK_PLANE) {
+                        for (int j = 0; j < m; j += 4) {
+                            uint32_t b[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const CullEntry E = S.cull[e + j + u];
+                                b[u] = !(dot(V3{E.x, E.y, E.z}, ac) > E.w);
+                            }
+                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        }
+                    } else
+                        got = 0xFFFFFFFFu;
+                    mw |= (got & mmask) << cnt;
+#ifdef MOPA_VK_STATS
+                    for (int j = 0; j < m; j++) VK_STAT(S.pairs[e + j].cls, 0);
+#endif
+                    e += m; rem -= m; cnt += m;
+                    if (cnt == 32) flush(e - 32);
                 }
             }
+            if (cnt > 0) flush(e - cnt);
         }
-        res[tid] = first;
         __syncthreads();
-        for (int k = 0; k < 2; k++) {
-            const int cnt = min(qcount[k], QCAP);
+        // ---- phase C: analytic pairs, then box-box
+#pragma unroll 1
+        for (int list = 0; list < WL_MPR; list++) {
+            const int cnt = min(wcount[list], wl_cap(list));
+            const uint32_t *items = wl_base(list);
             for (int i = tid; i < cnt; i += NQ) {
-                const uint32_t item = queue[k * QCAP + i];
+                const uint32_t item = items[i];
+                const int ql = item >> 16, p = item & 0xFFFF;
+                if (!exact && res[ql] != 0xFFFFFFFFu) continue;   // already known to be invalid
+                eval_item<MESH>(S, frames, NQ, ql, S.pairs[p], thr, &res[ql]);
+            }
+            if (!exact) __syncthreads();    // the cheap verdicts spare the expensive items of invalid states
+        }
+        // portal-refinement candidates: conservative pre-test, survivors are queued with their frames
+        {
+            const int cnt = min(wcount[WL_MPR], wl_cap(WL_MPR));
+            const uint32_t *items = wl_base(WL_MPR);
+            for (int i = tid; i < cnt; i += NQ) {
+                const uint32_t item = items[i];
                 const int ql = item >> 16, p = item & 0xFFFF;
                 if (!exact && res[ql] != 0xFFFFFFFFu) continue;
                 const PairRec pr = S.pairs[p];
                 Geom a, b;
                 load_geom<MESH>(a, S.recs[pr.ga], frames, NQ, ql);
                 load_geom<MESH>(b, S.recs[pr.gb], frames, NQ, ql);
-                float dist = heavy_dist<MESH>(pr.cls, a, b);
-                if (dist <= thr) atomicMin(&res[ql], (uint32_t)pr.canon);
+                if (mpr_certainly_separate(a, b)) continue;
+                VK_STAT(pr.cls, 3);
+                const int slot = atomicAdd(&wcount[4], 1);
+                if (slot < mq_cap) {
+                    MprItem &it = mq[slot];
+                    it.q = tile * NQ + ql; it.p = p;
+                    it.ca[0] = a.c.x; it.ca[1] = a.c.y; it.ca[2] = a.c.z; it.cb[0] = b.c.x; it.cb[1] = b.c.y; it.cb[2] = b.c.z;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) { it.Ra[k] = a.R.m[k]; it.Rb[k] = b.R.m[k]; }
+                } else
+                    eval_item_overflow<MESH>(smem, frames, NQ, ql, p, thr, &res[ql]);
             }
         }
         __syncthreads();
-        if (active) {
-            uint32_t r = res[tid];
+        if (q < n) out[q] = res[tid];          // raw verdict; queued refinements may still lower it
+        __syncthreads();
+        if (wcount[4] >= mq_run || tile + (int)gridDim.x >= ntile) run_queue();   // enough work queued, or this was the CTA's last tile
+    }
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const int q = tile * NQ + tid;
+        if (q < n) {
+            const uint32_t r = out[q];
             out[q] = (r == 0xFFFFFFFFu) ? 1u : (exact ? ((r + 1u) << 8) : 0u);
         }
     }
 }
 
 constexpr int VK_NQ = 128;
-constexpr int VK_QCAP = 1024;
+constexpr int VK_MQ_RUN = 8 * VK_NQ;    // queued refinements per CTA before phase D runs (8 per thread)
 
-size_t validity_smem_bytes(const SceneHeader &H) {
-    return (size_t)H.blob_bytes + (size_t)H.frame_floats * VK_NQ * 4 + VK_NQ * 4 + 2 * VK_QCAP * 4 + 16;
+// shared-memory plan for one scene: [blob][frames NQ x ffs][res NQ][counters][work lists]; the lists take what is left of a third of an SM
+struct VkPlan { int ffs, cap_cheap, cap_box, cap_mpr, mq_cap; size_t smem; int per_sm; };
+static VkPlan validity_plan(const SceneHeader &H) {
+    VkPlan P;
+    P.ffs = H.frame_floats;
+    const size_t fixed = (size_t)H.blob_bytes + (size_t)P.ffs * VK_NQ * 4 + VK_NQ * 4 + 64 + 16;
+    const size_t sm_total = 228 * 1024, reserve = 1024;
+    int per_sm = 4;
+    size_t lists = 0;
+    for (; per_sm >= 1; per_sm--) {   // most resident CTAs that still leave >= 4 KB of work lists each
+        const size_t budget = sm_total / per_sm - reserve;
+        if (budget > 227 * 1024) continue;
+        if (budget >= fixed + 4096) { lists = budget - fixed; break; }
+    }
+    if (per_sm < 1) { per_sm = 1; lists = 4096; }
+    if (lists > 16384) lists = 16384;
+    const int items = (int)(lists / 4) & ~3;
+    P.cap_box = items / 6; P.cap_mpr = items / 2; P.cap_cheap = items - P.cap_box - P.cap_mpr;   // ~ 4 : 1.4 : 5.6 items per query
+    P.mq_cap = VK_MQ_RUN + P.cap_mpr;
+    P.smem = fixed + (size_t)items * 4;
+    P.per_sm = per_sm;
+    return P;
+}
+size_t validity_smem_bytes(const SceneHeader &H) { return validity_plan(H).smem; }
+
+// per (device, stream) slab of queued refinement items: launches on one stream are ordered, launches on different streams
+// (the rollout's main and planner streams) must not share it
+static MprItem *validity_scratch(cudaStream_t stream, size_t bytes, cudaError_t &err) {
+    struct Slab { void *p; size_t bytes; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Slab> slabs;
+    int dev = 0;
+    err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    Slab &s = slabs[std::make_pair(dev, stream)];
+    if (s.bytes < bytes) {
+        if (s.p) { err = cudaStreamSynchronize(stream); if (err != cudaSuccess) return nullptr; cudaFree(s.p); s.p = nullptr; s.bytes = 0; }
+        err = cudaMalloc(&s.p, bytes);
+        if (err != cudaSuccess) { s.p = nullptr; return nullptr; }
+        s.bytes = bytes;
+    }
+    return (MprItem *)s.p;
 }
 
 cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
                             uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
     if (n <= 0) return cudaSuccess;
     static bool attr_set[2] = {false, false};
-    size_t smem = validity_smem_bytes(H);
+    const VkPlan P = validity_plan(H);
     const int mesh = H.n_hull_vert > 0;   // scenes with mesh colliders run the instantiation that carries the hull support
-    auto kern = mesh ? is_valid_kernel<VK_NQ, VK_QCAP, true> : is_valid_kernel<VK_NQ, VK_QCAP, false>;
+    auto kern = mesh ? is_valid_kernel<VK_NQ, true> : is_valid_kernel<VK_NQ, false>;
     if (!attr_set[mesh]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[mesh] = true;
     }
     int ntile = (n + VK_NQ - 1) / VK_NQ;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    int grid = sm_count * per_sm;
+    int grid = sm_count * P.per_sm;
     if (grid > ntile) grid = ntile;
-    kern<<<grid, VK_NQ, smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact, d_n, d_n_mult);
+    cudaError_t e = cudaSuccess;
+    MprItem *mq = validity_scratch(stream, (size_t)sm_count * P.per_sm * P.mq_cap * sizeof(MprItem), e);
+    if (!mq) return e;
+    kern<<<grid, VK_NQ, P.smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact, d_n, d_n_mult, P.ffs, P.cap_cheap, P.cap_box, P.cap_mpr,
+                                             mq, P.mq_cap, VK_MQ_RUN);
     return cudaGetLastError();
 }
+
+#ifdef MOPA_VK_STATS
+extern "C" int mopa_debug_vk_stats(unsigned long long *out64) { return (int)cudaMemcpyFromSymbol(out64, g_vk_stats, sizeof(g_vk_stats)); }
+#endif
 
 }  // namespace mopa

@@ -19,6 +19,8 @@ struct SceneView {  // pointers into the shared-memory copy of the scene blob
     const ConstFrame *consts;
     const GeomRec *recs;
     const PairRec *pairs;
+    const CullEntry *cull;
+    const CullGroup *groups;
 };
 
 __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
@@ -30,7 +32,24 @@ __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
     v.consts = reinterpret_cast<const ConstFrame *>(blob + v.H->off_const);
     v.recs = reinterpret_cast<const GeomRec *>(blob + v.H->off_rec);
     v.pairs = reinterpret_cast<const PairRec *>(blob + v.H->off_pair);
+    v.cull = reinterpret_cast<const CullEntry *>(blob + v.H->off_cull);
+    v.groups = reinterpret_cast<const CullGroup *>(blob + v.H->off_group);
     return v;
+}
+
+// cull test of one pair for the state whose frames sit at frames[slot * stride + lane] (see scene.h: CullKind)
+__device__ __forceinline__ bool cull_survives(const PairRec &pr, const CullEntry &e, const float *frames, int stride, int lane) {
+    if (pr.ckind == CK_NONE) return true;
+    const float *fa = frames + (size_t)pr.anchor_slot * stride + lane;
+    const V3 ac{fa[0], fa[stride], fa[2 * stride]};
+    if (pr.ckind == CK_PLANE) return !(dot(V3{e.x, e.y, e.z}, ac) > e.w);
+    V3 pc{e.x, e.y, e.z};
+    if (pr.ckind == CK_SPHERE_MOVING) {
+        const float *fp = frames + (size_t)pr.partner_slot * stride + lane;
+        pc = V3{fp[0], fp[stride], fp[2 * stride]};
+    }
+    const V3 d = pc - ac;
+    return !(dot(d, d) > e.w);
 }
 
 struct Frame { V3 pos; Q4 quat; M3 mat; };
