@@ -115,7 +115,12 @@ typedef struct mopa_env mopa_env;
 typedef struct mopa_sawyer_task {
     int32_t kind;                 /* 0: SawyerPushObstacle-v0, 1: SawyerLiftObstacle-v0 (8-D action: 7 joints + gripper; body_cube = can),
                                    * 2: SawyerAssemblyObstacle-v0 (body_cube = peg, body_rclaw = the part that
-                                   * carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd) */
+                                   * carries the hole sites, site_right_eef / site_left_eef = pegHead / pegEnd),
+                                   * 3: PusherObstacle-v0 (env/pusher/pusher_obstacle.py; BASELINE configs[0]): n_arm = 4 hinge joints
+                                   * (arm_* entries 0..3), body_ee = fingertip, site_grip = site "fingertip", body_cube = box,
+                                   * body_rclaw = target, grip_qadr / grip_vadr = the box slides (qpos[-2:]), target_qadr = the
+                                   * goal slides (qpos[-4:-2]); velocity actuators driven by the PID law of BaseEnv._get_control
+                                   * (env/base.py:200-209) re-evaluated before each of the nsub mj_steps (RK4, dt 0.01) */
     int32_t arm_qadr[7], arm_vadr[7], arm_dof[7];   /* qpos / qvel addresses and simulated-dof indices of right_j0..6 */
     int32_t grip_qadr[2], grip_vadr[2];             /* rc_close, lc_close */
     int32_t body_ee, body_cube, body_rclaw, body_lclaw; /* simulated-body indices */
@@ -127,10 +132,12 @@ typedef struct mopa_sawyer_task {
     double site_hole[3], site_hole_bottom[3];       /* assembly: sites "hole" / "hole_bottom" in their body frame */
     /* lift (env/sawyer/sawyer_lift_obstacle.py:92-148): simulated-geom indices of the can and of the left / right finger geoms
      * (l_finger_g0, l_finger_g1, l_fingertip_g0 / r_*; -1 = absent) whose contacts define has_grasp, and z of body bin1 */
-    int32_t geom_cube, geom_lfinger[3], geom_rfinger[3], pad_;
+    int32_t geom_cube, geom_lfinger[3], geom_rfinger[3];
+    int32_t n_arm;                /* arm joints the policy moves: 7 (0 is read as 7), 4 for the Pusher */
     double bin_z;
     double unstable_penalty;      /* env_config["unstable_penalty"] (env/base.py:36, default 0): subtracted from the reward of a step whose
                                    * simulation diverged (BaseEnv._do_simulation / _after_step, env/base.py:300-304, 388-400) */
+    double pid_kp, pid_kd, pid_ki;  /* Pusher: gains of BaseEnv._get_control (150, 20, 0.1; integral leak 0.95) */
 } mopa_sawyer_task;
 
 typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
@@ -153,6 +160,7 @@ typedef struct mopa_env_buffers {   /* device pointers, n_envs rows each */
     uint8_t *grasp;      /* [n]     nullable (lift): bit 0 / 1 = the can touched a left / right finger geom in the contact list of the
                           *         latest simulated step; a planner-failure step (no mj_step) evaluates compute_reward on this stale
                           *         list exactly as the reference reads mjData.contact there (rl/mopa_rollouts.py:312) */
+    double *i_term;      /* [n][4]  nullable (Pusher): integral term of the PID law, carried across env.steps (BaseEnv._i_term) */
     uint8_t *unstable;   /* [n]     nullable: 1 when the latest step produced a non-finite / huge (> 1e10, mjMAXVAL) state: the step is
                           *         discarded (state row untouched), the episode terminates with -unstable_penalty, and the caller
                           *         resets the environment (BaseEnv._do_simulation: reset() + _fail, env/base.py:388-400) */
@@ -176,6 +184,14 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
  *   2  planner failure: compute_reward + _after_step without simulation (rl/mopa_rollouts.py:304-327). */
 int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
                   const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream);
+
+/* PusherObstacleEnv._reset (env/pusher/pusher_obstacle.py:40-67) for every env whose mask byte is non-zero (d_mask nullable = all):
+ * rejection sampling of (goal, box, joint noise, velocity noise) until the state has no contact, the box is farther than 0.1 from
+ * the target and goal_x <= box_x.  Draws come from the counter-based generator keyed by (seed, global env id * 1000003 + attempt,
+ * episode); d_episode int64[n] holds each env's episode number and is incremented for the envs that were reset.  qpos0: host,
+ * nq doubles (the keyframe the noise is added to).  Also clears the episode counters and refreshes the observation. */
+int mopa_env_reset_pusher(mopa_env *e, const mopa_env_buffers *buf, const uint8_t *d_mask, uint64_t seed, int64_t env_id_offset,
+                          int64_t *d_episode, const double *qpos0, int32_t n_envs, void *stream);
 
 /* Batched inverse kinematics on a site pose - replaces qpos_from_site_pose (env/inverse_kinematics.py:18-135, called by
  * MoPARolloutRunner._cart2dispalcement, rl/mopa_rollouts.py:683-728): damped least squares with the reference's constants

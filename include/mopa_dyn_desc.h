@@ -75,6 +75,8 @@ typedef struct mopa_dyn_desc {
     const int32_t *g_condim;  /* [ngeom] */
     const int32_t *p_g1;      /* [npair] indices into the contact geoms */
     const int32_t *p_g2;
+    int32_t integrator;       /* <option integrator>: 0 Euler (semi-implicit, implicit joint damping), 1 RK4 (mj_RungeKutta, N = 4) */
+    int32_t pad_;
 } mopa_dyn_desc;
 
 #ifdef __cplusplus

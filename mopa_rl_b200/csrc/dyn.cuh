@@ -45,6 +45,7 @@ struct DynDev {
     double g_mat[DMAXG][9];   // rotation matrix: world (static geom) or local (moving geom)
     int g_mslot[DMAXG];       // -2 static, -1 moving with identity local rotation, >= 0 slot in the per-substep world-matrix cache
     int gm_geom[DMAXGM], ngm;
+    int integrator;           // 0 Euler, 1 RK4
 };
 
 struct Sv6 { double w[3], v[3]; };

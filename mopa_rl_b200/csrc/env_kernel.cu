@@ -25,6 +25,7 @@ static void fill_model(const mopa_dyn_desc *d, DynDev &m) {
     memset(&m, 0, sizeof(m));
     m.nq = d->nq; m.nv = d->nv; m.nb = d->nb; m.nd = d->nd; m.nact = d->nact; m.ngeom = d->ngeom; m.npair = d->npair;
     m.iterations = d->iterations; m.h = d->timestep; m.tolerance = d->tolerance;
+    m.integrator = d->integrator;
     for (int k = 0; k < 3; k++) m.g[k] = d->gravity[k];
     for (int i = 0; i < d->nb; i++) {
         m.b_parent[i] = d->b_parent[i]; m.b_jtype[i] = d->b_jtype[i]; m.b_qadr[i] = d->b_qadr[i]; m.b_vadr[i] = d->b_vadr[i];
@@ -92,7 +93,9 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
         mopa_set_error("mopa_env_create: scene exceeds the compiled limits of the env kernel");
         return MOPA_ERR_MODEL;
     }
-    if (task->kind < 0 || task->kind > 2) { mopa_set_error("mopa_env_create: task kind must be 0 (push), 1 (lift) or 2 (assembly)"); return MOPA_ERR_MODEL; }
+    if (task->kind < 0 || task->kind > 3) { mopa_set_error("mopa_env_create: task kind must be 0 (push), 1 (lift), 2 (assembly) or 3 (pusher)"); return MOPA_ERR_MODEL; }
+    if (task->kind == 3 && (task->n_arm != 4 || dyn->nb > 14 || dyn->ngeom > 32)) { mopa_set_error("mopa_env_create: the pusher task needs n_arm = 4 and a scene within the small workspace"); return MOPA_ERR_MODEL; }
+    if (task->kind != 3 && dyn->integrator != 0) { mopa_set_error("mopa_env_create: the Sawyer tasks integrate with Euler (RK4 is built for the pusher task)"); return MOPA_ERR_MODEL; }
     if (task->kind == 1 && (task->geom_cube < 0 || task->geom_cube >= dyn->ngeom)) { mopa_set_error("mopa_env_create: lift task without the can's contact geom"); return MOPA_ERR_MODEL; }
     mopa_env *e = new mopa_env();
     e->device = device;
@@ -125,6 +128,7 @@ void mopa_env_destroy(mopa_env *e) {
     cudaDeviceSynchronize();
     mopa::env_slot_release(e);
     if (e->d_model) cudaFree(e->d_model);
+    if (e->d_qpos0) cudaFree(e->d_qpos0);
     delete e;
 }
 
@@ -154,9 +158,22 @@ int mopa_env_forward(mopa_env *e, const mopa_env_buffers *buf, const int32_t *d_
     return MOPA_OK;
 }
 
+int mopa_env_reset_pusher(mopa_env *e, const mopa_env_buffers *buf, const uint8_t *d_mask, uint64_t seed, int64_t env_id_offset,
+                          int64_t *d_episode, const double *qpos0, int32_t n_envs, void *stream) {
+    if (!e || !buf || !d_episode || !qpos0 || n_envs < 0 || e->task.kind != 3) { mopa_set_error("mopa_env_reset_pusher: bad argument"); return MOPA_ERR_ARG; }
+    if (n_envs == 0) return MOPA_OK;
+    ENV_TRY(cudaSetDevice(e->device));
+    if (!e->d_qpos0) {
+        ENV_TRY(cudaMalloc(&e->d_qpos0, sizeof(double) * e->h_model.nq));
+        ENV_TRY(cudaMemcpy(e->d_qpos0, qpos0, sizeof(double) * e->h_model.nq, cudaMemcpyHostToDevice));
+    }
+    ENV_TRY(mopa::launch_pusher(e, *buf, nullptr, 0, nullptr, d_mask, n_envs, 3, nullptr, (unsigned long long)seed, (long long)env_id_offset, (long long *)d_episode, (cudaStream_t)stream));
+    return MOPA_OK;
+}
+
 int mopa_env_step(mopa_env *e, const mopa_env_buffers *buf, const float *d_action, int32_t action_stride,
                   const uint8_t *d_is_planner, const uint8_t *d_mask, int32_t n_envs, void *stream) {
-    if (!e || !buf || !d_action || action_stride < 7 || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
+    if (!e || !buf || !d_action || action_stride < (e->task.kind == 3 ? 4 : 7) || n_envs < 0) { mopa_set_error("mopa_env_step: bad argument"); return MOPA_ERR_ARG; }
     if (n_envs == 0) return MOPA_OK;
     ENV_TRY(cudaSetDevice(e->device));
     ENV_TRY(mopa::launch_env_warp(e, *buf, d_action, action_stride, d_is_planner, d_mask, n_envs, 0, nullptr, (cudaStream_t)stream));

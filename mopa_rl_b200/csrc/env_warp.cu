@@ -255,15 +255,38 @@ __device__ __noinline__ void kbi_ni(const DynDev &m, const double *solref, const
     d_kbi(m, solref, solimp, pos, margin, K, B, imp);
 }
 
+// mj_integratePos with the velocities in W.qd: hinge / slide joints linear, free joints by the exponential map of the angular velocity
+template <int WB, int WG, int WC>
+__device__ __forceinline__ void w_integrate_pos(const DynDev &m, WarpWS<WB, WG, WC> &W, double h, int lane) {
+    if (lane < m.nb) {
+        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i], a = m.b_qadr[i];
+        if (jt == 2 || jt == 3) W.q[a] += h * W.qd[da];
+        else if (jt == 0) {
+            for (int k = 0; k < 3; k++) W.q[a + k] += h * W.qd[da + k];
+            const double w[3] = {W.qd[da + 3], W.qd[da + 4], W.qd[da + 5]}, n = sqrt(d_dot(w, w)), ang = n * h;
+            if (ang > 0) {
+                const double sn = sin(0.5 * ang) / n, dq[4] = {cos(0.5 * ang), w[0] * sn, w[1] * sn, w[2] * sn};
+                double qn[4], q0[4] = {W.q[a + 3], W.q[a + 4], W.q[a + 5], W.q[a + 6]};
+                d_qmul(qn, q0, dq);
+                const double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+                for (int k = 0; k < 4; k++) W.q[a + 3 + k] = qn[k] / nn;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // One mj_step for the warp's environment.  W.q / W.v hold the state, W.ctrl the controls,
-// `comp` the dofs whose qfrc_applied is the previous qfrc_bias.  integrate=false: kinematics + bias only.
+// `comp` the dofs whose qfrc_applied is the previous qfrc_bias.  smode: 0 kinematics + bias only (sim.forward), 1 one mj_step
+// with the semi-implicit Euler integrator, 2 forward dynamics only: W.rhs <- qacc = M^-1 (tau + J^T f) (a stage of mj_RungeKutta),
+// 3 kinematics + contact detection only (ncon of a candidate reset state).
 // `sync`: the warps of a CTA walk the stages in step (CTA barrier between stages) so that they share
 // instruction-cache lines; `active` = false warps only take part in the barriers.
 // profiling / tuning hooks (MOPA_ENV_PROF=1, MOPA_ENV_SYNC_MASK=bits): per-stage clock64 sums, lane 0 of every warp
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
 template <int WB, int WG, int WC>
-__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, bool integrate, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
+__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
                                        bool active, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
@@ -466,7 +489,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         W.bias[lane] = s;
     }
     __syncwarp();
-    if (!integrate) return;
+    if (smode == 0) return;
     STAGE_SYNC(2);   // 2: RNE done
     // ---- composite inertias (lanes = 13 components), joint-space inertia (lane = dof)
     for (int i = nb - 1; i >= 0; i--) {
@@ -712,6 +735,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         PROF_MARK(24);
     }
     ncon_out = ncp;
+    if (smode == 3) return;
     STAGE_SYNC(5);   // 5: contact points done
     const int nc = nlim + 3 * ncp;
     double fcv = 0.0;  // lane k: constraint force on dof k
@@ -1011,31 +1035,21 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         if (lane == 0) W.wn = 0;
     }
     STAGE_SYNC(6);   // 6: constraint forces done
-    // ---- semi-implicit Euler with implicit joint damping
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
+    if (smode == 2) {   // explicit stage of mj_RungeKutta: qacc = M^-1 (tau + J^T f), joint damping is part of tau
+        w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.f, lane);
+        STAGE_SYNC(7);
+        return;
+    }
+    // ---- semi-implicit Euler with implicit joint damping
     w_factor_solve(W.M, m.d_damping, m.h, nd, W.L, W.invd, W.rhs, W.f, lane);
     if (lane < nd) {
         W.qd[lane] += m.h * W.rhs[lane];
         W.v[m.d_vadr[lane]] = W.qd[lane];
     }
     __syncwarp();
-    if (lane < nb) {
-        const int i = lane, jt = m.b_jtype[i], da = m.b_dadr[i], a = m.b_qadr[i];
-        if (jt == 2 || jt == 3) W.q[a] += m.h * W.qd[da];
-        else if (jt == 0) {
-            for (int k = 0; k < 3; k++) W.q[a + k] += m.h * W.qd[da + k];
-            const double w[3] = {W.qd[da + 3], W.qd[da + 4], W.qd[da + 5]}, n = sqrt(d_dot(w, w)), ang = n * m.h;
-            if (ang > 0) {
-                const double sn = sin(0.5 * ang) / n, dq[4] = {cos(0.5 * ang), w[0] * sn, w[1] * sn, w[2] * sn};
-                double qn[4], q0[4] = {W.q[a + 3], W.q[a + 4], W.q[a + 5], W.q[a + 6]};
-                d_qmul(qn, q0, dq);
-                const double nn = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-                for (int k = 0; k < 4; k++) W.q[a + 3 + k] = qn[k] / nn;
-            }
-        }
-    }
-    __syncwarp();
+    w_integrate_pos(m, W, m.h, lane);
     STAGE_SYNC(7);   // 7: state advanced
 }
 
@@ -1270,6 +1284,232 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// PusherObstacle-v0 (BASELINE configs[0]; env/pusher/pusher_obstacle.py:40-67, 185-284; PID of BaseEnv._get_control,
+// env/base.py:200-209): 4 hinge joints under velocity actuators, RK4 with dt = 0.01, int(frame_dt / dt) = 100 mj_steps per
+// env.step with the PID law re-evaluated before each of them.  Same warp-per-environment workspace and the same w_substep
+// as the Sawyer tasks; its own kernel so that the Sawyer kernels keep their code and register budget.
+__device__ __forceinline__ unsigned long long pz_mix(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double pz_uniform(unsigned long long seed, unsigned long long stream, unsigned long long counter, unsigned long long dim) {   // mopa_rl_b200/rng.py uniform01
+    unsigned long long x = pz_mix(seed ^ (stream * 0x9E3779B97F4A7C15ULL));
+    x = pz_mix(x + ((counter << 8) | dim) * 0xD1342543DE82EF95ULL);
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// one mj_step: Euler, or mj_RungeKutta with N = 4 (A = [[1/2], [0, 1/2], [0, 0, 1]], B = [1/6, 1/3, 1/3, 1/6]; every stage runs the
+// full forward dynamics incl. collision and the constraint solver; mjData keeps the frames / contacts of the last stage)
+template <int WB, int WG, int WC>
+__device__ __forceinline__ void w_mj_step(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, int lane, int &ncon, int &nwt,
+                                          double &cforce, const int4 keep, bool active, bool sync) {
+    if (m.integrator == 0) { w_substep(m, mg, W, 0u, 1, lane, ncon, nwt, cforce, keep, active, sync); return; }
+    if (!active) { for (int i = 0; i < 4; i++) w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, sync); return; }
+    const int nd = m.nd, va = lane < nd ? m.d_vadr[lane] : 0;
+    const double q0a = lane < m.nq ? W.q[lane] : 0.0, q0b = lane + 32 < m.nq ? W.q[lane + 32] : 0.0;
+    const double v0a = lane < m.nv ? W.v[lane] : 0.0, v0b = lane + 32 < m.nv ? W.v[lane + 32] : 0.0;
+    double Fv[4], Fa[4];
+    auto stage_state = [&](double dv, double da) {   // X = X0 + h (dv, da)
+        if (lane < m.nq) W.q[lane] = q0a;
+        if (lane + 32 < m.nq) W.q[lane + 32] = q0b;
+        if (lane < m.nv) W.v[lane] = v0a;
+        if (lane + 32 < m.nv) W.v[lane + 32] = v0b;
+        if (lane < nd) W.qd[lane] = dv;
+        __syncwarp();
+        w_integrate_pos(m, W, m.h, lane);
+        if (lane < nd) W.v[va] = W.v[va] + m.h * da;
+        __syncwarp();
+    };
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i > 0) {
+            double dv = 0.0, da = 0.0;
+#pragma unroll
+            for (int j = 0; j < i; j++) {
+                const double a = (j == i - 1) ? (i == 3 ? 1.0 : 0.5) : 0.0;
+                dv += a * Fv[j]; da += a * Fa[j];
+            }
+            stage_state(dv, da);
+        }
+        Fv[i] = lane < nd ? W.v[va] : 0.0;
+        w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, true, sync);
+        Fa[i] = lane < nd ? W.rhs[lane] : 0.0;
+        __syncwarp();
+    }
+    double dv = 0.0, da = 0.0;
+    const double Bc[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+#pragma unroll
+    for (int j = 0; j < 4; j++) { dv += Bc[j] * Fv[j]; da += Bc[j] * Fa[j]; }
+    stage_state(dv, da);
+}
+
+template <int WB, int WG, int WC>
+__device__ void pusher_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> &W, float *obs, int lane) {
+    // PusherObstacleEnv._get_obs (:185-205): cos / sin of the 4 joint angles, box qpos, joint velocities, box velocity, fingertip xy, goal
+    if (lane != 0) return;
+    int o = 0;
+    for (int k = 0; k < 4; k++) obs[o++] = (float)cos(W.q[T.arm_qadr[k]]);
+    for (int k = 0; k < 4; k++) obs[o++] = (float)sin(W.q[T.arm_qadr[k]]);
+    for (int k = 0; k < 2; k++) obs[o++] = (float)W.q[T.grip_qadr[k]];
+    for (int k = 0; k < 4; k++) obs[o++] = (float)W.v[T.arm_vadr[k]];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)W.v[T.grip_vadr[k]];
+    double tip[3];
+    w_site(tip, W, 0, T.site_grip);
+    obs[o++] = (float)tip[0]; obs[o++] = (float)tip[1];
+    for (int k = 0; k < 2; k++) obs[o++] = (float)W.q[T.target_qadr[k]];
+    while (o < 40) obs[o++] = 0.0f;   // 20 observation floats, row padded to 40
+}
+
+template <int WB, int WG, int WC, int ENV_WARPS>
+__global__ void __launch_bounds__(ENV_WARPS * 32, 1)
+pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffers B, const float *__restrict__ action, int action_stride,
+                   const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int fwd, const int32_t *__restrict__ ids,
+                   unsigned long long seed, long long env_id_offset, long long *__restrict__ d_episode, const double *__restrict__ qpos0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWS<WB, WG, WC> &W = reinterpret_cast<WarpWS<WB, WG, WC> *>(smem_raw)[warp];
+    const DynDev &m = c_models[model_slot];
+    const mopa_sawyer_task &T = c_tasks[model_slot];
+    const int t = blockIdx.x * ENV_WARPS + warp;
+    const int e = t < n ? (ids ? ids[t] : t) : 0;
+    const bool live = t < n && (!mask || mask[e]);
+    const int nstage = m.integrator == 0 ? 1 : 4;
+    int ncon = 0, nwt = 0;
+    double cforce = 0;
+    const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_rclaw);
+    if (!live) {   // still take part in the CTA barriers of the substep loop
+        if (fwd == 0)
+            for (int s = 0; s < T.nsub * nstage; s++) w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, true);
+        return;
+    }
+    if (lane < DMAXA) W.ctrl[lane] = 0.0;
+    if (lane == 0) W.wn = 0;
+    if (lane < WD) W.bias_prev[lane] = 0.0;
+    if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
+    if (fwd == 3) {   // ---- _reset: rejection sampling
+        const unsigned long long gid = (unsigned long long)(env_id_offset + e), ep = (unsigned long long)d_episode[e];
+        const int nq = m.nq, nv = m.nv;
+        for (int attempt = 0; attempt < 1000; attempt++) {
+            const unsigned long long st = gid * 1000003ULL + (unsigned long long)attempt;
+            for (int k = lane; k < nq; k += 32) W.q[k] = qpos0[k] + (-0.02 + __dmul_rn(0.04, pz_uniform(seed, st, ep, 4ULL + k)));   // no FMA contraction: the draws are input data, bit-equal to rng.py
+            for (int k = lane; k < nv; k += 32) W.v[k] = k >= nv - 4 ? 0.0 : -0.005 + __dmul_rn(0.01, pz_uniform(seed, st, ep, 4ULL + nq + k));
+            __syncwarp();
+            const double lo[2] = {-0.35, 0.13}, hi[2] = {-0.24, 0.2};
+            const double g0 = lo[0] + __dmul_rn(hi[0] - lo[0], pz_uniform(seed, st, ep, 0)), g1 = lo[1] + __dmul_rn(hi[1] - lo[1], pz_uniform(seed, st, ep, 1));
+            const double b0 = lo[0] + __dmul_rn(hi[0] - lo[0], pz_uniform(seed, st, ep, 2)), b1 = lo[1] + __dmul_rn(hi[1] - lo[1], pz_uniform(seed, st, ep, 3));
+            if (lane == 0) { W.q[nq - 4] = g0; W.q[nq - 3] = g1; W.q[nq - 2] = b0; W.q[nq - 1] = b1; }
+            __syncwarp();
+            w_substep(m, mg, W, 0u, 3, lane, ncon, nwt, cforce, keep, true, false);
+            double d2 = 0;
+            for (int k = 0; k < 3; k++) d2 += (W.kxpos[1][k] - W.kxpos[2][k]) * (W.kxpos[1][k] - W.kxpos[2][k]);
+            if (ncon == 0 && sqrt(d2) > 0.1 && g0 <= b0) break;
+        }
+        for (int k = lane; k < nq; k += 32) B.qpos[(size_t)e * nq + k] = W.q[k];
+        for (int k = lane; k < nv; k += 32) B.qvel[(size_t)e * nv + k] = W.v[k];
+        if (lane < 4 && B.i_term) B.i_term[(size_t)e * 4 + lane] = 0.0;
+        pusher_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+        if (lane == 0) {
+            d_episode[e] += 1;
+            B.has_prev[e] = 0; B.ep_len[e] = 0; B.ep_rew[e] = 0.0; B.done[e] = 0; B.success[e] = 0; B.reward[e] = 0.0;
+            if (B.unstable) B.unstable[e] = 0;
+            if (B.ncon) B.ncon[e] = 0;
+        }
+        return;
+    }
+    for (int k = lane; k < m.nq; k += 32) W.q[k] = B.qpos[(size_t)e * m.nq + k];
+    for (int k = lane; k < m.nv; k += 32) W.v[k] = B.qvel[(size_t)e * m.nv + k];
+    __syncwarp();
+    if (fwd == 1) {   // sim.forward() + _get_obs()
+        w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+        pusher_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+        return;
+    }
+    const int mode = is_planner ? is_planner[e] : 0;
+    const bool planner = mode == 1, had_prev = B.has_prev[e] != 0;
+    // desired_state = prev_state + action (the clipped / scaled variants computed before it are dead code in the reference, :253-266)
+    double prev = 0, desired = 0, iterm = 0;
+    if (lane < 4) {
+        prev = (!planner || !had_prev) ? W.q[T.arm_qadr[lane]] : B.prev_state[(size_t)e * 7 + lane];
+        desired = prev + (double)action[(size_t)e * action_stride + lane];
+        iterm = B.i_term ? B.i_term[(size_t)e * 4 + lane] : 0.0;
+    }
+    if (mode == 2) w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+    for (int s = 0; s < T.nsub; s++) {
+        if (mode != 2 && lane < 4) {   // BaseEnv._get_control: PID on the joint error, re-evaluated before every mj_step
+            const double p = T.pid_kp * (desired - W.q[T.arm_qadr[lane]]);
+            const double d = T.pid_kd * (0.0 - W.v[T.arm_vadr[lane]]);
+            iterm = 0.95 * iterm + T.pid_ki * (prev - W.q[T.arm_qadr[lane]]);
+            W.ctrl[lane] = p + d + iterm;
+        }
+        __syncwarp();
+        w_mj_step(m, mg, W, lane, ncon, nwt, cforce, keep, mode != 2, true);
+    }
+    // instability guard (see env_step_warp_kernel)
+    bool unstable = false;
+    if (mode != 2) {
+        bool bad = false;
+        for (int k = lane; k < m.nq; k += 32) { const double x = W.q[k]; if (!(fabs(x) <= 1e10)) bad = true; }
+        for (int k = lane; k < m.nv; k += 32) { const double x = W.v[k]; if (!(fabs(x) <= 1e10)) bad = true; }
+        unstable = __any_sync(FULL, bad);
+        if (unstable) {
+            for (int k = lane; k < m.nq; k += 32) W.q[k] = B.qpos[(size_t)e * m.nq + k];
+            for (int k = lane; k < m.nv; k += 32) W.v[k] = B.qvel[(size_t)e * m.nv + k];
+            __syncwarp();
+            w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+            ncon = 0; cforce = 0.0;
+        }
+    }
+    // PusherObstacleEnv.compute_reward (:223-238)
+    double reward = 0;
+    bool success = false, terminal = false;
+    {
+        double tip[3], dbg = 0, dbt = 0;
+        w_site(tip, W, 0, T.site_grip);
+        for (int k = 0; k < 3; k++) {
+            dbg += (W.kxpos[1][k] - tip[k]) * (W.kxpos[1][k] - tip[k]);
+            dbt += (W.kxpos[1][k] - W.kxpos[2][k]) * (W.kxpos[1][k] - W.kxpos[2][k]);
+        }
+        dbg = sqrt(dbg); dbt = sqrt(dbt);
+        if (dbg < 0.1) reward += 0.1 * (1 - tanh(5 * dbg));
+        if (dbt < 0.1) reward += 0.3 * (1 - tanh(5 * dbt));
+        if (dbt < T.distance_threshold) { success = true; terminal = true; reward += T.success_reward; }
+    }
+    if (unstable) { reward = -T.unstable_penalty; success = false; terminal = true; }
+    if (mode != 2) pusher_write_obs(T, W, B.obs + (size_t)e * 40, lane);
+    __syncwarp();
+    // _after_step: joint-limit projection (set_state + forward), episode accounting
+    bool clipped = false;
+    if (lane < m.nd && m.d_limited[lane] && m.d_qadr[lane] >= 0) {
+        double &x = W.q[m.d_qadr[lane]];
+        if (x < m.d_range[lane][0]) { x = m.d_range[lane][0]; clipped = true; }
+        else if (x > m.d_range[lane][1]) { x = m.d_range[lane][1]; clipped = true; }
+    }
+    clipped = __any_sync(FULL, clipped) && !unstable;
+    __syncwarp();
+    if (clipped) w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+    if (!unstable) {
+        for (int k = lane; k < m.nq; k += 32) B.qpos[(size_t)e * m.nq + k] = W.q[k];
+        for (int k = lane; k < m.nv; k += 32) B.qvel[(size_t)e * m.nv + k] = W.v[k];
+        if (mode != 2 && lane < 4) { B.prev_state[(size_t)e * 7 + lane] = desired; if (B.i_term) B.i_term[(size_t)e * 4 + lane] = iterm; }
+    }
+    if (lane == 0) {
+        if (mode != 2) B.has_prev[e] = 1;
+        const int len = B.ep_len[e] + 1;
+        if (len == T.max_episode_steps) terminal = true;
+        B.ep_len[e] = len;
+        B.ep_rew[e] += reward;
+        B.reward[e] = reward;
+        B.done[e] = terminal ? 1 : 0;
+        B.success[e] = success ? 1 : 0;
+        if (B.ncon) B.ncon[e] = ncon;
+        if (B.work && mode != 2) B.work[e] = nwt;
+        if (B.cforce) B.cforce[e] = mode != 2 ? cforce : 0.0;
+        if (B.unstable) B.unstable[e] = unstable ? 1 : 0;
+    }
+}
+
 cudaError_t env_tune_set(int prof, int sync_mask) {
     EnvTune t{prof, sync_mask};
     cudaError_t e = cudaMemcpyToSymbol(c_tune, &t, sizeof(t));
@@ -1319,6 +1559,8 @@ cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const floa
                             const uint8_t *mask, int n, int forward_only, const int32_t *ids, cudaStream_t stream) {
     static int small_warps = -1;   // tuning hook: MOPA_ENV_WARPS=7 runs two 7-warp CTAs per SM (smaller barrier domains)
     if (small_warps < 0) { const char *w = getenv("MOPA_ENV_WARPS"); small_warps = (w && atoi(w) == 7) ? 1 : 0; }
+    if (env->task.kind == 3)   // PusherObstacle-v0 has its own kernel (RK4 + PID); forward_only maps onto its sim.forward mode
+        return launch_pusher(env, B, action, action_stride, is_planner, mask, n, forward_only ? 1 : 0, ids, 0ULL, 0LL, nullptr, stream);
     cudaError_t e = env_slot_claim(env, stream, false);
     if (e != cudaSuccess) return e;
     const int model_slot = env->model_slot, nb = env->h_model.nb, ngeom = env->h_model.ngeom, ngm = env->h_model.ngm;
@@ -1329,6 +1571,25 @@ cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const floa
     if (small)
         return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
     return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+}
+
+cudaError_t launch_pusher(mopa_env *env, const mopa_env_buffers &B, const float *action, int action_stride, const uint8_t *is_planner,
+                          const uint8_t *mask, int n, int fwd, const int32_t *ids, unsigned long long seed, long long env_id_offset,
+                          long long *d_episode, cudaStream_t stream) {
+    cudaError_t e = env_slot_claim(env, stream, false);
+    if (e != cudaSuccess) return e;
+    constexpr int PW = 8;   // 8 warps per CTA: the Pusher runs with few environments, small CTAs spread them over the SMs
+    static bool attr_set = false;
+    const size_t smem = sizeof(WarpWS<14, 32, 24>) * PW;
+    auto kern = pusher_warp_kernel<14, 32, 24, PW>;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<(n + PW - 1) / PW, PW * 32, smem, stream>>>(env->model_slot, env->d_model, B, action, action_stride, is_planner, mask, n, fwd, ids, seed,
+                                                      env_id_offset, d_episode, env->d_qpos0);
+    return cudaGetLastError();
 }
 
 // 14 workspaces + one 1-warp planner CTA (<= 18 KB + 1 KB reserved each) must fit the 228 KB of an SM together

@@ -32,6 +32,7 @@ class DynDesc(C.Structure):
         ("a_gear", _D), ("a_ctrlrange", _D), ("a_forcerange", _D),
         ("g_body", _I), ("g_geomid", _I), ("g_type", _I), ("g_pos", _D), ("g_quat", _D), ("g_size", _D), ("g_rbound", _D),
         ("g_margin", _D), ("g_friction", _D), ("g_solref", _D), ("g_solimp", _D), ("g_condim", _I), ("p_g1", _I), ("p_g2", _I),
+        ("integrator", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -218,6 +219,7 @@ class DynModel:
         d.ngeom, d.npair, d.iterations = len(used), len(pairs), int(m.opt_iterations)
         d.timestep = float(m.opt_timestep)
         d.tolerance = float(m.opt_tolerance)
+        d.integrator = int(getattr(m, "opt_integrator", 0))
         for k in range(3):
             d.gravity[k] = float(m.opt_gravity[k])
         for name, ctype in DynDesc._fields_:

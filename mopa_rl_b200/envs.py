@@ -32,13 +32,13 @@ class SawyerTask(C.Structure):
                 ("site_left_eef", C.c_double * 3), ("site_grip", C.c_double * 3), ("target_base", C.c_double * 3),
                 ("ac_scale", C.c_double), ("distance_threshold", C.c_double), ("success_reward", C.c_double),
                 ("site_hole", C.c_double * 3), ("site_hole_bottom", C.c_double * 3),
-                ("geom_cube", C.c_int32), ("geom_lfinger", C.c_int32 * 3), ("geom_rfinger", C.c_int32 * 3), ("pad_", C.c_int32),
-                ("bin_z", C.c_double), ("unstable_penalty", C.c_double)]
+                ("geom_cube", C.c_int32), ("geom_lfinger", C.c_int32 * 3), ("geom_rfinger", C.c_int32 * 3), ("n_arm", C.c_int32),
+                ("bin_z", C.c_double), ("unstable_penalty", C.c_double), ("pid_kp", C.c_double), ("pid_kd", C.c_double), ("pid_ki", C.c_double)]
 
 
 class EnvBuffers(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("qpos", "qvel", "prev_state", "bias_prev", "has_prev", "ep_len", "ep_rew", "obs",
-                                           "reward", "done", "success", "ncon", "work", "cforce", "grasp", "unstable")]
+                                           "reward", "done", "success", "ncon", "work", "cforce", "grasp", "i_term", "unstable")]
 
 
 def make_push_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.05, distance_threshold=0.06, success_reward=150.0,
@@ -128,6 +128,42 @@ def make_lift_task(model, dyn, max_episode_steps=250, frame_dt=0.15, ac_scale=0.
         t.geom_lfinger[k] = sim_geom.get(model.geom_name2id(LIFT_LEFT_FINGER_GEOMS[k]), -1)
         t.geom_rfinger[k] = sim_geom.get(model.geom_name2id(LIFT_RIGHT_FINGER_GEOMS[k]), -1)
     t.bin_z = float(model.body_pos[model.body_name2id("bin1")][2])
+    return t
+
+
+def make_pusher_task(model, dyn, max_episode_steps=400, frame_dt=1.0, distance_threshold=0.05, success_reward=150.0, unstable_penalty=0.0,
+                     kp=150.0, kd=20.0, ki=0.1, **_):
+    """PusherObstacle-v0 (env/pusher/pusher_obstacle.py; BASELINE configs[0]): kind 3 of mopa_sawyer_task.  4 hinge joints under velocity
+    actuators (gear 10) driven by the PID law of BaseEnv._get_control (env/base.py:200-209), RK4 with dt 0.01, int(frame_dt / dt) = 100
+    mj_steps per env.step; max_episode_steps 400 as in scripts/2d/mopa.sh."""
+    t = SawyerTask()
+    t.kind, t.n_arm = 3, 4
+    t.unstable_penalty = float(unstable_penalty)
+    sim_body = {b: i for i, b in enumerate(dyn.bodies) if b >= 0}
+    for k in range(4):
+        j = "joint%d" % k
+        t.arm_qadr[k] = model.get_joint_qpos_addr(j)
+        t.arm_vadr[k] = model.get_joint_qvel_addr(j)
+        t.arm_dof[k] = list(dyn.dof_vadr).index(t.arm_vadr[k])
+    for k, j in enumerate(["box_x", "box_y"]):          # qpos[-2:] / qvel[-2:]
+        t.grip_qadr[k] = model.get_joint_qpos_addr(j)
+        t.grip_vadr[k] = model.get_joint_qvel_addr(j)
+    for k, j in enumerate(["target_x", "target_y"]):    # qpos[-4:-2]: the goal
+        t.target_qadr[k] = model.get_joint_qpos_addr(j)
+    assert [t.target_qadr[0], t.target_qadr[1], t.grip_qadr[0], t.grip_qadr[1]] == list(range(model.nq - 4, model.nq))
+    t.body_ee = sim_body[model.body_name2id("fingertip")]
+    t.body_cube = sim_body[model.body_name2id("box")]
+    t.body_rclaw = t.body_lclaw = sim_body[model.body_name2id("target")]
+    t.max_episode_steps = int(max_episode_steps)
+    t.nsub = int(frame_dt / model.opt_timestep)
+    p = model.site_pos[model.site_name2id("fingertip")]
+    for k in range(3):
+        t.site_grip[k] = float(p[k])
+    t.geom_cube = -1
+    for k in range(3):
+        t.geom_lfinger[k] = t.geom_rfinger[k] = -1
+    t.ac_scale, t.distance_threshold, t.success_reward = 0.1, float(distance_threshold), float(success_reward)   # _ac_scale: pusher_obstacle.py:33
+    t.pid_kp, t.pid_kd, t.pid_ki = float(kp), float(kd), float(ki)
     return t
 
 
@@ -222,6 +258,7 @@ class VecSawyerPushObstacle:
         self.cforce = torch.zeros(n, dtype=f64, device=dev)   # get_contact_force() of every env after the latest step
         self.grasp = torch.zeros(n, dtype=torch.uint8, device=dev)      # lift: finger-touch flags of the latest simulated step
         self.unstable = torch.zeros(n, dtype=torch.uint8, device=dev)   # 1 = the latest step diverged and was discarded (episode ends)
+        self.i_term = torch.zeros(n, 4, dtype=f64, device=dev)          # Pusher: integral term of the PID law
         self.buf = EnvBuffers(*[getattr(self, k).data_ptr() for k, _ in EnvBuffers._fields_])
         self.env_ids = np.arange(n, dtype=np.int64) + int(env_id_offset)
         self.episode_idx = np.zeros(n, dtype=np.int64)
@@ -323,3 +360,41 @@ class VecSawyerLiftObstacle(VecSawyerPushObstacle):
     MANIPULATION_BODIES = ("cube",)
     make_task = staticmethod(make_lift_task)
     reset_state = staticmethod(lift_reset_state)
+
+
+class VecPusherObstacle(VecSawyerPushObstacle):
+    """N device-resident PusherObstacle-v0 environments (BASELINE configs[0]).  Actions are 4-D joint displacements; the
+    observation row keeps the 40-float stride, its first 20 floats are cos / sin of the joint angles (4 + 4), box qpos 2, joint
+    velocities 4, box velocity 2, fingertip xy 2, goal 2 (env/pusher/pusher_obstacle.py:185-205).  reset() runs the reference's
+    rejection sampling (:40-67) on the device."""
+    ENV_ID = "PusherObstacle-v0"
+    OBS_DIM = 20
+    ACTION_DIM = 4
+    INIT_QPOS = np.zeros(7)
+    STATIC_BODIES = ()
+    MANIPULATION_BODIES = ()
+    make_task = staticmethod(make_pusher_task)
+
+    def __init__(self, n_envs, seed=1234, device=0, env_id_offset=0, model=None, max_episode_steps=400, contacts=True, **task_kwargs):
+        super().__init__(n_envs, seed=seed, device=device, env_id_offset=env_id_offset, model=model, max_episode_steps=max_episode_steps,
+                         contacts=contacts, **task_kwargs)
+        self.ref_joint_pos_indexes = [int(self.task.arm_qadr[k]) for k in range(4)]
+        self.episode_dev = self.torch.zeros(self.n, dtype=self.torch.int64, device=self.dev)   # episode number of every env (reset draws)
+        self._qpos0 = np.ascontiguousarray(self.model.qpos0, dtype=np.float64)
+        self._L.mopa_env_reset_pusher.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+
+    def reset(self, ids=None):
+        torch = self.torch
+        mask = None
+        if ids is not None:
+            ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+            if len(ids) == 0:
+                return self.obs
+            mask = torch.zeros(self.n, dtype=torch.uint8, device=self.dev)
+            mask[torch.as_tensor(ids, device=self.dev)] = 1
+        check(self._L.mopa_env_reset_pusher(self.h, C.byref(self.buf), C.c_void_p(mask.data_ptr()) if mask is not None else None,
+                                            int(self.seed) & 0xFFFFFFFFFFFFFFFF, int(self.env_ids[0]), C.c_void_p(self.episode_dev.data_ptr()),
+                                            self._qpos0.ctypes.data_as(C.c_void_p), self.n, C.c_void_p(self._stream())))
+        self._keep_mask = mask
+        self.episode_idx = self.episode_dev.cpu().numpy()
+        return self.obs
