@@ -30,17 +30,33 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "env-steps/sec (incl. planner) SawyerPushObstacle-v0"
 METRIC_ASSEMBLY = "env-steps/sec (incl. planner) SawyerAssemblyObstacle-v0"
-TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0"}
+TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0", "pusher": "PusherObstacle-v0"}
 
 
 # scripts/3d/{push,assembly,lift}/mopa.sh: omega per task (action_range 0.5, reuse_data, max_reuse_data 15 in all three)
-TASK_OMEGA = {"push": 0.7, "assembly": 0.7, "lift": 0.5}
+TASK_OMEGA = {"push": 0.7, "assembly": 0.7, "lift": 0.5, "pusher": 0.5}
 
 
 def task_config(task, max_iter):
     from mopa_rl_b200.rollout import MoPAConfig
 
+    if task == "pusher":
+        # BASELINE configs[0]: scripts/2d/mopa.sh (omega 0.5, action_range 1.0, reuse_data, max_reuse_data 30) + config/pusher.py (range 0.2,
+        # simple_planner_range 0.1, contact_threshold -0.0015, step_size 0.04, joint_margin 0; timelimit 1.0 s / simple 0.02 s -> half the
+        # iteration cap of the 2.0 s Sawyer presets, and 1 % of it for the simple planner)
+        return MoPAConfig(omega=0.5, action_range=1.0, ac_scale=0.1, step_size=0.04, joint_margin=0.0, contact_threshold=-0.0015, range=0.2,
+                          simple_planner_range=0.1, max_iter=max(1, max_iter // 2), simple_max_iter=max(1, max_iter // 100), reuse_data=True,
+                          max_reuse_data=30)
     return MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15, omega=TASK_OMEGA[task])
+
+
+def task_env_class(task):
+    from mopa_rl_b200 import envs
+
+    return {"assembly": envs.VecSawyerAssemblyObstacle, "lift": envs.VecSawyerLiftObstacle, "pusher": envs.VecPusherObstacle}.get(task, envs.VecSawyerPushObstacle)
+
+
+TASK_ADIM = {"push": 7, "assembly": 7, "lift": 8, "pusher": 4}
 
 
 def task_metric(task):
@@ -146,20 +162,20 @@ def _cpu_rollout_worker(args):
     from mopa_rl_b200 import rng
     from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.model import load_model
-    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerLiftObstacle, VecSawyerPushObstacle
-    from mopa_rl_b200.rollout import MoPAConfig, env_planner_inputs
+    from mopa_rl_b200.rollout import env_planner_inputs
     from oracle.rollout_oracle import ScalarMoPARunner
 
-    cls = {"assembly": VecSawyerAssemblyObstacle, "lift": VecSawyerLiftObstacle}.get(task, VecSawyerPushObstacle)
+    cls = task_env_class(task)
     model = load_model(cls.ENV_ID)
     ignored, passive, _ = env_planner_inputs(cls, model)
-    adim = 8 if task == "lift" else 7
+    adim = TASK_ADIM[task]
 
     def policy(g, k):
         u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(adim, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), task_config(task, max_iter), ignored, passive, gid, seed, policy, task=task)
+    r = ScalarMoPARunner(model, DynModel(model), task_config(task, max_iter), ignored, passive, gid, seed, policy, task=task,
+                         max_episode_steps=400 if task == "pusher" else 250)
     t0 = time.perf_counter()
     for _ in range(macros):
         r.macro_step()
@@ -257,11 +273,10 @@ def run_rollout(args):
     import torch
     import torch.distributed as dist
 
-    from mopa_rl_b200.envs import VecSawyerAssemblyObstacle, VecSawyerLiftObstacle, VecSawyerPushObstacle
     from mopa_rl_b200.replay import ReplicatedReplay
     from mopa_rl_b200.rollout import NativeMoPARolloutRunner
 
-    env_cls = {"assembly": VecSawyerAssemblyObstacle, "lift": VecSawyerLiftObstacle}.get(args.task, VecSawyerPushObstacle)
+    env_cls = task_env_class(args.task)
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -320,7 +335,7 @@ def run_rollout(args):
     replay_size = replay.device_size()
     xbytes = replay.bytes_exchanged / max(1, args.settle + args.warmup + args.steps)
     # end-to-end arm: host-side policy loop + transition records read back to pinned host memory every tick
-    hp = HostLoopPolicy(torch, dev, 99 + rank, n, 8 if args.task == "lift" else 7)
+    hp = HostLoopPolicy(torch, dev, 99 + rank, n, TASK_ADIM[args.task])
     runner2 = make(policy=hp)
     replay2 = ReplicatedReplay(torch, dev, capacity=1 << 20, slab_capacity=slab)
     h_block = torch.zeros(1 + slab, 92, dtype=torch.float32).pin_memory()
@@ -335,7 +350,10 @@ def run_rollout(args):
     tot_steps, tot_steps2 = float(cnt[0]), float(cnt[1])
     if rank == 0:
         peak, peak_kind = measured_peaks()
-        bytes_per_env_step = 816  # 352 B state/action in + 464 B state/obs out
+        # fp32 rows in (qpos, qvel, action 8, prev_state 8) + out (qpos, qvel, obs 40, reward / done / pad 4): 816 B for push
+        m_ = runner.venv.model
+        pad4 = lambda k: (k + 3) // 4 * 4
+        bytes_per_env_step = 4 * (2 * pad4(m_.nq) + 2 * pad4(m_.nv) + 8 + 8 + 40 + 4)
         achieved = bytes_per_env_step * n / (k_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         # same protocol as `--impl reference` (one scalar runner per host core, args.cpu_macros macro actions each, rate = env-steps /
@@ -369,7 +387,12 @@ def run_rollout(args):
 def rollout_config(args, n, **extra):
     """The `config` object of the rollout line; both arms print the same workload keys."""
     wl = (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]).replace("OMEGA", str(TASK_OMEGA[args.task]))
-    cfg = {"workload": wl, "reuse_data": True, "max_reuse_data": 15, "envs_per_gpu": n, "substeps_per_env_step": 75, "max_iter": args.max_iter}
+    if args.task == "pusher":
+        wl = wl.replace("action_range 0.5, RRT-Connect range 0.1", "action_range 1.0, RRT-Connect range 0.2")
+    cfg = {"workload": wl, "reuse_data": True, "max_reuse_data": 30 if args.task == "pusher" else 15, "envs_per_gpu": n,
+           "substeps_per_env_step": "100 RK4 mj_steps (400 forward-dynamics evaluations)" if args.task == "pusher" else 75, "max_iter": args.max_iter}
+    if args.task == "pusher":
+        cfg["baseline_config"] = "BASELINE configs[0] (PusherObstacle-v0 MoPA-SAC; the reference runs it with 1 env on the CPU): vectorised here, the reference arm runs one scalar env per host core"
     if extra:
         cfg.update({
             "settle_ticks": args.settle,
@@ -494,9 +517,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
-    ap.add_argument("--task", default="push", choices=["push", "assembly", "lift"],
+    ap.add_argument("--task", default="push", choices=["push", "assembly", "lift", "pusher"],
                     help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3]), "
-                         "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there)")
+                         "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there), pusher = PusherObstacle-v0 (configs[0])")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
     ap.add_argument("--cpu-macros", type=int, default=150, help="macro actions per scalar runner in the cpu_baseline leg and per step of --impl reference "
                                                                    "(one protocol for both: ~2.5 s of CPU work per runner)")

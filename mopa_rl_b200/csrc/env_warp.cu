@@ -285,15 +285,14 @@ __device__ __forceinline__ void w_integrate_pos(const DynDev &m, WarpWS<WB, WG, 
 // profiling / tuning hooks (MOPA_ENV_PROF=1, MOPA_ENV_SYNC_MASK=bits): per-stage clock64 sums, lane 0 of every warp
 #define PROF_MARK(id) do { if (c_tune.prof) { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_prof[id], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
 #define STAGE_SYNC(k) do { PROF_MARK(2 * (k)); if (sync && ((c_tune.sync_mask >> (k)) & 1)) __syncthreads(); PROF_MARK(2 * (k) + 1); } while (0)
+// One mj_step is three out-of-line stages (each gets its own register allocation: as one function the live ranges of
+// the kinematics, the contact generator and the solver overlapped and spilled): dynamics terms up to the unconstrained
+// acceleration, constraint discovery (joint limits, contact points), constraint solve + integration.  State passes through
+// the warp's shared-memory workspace; the barrier-only path of inactive warps lives in the driver w_substep.
 template <int WB, int WG, int WC>
-__device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
-                                       bool active, bool sync) {
+__device__ __noinline__ bool w_stage_dynamics(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, const int4 keep_bodies, bool sync) {
     const int nb = m.nb, nd = m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
-    if (!active) {   // barrier-only participant: one barrier per stage boundary below
-        for (int k = 1; k <= 7; k++) STAGE_SYNC(k);
-        return;
-    }
     if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
     __syncwarp();
     // ---- kinematics, lane = body, in registers: (1) local transform of the body incl. its joint (the
@@ -489,7 +488,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         W.bias[lane] = s;
     }
     __syncwarp();
-    if (smode == 0) return;
+    if (smode == 0) return false;
     STAGE_SYNC(2);   // 2: RNE done
     // ---- composite inertias (lanes = 13 components), joint-space inertia (lane = dof)
     for (int i = nb - 1; i >= 0; i--) {
@@ -538,6 +537,13 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
     w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.f, lane);
 
     STAGE_SYNC(4);   // 4: unconstrained acceleration done
+    return true;
+}
+
+template <int WB, int WG, int WC, bool RK>
+__device__ __noinline__ int w_stage_contacts(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, int lane, int &nlim_out) {
+    const int nd = m.nd;
+    long long t_last = c_tune.prof ? clock64() : 0;
     // ---- constraint rows.  Limits first (dof order), then contacts (pair order).
     int nlim = 0;
     {
@@ -734,8 +740,14 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
         __syncwarp();
         PROF_MARK(24);
     }
-    ncon_out = ncp;
-    if (smode == 3) return;
+    nlim_out = nlim;
+    return ncp;
+}
+
+template <int WB, int WG, int WC, bool RK>
+__device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, int smode, int lane, int nlim, int ncp, int &nwt_out, double &cforce_out, bool sync) {
+    const int nb = m.nb, nd = m.nd;
+    long long t_last = c_tune.prof ? clock64() : 0;
     STAGE_SYNC(5);   // 5: contact points done
     const int nc = nlim + 3 * ncp;
     double fcv = 0.0;  // lane k: constraint force on dof k
@@ -1037,7 +1049,7 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
     STAGE_SYNC(6);   // 6: constraint forces done
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
-    if (smode == 2) {   // explicit stage of mj_RungeKutta: qacc = M^-1 (tau + J^T f), joint damping is part of tau
+    if (RK && smode == 2) {   // explicit stage of mj_RungeKutta: qacc = M^-1 (tau + J^T f), joint damping is part of tau
         w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.f, lane);
         STAGE_SYNC(7);
         return;
@@ -1051,6 +1063,22 @@ __device__ __noinline__ void w_substep(const DynDev &m, const DynDev *__restrict
     __syncwarp();
     w_integrate_pos(m, W, m.h, lane);
     STAGE_SYNC(7);   // 7: state advanced
+}
+
+template <int WB, int WG, int WC, bool RK = false>   // RK: the instantiation that also serves smode 2 / 3 (Pusher); the Sawyer kernels keep their code
+__device__ __forceinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
+                                          bool active, bool sync) {
+    if (!active) {   // barrier-only participant: one barrier per stage boundary
+        long long t_last = c_tune.prof ? clock64() : 0;
+        for (int k = 1; k <= 7; k++) STAGE_SYNC(k);
+        return;
+    }
+    if (!w_stage_dynamics(m, mg, W, comp, smode, lane, keep_bodies, sync)) return;
+    int nlim = 0;
+    const int ncp = w_stage_contacts<WB, WG, WC, RK>(m, mg, W, lane, nlim);
+    ncon_out = ncp;
+    if (RK && smode == 3) return;
+    w_stage_solve<WB, WG, WC, RK>(m, mg, W, smode, lane, nlim, ncp, nwt_out, cforce_out, sync);
 }
 
 // kept frame slots: 0 = end-effector body, 1 = cube, 2 = right claw, 3 = left claw
@@ -1305,8 +1333,8 @@ __device__ __forceinline__ double pz_uniform(unsigned long long seed, unsigned l
 template <int WB, int WG, int WC>
 __device__ __forceinline__ void w_mj_step(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, int lane, int &ncon, int &nwt,
                                           double &cforce, const int4 keep, bool active, bool sync) {
-    if (m.integrator == 0) { w_substep(m, mg, W, 0u, 1, lane, ncon, nwt, cforce, keep, active, sync); return; }
-    if (!active) { for (int i = 0; i < 4; i++) w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, sync); return; }
+    if (m.integrator == 0) { w_substep<WB, WG, WC, true>(m, mg, W, 0u, 1, lane, ncon, nwt, cforce, keep, active, sync); return; }
+    if (!active) { for (int i = 0; i < 4; i++) w_substep<WB, WG, WC, true>(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, sync); return; }
     const int nd = m.nd, va = lane < nd ? m.d_vadr[lane] : 0;
     const double q0a = lane < m.nq ? W.q[lane] : 0.0, q0b = lane + 32 < m.nq ? W.q[lane + 32] : 0.0;
     const double v0a = lane < m.nv ? W.v[lane] : 0.0, v0b = lane + 32 < m.nv ? W.v[lane + 32] : 0.0;
@@ -1334,7 +1362,7 @@ __device__ __forceinline__ void w_mj_step(const DynDev &m, const DynDev *__restr
             stage_state(dv, da);
         }
         Fv[i] = lane < nd ? W.v[va] : 0.0;
-        w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, true, sync);
+        w_substep<WB, WG, WC, true>(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, true, sync);
         Fa[i] = lane < nd ? W.rhs[lane] : 0.0;
         __syncwarp();
     }
@@ -1381,7 +1409,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
     const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_rclaw);
     if (!live) {   // still take part in the CTA barriers of the substep loop
         if (fwd == 0)
-            for (int s = 0; s < T.nsub * nstage; s++) w_substep(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, true);
+            for (int s = 0; s < T.nsub * nstage; s++) w_substep<WB, WG, WC, true>(m, mg, W, 0u, 2, lane, ncon, nwt, cforce, keep, false, true);
         return;
     }
     if (lane < DMAXA) W.ctrl[lane] = 0.0;
@@ -1401,7 +1429,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
             const double b0 = lo[0] + __dmul_rn(hi[0] - lo[0], pz_uniform(seed, st, ep, 2)), b1 = lo[1] + __dmul_rn(hi[1] - lo[1], pz_uniform(seed, st, ep, 3));
             if (lane == 0) { W.q[nq - 4] = g0; W.q[nq - 3] = g1; W.q[nq - 2] = b0; W.q[nq - 1] = b1; }
             __syncwarp();
-            w_substep(m, mg, W, 0u, 3, lane, ncon, nwt, cforce, keep, true, false);
+            w_substep<WB, WG, WC, true>(m, mg, W, 0u, 3, lane, ncon, nwt, cforce, keep, true, false);
             double d2 = 0;
             for (int k = 0; k < 3; k++) d2 += (W.kxpos[1][k] - W.kxpos[2][k]) * (W.kxpos[1][k] - W.kxpos[2][k]);
             if (ncon == 0 && sqrt(d2) > 0.1 && g0 <= b0) break;
@@ -1422,7 +1450,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
     for (int k = lane; k < m.nv; k += 32) W.v[k] = B.qvel[(size_t)e * m.nv + k];
     __syncwarp();
     if (fwd == 1) {   // sim.forward() + _get_obs()
-        w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+        w_substep<WB, WG, WC, true>(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
         pusher_write_obs(T, W, B.obs + (size_t)e * 40, lane);
         return;
     }
@@ -1435,7 +1463,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
         desired = prev + (double)action[(size_t)e * action_stride + lane];
         iterm = B.i_term ? B.i_term[(size_t)e * 4 + lane] : 0.0;
     }
-    if (mode == 2) w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+    if (mode == 2) w_substep<WB, WG, WC, true>(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
     for (int s = 0; s < T.nsub; s++) {
         if (mode != 2 && lane < 4) {   // BaseEnv._get_control: PID on the joint error, re-evaluated before every mj_step
             const double p = T.pid_kp * (desired - W.q[T.arm_qadr[lane]]);
@@ -1457,7 +1485,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
             for (int k = lane; k < m.nq; k += 32) W.q[k] = B.qpos[(size_t)e * m.nq + k];
             for (int k = lane; k < m.nv; k += 32) W.v[k] = B.qvel[(size_t)e * m.nv + k];
             __syncwarp();
-            w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+            w_substep<WB, WG, WC, true>(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
             ncon = 0; cforce = 0.0;
         }
     }
@@ -1488,7 +1516,7 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
     }
     clipped = __any_sync(FULL, clipped) && !unstable;
     __syncwarp();
-    if (clipped) w_substep(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
+    if (clipped) w_substep<WB, WG, WC, true>(m, mg, W, 0u, 0, lane, ncon, nwt, cforce, keep, true, false);
     if (!unstable) {
         for (int k = lane; k < m.nq; k += 32) B.qpos[(size_t)e * m.nq + k] = W.q[k];
         for (int k = lane; k < m.nv; k += 32) B.qvel[(size_t)e * m.nv + k] = W.v[k];

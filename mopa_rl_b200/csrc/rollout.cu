@@ -14,6 +14,7 @@
 // round trip.  The policy is the only part evaluated outside (between mopa_rollout_pre and _step).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -44,6 +45,7 @@ struct RrtBatch {   // one batch of RRT-Connect problems (two of them: being fil
     // densification
     float *dens32;               // [cap][max_path - 1][kmax][row]
     uint32_t *dens_res;          // [cap][max_path - 1][kmax]
+    double *wp64;                // [cap][max_path][7] the planner's waypoints re-based on the start state (SamplingBasedPlanner.plan :72-101)
     int *nst;                    // [cap][max_path - 1]  > 0 interior states of the hop, 0 end point only, -(1 + s) fallback path s
     int *ok;                     // [cap]
     // blocked hops -> "simple" planner, then the main planner (SACAgent.simple_interpolate with use_planner, rl/sac_agent.py:300-311)
@@ -67,6 +69,8 @@ struct RoDev {   // everything the kernels need, passed by value
     long long env_id_offset;
     double jlo[7], jhi[7], init_qpos[7];
     int arm_qadr[7], target_qadr[2];
+    int na;                      // arm joints the policy moves (7 Sawyer, 4 Pusher)
+    unsigned unlim;              // bit k: arm joint k is an unlimited hinge (SO(2) in the planner, never clipped): Pusher joint0
     const double *qpos0;         // [nq]
     // per environment
     double *traj;                // [n][max_traj][7]
@@ -128,6 +132,19 @@ __device__ __forceinline__ double ro_normal(unsigned long long seed, unsigned lo
     const double u1 = ro_uniform(seed, stream, counter, dim * 2), u2 = ro_uniform(seed, stream, counter, dim * 2 + 1);
     return sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2);
 }
+// util/env.py:15-25 joint_convert: unlimited joints are wrapped with period 3.14 (not pi) before they go to the planner
+// (SamplingBasedPlanner.convert_nonlimited).  Python's float // and % (CPython float_divmod): the quotient is a whole number here.
+__device__ __forceinline__ double ro_joint_convert(double angle) {
+    const double w = angle > 0 ? 3.14 : -3.14;
+    double mod = fmod(angle, w);
+    double div = (angle - mod) / w;
+    if (mod != 0.0) { if ((w < 0) != (mod < 0)) { mod += w; div -= 1.0; } }
+    else mod = copysign(0.0, w);
+    double fl = 0.0;
+    if (div != 0.0) { fl = floor(div); if (div - fl > 0.5) fl += 1.0; }
+    const bool even = fmod(fl, 2.0) == 0.0;
+    return even ? mod : (angle > 0 ? mod - 3.14 : mod + 3.14);
+}
 __device__ __forceinline__ void ro_count(long long *c, int which, long long v = 1) { atomicAdd((unsigned long long *)(c + which), (unsigned long long)v); }
 
 // ---- 1. finished macro actions: transition records, episode resets (SawyerPushObstacleEnv._reset, :36-51)
@@ -174,7 +191,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     // env.form_action(traj[goal], traj[start]) -> SACAgent.invert_displacement (piecewise)
                     float ia[7];
                     bool planner_ac = false, valid_ac = true;
-                    for (int k = 0; k < 7; k++) {
+                    for (int k = 0; k < S.na; k++) {
                         const double d = tr[goal * 7 + k] - tr[start * 7 + k], ad = fabs(d);
                         const double a = S.ac_normal ? d / S.action_range
                                          : ad < S.ac_scale ? d * (S.omega / S.ac_scale)
@@ -187,7 +204,7 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                     if (!planner_ac || !valid_ac) continue;
                     float xr[92];
                     for (int k = 0; k < 40; k++) xr[k] = oh[start * 40 + k];
-                    for (int k = 0; k < 7; k++) xr[40 + k] = ia[k];
+                    for (int k = 0; k < 8; k++) xr[40 + k] = k < S.na ? ia[k] : 0.0f;
                     xr[47] = S.discrete ? S.ac[(size_t)e * 8 + 7] : 0.0f;   // inter_subgoal_ac["ac_type"] = ac["ac_type"] (:266-267)
                     xr[48] = (float)((rh[goal] - rh[start]) * pow(S.discount, -(double)(start + 1)));
                     xr[49] = S.done_hist[(size_t)e * S.max_traj + goal] ? 1.0f : 0.0f;
@@ -213,13 +230,15 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
                 }
                 S.ep_cforce[e] = 0.0;
                 const unsigned long long gid = (unsigned long long)(S.env_id_offset + e), ep = (unsigned long long)S.episode_idx[e];
-                double *q = B.qpos + (size_t)e * S.nq;
-                for (int k = 0; k < S.nq; k++) q[k] = S.qpos0[k];
-                for (int k = 0; k < 7; k++) q[S.arm_qadr[k]] = S.init_qpos[k] + 0.02 * ro_normal(S.seed_env, gid, ep, (unsigned long long)k);
-                if (S.task_kind == 0)   // push: the target slides (sawyer_push_obstacle.py:41-47)
-                    for (int k = 0; k < 2; k++) q[S.target_qadr[k]] += -0.01 + 0.02 * ro_uniform(S.seed_env, gid, ep, 100ULL + k);
-                for (int k = 0; k < nv; k++) B.qvel[(size_t)e * nv + k] = 0.0;
-                S.episode_idx[e] += 1;
+                if (S.task_kind != 3) {
+                    double *q = B.qpos + (size_t)e * S.nq;
+                    for (int k = 0; k < S.nq; k++) q[k] = S.qpos0[k];
+                    for (int k = 0; k < S.na; k++) q[S.arm_qadr[k]] = S.init_qpos[k] + 0.02 * ro_normal(S.seed_env, gid, ep, (unsigned long long)k);
+                    if (S.task_kind == 0)   // push: the target slides (sawyer_push_obstacle.py:41-47)
+                        for (int k = 0; k < 2; k++) q[S.target_qadr[k]] += -0.01 + 0.02 * ro_uniform(S.seed_env, gid, ep, 100ULL + k);
+                    for (int k = 0; k < nv; k++) B.qvel[(size_t)e * nv + k] = 0.0;
+                    S.episode_idx[e] += 1;
+                }   // Pusher: the rejection-sampled reset needs the collision check and runs in the env kernel (mopa_rollout_pre)
                 B.ep_len[e] = 0; B.ep_rew[e] = 0.0; B.done[e] = 0; B.success[e] = 0;
                 if (B.grasp) B.grasp[e] = 0;
                 reset = 1;
@@ -240,7 +259,7 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
     if (e >= S.n || !S.need[e]) return;
     float a32[7];
     bool is_mp = false;
-    for (int k = 0; k < 7; k++) {
+    for (int k = 0; k < S.na; k++) {
         float a = actions[(size_t)e * S.adim + k];
         a = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
         a32[k] = a;
@@ -266,7 +285,7 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
     float *q32 = S.q32a + (size_t)slot * S.row;
     for (int k = 0; k < S.nq; k++) tg[k] = curr[k];
     const double w = S.omega;
-    for (int k = 0; k < 7; k++) {
+    for (int k = 0; k < S.na; k++) {
         const double a = (double)a32[k], aa = fabs(a);
         const double disp = S.ac_normal ? a * S.action_range
                             : aa < w ? a / (w / S.ac_scale)
@@ -342,10 +361,10 @@ __global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
     if (lane == 0) { S.plan_ok[slot] = ok ? 1 : 0; S.nstep[slot] = 0; }
     if (!ok) { if (lane == 0) { ro_count(S.counters, C_INVALID); ro_count(S.counters, C_MP_FAIL); } return; }
     bool out = false;
-    for (int k = 0; k < 7; k++) { const double x = curr[S.arm_qadr[k]]; if (x < S.jlo[k] || x > S.jhi[k]) out = true; }
+    for (int k = 0; k < S.na; k++) { const double x = curr[S.arm_qadr[k]]; if (x < S.jlo[k] || x > S.jhi[k]) out = true; }
     for (int k = lane; k < S.nq; k += 32) c[k] = curr[k];
     __syncwarp();
-    if (out && lane < 7) {
+    if (out && lane < S.na) {
         double x = curr[S.arm_qadr[lane]];
         const double lo = S.jlo[lane] + S.joint_margin, hi = S.jhi[lane] - S.joint_margin;
         x = x < lo ? lo : x;
@@ -355,7 +374,7 @@ __global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
     __syncwarp();
     const double lim = S.ac_scale * 0.8;
     double diff[7], sf = 1.0, run[7];
-    for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
+    for (int k = 0; k < S.na; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
     int nstep = (int)floor(sf);
     if (nstep > RO_JMAX) nstep = RO_JMAX;
     if (lane == 0) S.nstep[slot] = nstep;
@@ -364,8 +383,8 @@ __global__ void ro_interp_kernel(RoDev S, mopa_env_buffers B) {
         for (int k = lane; k < S.row; k += 32) q32[k] = k < S.nq ? (float)c[k] : 0.0f;
         __syncwarp();
         if (j < nstep) {
-            for (int k = 0; k < 7; k++) run[k] = run[k] + diff[k] / sf;
-            if (lane < 7) {
+            for (int k = 0; k < S.na; k++) run[k] = run[k] + diff[k] / sf;
+            if (lane < S.na) {
                 double v = run[0];
 #pragma unroll
                 for (int k = 1; k < 7; k++) if (lane == k) v = run[k];
@@ -386,11 +405,11 @@ __global__ void ro_interp_finish_kernel(RoDev S, RrtBatch Q) {
     if (straight) {
         const double lim = S.ac_scale * 0.8;
         double diff[7], sf = 1.0, run[7];
-        for (int k = 0; k < 7; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
+        for (int k = 0; k < S.na; k++) { diff[k] = tg[S.arm_qadr[k]] - c[S.arm_qadr[k]]; const double s = fabs(diff[k]) / lim; if (s > sf) sf = s; run[k] = c[S.arm_qadr[k]]; }
         double *tr = S.traj + (size_t)e * S.max_traj * 7;
         for (int j = 0; j < nstep; j++)
-            for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[j * 7 + k] = run[k]; }
-        for (int k = 0; k < 7; k++) tr[nstep * 7 + k] = tg[S.arm_qadr[k]];
+            for (int k = 0; k < S.na; k++) { run[k] = run[k] + diff[k] / sf; tr[j * 7 + k] = run[k]; }
+        for (int k = 0; k < S.na; k++) tr[nstep * 7 + k] = tg[S.arm_qadr[k]];
         S.kind[e] = 1; S.traj_len[e] = nstep + 1; S.traj_pos[e] = 0;
         ro_count(S.counters, C_INTERP);
         ro_count(S.counters, C_INTERP_PATH_LEN, nstep + 1);
@@ -403,11 +422,63 @@ __global__ void ro_interp_finish_kernel(RoDev S, RrtBatch Q) {
         Q.start32[(size_t)r * S.row + k] = k < S.nq ? (float)c[k] : 0.0f;
         Q.goal32[(size_t)r * S.row + k] = k < S.nq ? (float)tg[k] : 0.0f;
     }
+    for (int k = 0; k < S.na; k++)
+        if ((S.unlim >> k) & 1u) {   // convert_nonlimited on copies of start / goal (sampling_based_planner.py:63-66)
+            Q.start32[(size_t)r * S.row + S.arm_qadr[k]] = (float)ro_joint_convert(c[S.arm_qadr[k]]);
+            Q.goal32[(size_t)r * S.row + S.arm_qadr[k]] = (float)ro_joint_convert(tg[S.arm_qadr[k]]);
+        }
     for (int k = 0; k < S.nq; k++) Q.start64[(size_t)r * S.nq + k] = c[k];
     Q.keys[r] = ((unsigned long long)(S.env_id_offset + e) << 32) + (unsigned long long)S.plan_count[e];   // invariant to batching / GPU count
     S.plan_count[e] += 1;
     S.kind[e] = 3; S.traj_len[e] = 1; S.traj_pos[e] = 0;   // waits for the plan
     ro_count(S.counters, C_RRT_PROBLEMS);
+}
+
+// ---- 6a. the planner's waypoints re-based on the (clipped, f64) start state (SamplingBasedPlanner.plan, :72-101).  All joints
+// limited (Sawyer): start + (waypoint - first waypoint).  With an unlimited joint (Pusher joint0) the planner saw wrapped
+// angles: waypoint deltas are accumulated on the un-wrapped start, going the short way round across +-3.14.
+// One thread per problem (the accumulation is sequential; paths have at most max_path rows).
+__global__ void ro_rebase_kernel(RoDev S, RrtBatch Q) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cnt = min(*Q.cnt, S.rrt_cap);
+    if (r >= cnt || Q.status[r] != 0) return;
+    const int L = Q.plen[r];
+    const float *path = Q.path + (size_t)r * S.max_path * S.row;
+    const double *st = Q.start64 + (size_t)r * S.nq;
+    double *wp = Q.wp64 + (size_t)r * S.max_path * 7;
+    for (int k = 0; k < S.na; k++) {
+        const int a = S.arm_qadr[k];
+        wp[k] = st[a];
+        if (S.unlim == 0) {
+            const double p0 = (double)path[a];
+            for (int i = 1; i < L; i++) wp[(size_t)i * 7 + k] = st[a] + ((double)path[(size_t)i * S.row + a] - p0);
+        } else {
+            const bool un = (S.unlim >> k) & 1u;
+            double acc = st[a];
+            for (int i = 1; i < L; i++) {
+                const double pv = (double)path[(size_t)(i - 1) * S.row + a], sv = (double)path[(size_t)i * S.row + a];
+                double delta = sv - pv;
+                if (un && fabs(sv - pv) > 3.14) {
+                    if (pv > 0 && sv <= 0) delta = 3.14 - pv + sv + 3.14;
+                    else if (pv < 0 && sv > 0) delta = -(3.14 - sv + pv + 3.14);
+                }
+                acc = acc + delta;
+                wp[(size_t)i * 7 + k] = acc;
+            }
+        }
+    }
+}
+// hop i of problem r: start / end / difference of the re-based waypoints i, i + 1
+__device__ __forceinline__ void ro_hop(const RoDev &S, const double *wp, int i, double *hs, double *he, double *diff, double &sf) {
+    const double lim = S.ac_scale * 0.8;
+    sf = 1.0;
+    for (int k = 0; k < S.na; k++) {
+        hs[k] = wp[(size_t)i * 7 + k];
+        he[k] = wp[(size_t)(i + 1) * 7 + k];
+        diff[k] = he[k] - hs[k];
+        const double s = fabs(diff[k]) / lim;
+        if (s > sf) sf = s;
+    }
 }
 
 // ---- 6. finished RRT batch: re-base on the start (SamplingBasedPlanner.plan), densify (SACAgent.plan :216-233).
@@ -424,51 +495,28 @@ __global__ void ro_rrt_densify_kernel(RoDev S, RrtBatch Q) {
     const int L = Q.plen[r];
     const float *path = Q.path + (size_t)r * S.max_path * S.row;
     const double *st = Q.start64 + (size_t)r * S.nq;
-    const double lim = S.ac_scale * 0.8;
     for (int i = lane; i < H; i += 32) {
         int nst = 0;
         float *rows = Q.dens32 + ((size_t)r * H + i) * S.kmax * S.row;
         if (i < L - 1) {
-            double hs[7], diff[7], sf = 1.0;
+            double hs[7], he[7], diff[7], sf;
             bool need = false;
-            for (int k = 0; k < 7; k++) {
-                const int a = S.arm_qadr[k];
-                const double p0 = (double)path[a];
-                const double he = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
-                hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
-                diff[k] = he - hs[k];
-                if (fabs(diff[k]) > S.ac_scale) need = true;
-                const double s = fabs(diff[k]) / lim;
-                if (s > sf) sf = s;
-            }
+            ro_hop(S, Q.wp64 + (size_t)r * S.max_path * 7, i, hs, he, diff, sf);
+            for (int k = 0; k < S.na; k++) if (fabs(diff[k]) > S.ac_scale) need = true;
             if (need && S.interpolation) { nst = (int)floor(sf); if (nst > S.kmax) nst = S.kmax; }
             double run[7];
-            for (int k = 0; k < 7; k++) run[k] = hs[k];
+            for (int k = 0; k < S.na; k++) run[k] = hs[k];
             for (int j = 0; j < S.kmax; j++) {
                 float *q32 = rows + (size_t)j * S.row;
                 for (int k = 0; k < S.row; k++) q32[k] = k < S.nq ? (float)st[k] : 0.0f;
                 if (j < nst)
-                    for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; q32[S.arm_qadr[k]] = (float)run[k]; }
+                    for (int k = 0; k < S.na; k++) { run[k] = run[k] + diff[k] / sf; q32[S.arm_qadr[k]] = (float)run[k]; }
             }
         } else {
             for (int j = 0; j < S.kmax; j++)
                 for (int k = 0; k < S.row; k++) rows[(size_t)j * S.row + k] = k < S.nq ? (float)st[k] : 0.0f;
         }
         Q.nst[(size_t)r * H + i] = nst;
-    }
-}
-// hop i of problem r, re-based on the (clipped, f64) start state as SamplingBasedPlanner.plan does: start / end / difference
-__device__ __forceinline__ void ro_hop(const RoDev &S, const float *path, const double *st, int i, double *hs, double *he, double *diff, double &sf) {
-    const double lim = S.ac_scale * 0.8;
-    sf = 1.0;
-    for (int k = 0; k < 7; k++) {
-        const int a = S.arm_qadr[k];
-        const double p0 = (double)path[a];
-        he[k] = st[a] + ((double)path[(size_t)(i + 1) * S.row + a] - p0);
-        hs[k] = i == 0 ? st[a] : st[a] + ((double)path[(size_t)i * S.row + a] - p0);
-        diff[k] = he[k] - hs[k];
-        const double s = fabs(diff[k]) / lim;
-        if (s > sf) sf = s;
     }
 }
 // Hops whose interior states are invalid become planning problems of their own (simple_interpolate with use_planner=True,
@@ -493,10 +541,14 @@ __global__ void ro_fb_collect_kernel(RoDev S, RrtBatch Q) {
                 if (slot >= S.fb_cap) slot = -2;
                 else {
                     double hs[7], he[7], diff[7], sf;
-                    ro_hop(S, path, st, i, hs, he, diff, sf);
+                    ro_hop(S, Q.wp64 + (size_t)r * S.max_path * 7, i, hs, he, diff, sf);
                     float *s32 = Q.fb_start32 + (size_t)slot * S.row, *g32 = Q.fb_goal32 + (size_t)slot * S.row;
                     for (int k = 0; k < S.row; k++) { const float v = k < S.nq ? (float)st[k] : 0.0f; s32[k] = v; g32[k] = v; }
-                    for (int k = 0; k < 7; k++) { s32[S.arm_qadr[k]] = (float)hs[k]; g32[S.arm_qadr[k]] = (float)he[k]; }
+                    for (int k = 0; k < S.na; k++) {
+                        const bool un = (S.unlim >> k) & 1u;   // convert_nonlimited, as for the main problem
+                        s32[S.arm_qadr[k]] = (float)(un ? ro_joint_convert(hs[k]) : hs[k]);
+                        g32[S.arm_qadr[k]] = (float)(un ? ro_joint_convert(he[k]) : he[k]);
+                    }
                     Q.fb_prob[slot] = r; Q.fb_hop[slot] = i;
                     Q.fb_keys[slot] = (Q.keys[r] * 0x9E3779B97F4A7C15ULL) ^ (unsigned long long)(i + 1);
                 }
@@ -561,20 +613,34 @@ __global__ void ro_rrt_finish_kernel(RoDev S, RrtBatch Q) {
         const int off = carry + incl - c;
         if (live) {
             double hs[7], he[7], diff[7], sf;
-            ro_hop(S, path, st, i, hs, he, diff, sf);
+            ro_hop(S, Q.wp64 + (size_t)r * S.max_path * 7, i, hs, he, diff, sf);
             if (slot >= 0) {   // the fallback planner's waypoints, re-based on the hop's start (first row dropped: PlannerAgent.plan)
                 const float *fp = Q.fb_path + (size_t)slot * S.fb_max_path * S.row;
-                for (int j = 1; j <= c; j++)
-                    for (int k = 0; k < 7; k++) {
-                        const int a = S.arm_qadr[k];
-                        tr[(size_t)(off + j - 1) * 7 + k] = hs[k] + ((double)fp[(size_t)j * S.row + a] - (double)fp[a]);
+                for (int k = 0; k < S.na; k++) {
+                    const int a = S.arm_qadr[k];
+                    if (S.unlim == 0) {
+                        for (int j = 1; j <= c; j++) tr[(size_t)(off + j - 1) * 7 + k] = hs[k] + ((double)fp[(size_t)j * S.row + a] - (double)fp[a]);
+                    } else {   // accumulate the deltas on the un-wrapped hop start (see ro_rebase_kernel)
+                        const bool un = (S.unlim >> k) & 1u;
+                        double acc = hs[k];
+                        for (int j = 1; j <= c; j++) {
+                            const double pv = (double)fp[(size_t)(j - 1) * S.row + a], sv = (double)fp[(size_t)j * S.row + a];
+                            double delta = sv - pv;
+                            if (un && fabs(sv - pv) > 3.14) {
+                                if (pv > 0 && sv <= 0) delta = 3.14 - pv + sv + 3.14;
+                                else if (pv < 0 && sv > 0) delta = -(3.14 - sv + pv + 3.14);
+                            }
+                            acc = acc + delta;
+                            tr[(size_t)(off + j - 1) * 7 + k] = acc;
+                        }
                     }
+                }
             } else {
                 double run[7];
-                for (int k = 0; k < 7; k++) run[k] = hs[k];
+                for (int k = 0; k < S.na; k++) run[k] = hs[k];
                 for (int j = 0; j < nst; j++)
-                    for (int k = 0; k < 7; k++) { run[k] = run[k] + diff[k] / sf; tr[(size_t)(off + j) * 7 + k] = run[k]; }
-                for (int k = 0; k < 7; k++) tr[(size_t)(off + nst) * 7 + k] = he[k];
+                    for (int k = 0; k < S.na; k++) { run[k] = run[k] + diff[k] / sf; tr[(size_t)(off + j) * 7 + k] = run[k]; }
+                for (int k = 0; k < S.na; k++) tr[(size_t)(off + nst) * 7 + k] = he[k];
             }
         }
         carry += __shfl_sync(0xffffffffu, incl, 31);
@@ -643,13 +709,13 @@ __global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
     float *sa = S.step_action + (size_t)e * 8;
     if (kind == 0) {
         // direct execution: ac / omega, or the raw action with discrete_action (rl/mopa_rollouts.py:347-352)
-        for (int k = 0; k < 7; k++) sa[k] = S.discrete ? S.ac[(size_t)e * 8 + k] : (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
+        for (int k = 0; k < S.na; k++) sa[k] = S.discrete ? S.ac[(size_t)e * 8 + k] : (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
         if (S.adim == 8) sa[7] = S.ac[(size_t)e * 8 + 7];   // rescaled_ac: only the joint entries are divided by omega (:349-352)
     } else if (kind == 1) {
         int pos = S.traj_pos[e];
         if (pos > S.max_traj - 1) pos = S.max_traj - 1;
         const double *nx = S.traj + ((size_t)e * S.max_traj + pos) * 7;
-        for (int k = 0; k < 7; k++) sa[k] = (float)(nx[k] - B.qpos[(size_t)e * S.nq + S.arm_qadr[k]]);
+        for (int k = 0; k < S.na; k++) sa[k] = (float)(nx[k] - B.qpos[(size_t)e * S.nq + S.arm_qadr[k]]);
         // lift: form_action's gripper entry = (gripper qpos of the waypoint = of the plan's start state) - current one; the
         // policy's gripper action replaces it on the last waypoint (rl/mopa_rollouts.py:170-175)
         if (S.adim == 8) sa[7] = (S.traj_pos[e] >= S.traj_len[e] - 1) ? S.ac[(size_t)e * 8 + 7] : (float)(S.grip0[e] - B.qpos[(size_t)e * S.nq + S.grip_qadr0]);
@@ -768,13 +834,16 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.step_size = cfg->step_size; S.joint_margin = cfg->joint_margin; S.range = cfg->range;
     S.seed_env = cfg->seed_env; S.env_id_offset = cfg->env_id_offset;
     S.heavy_work = env->task.nsub + env->task.nsub / 8;
+    S.na = env->task.n_arm > 0 ? env->task.n_arm : 7;
+    if (S.na > 7) { mopa_set_error("mopa_rollout_create: more than 7 arm joints"); delete r; return MOPA_ERR_ARG; }
     for (int k = 0; k < 7; k++) { S.jlo[k] = cfg->jnt_lo[k]; S.jhi[k] = cfg->jnt_hi[k]; S.init_qpos[k] = cfg->init_qpos[k]; S.arm_qadr[k] = env->task.arm_qadr[k]; }
+    for (int k = 0; k < S.na; k++) if (std::isinf(cfg->jnt_lo[k]) || std::isinf(cfg->jnt_hi[k])) S.unlim |= 1u << k;   // unlimited hinge: infinite range
     for (int k = 0; k < 2; k++) S.target_qadr[k] = env->task.target_qadr[k];
     S.macro_index = (long long *)d_macro_index; S.slab = d_slab; S.emit_flag = d_emit_flag; S.counters = (long long *)d_counters;
     S.ring = d_ring; S.ring_cap = ring_capacity;
     S.discrete = cfg->discrete_action ? 1 : 0;
     S.ac_normal = cfg->ac_space_normal ? 1 : 0;
-    S.adim = env->task.kind == 1 ? 8 : 7;
+    S.adim = env->task.kind == 1 ? 8 : (env->task.kind == 3 ? 4 : 7);
     S.grip_qadr0 = env->task.grip_qadr[0];
     if (S.adim == 8 && S.discrete) { mopa_set_error("mopa_rollout_create: discrete_action is not built for the 8-D lift action (record slot 47 is taken)"); delete r; return MOPA_ERR_ARG; }
     S.reuse_data = cfg->reuse_data ? 1 : 0;
@@ -804,6 +873,7 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
         A(Q.cnt, 1); A(Q.env, cap); A(Q.start32, cap * row); A(Q.goal32, cap * row); A(Q.start64, cap * nq); A(Q.keys, cap);
         A(Q.path, cap * S.max_path * row); A(Q.ids, cap * S.max_path); A(Q.plen, cap); A(Q.status, cap);
         A(Q.dens32, cap * H * S.kmax * row); A(Q.dens_res, cap * H * S.kmax); A(Q.nst, cap * H); A(Q.ok, cap);
+        A(Q.wp64, cap * S.max_path * 7);
         const size_t fc = S.fb_cap, fp = S.fb_max_path;
         A(Q.fb_cnt, 1); A(Q.fb_prob, fc); A(Q.fb_hop, fc); A(Q.fb_start32, fc * row); A(Q.fb_goal32, fc * row); A(Q.fb_keys, fc);
         A(Q.fb_path, fc * fp * row); A(Q.fb_ids, fc * fp); A(Q.fb_plen, fc); A(Q.fb_status, fc); A(Q.fb_status1, fc); A(Q.hop_fb, cap * H);
@@ -874,6 +944,7 @@ static int ro_launch_rrt(mopa_rollout *r, RrtBatch &Q) {
     const int warps_blocks = (S.rrt_cap * 32 + 127) / 128, H = S.max_path - 1;
     RO_TRY(launch_plan(p, Q.start32, Q.goal32, S.row, Q.keys, S.rrt_cap, r->max_iter, Q.path, Q.ids, S.max_path, Q.plen, Q.status, nullptr, nullptr,
                        ps, Q.cnt, r->plan_cta_warps));   // 1-warp CTAs: small enough to share an SM with an env-step CTA
+    ro_rebase_kernel<<<(S.rrt_cap + 127) / 128, 128, 0, ps>>>(S, Q);
     ro_rrt_densify_kernel<<<warps_blocks, 128, 0, ps>>>(S, Q);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, Q.dens32, S.row, S.rrt_cap * H * S.kmax, Q.dens_res, 0, p->sm_count, ps, Q.cnt, H * S.kmax));
     RO_TRY(cudaMemsetAsync(Q.fb_cnt, 0, sizeof(int), ps));
@@ -884,7 +955,7 @@ static int ro_launch_rrt(mopa_rollout *r, RrtBatch &Q) {
     RO_TRY(cudaMemcpyAsync(Q.fb_status1, Q.fb_status, sizeof(int) * S.fb_cap, cudaMemcpyDeviceToDevice, ps));
     RO_TRY(launch_plan(p, Q.fb_start32, Q.fb_goal32, S.row, Q.fb_keys, S.fb_cap, r->max_iter, Q.fb_path, Q.fb_ids, S.fb_max_path, Q.fb_plen,
                        Q.fb_status, nullptr, nullptr, ps, Q.fb_cnt, r->plan_cta_warps, 0.f, 1, 0xA5A5A5A5A5A5A5A5ULL));
-    r->launches += 6;
+    r->launches += 7;
     return MOPA_OK;
 }
 
@@ -907,7 +978,10 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
     if (S.xslab) RO_TRY(cudaMemsetAsync(S.xcount, 0, sizeof(int), st));
     ro_pre_kernel<<<blocks, 128, 0, st>>>(S, r->buf, r->env->h_model.nv);
     RO_TRY(cudaGetLastError());
-    RO_TRY(launch_env_warp(r->env, r->buf, nullptr, 0, nullptr, S.reset_flag, S.n, 1, nullptr, st));
+    if (S.task_kind == 3)   // PusherObstacleEnv._reset: rejection sampling with the collision check, draws keyed by (env id, episode)
+        RO_TRY(launch_pusher(r->env, r->buf, nullptr, 0, nullptr, S.reset_flag, S.n, 3, nullptr, S.seed_env, S.env_id_offset, S.episode_idx, st));
+    else
+        RO_TRY(launch_env_warp(r->env, r->buf, nullptr, 0, nullptr, S.reset_flag, S.n, 1, nullptr, st));
     r->launches += 2;
     return MOPA_OK;
 }

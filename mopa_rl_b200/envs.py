@@ -375,6 +375,16 @@ class VecPusherObstacle(VecSawyerPushObstacle):
     MANIPULATION_BODIES = ()
     make_task = staticmethod(make_pusher_task)
 
+    @staticmethod
+    def planner_inputs(model):
+        """ignored contacts / passive joints as rl/trainer.py:62-75 derives them from env/pusher/pusher_obstacle.py:
+        manipulation geom `box` x the static obstacle geoms (:138-151), joints 0-3 active."""
+        static = [model.geom_name2id("obstacle%d_geom" % i) for i in range(1, 8)]
+        box = model.geom_name2id("box")
+        ignored = [(min(box, g), max(box, g)) for g in static]
+        ref = [model.get_joint_qpos_addr("joint%d" % i) for i in range(4)]
+        return ignored, [i for i in range(model.nq) if i not in ref], ref
+
     def __init__(self, n_envs, seed=1234, device=0, env_id_offset=0, model=None, max_episode_steps=400, contacts=True, **task_kwargs):
         super().__init__(n_envs, seed=seed, device=device, env_id_offset=env_id_offset, model=model, max_episode_steps=max_episode_steps,
                          contacts=contacts, **task_kwargs)

@@ -73,7 +73,9 @@ def planner_inputs(model, static_bodies=("table", "bin1"), manipulation_geoms=("
 
 
 def env_planner_inputs(venv_cls, model):
-    """planner_inputs for a vectorised env class (STATIC_BODIES / MANIPULATION_BODIES)."""
+    """planner_inputs for a vectorised env class (STATIC_BODIES / MANIPULATION_BODIES, or its own planner_inputs)."""
+    if hasattr(venv_cls, "planner_inputs"):
+        return venv_cls.planner_inputs(model)
     return planner_inputs(model, static_bodies=venv_cls.STATIC_BODIES, manipulation_bodies=venv_cls.MANIPULATION_BODIES)
 
 
@@ -171,8 +173,11 @@ class NativeMoPARolloutRunner:
         c.omega, c.action_range, c.ac_scale, c.discount = cfg.omega, cfg.action_range, cfg.ac_scale, cfg.discount_factor
         c.step_size, c.joint_margin, c.range = cfg.step_size, cfg.joint_margin, cfg.range
         c.seed_env, c.env_id_offset = venv.seed, int(venv.env_ids[0])
-        for k in range(7):
-            c.jnt_lo[k], c.jnt_hi[k], c.init_qpos[k] = float(m.jnt_range[jid[k], 0]), float(m.jnt_range[jid[k], 1]), float(venv.INIT_QPOS[k])
+        for k in range(len(ref)):   # unlimited hinges (Pusher joint0): infinite range = never clipped, SO(2) in the planner
+            lim = bool(m.jnt_limited[jid[k]])
+            c.jnt_lo[k] = float(m.jnt_range[jid[k], 0]) if lim else -np.inf
+            c.jnt_hi[k] = float(m.jnt_range[jid[k], 1]) if lim else np.inf
+            c.init_qpos[k] = float(venv.INIT_QPOS[k])
         self._qpos0 = np.ascontiguousarray(m.qpos0, dtype=np.float64)
         c.qpos0 = self._qpos0.ctypes.data
         c.reuse_data, c.max_reuse_data, c.seed_reuse = int(cfg.reuse_data), self.max_reuse, (int(cfg.seed) + 0x5EED) & 0xFFFFFFFFFFFFFFFF
@@ -302,5 +307,6 @@ def run_episodes(venv, config=None, policy=None, episodes_per_env=1, max_ticks=1
             break
     info = runner.episode_stats()
     info.update({k: v for k, v in runner.counters.items() if k in ("mp", "rl", "interpolation", "mp_fail", "approximate", "invalid")})
+    info["per_env"] = runner.ep_stats.cpu().numpy().copy()   # [n, 5]: episodes, sum of len / rew / success / contact force
     runner.close()
     return info

@@ -48,6 +48,7 @@ class ScalarMoPARunner:
         self.macro_index = 0
         self.env_steps = 0
         self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, reused=0, fb_simple=0, fb_main=0, densify_fallback=0)
+        self.contact_force_sum = 0.0   # run_episode: total_contact_force += env.get_contact_force() after every simulated env.step (:538-539, 636-646)
         self.extra_records = []   # relabelled records (reuse_data) of the latest macro step
         self.ob = self._reset()
 
@@ -230,6 +231,7 @@ class ScalarMoPARunner:
                         g = grip_ac if i == len(traj) - 1 else grip_q0 - env.qpos[env.grip_q[0]]
                         a = np.concatenate([a, [np.float64(np.float32(g))]])
                     self.ob, rew, done = env.step(a, is_planner=True)
+                    self.contact_force_sum += getattr(env, "contact_force", 0.0)
                     meta += cfg.discount_factor ** i * rew
                     ob_list.append(self.ob.copy()), rew_list.append(meta), done_list.append(done)
                     steps += 1
@@ -252,6 +254,7 @@ class ScalarMoPARunner:
             if lift:
                 direct = np.concatenate([direct, [grip_ac]])
             self.ob, rec_rew, done = env.step(direct, is_planner=False)
+            self.contact_force_sum += getattr(env, "contact_force", 0.0)
             intra, steps = 0, 1
         env.prev_state = None                                       # env._reset_prev_state()
         self.env_steps += steps

@@ -152,23 +152,49 @@ def test_native_runner_reuse_data_matches_scalar_reference_loop(push_model, orac
     print("reuse_data: %d records (%d relabelled), worst |obs diff| %.2e" % (len(rec), c["reused"], worst))
 
 
-def test_run_episodes_reports_reference_episode_info(push_model, oracle_built):
-    """Evaluation path (run_episode, rl/mopa_rollouts.py:401-681): per-episode len / rew / success / contact_force."""
+def test_run_episodes_matches_scalar_episodes(push_model, oracle_built):
+    """Evaluation path (run_episode, rl/mopa_rollouts.py:401-681): per-episode len / rew / success / contact_force of every
+    environment against the scalar restatement run for the same number of episodes."""
     import torch
 
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.envs import VecSawyerPushObstacle
-    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, run_episodes
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, planner_inputs, run_episodes
+    from oracle.rollout_oracle import ScalarMoPARunner
 
-    n, horizon = 8, 12
-    venv = VecSawyerPushObstacle(n, seed=11, max_episode_steps=horizon)
-    info = run_episodes(venv, MoPAConfig(max_iter=100, seed=2), policy=CounterPolicy(torch, venv.dev, 5), episodes_per_env=2)
-    assert info["episodes"] >= 2 * n
-    assert info["episode_success"] == 0.0 and abs(info["len"] - horizon) < 1e-9     # random actions never push the cube home
-    assert info["rew"] >= 0.0
-    # the cube rests on the bin floor in (almost) every step: contact force per step ~ its weight
-    weight = push_model.body_mass[push_model.body_name2id("cube")] * 9.81
-    assert 0.5 * weight * horizon < info["contact_force"] < 3.0 * weight * horizon, (info, weight)
+    n, horizon, episodes, seed = 8, 12, 2, 11
+    cfg = MoPAConfig(max_iter=100, seed=2)
+    venv = VecSawyerPushObstacle(n, seed=seed, max_episode_steps=horizon)
+    info = run_episodes(venv, cfg, policy=CounterPolicy(torch, venv.dev, 5), episodes_per_env=episodes)
+    assert info["episodes"] >= episodes * n
     assert info["mp"] + info["rl"] + info["interpolation"] + info["mp_fail"] > 0
+
+    def policy(gid, k):
+        u = rng.uniform01(5, np.uint64(gid), np.uint64(k), np.arange(7, dtype=np.uint64))
+        return (2.0 * u - 1.0).astype(np.float32)
+
+    ignored, passive, _ = planner_inputs(push_model)
+    dm = DynModel(push_model)
+    per = info["per_env"]
+    for e in range(n):
+        ref = ScalarMoPARunner(push_model, dm, cfg, ignored, passive, e, seed, policy, max_episode_steps=horizon)
+        done_eps, tot_len, tot_rew, tot_succ = 0, 0, 0.0, 0.0
+        target = int(per[e, 0])                          # the device may have finished more than `episodes` before the last check
+        while done_eps < target:
+            rec = ref.macro_step()
+            if rec[49] == 1.0:
+                done_eps += 1
+                tot_len += ref.env.ep_len
+                tot_rew += ref.env.ep_rew
+                tot_succ += float(ref.env.success)
+        assert per[e, 1] == tot_len, (e, per[e], tot_len)
+        assert abs(per[e, 2] - tot_rew) < 1e-6 and per[e, 3] == tot_succ, (e, per[e], tot_rew, tot_succ)
+        assert abs(per[e, 4] - ref.contact_force_sum) <= 1e-6 * max(1.0, ref.contact_force_sum), (e, per[e, 4], ref.contact_force_sum)
+    # sanity of the aggregate: the cube rests on the bin floor in (almost) every step, contact force per step ~ its weight
+    weight = push_model.body_mass[push_model.body_name2id("cube")] * 9.81
+    assert 0.5 * weight * horizon < info["contact_force"] < 3.0 * weight * horizon, (info["contact_force"], weight)
+    print("run_episodes: %d episodes, mean len %.1f rew %.4f contact force %.4f - per-env sums equal the scalar loop's" % (info["episodes"], info["len"], info["rew"], info["contact_force"]))
 
 
 @pytest.mark.parametrize("ac_space_type", ["piecewise", "normal"])
