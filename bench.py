@@ -285,7 +285,7 @@ def run_rollout(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
     cfg = task_config(args.task, args.max_iter)   # scripts/3d/<task>/mopa.sh
-    slab = args.slab or n
+    slab = args.slab or max(1024, n // 2)   # steady state emits ~0.32 n records per tick; bursts queue up and drain over the next ticks
 
     def barrier():
         torch.cuda.synchronize()
@@ -358,7 +358,8 @@ def run_rollout(args):
         cores = os.cpu_count() or 1
         # same protocol as `--impl reference` (one scalar runner per host core, args.cpu_macros macro actions each, rate = env-steps /
         # busy time of the slowest runner); a short sample when other ranks are waiting
-        cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, args.cpu_macros if world == 1 else min(args.cpu_macros, 24), 1234, args.max_iter, task=args.task)
+        cpu_macros = args.cpu_macros if world == 1 else min(args.cpu_macros, 24)
+        cpu_rate, cpu_steps, cpu_busy, _ = cpu_rollout_rate(cores, cpu_macros, 1234, args.max_iter, task=args.task)
         line = {
             "metric": task_metric(args.task), "value": tot_steps / (wall_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -377,7 +378,7 @@ def run_rollout(args):
                          "second_bound": ncu_pipe(args.traffic_file),
                          "note": "75 substeps per env.step run on chip: the kernel is fp64 latency bound, not HBM bound (see DESIGN.md section 4)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d macro actions on each of %d scalar runners (%d env-steps, %.1f s)" % (args.cpu_macros, cores, cpu_steps, cpu_busy)},
+                             "sample": "%d macro actions on each of %d scalar runners (%d env-steps, %.1f s)" % (cpu_macros, cores, cpu_steps, cpu_busy)},
         }
         print(json.dumps(line))
     if world > 1:
@@ -512,7 +513,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10, help="untimed warm-up ticks (after the settle phase)")
     ap.add_argument("--settle", type=int, default=40, help="untimed ticks before the warm-up: lets the start-up planning burst (every env plans at tick 0) decay")
-    ap.add_argument("--slab", type=int, default=0, help="rows of the per-tick replay exchange block (0 = envs per GPU)")
+    ap.add_argument("--slab", type=int, default=0, help="rows of the per-tick replay exchange block (0 = half the envs per GPU, at least 1024)")
     ap.add_argument("--traffic-file", default="r2_envwarp_traffic.json", help="profiles/<file>: dram bytes per launch + pipe utilisation from the ncu capture")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
