@@ -201,6 +201,7 @@ _OBS_KEYS = {
              ("cube_pos", 3), ("cube_quat", 4), ("gripper_to_cube", 3)),
     "assembly": (("joint_pos", 7), ("joint_vel", 7), ("gripper_qpos", 2), ("gripper_qvel", 2), ("eef_pos", 3), ("eef_quat", 4),
                  ("hole", 3), ("pegHead", 3), ("pegEnd", 3), ("peg_quat", 4)),   # sawyer_assembly_obstacle.py:52-58
+    "pusher": (("default", 16), ("fingertip", 2), ("goal", 2)),                   # pusher_obstacle.py:185-205
 }
 
 
@@ -208,6 +209,9 @@ class SawyerEnvView(Env):
     """One environment with the reference's ``SawyerEnv`` surface (env/base.py, env/sawyer/sawyer.py)."""
     TASK = "push"
     VEC_CLASS = "VecSawyerPushObstacle"
+    ROBOT_JOINTS = tuple("right_j%d" % i for i in range(7))
+    GRIPPER_JOINTS = ("rc_close", "lc_close")
+    WORLD = ([-1.2, -1.2, 0.0], [1.2, 1.2, 2.0])   # env/sawyer/sawyer.py:52-53
 
     def __init__(self, seed=1234, device=0, max_episode_steps=250, venv=None, **kwargs):
         from . import envs
@@ -229,13 +233,13 @@ class SawyerEnvView(Env):
         self.xml_path = os.path.join(ASSET_DIR, _ALIASES[getattr(envs, self.VEC_CLASS).ENV_ID] + ".xml")
         self.max_episode_steps = int(max_episode_steps)
         self._ac_scale = float(self._venv.task.ac_scale)
-        self.robot_joints = ["right_j%d" % i for i in range(7)]
+        self.robot_joints = list(self.ROBOT_JOINTS)
         self.ref_joint_pos_indexes = [m.get_joint_qpos_addr(j) for j in self.robot_joints]
         self.ref_joint_vel_indexes = [m.get_joint_qvel_addr(j) for j in self.robot_joints]
-        self.ref_gripper_joint_pos_indexes = [m.get_joint_qpos_addr(j) for j in ("rc_close", "lc_close")]
+        self.ref_gripper_joint_pos_indexes = [m.get_joint_qpos_addr(j) for j in self.GRIPPER_JOINTS]
         self.dof = int(getattr(self._venv, "ACTION_DIM", 7))
-        self.robot_dof = 7
-        self.min_world_size, self.max_world_size = [-1.2, -1.2, 0.0], [1.2, 1.2, 2.0]   # env/sawyer/sawyer.py:52-53
+        self.robot_dof = len(self.robot_joints)
+        self.min_world_size, self.max_world_size = list(self.WORLD[0]), list(self.WORLD[1])
         # env/base.py:67-99: per-qpos joint index table, limits (unlimited -> +-3.14), joint_space
         self.jnt_indices = []
         for i, t in enumerate(m.jnt_type):
@@ -252,6 +256,10 @@ class SawyerEnvView(Env):
         cls = getattr(envs, self.VEC_CLASS)
         self.static_geom_ids = [g for g in range(m.ngeom) if body_of(g) in cls.STATIC_BODIES]
         self.manipulation_geom_ids = [g for g in range(m.ngeom) if body_of(g) in cls.MANIPULATION_BODIES]
+        if hasattr(cls, "planner_inputs"):   # envs that name geoms instead of bodies (PusherObstacleEnv.static_geoms / manipulation_geom)
+            ign, _, _ = cls.planner_inputs(m)
+            self.manipulation_geom_ids = sorted({a for a, b in ign} & {m.geom_name2id("box")}) or sorted({a for a, _ in ign})
+            self.static_geom_ids = sorted({g for pair in ign for g in pair} - set(self.manipulation_geom_ids))
         self._pending = None       # (done, info) of a compute_reward() call waiting for its _after_step()
         self._last = (0.0, False)
 
@@ -271,7 +279,8 @@ class SawyerEnvView(Env):
         info = {}
         if done:
             info = dict(episode_success=int(self._venv.success[0].item()), episode_reward=float(self._venv.ep_rew[0].item()),
-                        episode_length=int(self._venv.ep_len[0].item()), episode_unstable=0)
+                        episode_length=int(self._venv.ep_len[0].item()),
+                        episode_unstable=int(self._venv.unstable[0].item()) if hasattr(self._venv, "unstable") else 0)
         return info
 
     # ---- gym API
@@ -384,7 +393,24 @@ class SawyerAssemblyObstacleEnv(SawyerEnvView):
     TASK, VEC_CLASS = "assembly", "VecSawyerAssemblyObstacle"
 
 
+class PusherObstacleEnv(SawyerEnvView):
+    """PusherObstacle-v0 (env/pusher/pusher_obstacle.py; BASELINE configs[0]): 4-D joint-displacement actions, observation
+    keys default (cos / sin of the joint angles, box qpos, joint velocities, box velocity) / fingertip / goal."""
+    TASK, VEC_CLASS = "pusher", "VecPusherObstacle"
+    ROBOT_JOINTS = ("joint0", "joint1", "joint2", "joint3")
+    GRIPPER_JOINTS = ()
+    WORLD = ([-0.41, -0.41], [0.41, 0.41])        # pusher_obstacle.py:34-35
+
+    def form_action(self, next_qpos, curr_qpos=None):
+        """BaseEnv.form_action (env/base.py:402-410)."""
+        if curr_qpos is None:
+            curr_qpos = self._qpos_host()
+        next_qpos, curr_qpos = np.asarray(next_qpos), np.asarray(curr_qpos)
+        return OrderedDict([("default", next_qpos[self.ref_joint_pos_indexes] - curr_qpos[self.ref_joint_pos_indexes])])
+
+
 # env/__init__.py:7-32
+register("PusherObstacle-v0", PusherObstacleEnv)
 register("SawyerPushObstacle-v0", SawyerPushObstacleEnv)
 register("SawyerLiftObstacle-v0", SawyerLiftObstacleEnv)
 register("SawyerAssemblyObstacle-v0", SawyerAssemblyObstacleEnv)

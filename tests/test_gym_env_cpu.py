@@ -61,14 +61,15 @@ def test_gym_shim_and_registration():
     d = G.Dict([("default", b), ("ac_type", G.Discrete(2))])
     s = d.sample()
     assert list(s.keys()) == ["default", "ac_type"] and s["ac_type"] in (0, 1)
-    assert set(G._REGISTRY) >= {"SawyerPushObstacle-v0", "SawyerLiftObstacle-v0", "SawyerAssemblyObstacle-v0"}
+    assert set(G._REGISTRY) >= {"SawyerPushObstacle-v0", "SawyerLiftObstacle-v0", "SawyerAssemblyObstacle-v0", "PusherObstacle-v0"}
     with pytest.raises(KeyError):
         G.make("Nope-v0")
 
 
 @pytest.mark.parametrize("cls_name,scene,dof,obs_dim", [("SawyerPushObstacleEnv", "SawyerPushObstacle-v0", 7, 40),
                                                          ("SawyerLiftObstacleEnv", "SawyerLiftObstacle-v0", 8, 35),
-                                                         ("SawyerAssemblyObstacleEnv", "SawyerAssemblyObstacle-v0", 7, 38)])
+                                                         ("SawyerAssemblyObstacleEnv", "SawyerAssemblyObstacle-v0", 7, 38),
+                                                         ("PusherObstacleEnv", "PusherObstacle-v0", 4, 20)])
 def test_env_view_spaces_and_tables(cls_name, scene, dof, obs_dim):
     from mopa_rl_b200 import gym_env as G
     from mopa_rl_b200.model import load_model
@@ -80,16 +81,26 @@ def test_env_view_spaces_and_tables(cls_name, scene, dof, obs_dim):
     ob = env.reset()
     assert isinstance(ob, OrderedDict) and np.array_equal(np.concatenate(list(ob.values())), np.arange(obs_dim))
     # observation keys in the reference's order (env/sawyer/sawyer.py:317-338 + the task's _get_obs)
-    tail = {"SawyerPushObstacleEnv": ["target_pos", "cube_pos", "cube_quat", "gripper_to_cube", "cube_to_target"],
-            "SawyerLiftObstacleEnv": ["cube_pos", "cube_quat", "gripper_to_cube"],
-            "SawyerAssemblyObstacleEnv": ["hole", "pegHead", "pegEnd", "peg_quat"]}[cls_name]
-    assert list(ob.keys()) == ["joint_pos", "joint_vel", "gripper_qpos", "gripper_qvel", "eef_pos", "eef_quat"] + tail
+    pusher = cls_name == "PusherObstacleEnv"
+    if pusher:   # env/pusher/pusher_obstacle.py:185-205
+        assert list(ob.keys()) == ["default", "fingertip", "goal"] and [len(v) for v in ob.values()] == [16, 2, 2]
+    else:
+        tail = {"SawyerPushObstacleEnv": ["target_pos", "cube_pos", "cube_quat", "gripper_to_cube", "cube_to_target"],
+                "SawyerLiftObstacleEnv": ["cube_pos", "cube_quat", "gripper_to_cube"],
+                "SawyerAssemblyObstacleEnv": ["hole", "pegHead", "pegEnd", "peg_quat"]}[cls_name]
+        assert list(ob.keys()) == ["joint_pos", "joint_vel", "gripper_qpos", "gripper_qvel", "eef_pos", "eef_quat"] + tail
     # env/base.py:67-99: one jnt_indices entry per qpos element, free joints count 7 times; unlimited joints +-3.14
     assert len(env.jnt_indices) == m.nq and env.sim.model.nq == m.nq
     lim = np.asarray(m.jnt_limited).astype(bool)
     assert np.all(env._jnt_minimum[~lim] == -3.14) and np.all(env._jnt_maximum[~lim] == 3.14)
     assert np.array_equal(env._jnt_minimum[lim], m.jnt_range[lim, 0])
     assert env.joint_space["default"].shape == (m.njnt,)
+    if pusher:
+        assert env.ref_joint_pos_indexes == list(range(4)) and not lim[0] and env.min_world_size == [-0.41, -0.41]
+        assert [m.names["geom"][g] if "geom" in m.names else g for g in env.manipulation_geom_ids] and len(env.static_geom_ids) == 7
+        assert env.manipulation_geom_ids == [m.geom_name2id("box")]
+        assert np.allclose(env.form_action(m.qpos0 + 0.03)["default"], 0.03) and len(env.form_action(m.qpos0)["default"]) == 4
+        return
     assert env.ref_joint_pos_indexes == list(range(7)) and env._ac_scale == 0.05
     cube_like = set(m.names["body"][m.geom_bodyid[g]] for g in env.manipulation_geom_ids)
     assert cube_like and all(m.names["body"][m.geom_bodyid[g]] in ("table", "bin1") for g in env.static_geom_ids)

@@ -21,25 +21,40 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BENCH_SEED_ENV, BENCH_SEED_POLICY, BENCH_SEED_CFG = 1234, 1241, 1234   # bench.py: venv seed 1234, policy seed + 7, MoPAConfig.seed
 
 
+TASKS = {   # task -> (env id, envs per GPU of the bench configuration, omega of scripts/3d/<task>/mopa.sh, action dims, subset size)
+    "push": ("SawyerPushObstacle-v0", 4096, 0.7, 7, 64),
+    "assembly": ("SawyerAssemblyObstacle-v0", 16384, 0.7, 7, 32),
+    "lift": ("SawyerLiftObstacle-v0", 1024, 0.5, 8, 32),
+}
+
+
+def _task_cls(task):
+    from mopa_rl_b200 import envs
+
+    return {"push": envs.VecSawyerPushObstacle, "assembly": envs.VecSawyerAssemblyObstacle, "lift": envs.VecSawyerLiftObstacle}[task]
+
+
 def _scalar_episode(args):
     """Worker: the scalar loop of one environment until its first episode ends; logs the state after every env.step."""
-    gid, horizon = args
+    gid, horizon = args[:2]
+    task = args[2] if len(args) > 2 else "push"
     sys.path.insert(0, ROOT)
     from mopa_rl_b200 import rng
     from mopa_rl_b200.dynmodel import DynModel
     from mopa_rl_b200.model import load_model
-    from mopa_rl_b200.rollout import MoPAConfig, planner_inputs
+    from mopa_rl_b200.rollout import MoPAConfig, env_planner_inputs
     from oracle.rollout_oracle import ScalarMoPARunner
 
-    model = load_model("SawyerPushObstacle-v0")
-    ignored, passive, _ = planner_inputs(model)
-    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG)
+    env_id, _, omega, adim, _ = TASKS[task]
+    model = load_model(env_id)
+    ignored, passive, _ = env_planner_inputs(_task_cls(task), model)
+    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG, omega=omega)
 
     def policy(g, k):
-        u = rng.uniform01(BENCH_SEED_POLICY, np.uint64(g), np.uint64(k), np.arange(7, dtype=np.uint64))
+        u = rng.uniform01(BENCH_SEED_POLICY, np.uint64(g), np.uint64(k), np.arange(adim, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), cfg, ignored, passive, gid, BENCH_SEED_ENV, policy, max_episode_steps=horizon)
+    r = ScalarMoPARunner(model, DynModel(model), cfg, ignored, passive, gid, BENCH_SEED_ENV, policy, max_episode_steps=horizon, task=task)
     states, env = {}, r.env
     step0, null0 = env.step, env.null_step
 
@@ -65,20 +80,24 @@ def _scalar_episode(args):
     return gid, np.stack([states[k][0] for k in range(1, n + 1)]), np.stack([states[k][1] for k in range(1, n + 1)]), np.stack(records)
 
 
-def test_bench_config_subset_matches_scalar_loop_over_a_full_episode(oracle_built):
+@pytest.mark.parametrize("task", ["push", "assembly", "lift"])
+def test_bench_config_subset_matches_scalar_loop_over_a_full_episode(oracle_built, task):
+    """push: BASELINE configs[1] (4096 envs); assembly: configs[3] (16384 envs, max_iter 1000); lift: the per-GPU share of
+    configs[2] (1024 envs, omega 0.5)."""
     import torch
 
-    from mopa_rl_b200.envs import VecSawyerPushObstacle
     from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner
 
-    n, horizon, nsub = 4096, 250, 64
-    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG)
-    venv = VecSawyerPushObstacle(n, seed=BENCH_SEED_ENV, max_episode_steps=horizon)
-    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, BENCH_SEED_POLICY))
+    _, n, omega, adim, nsub = TASKS[task]
+    horizon, no = 250, _task_cls(task).OBS_DIM
+    cfg = MoPAConfig(max_iter=1000, reuse_data=True, max_reuse_data=15, seed=BENCH_SEED_CFG, omega=omega)
+    venv = _task_cls(task)(n, seed=BENCH_SEED_ENV, max_episode_steps=horizon)
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=CounterPolicy(torch, venv.dev, BENCH_SEED_POLICY, action_dim=adim),
+                                     transition_capacity=max(1 << 20, n * 512))   # every record of the run must still be in the ring at the end
     subset = np.sort(np.random.default_rng(2026).choice(n, nsub, replace=False))
     sub_t = torch.as_tensor(subset, device=venv.dev)
     with mp.get_context("fork").Pool(min(nsub, os.cpu_count() or 1)) as pool:
-        job = pool.map_async(_scalar_episode, [(int(g), horizon) for g in subset])
+        job = pool.map_async(_scalar_episode, [(int(g), horizon, task) for g in subset])
         # device side: tick until every subset env has finished its first episode; log (episode, ep_len, qpos, qvel) per tick
         logs = {int(g): {} for g in subset}
         episode = np.zeros(nsub, np.int64)
@@ -131,13 +150,13 @@ def test_bench_config_subset_matches_scalar_loop_over_a_full_episode(oracle_buil
         mine = rec[rec[:, 51] == gid][:len(srec)]
         assert len(mine) == len(srec), (gid, len(mine), len(srec))
         for k, (r, o) in enumerate(zip(mine, srec)):   # the macro-action structure agrees for every environment
-            assert np.allclose(r[40:47], o[40:47], atol=1e-6), (gid, k)
+            assert np.allclose(r[40:40 + adim], o[40:40 + adim], atol=1e-6), (gid, k)
             assert r[49] == o[49] and r[50] == o[50], (gid, k, r[48:51], o[48:51])
             if first_heavy > len(sq):
                 assert abs(r[48] - o[48]) < 1e-4, (gid, k, r[48], o[48])
-                worst_obs = max(worst_obs, np.abs(r[0:40] - o[0:40]).max(), np.abs(r[52:92] - o[52:92]).max())
+                worst_obs = max(worst_obs, np.abs(r[0:no] - o[0:no]).max(), np.abs(r[52:52 + no] - o[52:52 + no]).max())
         n_rec += len(srec)
-    print("bench-config parity: %d envs x %d env.steps, %d records; %d env.steps before any heavy-contact step: max |dqpos| %.3e, max |dqvel| %.3e "
+    print(task + " bench-config parity: %d envs x %d env.steps, %d records; %d env.steps before any heavy-contact step: max |dqpos| %.3e, max |dqvel| %.3e "
           "(after 1 / 75 / 250 env.steps: %.3e / %.3e / %.3e), max |dobs| %.3e; %d env.steps at / after a heavy-contact step: max |dqpos| %.3e, "
           "max |dqvel| %.3e; %d of %d environments within 1e-5 over the whole episode; counters %s"
           % (nsub, horizon, n_rec, n_steps, worst_q, worst_v, err_at[1], err_at[75], err_at[250], worst_obs, n_late, late_q, late_v, clean_envs, nsub,
