@@ -285,7 +285,7 @@ def run_rollout(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
     cfg = task_config(args.task, args.max_iter)   # scripts/3d/<task>/mopa.sh
-    slab = args.slab or max(1024, n // 2)   # steady state emits ~0.32 n records per tick; bursts queue up and drain over the next ticks
+    slab = args.slab or max(1024, n)   # steady state emits ~0.67 n records per tick (main + relabelled, push preset); bursts queue up and drain
 
     def barrier():
         torch.cuda.synchronize()
@@ -513,7 +513,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10, help="untimed warm-up ticks (after the settle phase)")
     ap.add_argument("--settle", type=int, default=40, help="untimed ticks before the warm-up: lets the start-up planning burst (every env plans at tick 0) decay")
-    ap.add_argument("--slab", type=int, default=0, help="rows of the per-tick replay exchange block (0 = half the envs per GPU, at least 1024)")
+    ap.add_argument("--slab", type=int, default=0, help="rows of the per-tick replay exchange block (0 = envs per GPU, at least 1024)")
     ap.add_argument("--traffic-file", default="r2_envwarp_traffic.json", help="profiles/<file>: dram bytes per launch + pipe utilisation from the ncu capture")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
