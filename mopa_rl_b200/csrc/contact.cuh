@@ -298,6 +298,37 @@ DYN_HD inline int pair_contacts(CPoint *out, const CGeom &ga, const CGeom &gb, d
                 for (int k = 0; k < 3; k++) { out[n].n[k] = pn[k]; out[n].pos[k] = c[k] - pn[k] * (g2.size[0] + 0.5 * dist); }
                 n++;
             }
+        } else if (t2 == 5) {
+            // plane - cylinder, the construction of MuJoCo's mjc_PlaneCylinder: the deepest rim point of the cap that faces the
+            // plane, the rim point of the other cap in the same radial direction, and - for a cylinder lying nearly flat on that
+            // cap - two more points of its rim (a triangle with the first one).
+            double a[3], vec[3];
+            c_colk(a, g2.R, 2);
+            double prj = d_dot(pn, a);
+            if (prj > 0) { for (int k = 0; k < 3; k++) a[k] = -a[k]; prj = -prj; }   // a points towards the plane
+            for (int k = 0; k < 3; k++) vec[k] = a[k] * prj - pn[k];                     // radial direction of steepest descent
+            double len = sqrt(d_dot(vec, vec));
+            if (len < 1e-12) {   // axis parallel to the normal: any radial direction (MuJoCo takes the cylinder's x axis)
+                c_colk(vec, g2.R, 0);
+                len = 1.0;
+            }
+            for (int k = 0; k < 3; k++) vec[k] *= g2.size[0] / len;
+            const double hh = g2.size[1];
+            double P[4][3], v1[3];
+            d_cross(v1, vec, a);
+            for (int k = 0; k < 3; k++) {
+                P[0][k] = g2.c[k] + hh * a[k] + vec[k];
+                P[1][k] = g2.c[k] - hh * a[k] + vec[k];
+                P[2][k] = g2.c[k] + hh * a[k] - 0.5 * vec[k] + 0.8660254037844386 * v1[k];
+                P[3][k] = g2.c[k] + hh * a[k] - 0.5 * vec[k] - 0.8660254037844386 * v1[k];
+            }
+            for (int q = 0; q < 4; q++) {
+                const double dist = (P[q][0] - g1.c[0]) * pn[0] + (P[q][1] - g1.c[1]) * pn[1] + (P[q][2] - g1.c[2]) * pn[2];
+                if (dist >= margin) continue;
+                out[n].dist = dist;
+                for (int k = 0; k < 3; k++) { out[n].n[k] = pn[k]; out[n].pos[k] = P[q][k] - pn[k] * 0.5 * dist; }
+                n++;
+            }
         } else if (t2 == 6) {
             for (int q = 0; q < 8 && n < 4; q++) {
                 double l[3] = {(q & 1 ? 1 : -1) * g2.size[0], (q & 2 ? 1 : -1) * g2.size[1], (q & 4 ? 1 : -1) * g2.size[2]}, c[3];

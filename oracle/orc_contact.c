@@ -314,6 +314,32 @@ static int pair_contacts(cpoint *out, const cgeom *ga, const cgeom *gb, double m
                 for (int k = 0; k < 3; k++) { out[n].n[k] = pn[k]; out[n].pos[k] = c[k] - pn[k] * (g2->size[0] + 0.5 * dist); }
                 n++;
             }
+        } else if (t2 == 5) {
+            /* plane - cylinder as MuJoCo's mjc_PlaneCylinder builds it: deepest rim point of the cap facing the plane, the rim
+               point of the other cap in the same radial direction, two more rim points of the near cap (triangle) */
+            double a[3], vec[3], v1[3], P[4][3];
+            colk(a, g2->R, 2);
+            double prj = dot3(pn, a);
+            if (prj > 0) { for (int k = 0; k < 3; k++) a[k] = -a[k]; prj = -prj; }
+            for (int k = 0; k < 3; k++) vec[k] = a[k] * prj - pn[k];
+            double len = sqrt(dot3(vec, vec));
+            if (len < 1e-12) { colk(vec, g2->R, 0); len = 1.0; }
+            for (int k = 0; k < 3; k++) vec[k] *= g2->size[0] / len;
+            const double hh = g2->size[1];
+            cross3(v1, vec, a);
+            for (int k = 0; k < 3; k++) {
+                P[0][k] = g2->c[k] + hh * a[k] + vec[k];
+                P[1][k] = g2->c[k] - hh * a[k] + vec[k];
+                P[2][k] = g2->c[k] + hh * a[k] - 0.5 * vec[k] + 0.8660254037844386 * v1[k];
+                P[3][k] = g2->c[k] + hh * a[k] - 0.5 * vec[k] - 0.8660254037844386 * v1[k];
+            }
+            for (int q = 0; q < 4; q++) {
+                double dist = (P[q][0] - g1->c[0]) * pn[0] + (P[q][1] - g1->c[1]) * pn[1] + (P[q][2] - g1->c[2]) * pn[2];
+                if (dist >= margin) continue;
+                out[n].dist = dist;
+                for (int k = 0; k < 3; k++) { out[n].n[k] = pn[k]; out[n].pos[k] = P[q][k] - pn[k] * 0.5 * dist; }
+                n++;
+            }
         } else if (t2 == 6) {
             for (int q = 0; q < 8 && n < 4; q++) {
                 double l[3] = {(q & 1 ? 1 : -1) * g2->size[0], (q & 2 ? 1 : -1) * g2->size[1], (q & 4 ? 1 : -1) * g2->size[2]}, c[3];

@@ -196,6 +196,56 @@ def test_lift_env_step_matches_oracle(oracle_built):
     print("lift max abs error:", worst, sorted(kinds))
 
 
+def test_lift_can_on_the_ground_plane_matches_oracle(oracle_built):
+    """Plane - cylinder contacts (mjc_PlaneCylinder): the can dropped onto the ground beside the table, standing, lying on its side and
+    tilted so that it lands on its rim and tumbles; kernel and oracle integrate the same trajectory."""
+    import torch
+
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerLiftObstacle, lift_reset_state
+    from mopa_rl_b200.model import load_model
+    from oracle.env_oracle import LiftEnvOracle
+
+    model = load_model("SawyerLiftObstacle-v0")
+    n = 12
+    venv = VecSawyerLiftObstacle(n, seed=3, max_episode_steps=20)
+    venv.reset()
+    dm = DynModel(model)
+    q0, v0 = lift_reset_state(model, 3, np.arange(n), np.zeros(n, dtype=np.int64))
+    a = model.get_joint_qpos_addr("cube")[0]
+    va = model.get_joint_qvel_addr("cube")[0]
+    rng = np.random.default_rng(8)
+    for i in range(n):
+        q0[i, a:a + 3] = [-0.6 + 0.02 * i, 0.9, 0.06 + 0.01 * (i % 3)]
+        if i % 3 == 0:
+            quat = np.array([1.0, 0.0, 0.0, 0.0])
+        elif i % 3 == 1:
+            quat = np.array([np.sqrt(0.5), np.sqrt(0.5), 0.0, 0.0])
+        else:
+            quat = rng.normal(size=4)
+        q0[i, a + 3:a + 7] = quat / np.linalg.norm(quat)
+        v0[i, va:va + 3] = rng.uniform(-0.3, 0.3, 3)
+    venv.set_state(np.arange(n), q0, v0)
+    envs = [LiftEnvOracle(model, dm, max_episode_steps=20) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.reset_to(q0[i], v0[i])
+    worst, touched = 0.0, 0
+    for s in range(6):
+        act = np.zeros((n, 8), np.float32)
+        act[:, :7] = rng.uniform(-0.3, 0.3, (n, 7))
+        venv.step(torch.as_tensor(act, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda"))
+        torch.cuda.synchronize()
+        gq, gv = venv.qpos.cpu().numpy(), venv.qvel.cpu().numpy()
+        for i, e in enumerate(envs):
+            e.step(act[i].astype(np.float64), False)
+            worst = max(worst, np.abs(gq[i] - e.qpos).max(), np.abs(gv[i] - e.qvel).max())
+            touched += int(s == 5 and e.qpos[a + 2] < 0.06 and np.abs(e.qvel[va + 2]) < 0.5)
+    assert touched >= 8, touched                           # the cans are held up by the ground, not falling through it
+    assert min(e.qpos[a + 2] for e in envs) > 0.02
+    assert worst < TOL, worst
+    print("can on the ground max abs error:", worst)
+
+
 def test_gym_env_view_drop_in_loop(push_model, oracle_built):
     """The reference-facing N = 1 view (gym_env.make, env/__init__.py:7-32 + BaseEnv API) driven the way
     rl/trainer.py:62-75 and rl/mopa_rollouts.py drive the reference env - trainer-style planner set-up from the env's

@@ -262,3 +262,38 @@ def test_pusher_env_oracle_tracks_pushes_and_matches_golden(pusher):
         moved = moved or np.abs(env.qpos[-2:] - g["qpos0"][-2:]).max() > 0.01
         assert 0.0 < r < 0.1 and not d
     assert moved and g["ncon"].max() >= 1
+
+
+# ---------------------------------------------------------------------------- plane - cylinder contacts (the lift can on the ground plane)
+def test_can_rests_on_the_ground_plane_upright_and_on_its_side(oracle_built):
+    """engine_collision_primitive.c mjc_PlaneCylinder: up to three points under the rim nearest the plane when the can stands (disc contact),
+    two along the lowest generator when it lies on its side.  Known answers: the can's centre settles at half height / radius above the
+    ground (sub-mm sink), it keeps its orientation and it stops."""
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.model import load_model
+    from oracle.oracle import OracleDyn
+
+    m = load_model("SawyerLiftObstacle-v0")
+    dm = DynModel(m)
+    A = dm._arr
+    gi = [i for i, g in enumerate(dm.geoms) if g == m.geom_name2id("cube")][0]
+    assert int(A["g_type"][gi]) == 5
+    r, hh = float(A["g_size"][gi][0]), float(A["g_size"][gi][1])
+    off = float(A["g_pos"][gi][2])
+    a = m.get_joint_qpos_addr("cube")[0]
+    va = m.get_joint_qvel_addr("cube")[0]
+    od = OracleDyn(dm)
+    for quat, rest, ncon_want in (([1.0, 0.0, 0.0, 0.0], hh - off, 3), ([np.sqrt(0.5), np.sqrt(0.5), 0.0, 0.0], r, 2)):
+        q = m.qpos0.copy()
+        v = np.zeros(m.nv)
+        q[a:a + 3] = [-0.6, 0.9, rest + 0.05]        # clear of the table and the robot pedestal
+        q[a + 3:a + 7] = quat
+        bias = np.zeros(dm.nd)
+        comp = np.zeros(dm.nd, np.int32)
+        ctrl = np.array([q[int(dm.dof_qadr[int(k)])] for k in A["a_dof"]])   # position actuators hold the arm where it is
+        for _ in range(8):
+            q, v, bias, _, _, ncon = od.step(q, v, ctrl, comp, bias, 75)
+        assert ncon == ncon_want, (quat, ncon)
+        assert rest - 1.5e-3 < q[a + 2] < rest + 1e-4, (quat, q[a + 2], rest)
+        assert np.abs(v[va:va + 3]).max() < 1e-3
+        assert abs(abs(np.dot(q[a + 3:a + 7], quat)) - 1.0) < 1e-3           # neither tips over nor rolls away
