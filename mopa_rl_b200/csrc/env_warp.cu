@@ -51,8 +51,16 @@ struct WarpWS {
     double q[36], v[36];
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
         WarpKin<WB> k;
-        double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
+        struct {
+            double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
+            // Behind A lie k.vel / k.frc / k.inert, dead once the inertia matrix exists: the factor of M + h * diag(damping)
+            // (implicit joint damping of the Euler update) is produced there by the upper half-warp while the lower one
+            // factors M, and waits for the velocity update at the end of the substep.
+            double L2[NTRI], invd2[WD];
+            alignas(16) double col2[2 * (WD + 2)];
+        };
     };
+    static_assert(WC * WD >= WB * 16 + WD * 6, "A must cover xpos / xquat / xmat / S so that L2 only overlaps arrays dead after stage 3");
     double kxpos[4][3], kxquat[2][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
     double M[NTRI], L[NTRI], invd[WD];
     double qd[WD], bias[WD], tau[WD], qacc0[WD], a[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
@@ -99,10 +107,10 @@ __device__ __forceinline__ double warp_sum(double x) {
 // solves of the caller.  Rows / columns nd..WD-1 are identity padding (no bound checks inside).
 //   (M + hs * diag) = L L^T,  x <- (M + hs * diag)^-1 x      x: shared, nd entries; col: shared, WD + 2 doubles, 16-byte aligned
 template <int J, int K>
-__device__ __forceinline__ void wfs_update(double (&row)[WD], const double (&c)[WD], int lane) {
+__device__ __forceinline__ void wfs_update(double (&row)[WD], const double (&c)[WD], int li) {
     if constexpr (K < WD) {
-        if (lane >= K) row[K] -= row[J] * c[K];
-        wfs_update<J, K + 1>(row, c, lane);
+        if (li >= K) row[K] -= row[J] * c[K];
+        wfs_update<J, K + 1>(row, c, li);
     }
 }
 template <int J, int K2>
@@ -114,53 +122,76 @@ __device__ __forceinline__ void wfs_fetch(double (&c)[WD], const double *col) {
     }
 }
 template <int J>
-__device__ __forceinline__ void wfs_column(double (&row)[WD], double &xr, double &rme, int lane, double *col) {
+__device__ __forceinline__ void wfs_column(double (&row)[WD], double &xr, double &rme, int li, bool act, double *col) {
     if constexpr (J < WD) {
-        if (lane == J) { col[WD] = row[J]; col[WD + 1] = xr; }
+        if (li == J && act) { col[WD] = row[J]; col[WD + 1] = xr; }
         __syncwarp();
         const double djj = col[WD], rinv = rsqrt(djj), yj = col[WD + 1] * rinv;
-        if (lane == J) { row[J] = djj * rinv; rme = rinv; xr = yj; }
-        else if (lane > J) { row[J] *= rinv; xr -= row[J] * yj; if (lane < WD) col[lane] = row[J]; }
+        if (li == J) { row[J] = djj * rinv; rme = rinv; xr = yj; }
+        else if (li > J) { row[J] *= rinv; xr -= row[J] * yj; if (act) col[li] = row[J]; }
         __syncwarp();
         if constexpr (J + 1 < WD) {
             double c[WD];
             wfs_fetch<J, (J + 1) / 2>(c, col);
-            wfs_update<J, J + 1>(row, c, lane);
+            wfs_update<J, J + 1>(row, c, li);
         }
-        wfs_column<J + 1>(row, xr, rme, lane, col);
+        wfs_column<J + 1>(row, xr, rme, li, act, col);
     }
 }
 template <int K>
-__device__ __forceinline__ void wfs_load(double (&row)[WD], const double *Msrc, double dd, int lane, bool live) {
+__device__ __forceinline__ void wfs_load(double (&row)[WD], const double *Msrc, double dd, int li, bool live) {
     if constexpr (K < WD) {
-        row[K] = (live && K <= lane) ? Msrc[TRI(lane, K)] : 0.0;
-        if (K == lane) row[K] = live ? row[K] + dd : 1.0;
-        wfs_load<K + 1>(row, Msrc, dd, lane, live);
+        row[K] = (live && K <= li) ? Msrc[TRI(li, K)] : 0.0;
+        if (K == li) row[K] = live ? row[K] + dd : 1.0;
+        wfs_load<K + 1>(row, Msrc, dd, li, live);
     }
 }
 template <int K>
-__device__ __forceinline__ void wfs_store(const double (&row)[WD], double *Lout, int lane, bool live) {
+__device__ __forceinline__ void wfs_store(const double (&row)[WD], double *Lout, int li, bool live) {
     if constexpr (K < WD) {
-        if (live && K <= lane) Lout[TRI(lane, K)] = row[K];
-        wfs_store<K + 1>(row, Lout, lane, live);
+        if (live && K <= li) Lout[TRI(li, K)] = row[K];
+        wfs_store<K + 1>(row, Lout, li, live);
     }
 }
+// Lanes 0..15 factor Msrc + hs * diag and solve for x.  When Lout2 is given, lanes 16..31 factor Msrc + hs2 * diag2 in the same
+// instruction stream (factor only: Lout2 / invd2 feed w_solve_stored later); `col` then holds 2 x (WD + 2) doubles.
 __device__ __noinline__ void w_factor_solve(const double *Msrc, const double *diag, double hs, int nd, double *Lout, double *invd, double *x,
-                                            double *col, int lane) {
+                                            double *col, int lane, double *Lout2 = nullptr, double *invd2 = nullptr,
+                                            const double *diag2 = nullptr, double hs2 = 0.0) {
     double row[WD];
-    const bool live = lane < nd;
-    wfs_load<0>(row, Msrc, (diag && live) ? hs * diag[lane] : 0.0, lane, live);
-    double xr = live ? x[lane] : 0.0, rme = 0.0;
-    wfs_column<0>(row, xr, rme, lane, col);
-    wfs_store<0>(row, Lout, lane, live);
-    if (live) invd[lane] = rme;
+    const int li = lane & 15, half = lane >> 4;
+    const bool act = half == 0 || Lout2 != nullptr;   // this half-warp owns a matrix
+    const bool live = act && li < nd;
+    const double *dg = half ? diag2 : diag;
+    wfs_load<0>(row, Msrc, (dg && live) ? (half ? hs2 : hs) * dg[li] : 0.0, li, live);
+    double xr = (live && half == 0) ? x[li] : 0.0, rme = 0.0;
+    wfs_column<0>(row, xr, rme, li, act, col + (act ? half * (WD + 2) : 0));
+    wfs_store<0>(row, half ? Lout2 : Lout, li, live);
+    if (live) (half ? invd2 : invd)[li] = rme;
     __syncwarp();
-    // backward substitution L^T x = y: lane i publishes x_i, the lanes above it eliminate
+    // backward substitution L^T x = y: lane i broadcasts x_i, the lanes below it eliminate
     for (int i = nd - 1; i >= 0; i--) {
-        if (lane == i) { xr *= rme; col[WD] = xr; }
-        __syncwarp();
-        if (lane < i) xr -= Lout[TRI(i, lane)] * col[WD];
-        __syncwarp();
+        const double xi = shfl_d(xr * rme, i);
+        if (lane == i) xr = xi;
+        else if (lane < i) xr -= Lout[TRI(i, lane)] * xi;
+    }
+    if (lane < nd) x[lane] = xr;
+    __syncwarp();
+}
+// x <- (L L^T)^-1 x with a factor w_factor_solve stored earlier (same operation order as its fused forward substitution)
+__device__ __noinline__ void w_solve_stored(const double *L, const double *invd, int nd, double *x, int lane) {
+    const bool live = lane < nd;
+    double xr = live ? x[lane] : 0.0;
+    const double rme = live ? invd[lane] : 0.0;
+    for (int i = 0; i < nd; i++) {
+        const double yi = shfl_d(xr * rme, i);
+        if (lane == i) xr = yi;
+        else if (lane > i && live) xr -= L[TRI(lane, i)] * yi;
+    }
+    for (int i = nd - 1; i >= 0; i--) {
+        const double xi = shfl_d(xr * rme, i);
+        if (lane == i) xr = xi;
+        else if (lane < i) xr -= L[TRI(i, lane)] * xi;
     }
     if (live) x[lane] = xr;
     __syncwarp();
@@ -534,7 +565,8 @@ __device__ __noinline__ bool w_stage_dynamics(const DynDev &m, const DynDev *__r
     STAGE_SYNC(3);   // 3: inertia matrix and forces done
     if (lane < nd) W.qacc0[lane] = W.tau[lane];
     __syncwarp();
-    w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.f, lane);
+    // upper half-warp: the factor the velocity update needs (Euler: M + h * diag(damping); explicit RK4 stage: M itself)
+    w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
 
     STAGE_SYNC(4);   // 4: unconstrained acceleration done
     return true;
@@ -1050,12 +1082,12 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
     if (RK && smode == 2) {   // explicit stage of mj_RungeKutta: qacc = M^-1 (tau + J^T f), joint damping is part of tau
-        w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.f, lane);
+        w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane);
         STAGE_SYNC(7);
         return;
     }
-    // ---- semi-implicit Euler with implicit joint damping
-    w_factor_solve(W.M, m.d_damping, m.h, nd, W.L, W.invd, W.rhs, W.f, lane);
+    // ---- semi-implicit Euler with implicit joint damping (factor of M + h * diag(damping) from stage 4)
+    w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane);
     if (lane < nd) {
         W.qd[lane] += m.h * W.rhs[lane];
         W.v[m.d_vadr[lane]] = W.qd[lane];

@@ -20,3 +20,4 @@ for k in range(1, 8):
     print("stage %d %-12s work %5.1f%%  wait %5.1f%%" % (k, names[k - 1], 100 * v[2 * k] / tot, 100 * v[2 * k + 1] / tot))
 print("within 5: broadphase %.1f%%  narrowphase %.1f%%;  within 6: rows %.1f%%  Newton %.1f%%" % tuple(100 * v[k] / tot for k in (23, 24, 25, 26)))
 print("newton steps per substep %.3f" % (v[20] / max(v[22], 1)))
+print("clocks per constrained substep (lane 0 of every warp, all stages): %.0f; constrained substeps %.3g" % (tot / max(v[22], 1), v[22]))
