@@ -143,14 +143,14 @@ __device__ __forceinline__ bool states_all_valid(const WarpCtx &W, const SpaceDe
         fk_state(W.S, rq, W.frames, PW_STATES, lane);
     }
     __syncwarp();
-    const int npair = W.S.H->n_pair;
+    const int npair = W.S.H->n_real;   // the non-dummy entries of the pair table
     const int total = count * npair;
     const float thr = W.S.H->threshold;
     bool bad = false;
     for (int base = 0; base < total; base += 32) {
         const int i = base + lane;
         if (i < total) {
-            const int k = i / npair, p = i - k * npair;
+            const int k = i / npair, p = W.S.real[i - k * npair];
             const PairRec pr = W.S.pairs[p];
             const bool survive = cull_survives(pr, W.S.cull[p], W.frames, PW_STATES, k);
             if (survive && pr.cls <= PC_MPR) {

@@ -51,10 +51,14 @@ struct GeomRec {  // every collidable geom that appears in at least one candidat
     int geom_id;     // mjModel geom id
     int pad;
 };
-// Candidate pairs, in kernel order: sorted by the kind of cull test, then by anchor (the first moving geom); runs are padded
-// to multiples of four with dummy pairs (cls = PC_NONE) that never survive the cull.  Two parallel arrays, 16 bytes per pair each: what the narrow
-// phase needs (PairRec) and what the cull sweep needs (CullEntry); runs of pairs with the same (cull kind, anchor) are
-// described by CullGroup records so that the sweep loads the anchor centre once per run and has branch-free inner loops.
+// Candidate pairs, in kernel order: sorted by the kind of cull test, then by anchor (the first moving geom).  Two parallel arrays,
+// 16 bytes per pair each: what the narrow phase needs (PairRec) and what the cull sweep needs (CullEntry).  Runs of pairs with the
+// same (cull kind, anchor) are described by CullGroup records: the sweep loads the anchor centre once per run and has branch-free
+// inner loops.  The arrays are laid out in windows of 32 entries (one survivor mask word per window): a run never straddles a
+// window (longer runs are split), runs are padded to multiples of four and windows are filled up with dummy pairs (cls = PC_NONE)
+// that never survive a cull test.  `real` lists the indices of the non-dummy entries for consumers that walk the pairs one by one.
+// Pairs of a moving and a static geom whose bounding spheres can never touch, whatever the joint angles, are dropped when the
+// scene is built (scene_build.cu: reach spheres).
 struct PairRec {
     uint16_t anchor_slot, partner_slot;  // frame-store offsets; partner_slot == 0xFFFF: static partner
     uint16_t ga, gb;    // GeomRec indices, kind(ga) <= kind(gb)  (the order the narrowphase expects)
@@ -69,8 +73,13 @@ enum CullKind : int {
     CK_PLANE = 2,           // e = (unit normal of the static plane, offset): cull when dot(normal, anchor centre) > e.w
     CK_NONE = 3             // always passed to the narrow phase
 };
-struct CullEntry { float x, y, z, w; };
-struct CullGroup { uint16_t anchor_slot, kind, count, pad; };
+struct alignas(16) CullEntry { float x, y, z, w; };
+struct CullGroup {
+    uint16_t anchor_slot;   // frame-store offset of the anchor centre
+    uint8_t kind, count;    // CullKind; entries in the run (multiple of four, <= 32)
+    uint8_t bitpos, flush;  // position of the run's first entry in its window; last run of the window
+    uint16_t first;         // index of the run's first entry
+};
 
 struct SceneHeader {
     int nq, nq4;             // qpos row length, and in float4 units (row stride = 4*nq4 floats)
@@ -83,6 +92,8 @@ struct SceneHeader {
     int off_hull;            // hull vertices of collision meshes (float xyz triplets)
     int n_hull_vert;
     int off_cull, off_group, n_group;   // CullEntry[n_pair] (parallel to the pair records), CullGroup[n_group]
+    int off_real, n_real;               // uint16 indices of the non-dummy pair entries
+    int n_pruned;                       // candidate pairs dropped at build time (bounding spheres out of reach for every joint configuration)
 };
 
 struct HostScene {

@@ -6,6 +6,7 @@
 // the query-independent half of MuJoCo's collision pipeline: the
 // candidate-pair filters and the world frames of world-welded geoms.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -54,6 +55,67 @@ static int append(std::vector<unsigned char> &blob, const std::vector<T> &v) {
     const unsigned char *p = (const unsigned char *)v.data();
     blob.insert(blob.end(), p, p + sizeof(T) * v.size());
     return off;
+}
+
+// ---- reach spheres.  Where can the centre of a geom be, whatever the joint values?  Walking from the geom's body up to `stop`
+// (exclusive), a sphere (c, r) in the current body's frame is carried through the body's joints - a hinge sweeps the centre on a
+// circle around its axis (any angle), a limited slide moves it along its axis (three times the joint range is allowed for,
+// soft limits are overshot in simulation), free / ball / unlimited slide joints give up - and through the body's fixed offset
+// into the parent's frame.  The result bounds the centre in the frame of `stop` (after stop's own joints).  Double precision;
+// the callers add a millimetre of slack.
+struct Reach { double c[3]; double r; bool bounded; };
+static void quat_rot(const double *q, const double *v, double *out) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double t[3] = {2 * (y * v[2] - z * v[1]), 2 * (z * v[0] - x * v[2]), 2 * (x * v[1] - y * v[0])};
+    out[0] = v[0] + w * t[0] + (y * t[2] - z * t[1]);
+    out[1] = v[1] + w * t[1] + (z * t[0] - x * t[2]);
+    out[2] = v[2] + w * t[2] + (x * t[1] - y * t[0]);
+}
+static Reach reach_of_geom(const mopa_model_desc *d, int g, int stop) {
+    Reach R;
+    R.bounded = true; R.r = 0.0;
+    for (int k = 0; k < 3; k++) R.c[k] = d->geom_pos[3 * g + k];
+    for (int b = d->geom_bodyid[g]; b != stop; b = d->body_parentid[b]) {
+        if (b == 0) { R.bounded = false; return R; }   // stop is not an ancestor
+        for (int k = d->body_jntnum[b] - 1; k >= 0; k--) {
+            const int j = d->body_jntadr[b] + k;
+            double ax[3] = {d->jnt_axis[3 * j], d->jnt_axis[3 * j + 1], d->jnt_axis[3 * j + 2]};
+            const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+            if (d->jnt_type[j] == MOPA_JNT_HINGE && an > 0) {
+                double rel[3], along = 0;
+                for (int c = 0; c < 3; c++) { ax[c] /= an; rel[c] = R.c[c] - d->jnt_pos[3 * j + c]; along += rel[c] * ax[c]; }
+                double rho2 = 0;
+                for (int c = 0; c < 3; c++) { const double perp = rel[c] - along * ax[c]; rho2 += perp * perp; R.c[c] = d->jnt_pos[3 * j + c] + along * ax[c]; }
+                R.r += sqrt(rho2);
+            } else if (d->jnt_type[j] == MOPA_JNT_SLIDE && an > 0 && d->jnt_limited[j]) {
+                const double lo = d->jnt_range[2 * j], hi = d->jnt_range[2 * j + 1], mid = 0.5 * (lo + hi) - d->qpos0[d->jnt_qposadr[j]];
+                for (int c = 0; c < 3; c++) R.c[c] += ax[c] / an * mid;
+                R.r += 1.5 * (hi - lo);
+            } else { R.bounded = false; return R; }
+        }
+        double w[3];
+        quat_rot(d->body_quat + 4 * b, R.c, w);
+        for (int c = 0; c < 3; c++) R.c[c] = d->body_pos[3 * b + c] + w[c];
+    }
+    return R;
+}
+static int common_ancestor(const mopa_model_desc *d, int b1, int b2) {
+    for (int a = b1;; a = d->body_parentid[a]) {
+        for (int b = b2;; b = d->body_parentid[b]) {
+            if (a == b) return a;
+            if (b == 0) break;
+        }
+        if (a == 0) return 0;
+    }
+}
+// true when the bounding spheres of the two geoms (radius sum + margin, MuJoCo's filter) cannot touch for any joint configuration
+static bool never_in_reach(const mopa_model_desc *d, int g1, int g2, double margin) {
+    const int stop = common_ancestor(d, d->geom_bodyid[g1], d->geom_bodyid[g2]);
+    const Reach A = reach_of_geom(d, g1, stop), B = reach_of_geom(d, g2, stop);
+    if (!A.bounded || !B.bounded) return false;
+    double dist2 = 0;
+    for (int c = 0; c < 3; c++) dist2 += (A.c[c] - B.c[c]) * (A.c[c] - B.c[c]);
+    return sqrt(dist2) - A.r - B.r > d->geom_rbound[g1] + d->geom_rbound[g2] + margin + 1e-3;
 }
 
 void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored, double threshold, HostScene &out) {
@@ -223,6 +285,7 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     // ---- pair records + cull entries
     struct PairBuild { PairRec P; CullEntry E; int list; };
     std::vector<PairBuild> pb;
+    int n_pruned = 0;
     for (int p = 0; p < npair; p++) {
         int g1 = out.canon_g1[p], g2 = out.canon_g2[p];
         if (d->geom_type[g1] > d->geom_type[g2]) std::swap(g1, g2);  // lower mjtGeom first, ties keep g1<g2
@@ -259,10 +322,24 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
             if (partner->slot < 0) { P.ckind = CK_SPHERE_STATIC; E.x = partner->px; E.y = partner->py; E.z = partner->pz; }
             else { P.ckind = CK_SPHERE_MOVING; const int off = partner->slot; memcpy(&E.x, &off, 4); }
         }
-        if (X.list < 3) pb.push_back(X);   // pairs of classes the narrow phase does not know never collide (PC_NONE)
+        if (X.list == 3) continue;   // pairs of classes the narrow phase does not know never collide (PC_NONE)
+        // out of reach for every joint configuration: the pair can never pass MuJoCo's bounding-sphere filter (plane pairs: the
+        // geom's lowest possible point stays above the plane), so it is not a candidate at all
+        bool pruned = false;
+        if (A.kind == K_PLANE) {
+            if (P.ckind == CK_PLANE) {
+                const Reach Rb = reach_of_geom(d, g2, 0);
+                if (Rb.bounded) {
+                    const double h = A.m[2] * (Rb.c[0] - A.px) + A.m[5] * (Rb.c[1] - A.py) + A.m[8] * (Rb.c[2] - A.pz) - Rb.r - B.rbound;
+                    pruned = h > 1e-3 + fmax(threshold, 0.0);
+                }
+            }
+        } else
+            pruned = never_in_reach(d, g1, g2, margin);
+        if (pruned) { n_pruned++; continue; }
+        pb.push_back(X);
     }
-    // kernel order: runs of (cull kind, anchor); every run is padded to a multiple of four entries with dummy pairs that never
-    // survive the cull (the sweep tests four entries per trip without bounds checks)
+    // kernel order: runs of (cull kind, anchor) in windows of 32 entries (see scene.h)
     std::stable_sort(pb.begin(), pb.end(), [](const PairBuild &a, const PairBuild &b) {
         if (a.P.ckind != b.P.ckind) return a.P.ckind < b.P.ckind;
         if (a.P.anchor_slot != b.P.anchor_slot) return a.P.anchor_slot < b.P.anchor_slot;
@@ -271,27 +348,39 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     std::vector<PairRec> pairs;
     std::vector<CullEntry> cull;
     std::vector<CullGroup> groups;
-    auto pad_group = [&]() {
-        if (groups.empty() || groups.back().kind == CK_NONE) return;
-        while (groups.back().count % 4) {
-            PairRec D;
-            memset(&D, 0, sizeof(D));
-            D.cls = PC_NONE; D.ckind = (uint8_t)groups.back().kind; D.anchor_slot = groups.back().anchor_slot; D.partner_slot = groups.back().anchor_slot;
-            D.canon = 0xFFFF;
-            CullEntry E{0.0f, 0.0f, 0.0f, -1.0f};   // |d|^2 > -1 and 0 > -1: culled by every kind of test
-            if (groups.back().kind == CK_SPHERE_MOVING) { const int off = groups.back().anchor_slot; memcpy(&E.x, &off, 4); }
-            pairs.push_back(D); cull.push_back(E);
-            groups.back().count++;
-        }
+    std::vector<uint16_t> real;
+    auto push_dummy = [&](int kind, int anchor_slot) {
+        PairRec D;
+        memset(&D, 0, sizeof(D));
+        D.cls = PC_NONE; D.ckind = (uint8_t)(kind == CK_NONE ? CK_PLANE : kind); D.anchor_slot = (uint16_t)anchor_slot; D.partner_slot = (uint16_t)anchor_slot;
+        D.canon = 0xFFFF;
+        CullEntry E{0.0f, 0.0f, 0.0f, -1.0f};   // |d|^2 > -1 and 0 > -1: culled by every kind of test
+        if (D.ckind == CK_SPHERE_MOVING) { const int off = anchor_slot; memcpy(&E.x, &off, 4); }
+        pairs.push_back(D); cull.push_back(E);
     };
-    for (size_t i = 0; i < pb.size(); i++) {
-        const bool fresh = i == 0 || pb[i].P.ckind != pb[i - 1].P.ckind || pb[i].P.anchor_slot != pb[i - 1].P.anchor_slot;
-        if (fresh) { pad_group(); groups.push_back(CullGroup{pb[i].P.anchor_slot, pb[i].P.ckind, 0, 0}); }
-        pairs.push_back(pb[i].P);
-        cull.push_back(pb[i].E);
-        groups.back().count++;
+    for (size_t i = 0; i < pb.size();) {
+        size_t j = i;
+        while (j < pb.size() && pb[j].P.ckind == pb[i].P.ckind && pb[j].P.anchor_slot == pb[i].P.anchor_slot) j++;
+        const int kind = pb[i].P.ckind, anchor = pb[i].P.anchor_slot;
+        while (i < j) {   // the run, in pieces of at most 32 entries that do not straddle a window
+            const int n = (int)std::min<size_t>(j - i, 32), padded = kind == CK_NONE ? n : (n + 3) & ~3;
+            int bitpos = (int)(pairs.size() % 32);
+            if (bitpos + padded > 32) {   // close the window
+                while (pairs.size() % 32) push_dummy(CK_PLANE, 0);
+                bitpos = 0;
+            }
+            CullGroup G;
+            memset(&G, 0, sizeof(G));
+            G.anchor_slot = (uint16_t)anchor; G.kind = (uint8_t)kind; G.count = (uint8_t)padded; G.bitpos = (uint8_t)bitpos; G.first = (uint16_t)pairs.size();
+            for (int k = 0; k < n; k++) { real.push_back((uint16_t)pairs.size()); pairs.push_back(pb[i + k].P); cull.push_back(pb[i + k].E); }
+            for (int k = n; k < padded; k++) push_dummy(kind, anchor);
+            groups.push_back(G);
+            i += n;
+        }
     }
-    pad_group();
+    while (pairs.size() % 32) push_dummy(CK_PLANE, 0);
+    for (size_t g = 0; g < groups.size(); g++)   // the last run of every window flushes the survivor mask
+        groups[g].flush = (g + 1 == groups.size() || groups[g + 1].bitpos == 0) ? 1 : 0;
     if (pairs.size() >= 65535) throw std::runtime_error("too many candidate pairs");
 
     // ---- pack
@@ -313,6 +402,9 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     H.off_cull = append(blob, cull);
     H.off_group = append(blob, groups);
     H.n_group = (int)groups.size();
+    H.off_real = append(blob, real);
+    H.n_real = (int)real.size();
+    H.n_pruned = n_pruned;
     std::vector<float> hull(3 * (size_t)d->nmeshvert);
     for (size_t k = 0; k < hull.size(); k++) hull[k] = (float)d->mesh_vert[k];
     H.off_hull = append(blob, hull);

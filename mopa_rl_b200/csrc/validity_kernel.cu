@@ -159,12 +159,14 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
         }
         __syncthreads();
         // ---- phase B.  Every lane sweeps (rows beyond n hold stale frames and push nothing) so that the warp can be
-        // re-converged explicitly after the divergent push loop.  Runs of pairs with the same cull kind and anchor share
-        // the anchor centre; survivors are collected 32 pairs at a time in a register mask.
+        // re-converged explicitly after the divergent push loop.  The pair table is laid out in windows of 32 entries; a run of
+        // pairs with the same cull kind and anchor never straddles a window, is padded to a multiple of four and shares the
+        // anchor centre.  Each test leaves its verdict in the sign of (cull bound - measured value): exactly the comparison of the
+        // filter (a difference of two floats has the sign of the comparison), shifted into the run's mask with one funnel shift.
+        // Entries are visited last to first so that entry j of the run ends up in bit j.
         {
             const uint32_t live = q < n ? 0xFFFFFFFFu : 0u;
-            uint32_t mw = 0u;
-            int cnt = 0, e = 0;              // bits collected in mw; next pair (uniform)
+            uint32_t mw = 0u;                 // survivors of the current window
             auto flush = [&](int base) {      // pairs base .. base + 31 <-> bits of mw
                 mw &= live;
                 while (mw) {
@@ -178,7 +180,6 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                     else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
                 }
                 __syncwarp();
-                cnt = 0;
             };
             const int ngroup = S.H->n_group;
 #pragma unroll 1
@@ -186,58 +187,43 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                 const CullGroup G = S.groups[g];
                 const float *fa = frames + (int)G.anchor_slot * NQ + tid;
                 const V3 ac{fa[0], fa[NQ], fa[2 * NQ]};
-                int rem = G.count;
-                while (rem > 0) {
-                    const int m = min(rem, 32 - cnt);
-                    // four independent tests per trip (the tests are short dependent chains: instruction-level parallelism
-                    // is what hides their latency at 12 resident warps); runs are padded to multiples of four, and a trip that
-                    // reaches past m only reads entries of the same run, which are masked out
-                    const uint32_t mmask = m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
-                    uint32_t got = 0u;
-                    if (G.kind == CK_SPHERE_STATIC) {
-                        for (int j = 0; j < m; j += 4) {
-                            uint32_t b[4];
+                const CullEntry *E0 = S.cull + G.first;
+                uint32_t culled = 0u;
+                if (G.kind == CK_SPHERE_STATIC) {
+                    for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const CullEntry E = S.cull[e + j + u];
-                                const V3 d = V3{E.x, E.y, E.z} - ac;
-                                b[u] = !(dot(d, d) > E.w);
-                            }
-                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        for (int u = 3; u >= 0; u--) {
+                            const CullEntry E = E0[j + u];
+                            const V3 d = V3{E.x, E.y, E.z} - ac;
+                            culled = __funnelshift_l(__float_as_uint(E.w - dot(d, d)), culled, 1);
                         }
-                    } else if (G.kind == CK_SPHERE_MOVING) {
-                        for (int j = 0; j < m; j += 4) {
-                            uint32_t b[4];
+                    }
+                } else if (G.kind == CK_SPHERE_MOVING) {
+                    for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const CullEntry E = S.cull[e + j + u];
-                                const float *fp = frames + __float_as_int(E.x) * NQ + tid;
-                                const V3 d = V3{fp[0], fp[NQ], fp[2 * NQ]} - ac;
-                                b[u] = !(dot(d, d) > E.w);
-                            }
-                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        for (int u = 3; u >= 0; u--) {
+                            const CullEntry E = E0[j + u];
+                            const float *fp = frames + __float_as_int(E.x) * NQ + tid;
+                            const V3 d = V3{fp[0], fp[NQ], fp[2 * NQ]} - ac;
+                            culled = __funnelshift_l(__float_as_uint(E.w - dot(d, d)), culled, 1);
                         }
-                    } else if (G.kind == CK_PLANE) {
-                        for (int j = 0; j < m; j += 4) {
-                            uint32_t b[4];
+                    }
+                } else if (G.kind == CK_PLANE) {
+                    for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const CullEntry E = S.cull[e + j + u];
-                                b[u] = !(dot(V3{E.x, E.y, E.z}, ac) > E.w);
-                            }
-                            got |= (b[0] | (b[1] << 1) | (b[2] << 2) | (b[3] << 3)) << j;
+                        for (int u = 3; u >= 0; u--) {
+                            const CullEntry E = E0[j + u];
+                            culled = __funnelshift_l(__float_as_uint(E.w - dot(V3{E.x, E.y, E.z}, ac)), culled, 1);
                         }
-                    } else
-                        got = 0xFFFFFFFFu;
-                    mw |= (got & mmask) << cnt;
-#ifdef MOPA_VK_STATS
-                    for (int j = 0; j < m; j++) VK_STAT(S.pairs[e + j].cls, 0);
-#endif
-                    e += m; rem -= m; cnt += m;
-                    if (cnt == 32) flush(e - 32);
+                    }
                 }
+                const uint32_t cmask = G.count == 32 ? 0xFFFFFFFFu : ((1u << G.count) - 1u);
+                mw |= (~culled & cmask) << G.bitpos;
+#ifdef MOPA_VK_STATS
+                for (int j = 0; j < G.count; j++) VK_STAT(S.pairs[G.first + j].cls, 0);
+#endif
+                if (G.flush) { flush((int)G.first - (int)G.bitpos); mw = 0u; }
             }
-            if (cnt > 0) flush(e - cnt);
         }
         __syncthreads();
         // ---- phase C: analytic pairs, then box-box

@@ -21,6 +21,7 @@ struct SceneView {  // pointers into the shared-memory copy of the scene blob
     const PairRec *pairs;
     const CullEntry *cull;
     const CullGroup *groups;
+    const uint16_t *real;
 };
 
 __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
@@ -34,6 +35,7 @@ __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
     v.pairs = reinterpret_cast<const PairRec *>(blob + v.H->off_pair);
     v.cull = reinterpret_cast<const CullEntry *>(blob + v.H->off_cull);
     v.groups = reinterpret_cast<const CullGroup *>(blob + v.H->off_group);
+    v.real = reinterpret_cast<const uint16_t *>(blob + v.H->off_real);
     return v;
 }
 
@@ -53,30 +55,38 @@ __device__ __forceinline__ bool cull_survives(const PairRec &pr, const CullEntry
 }
 
 struct Frame { V3 pos; Q4 quat; M3 mat; };
+struct Pose { V3 pos; Q4 quat; };
 
 // Forward kinematics of the collision-relevant sub-tree for one state.  `q` is the qpos
 // row (fp32).  World frames of moving geoms are written to frames[(slot+k)*stride + lane].
+// The running frame lives in registers; a body whose parent is not its predecessor in the (depth-first) body order restarts
+// from one of two saved poses or from the constant frame of a world-welded parent.  Those restarts and saves are rare and the
+// same for every lane, so they sit behind real branches instead of register selects on every body.
 template <class QPos>
 __device__ __forceinline__ void fk_state(const SceneView &S, const QPos &q, float *frames, int stride, int lane) {
-    Frame cur, s0, s1;
+    Frame cur;
+    Pose s0, s1;
     cur.pos = V3{0, 0, 0}; cur.quat = Q4{1, 0, 0, 0}; cur.mat = q2m(cur.quat);
-    s0 = cur; s1 = cur;
+    s0.pos = cur.pos; s0.quat = cur.quat; s1 = s0;
     const int nb = S.H->n_body;
+#pragma unroll 1
     for (int b = 0; b < nb; b++) {
         const FkBody B = S.bodies[b];
-        Frame P;
-        if (B.parent_sel == SEL_CUR) P = cur;
-        else if (B.parent_sel == SEL_SLOT0) P = s0;
-        else if (B.parent_sel == SEL_SLOT1) P = s1;
-        else {
-            const ConstFrame &c = S.consts[B.const_idx];
-            P.pos = V3{c.px, c.py, c.pz};
-            P.quat = Q4{c.qw, c.qx, c.qy, c.qz};
+        if (B.parent_sel != SEL_CUR) {
+            if (B.parent_sel == SEL_CONST) {
+                const ConstFrame &c = S.consts[B.const_idx];
+                cur.pos = V3{c.px, c.py, c.pz};
+                cur.quat = Q4{c.qw, c.qx, c.qy, c.qz};
 #pragma unroll
-            for (int k = 0; k < 9; k++) P.mat.m[k] = c.m[k];
+                for (int k = 0; k < 9; k++) cur.mat.m[k] = c.m[k];
+            } else {
+                const Pose &s = B.parent_sel == SEL_SLOT0 ? s0 : s1;
+                cur.pos = s.pos; cur.quat = s.quat;
+                cur.mat = q2m(cur.quat);   // what the saved body computed
+            }
         }
-        V3 pos = P.pos + mulMV(P.mat, V3{B.px, B.py, B.pz});
-        Q4 quat = qmul(P.quat, Q4{B.qw, B.qx, B.qy, B.qz});
+        V3 pos = cur.pos + mulMV(cur.mat, V3{B.px, B.py, B.pz});
+        Q4 quat = qmul(cur.quat, Q4{B.qw, B.qx, B.qy, B.qz});
         for (int j = B.jnt_begin; j < B.jnt_end; j++) {
             const FkJoint J = S.joints[j];
             if (J.type == J_HINGE) {
@@ -100,8 +110,10 @@ __device__ __forceinline__ void fk_state(const SceneView &S, const QPos &q, floa
             }
         }
         cur.pos = pos; cur.quat = quat; cur.mat = q2m(quat);
-        if (B.save_sel == 0) s0 = cur;
-        else if (B.save_sel == 1) s1 = cur;
+        if (B.save_sel >= 0) {
+            if (B.save_sel == 0) { s0.pos = pos; s0.quat = quat; }
+            else { s1.pos = pos; s1.quat = quat; }
+        }
         for (int g = B.geom_begin; g < B.geom_end; g++) {
             const FkGeom &G = S.geoms[g];
             V3 gp = cur.pos + mulMV(cur.mat, V3{G.px, G.py, G.pz});
