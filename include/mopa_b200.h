@@ -63,6 +63,12 @@ void mopa_planner_destroy(mopa_planner *p);
 int mopa_planner_info(const mopa_planner *p, int32_t *nq, int32_t *n_pairs, int32_t *n_active);
 /* Canonical candidate pair list (mjModel geom ids), n_pairs entries each. */
 int mopa_planner_pairs(const mopa_planner *p, int32_t *geom1, int32_t *geom2);
+/* Host-only view of the pair table the kernels sweep (no device needed): which canonical candidate pairs are kept after the
+ * build-time reach analysis (pairs whose bounding spheres cannot touch for any joint configuration are dropped, see
+ * csrc/scene_build.cu).  kept[i] = 1 / 0 per canonical pair (n_pairs entries, may be NULL);
+ * stats[0..7] = table entries incl. padding, kept pairs, cull runs, dropped pairs, canonical pairs, table bytes, frame floats per state, 0. */
+int mopa_scene_pair_table(const mopa_model_desc *model, const int32_t *ignored_pairs, int32_t n_ignored, double contact_threshold,
+                          int32_t *stats, uint8_t *kept, int32_t n_pairs);
 
 /* Replaces MujocoStateValidityChecker::isValid (mujoco_ompl_interface.cpp:909-978), batched.
  *   d_qpos      device, n rows of fp32 qpos, row_stride floats apart (row_stride >= nq)

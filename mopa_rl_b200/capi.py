@@ -38,6 +38,7 @@ def lib():
         L.mopa_planner_destroy.restype = None
         L.mopa_planner_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.mopa_planner_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mopa_scene_pair_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
         L.mopa_is_valid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.mopa_is_valid_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.mopa_is_valid_host_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
@@ -48,6 +49,21 @@ def lib():
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
+
+
+def scene_pair_table(model, ignored_pairs=(), contact_threshold=0.0):
+    """Host-only: which canonical candidate pairs the kernels' pair table keeps after the build-time reach analysis.
+    Returns (stats dict, kept uint8[n_canonical])."""
+    from .model import make_desc
+    desc, keep = make_desc(model)
+    ign = np.ascontiguousarray(np.array(list(ignored_pairs), dtype=np.int32).reshape(-1, 2))
+    st = np.zeros(8, np.int32)
+    L = lib()
+    check(L.mopa_scene_pair_table(C.byref(desc), _p(ign) if len(ign) else None, len(ign), float(contact_threshold), _p(st), None, 0))
+    kept = np.zeros(int(st[4]), np.uint8)
+    check(L.mopa_scene_pair_table(C.byref(desc), _p(ign) if len(ign) else None, len(ign), float(contact_threshold), _p(st), _p(kept), len(kept)))
+    names = ("entries", "kept", "runs", "dropped", "canonical", "table_bytes", "frame_floats")
+    return dict(zip(names, (int(x) for x in st))), kept
 
 
 def _check_abi(L):

@@ -103,6 +103,26 @@ int mopa_planner_info(const mopa_planner *p, int32_t *nq, int32_t *n_pairs, int3
     return MOPA_OK;
 }
 
+int mopa_scene_pair_table(const mopa_model_desc *model, const int32_t *ignored_pairs, int32_t n_ignored, double contact_threshold,
+                          int32_t *stats, uint8_t *kept, int32_t n_pairs) {
+    if (!model || !stats) { g_err = "bad argument"; return MOPA_ERR_ARG; }
+    try {
+        mopa::HostScene sc;
+        mopa::build_scene(model, ignored_pairs, n_ignored, contact_threshold, sc);
+        const mopa::SceneHeader &H = sc.hdr;
+        const int32_t st[8] = {H.n_pair, H.n_real, H.n_group, H.n_pruned, (int32_t)sc.canon_g1.size(), H.blob_bytes, H.frame_floats, 0};
+        for (int k = 0; k < 8; k++) stats[k] = st[k];
+        if (kept) {
+            if (n_pairs != (int32_t)sc.canon_g1.size()) { g_err = "n_pairs does not match the canonical pair count"; return MOPA_ERR_ARG; }
+            for (int i = 0; i < n_pairs; i++) kept[i] = 0;
+            const mopa::PairRec *pairs = reinterpret_cast<const mopa::PairRec *>(sc.blob.data() + H.off_pair);
+            const uint16_t *real = reinterpret_cast<const uint16_t *>(sc.blob.data() + H.off_real);
+            for (int i = 0; i < H.n_real; i++) kept[pairs[real[i]].canon] = 1;
+        }
+    } catch (const std::exception &e) { g_err = e.what(); return MOPA_ERR_ARG; }
+    return MOPA_OK;
+}
+
 int mopa_planner_pairs(const mopa_planner *p, int32_t *geom1, int32_t *geom2) {
     if (!p || !geom1 || !geom2) { g_err = "bad argument"; return MOPA_ERR_ARG; }
     for (size_t i = 0; i < p->scene.canon_g1.size(); i++) { geom1[i] = p->scene.canon_g1[i]; geom2[i] = p->scene.canon_g2[i]; }

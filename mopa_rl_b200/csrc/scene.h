@@ -93,6 +93,7 @@ struct SceneHeader {
     int n_hull_vert;
     int off_cull, off_group, n_group;   // CullEntry[n_pair] (parallel to the pair records), CullGroup[n_group]
     int off_real, n_real;               // uint16 indices of the non-dummy pair entries
+    int off_wmask;                      // uint32 [n_pair / 32][4]: per window, which entries belong to work list 0 / 1 / 2 (analytic, box-box, portal refinement)
     int n_pruned;                       // candidate pairs dropped at build time (bounding spheres out of reach for every joint configuration)
 };
 

@@ -362,13 +362,10 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
         size_t j = i;
         while (j < pb.size() && pb[j].P.ckind == pb[i].P.ckind && pb[j].P.anchor_slot == pb[i].P.anchor_slot) j++;
         const int kind = pb[i].P.ckind, anchor = pb[i].P.anchor_slot;
-        while (i < j) {   // the run, in pieces of at most 32 entries that do not straddle a window
-            const int n = (int)std::min<size_t>(j - i, 32), padded = kind == CK_NONE ? n : (n + 3) & ~3;
-            int bitpos = (int)(pairs.size() % 32);
-            if (bitpos + padded > 32) {   // close the window
-                while (pairs.size() % 32) push_dummy(CK_PLANE, 0);
-                bitpos = 0;
-            }
+        while (i < j) {   // the run, cut where it would straddle a window (every piece but the last fills its window exactly)
+            while (pairs.size() % 4) push_dummy(CK_PLANE, 0);   // after an unpadded CK_NONE run
+            const int bitpos = (int)(pairs.size() % 32);
+            const int n = (int)std::min<size_t>(j - i, 32 - bitpos), padded = kind == CK_NONE ? n : (n + 3) & ~3;
             CullGroup G;
             memset(&G, 0, sizeof(G));
             G.anchor_slot = (uint16_t)anchor; G.kind = (uint8_t)kind; G.count = (uint8_t)padded; G.bitpos = (uint8_t)bitpos; G.first = (uint16_t)pairs.size();
@@ -402,6 +399,14 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     H.off_cull = append(blob, cull);
     H.off_group = append(blob, groups);
     H.n_group = (int)groups.size();
+    std::vector<uint32_t> wmask(pairs.size() / 32 * 4, 0u);
+    for (size_t i = 0; i < pairs.size(); i++) {
+        const int cls = pairs[i].cls;
+        if (cls > PC_MPR) continue;   // dummies
+        const int list = cls < PC_BOX_BOX ? 0 : (cls == PC_BOX_BOX ? 1 : 2);
+        wmask[i / 32 * 4 + list] |= 1u << (i % 32);
+    }
+    H.off_wmask = append(blob, wmask);
     H.off_real = append(blob, real);
     H.n_real = (int)real.size();
     H.n_pruned = n_pruned;

@@ -167,19 +167,46 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
         {
             const uint32_t live = q < n ? 0xFFFFFFFFu : 0u;
             uint32_t mw = 0u;                 // survivors of the current window
+            // Survivors of one window -> work lists, without per-item atomics: the scene tells which entries of the window
+            // belong to which list, every lane counts its survivors per list, one warp scan (three 11-bit counters packed in a
+            // word) gives each lane its offsets, three lanes reserve the warp's share of the lists, and the lanes write their
+            // items.  Called by all lanes (the run table is uniform).
             auto flush = [&](int base) {      // pairs base .. base + 31 <-> bits of mw
                 mw &= live;
-                while (mw) {
-                    const int p = base + __ffs(mw) - 1;
-                    mw &= mw - 1;
-                    const int cls = S.pairs[p].cls;
-                    VK_STAT(cls, 1);
-                    const int list = cls < PC_BOX_BOX ? WL_CHEAP : (cls == PC_BOX_BOX ? WL_BOX : WL_MPR);
-                    const int idx = atomicAdd(&wcount[list], 1);
-                    if (idx < wl_cap(list)) wl_base(list)[idx] = ((uint32_t)tid << 16) | (uint32_t)p;
-                    else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
+                const uint4 wm = S.wmask[base >> 5];
+                const uint32_t m0 = mw & wm.x, m1 = mw & wm.y, m2 = mw & wm.z;
+                const uint32_t packed = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 11) | ((uint32_t)__popc(m2) << 22);
+                if (__any_sync(0xffffffffu, packed != 0u)) {
+                    const int lane = tid & 31;
+                    uint32_t incl = packed;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - packed;
+                    int reserved = 0;
+                    if (lane < WL_COUNT) {
+                        const int c = (int)((total >> (11 * lane)) & 0x7FFu);
+                        if (c) reserved = atomicAdd(&wcount[lane], c);
+                    }
+                    auto emit = [&](uint32_t bits, int list, int idx) {
+                        uint32_t *buf = wl_base(list);
+                        const int cap = wl_cap(list);
+                        while (bits) {
+                            const int p = base + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            VK_STAT(S.pairs[p].cls, 1);
+                            if (idx < cap) buf[idx] = ((uint32_t)tid << 16) | (uint32_t)p;
+                            else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
+                            idx++;
+                        }
+                    };
+                    emit(m0, WL_CHEAP, __shfl_sync(0xffffffffu, reserved, WL_CHEAP) + (int)(excl & 0x7FFu));
+                    emit(m1, WL_BOX, __shfl_sync(0xffffffffu, reserved, WL_BOX) + (int)((excl >> 11) & 0x7FFu));
+                    emit(m2, WL_MPR, __shfl_sync(0xffffffffu, reserved, WL_MPR) + (int)(excl >> 22));
+                    __syncwarp();
                 }
-                __syncwarp();
             };
             const int ngroup = S.H->n_group;
 #pragma unroll 1

@@ -22,6 +22,7 @@ struct SceneView {  // pointers into the shared-memory copy of the scene blob
     const CullEntry *cull;
     const CullGroup *groups;
     const uint16_t *real;
+    const uint4 *wmask;
 };
 
 __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
@@ -36,6 +37,7 @@ __device__ __forceinline__ SceneView view_scene(const unsigned char *blob) {
     v.cull = reinterpret_cast<const CullEntry *>(blob + v.H->off_cull);
     v.groups = reinterpret_cast<const CullGroup *>(blob + v.H->off_group);
     v.real = reinterpret_cast<const uint16_t *>(blob + v.H->off_real);
+    v.wmask = reinterpret_cast<const uint4 *>(blob + v.H->off_wmask);
     return v;
 }
 
