@@ -65,7 +65,8 @@ struct PairRec {
     uint16_t canon;     // index in the canonical (g1<g2 lexicographic) candidate list
     uint8_t cls;        // PairClass
     uint8_t ckind;      // CullKind
-    uint32_t pad;
+    uint8_t mkey;       // portal-refinement pairs: rank (< 16) of the pair's (kind, kind) combination among those of the scene;
+    uint8_t pad[3];     //   the queued refinements are grouped by it so that the lanes of a warp run the same support routines
 };
 enum CullKind : int {
     CK_SPHERE_STATIC = 0,   // e = (partner centre, squared cull distance): cull when |centre - anchor centre|^2 > e.w

@@ -285,6 +285,7 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
     // ---- pair records + cull entries
     struct PairBuild { PairRec P; CullEntry E; int list; };
     std::vector<PairBuild> pb;
+    std::vector<int> mpr_combos;
     int n_pruned = 0;
     for (int p = 0; p < npair; p++) {
         int g1 = out.canon_g1[p], g2 = out.canon_g2[p];
@@ -298,6 +299,13 @@ void build_scene(const mopa_model_desc *d, const int32_t *ignored, int nignored,
         P.gb = (uint16_t)rec_of_geom[g2];
         P.canon = (uint16_t)p;
         P.cls = (uint8_t)pair_class(A.kind, B.kind);
+        if (P.cls == PC_MPR) {
+            const int combo = A.kind * 8 + B.kind;
+            size_t k = 0;
+            while (k < mpr_combos.size() && mpr_combos[k] != combo) k++;
+            if (k == mpr_combos.size()) mpr_combos.push_back(combo);
+            P.mkey = (uint8_t)(k < 15 ? k : 15);
+        }
         X.list = P.cls < PC_BOX_BOX ? 0 : (P.cls == PC_BOX_BOX ? 1 : (P.cls == PC_MPR ? 2 : 3));
         float margin = fmaxf((float)d->geom_margin[g1], (float)d->geom_margin[g2]);
         const GeomRec *anchor = &A, *partner = &B;

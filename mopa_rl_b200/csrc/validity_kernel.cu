@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
     float *frames = reinterpret_cast<float *>(smem + blob_bytes);         // [ffs][NQ]
     uint32_t *res = reinterpret_cast<uint32_t *>(frames + (size_t)ffs * NQ);
     int *wcount = reinterpret_cast<int *>(res + NQ);                        // [0..2] work lists, [4] queue length, [5] queue cursor, [8..10] list offsets, [12..14] capacities
-    uint32_t *wl0 = reinterpret_cast<uint32_t *>(wcount + 16);              // the three lists, back to back
+    uint32_t *wl0 = reinterpret_cast<uint32_t *>(wcount + 48);              // the three lists, back to back; wcount[16..47]: key histogram / offsets of the queue sort
     auto wl_base = [&](int list) { return wl0 + wcount[8 + list]; };
     auto wl_cap = [&](int list) { return wcount[12 + list]; };
     MprItem *mq = mq_all + (size_t)blockIdx.x * mq_cap;
@@ -101,6 +101,18 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
         const int cnt = min(wcount[4], mq_cap);
         __syncthreads();
         if (cnt > 0) {
+            // group the queue by the (kind, kind) combination of its pairs: a counting sort of item indices into the idle
+            // work-list memory, so that neighbouring lanes - which take neighbouring positions - run the same support routines
+            uint16_t *order = reinterpret_cast<uint16_t *>(wl0);
+            int *hist = wcount + 16;
+            if (tid < 32) hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < cnt; i += NQ) atomicAdd(&hist[S.pairs[mq[i].p].mkey], 1);
+            __syncthreads();
+            if (tid == 0) { int run = 0; for (int k = 0; k < 16; k++) { const int c = hist[k]; hist[16 + k] = run; run += c; } }
+            __syncthreads();
+            for (int i = tid; i < cnt; i += NQ) order[atomicAdd(&hist[16 + S.pairs[mq[i].p].mkey], 1)] = (uint16_t)i;
+            __syncthreads();
             MprSM m;
             Geom a, b;
             int iq = 0;
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                     const int idx = atomicAdd(&wcount[5], 1);
                     if (idx >= cnt) exhausted = true;
                     else {
-                        const MprItem &it = mq[idx];
+                        const MprItem &it = mq[order[idx]];
                         iq = it.q;
                         if (exact || out[iq] == 0xFFFFFFFFu) {   // fast mode: nothing to learn about a state already known to be invalid
                             const PairRec pr = S.pairs[it.p];
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                             for (int k = 0; k < 9; k++) { a.R.m[k] = it.Ra[k]; b.R.m[k] = it.Rb[k]; }
                             mpr_begin(m, a, b);
                             active = true;
+                            VK_STAT(14, 0);
                         }
                     }
                 }
@@ -134,6 +147,11 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                     if (__all_sync(0xffffffffu, exhausted)) break;
                     continue;
                 }
+#ifdef MOPA_VK_STATS   // [13][k]: trips in phase k; [14]: items begun, active lanes summed over trips, warp trips, kind-pair changes
+                if (active) VK_STAT(13, m.phase & 3);
+                if ((tid & 31) == 0) { atomicAdd(&g_vk_stats[14][1], (unsigned long long)__popc(__ballot_sync(0xffffffffu, active))); VK_STAT(14, 2); }
+                else __ballot_sync(0xffffffffu, active);
+#endif
                 if (active) {
                     float depth = 0.0f;
                     const int r = mpr_trip<MESH>(m, a, b, &depth);
@@ -190,16 +208,24 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                         const int c = (int)((total >> (11 * lane)) & 0x7FFu);
                         if (c) reserved = atomicAdd(&wcount[lane], c);
                     }
+                    const uint32_t item0 = (((uint32_t)tid << 16) | (uint32_t)base) - 1u;   // + __ffs(bits) = (query, pair)
                     auto emit = [&](uint32_t bits, int list, int idx) {
-                        uint32_t *buf = wl_base(list);
-                        const int cap = wl_cap(list);
-                        while (bits) {
-                            const int p = base + __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            VK_STAT(S.pairs[p].cls, 1);
-                            if (idx < cap) buf[idx] = ((uint32_t)tid << 16) | (uint32_t)p;
-                            else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
-                            idx++;
+                        uint32_t *dst = wl_base(list) + idx;
+                        if (idx + __popc(bits) <= wl_cap(list)) {   // the common case: no bounds check per item
+                            while (bits) {
+                                VK_STAT(S.pairs[base + __ffs(bits) - 1].cls, 1);
+                                *dst++ = item0 + (uint32_t)__ffs(bits);
+                                bits &= bits - 1;
+                            }
+                        } else {
+                            const int room = wl_cap(list) - idx;
+                            for (int k = 0; bits; k++) {
+                                const int p = base + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                VK_STAT(S.pairs[p].cls, 1);
+                                if (k < room) dst[k] = ((uint32_t)tid << 16) | (uint32_t)p;
+                                else eval_item_overflow<MESH>(smem, frames, NQ, tid, p, thr, &res[tid]);
+                            }
                         }
                     };
                     emit(m0, WL_CHEAP, __shfl_sync(0xffffffffu, reserved, WL_CHEAP) + (int)(excl & 0x7FFu));
@@ -313,7 +339,7 @@ struct VkPlan { int ffs, cap_cheap, cap_box, cap_mpr, mq_cap; size_t smem; int p
 static VkPlan validity_plan(const SceneHeader &H) {
     VkPlan P;
     P.ffs = H.frame_floats;
-    const size_t fixed = (size_t)H.blob_bytes + (size_t)P.ffs * VK_NQ * 4 + VK_NQ * 4 + 64 + 16;
+    const size_t fixed = (size_t)H.blob_bytes + (size_t)P.ffs * VK_NQ * 4 + VK_NQ * 4 + 192 + 16;
     const size_t sm_total = 228 * 1024, reserve = 1024;
     int per_sm = 4;
     size_t lists = 0;

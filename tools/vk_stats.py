@@ -29,3 +29,5 @@ for i, nm in enumerate(names):
     if s[i, 0]:
         print("%-16s %10.2f %10.2f %10.3f %10.3f" % (nm, s[i, 0] / n, s[i, 1] / n, s[i, 2] / n, s[i, 3] / n))
 print("%-16s %10.2f %10.2f %10.3f" % ("total", s[:, 0].sum() / n, s[:, 1].sum() / n, s[:, 2].sum() / n))
+print("portal refinement: items begun %.3f per query; trips per item by phase (v1, v2, v3, refine): %s; active lanes per warp trip %.1f" % (
+    s[14, 0] / n, " ".join("%.2f" % (s[13, k] / max(s[14, 0], 1)) for k in range(4)), s[14, 1] / max(s[14, 2], 1)))
