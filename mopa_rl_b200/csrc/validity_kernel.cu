@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                 const CullEntry *E0 = S.cull + G.first;
                 uint32_t culled = 0u;
                 if (G.kind == CK_SPHERE_STATIC) {
+#pragma unroll 1
                     for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
                         for (int u = 3; u >= 0; u--) {
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                         }
                     }
                 } else if (G.kind == CK_SPHERE_MOVING) {
+#pragma unroll 1
                     for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
                         for (int u = 3; u >= 0; u--) {
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
                         }
                     }
                 } else if (G.kind == CK_PLANE) {
+#pragma unroll 1
                     for (int j = G.count - 4; j >= 0; j -= 4) {
 #pragma unroll
                         for (int u = 3; u >= 0; u--) {
