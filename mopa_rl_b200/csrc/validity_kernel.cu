@@ -64,7 +64,7 @@ __device__ __noinline__ void eval_item_overflow(const unsigned char *blob, const
 }
 
 template <int NQ, bool MESH>
-__global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
+__global__ void __launch_bounds__(NQ, NQ <= 128 ? 3 : 1) is_valid_kernel(const unsigned char *__restrict__ blob_g, int blob_bytes,
                                                       const float *__restrict__ qpos, int row_stride, int n,
                                                       uint32_t *__restrict__ out, int exact, const int *__restrict__ d_n, int d_n_mult,
                                                       int ffs, int cap_cheap, int cap_box, int cap_mpr, MprItem *__restrict__ mq_all,
@@ -334,30 +334,42 @@ __global__ void __launch_bounds__(NQ, 3) is_valid_kernel(const unsigned char *__
     }
 }
 
-constexpr int VK_NQ = 128;
-constexpr int VK_MQ_RUN = 8 * VK_NQ;    // queued refinements per CTA before phase D runs (8 per thread)
+// Queries per CTA.  One large CTA per SM is preferred over several small ones: its warps walk the phases together, so the code
+// an SM executes at any moment is one phase's loop (the kernel is ~130 KB of SASS, the instruction cache next to the SM 32 KB;
+// three independent 128-thread CTAs kept three different phases in flight and the kernel waited for instructions), and the
+// scene tables exist once per SM.  The frame store (frame floats x 4 B per query) decides which size fits.
+static const int VK_NQ_CHOICES[] = {384, 256, 128};
 
-// shared-memory plan for one scene: [blob][frames NQ x ffs][res NQ][counters][work lists]; the lists take what is left of a third of an SM
-struct VkPlan { int ffs, cap_cheap, cap_box, cap_mpr, mq_cap; size_t smem; int per_sm; };
-static VkPlan validity_plan(const SceneHeader &H) {
+// shared-memory plan for one scene: [blob][frames NQ x ffs][res NQ][counters][work lists]
+struct VkPlan { int nq, ffs, cap_cheap, cap_box, cap_mpr, mq_cap, mq_run; size_t smem; int per_sm; };
+static VkPlan validity_plan(const SceneHeader &H, long long n = -1, int sm_count = 148) {
     VkPlan P;
     P.ffs = H.frame_floats;
-    const size_t fixed = (size_t)H.blob_bytes + (size_t)P.ffs * VK_NQ * 4 + VK_NQ * 4 + 192 + 16;
     const size_t sm_total = 228 * 1024, reserve = 1024;
-    int per_sm = 4;
-    size_t lists = 0;
-    for (; per_sm >= 1; per_sm--) {   // most resident CTAs that still leave >= 4 KB of work lists each
-        const size_t budget = sm_total / per_sm - reserve;
-        if (budget > 227 * 1024) continue;
-        if (budget >= fixed + 4096) { lists = budget - fixed; break; }
+    size_t lists = 0, fixed = 0;
+    P.nq = 128; P.per_sm = 0;
+    for (int nq : VK_NQ_CHOICES) {
+        fixed = (size_t)H.blob_bytes + (size_t)P.ffs * nq * 4 + (size_t)nq * 4 + 192 + 16;
+        if (nq > 128) {   // one CTA per SM, lists of >= 4 KB per 128 queries; small batches keep the small CTAs (more SMs busy)
+            if (n >= 0 && n < (long long)nq * sm_count) continue;
+            const size_t budget = 227 * 1024 - reserve, need = 4096 * (size_t)(nq / 128);
+            if (budget >= fixed + need) { P.nq = nq; P.per_sm = 1; lists = budget - fixed; break; }
+            continue;
+        }
+        for (int per_sm = 4; per_sm >= 1; per_sm--) {   // most resident CTAs that still leave >= 4 KB of work lists each
+            const size_t budget = sm_total / per_sm - reserve;
+            if (budget > 227 * 1024) continue;
+            if (budget >= fixed + 4096) { P.per_sm = per_sm; lists = budget - fixed; break; }
+        }
     }
-    if (per_sm < 1) { per_sm = 1; lists = 4096; }
-    if (lists > 16384) lists = 16384;
+    if (P.per_sm < 1) { P.per_sm = 1; lists = 4096; }
+    const size_t lists_max = 16384 * (size_t)(P.nq / 128);
+    if (lists > lists_max) lists = lists_max;
     const int items = (int)(lists / 4) & ~3;
     P.cap_box = items / 6; P.cap_mpr = items / 2; P.cap_cheap = items - P.cap_box - P.cap_mpr;   // ~ 4 : 1.4 : 5.6 items per query
-    P.mq_cap = VK_MQ_RUN + P.cap_mpr;
+    P.mq_run = 8 * P.nq;    // queued refinements per CTA before phase D runs (8 per thread)
+    P.mq_cap = P.mq_run + P.cap_mpr;
     P.smem = fixed + (size_t)items * 4;
-    P.per_sm = per_sm;
     return P;
 }
 size_t validity_smem_bytes(const SceneHeader &H) { return validity_plan(H).smem; }
@@ -382,27 +394,38 @@ static MprItem *validity_scratch(cudaStream_t stream, size_t bytes, cudaError_t 
     return (MprItem *)s.p;
 }
 
-cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
-                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
-    if (n <= 0) return cudaSuccess;
-    static bool attr_set[2] = {false, false};
-    const VkPlan P = validity_plan(H);
-    const int mesh = H.n_hull_vert > 0;   // scenes with mesh colliders run the instantiation that carries the hull support
-    auto kern = mesh ? is_valid_kernel<VK_NQ, true> : is_valid_kernel<VK_NQ, false>;
-    if (!attr_set[mesh]) {
+template <int NQ, bool MESH>
+static cudaError_t launch_is_valid_t(const VkPlan &P, const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
+                                     uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
+    static bool attr_set = false;
+    auto kern = is_valid_kernel<NQ, MESH>;
+    if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set[mesh] = true;
+        attr_set = true;
     }
-    int ntile = (n + VK_NQ - 1) / VK_NQ;
+    const int ntile = (n + NQ - 1) / NQ;
     int grid = sm_count * P.per_sm;
     if (grid > ntile) grid = ntile;
     cudaError_t e = cudaSuccess;
     MprItem *mq = validity_scratch(stream, (size_t)sm_count * P.per_sm * P.mq_cap * sizeof(MprItem), e);
     if (!mq) return e;
-    kern<<<grid, VK_NQ, P.smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact, d_n, d_n_mult, P.ffs, P.cap_cheap, P.cap_box, P.cap_mpr,
-                                             mq, P.mq_cap, VK_MQ_RUN);
+    kern<<<grid, NQ, P.smem, stream>>>(d_blob, H.blob_bytes, d_qpos, row_stride, n, d_out, exact, d_n, d_n_mult, P.ffs, P.cap_cheap, P.cap_box, P.cap_mpr,
+                                       mq, P.mq_cap, P.mq_run);
     return cudaGetLastError();
+}
+
+cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
+                            uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n, int d_n_mult) {
+    if (n <= 0) return cudaSuccess;
+    const VkPlan P = validity_plan(H, n, sm_count);
+    const bool mesh = H.n_hull_vert > 0;   // scenes with mesh colliders run the instantiation that carries the hull support
+#define VK_LAUNCH(NQ_) (mesh ? launch_is_valid_t<NQ_, true>(P, d_blob, H, d_qpos, row_stride, n, d_out, exact, sm_count, stream, d_n, d_n_mult) \
+                             : launch_is_valid_t<NQ_, false>(P, d_blob, H, d_qpos, row_stride, n, d_out, exact, sm_count, stream, d_n, d_n_mult))
+    if (P.nq == 384) return VK_LAUNCH(384);
+    if (P.nq == 256) return VK_LAUNCH(256);
+    return VK_LAUNCH(128);
+#undef VK_LAUNCH
 }
 
 #ifdef MOPA_VK_STATS
