@@ -48,12 +48,15 @@ __device__ unsigned long long g_vk_stats[16][4];
 struct MprItem { int q, p; float ca[3], Ra[9], cb[3], Rb[9]; };   // 104 bytes: global query row, pair, the two world frames
 
 // one (query, pair) item of the analytic / box-box classes: distance against the threshold
-template <bool MESH>
+// (WITH_MPR = false: the caller only passes analytic and box-box pairs - phase C; keeps the portal routine out of its loop body)
+template <bool MESH, bool WITH_MPR = true>
 __device__ __forceinline__ void eval_item(const SceneView &S, const float *frames, int stride, int ql, const PairRec &pr, float thr, uint32_t *res_q) {
     Geom a, b;
     load_geom<MESH>(a, S.recs[pr.ga], frames, stride, ql);
     load_geom<MESH>(b, S.recs[pr.gb], frames, stride, ql);
-    const float dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
+    float dist;
+    if (WITH_MPR) dist = pr.cls >= PC_BOX_BOX ? heavy_dist<MESH>(pr.cls, a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
+    else dist = pr.cls == PC_BOX_BOX ? box_box(a, b) : cheap_dist<MESH>(pr.cls, a, b, thr);
     if (dist <= thr) { atomicMin(res_q, (uint32_t)pr.canon); VK_STAT(pr.cls, 2); }
 }
 // the same for any class, out of line: a work list / queue that is full makes the pushing lane evaluate its item in place (rare)
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(NQ, NQ <= 128 ? 3 : 1) is_valid_kernel(const u
                 const uint32_t item = items[i];
                 const int ql = item >> 16, p = item & 0xFFFF;
                 if (!exact && res[ql] != 0xFFFFFFFFu) continue;   // already known to be invalid
-                eval_item<MESH>(S, frames, NQ, ql, S.pairs[p], thr, &res[ql]);
+                eval_item<MESH, false>(S, frames, NQ, ql, S.pairs[p], thr, &res[ql]);
             }
             if (!exact) __syncthreads();    // the cheap verdicts spare the expensive items of invalid states
         }
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(NQ, NQ <= 128 ? 3 : 1) is_valid_kernel(const u
 // an SM executes at any moment is one phase's loop (the kernel is ~130 KB of SASS, the instruction cache next to the SM 32 KB;
 // three independent 128-thread CTAs kept three different phases in flight and the kernel waited for instructions), and the
 // scene tables exist once per SM.  The frame store (frame floats x 4 B per query) decides which size fits.
-static const int VK_NQ_CHOICES[] = {384, 256, 128};
+static const int VK_NQ_CHOICES[] = {448, 384, 256, 128};
 
 // shared-memory plan for one scene: [blob][frames NQ x ffs][res NQ][counters][work lists]
 struct VkPlan { int nq, ffs, cap_cheap, cap_box, cap_mpr, mq_cap, mq_run; size_t smem; int per_sm; };
@@ -422,6 +425,7 @@ cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, c
     const bool mesh = H.n_hull_vert > 0;   // scenes with mesh colliders run the instantiation that carries the hull support
 #define VK_LAUNCH(NQ_) (mesh ? launch_is_valid_t<NQ_, true>(P, d_blob, H, d_qpos, row_stride, n, d_out, exact, sm_count, stream, d_n, d_n_mult) \
                              : launch_is_valid_t<NQ_, false>(P, d_blob, H, d_qpos, row_stride, n, d_out, exact, sm_count, stream, d_n, d_n_mult))
+    if (P.nq == 448) return VK_LAUNCH(448);
     if (P.nq == 384) return VK_LAUNCH(384);
     if (P.nq == 256) return VK_LAUNCH(256);
     return VK_LAUNCH(128);
