@@ -470,11 +470,29 @@ def run_validity(args):
         planner.is_valid_host_f32(h_pinned.data_ptr(), row, n, h_words.data_ptr(), 0)
     barrier()
     e2e_s = time.perf_counter() - t0
+    full_rows_e2e_s, e2e_api, e2e_h2d = e2e_s, "mopa_is_valid_host_f32 (pinned host rows of nq floats in, result words out)", n * row * 4
+    # The reference's own convention (KinematicPlanner::isValidState): a state is the vector of the planned joints, the passive
+    # joints are the planner's.  Applies when the passive entries are the same in every query (push scene: all at qpos0).
+    passive_cols = [i for i in range(model.nq) if i not in set(ref)]
+    if sorted(ref) == list(ref) and np.all(hq[:, passive_cols] == hq[0, passive_cols]):
+        h_active = torch.from_numpy(np.ascontiguousarray(hq[:, ref])).pin_memory()
+        base = hq[0, :model.nq].copy()
+        h_words_full = h_words.clone()
+        planner.is_valid_active_host_f32(h_active.data_ptr(), n, base, h_words.data_ptr(), 0)
+        assert torch.equal(h_words, h_words_full), "active-joint and full-row entry points disagree"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            planner.is_valid_active_host_f32(h_active.data_ptr(), n, base, h_words.data_ptr(), 0)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_api = "mopa_is_valid_active_host_f32 (pinned host states of the %d planned joints in - the reference's isValidState convention -, result words out)" % len(ref)
+        e2e_h2d = n * len(ref) * 4
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, full_rows_e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(t[0]), float(t[1])
+    total_ms, e2e_s, full_rows_e2e_s = float(t[0]), float(t[1]), float(t[2])
     words = d_r.cpu().numpy().view(np.uint32)
     assert np.array_equal(words & 1, h_words.numpy().view(np.uint32) & 1), "device-resident and end-to-end paths disagree"
     if rank == 0:
@@ -493,8 +511,8 @@ def run_validity(args):
             "config": {"workload": (WORKLOADS["validity"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]), "queries_per_gpu": n, "row_bytes": row * 4,
                        "l2": "inputs (%.2f GB per GPU) larger than L2" % (n * row * 4 / 1e9), "valid_fraction": float((words & 1).mean())},
             "clocks": clocks,
-            "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * row * 4, "d2h_bytes_per_step": n * 4,
-                    "api": "mopa_is_valid_host_f32 (pinned host rows in, result words out)"},
+            "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": n * 4,
+                    "api": e2e_api, "full_rows_value": world * n * e2e_steps / full_rows_e2e_s, "full_rows_h2d_bytes_per_step": n * row * 4},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (lambda t: None if t is None else int(t * n / 2_000_000))(ncu_traffic("r2_validity_traffic.json") if args.task == "push" else None),

@@ -86,6 +86,14 @@ int mopa_is_valid_host(mopa_planner *p, const double *qpos, int32_t n, uint8_t *
  * host->device copy, the kernel and the device->host copy of the result words overlap. */
 int mopa_is_valid_host_f32(mopa_planner *p, const float *qpos, int32_t row_stride, int32_t n, uint32_t *words, int32_t flags);
 
+/* The reference's own calling convention (KinematicPlanner::isValidState(std::vector<double> state_vec),
+ * KinematicPlanner.cpp:253-286; SamplingBasedPlanner.isValidState in sampling_based_planner.py): a state is the vector of
+ * the ACTIVE joints (the planner's state space, n_active values, in the order of mopa_planner_info / the non-passive qpos
+ * indices), the passive joints keep the values of base_qpos (nq floats, host) - the planner's own mjData in the reference.
+ * n host states of n_active floats each (pinned memory recommended); 5x less host->device traffic than full qpos rows for
+ * the Sawyer scenes.  Rows are expanded on the device and checked by the same kernel: identical result words. */
+int mopa_is_valid_active_host_f32(mopa_planner *p, const float *active, int32_t n, const float *base_qpos, uint32_t *words, int32_t flags);
+
 /* Node capacity of each RRT tree (default 4096).  A tree that fills up stops growing. */
 int mopa_planner_set_max_nodes(mopa_planner *p, int32_t max_nodes);
 

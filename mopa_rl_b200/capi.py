@@ -42,6 +42,7 @@ def lib():
         L.mopa_is_valid_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.mopa_is_valid_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.mopa_is_valid_host_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+        L.mopa_is_valid_active_host_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.mopa_planner_set_max_nodes.argtypes = [C.c_void_p, C.c_int32]
         L.mopa_plan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -153,6 +154,23 @@ class NativePlanner:
     def is_valid_host_f32(self, qpos_ptr, row_stride, n, words_ptr, flags=VALID_FAST):
         """Host fp32 rows (ideally pinned) -> result words in host memory; pipelined copies; blocks until done."""
         check(self._L.mopa_is_valid_host_f32(self.h, C.c_void_p(qpos_ptr), int(row_stride), int(n), C.c_void_p(words_ptr), int(flags)))
+
+    def is_valid_active_host_f32(self, active_ptr, n, base_qpos, words_ptr, flags=VALID_FAST):
+        """The reference's convention (KinematicPlanner::isValidState): host fp32 states of the n_active planned joints
+        (ideally pinned), passive joints from `base_qpos` (nq values) -> result words in host memory; blocks until done."""
+        base = np.ascontiguousarray(base_qpos, dtype=np.float32)
+        if base.shape != (self.nq,):
+            raise ValueError("base_qpos must have dimension nq: %d" % self.nq)
+        check(self._L.mopa_is_valid_active_host_f32(self.h, C.c_void_p(active_ptr), int(n), _p(base), C.c_void_p(words_ptr), int(flags)))
+
+    def is_valid_active(self, active, base_qpos, flags=VALID_FAST):
+        """numpy convenience over is_valid_active_host_f32: active[n, n_active] -> valid[n] (bool)."""
+        a = np.ascontiguousarray(np.atleast_2d(active), dtype=np.float32)
+        if a.shape[1] != self.n_active:
+            raise ValueError("active states must have dimension n_active: %d" % self.n_active)
+        words = np.zeros(len(a), np.uint32)
+        self.is_valid_active_host_f32(a.ctypes.data, len(a), base_qpos, words.ctypes.data, flags)
+        return (words & 1).astype(bool) if not flags else words
 
     def set_max_nodes(self, max_nodes):
         check(self._L.mopa_planner_set_max_nodes(self.h, int(max_nodes)))

@@ -89,6 +89,7 @@ void mopa_planner_destroy(mopa_planner *p) {
     for (int k = 0; k < 2; k++) {
         if (p->pipe_q[k]) cudaFree(p->pipe_q[k]);
         if (p->pipe_r[k]) cudaFree(p->pipe_r[k]);
+        if (p->pipe_a[k]) cudaFree(p->pipe_a[k]);
         if (p->pipe_stream[k]) cudaStreamDestroy(p->pipe_stream[k]);
     }
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -207,6 +208,56 @@ int mopa_is_valid_host_f32(mopa_planner *p, const float *qpos, int32_t row_strid
         cudaStream_t st = p->pipe_stream[k];
         CUDA_TRY(cudaMemcpyAsync(p->pipe_q[k], qpos + (size_t)off * row_stride, (size_t)m * row_stride * sizeof(float), cudaMemcpyHostToDevice, st));
         CUDA_TRY(mopa::launch_is_valid(p->d_blob, p->scene.hdr, p->pipe_q[k], row_stride, m, p->pipe_r[k], flags & MOPA_VALID_FIRST_PAIR, p->sm_count, st));
+        CUDA_TRY(cudaMemcpyAsync(words + off, p->pipe_r[k], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[1]));
+    return MOPA_OK;
+}
+
+// full qpos rows from rows that hold the active joints only: row[adr[k]] = active[k], every other entry from the base row
+__global__ void expand_active_rows_kernel(const float *__restrict__ active, int na, const int *__restrict__ adr, const float *__restrict__ base,
+                                          int nq, int row_stride, int n, float *__restrict__ rows) {
+    const long long total = (long long)n * row_stride;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / row_stride), c = (int)(i - (long long)r * row_stride);
+        float v = c < nq ? base[c] : 0.0f;
+        for (int k = 0; k < na; k++) if (adr[k] == c) v = active[(size_t)r * na + k];
+        rows[i] = v;
+    }
+}
+
+int mopa_is_valid_active_host_f32(mopa_planner *p, const float *active, int32_t n, const float *base_qpos, uint32_t *words, int32_t flags) {
+    if (!p || n < 0 || !base_qpos || (n > 0 && (!active || !words))) { g_err = "mopa_is_valid_active_host_f32: bad argument"; return MOPA_ERR_ARG; }
+    if (n == 0) return MOPA_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int chunk = 1 << 19, nq = p->scene.hdr.nq, row = 4 * p->scene.hdr.nq4, na = p->space.n_active;
+    if (!p->pipe_q[0] || p->pipe_stride != row) {
+        for (int k = 0; k < 2; k++) {
+            if (p->pipe_q[k]) cudaFree(p->pipe_q[k]);
+            if (p->pipe_r[k]) cudaFree(p->pipe_r[k]);
+            p->pipe_q[k] = nullptr; p->pipe_r[k] = nullptr;
+            CUDA_TRY(cudaMalloc(&p->pipe_q[k], (size_t)chunk * row * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&p->pipe_r[k], (size_t)chunk * sizeof(uint32_t)));
+            if (!p->pipe_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&p->pipe_stream[k], cudaStreamNonBlocking));
+        }
+        p->pipe_stride = row;
+    }
+    if (!p->pipe_a[0]) {
+        for (int k = 0; k < 2; k++) CUDA_TRY(cudaMalloc(&p->pipe_a[k], (size_t)chunk * na * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&p->d_base_row, (size_t)nq * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&p->d_active_adr, (size_t)na * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(p->d_active_adr, p->space.active_qadr.data(), (size_t)na * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(p->d_base_row, base_qpos, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice));   // synchronous: ordered before both streams' work
+    int k = 0;
+    for (int off = 0; off < n; off += chunk, k ^= 1) {
+        const int m = (n - off) < chunk ? (n - off) : chunk;
+        cudaStream_t st = p->pipe_stream[k];
+        CUDA_TRY(cudaMemcpyAsync(p->pipe_a[k], active + (size_t)off * na, (size_t)m * na * sizeof(float), cudaMemcpyHostToDevice, st));
+        expand_active_rows_kernel<<<p->sm_count * 8, 256, 0, st>>>(p->pipe_a[k], na, p->d_active_adr, p->d_base_row, nq, row, m, p->pipe_q[k]);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(mopa::launch_is_valid(p->d_blob, p->scene.hdr, p->pipe_q[k], row, m, p->pipe_r[k], flags & MOPA_VALID_FIRST_PAIR, p->sm_count, st));
         CUDA_TRY(cudaMemcpyAsync(words + off, p->pipe_r[k], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(p->pipe_stream[0]));

@@ -46,6 +46,10 @@ struct mopa_planner {
     uint32_t *pipe_r[2] = {nullptr, nullptr};
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};
     int pipe_stride = 0;
+    // mopa_is_valid_active_host_f32: compact rows (active joints only) as uploaded, and the row the passive joints come from
+    float *pipe_a[2] = {nullptr, nullptr};
+    float *d_base_row = nullptr;
+    int *d_active_adr = nullptr;
     // RRT-Connect work buffers (plan.cu)
     void *plan_buffers = nullptr;
     int max_nodes = 4096;  // node capacity per tree

@@ -54,6 +54,29 @@ def test_edge_sizes(push_pair, push_model):
         native.is_valid_host(np.zeros(push_model.nq - 1))
 
 
+def test_active_joint_states_give_the_same_words_as_full_rows(push_pair, push_model):
+    """KinematicPlanner::isValidState's own convention (KinematicPlanner.cpp:253-286): a state is the vector of the planned joints,
+    the passive joints come from the planner's qpos.  Sizes on both sides of the 448-query CTA switch, both result formats,
+    a moved cube in the base row."""
+    native, orc, ref = push_pair
+    assert native.n_active == len(ref) == 7
+    base = push_model.qpos0.copy()
+    a = push_model.get_joint_qpos_addr("cube")[0]
+    base[a:a + 3] += [0.03, -0.05, 0.02]
+    base = base.astype(np.float32).astype(np.float64)
+    for n in (0, 1, 1000, 70000, 150001):
+        q = random_qpos(push_model, n, 300 + n, ref) if n else np.zeros((0, push_model.nq))
+        q[:, [i for i in range(push_model.nq) if i not in ref]] = base[[i for i in range(push_model.nq) if i not in ref]]
+        act = np.ascontiguousarray(q[:, ref], dtype=np.float32)
+        ow = orc.is_valid(q) if n else np.zeros(0, np.uint32)
+        w = native.is_valid_active(act, base, flags=1) if n else np.zeros(0, np.uint32)
+        assert np.array_equal(w, ow), (n, int((w != ow).sum()))
+        if n:
+            assert np.array_equal(native.is_valid_active(act, base), (ow & 1).astype(bool))
+    with pytest.raises(ValueError):
+        native.is_valid_active(np.zeros((3, 6), np.float32), base)
+
+
 def test_passive_dims_matter_only_where_they_should(push_pair, push_model):
     """Ghost-arm joints (contype=conaffinity=0 chains) never change validity; the cube pose does."""
     native, orc, ref = push_pair
