@@ -103,6 +103,7 @@ int mopa_env_create(const mopa_dyn_desc *dyn, const mopa_sawyer_task *task, int3
     mopa::fill_model(dyn, e->h_model);
     if (e->h_model.ngm > mopa::DMAXGM) { mopa_set_error("mopa_env_create: more rotated moving geoms than the env kernel caches"); delete e; return MOPA_ERR_MODEL; }
     cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (err == cudaSuccess) err = cudaMalloc(&e->d_model, sizeof(mopa::DynDev));
     if (err == cudaSuccess) err = cudaMemcpy(e->d_model, &e->h_model, sizeof(mopa::DynDev), cudaMemcpyHostToDevice);
     static int next_slot = 0;

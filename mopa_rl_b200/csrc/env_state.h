@@ -12,7 +12,7 @@ cudaError_t env_prof_read(unsigned long long *out);
 }
 
 struct mopa_env {
-    int device = 0;
+    int device = 0, sm_count = 148;
     int model_slot = 0;          // slot of this scene in the warp kernel's constant memory
     mopa::DynDev *d_model = nullptr;
     mopa::DynDev h_model;

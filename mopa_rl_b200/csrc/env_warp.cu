@@ -1165,7 +1165,7 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> 
 
 
 template <int WB, int WG, int WC, int ENV_WARPS>
-__global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 ? 2 : 1))
+__global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 && WB <= 14 ? 2 : 1))
 env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
                      const int32_t *__restrict__ ids) {
@@ -1582,7 +1582,7 @@ cudaError_t env_prof_read(unsigned long long *out) { return cudaMemcpyFromSymbol
 template <int WB, int WG, int WC, int ENV_WARPS>
 static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_env_buffers &B, const float *action,
                                      int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
-                                     const int32_t *ids, cudaStream_t stream) {
+                                     const int32_t *ids, cudaStream_t stream, int sm_count) {
     static bool attr_set = false;
     static_assert(sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS <= 227 * 1024, "warp workspaces exceed the shared memory of an SM");
     const size_t smem = sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS;
@@ -1592,6 +1592,9 @@ static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, cons
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    if (n <= 0) return cudaSuccess;
+    // full CTAs of ENV_WARPS environments (dealing them evenly over rounds x SMs CTAs - fewer warps per SM, the rest idle at the
+    // barriers - was measured: 2-5 % slower on all three tasks)
     kern<<<(n + ENV_WARPS - 1) / ENV_WARPS, ENV_WARPS * 32, smem, stream>>>(model_slot, d_model, B, action, action_stride, is_planner, mask, n,
                                                                             forward_only, ids);
     return cudaGetLastError();
@@ -1626,11 +1629,16 @@ cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const floa
     const int model_slot = env->model_slot, nb = env->h_model.nb, ngeom = env->h_model.ngeom, ngm = env->h_model.ngm;
     const DynDev *d_model = env->d_model;
     const bool small = nb <= 14 && ngeom <= 32 && ngm <= WarpWS<14, 32, 24>::WGM;
-    if (small && small_warps)
-        return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+    // A launch is `rounds x the latency of one env.step`, and that latency grows with the warps an SM interleaves: a batch that
+    // fits one round of 7-warp CTAs (<= 7 environments per SM) runs them instead of filling fewer SMs with 11 / 14 warps.
+    const bool one_light_round = n <= 7 * env->sm_count;
+    if (small && (small_warps || one_light_round))
+        return launch_env_warp_t<14, 32, 24, 7>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count);
     if (small)
-        return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
-    return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream);
+        return launch_env_warp_t<14, 32, 24, 14>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count);
+    if (one_light_round)
+        return launch_env_warp_t<DMAXB, DMAXG, 32, 7>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count);
+    return launch_env_warp_t<DMAXB, DMAXG, 32, 11>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count);
 }
 
 cudaError_t launch_pusher(mopa_env *env, const mopa_env_buffers &B, const float *action, int action_stride, const uint8_t *is_planner,
