@@ -323,9 +323,9 @@ __device__ __forceinline__ void w_integrate_pos(const DynDev &m, WarpWS<WB, WG, 
 // ND: the scene's dof count as a compile-time constant (0 = read it from the model).  All three Sawyer scenes have 15 simulated dofs;
 // with the count fixed the per-dof / per-row loops unroll and their index arithmetic folds (the kernel is bound by the dependent
 // instruction chain of one env.step, and 2/3 of its instructions were loop control and addressing).
-template <int WB, int WG, int WC, int ND>
+template <int WB, int WG, int WC, int ND, int NB>   // NB: likewise the number of simulated bodies (14 on the push scene)
 __device__ __noinline__ bool w_stage_dynamics(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, const int4 keep_bodies, bool sync) {
-    const int nb = m.nb, nd = ND > 0 ? ND : m.nd;
+    const int nb = NB > 0 ? NB : m.nb, nd = ND > 0 ? ND : m.nd;
     long long t_last = c_tune.prof ? clock64() : 0;
     if (lane < nd) W.qd[lane] = W.v[m.d_vadr[lane]];
     __syncwarp();
@@ -1100,7 +1100,7 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
     STAGE_SYNC(7);   // 7: state advanced
 }
 
-template <int WB, int WG, int WC, bool RK = false, int ND = 0>   // RK: the instantiation that also serves smode 2 / 3 (Pusher); the Sawyer kernels keep their code
+template <int WB, int WG, int WC, bool RK = false, int ND = 0, int NB = 0>   // RK: the instantiation that also serves smode 2 / 3 (Pusher); the Sawyer kernels keep their code
 __device__ __forceinline__ void w_substep(const DynDev &m, const DynDev *__restrict__ mg, WarpWS<WB, WG, WC> &W, unsigned comp, int smode, int lane, int &ncon_out, int &nwt_out, double &cforce_out, const int4 keep_bodies,
                                           bool active, bool sync) {
     if (!active) {   // barrier-only participant: one barrier per stage boundary
@@ -1108,7 +1108,7 @@ __device__ __forceinline__ void w_substep(const DynDev &m, const DynDev *__restr
         for (int k = 1; k <= 7; k++) STAGE_SYNC(k);
         return;
     }
-    if (!w_stage_dynamics<WB, WG, WC, ND>(m, mg, W, comp, smode, lane, keep_bodies, sync)) return;
+    if (!w_stage_dynamics<WB, WG, WC, ND, NB>(m, mg, W, comp, smode, lane, keep_bodies, sync)) return;
     int nlim = 0;
     const int ncp = w_stage_contacts<WB, WG, WC, RK, ND>(m, mg, W, lane, nlim);
     ncon_out = ncp;
@@ -1167,7 +1167,7 @@ __device__ void w_write_obs(const mopa_sawyer_task &T, const WarpWS<WB, WG, WC> 
 }
 
 
-template <int WB, int WG, int WC, int ENV_WARPS, int ND>
+template <int WB, int WG, int WC, int ENV_WARPS, int ND, int NB>
 __global__ void __launch_bounds__(ENV_WARPS * 32, (ENV_WARPS <= 7 && WB <= 14 ? 2 : 1))
 env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffers B, const float *__restrict__ action,
                      int action_stride, const uint8_t *__restrict__ is_planner, const uint8_t *__restrict__ mask, int n, int forward_only,
@@ -1184,7 +1184,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
         if (!forward_only) {
             int dummy = 0;
             double dummyf = 0;
-            for (int s = 0; s < T.nsub; s++) w_substep<WB, WG, WC, false, ND>(m, mg, W, 0u, true, lane, dummy, dummy, dummyf, make_int4(0, 0, 0, 0), false, true);
+            for (int s = 0; s < T.nsub; s++) w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, 0u, true, lane, dummy, dummy, dummyf, make_int4(0, 0, 0, 0), false, true);
         }
         return;
     }
@@ -1199,7 +1199,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
     int ncon = 0, nwt = 0;   // contacts of the last substep; Newton steps of this env.step (cost feedback for the caller's grouping)
     const int4 keep = make_int4(T.body_ee, T.body_cube, T.body_rclaw, T.body_lclaw);
     if (forward_only) {
-        w_substep<WB, WG, WC, false, ND>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
+        w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
         if (lane < WD) B.bias_prev[(size_t)e * WD + lane] = lane < m.nd ? W.bias[lane] : 0.0;
         w_write_obs(T, W, B.obs + (size_t)e * 40, lane);
         return;
@@ -1219,9 +1219,9 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
     __syncwarp();
     unsigned comp = 0;
     for (int k = 0; k < 7; k++) comp |= 1u << T.arm_dof[k];
-    if (mode == 2) w_substep<WB, WG, WC, false, ND>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
+    if (mode == 2) w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
     for (int s = 0; s < T.nsub; s++) {
-        w_substep<WB, WG, WC, false, ND>(m, mg, W, comp, true, lane, ncon, nwt, cforce, keep, mode != 2, true);
+        w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, comp, true, lane, ncon, nwt, cforce, keep, mode != 2, true);
         if (mode != 2 && lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1242,7 +1242,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
             corrupt = __any_sync(FULL, bad2);
             if (lane == 0) W.wn = 0;
             __syncwarp();
-            if (!corrupt) w_substep<WB, WG, WC, false, ND>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
+            if (!corrupt) w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
             ncon = 0; cforce = 0.0;
         }
     }
@@ -1320,7 +1320,7 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
     clipped = __any_sync(FULL, clipped) && !unstable;
     __syncwarp();
     if (clipped) {
-        w_substep<WB, WG, WC, false, ND>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
+        w_substep<WB, WG, WC, false, ND, NB>(m, mg, W, 0u, false, lane, ncon, nwt, cforce, keep, true, false);
         if (lane < m.nd) W.bias_prev[lane] = W.bias[lane];
         __syncwarp();
     }
@@ -1582,14 +1582,14 @@ cudaError_t env_tune_set(int prof, int sync_mask) {
 }
 cudaError_t env_prof_read(unsigned long long *out) { return cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * 32); }
 
-template <int WB, int WG, int WC, int ENV_WARPS, int ND>
+template <int WB, int WG, int WC, int ENV_WARPS, int ND, int NB>
 static cudaError_t launch_env_warp_t(int model_slot, const DynDev *d_model, const mopa_env_buffers &B, const float *action,
                                      int action_stride, const uint8_t *is_planner, const uint8_t *mask, int n, int forward_only,
                                      const int32_t *ids, cudaStream_t stream, int sm_count) {
     static bool attr_set = false;
     static_assert(sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS <= 227 * 1024, "warp workspaces exceed the shared memory of an SM");
     const size_t smem = sizeof(WarpWS<WB, WG, WC>) * ENV_WARPS;
-    auto kern = env_step_warp_kernel<WB, WG, WC, ENV_WARPS, ND>;
+    auto kern = env_step_warp_kernel<WB, WG, WC, ENV_WARPS, ND, NB>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1632,15 +1632,16 @@ cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const floa
     const int model_slot = env->model_slot, nb = env->h_model.nb, ngeom = env->h_model.ngeom, ngm = env->h_model.ngm;
     const DynDev *d_model = env->d_model;
     const bool small = nb <= 14 && ngeom <= 32 && ngm <= WarpWS<14, 32, 24>::WGM;
-#define ENV_LAUNCH(WB_, WG_, WC_, W_, ND_) launch_env_warp_t<WB_, WG_, WC_, W_, ND_>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count)
-    if (env->h_model.nd != 15) return ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 0);   // any other scene: the generic instantiation
+#define ENV_LAUNCH(WB_, WG_, WC_, W_, ND_, NB_) launch_env_warp_t<WB_, WG_, WC_, W_, ND_, NB_>(model_slot, d_model, B, action, action_stride, is_planner, mask, n, forward_only, ids, stream, env->sm_count)
+    if (env->h_model.nd != 15) return ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 0, 0);   // any other scene: the generic instantiation
     // A launch is `rounds x the latency of one env.step`, and that latency grows with the warps an SM interleaves: a batch that
     // fits one round of 7-warp CTAs (<= 7 environments per SM) runs them instead of filling fewer SMs with 11 / 14 warps.
     const bool one_light_round = n <= 7 * env->sm_count;
-    if (small && (small_warps || one_light_round)) return ENV_LAUNCH(14, 32, 24, 7, 15);
-    if (small) return ENV_LAUNCH(14, 32, 24, 14, 15);
-    if (one_light_round) return ENV_LAUNCH(DMAXB, DMAXG, 32, 7, 15);
-    return ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 15);
+    const bool small14 = small && nb == 14;   // the push scene: body count fixed as well
+    if (small14 && (small_warps || one_light_round)) return ENV_LAUNCH(14, 32, 24, 7, 15, 14);
+    if (small14) return ENV_LAUNCH(14, 32, 24, 14, 15, 14);
+    if (one_light_round) return ENV_LAUNCH(DMAXB, DMAXG, 32, 7, 15, 0);
+    return ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 15, 0);
 #undef ENV_LAUNCH
 }
 
