@@ -1640,6 +1640,8 @@ cudaError_t launch_env_warp(mopa_env *env, const mopa_env_buffers &B, const floa
     const bool small14 = small && nb == 14;   // the push scene: body count fixed as well
     if (small14 && (small_warps || one_light_round)) return ENV_LAUNCH(14, 32, 24, 7, 15, 14);
     if (small14) return ENV_LAUNCH(14, 32, 24, 14, 15, 14);
+    if (nb == 18) return one_light_round ? ENV_LAUNCH(DMAXB, DMAXG, 32, 7, 15, 18) : ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 15, 18);   // lift scene
+    if (nb == 19) return one_light_round ? ENV_LAUNCH(DMAXB, DMAXG, 32, 7, 15, 19) : ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 15, 19);   // assembly scene
     if (one_light_round) return ENV_LAUNCH(DMAXB, DMAXG, 32, 7, 15, 0);
     return ENV_LAUNCH(DMAXB, DMAXG, 32, 11, 15, 0);
 #undef ENV_LAUNCH
