@@ -57,7 +57,7 @@ struct WarpWS {
             // (implicit joint damping of the Euler update) is produced there by the upper half-warp while the lower one
             // factors M, and waits for the velocity update at the end of the substep.
             double L2[NTRI], invd2[WD];
-            alignas(16) double col2[2 * (WD + 2)];
+            alignas(16) double col2[4 * (WD + 2)];   // column buffers of w_factor_solve: per (half-warp, diagonal block)
         };
     };
     static_assert(WC * WD >= WB * 16 + WD * 6, "A must cover xpos / xquat / xmat / S so that L2 only overlaps arrays dead after stage 3");
@@ -76,6 +76,7 @@ struct WarpWS {
     int blk[WD];             // first dof of the kinematic tree that owns each dof
     unsigned short cand[WCAND];
     int ncand, ncp;
+    int blk0;                // dofs [0, blk0) and [blk0, nd) are two kinematic trees (0: any other structure): M is block diagonal
 };
 
 #define FULL 0xffffffffu
@@ -106,92 +107,106 @@ __device__ __forceinline__ double warp_sum(double x) {
 // (packed lower triangle, plus 1 / L_ii) for the backward substitution and for later triangular
 // solves of the caller.  Rows / columns nd..WD-1 are identity padding (no bound checks inside).
 //   (M + hs * diag) = L L^T,  x <- (M + hs * diag)^-1 x      x: shared, nd entries; col: shared, WD + 2 doubles, 16-byte aligned
-template <int J, int K>
-__device__ __forceinline__ void wfs_update(double (&row)[WD], const double (&c)[WD], int li) {
-    if constexpr (K < WD) {
-        if (li >= K) row[K] -= row[J] * c[K];
-        wfs_update<J, K + 1>(row, c, li);
+template <int N, int J, int K>
+__device__ __forceinline__ void wfs_update(double (&row)[N], const double (&c)[N], int lj) {
+    if constexpr (K < N) {
+        if (lj >= K) row[K] -= row[J] * c[K];
+        wfs_update<N, J, K + 1>(row, c, lj);
     }
 }
-template <int J, int K2>
-__device__ __forceinline__ void wfs_fetch(double (&c)[WD], const double *col) {
-    if constexpr (2 * K2 < WD) {
+template <int N, int K2>
+__device__ __forceinline__ void wfs_fetch(double (&c)[N], const double *col) {
+    if constexpr (2 * K2 < N) {
         const double2 v = reinterpret_cast<const double2 *>(col)[K2];
-        c[2 * K2] = v.x; c[2 * K2 + 1] = v.y;
-        wfs_fetch<J, K2 + 1>(c, col);
+        c[2 * K2] = v.x;
+        if constexpr (2 * K2 + 1 < N) c[2 * K2 + 1] = v.y;
+        wfs_fetch<N, K2 + 1>(c, col);
     }
 }
-template <int J>
-__device__ __forceinline__ void wfs_column(double (&row)[WD], double &xr, double &rme, int li, bool act, double *col) {
-    if constexpr (J < WD) {
-        if (li == J && act) { col[WD] = row[J]; col[WD + 1] = xr; }
+template <int N, int J>
+__device__ __forceinline__ void wfs_column(double (&row)[N], double &xr, double &rme, int lj, bool act, double *col) {
+    if constexpr (J < N) {
+        if (lj == J && act) { col[WD] = row[J]; col[WD + 1] = xr; }
         __syncwarp();
         const double djj = col[WD], rinv = rsqrt(djj), yj = col[WD + 1] * rinv;
-        if (li == J) { row[J] = djj * rinv; rme = rinv; xr = yj; }
-        else if (li > J) { row[J] *= rinv; xr -= row[J] * yj; if (act) col[li] = row[J]; }
+        if (lj == J) { row[J] = djj * rinv; rme = rinv; xr = yj; }
+        else if (lj > J) { row[J] *= rinv; xr -= row[J] * yj; if (act) col[lj] = row[J]; }
         __syncwarp();
-        if constexpr (J + 1 < WD) {
-            double c[WD];
-            wfs_fetch<J, (J + 1) / 2>(c, col);
-            wfs_update<J, J + 1>(row, c, li);
+        if constexpr (J + 1 < N) {
+            double c[N];
+            wfs_fetch<N, (J + 1) / 2>(c, col);
+            wfs_update<N, J, J + 1>(row, c, lj);
         }
-        wfs_column<J + 1>(row, xr, rme, li, act, col);
+        wfs_column<N, J + 1>(row, xr, rme, lj, act, col);
     }
 }
-template <int K>
-__device__ __forceinline__ void wfs_load(double (&row)[WD], const double *Msrc, double dd, int li, bool live) {
-    if constexpr (K < WD) {
-        row[K] = (live && K <= li) ? Msrc[TRI(li, K)] : 0.0;
-        if (K == li) row[K] = live ? row[K] + dd : 1.0;
-        wfs_load<K + 1>(row, Msrc, dd, li, live);
+template <int N, int K>
+__device__ __forceinline__ void wfs_load(double (&row)[N], const double *Msrc, double dd, int li, int s, bool live) {
+    if constexpr (K < N) {
+        row[K] = (live && s + K <= li) ? Msrc[TRI(li, s + K)] : 0.0;
+        if (s + K == li) row[K] = live ? row[K] + dd : 1.0;
+        wfs_load<N, K + 1>(row, Msrc, dd, li, s, live);
     }
 }
-template <int K>
-__device__ __forceinline__ void wfs_store(const double (&row)[WD], double *Lout, int li, bool live) {
-    if constexpr (K < WD) {
-        if (live && K <= li) Lout[TRI(li, K)] = row[K];
-        wfs_store<K + 1>(row, Lout, li, live);
+template <int N, int K>
+__device__ __forceinline__ void wfs_store(const double (&row)[N], double *Lout, int li, int s, bool live) {
+    if constexpr (K < N) {
+        if (live && s + K <= li) Lout[TRI(li, s + K)] = row[K];
+        wfs_store<N, K + 1>(row, Lout, li, s, live);
     }
 }
 // Lanes 0..15 factor Msrc + hs * diag and solve for x.  When Lout2 is given, lanes 16..31 factor Msrc + hs2 * diag2 in the same
-// instruction stream (factor only: Lout2 / invd2 feed w_solve_stored later); `col` then holds 2 x (WD + 2) doubles.
+// instruction stream (factor only: Lout2 / invd2 feed w_solve_stored later).
+// BLK0 > 0: the matrix is block diagonal with blocks [0, BLK0) and [BLK0, nd) - two kinematic trees, e.g. the arm and the free
+// object, and no constraint row that couples them - and the two blocks are eliminated side by side: a lane keeps the part of its
+// row that lies inside its block (register k <-> column block start + k), every block has its own column buffer, and the sweep
+// runs over max(block size) columns instead of WD (9 instead of 16 on the Sawyer scenes, with 9 row registers instead of 16).
+// The entries outside the blocks are exact zeros in the dense elimination too (x - 0 * y = x), so the factor is the same bit for
+// bit; they are neither written nor read here.  `col`: (WD + 2) doubles per (half-warp, block) in use, 16-byte aligned.
+template <int BLK0>
 __device__ __noinline__ void w_factor_solve(const double *Msrc, const double *diag, double hs, int nd, double *Lout, double *invd, double *x,
                                             double *col, int lane, double *Lout2 = nullptr, double *invd2 = nullptr,
                                             const double *diag2 = nullptr, double hs2 = 0.0) {
-    double row[WD];
+    constexpr int N = BLK0 > 0 ? (BLK0 > WD - BLK0 ? BLK0 : WD - BLK0) : WD;   // columns of the largest block
+    double row[N];
     const int li = lane & 15, half = lane >> 4;
+    const int b = (BLK0 > 0 && li >= BLK0) ? 1 : 0, s = b ? BLK0 : 0, lj = li - s;
     const bool act = half == 0 || Lout2 != nullptr;   // this half-warp owns a matrix
     const bool live = act && li < nd;
     const double *dg = half ? diag2 : diag;
-    wfs_load<0>(row, Msrc, (dg && live) ? (half ? hs2 : hs) * dg[li] : 0.0, li, live);
+    wfs_load<N, 0>(row, Msrc, (dg && live) ? (half ? hs2 : hs) * dg[li] : 0.0, li, s, live);
     double xr = (live && half == 0) ? x[li] : 0.0, rme = 0.0;
-    wfs_column<0>(row, xr, rme, li, act, col + (act ? half * (WD + 2) : 0));
-    wfs_store<0>(row, half ? Lout2 : Lout, li, live);
+    wfs_column<N, 0>(row, xr, rme, lj, act, col + (act ? (half * 2 + b) * (WD + 2) : 0));
+    wfs_store<N, 0>(row, half ? Lout2 : Lout, li, s, live);
     if (live) (half ? invd2 : invd)[li] = rme;
     __syncwarp();
-    // backward substitution L^T x = y: lane i broadcasts x_i, the lanes below it eliminate
+    // backward substitution L^T x = y: lane i broadcasts x_i, the lanes below it (in its block) eliminate
     for (int i = nd - 1; i >= 0; i--) {
         const double xi = shfl_d(xr * rme, i);
+        const int si = (BLK0 > 0 && i >= BLK0) ? BLK0 : 0;
         if (lane == i) xr = xi;
-        else if (lane < i) xr -= Lout[TRI(i, lane)] * xi;
+        else if (lane < i && lane >= si) xr -= Lout[TRI(i, lane)] * xi;
     }
     if (lane < nd) x[lane] = xr;
     __syncwarp();
 }
+constexpr int SAWYER_BLK0 = 9;   // the arm + gripper tree of the Sawyer scenes has 9 dofs; the free object follows
 // x <- (L L^T)^-1 x with a factor w_factor_solve stored earlier (same operation order as its fused forward substitution)
-__device__ __noinline__ void w_solve_stored(const double *L, const double *invd, int nd, double *x, int lane) {
+__device__ __noinline__ void w_solve_stored(const double *L, const double *invd, int nd, double *x, int lane, int blk0) {
     const bool live = lane < nd;
     double xr = live ? x[lane] : 0.0;
     const double rme = live ? invd[lane] : 0.0;
+    const int sl = (blk0 > 0 && lane >= blk0) ? blk0 : 0;   // first column of this lane's block
     for (int i = 0; i < nd; i++) {
         const double yi = shfl_d(xr * rme, i);
         if (lane == i) xr = yi;
-        else if (lane > i && live) xr -= L[TRI(lane, i)] * yi;
+        else if (lane > i && live && i >= sl) xr -= L[TRI(lane, i)] * yi;
     }
     for (int i = nd - 1; i >= 0; i--) {
         const double xi = shfl_d(xr * rme, i);
+        const int si = (blk0 > 0 && i >= blk0) ? blk0 : 0;
         if (lane == i) xr = xi;
-        else if (lane < i) xr -= L[TRI(i, lane)] * xi;
+        else if (lane < i && lane >= si) xr -= L[TRI(i, lane)] * xi;
     }
     if (live) x[lane] = xr;
     __syncwarp();
@@ -569,7 +584,8 @@ __device__ __noinline__ bool w_stage_dynamics(const DynDev &m, const DynDev *__r
     if (lane < nd) W.qacc0[lane] = W.tau[lane];
     __syncwarp();
     // upper half-warp: the factor the velocity update needs (Euler: M + h * diag(damping); explicit RK4 stage: M itself)
-    w_factor_solve(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
+    if (W.blk0 == SAWYER_BLK0) w_factor_solve<SAWYER_BLK0>(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
+    else w_factor_solve<0>(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
 
     STAGE_SYNC(4);   // 4: unconstrained acceleration done
     return true;
@@ -848,6 +864,15 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
             jv += jw;
         }
         __syncwarp();   // every Jacobian row is complete: the kinematic arrays may now be overwritten (W.A aliases them)
+        // The Hessian M + J^T K J stays block diagonal (arm | free object) unless a constraint row touches dofs of both trees
+        // (the arm in contact with the object): only then the dense elimination is needed.
+        bool both = false;
+        if (W.blk0 > 0 && r < nc) {
+            bool lo_nz = false, hi_nz = false;
+            for (int k = 0; k < nd; k++) { const bool nz = W.Y[r * YS + k] != 0.0; if (k < W.blk0) lo_nz |= nz; else hi_nz |= nz; }
+            both = lo_nz && hi_nz;
+        }
+        const int hblk = __any_sync(FULL, both) ? 0 : W.blk0;
         // ---- regulariser R = (1 - imp) / imp * (J M^-1 J^T)_rr with y = L^-1 J^T by forward substitution (lane = row)
         double aref = 0, Dr = 0;
         if (r < nc) {
@@ -1016,7 +1041,8 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
             const double matme = lane < nd ? W.z[lane] : 0.0;
             if (lane < nd) W.rhs[lane] = -gme;
             __syncwarp();
-            w_factor_solve(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.f, lane);
+            if (hblk == SAWYER_BLK0) w_factor_solve<SAWYER_BLK0>(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.col2, lane);
+            else w_factor_solve<0>(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.col2, lane);
             double pme = 0, mp = 0;
             if (lane < nd) {
                 pme = W.rhs[lane];
@@ -1085,12 +1111,12 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
     if (lane < nd) W.rhs[lane] = W.tau[lane] + fcv;
     __syncwarp();
     if (RK && smode == 2) {   // explicit stage of mj_RungeKutta: qacc = M^-1 (tau + J^T f), joint damping is part of tau
-        w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane);
+        w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane, W.blk0);
         STAGE_SYNC(7);
         return;
     }
     // ---- semi-implicit Euler with implicit joint damping (factor of M + h * diag(damping) from stage 4)
-    w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane);
+    w_solve_stored(W.L2, W.invd2, nd, W.rhs, lane, W.blk0);
     if (lane < nd) {
         W.qd[lane] += m.h * W.rhs[lane];
         W.v[m.d_vadr[lane]] = W.qd[lane];
@@ -1194,6 +1220,14 @@ env_step_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buf
     if (lane < DMAXA) W.ctrl[lane] = 0.0;
     if (lane == 0) W.wn = 0;
     if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
+    __syncwarp();
+    if (lane == 0) {   // two kinematic trees with contiguous dofs: [0, k) and [k, nd)
+        int k = 1;
+        while (k < m.nd && W.blk[k] == W.blk[0]) k++;
+        bool two = k < m.nd;
+        for (int j = k; j < m.nd && two; j++) two = W.blk[j] == W.blk[k];
+        W.blk0 = (two && k == SAWYER_BLK0 && m.nd - k <= WD - SAWYER_BLK0 && !((c_tune.sync_mask >> 9) & 1)) ? k : 0;   // (tuning bit 9: force the dense elimination)
+    }
     __syncwarp();
     double cforce = 0;
     int ncon = 0, nwt = 0;   // contacts of the last substep; Newton steps of this env.step (cost feedback for the caller's grouping)
@@ -1451,6 +1485,14 @@ pusher_warp_kernel(int model_slot, const DynDev *__restrict__ mg, mopa_env_buffe
     if (lane == 0) W.wn = 0;
     if (lane < WD) W.bias_prev[lane] = 0.0;
     if (lane < m.nd) { int r = lane; while (m.d_parent[r] >= 0) r = m.d_parent[r]; W.blk[lane] = r; }
+    __syncwarp();
+    if (lane == 0) {   // two kinematic trees with contiguous dofs: [0, k) and [k, nd)
+        int k = 1;
+        while (k < m.nd && W.blk[k] == W.blk[0]) k++;
+        bool two = k < m.nd;
+        for (int j = k; j < m.nd && two; j++) two = W.blk[j] == W.blk[k];
+        W.blk0 = (two && k == SAWYER_BLK0 && m.nd - k <= WD - SAWYER_BLK0 && !((c_tune.sync_mask >> 9) & 1)) ? k : 0;   // (tuning bit 9: force the dense elimination)
+    }
     if (fwd == 3) {   // ---- _reset: rejection sampling
         const unsigned long long gid = (unsigned long long)(env_id_offset + e), ep = (unsigned long long)d_episode[e];
         const int nq = m.nq, nv = m.nv;

@@ -149,8 +149,11 @@ def test_bench_config_subset_matches_scalar_loop_over_a_full_episode(oracle_buil
                 n_late += 1
         mine = rec[rec[:, 51] == gid][:len(srec)]
         assert len(mine) == len(srec), (gid, len(mine), len(srec))
+        # actions of relabelled records are displacements between visited states: they inherit the state error, so the
+        # rounding-level bound only holds for environments without a heavy-contact step (see above)
+        atol_ac = 1e-6 if first_heavy > len(sq) else 1e-3
         for k, (r, o) in enumerate(zip(mine, srec)):   # the macro-action structure agrees for every environment
-            assert np.allclose(r[40:40 + adim], o[40:40 + adim], atol=1e-6), (gid, k)
+            assert np.allclose(r[40:40 + adim], o[40:40 + adim], atol=atol_ac), (gid, k)
             assert r[49] == o[49] and r[50] == o[50], (gid, k, r[48:51], o[48:51])
             if first_heavy > len(sq):
                 assert abs(r[48] - o[48]) < 1e-4, (gid, k, r[48], o[48])
