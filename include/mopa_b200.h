@@ -245,6 +245,20 @@ typedef struct mopa_rollout_config {
     int32_t debug_block_mod;      /* test hook, 0 = off: treat the interior of densification hop i of a problem as blocked when
                                      (problem key + i) % debug_block_mod == 0, so that conformance tests reach the fallback planners
                                      (naturally ~0.3 % of the RRT plans have such a hop) */
+    /* config.use_ik_target (the MoPA-SAC IK presets, rl/mopa_rollouts.py:90-101, 355-362, 683-728): the policy acts in Cartesian
+     * space - action row = (default[3], quat[4], gripper) - and every macro action starts with _cart2dispalcement: target position
+     * = clip(site + action_range * default, world box), target orientation = mat2quat(site_xmat)[[3, 0, 1, 1]] (x) quat / |quat|
+     * (the reference's index list, kept), qpos_from_site_pose(max_steps, tol) on the arm joints, joint displacement = clipped
+     * result - current.  The displacement then takes the place of the action: |d_k| > omega -> planner branch, whose target is
+     * the CURRENT state in the reference (the increment sits behind `if not config.use_ik_target`, :114-131: the plan is a
+     * two-step hold), else env.step(d / omega (+ gripper)).  Use mopa_rollout_step_ik. */
+    int32_t use_ik_target;
+    int32_t ik_body;              /* simulated-body index that carries the site config.ik_target */
+    double ik_site_local[3];      /* the site's position in that body's frame (its local rotation must be the identity) */
+    double ik_world_lo[3], ik_world_hi[3];   /* env.min_world_size / env.max_world_size */
+    int32_t ik_max_steps;         /* 100 in the reference */
+    int32_t ik_pad_;
+    double ik_tol;                /* 1e-2 in the reference */
 } mopa_rollout_config;
 /* Counter slots of d_counters (int64[24]; the named ones below, the rest reserved). */
 #define MOPA_RO_COUNTERS "mp,rl,interpolation,mp_fail,approximate,invalid,densify_fallback,episodes,success,mp_path_len,interpolation_path_len,env_steps,transitions,rrt_dropped,rrt_problems,waiting,reused,unstable,fb_simple,fb_main"
@@ -265,6 +279,9 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream);
 int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream);
 /* discrete_action handles: d_ac_type uint8[n] (0 = direct execution, 1 = motion planner), the policy's ac["ac_type"]. */
 int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const uint8_t *d_ac_type, void *stream);
+/* use_ik_target handles: d_actions float[n][8] = (default[3], quat[4], gripper) per environment; the IK solve runs on the device
+ * for the environments that start a macro action, the records keep the policy's Cartesian action. */
+int mopa_rollout_step_ik(mopa_rollout *r, const float *d_actions, void *stream);
 /* Replicated replay (the consumer rl/dataset.py:7-37 replaces): step 1 of the per-tick exchange.  Copies the records emitted
  * since the previous call - at most `cap`, the rest stays queued in the ring - to d_send float[1 + cap][92]: row 0 is a header whose
  * first word holds the record count (int32 bits), rows 1.. the records.  The caller all-gathers d_send across ranks (NCCL) and hands

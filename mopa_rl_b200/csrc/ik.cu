@@ -26,6 +26,9 @@ struct IkArgs {
     int n, nq, body, nj, max_steps, use_quat;
     int jdof[IK_MAXJ];            // simulated-dof index of every movable joint
     double site[3], tol, rot_weight, max_update_norm, progress_thresh, reg;
+    // rollout mode (MoPARolloutRunner._cart2dispalcement): the target comes from the policy's Cartesian action and the start pose
+    int roll;
+    double action_range, world_lo[3], world_hi[3], jlo[IK_MAXJ], jhi[IK_MAXJ];
 };
 
 // mju_mat2Quat / mju_quat2Vel (dt = 1) as the reference calls them through dm_control's mjlib
@@ -57,10 +60,17 @@ __device__ inline void ik_quat2vel(double *res, const double *q) {
 
 __global__ void ik_kernel(const DynDev *__restrict__ mg, IkArgs A, const double *__restrict__ qpos_in, const double *__restrict__ target_pos,
                           const double *__restrict__ target_quat, double *__restrict__ qpos_out, double *__restrict__ err_out,
-                          int *__restrict__ steps_out, unsigned char *__restrict__ success_out) {
+                          int *__restrict__ steps_out, unsigned char *__restrict__ success_out,
+                          const float *__restrict__ policy_ac, const unsigned char *__restrict__ need, float *__restrict__ joint_ac) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= A.n) return;
+    if (A.roll && need && !need[t]) return;   // rollout mode: only the environments that start a macro action
     const DynDev &m = *mg;
+    double tpos[3], tquat[4];   // the target of this problem
+    if (!A.roll) {
+        for (int k = 0; k < 3; k++) tpos[k] = target_pos[(size_t)t * 3 + k];
+        if (A.use_quat) for (int k = 0; k < 4; k++) tquat[k] = target_quat[(size_t)t * 4 + k];
+    }
     double *q = qpos_out + (size_t)t * A.nq;
     for (int k = 0; k < A.nq; k++) q[k] = qpos_in[(size_t)t * A.nq + k];
     // chain of bodies from the tree root to the site's body
@@ -130,15 +140,34 @@ __global__ void ik_kernel(const DynDev *__restrict__ mg, IkArgs A, const double 
         double sp[3], tv[3];
         d_mv(tv, R, A.site);
         for (int k = 0; k < 3; k++) sp[k] = pos[k] + tv[k];
+        if (A.roll && steps == 0) {
+            // rl/mopa_rollouts.py:91-98: target_cart = clip(site_xpos + action_range * ac["default"], min_world_size, max_world_size)
+            const float *ac = policy_ac + (size_t)t * 8;
+            for (int k = 0; k < 3; k++) {
+                const double c = sp[k] + A.action_range * (double)ac[k];
+                tpos[k] = c < A.world_lo[k] ? A.world_lo[k] : (c > A.world_hi[k] ? A.world_hi[k] : c);
+            }
+            // :692-697: util.env.mat2quat(site_xmat) - the unit quaternion of the float32 copy of the matrix with w >= 0, returned as
+            // (x, y, z, w) - then the index list [3, 0, 1, 1] (sic) = (w, x, y, y), times the normalised action quaternion
+            double Rf[9], sq[4];
+            for (int k = 0; k < 9; k++) Rf[k] = (double)(float)R[k];
+            ik_mat2quat(sq, Rf);
+            if (sq[0] < 0) for (int k = 0; k < 4; k++) sq[k] = -sq[k];
+            const double t0[4] = {sq[0], sq[1], sq[2], sq[2]};
+            const float a0 = ac[3], a1 = ac[4], a2 = ac[5], a3 = ac[6];
+            const float an = sqrtf(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);
+            const double aq[4] = {(double)(a0 / an), (double)(a1 / an), (double)(a2 / an), (double)(a3 / an)};
+            d_qmul(tquat, t0, aq);
+        }
         // ---- error
         double err[6] = {0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < 3; k++) err[k] = target_pos[(size_t)t * 3 + k] - sp[k];
+        for (int k = 0; k < 3; k++) err[k] = tpos[k] - sp[k];
         err_norm = sqrt(err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
         if (A.use_quat) {
             double sq[4], nq4[4], eq[4];
             ik_mat2quat(sq, R);
             nq4[0] = sq[0]; nq4[1] = -sq[1]; nq4[2] = -sq[2]; nq4[3] = -sq[3];
-            d_qmul(eq, target_quat + (size_t)t * 4, nq4);
+            d_qmul(eq, tquat, nq4);
             ik_quat2vel(err + 3, eq);
             err_norm += sqrt(err[3] * err[3] + err[4] * err[4] + err[5] * err[5]) * A.rot_weight;
         }
@@ -184,10 +213,38 @@ __global__ void ik_kernel(const DynDev *__restrict__ mg, IkArgs A, const double 
         const double sc = un > A.max_update_norm ? A.max_update_norm / un : 1.0;
         for (int j = 0; j < A.nj; j++) q[m.d_qadr[A.jdof[j]]] += g[j] * sc;
     }
+    if (A.roll) {
+        // :710-727: target_qpos[ref] = result.qpos[ref], clipped to the joint ranges; displacement = target - current (+ the gripper entry)
+        for (int j = 0; j < A.nj; j++) {
+            const int a = m.d_qadr[A.jdof[j]];
+            double v = q[a];
+            v = v < A.jlo[j] ? A.jlo[j] : (v > A.jhi[j] ? A.jhi[j] : v);
+            joint_ac[(size_t)t * 8 + j] = (float)(v - qpos_in[(size_t)t * A.nq + a]);
+        }
+        joint_ac[(size_t)t * 8 + 7] = policy_ac[(size_t)t * 8 + 7];
+        return;
+    }
     if (steps == A.max_steps && steps > 0) steps = A.max_steps - 1;   // Python's `for steps in range(max_steps)` leaves the last index
     err_out[t] = err_norm;
     steps_out[t] = steps;
     success_out[t] = success ? 1 : 0;
+}
+
+// rollout front end of mopa_rollout_step_ik: Cartesian policy actions -> joint displacement rows for the environments flagged in `need`
+cudaError_t launch_ik_rollout(mopa_env *e, const double *d_qpos, const float *d_policy_ac, const unsigned char *d_need, int body,
+                              const double *site_local, const int *joint_dofs, int n_joints, int n, int max_steps, double tol,
+                              double action_range, const double *world_lo, const double *world_hi, const double *jlo, const double *jhi,
+                              double *d_qpos_scratch, float *d_joint_ac, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    if (n_joints < 1 || n_joints > IK_MAXJ - 1) return cudaErrorInvalidValue;
+    IkArgs A;
+    A.n = n; A.nq = e->h_model.nq; A.body = body; A.nj = n_joints; A.max_steps = max_steps; A.use_quat = 1; A.roll = 1;
+    for (int j = 0; j < n_joints; j++) { A.jdof[j] = joint_dofs[j]; A.jlo[j] = jlo[j]; A.jhi[j] = jhi[j]; }
+    for (int k = 0; k < 3; k++) { A.site[k] = site_local[k]; A.world_lo[k] = world_lo[k]; A.world_hi[k] = world_hi[k]; }
+    A.tol = tol; A.rot_weight = 1.0; A.max_update_norm = 2.0; A.progress_thresh = 20.0; A.reg = 3e-2; A.action_range = action_range;
+    ik_kernel<<<(n + 63) / 64, 64, 0, stream>>>(e->d_model, A, d_qpos, nullptr, nullptr, d_qpos_scratch, nullptr, nullptr, nullptr, d_policy_ac, d_need,
+                                                d_joint_ac);
+    return cudaGetLastError();
 }
 
 }  // namespace mopa
@@ -202,6 +259,7 @@ extern "C" int mopa_ik_batch(mopa_env *e, const double *d_qpos, const double *d_
     }
     if (n == 0) return MOPA_OK;
     mopa::IkArgs A;
+    A.roll = 0;
     A.n = n; A.nq = e->h_model.nq; A.body = body; A.nj = n_joints; A.max_steps = max_steps; A.use_quat = d_target_quat ? 1 : 0;
     for (int j = 0; j < n_joints; j++) A.jdof[j] = joint_dofs[j];
     for (int k = 0; k < 3; k++) A.site[k] = site_local[k];
@@ -209,7 +267,7 @@ extern "C" int mopa_ik_batch(mopa_env *e, const double *d_qpos, const double *d_
     cudaError_t err = cudaSetDevice(e->device);
     if (err == cudaSuccess) {
         mopa::ik_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->d_model, A, d_qpos, d_target_pos, d_target_quat, d_qpos_out, d_err, d_steps,
-                                                                        d_success);
+                                                                        d_success, nullptr, nullptr, nullptr);
         err = cudaGetLastError();
     }
     if (err != cudaSuccess) { mopa_set_error(std::string("mopa_ik_batch: ") + cudaGetErrorString(err)); return MOPA_ERR_CUDA; }

@@ -29,6 +29,11 @@ namespace mopa {
 cudaError_t launch_is_valid(const unsigned char *d_blob, const SceneHeader &H, const float *d_qpos, int row_stride, int n,
                             uint32_t *d_out, int exact, int sm_count, cudaStream_t stream, const int *d_n = nullptr, int d_n_mult = 1);
 
+cudaError_t launch_ik_rollout(mopa_env *e, const double *d_qpos, const float *d_policy_ac, const unsigned char *d_need, int body,
+                              const double *site_local, const int *joint_dofs, int n_joints, int n, int max_steps, double tol,
+                              double action_range, const double *world_lo, const double *world_hi, const double *jlo, const double *jhi,
+                              double *d_qpos_scratch, float *d_joint_ac, cudaStream_t stream);
+
 constexpr int RO_JMAX = 16;     // interpolation points checked per straight-line plan
 constexpr int RO_NQ = 40;       // qpos capacity (same as the env kernel)
 enum { C_MP = 0, C_RL, C_INTERP, C_MP_FAIL, C_APPROX, C_INVALID, C_DENSIFY_FALLBACK, C_EPISODES, C_SUCCESS, C_MP_PATH_LEN,
@@ -95,6 +100,11 @@ struct RoDev {   // everything the kernels need, passed by value
     double *grip0;               // [n] gripper qpos when the current plan was made (SawyerEnv.form_action with dof == 8, :290-296)
     int ac_normal;               // config.ac_space_type == "normal": displacement = a * action_range (rl/sac_agent.py:160-163, 180-181)
     int discrete;                // config.discrete_action: the policy's ac_type chooses planner / direct execution
+    int ik_mode;                 // config.use_ik_target: the action row handed to ro_begin is the IK joint displacement (radians), the
+                                 // record keeps the policy's Cartesian action, a planner-branch target is the current state
+    float *ctl;                  // [n][8] what is executed: the clipped action, or the IK displacement (+ gripper)
+    float *ik_ac;                // [n][8] IK mode: joint displacement rows produced by the IK front end
+    double *ik_q;                // [n][nq] IK mode: scratch states of the solver
     unsigned long long seed_reuse;
     float *ob_hist;              // [n][max_traj][40]  observation after step i of the current plan
     double *rew_hist;            // [n][max_traj]      cumulative discounted reward after step i
@@ -254,16 +264,20 @@ __global__ void ro_pre_kernel(RoDev S, mopa_env_buffers B, int nv) {
 
 // ---- 2. new macro actions: direct action, or planner target (SACAgent.convert2planner_displacement + target clip)
 // config.discrete_action (rl/mopa_rollouts.py:86-88, 104-111): the branch is chosen by the policy's ac_type instead of |a| > omega.
-__global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__restrict__ actions, const unsigned char *__restrict__ ac_type) {
+// use_ik_target (rec_actions != nullptr): `actions` holds the joint displacement of _cart2dispalcement (radians, not clipped to the action
+// box: the reference compares it with omega and divides it by omega as it is), rec_actions the policy's (default[3], quat[4], gripper).
+__global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__restrict__ actions, const unsigned char *__restrict__ ac_type,
+                                const float *__restrict__ rec_actions) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n || !S.need[e]) return;
     float a32[7];
     bool is_mp = false;
     for (int k = 0; k < S.na; k++) {
         float a = actions[(size_t)e * S.adim + k];
-        a = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
+        if (!rec_actions) a = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
         a32[k] = a;
-        S.ac[(size_t)e * 8 + k] = a;
+        S.ctl[(size_t)e * 8 + k] = a;
+        S.ac[(size_t)e * 8 + k] = rec_actions ? rec_actions[(size_t)e * 8 + k] : a;
         if (fabs((double)a) > S.omega) is_mp = true;
     }
     if (S.discrete) { is_mp = ac_type[e] != 0; S.ac[(size_t)e * 8 + 7] = is_mp ? 1.0f : 0.0f; }
@@ -290,6 +304,7 @@ __global__ void ro_begin_kernel(RoDev S, mopa_env_buffers B, const float *__rest
         const double disp = S.ac_normal ? a * S.action_range
                             : aa < w ? a / (w / S.ac_scale)
                                      : (a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0)) * (S.ac_scale + (S.action_range - S.ac_scale) * ((aa - w) / (1 - w)));
+        if (rec_actions) continue;   // use_ik_target: target_qpos stays curr_qpos (rl/mopa_rollouts.py:82, 114-131)
         double t = curr[S.arm_qadr[k]] + disp;
         t = t < S.jlo[k] ? S.jlo[k] : t;
         t = t > S.jhi[k] ? S.jhi[k] : t;
@@ -709,7 +724,7 @@ __global__ void ro_stage_kernel(RoDev S, mopa_env_buffers B) {
     float *sa = S.step_action + (size_t)e * 8;
     if (kind == 0) {
         // direct execution: ac / omega, or the raw action with discrete_action (rl/mopa_rollouts.py:347-352)
-        for (int k = 0; k < S.na; k++) sa[k] = S.discrete ? S.ac[(size_t)e * 8 + k] : (float)((double)S.ac[(size_t)e * 8 + k] / S.omega);
+        for (int k = 0; k < S.na; k++) sa[k] = S.discrete ? S.ctl[(size_t)e * 8 + k] : (float)((double)S.ctl[(size_t)e * 8 + k] / S.omega);
         if (S.adim == 8) sa[7] = S.ac[(size_t)e * 8 + 7];   // rescaled_ac: only the joint entries are divided by omega (:349-352)
     } else if (kind == 1) {
         int pos = S.traj_pos[e];
@@ -761,6 +776,7 @@ struct mopa_rollout {
     int simple_max_iter = 25;    // iteration cap of the "simple" planner (stands in for simple_planner_timelimit)
     float simple_range = 0.05f;  // config.simple_planner_range
     int pack_parity = 0;
+    mopa_rollout_config cfg;     // the creation-time configuration (the IK front end reads its site / world-box fields)
     int *h_overflow = nullptr;   // mapped host memory: see RoDev::xfer_overflow
     int plan_cta_warps = 1;      // tuning hook: MOPA_PLAN_CTA_WARPS
     cudaStream_t plan_stream = nullptr;
@@ -815,6 +831,10 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
             return MOPA_ERR_ARG;
         }
     }
+    if (cfg->use_ik_target && (cfg->discrete_action || env->task.kind != 1 || cfg->ik_body < 0 || cfg->ik_body >= env->h_model.nb || cfg->ik_max_steps < 1)) {
+        mopa_set_error("mopa_rollout_create: use_ik_target needs the lift task (8-entry Cartesian actions), no discrete_action and a valid ik_body");
+        return MOPA_ERR_ARG;
+    }
     mopa_rollout *r = new mopa_rollout();
     r->env = env; r->planner = planner; r->buf = *buf; r->max_iter = cfg->max_iter;
     r->simple_max_iter = cfg->simple_max_iter > 0 ? cfg->simple_max_iter : 0;   // 0: the simple planner gives up at once (tests of the main-planner retry)
@@ -843,6 +863,8 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     S.ring = d_ring; S.ring_cap = ring_capacity;
     S.discrete = cfg->discrete_action ? 1 : 0;
     S.ac_normal = cfg->ac_space_normal ? 1 : 0;
+    S.ik_mode = cfg->use_ik_target ? 1 : 0;
+    r->cfg = *cfg;
     S.adim = env->task.kind == 1 ? 8 : (env->task.kind == 3 ? 4 : 7);
     S.grip_qadr0 = env->task.grip_qadr[0];
     if (S.adim == 8 && S.discrete) { mopa_set_error("mopa_rollout_create: discrete_action is not built for the 8-D lift action (record slot 47 is taken)"); delete r; return MOPA_ERR_ARG; }
@@ -860,7 +882,8 @@ int mopa_rollout_create(mopa_env *env, mopa_planner *planner, const mopa_env_buf
     A(S.traj, (size_t)n * S.max_traj * 7);
     A(S.traj_len, n); A(S.traj_pos, n); A(S.executed, n);
     A(S.kind, n); A(S.pending, n); A(S.macro_done, n); A(S.need, n); A(S.reset_flag, n); A(S.step_mode, n); A(S.step_mask, n);
-    A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
+    A(S.prev_ob, (size_t)n * 40); A(S.ac, (size_t)n * 8); A(S.ctl, (size_t)n * 8); A(S.step_action, (size_t)n * 8);
+    if (S.ik_mode) { A(S.ik_ac, (size_t)n * 8); A(S.ik_q, (size_t)n * nq); }
     A(S.meta_rew, n); A(S.plan_count, n); A(S.episode_idx, n);
     A(S.grip0, n); A(S.cnt_plan, 1); A(S.cnt_back, 1); A(S.cnt_ids, 2); A(S.ids, n); A(S.ep_cforce, n);
     if (S.reuse_data) { A(S.ob_hist, (size_t)n * S.max_traj * 40); A(S.rew_hist, (size_t)n * S.max_traj); A(S.done_hist, (size_t)n * S.max_traj); }
@@ -988,7 +1011,14 @@ int mopa_rollout_pre(mopa_rollout *r, int32_t wait_rrt, void *stream) {
 
 /* Second half: d_actions [n][7] = the policy's output for every environment (used where a new macro
  * action starts).  Planning glue, RRT launch, env.step for every non-waiting environment, bookkeeping. */
-int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) { return mopa_rollout_step_discrete(r, d_actions, nullptr, stream); }
+int mopa_rollout_step(mopa_rollout *r, const float *d_actions, void *stream) {
+    if (r && r->S.ik_mode) { mopa_set_error("mopa_rollout_step: the handle runs use_ik_target, call mopa_rollout_step_ik"); return MOPA_ERR_ARG; }
+    return mopa_rollout_step_discrete(r, d_actions, nullptr, stream);
+}
+int mopa_rollout_step_ik(mopa_rollout *r, const float *d_actions, void *stream) {
+    if (!r || !r->S.ik_mode) { mopa_set_error("mopa_rollout_step_ik: the handle was not created with use_ik_target"); return MOPA_ERR_ARG; }
+    return mopa_rollout_step_discrete(r, d_actions, nullptr, stream);
+}
 
 /* Same with the policy's ac_type [n] (0 = direct execution, 1 = motion planner); required when the handle was created
  * with discrete_action (scripts/3d/push/mopa_discrete.sh), ignored otherwise. */
@@ -1001,7 +1031,17 @@ int mopa_rollout_step_discrete(mopa_rollout *r, const float *d_actions, const ui
     RO_TRY(cudaSetDevice(r->env->device));
     const int blocks = (S.n + 127) / 128;
     RrtBatch &Q = r->batch[r->fill];
-    ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, d_actions, d_ac_type);
+    const float *begin_actions = d_actions, *rec_actions = nullptr;
+    if (S.ik_mode) {   // _cart2dispalcement for the environments that start a macro action: Cartesian action -> joint displacement row
+        const mopa_rollout_config &C = r->cfg;
+        int dofs[7];
+        for (int k = 0; k < 7; k++) dofs[k] = r->env->task.arm_dof[k];
+        RO_TRY(launch_ik_rollout(r->env, r->buf.qpos, d_actions, S.need, C.ik_body, C.ik_site_local, dofs, S.na, S.n, C.ik_max_steps, C.ik_tol,
+                                 S.action_range, C.ik_world_lo, C.ik_world_hi, S.jlo, S.jhi, S.ik_q, S.ik_ac, st));
+        begin_actions = S.ik_ac; rec_actions = d_actions;
+        r->launches += 1;
+    }
+    ro_begin_kernel<<<blocks, 128, 0, st>>>(S, r->buf, begin_actions, d_ac_type, rec_actions);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32a, S.row, S.n, S.res_a, 0, p->sm_count, st, S.cnt_plan, 1));
     ro_backoff_kernel<<<(S.n * 32 + 127) / 128, 128, 0, st>>>(S, r->buf);
     RO_TRY(launch_is_valid(p->d_blob, p->scene.hdr, S.q32b, S.row, S.n * S.num_trials, S.res_b, 0, p->sm_count, st, S.cnt_back, S.num_trials));

@@ -47,6 +47,10 @@ class MoPAConfig:
     ac_space_type = "piecewise"  # "normal" (lift / assembly / 2d mopa_discrete.sh): displacement = a * action_range
     discrete_action = False    # scripts/3d/*/mopa_discrete.sh (with omega = 0): the policy's ac_type picks planner / direct
     debug_block_mod = 0        # test hook (mopa_rollout_config.debug_block_mod): force densification hops into the fallback planners
+    use_ik_target = False      # scripts/3d/*/mopa_ik.sh: Cartesian actions (default[3], quat[4], gripper) through qpos_from_site_pose
+    ik_target = "grip_site"
+    ik_max_steps = 100         # rl/mopa_rollouts.py:706-707
+    ik_tol = 1e-2
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -127,7 +131,10 @@ class _RolloutConfig(_C.Structure):
                [("seed_env", _C.c_uint64), ("env_id_offset", _C.c_int64), ("jnt_lo", _C.c_double * 7), ("jnt_hi", _C.c_double * 7),
                 ("init_qpos", _C.c_double * 7), ("qpos0", _C.c_void_p), ("reuse_data", _C.c_int32), ("max_reuse_data", _C.c_int32),
                 ("seed_reuse", _C.c_uint64), ("discrete_action", _C.c_int32), ("ac_space_normal", _C.c_int32),
-                ("simple_planner_range", _C.c_double), ("simple_max_iter", _C.c_int32), ("debug_block_mod", _C.c_int32)]
+                ("simple_planner_range", _C.c_double), ("simple_max_iter", _C.c_int32), ("debug_block_mod", _C.c_int32),
+                ("use_ik_target", _C.c_int32), ("ik_body", _C.c_int32), ("ik_site_local", _C.c_double * 3),
+                ("ik_world_lo", _C.c_double * 3), ("ik_world_hi", _C.c_double * 3), ("ik_max_steps", _C.c_int32), ("ik_pad_", _C.c_int32),
+                ("ik_tol", _C.c_double)]
 
 
 class NativeMoPARolloutRunner:
@@ -187,6 +194,22 @@ class NativeMoPARolloutRunner:
         c.ac_space_normal = int(cfg.ac_space_type == "normal")
         c.simple_planner_range, c.simple_max_iter = float(cfg.simple_planner_range), int(cfg.simple_max_iter)
         c.debug_block_mod = int(cfg.debug_block_mod)
+        c.use_ik_target = int(bool(cfg.use_ik_target))
+        if cfg.use_ik_target:
+            from .inverse_kinematics import site_frame
+
+            if cfg.discrete_action or self.action_dim != 8:
+                raise NotImplementedError("use_ik_target: built for the 8-entry Cartesian action (default[3], quat[4], gripper) of the lift "
+                                          "task without discrete_action (rl/trainer.py:113-135)")
+            sid = m.site_name2id(cfg.ik_target)
+            if not np.allclose(m.site_quat[sid], [1, 0, 0, 0]):
+                raise NotImplementedError("use_ik_target: the ik_target site must not be rotated against its body")
+            body, local = site_frame(m, venv.dyn, cfg.ik_target)
+            c.ik_body = int(body)
+            lo, hi = getattr(venv, "WORLD", ((-1.2, -1.2, 0.0), (1.2, 1.2, 2.0)))   # SawyerEnv.min_world_size / max_world_size (sawyer.py:52-53)
+            for k in range(3):
+                c.ik_site_local[k], c.ik_world_lo[k], c.ik_world_hi[k] = float(local[k]), float(lo[k]), float(hi[k])
+            c.ik_max_steps, c.ik_tol = int(cfg.ik_max_steps), float(cfg.ik_tol)
         L = lib()
         L.mopa_rollout_create.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p,
                                           _C.c_void_p, _C.c_int64, _C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_int32, _C.c_void_p, _C.POINTER(_C.c_void_p)]
@@ -195,6 +218,7 @@ class NativeMoPARolloutRunner:
         L.mopa_rollout_pre.argtypes = [_C.c_void_p, _C.c_int32, _C.c_void_p]
         L.mopa_rollout_step.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
         L.mopa_rollout_step_discrete.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.mopa_rollout_step_ik.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_void_p]
         L.mopa_rollout_busy.argtypes = [_C.c_void_p]
         L.mopa_rollout_launches.argtypes = [_C.c_void_p]
         L.mopa_rollout_launches.restype = _C.c_int64
@@ -237,6 +261,9 @@ class NativeMoPARolloutRunner:
         if self.cfg.discrete_action:
             self._check(self._L.mopa_rollout_step_discrete(self.h, ac.data_ptr(), ac_type.data_ptr(), self._stream()))
             self._keep = (ac, ac_type)
+        elif self.cfg.use_ik_target:   # policy -> (default[3], quat[4], gripper): the IK solve runs inside the step
+            self._check(self._L.mopa_rollout_step_ik(self.h, ac.data_ptr(), self._stream()))
+            self._keep = ac
         else:
             self._check(self._L.mopa_rollout_step(self.h, ac.data_ptr(), self._stream()))
             self._keep = ac

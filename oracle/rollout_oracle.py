@@ -50,6 +50,13 @@ class ScalarMoPARunner:
         self.counters = dict(mp=0, rl=0, interpolation=0, mp_fail=0, approximate=0, invalid=0, reused=0, fb_simple=0, fb_main=0, densify_fallback=0)
         self.contact_force_sum = 0.0   # run_episode: total_contact_force += env.get_contact_force() after every simulated env.step (:538-539, 636-646)
         self.extra_records = []   # relabelled records (reuse_data) of the latest macro step
+        if getattr(cfg, "use_ik_target", False):   # MoPA-SAC IK presets: _cart2dispalcement on the oracle's kinematic chain
+            from mopa_rl_b200.inverse_kinematics import site_frame   # data-format helper only (site -> simulated body, local position)
+            from oracle.ik_oracle import IKOracle
+
+            body, local = site_frame(model, dynmodel, cfg.ik_target)
+            dofs = [list(dynmodel.dof_vadr).index(model.get_joint_qvel_addr("right_j%d" % k)) for k in range(7)]
+            self.ik = IKOracle(dynmodel, body, local, dofs)
         self.ob = self._reset()
 
     def _reset(self):
@@ -192,9 +199,13 @@ class ScalarMoPARunner:
         ac = np.asarray(ac, np.float64).astype(np.float32).astype(np.float64)
         lift = self.task == "lift"                                 # 8-D action: 7 joint entries + gripper
         grip_ac = float(ac[7]) if lift else None
+        use_ik = bool(getattr(cfg, "use_ik_target", False))
+        policy_ac = ac.copy()                                      # what the record keeps
+        curr = env.qpos.copy()
+        if use_ik:                                                 # ac = (default[3], quat[4], gripper): rl/mopa_rollouts.py:90-101
+            ac = np.concatenate([self._cart2displacement(ac, curr), [ac[7]]])
         ac = ac[:self.na]
         self.macro_index += 1
-        curr = env.qpos.copy()
         is_mp = bool(ac_type) if discrete else bool(np.any(np.abs(ac) > cfg.omega))   # rl/mopa_rollouts.py:86-88, 104-111
         self._ac_type = float(is_mp) if discrete else 0.0
         steps = 0
@@ -208,7 +219,8 @@ class ScalarMoPARunner:
             if getattr(cfg, "ac_space_type", "piecewise") == "normal":   # rl/sac_agent.py:160-163
                 disp = ac * cfg.action_range
             target = curr.copy()
-            target[:self.na] = np.clip(curr[:self.na] + disp, self.jlo, self.jhi)
+            if not use_ik:                                         # the increment sits behind `if not config.use_ik_target` (:114-131)
+                target[:self.na] = np.clip(curr[:self.na] + disp, self.jlo, self.jhi)
             if cfg.invalid_target_handling and not self._valid(target):
                 trial = 0
                 while not self._valid(target) and trial < cfg.num_trials:
@@ -264,7 +276,35 @@ class ScalarMoPARunner:
         no = len(prev_ob)   # 40 (push) / 38 (assembly): observation rows keep the 40-float stride
         rec[0:no], rec[40:40 + self.na], rec[48], rec[49], rec[50], rec[52:52 + no] = prev_ob, ac, rec_rew, float(done), intra, self.ob
         rec[47] = grip_ac if lift else self._ac_type
+        if use_ik:
+            rec[40:48] = policy_ac
         return rec
+
+    def _cart2displacement(self, ac, curr):
+        """MoPARolloutRunner._cart2dispalcement (rl/mopa_rollouts.py:683-728) with util.env.mat2quat (:232-289) spelled out: the
+        float32 copy of the site matrix, the eigenvector of K for the largest eigenvalue, w >= 0, returned as (x, y, z, w); then the
+        reference's index list [3, 0, 1, 1]; quat_mul = mju_mulQuat; qpos_from_site_pose(max_steps, tol) on the arm joints."""
+        cfg = self.cfg
+        sp, R, _ = self.ik.site_pose(curr)
+        lo, hi = np.array([-1.2, -1.2, 0.0]), np.array([1.2, 1.2, 2.0])          # SawyerEnv.min_world_size / max_world_size (sawyer.py:52-53)
+        target_cart = np.clip(sp + cfg.action_range * ac[:3], lo, hi)
+        M = np.array(R, dtype=np.float32)
+        m00, m01, m02, m10, m11, m12, m20, m21, m22 = [float(x) for x in M.ravel()]
+        K = np.array([[m00 - m11 - m22, 0.0, 0.0, 0.0], [m01 + m10, m11 - m00 - m22, 0.0, 0.0],
+                      [m02 + m20, m12 + m21, m22 - m00 - m11, 0.0], [m21 - m12, m02 - m20, m10 - m01, m00 + m11 + m22]]) / 3.0
+        w, V = np.linalg.eigh(K)
+        q = V[[3, 0, 1, 2], np.argmax(w)]
+        if q[0] < 0.0:
+            q = -q
+        q = q[[1, 2, 3, 0]]                                                       # (x, y, z, w)
+        target_quat = q[[3, 0, 1, 1]]
+        aq = np.asarray(ac[3:7], np.float32)
+        aq = (aq / np.linalg.norm(aq)).astype(np.float64)
+        from oracle.ik_oracle import _qmul
+        target_quat = _qmul(target_quat, aq)
+        qres, _, _, _ = self.ik.solve(curr, target_cart, target_quat, max_steps=int(cfg.ik_max_steps), tol=float(cfg.ik_tol))
+        tgt = np.clip(qres[:self.na], self.jlo, self.jhi)
+        return (tgt - curr[:self.na]).astype(np.float32).astype(np.float64)      # the device front end hands the displacement over as fp32
 
     def _reuse(self, ob_list, rew_list, done_list, traj):
         """rl/mopa_rollouts.py:223-302: resample (start, goal) waypoint pairs of the executed plan; the reference's

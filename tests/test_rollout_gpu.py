@@ -307,6 +307,76 @@ def test_native_runner_lift_matches_scalar_reference_loop(oracle_built):
     print("lift: native vs scalar runner: %d records, worst |obs diff| %.2e, counters %s" % (len(rec), worst, c))
 
 
+@pytest.mark.parametrize("omega", [0.05, 3.0], ids=["preset-omega-holds", "large-omega-direct"])
+def test_ik_target_rollout_matches_scalar_reference_loop(oracle_built, omega):
+    """config.use_ik_target (scripts/3d/lift/mopa_ik.sh: omega 0.05, action_range 0.2, ik_target grip_site): the policy acts in
+    Cartesian space, (default[3], quat[4], gripper); every macro action runs _cart2dispalcement (rl/mopa_rollouts.py:683-728) -
+    mat2quat of the site frame with the reference's [3, 0, 1, 1] index list, qpos_from_site_pose(max_steps 100, tol 1e-2) -
+    and the joint displacement decides: above omega the "planner" branch, whose target is the current state in the reference
+    (a two-step hold, gripper entry on the second step), else env.step(displacement / omega + gripper).  With the preset's
+    omega every action of a random policy ends in the hold (the [3, 0, 1, 1] orientation target is never the current one, the
+    wrist always has to turn by more than 0.05 rad); a large omega sends most actions down the direct branch.  The scalar
+    side takes the reference's eigendecomposition route through mat2quat, the kernel the closed form: they agree to float32
+    resolution of the matrix."""
+    import torch
+
+    from mopa_rl_b200 import rng
+    from mopa_rl_b200.dynmodel import DynModel
+    from mopa_rl_b200.envs import VecSawyerLiftObstacle
+    from mopa_rl_b200.model import load_model
+    from mopa_rl_b200.rollout import CounterPolicy, MoPAConfig, NativeMoPARolloutRunner, env_planner_inputs
+    from oracle.rollout_oracle import ScalarMoPARunner
+
+    model = load_model("SawyerLiftObstacle-v0")
+    n, ticks, seed, off = 8, 36, 77, 20
+    cfg = MoPAConfig(omega=omega, action_range=0.2, max_iter=150, seed=9, reuse_data=True, max_reuse_data=15, use_ik_target=True)
+    venv = VecSawyerLiftObstacle(n, seed=seed, max_episode_steps=16, env_id_offset=off)
+    base = CounterPolicy(torch, venv.dev, 23, action_dim=8)
+
+    def device_policy(obs, gid, mi):
+        a = base(obs, gid, mi).clone()
+        small = (mi % 2 == 0)
+        a[small, :3] = a[small, :3] * 0.04
+        return a
+
+    runner = NativeMoPARolloutRunner(venv, cfg, policy=device_policy)
+    for _ in range(ticks):
+        runner.tick()
+    runner.drain()
+    torch.cuda.synchronize()
+    c = runner.counters
+    rec = runner.transitions[:c["transitions"]].cpu().numpy()
+    assert c["mp"] == 0 and c["reused"] == 0 and c["mp_fail"] == 0, c   # IK "plans" are two-step holds: nothing to relabel, no RRT
+    assert (c["interpolation"] > n and c["rl"] == 0) if omega < 1 else (c["rl"] > n), c   # (some wrist turns exceed even 3 rad)
+
+    def policy(gid, k):
+        u = rng.uniform01(23, np.uint64(gid), np.uint64(k), np.arange(8, dtype=np.uint64))
+        a = (2.0 * u - 1.0).astype(np.float32)
+        if k % 2 == 0:
+            a[:3] = a[:3] * np.float32(0.04)
+        return a
+
+    ignored, passive, _ = env_planner_inputs(VecSawyerLiftObstacle, model)
+    dm = DynModel(model)
+    worst, n_direct, n_hold = 0.0, 0, 0
+    for e in range(n):
+        gid = off + e
+        mine = rec[rec[:, 51] == gid]
+        ref = ScalarMoPARunner(model, dm, cfg, ignored, passive, gid, seed, policy, max_episode_steps=16, task="lift")
+        for k, r in enumerate(mine):
+            o = ref.macro_step()
+            assert np.array_equal(r[40:48], o[40:48]), (e, k, r[40:48], o[40:48])          # the record keeps the Cartesian action
+            assert r[49] == o[49] and r[50] == o[50], (e, k, r[48:51], o[48:51])
+            assert abs(r[48] - o[48]) < 1e-4, (e, k, r[48], o[48])
+            d = max(np.abs(r[0:35] - o[0:35]).max(), np.abs(r[52:87] - o[52:87]).max())
+            worst = max(worst, d)
+            assert d < 2e-4, (e, k, d)
+            n_direct += r[50] == 0
+            n_hold += r[50] == 1
+    assert (n_hold > n and n_direct == 0) if omega < 1 else (n_direct > n), (n_direct, n_hold)
+    print("lift IK: native vs scalar runner: %d records (%d direct, %d holds), worst |obs diff| %.2e, counters %s" % (len(rec), n_direct, n_hold, worst, c))
+
+
 @pytest.mark.parametrize("simple_max_iter", [3, 0], ids=["simple-planner", "main-planner-retry"])
 def test_blocked_hops_go_through_the_simple_and_the_main_planner(push_model, oracle_built, simple_max_iter):
     """SACAgent.simple_interpolate(use_planner=True) (rl/sac_agent.py:300-311): a densification hop whose interior is blocked is
