@@ -30,11 +30,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "env-steps/sec (incl. planner) SawyerPushObstacle-v0"
 METRIC_ASSEMBLY = "env-steps/sec (incl. planner) SawyerAssemblyObstacle-v0"
-TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0", "pusher": "PusherObstacle-v0"}
+TASK_ENV = {"push": "SawyerPushObstacle-v0", "assembly": "SawyerAssemblyObstacle-v0", "lift": "SawyerLiftObstacle-v0", "lift-ik": "SawyerLiftObstacle-v0",
+            "pusher": "PusherObstacle-v0"}
 
 
 # scripts/3d/{push,assembly,lift}/mopa.sh: omega per task (action_range 0.5, reuse_data, max_reuse_data 15 in all three)
-TASK_OMEGA = {"push": 0.7, "assembly": 0.7, "lift": 0.5, "pusher": 0.5}
+TASK_OMEGA = {"push": 0.7, "assembly": 0.7, "lift": 0.5, "lift-ik": 0.05, "pusher": 0.5}
 
 
 def task_config(task, max_iter):
@@ -47,16 +48,20 @@ def task_config(task, max_iter):
         return MoPAConfig(omega=0.5, action_range=1.0, ac_scale=0.1, step_size=0.04, joint_margin=0.0, contact_threshold=-0.0015, range=0.2,
                           simple_planner_range=0.1, max_iter=max(1, max_iter // 2), simple_max_iter=max(1, max_iter // 100), reuse_data=True,
                           max_reuse_data=30)
+    if task == "lift-ik":
+        # BASELINE configs[2]: scripts/3d/lift/mopa_ik.sh (MoPA-SAC IK: use_ik_target, ik_target grip_site, action_range 0.2, omega 0.05)
+        return MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15, omega=0.05, action_range=0.2, use_ik_target=True, ik_target="grip_site")
     return MoPAConfig(max_iter=max_iter, reuse_data=True, max_reuse_data=15, omega=TASK_OMEGA[task])
 
 
 def task_env_class(task):
     from mopa_rl_b200 import envs
 
-    return {"assembly": envs.VecSawyerAssemblyObstacle, "lift": envs.VecSawyerLiftObstacle, "pusher": envs.VecPusherObstacle}.get(task, envs.VecSawyerPushObstacle)
+    return {"assembly": envs.VecSawyerAssemblyObstacle, "lift": envs.VecSawyerLiftObstacle, "lift-ik": envs.VecSawyerLiftObstacle,
+            "pusher": envs.VecPusherObstacle}.get(task, envs.VecSawyerPushObstacle)
 
 
-TASK_ADIM = {"push": 7, "assembly": 7, "lift": 8, "pusher": 4}
+TASK_ADIM = {"push": 7, "assembly": 7, "lift": 8, "lift-ik": 8, "pusher": 4}
 
 
 def task_metric(task):
@@ -174,7 +179,7 @@ def _cpu_rollout_worker(args):
         u = rng.uniform01(seed + 7, np.uint64(g), np.uint64(k), np.arange(adim, dtype=np.uint64))
         return (2.0 * u - 1.0).astype(np.float32)
 
-    r = ScalarMoPARunner(model, DynModel(model), task_config(task, max_iter), ignored, passive, gid, seed, policy, task=task,
+    r = ScalarMoPARunner(model, DynModel(model), task_config(task, max_iter), ignored, passive, gid, seed, policy, task="lift" if task == "lift-ik" else task,
                          max_episode_steps=400 if task == "pusher" else 250)
     t0 = time.perf_counter()
     for _ in range(macros):
@@ -390,6 +395,8 @@ def rollout_config(args, n, **extra):
     wl = (WORKLOADS["rollout"] % n).replace("SawyerPushObstacle-v0", TASK_ENV[args.task]).replace("OMEGA", str(TASK_OMEGA[args.task]))
     if args.task == "pusher":
         wl = wl.replace("action_range 0.5, RRT-Connect range 0.1", "action_range 1.0, RRT-Connect range 0.2")
+    if args.task == "lift-ik":
+        wl = wl.replace("MoPA (", "MoPA-SAC IK (use_ik_target, ik_target grip_site, Cartesian actions through the device IK front end; ").replace("action_range 0.5", "action_range 0.2")
     cfg = {"workload": wl, "reuse_data": True, "max_reuse_data": 30 if args.task == "pusher" else 15, "envs_per_gpu": n,
            "substeps_per_env_step": "100 RK4 mj_steps (400 forward-dynamics evaluations)" if args.task == "pusher" else 75, "max_iter": args.max_iter}
     if args.task == "pusher":
@@ -536,9 +543,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rollout", choices=["rollout", "validity"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (rollout)")
-    ap.add_argument("--task", default="push", choices=["push", "assembly", "lift", "pusher"],
+    ap.add_argument("--task", default="push", choices=["push", "assembly", "lift", "lift-ik", "pusher"],
                     help="rollout scene: push = SawyerPushObstacle-v0 (BASELINE metric, default), assembly = SawyerAssemblyObstacle-v0 (configs[3]), "
-                         "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there), pusher = PusherObstacle-v0 (configs[0])")
+                         "lift = SawyerLiftObstacle-v0 (configs[2] scene, joint-space MoPA-SAC; 1024 envs per GPU there), lift-ik = the same scene with the "
+                         "MoPA-SAC IK preset of configs[2] (use_ik_target), pusher = PusherObstacle-v0 (configs[0])")
     ap.add_argument("--max-iter", type=int, default=1000, help="RRT-Connect iteration cap (stands in for --timelimit)")
     ap.add_argument("--cpu-macros", type=int, default=150, help="macro actions per scalar runner in the cpu_baseline leg and per step of --impl reference "
                                                                    "(one protocol for both: ~2.5 s of CPU work per runner)")

@@ -35,7 +35,7 @@ json.dump({"kernel": "env_step_warp_kernel<14,32,24,14,15,14>", "envs": 4096, "d
            "source": "profiles/r2_envwarp_summary.txt"}, open('profiles/r2_envwarp_traffic.json', 'w'), indent=1)
 old = [l for l in open('profiles/r2_bench_lines.jsonl') if l.startswith('{')]
 multi = [l.strip() for l in old if json.loads(l).get('n_gpus', 1) > 1]
-out = [open('gpurun_out/r2f_bench_%s.json' % f).read().strip().splitlines()[-1] for f in ['rollout', 'validity', 'validity_lift', 'reference', 'pusher', 'lift', 'assembly']]
+out = [open('gpurun_out/r2f_bench_%s.json' % f).read().strip().splitlines()[-1] for f in ['rollout', 'validity', 'validity_lift', 'reference', 'pusher', 'lift', 'lift_ik', 'assembly']]
 open('profiles/r2_bench_lines.jsonl', 'w').write('\n'.join(out + multi) + '\n')
 for l in out:
     d = json.loads(l); print(d['metric'][:64], round(d['value']), 'e2e', round(d['e2e']['value']), d.get('roofline', {}).get('kernel_ms_per_launch'))
