@@ -297,3 +297,34 @@ def test_can_rests_on_the_ground_plane_upright_and_on_its_side(oracle_built):
         assert rest - 1.5e-3 < q[a + 2] < rest + 1e-4, (quat, q[a + 2], rest)
         assert np.abs(v[va:va + 3]).max() < 1e-3
         assert abs(abs(np.dot(q[a + 3:a + 7], quat)) - 1.0) < 1e-3           # neither tips over nor rolls away
+
+
+# ---------------------------------------------------------------------------- use_ik_target: mat2quat, the two routes
+def test_mat2quat_eigen_route_equals_the_closed_form_up_to_float32_resolution():
+    """util.env.mat2quat (util/env.py:232-289) takes the eigenvector of a symmetric 4x4 matrix built from the float32 copy of the
+    rotation and fixes the sign with w >= 0; the device IK front end (csrc/ik.cu, rollout mode) uses mju_mat2Quat's closed form on
+    the same float32 copy and the same sign rule.  Both are the unit quaternion of the rotation: they must agree to the resolution
+    of the float32 matrix, also near w = 0 where the sign rule flips (the target orientation is sign invariant there)."""
+    from oracle.ik_oracle import _mat2quat, _q2m
+
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for k in range(400):
+        q = rng.normal(size=4)
+        if k % 10 == 0:
+            q[0] = 1e-4 * rng.normal()                      # half-turn rotations: w close to 0
+        q /= np.linalg.norm(q)
+        R = _q2m(q)
+        M = np.array(R, dtype=np.float32)
+        m00, m01, m02, m10, m11, m12, m20, m21, m22 = [float(x) for x in M.ravel()]
+        K = np.array([[m00 - m11 - m22, 0.0, 0.0, 0.0], [m01 + m10, m11 - m00 - m22, 0.0, 0.0],
+                      [m02 + m20, m12 + m21, m22 - m00 - m11, 0.0], [m21 - m12, m02 - m20, m10 - m01, m00 + m11 + m22]]) / 3.0
+        w, V = np.linalg.eigh(K)
+        qe = V[[3, 0, 1, 2], np.argmax(w)]
+        qe = -qe if qe[0] < 0 else qe                        # (w, x, y, z)
+        qc = _mat2quat(M.astype(np.float64))
+        qc = -qc if qc[0] < 0 else qc
+        d = min(np.abs(qe - qc).max(), np.abs(qe + qc).max())   # same rotation; the sign may differ only when w ~ 0
+        assert np.abs(qe - qc).max() < 2e-6 or abs(qe[0]) < 1e-3, (k, qe, qc)
+        worst = max(worst, d)
+    assert worst < 2e-6, worst
