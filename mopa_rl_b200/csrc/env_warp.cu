@@ -52,7 +52,7 @@ struct WarpWS {
     union {              // the kinematic arrays are dead once the constraint Jacobians exist: A reuses them
         WarpKin<WB> k;
         struct {
-            double A[WC * WD];   // solver scratch, row r at A + r * WD: y = L^-1 J_r^T, then K_r (Hessian assembly)
+            double A[WC * YS];   // solver scratch, row r at A + r * YS (padded stride: lane = row accesses are bank-conflict free): y = L^-1 J_r^T, then K_r (Hessian assembly)
             // Behind A lie k.vel / k.frc / k.inert, dead once the inertia matrix exists: the factor of M + h * diag(damping)
             // (implicit joint damping of the Euler update) is produced there by the upper half-warp while the lower one
             // factors M, and waits for the velocity update at the end of the substep.
@@ -60,7 +60,7 @@ struct WarpWS {
             alignas(16) double col2[4 * (WD + 2)];   // column buffers of w_factor_solve: per (half-warp, diagonal block)
         };
     };
-    static_assert(WC * WD >= WB * 16 + WD * 6, "A must cover xpos / xquat / xmat / S so that L2 only overlaps arrays dead after stage 3");
+    static_assert(WC * YS >= WB * 16 + WD * 6, "A must cover xpos / xquat / xmat / S so that L2 only overlaps arrays dead after stage 3");
     double kxpos[4][3], kxquat[2][4], kxmat[4][9];   // frames of the bodies the env epilogue reads (mjData after mj_step)
     double M[NTRI], L[NTRI], invd[WD];
     double qd[WD], bias[WD], tau[WD], qacc0[WD], a[WD], rhs[WD], bias_prev[WD], ctrl[DMAXA], z[WD];
@@ -877,7 +877,7 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
         double aref = 0, Dr = 0;
         if (r < nc) {
             const double *jr = W.Y + r * YS;
-            double *yr = W.A + r * WD;
+            double *yr = W.A + r * YS;
             int k0 = 0;
             while (k0 < nd && jr[k0] == 0.0) k0++;          // leading exact zeros stay zero
             double diag = 0;
@@ -973,7 +973,7 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
                 for (int j = 0; j < nd; j++) {
                     double kk = h0 * W.Y[base * YS + j];
                     if (blockrow) kk += h1 * W.Y[(base + 1) * YS + j] + h2 * W.Y[(base + 2) * YS + j];
-                    W.A[r * WD + j] = kk;
+                    W.A[r * YS + j] = kk;
                 }
             }
             __syncwarp();
@@ -983,8 +983,8 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
                 while (TRI(i, 0) > e) i--;
                 const int j = e - TRI(i, 0);
                 double hh = W.M[e], hb = 0;
-                for (int s2 = 0; s2 + 1 < nc; s2 += 2) { hh += W.Y[s2 * YS + i] * W.A[s2 * WD + j]; hb += W.Y[(s2 + 1) * YS + i] * W.A[(s2 + 1) * WD + j]; }
-                if (nc & 1) hh += W.Y[(nc - 1) * YS + i] * W.A[(nc - 1) * WD + j];
+                for (int s2 = 0; s2 + 1 < nc; s2 += 2) { hh += W.Y[s2 * YS + i] * W.A[s2 * YS + j]; hb += W.Y[(s2 + 1) * YS + i] * W.A[(s2 + 1) * YS + j]; }
+                if (nc & 1) hh += W.Y[(nc - 1) * YS + i] * W.A[(nc - 1) * YS + j];
                 W.L[e] = hh + hb;
             }
             __syncwarp();
