@@ -191,6 +191,7 @@ __device__ __noinline__ void w_factor_solve(const double *Msrc, const double *di
     __syncwarp();
 }
 constexpr int SAWYER_BLK0 = 9;   // the arm + gripper tree of the Sawyer scenes has 9 dofs; the free object follows
+constexpr int SMALL_ND = 8;      // scenes with at most 8 dofs (PusherObstacle-v0): one block of 8 columns, the second block is empty - half the sweep
 // x <- (L L^T)^-1 x with a factor w_factor_solve stored earlier (same operation order as its fused forward substitution)
 __device__ __noinline__ void w_solve_stored(const double *L, const double *invd, int nd, double *x, int lane, int blk0) {
     const bool live = lane < nd;
@@ -585,6 +586,7 @@ __device__ __noinline__ bool w_stage_dynamics(const DynDev &m, const DynDev *__r
     __syncwarp();
     // upper half-warp: the factor the velocity update needs (Euler: M + h * diag(damping); explicit RK4 stage: M itself)
     if (W.blk0 == SAWYER_BLK0) w_factor_solve<SAWYER_BLK0>(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
+    else if (nd <= SMALL_ND) w_factor_solve<SMALL_ND>(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
     else w_factor_solve<0>(W.M, nullptr, 0.0, nd, W.L, W.invd, W.qacc0, W.col2, lane, W.L2, W.invd2, m.d_damping, smode == 2 ? 0.0 : m.h);
 
     STAGE_SYNC(4);   // 4: unconstrained acceleration done
@@ -1042,6 +1044,7 @@ __device__ __noinline__ void w_stage_solve(const DynDev &m, const DynDev *__rest
             if (lane < nd) W.rhs[lane] = -gme;
             __syncwarp();
             if (hblk == SAWYER_BLK0) w_factor_solve<SAWYER_BLK0>(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.col2, lane);
+            else if (nd <= SMALL_ND) w_factor_solve<SMALL_ND>(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.col2, lane);
             else w_factor_solve<0>(W.L, nullptr, 0.0, nd, W.L, W.invd, W.rhs, W.col2, lane);
             double pme = 0, mp = 0;
             if (lane < nd) {
